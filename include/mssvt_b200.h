@@ -1,0 +1,206 @@
+/*
+ * mssvt_b200.h -- C-ABI of libmssvt_b200.so: the B200 (sm_100a) implementation of the MsSVT
+ * mixed-scale sparse voxel attention backbone hot path.
+ *
+ * Drop-in boundary.  The reference binds its native layer with pybind11 (`mssvt_ops_cuda`,
+ * pcdet/ops/mssvt/src/ms_api.cpp:7-14, and four functions of `pointnet2_batch_cuda`,
+ * pcdet/ops/pointnet2/pointnet2_batch/src/pointnet2_api.cpp:10-24), passing at::Tensor.  Every
+ * function below replaces one of those entry points (cited per function) with:
+ *   - plain device pointers and sizes, no torch types;
+ *   - an explicit stream (`void *stream` = cudaStream_t; the reference always launches on the
+ *     legacy default stream);
+ *   - an int status instead of fprintf + exit(-1) (ms_sparse_attention_gpu.cu:110-114):
+ *       0 ok, -1 invalid argument, -2 CUDA launch/runtime error (mssvt_last_cuda_error()),
+ *       -3 workspace too small;
+ *   - caller-allocated outputs (as in the reference, mssvt_ops.py:16-17, 36-41, 77-85), but
+ *     the -1 / 0 pre-fill is done on the device by the callee, so outputs may be uninitialised.
+ * All functions are asynchronous with respect to the host and re-entrant; none of them
+ * synchronises, allocates device memory or keeps global state.
+ *
+ * Layout conventions (same as the reference): voxel / window indices are int32 rows
+ * [batch, z, y, x]; hash tables are (B, H, 2) int32 [key, value] with empty = -1,
+ * h(k) = k % H and linear probing; features are row-major fp32 (N, C).
+ */
+#ifndef MSSVT_B200_H
+#define MSSVT_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSSVT_OK 0
+#define MSSVT_ERR_INVALID (-1)
+#define MSSVT_ERR_LAUNCH (-2)
+#define MSSVT_ERR_WORKSPACE (-3)
+
+const char *mssvt_version(void);
+int mssvt_last_cuda_error(void);
+
+/* ---- utilities ------------------------------------------------------------------------- */
+
+int mssvt_fill_i32(int *p, long long count, int value, void *stream);
+
+/* per-sample row counts and their exclusive prefix, from the batch column of (n, 4) indices.
+ * Replaces the `.sum().item()` loops of with_bs_cnt (mssvt_backbone.py:124-130) and
+ * SparseTensor.build_map_table (mssvt_utils.py:35-38).  counts (B), start (B + 1). */
+int mssvt_count_samples(int num_rows, int batch_size, const int *indices, int *counts, int *start,
+                        void *stream);
+
+/* with_coords (mssvt_backbone.py:132-137): xyz (N, 3) = (idx[x,y,z] + 0.5) * voxel_size + min,
+ * three separately rounded fp32 operations.  voxel_size, range_min: 3 HOST floats each. */
+int mssvt_voxel_world_coords(int num_voxels, const int *v_indices, const float *voxel_size,
+                             const float *range_min, float *xyz, void *stream);
+
+/* ---- mssvt_ops_cuda replacements ---------------------------------------------------------- */
+
+/* build_mapping_with_hash_wrapper (ms_sparse_attention.cpp:23-35; kernel ..._gpu.cu:66-115).
+ * table: (batch_size, hash_size, 2), filled by this call. */
+int mssvt_build_hash_table(int x_max, int y_max, int z_max, int num_voxels, int hash_size,
+                           int batch_size, const int *v_indices, const int *v_bs_cnt, int *table,
+                           void *stream);
+
+/* Table content view (no reference counterpart; used by tests): values[i] = value stored for
+ * keys[i] in sample batch_ids[i], -1 if absent (hash_table_find, ..._gpu.cu:43-64). */
+int mssvt_hash_lookup(int hash_size, int num_queries, const int *batch_ids, const int *keys,
+                      const int *table, int *values, void *stream);
+
+/* window_with_hash_wrapper (ms_sparse_attention.cpp:37-59; kernel ..._gpu.cu:117-191) plus the
+ * Python mask/cat loop of WindowPartition.forward (mssvt_ops.py:45-53).
+ *   win_list  (list_capacity, 4) rows [b, wz, wy, wx] of all samples concatenated, numbered by
+ *             first occurrence in voxel order (the reference numbers by atomicAdd arrival);
+ *   table     (batch_size, hash_size, 2) window key -> per-sample row id, filled by this call;
+ *   win_count (batch_size + 2): per-sample window counts, [B] = total, [B+1] = windows dropped
+ *             because they exceed max_wins per sample or list_capacity (the reference writes
+ *             out of bounds in that case);
+ *   workspace: mssvt_window_partition_workspace_bytes(num_voxels) bytes of scratch. */
+long long mssvt_window_partition_workspace_bytes(int num_voxels);
+int mssvt_window_partition(int x_wgs, int y_wgs, int z_wgs, int x_ws, int y_ws, int z_ws,
+                           int num_voxels, int max_wins, int hash_size, int batch_size,
+                           int list_capacity, const int *v_indices, int *win_list, int *table,
+                           int *win_count, void *workspace, long long workspace_bytes,
+                           void *stream);
+
+/* gather_two_window_voxels_with_hash_wrapper (ms_sparse_attention.cpp:61-120; kernel
+ * ..._gpu.cu:193-381).  Same argument order as the reference wrapper; ind_* (W, max_*) padded
+ * with -1, coord_* (W, max_*, 3) padded with 0, all written in full by this call. */
+int mssvt_gather_two_window(int x_max, int y_max, int z_max, int x_ws, int y_ws, int z_ws,
+                            int max_odd, int max_even, int max_win1, int max_win2, int num_wins,
+                            int hash_size, int num_odd, int num_even, int num_win1, int num_win2,
+                            int *ind_odd, int *ind_even, int *ind_win1, int *ind_win2,
+                            int *coord_odd, int *coord_even, int *coord_win1, int *coord_win2,
+                            const int *q_odd, const int *q_even, const int *q_win1,
+                            const int *q_win2, const int *win_indices, const int *table,
+                            void *stream);
+
+/* gather_one_window_voxels_with_hash_wrapper (ms_sparse_attention.cpp:122-149; kernel
+ * ..._gpu.cu:383-458). */
+int mssvt_gather_one_window(int x_max, int y_max, int z_max, int x_ws, int y_ws, int z_ws,
+                            int max_win1, int num_wins, int hash_size, int num_win1, int *ind_win1,
+                            int *coord_win1, const int *q_win1, const int *win_indices,
+                            const int *table, void *stream);
+
+/* group_features_wrapper / group_features_grad_wrapper (group_features.cpp:29-68; kernels
+ * group_features_gpu.cu:73-129, 15-70).  out (M, C, nsample) is written in full (zeros where
+ * idx < 0); grad_features (N, C) is zeroed then accumulated. */
+int mssvt_group_features(int B, int M, int C, int nsample, const float *features,
+                         const int *features_batch_cnt, const int *idx, const int *idx_batch_cnt,
+                         float *out, void *stream);
+int mssvt_group_features_grad(int B, int M, int C, int N, int nsample, const float *grad_out,
+                              const int *idx, const int *idx_batch_cnt,
+                              const int *features_batch_cnt, float *grad_features, void *stream);
+
+/* ---- pointnet2_batch_cuda replacements (the four ops the backbone calls) -------------------- */
+
+/* farthest_point_sampling_wrapper (sampling.cpp:41-50; kernel sampling_gpu.cu:100-260), including
+ * the reference's tie order.  temp (b, n) scratch is only needed for n > ~50 000 (may be NULL). */
+int mssvt_fps(int b, int n, int m, const float *dataset, float *temp, int *idxs, void *stream);
+int mssvt_fps_log2_block(int n); /* log2 of the reference's FPS block size, cuda_utils.h:10-14 */
+
+/* gather_points_wrapper (sampling.cpp:13-24; kernel sampling_gpu.cu:15-51) */
+int mssvt_gather_points(int b, int c, int n, int m, const float *points, const int *idx,
+                        float *out, void *stream);
+
+/* three_nn_wrapper (interpolate.cpp:17-29; kernel interpolate_gpu.cu:16-81): squared distances */
+int mssvt_three_nn(int b, int n, int m, const float *unknown, const float *known, float *dist2,
+                   int *idx, void *stream);
+
+/* group_points_wrapper / group_points_grad_wrapper (group_points.cpp:18-44; kernels
+ * group_points_gpu.cu:53-92, 14-50) */
+int mssvt_group_points(int b, int c, int n, int npoints, int nsample, const float *points,
+                       const int *idx, float *out, void *stream);
+int mssvt_group_points_grad(int b, int c, int n, int npoints, int nsample, const float *grad_out,
+                            const int *idx, float *grad_points, void *stream);
+
+/* ---- fused entry points used by the backbone module ------------------------------------------ */
+
+/* Coordinate-only part of MixedScaleSparseTransformerBlock.forward (mssvt_backbone.py:213-258,
+ * 264-269, 300-307) in one kernel, one warp per window, with no host synchronisation: the
+ * number of windows is read from device memory (win_count_total) and bounds the work.
+ * Outputs per window w < *win_count_total (rows beyond are untouched):
+ *   q_row    (cap, nq)        global feature row of each query slot (-1 pad); nq = |odd| / |even|
+ *                             / max_win1 for cbs_pattern 1 / 0 / 2
+ *   win1_row (cap, max_win1)  global row of each win1 voxel (-1 pad)
+ *   k_row    (cap, 2K)        global row of each key slot: K from the win1 list, K from win2
+ *   k_mask   (cap, 2K)        1 where the reference masks the key
+ *   nn_idx   (cap, max_win1, 3) uint8, nn_w (cap, max_win1, 3): three_nn picks among the query
+ *                             slots and normalised inverse-distance weights (use_interp only)
+ *   covered  (num_voxels)     1 for every row the merge will overwrite (zeroed by this call)
+ *   fps_idx_tap (cap, 2K), counts_tap (cap, 4): optional raw FPS picks / list lengths (NULL ok)
+ * voxel_size, range_min: 3 HOST floats each. */
+int mssvt_block_geometry(int x_max, int y_max, int z_max, int x_ws, int y_ws, int z_ws,
+                         int hash_size, int num_odd, int num_even, int num_win1, int num_win2,
+                         int max_win1, int max_win2, int key_num_sample, int cbs_pattern,
+                         int use_interp, const float *voxel_size, const float *range_min,
+                         const int *q_odd, const int *q_even, const int *q_win1, const int *q_win2,
+                         int win_capacity, const int *win_count_total, const int *win_list,
+                         const int *table, const int *v_start, int num_voxels, int *q_row,
+                         int *win1_row, int *k_row, unsigned char *k_mask, unsigned char *nn_idx,
+                         float *nn_w, unsigned char *covered, int *fps_idx_tap, int *counts_tap,
+                         void *stream);
+
+/* One-window gather of the compress block without host synchronisation (same table walk as
+ * mssvt_gather_one_window): k_row (cap, max_win1) global feature rows, -1 padded. */
+int mssvt_window_rows(int x_max, int y_max, int z_max, int x_ws, int y_ws, int z_ws, int hash_size,
+                      int num_win1, int max_win1, const int *q_win1, int win_capacity,
+                      const int *win_count_total, const int *win_list, const int *table,
+                      const int *v_start, int *k_row, void *stream);
+
+/* nn.LayerNorm(C) over rows (mssvt_backbone.py:210, 352); num_rows_dev (may be NULL) bounds the
+ * row count from device memory. */
+int mssvt_layernorm(int num_rows, const int *num_rows_dev, int C, const float *x,
+                    const float *gamma, const float *beta, float eps, float *y, void *stream);
+
+/* Feature part of a two-window block between norm1 and the residual: gather + pos_proj +
+ * MixedScaleAttention + interpolation + merge (mssvt_backbone.py:260-336; mssvt_utils.py:88-157).
+ * `shape` is the AttnShape descriptor (mssvt_b200/csrc/block.cu; mirrored in mssvt_b200/_lib.py),
+ * `params` the transposed fp32 weight pack it indexes.  Writes merged[row] for covered rows. */
+int mssvt_block_attention(const void *shape, int shape_bytes, const float *params, int win_capacity,
+                          const int *win_count_total, const int *win_list, const float *xn,
+                          const float *xyz, const int *q_row, const int *k_row,
+                          const unsigned char *k_mask, const int *win1_row,
+                          const unsigned char *nn_idx, const float *nn_w, float *merged,
+                          void *stream);
+
+/* Attention of a one-window (compress) block (mssvt_backbone.py:361-383): out (cap, C). */
+int mssvt_compress_attention(const void *shape, int shape_bytes, const float *params,
+                             int win_capacity, const int *win_count_total, const int *win_list,
+                             const float *xn, const float *xyz, const int *k_row, float *out,
+                             void *stream);
+
+/* residual + norm2 + linear1 / ReLU / linear2 + residual (+ out_linear)
+ * (mssvt_backbone.py:337-343, 384-387).  `shape` is the FfnShape descriptor. */
+int mssvt_ffn(const void *shape, int shape_bytes, const float *params, int num_rows,
+              const int *num_rows_dev, const float *x, const float *merged,
+              const unsigned char *covered, float *y, void *stream);
+
+/* SparseTensor.dense() (mssvt_utils.py:50-62): out (B, C, D, H, W), zero-filled then scattered */
+int mssvt_dense_scatter(int num_rows, const int *num_rows_dev, int batch_size, int C, int D, int H,
+                        int W, const float *features, const int *indices, float *out, void *stream);
+
+int mssvt_sizeof_attn_shape(void);
+int mssvt_sizeof_ffn_shape(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSSVT_B200_H */

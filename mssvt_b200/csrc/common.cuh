@@ -1,0 +1,63 @@
+// common.cuh -- shared device helpers for the mssvt_b200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define MSSVT_OK 0
+#define MSSVT_ERR_INVALID (-1)   // bad argument (null pointer, size out of the supported range)
+#define MSSVT_ERR_LAUNCH (-2)    // kernel launch / CUDA runtime failure (see mssvt_last_cuda_error)
+#define MSSVT_ERR_WORKSPACE (-3) // workspace too small
+
+#define MSSVT_EMPTY (-1)         // EMPTY_KEY of the reference table (ms_cuda_utils.h:9)
+#define MSSVT_NUM_SMS 148
+
+namespace mssvt {
+
+extern int g_last_cuda_error;
+
+static inline int check_launch() {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        g_last_cuda_error = (int)e;
+        return MSSVT_ERR_LAUNCH;
+    }
+    return MSSVT_OK;
+}
+
+static inline int div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// grid for a grid-stride kernel: enough CTAs to cover `items`, capped at `waves` full waves of
+// the 148 SMs times the resident CTAs per SM.
+static inline int persistent_grid(long long items, int per_cta, int ctas_per_sm, int waves = 4) {
+    long long need = (items + per_cta - 1) / per_cta;
+    long long cap = (long long)MSSVT_NUM_SMS * ctas_per_sm * waves;
+    if (need < 1) need = 1;
+    return (int)(need < cap ? need : cap);
+}
+
+// ---- reference hash table: (H, 2) int32 [key, value], h(k) = k % H, linear probing
+// (ms_sparse_attention_gpu.cu:18-64).  One 8-byte load per probe.
+__device__ __forceinline__ int table_find(const int2 *__restrict__ tab, int hash_size, int key) {
+    int slot = (int)((unsigned)key % (unsigned)hash_size);
+    for (int probes = 0; probes < hash_size; ++probes) {
+        int2 kv = __ldg(tab + slot);
+        if (kv.x == key) return kv.y;
+        if (kv.x == MSSVT_EMPTY) return MSSVT_EMPTY;
+        slot = slot + 1 == hash_size ? 0 : slot + 1;
+    }
+    return MSSVT_EMPTY;
+}
+
+__device__ __forceinline__ unsigned lanemask_lt() {
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+// voxel-centre world coordinate exactly as with_coords (mssvt_backbone.py:133-137) evaluates it
+// in PyTorch: three separately rounded fp32 ops, never contracted into an FMA.
+__device__ __forceinline__ float world_coord(int idx, float cell, float lo) {
+    return __fadd_rn(__fmul_rn(__fadd_rn((float)idx, 0.5f), cell), lo);
+}
+
+}  // namespace mssvt

@@ -1,0 +1,332 @@
+// hash_window.cu -- voxel hash build, hash lookup, window partition (sm_100a).
+//
+// Replaces, behind the C-ABI of include/mssvt_b200.h:
+//   build_mapping_with_hash_kernel  pcdet/ops/mssvt/src/ms_sparse_attention_gpu.cu:66-115
+//   window_with_hash_kernel         pcdet/ops/mssvt/src/ms_sparse_attention_gpu.cu:117-191
+// and the CPU fill + H2D copies / per-sample Python loops around them in
+// pcdet/ops/mssvt/mssvt_ops.py:7-60.
+//
+// Table contract is the reference's: (B, H, 2) int32 [key, value], empty = -1, h(k) = k % H,
+// linear probing, so tables are interchangeable with the reference kernels.  Differences in HOW:
+//  * the -1 fill happens on the device with 16-byte stores (no 8*B*H-byte H2D copy);
+//  * a slot is claimed with ONE 64-bit CAS carrying key and value together, probes are single
+//    8-byte loads;
+//  * windows are numbered deterministically by first occurrence in voxel order (atomicMin of the
+//    voxel index + a two-level scan) instead of atomicAdd arrival order.
+#include "common.cuh"
+
+namespace mssvt {
+
+int g_last_cuda_error = 0;
+
+// ------------------------------------------------------------------------------- fill
+
+__global__ void k_fill_i32x4(int4 *__restrict__ p, size_t n16, int *__restrict__ tail, int ntail,
+                             int value) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    int4 v = make_int4(value, value, value, value);
+    for (; i < n16; i += stride) p[i] = v;
+    if (blockIdx.x == 0 && threadIdx.x < ntail) tail[threadIdx.x] = value;
+}
+
+// fill `count` int32 with `value`; p must be 16-byte aligned (torch allocations are).
+int fill_i32(int *p, size_t count, int value, cudaStream_t s) {
+    if (count == 0) return MSSVT_OK;
+    size_t n16 = count / 4;
+    int ntail = (int)(count % 4);
+    int grid = persistent_grid((long long)(n16 ? n16 : 1), 256, 8);
+    k_fill_i32x4<<<grid, 256, 0, s>>>((int4 *)p, n16, p + n16 * 4, ntail, value);
+    return check_launch();
+}
+
+// ------------------------------------------------------------------------------- hash build
+
+template <int MAXB>
+__device__ __forceinline__ int sample_start(const int *__restrict__ v_bs_cnt, int b) {
+    int s = 0;
+    for (int i = 0; i < b; ++i) s += __ldg(v_bs_cnt + i);
+    return s;
+}
+
+__global__ void k_hash_insert(int x_max, int y_max, int z_max, int num_voxels, int hash_size,
+                              const int4 *__restrict__ v_indices, const int *__restrict__ v_bs_cnt,
+                              unsigned long long *__restrict__ table) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= num_voxels) return;
+    int4 c = __ldg(v_indices + t);  // [b, z, y, x]
+    int b = c.x, z = c.y, y = c.z, x = c.w;
+    if (x >= x_max || x < 0 || y < 0 || y >= y_max || z < 0 || z >= z_max) return;
+    int local = t - sample_start<0>(v_bs_cnt, b);
+    int key = x * y_max * z_max + y * z_max + z;
+    unsigned long long *tab = table + (size_t)b * hash_size;
+    unsigned long long packed = (unsigned long long)(unsigned)key | ((unsigned long long)(unsigned)local << 32);
+    int slot = (int)((unsigned)key % (unsigned)hash_size);
+    for (int probes = 0; probes < hash_size; ++probes) {
+        unsigned long long prev = atomicCAS(tab + slot, ~0ull, packed);
+        if (prev == ~0ull) return;
+        if ((int)(unsigned)(prev & 0xffffffffull) == key) {
+            // duplicate coordinate: the reference lets the last writer win; sequential order
+            // (the oracle) means the highest voxel index, which atomicMax reproduces.
+            atomicMax((int *)(tab + slot) + 1, local);
+            return;
+        }
+        slot = slot + 1 == hash_size ? 0 : slot + 1;
+    }
+}
+
+__global__ void k_hash_lookup(int hash_size, int n, const int *__restrict__ batch_ids,
+                              const int *__restrict__ keys, const int2 *__restrict__ table,
+                              int *__restrict__ values) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    values[i] = table_find(table + (size_t)batch_ids[i] * hash_size, hash_size, keys[i]);
+}
+
+// world coordinates of every voxel, (N, 3) fp32 [x, y, z] (with_coords, mssvt_backbone.py:132-137)
+__global__ void k_world_coords(int n, const int4 *__restrict__ v_indices, float vx, float vy,
+                               float vz, float lx, float ly, float lz, float *__restrict__ xyz) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    int4 c = __ldg(v_indices + t);
+    xyz[3 * t + 0] = world_coord(c.w, vx, lx);
+    xyz[3 * t + 1] = world_coord(c.z, vy, ly);
+    xyz[3 * t + 2] = world_coord(c.y, vz, lz);
+}
+
+// per-sample voxel counts -> v_bs_cnt (B) and exclusive prefix v_start (B + 1); replaces the
+// per-sample `.sum().item()` loops (mssvt_utils.py:35-38, mssvt_backbone.py:124-130).
+__global__ void k_count_samples(int n, int batch_size, const int4 *__restrict__ v_indices,
+                                int *__restrict__ counts) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int b = t < n ? __ldg(v_indices + t).x : -1;
+    // samples are contiguous, so a warp usually holds one or two batch ids
+    unsigned active = __activemask();
+    if (b >= 0 && b < batch_size) {
+        unsigned peers = __match_any_sync(__activemask(), b);
+        if ((peers & lanemask_lt()) == 0) atomicAdd(counts + b, __popc(peers));
+    }
+    (void)active;
+}
+
+__global__ void k_prefix_small(int batch_size, const int *__restrict__ counts, int *__restrict__ start) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        int s = 0;
+        for (int b = 0; b < batch_size; ++b) { start[b] = s; s += counts[b]; }
+        start[batch_size] = s;
+    }
+}
+
+// ------------------------------------------------------------------------------- window partition
+
+#define WIN_BLOCK 1024
+
+// pass A: claim the window's slot, remember the lowest voxel index that maps to it
+__global__ void k_win_insert(int x_wgs, int y_wgs, int z_wgs, int x_ws, int y_ws, int z_ws,
+                             int num_voxels, int hash_size, const int4 *__restrict__ v_indices,
+                             int *__restrict__ table, int *__restrict__ slot_of) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= num_voxels) return;
+    int4 c = __ldg(v_indices + t);
+    int wz = c.y / z_ws, wy = c.z / y_ws, wx = c.w / x_ws;
+    int found = -1;
+    if (!(wx < 0 || wx >= x_wgs || wy < 0 || wy >= y_wgs || wz < 0 || wz >= z_wgs)) {
+        int *tab = table + (size_t)c.x * hash_size * 2;
+        int key = wx * y_wgs * z_wgs + wy * z_wgs + wz;
+        int slot = (int)((unsigned)key % (unsigned)hash_size);
+        for (int probes = 0; probes < hash_size; ++probes) {
+            int prev = atomicCAS(tab + 2 * slot, MSSVT_EMPTY, key);
+            if (prev == MSSVT_EMPTY || prev == key) {
+                atomicMin((unsigned *)(tab + 2 * slot + 1), (unsigned)t);
+                found = slot;
+                break;
+            }
+            slot = slot + 1 == hash_size ? 0 : slot + 1;
+        }
+    }
+    slot_of[t] = found;
+}
+
+// pass B: a voxel opens a window iff it is the lowest index in the slot; count per block and
+// per sample.  slot_of[t] is set to -1 for every other voxel.
+__global__ void __launch_bounds__(WIN_BLOCK)
+k_win_count(int num_voxels, int hash_size, int batch_size, const int4 *__restrict__ v_indices,
+            const int *__restrict__ table, int *__restrict__ slot_of, int *__restrict__ block_counts,
+            int *__restrict__ win_count) {
+    __shared__ int s_total;
+    if (threadIdx.x == 0) s_total = 0;
+    __syncthreads();
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int opens = 0, b = -1;
+    if (t < num_voxels) {
+        int slot = slot_of[t];
+        if (slot >= 0) {
+            b = __ldg(v_indices + t).x;
+            opens = table[((size_t)b * hash_size + slot) * 2 + 1] == t;
+            if (!opens) slot_of[t] = -1;
+        }
+    }
+    unsigned ball = __ballot_sync(0xffffffffu, opens);
+    if ((threadIdx.x & 31) == 0 && ball) atomicAdd(&s_total, __popc(ball));
+    if (opens) {
+        unsigned peers = __match_any_sync(__activemask(), b);
+        if ((peers & lanemask_lt()) == 0) atomicAdd(win_count + b, __popc(peers));
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        block_counts[blockIdx.x] = s_total;
+        if (s_total) atomicAdd(win_count + batch_size, s_total);
+    }
+}
+
+// pass C: rank = (#openers in earlier blocks) + (#openers earlier in this block); row `rank` of
+// the concatenated list gets [b, wz, wy, wx]; the table value becomes the per-sample row id.
+__global__ void __launch_bounds__(WIN_BLOCK)
+k_win_emit(int x_ws, int y_ws, int z_ws, int num_voxels, int hash_size, int batch_size,
+           int max_wins, int list_capacity, const int4 *__restrict__ v_indices,
+           int *__restrict__ table, const int *__restrict__ slot_of,
+           const int *__restrict__ block_counts, const int *__restrict__ win_count,
+           int4 *__restrict__ win_list, int *__restrict__ overflow) {
+    __shared__ int s_warp[WIN_BLOCK / 32];
+    __shared__ int s_base;
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // prefix over earlier blocks
+    int part = 0;
+    for (int i = threadIdx.x; i < blockIdx.x; i += blockDim.x) part += block_counts[i];
+    part = __reduce_add_sync(0xffffffffu, part);
+    if (lane == 0) s_warp[warp] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int s = 0;
+        for (int i = 0; i < WIN_BLOCK / 32; ++i) s += s_warp[i];
+        s_base = s;
+    }
+    __syncthreads();
+    int base = s_base;
+    __syncthreads();
+
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int slot = t < num_voxels ? slot_of[t] : -1;
+    int opens = slot >= 0;
+    unsigned ball = __ballot_sync(0xffffffffu, opens);
+    if (lane == 0) s_warp[warp] = __popc(ball);
+    __syncthreads();
+    int before = 0;
+    for (int i = 0; i < warp; ++i) before += s_warp[i];
+    if (!opens) return;
+    int rank = base + before + __popc(ball & lanemask_lt());
+    int4 c = __ldg(v_indices + t);
+    int first_row = 0;
+    for (int i = 0; i < c.x; ++i) first_row += win_count[i];
+    int local = rank - first_row;
+    if (local >= max_wins || rank >= list_capacity) {
+        atomicAdd(overflow, 1);
+        return;
+    }
+    win_list[rank] = make_int4(c.x, c.y / z_ws, c.z / y_ws, c.w / x_ws);
+    table[((size_t)c.x * hash_size + slot) * 2 + 1] = local;
+}
+
+}  // namespace mssvt
+
+using namespace mssvt;
+
+extern "C" {
+
+int mssvt_last_cuda_error(void) { return g_last_cuda_error; }
+
+const char *mssvt_version(void) { return "mssvt_b200 0.1 (sm_100a)"; }
+
+int mssvt_fill_i32(int *p, long long count, int value, void *stream) {
+    if (!p || count < 0) return MSSVT_ERR_INVALID;
+    return fill_i32(p, (size_t)count, value, (cudaStream_t)stream);
+}
+
+int mssvt_build_hash_table(int x_max, int y_max, int z_max, int num_voxels, int hash_size,
+                           int batch_size, const int *v_indices, const int *v_bs_cnt, int *table,
+                           void *stream) {
+    if (!table || hash_size <= 0 || batch_size <= 0 || num_voxels < 0) return MSSVT_ERR_INVALID;
+    if (num_voxels && (!v_indices || !v_bs_cnt)) return MSSVT_ERR_INVALID;
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = fill_i32(table, (size_t)batch_size * hash_size * 2, MSSVT_EMPTY, s);
+    if (rc || num_voxels == 0) return rc;
+    k_hash_insert<<<div_up(num_voxels, 256), 256, 0, s>>>(
+        x_max, y_max, z_max, num_voxels, hash_size, (const int4 *)v_indices, v_bs_cnt,
+        (unsigned long long *)table);
+    return check_launch();
+}
+
+int mssvt_hash_lookup(int hash_size, int num_queries, const int *batch_ids, const int *keys,
+                      const int *table, int *values, void *stream) {
+    if (num_queries < 0 || hash_size <= 0) return MSSVT_ERR_INVALID;
+    if (num_queries == 0) return MSSVT_OK;
+    if (!batch_ids || !keys || !table || !values) return MSSVT_ERR_INVALID;
+    k_hash_lookup<<<div_up(num_queries, 256), 256, 0, (cudaStream_t)stream>>>(
+        hash_size, num_queries, batch_ids, keys, (const int2 *)table, values);
+    return check_launch();
+}
+
+int mssvt_voxel_world_coords(int num_voxels, const int *v_indices, const float *voxel_size,
+                             const float *range_min, float *xyz, void *stream) {
+    if (num_voxels < 0 || !voxel_size || !range_min) return MSSVT_ERR_INVALID;
+    if (num_voxels == 0) return MSSVT_OK;
+    if (!v_indices || !xyz) return MSSVT_ERR_INVALID;
+    k_world_coords<<<div_up(num_voxels, 256), 256, 0, (cudaStream_t)stream>>>(
+        num_voxels, (const int4 *)v_indices, voxel_size[0], voxel_size[1], voxel_size[2],
+        range_min[0], range_min[1], range_min[2], xyz);
+    return check_launch();
+}
+
+int mssvt_count_samples(int num_rows, int batch_size, const int *indices, int *counts, int *start,
+                        void *stream) {
+    if (num_rows < 0 || batch_size <= 0 || !counts || !start) return MSSVT_ERR_INVALID;
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = fill_i32(counts, batch_size, 0, s);
+    if (rc) return rc;
+    if (num_rows) {
+        if (!indices) return MSSVT_ERR_INVALID;
+        k_count_samples<<<div_up(num_rows, 256), 256, 0, s>>>(num_rows, batch_size,
+                                                              (const int4 *)indices, counts);
+    }
+    k_prefix_small<<<1, 32, 0, s>>>(batch_size, counts, start);
+    return check_launch();
+}
+
+long long mssvt_window_partition_workspace_bytes(int num_voxels) {
+    long long blocks = (num_voxels + WIN_BLOCK - 1) / WIN_BLOCK;
+    return ((long long)num_voxels + blocks + 8) * 4;
+}
+
+// win_count: (batch_size + 2) int32 -> per-sample counts, [B] total, [B+1] rows that did not fit
+int mssvt_window_partition(int x_wgs, int y_wgs, int z_wgs, int x_ws, int y_ws, int z_ws,
+                           int num_voxels, int max_wins, int hash_size, int batch_size,
+                           int list_capacity, const int *v_indices, int *win_list, int *table,
+                           int *win_count, void *workspace, long long workspace_bytes,
+                           void *stream) {
+    if (!table || !win_count || hash_size <= 0 || batch_size <= 0 || num_voxels < 0 ||
+        x_ws <= 0 || y_ws <= 0 || z_ws <= 0)
+        return MSSVT_ERR_INVALID;
+    if (workspace_bytes < mssvt_window_partition_workspace_bytes(num_voxels)) return MSSVT_ERR_WORKSPACE;
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = fill_i32(table, (size_t)batch_size * hash_size * 2, MSSVT_EMPTY, s);
+    if (rc) return rc;
+    rc = fill_i32(win_count, batch_size + 2, 0, s);
+    if (rc || num_voxels == 0) return rc;
+    if (!v_indices || !win_list || !workspace) return MSSVT_ERR_INVALID;
+    int *slot_of = (int *)workspace;
+    int *block_counts = slot_of + num_voxels;
+    int blocks = div_up(num_voxels, WIN_BLOCK);
+    k_win_insert<<<div_up(num_voxels, 256), 256, 0, s>>>(x_wgs, y_wgs, z_wgs, x_ws, y_ws, z_ws,
+                                                         num_voxels, hash_size,
+                                                         (const int4 *)v_indices, table, slot_of);
+    k_win_count<<<blocks, WIN_BLOCK, 0, s>>>(num_voxels, hash_size, batch_size,
+                                             (const int4 *)v_indices, table, slot_of, block_counts,
+                                             win_count);
+    k_win_emit<<<blocks, WIN_BLOCK, 0, s>>>(x_ws, y_ws, z_ws, num_voxels, hash_size, batch_size,
+                                            max_wins, list_capacity, (const int4 *)v_indices, table,
+                                            slot_of, block_counts, win_count, (int4 *)win_list,
+                                            win_count + batch_size + 1);
+    return check_launch();
+}
+
+}  // extern "C"

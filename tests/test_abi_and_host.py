@@ -1,0 +1,93 @@
+"""CPU: the C-ABI library exports every symbol the header declares (no compute calls), the
+Python descriptor mirrors match the CUDA structs, and the host-side logic (offset tables, config,
+synthetic frames, module construction, state-dict names) behaves like the reference's."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, load_golden
+from mssvt_b200 import _lib
+from mssvt_b200.config import s0_model_cfg
+from mssvt_b200.mssvt_backbone import MixedScaleSparseTransformer, vox_query_table
+from mssvt_b200.synth import S0_GRID, S0_RANGE, S0_VOXEL, synth_frame
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "mssvt_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(mssvt_\w+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    assert os.path.exists(_lib.LIB_PATH), "run `make -C mssvt_b200/csrc` (or __graft_entry__.build())"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    names = _declared()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), "header declares %s but the library does not export it" % n
+    assert set(_lib.EXPORTS) == set(names), set(_lib.EXPORTS) ^ set(names)
+
+
+def test_descriptor_mirrors_match_cuda_structs():
+    lib = _lib.load()  # loading needs no GPU
+    assert lib.mssvt_sizeof_attn_shape() == ctypes.sizeof(_lib.AttnShape)
+    assert lib.mssvt_sizeof_ffn_shape() == ctypes.sizeof(_lib.FfnShape)
+    assert lib.mssvt_version().startswith(b"mssvt_b200")
+    # the reference's host-side FPS block size (cuda_utils.h:10-14)
+    for n, want in ((1, 0), (2, 1), (12, 3), (27, 4), (32, 5), (125, 6), (1024, 10), (5000, 10)):
+        assert lib.mssvt_fps_log2_block(n) == want
+
+
+def test_cpu_tensors_are_refused():
+    from mssvt_b200 import mssvt_ops
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        mssvt_ops.build_hash_table(1, 11, [4, 4, 4], torch.zeros((1, 4), dtype=torch.int32),
+                                   torch.ones(1, dtype=torch.int32))
+
+
+def test_query_tables_match_oracle_and_probe_counts():
+    from oracle.backbone import vox_query_table as orc_table
+    for w1, w2 in (([3, 3, 3], [5, 5, 5]), ([3, 3, 5], [7, 7, 9]), ([2, 2, 4], None), ([1, 1, 32], None)):
+        mine, ref = vox_query_table(w1, w2), orc_table(w1, w2)
+        assert mine.keys() == ref.keys()
+        for k in mine:
+            assert np.array_equal(mine[k], ref[k].numpy()), (w1, w2, k)
+    t = vox_query_table([3, 3, 3], [5, 5, 5])
+    assert [len(t[k]) for k in ("odd", "even", "win1", "win2")] == [12, 3, 12, 98]
+    t = vox_query_table([3, 3, 5], [7, 7, 9])
+    assert [len(t[k]) for k in ("odd", "even", "win1", "win2")] == [20, 5, 20, 396]
+
+
+def test_module_state_dict_names_load_reference_checkpoint():
+    blob, cfg, state = load_golden("s0_b2_n1200")
+    model = MixedScaleSparseTransformer(cfg, 64, blob["grid"].tolist(), list(S0_VOXEL), blob["pc_range"].tolist())
+    assert set(model.state_dict().keys()) == set(state.keys())
+    model.load_state_dict(state, strict=True)
+    assert model.num_point_features == 64
+    blk = model.backbone[0]
+    assert blk.max_num_odd == 12 and blk.max_num_even == 3 and blk.max_num_win1 == 27 and blk.max_num_win2 == 125
+    # construction rules of the reference: the last PARAMS entry cannot be a Block
+    bad = s0_model_cfg()
+    bad.PARAMS = bad.PARAMS[:3]
+    with pytest.raises(IndexError):
+        MixedScaleSparseTransformer(bad, 64, list(S0_GRID), list(S0_VOXEL), list(S0_RANGE))
+
+
+def test_fused_path_refuses_training_mode_and_cpu():
+    model = MixedScaleSparseTransformer(s0_model_cfg(hash_size=101), 64, list(S0_GRID), list(S0_VOXEL), list(S0_RANGE))
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        model({"voxel_features": torch.zeros(4, 64), "voxel_coords": torch.zeros(4, 4), "batch_size": 1})
+
+
+def test_synthetic_frames_are_deterministic_unique_and_sorted():
+    f1, c1 = synth_frame(3, 5000, batch_size=2, crop=0.3)
+    f2, c2 = synth_frame(3, 5000, batch_size=2, crop=0.3)
+    assert np.array_equal(c1, c2) and np.array_equal(f1, f2)
+    assert c1.shape == (10000, 4) and c1.dtype == np.int32 and f1.shape == (10000, 64)
+    key = ((c1[:, 0].astype(np.int64) * 468 + c1[:, 3]) * 468 + c1[:, 2]) * 32 + c1[:, 1]
+    assert (np.diff(key) > 0).all()  # unique, ordered by (b, x, y, z), samples contiguous
+    assert c1[:, 1].max() < 32 and c1[:, 2].max() < 468 and c1[:, 3].max() < 468 and c1.min() >= 0

@@ -1,0 +1,125 @@
+"""GPU: the fused backbone (module API -> C-ABI -> sm_100a kernels) against the golden vectors of
+the reference's Python layer and against the CPU oracle run live on the same seeded inputs.
+Bar: every index tensor bit-exact; features within 1e-4 * max|ref| (exact-fp32 FFMA kernels;
+only the summation order differs from the oracle's MKL GEMMs)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN_CASES, load_golden
+from oracle import backbone as orc
+from mssvt_b200.config import s0_model_cfg
+from mssvt_b200.mssvt_backbone import MixedScaleSparseTransformer
+from mssvt_b200.synth import S0_GRID, S0_RANGE, S0_VOXEL, synth_frame
+
+pytestmark = pytest.mark.gpu
+FEATURE_TOL = 1e-4  # relative to max|reference|, fp32 mode
+
+
+def run_product(cfg, state, grid, pc_range, feats, coords, batch):
+    model = MixedScaleSparseTransformer(cfg, feats.shape[1], list(grid), list(S0_VOXEL), list(pc_range))
+    model.load_state_dict(state, strict=True)
+    model = model.cuda().eval()
+    with torch.no_grad():
+        out = model({"voxel_features": feats.cuda(), "voxel_coords": coords.cuda().float(),
+                     "batch_size": batch})
+    assert out["encoded_spconv_tensor_stride"] == 1
+    return model, out["encoded_spconv_tensor"]
+
+
+def to_local(rows, win_b, v_start):
+    """global feature rows -> per-sample indices of the reference lists (-1 stays -1)"""
+    base = v_start[win_b.long()].unsqueeze(1)
+    return torch.where(rows >= 0, rows - base, rows)
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_backbone_matches_reference_golden(name):
+    blob, cfg, state = load_golden(name)
+    feats, coords = torch.from_numpy(blob["voxel_features"]), torch.from_numpy(blob["voxel_coords"])
+    model, sp = run_product(cfg, state, blob["grid"], blob["pc_range"], feats, coords, int(blob["batch_size"]))
+    assert torch.equal(sp.indices.cpu(), torch.from_numpy(blob["out_indices"]))
+    ref = torch.from_numpy(blob["out_features"])
+    err = (sp.features.cpu() - ref).abs().max().item()
+    assert err <= FEATURE_TOL * ref.abs().max().item(), err
+    dense = sp.dense()
+    assert dense.shape[0] == int(blob["batch_size"]) and dense.shape[1] == ref.shape[1]
+    idx = sp.indices.long()
+    assert torch.equal(dense[idx[:, 0], :, idx[:, 1], idx[:, 2], idx[:, 3]], sp.features)
+    assert int((dense != 0).any(1).sum()) <= idx.shape[0]
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_block_geometry_maps_bit_exact(name):
+    """sampled indices and gather maps of the first block vs the reference taps"""
+    blob, cfg, state = load_golden(name)
+    from mssvt_b200.mssvt_utils import SparseTensor
+    model = MixedScaleSparseTransformer(cfg, blob["voxel_features"].shape[1], blob["grid"].tolist(),
+                                        list(S0_VOXEL), blob["pc_range"].tolist()).cuda().eval()
+    coords = torch.from_numpy(blob["voxel_coords"]).cuda()
+    B = int(blob["batch_size"])
+    sp = SparseTensor(torch.from_numpy(blob["voxel_features"]).cuda(), coords, blob["grid"].tolist(),
+                      list(S0_VOXEL), blob["pc_range"].tolist(), B, cfg.HASH_SIZE)
+    blk = model.backbone[0]
+    g = blk.geometry(sp, taps=True)
+    W = int(g["win_count"][B])
+    assert W == blob["tap0/win_ind"].shape[0]
+    win = g["win_list"][:W].cpu()
+    assert torch.equal(win, torch.from_numpy(blob["tap0/win_ind"]))
+    v_start = sp.sample_counts()[1].cpu()
+    K = blk.key_num_sample
+    loc = lambda t: to_local(t[:W].cpu(), win[:, 0], v_start)
+    assert torch.equal(loc(g["q_row"]), torch.from_numpy(blob["tap0/q_ind"]))
+    assert torch.equal(loc(g["win1_row"]), torch.from_numpy(blob["tap0/win1_ind"]))
+    k_local = loc(g["k_row"])
+    assert torch.equal(k_local[:, :K], torch.from_numpy(blob["tap0/k_ind_win1"]))
+    assert torch.equal(k_local[:, K:], torch.from_numpy(blob["tap0/k_ind_win2"]))
+    fps = g["fps_idx"][:W].cpu()
+    assert torch.equal(fps[:, :K], torch.from_numpy(blob["tap0/fps_win1"]))
+    assert torch.equal(fps[:, K:], torch.from_numpy(blob["tap0/fps_win2"]))
+    mask = g["k_mask"][:W].cpu().bool()
+    assert torch.equal(mask[:, :K], torch.from_numpy(blob["tap0/k_mask_win1"]))
+    assert torch.equal(mask[:, K:], torch.from_numpy(blob["tap0/k_mask_win2"]))
+    if "tap0/nn_idx" in blob:
+        real = torch.from_numpy(blob["tap0/win1_ind"]) >= 0  # padded win1 slots go to the throw-away row
+        got = g["nn_idx"][:W].cpu().int()
+        assert torch.equal(got[real], torch.from_numpy(blob["tap0/nn_idx"])[real])
+
+
+def test_s0_block_and_backbone_vs_live_oracle_20k():
+    """BASELINE config 1 size: 20 k voxels, S0, batch 1 -- oracle computed live on the CPU"""
+    feats, coords = synth_frame(0, 20000, crop=0.38)
+    feats, coords = torch.from_numpy(feats), torch.from_numpy(coords)
+    cfg = s0_model_cfg()
+    torch.manual_seed(0)
+    model = MixedScaleSparseTransformer(cfg, 64, list(S0_GRID), list(S0_VOXEL), list(S0_RANGE))
+    state = {k: v.clone() for k, v in model.state_dict().items()}
+    taps = []
+    with torch.no_grad():
+        want = orc.backbone_forward(state, cfg, list(S0_GRID), list(S0_VOXEL), list(S0_RANGE), feats, coords, 1, taps=taps)
+    _, sp = run_product(cfg, state, S0_GRID, S0_RANGE, feats, coords, 1)
+    assert torch.equal(sp.indices.cpu(), want.indices)
+    err = (sp.features.cpu() - want.features).abs().max().item()
+    assert err <= FEATURE_TOL * want.features.abs().max().item(), err
+
+
+def test_full_size_frame_properties_150k():
+    """BASELINE config 2 size (too slow for the oracle in a unit test): size-independent checks"""
+    feats, coords = synth_frame(1, 150000)
+    feats, coords = torch.from_numpy(feats), torch.from_numpy(coords)
+    cfg = s0_model_cfg()
+    torch.manual_seed(0)
+    model = MixedScaleSparseTransformer(cfg, 64, list(S0_GRID), list(S0_VOXEL), list(S0_RANGE)).cuda().eval()
+    run = lambda f: model({"voxel_features": f.cuda(), "voxel_coords": coords.cuda().float(), "batch_size": 1})["encoded_spconv_tensor"]
+    with torch.no_grad():
+        a, b = run(feats), run(feats)
+    assert torch.equal(a.features, b.features) and torch.equal(a.indices, b.indices)  # run-to-run identical
+    assert torch.isfinite(a.features).all()
+    # output rows = occupied (x, y) pillars, in first-occurrence order of the sorted voxels
+    pillars = torch.unique(coords[:, 2].long() * 468 + coords[:, 3].long())
+    assert a.indices.shape[0] == pillars.numel() and a.spatial_shape == [468, 468, 1]
+    got = a.indices[:, 2].long() * 468 + a.indices[:, 3].long()
+    assert torch.equal(torch.sort(got.cpu())[0], pillars)
+    dense = a.dense()
+    assert dense.shape == (1, 64, 1, 468, 468)
+    assert torch.equal(dense[0, :, 0, a.indices[:, 2].long(), a.indices[:, 3].long()].t(), a.features)

@@ -1,0 +1,209 @@
+"""GPU: every operator of the drop-in API, called through the C-ABI, against the CPU oracle on
+the same seeded inputs -- bit-exact for all integer outputs and pure copies -- and, when
+oracle/_ref is present, against the reference's own CUDA kernels as well (which pins the oracle's
+C kernels to the real thing)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import backbone as orc
+from oracle import ops as oops
+from oracle import ref_kernels as ref
+from mssvt_b200 import mssvt_ops, pointnet2_utils
+from mssvt_b200.synth import S0_GRID, synth_frame
+
+pytestmark = pytest.mark.gpu
+HAVE_REF = ref.available()
+
+
+def cuda(t):
+    return t.cuda()
+
+
+def frame(seed, n, batch, crop):
+    _, coords = synth_frame(seed, n, batch_size=batch, crop=crop)
+    coords = torch.from_numpy(coords)
+    cnt = torch.bincount(coords[:, 0].long(), minlength=batch).int()
+    return coords, cnt
+
+
+def keys_of(coords, grid):
+    return (coords[:, 3] * grid[1] * grid[2] + coords[:, 2] * grid[2] + coords[:, 1]).int()
+
+
+@pytest.mark.parametrize("n,batch,hash_size", [(20000, 2, 50021), (3000, 3, 3001), (5, 1, 7)])
+def test_hash_build_lookups_bit_exact(n, batch, hash_size):
+    coords, cnt = frame(1, n, batch, 0.4)
+    grid = S0_GRID
+    want_tab = oops.build_hash_table(batch, hash_size, grid, coords, cnt)
+    got_tab = mssvt_ops.build_hash_table(batch, hash_size, grid, cuda(coords), cuda(cnt))
+    assert got_tab.shape == (batch, hash_size, 2) and got_tab.dtype == torch.int32
+    rng = np.random.default_rng(0)
+    absent = torch.from_numpy(rng.integers(0, grid[0] * grid[1] * grid[2], 4096).astype(np.int32))
+    q_keys = torch.cat([keys_of(coords, grid), absent])
+    q_b = torch.cat([coords[:, 0], torch.from_numpy(rng.integers(0, batch, 4096).astype(np.int32))]).int()
+    want = oops.hash_lookup(want_tab, q_b, q_keys)
+    got = mssvt_ops.hash_lookup(got_tab, cuda(q_b), cuda(q_keys)).cpu()
+    assert torch.equal(got, want)
+    # same set of occupied keys per sample (slot placement may differ: insertion order is free)
+    assert torch.equal(torch.sort(got_tab.cpu()[:, :, 0], 1)[0], torch.sort(want_tab[:, :, 0], 1)[0])
+    # tables are interchangeable: the oracle's table read by our lookup kernel
+    assert torch.equal(mssvt_ops.hash_lookup(cuda(want_tab), cuda(q_b), cuda(q_keys)).cpu(), want)
+    if HAVE_REF:
+        ref_tab = ref.build_hash_table(batch, hash_size, grid, cuda(coords), cuda(cnt))
+        assert torch.equal(mssvt_ops.hash_lookup(ref_tab, cuda(q_b), cuda(q_keys)).cpu(), want)
+
+
+def test_hash_build_out_of_range_and_empty():
+    coords = torch.tensor([[0, 1, 2, 3], [0, 40, 2, 3], [0, 1, -1, 3], [0, 2, 2, 2]], dtype=torch.int32)
+    cnt = torch.tensor([4], dtype=torch.int32)
+    want = oops.build_hash_table(1, 13, [8, 8, 8], coords, cnt)
+    got = mssvt_ops.build_hash_table(1, 13, [8, 8, 8], cuda(coords), cuda(cnt)).cpu()
+    assert torch.equal(torch.sort(got[0, :, 0])[0], torch.sort(want[0, :, 0])[0])
+    q = torch.tensor([3 * 64 + 2 * 8 + 1, 2 * 64 + 2 * 8 + 2], dtype=torch.int32)
+    assert mssvt_ops.hash_lookup(cuda(got), cuda(torch.zeros(2, dtype=torch.int32)), cuda(q)).tolist() == [0, 3]
+    empty = mssvt_ops.build_hash_table(2, 5, [8, 8, 8], torch.zeros((0, 4), dtype=torch.int32).cuda(),
+                                       torch.zeros(2, dtype=torch.int32).cuda())
+    assert (empty == -1).all()
+
+
+@pytest.mark.parametrize("win", [[3, 3, 3], [1, 1, 32], [2, 2, 4]])
+def test_window_partition_matches_oracle_order(win):
+    coords, cnt = frame(2, 20000, 2, 0.4)
+    grid = [S0_GRID[i] // win[i] for i in range(3)]
+    want_list, want_tab = oops.get_non_empty_window_center(win, 90000, 2, 50021, grid, coords)
+    got_list, got_tab = mssvt_ops.get_non_empty_window_center(win, 90000, 2, 50021, grid, cuda(coords))
+    assert torch.equal(got_list.cpu(), want_list)  # same rows in the same (first-occurrence) order
+    wkey = (want_list[:, 3] * grid[1] * grid[2] + want_list[:, 2] * grid[2] + want_list[:, 1]).int()
+    want_val = oops.hash_lookup(want_tab, want_list[:, 0], wkey)
+    got_val = mssvt_ops.hash_lookup(got_tab, cuda(want_list[:, 0].contiguous()), cuda(wkey)).cpu()
+    assert torch.equal(got_val, want_val)
+    if HAVE_REF:  # the reference numbers windows in atomic order: same set, any order
+        ref_list, _ = ref.get_non_empty_window_center(win, 90000, 2, 50021, grid, cuda(coords))
+        canon = lambda t: sorted(map(tuple, t.cpu().tolist()))
+        assert canon(ref_list) == canon(want_list)
+
+
+def test_window_partition_overflow_is_an_error_not_a_write_past_the_end():
+    coords, _ = frame(3, 5000, 1, 0.2)
+    with pytest.raises(RuntimeError, match="max_num_wins"):
+        mssvt_ops.get_non_empty_window_center([3, 3, 3], 100, 1, 20011, [156, 156, 10], cuda(coords))
+
+
+@pytest.mark.parametrize("w1,w2,caps", [([3, 3, 3], [5, 5, 5], (27, 125)), ([3, 3, 3], [5, 5, 5], (10, 40)),
+                                        ([3, 3, 5], [7, 7, 9], (45, 441))])
+def test_gather_two_window_bit_exact(w1, w2, caps):
+    coords, cnt = frame(4, 20000, 2, 0.4)
+    grid = [S0_GRID[i] // w1[i] for i in range(3)]
+    tab = oops.build_hash_table(2, 50021, S0_GRID, coords, cnt)
+    win, _ = oops.get_non_empty_window_center(w1, 90000, 2, 50021, grid, coords)
+    t = orc.vox_query_table(w1, w2)
+    args = (S0_GRID, w1, t["odd"].shape[0], t["even"].shape[0], caps[0], caps[1])
+    want = oops.gather_two_window_voxels(*args, t["odd"], t["even"], t["win1"], t["win2"], win, tab)
+    got = mssvt_ops.gather_two_window_voxels(*args, *[cuda(t[k]) for k in ("odd", "even", "win1", "win2")],
+                                             cuda(win), cuda(tab))
+    for g, w in zip(got, want):
+        assert torch.equal(g.cpu(), w)
+    if HAVE_REF:
+        r = ref.gather_two_window_voxels(*args, *[cuda(t[k]) for k in ("odd", "even", "win1", "win2")],
+                                         cuda(win), cuda(tab))
+        for g, w in zip(r, want):
+            assert torch.equal(g.cpu(), w)
+
+
+def test_gather_one_window_bit_exact_and_empty():
+    coords, cnt = frame(5, 20000, 2, 0.4)
+    w1 = [1, 1, 32]
+    grid = [S0_GRID[i] // w1[i] for i in range(3)]
+    tab = oops.build_hash_table(2, 50021, S0_GRID, coords, cnt)
+    win, _ = oops.get_non_empty_window_center(w1, 90000, 2, 50021, grid, coords)
+    t = orc.vox_query_table(w1)
+    want = oops.gather_one_window_voxels(S0_GRID, w1, 32, t["win1"], win, tab)
+    got = mssvt_ops.gather_one_window_voxels(S0_GRID, w1, 32, cuda(t["win1"]), cuda(win), cuda(tab))
+    assert torch.equal(got[0].cpu(), want[0]) and torch.equal(got[1].cpu(), want[1])
+    if HAVE_REF:
+        r = ref.gather_one_window_voxels(S0_GRID, w1, 32, cuda(t["win1"]), cuda(win), cuda(tab))
+        assert torch.equal(r[0].cpu(), want[0]) and torch.equal(r[1].cpu(), want[1])
+    none = mssvt_ops.gather_one_window_voxels(S0_GRID, w1, 32, cuda(t["win1"]), cuda(win[:0].contiguous()), cuda(tab))
+    assert none[0].shape == (0, 32) and none[1].shape == (0, 32, 3)
+
+
+@pytest.mark.parametrize("n,m,kind", [(27, 32, "grid"), (125, 32, "grid"), (12, 8, "grid"), (32, 32, "grid"),
+                                      (1, 4, "grid"), (64, 16, "float"), (200, 64, "float"),
+                                      (300, 40, "float"), (5000, 128, "float")])
+def test_fps_bit_exact_including_tie_order(n, m, kind):
+    rng = np.random.default_rng(n + m)
+    rows = 64 if n <= 300 else 3
+    if kind == "grid":  # integer offsets with padding at the origin: ties everywhere
+        pts = rng.integers(-3, 4, size=(rows, n, 3)).astype(np.float32)
+        pts[rng.random((rows, n)) < 0.5] = 0.0
+    else:
+        pts = rng.standard_normal((rows, n, 3)).astype(np.float32)
+    pts = torch.from_numpy(pts)
+    want = oops.farthest_point_sample(pts, m)
+    got = pointnet2_utils.farthest_point_sample(cuda(pts), m).cpu()
+    assert torch.equal(got, want)
+    if HAVE_REF:
+        assert torch.equal(ref.farthest_point_sample(cuda(pts), m).cpu(), want)
+
+
+def test_three_nn_bit_exact_on_voxel_grids():
+    rng = np.random.default_rng(9)
+    # voxel-centre coordinates: (idx + 0.5) * vs + lo in fp32 -> equidistant neighbours differ only
+    # by rounding noise, so the FMA contraction order decides the indices
+    vs, lo = np.float32([0.32, 0.32, 0.1875]), np.float32([-74.88, -74.88, -2.0])
+    idx_u = rng.integers(0, 468, size=(512, 27, 3)) % np.array([468, 468, 32])
+    idx_k = idx_u[:, :12] + rng.integers(-1, 2, size=(512, 12, 3))
+    unknown = torch.from_numpy(((idx_u.astype(np.float32) + np.float32(0.5)) * vs + lo).astype(np.float32))
+    known = torch.from_numpy(((idx_k.astype(np.float32) + np.float32(0.5)) * vs + lo).astype(np.float32))
+    known[:, 8:] = 0.0  # padded query slots sit at the world origin
+    wd, wi = oops.three_nn(unknown, known)
+    gd, gi = pointnet2_utils.three_nn(cuda(unknown), cuda(known))
+    assert torch.equal(gi.cpu(), wi)
+    assert torch.equal(gd.cpu() ** 2, wd ** 2) or torch.allclose(gd.cpu(), wd, rtol=1e-6, atol=0)
+    if HAVE_REF:
+        rd, ri = ref.three_nn(cuda(unknown), cuda(known))
+        assert torch.equal(ri.cpu(), wi) and torch.equal(rd.cpu(), gd.cpu())
+    # fewer than three known points: the unused bests stay at +inf / index 0
+    gd, gi = pointnet2_utils.three_nn(cuda(unknown[:4]), cuda(known[:4, :2].contiguous()))
+    wd, wi = oops.three_nn(unknown[:4], known[:4, :2].contiguous())
+    assert torch.equal(gi.cpu(), wi) and torch.isinf(gd[..., 2]).all()
+
+
+@pytest.mark.parametrize("C,ns", [(64, 32), (3, 27), (32, 125), (48, 5)])
+def test_grouping_operation_forward_backward(C, ns):
+    rng = np.random.default_rng(C * ns)
+    fbc = torch.tensor([700, 300, 500], dtype=torch.int32)
+    ibc = torch.tensor([40, 0, 25], dtype=torch.int32)
+    feats = torch.from_numpy(rng.standard_normal((1500, C)).astype(np.float32))
+    idx = torch.from_numpy(rng.integers(-1, 300, size=(65, ns)).astype(np.int32))
+    want = oops.grouping_operation(feats, fbc, idx, ibc)
+    f = cuda(feats).requires_grad_(True)
+    got = mssvt_ops.grouping_operation(f, cuda(fbc), cuda(idx), cuda(ibc))
+    assert torch.equal(got.detach().cpu(), want)  # pure copy: bit-exact
+    if HAVE_REF:
+        assert torch.equal(ref.grouping_operation(cuda(feats), cuda(fbc), cuda(idx), cuda(ibc)).cpu(), want)
+    g = torch.from_numpy(rng.standard_normal(want.shape).astype(np.float32))
+    got.backward(cuda(g))
+    want_grad = oops.grouping_operation_grad(g, 1500, fbc, idx, ibc)
+    assert torch.allclose(f.grad.cpu(), want_grad, rtol=1e-5, atol=1e-5)  # float atomics: order-free sum
+
+
+def test_gather_and_group_points_bit_exact():
+    rng = np.random.default_rng(2)
+    feats = torch.from_numpy(rng.standard_normal((7, 5, 40)).astype(np.float32))
+    idx = torch.from_numpy(rng.integers(0, 40, size=(7, 16)).astype(np.int32))
+    assert torch.equal(pointnet2_utils.gather_operation(cuda(feats), cuda(idx)).cpu(), oops.gather_operation(feats, idx))
+    idx3 = torch.from_numpy(rng.integers(0, 40, size=(7, 9, 3)).astype(np.int32))
+    want = oops.group_points(feats, idx3)
+    f = cuda(feats).requires_grad_(True)
+    got = pointnet2_utils.grouping_operation(f, cuda(idx3))
+    assert torch.equal(got.detach().cpu(), want)
+    got.sum().backward()
+    counts = torch.zeros(7, 40)
+    for b in range(7):
+        counts[b] = torch.bincount(idx3[b].reshape(-1).long(), minlength=40).float()
+    assert torch.allclose(f.grad.cpu(), counts[:, None, :].expand(7, 5, 40))
+    if HAVE_REF:
+        assert torch.equal(ref.group_points(cuda(feats), cuda(idx3)).cpu(), want)
+        assert torch.equal(ref.gather_operation(cuda(feats), cuda(idx)).cpu(), oops.gather_operation(feats, idx))
