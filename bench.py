@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py -- MsSVT backbone forward throughput on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            our arm (sm_100a kernels)
+    python bench.py --impl reference --gpus N ...            reference arm: the CPU restatement of
+                                                             the reference path on the host cores
+
+A step = one backbone forward (3 mixed-scale blocks + z-compress block, config S0) over one
+synthetic Waymo-scale frame per GPU (BASELINE config 2; with N > 1 GPUs every rank runs its own
+frames, config 4: sharded by frame, no data-path collective, weak scaling).
+  value  = voxels/s with the frames already resident in HBM, CUDA-event time over exactly K steps,
+           max over ranks;
+  e2e    = the same metric through the module API from pinned HOST buffers: H2D of the step's
+           features + coordinates, forward, D2H of the output features + indices, every step;
+  roofline      = the dominant kernel of the step against the measured HBM peak;
+  cpu_baseline  = the CPU oracle on the host cores, bounded sample (rank 0, N = 1 only).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from mssvt_b200.config import s0_model_cfg  # noqa: E402
+from mssvt_b200.synth import S0_GRID, S0_RANGE, S0_VOXEL, synth_frame  # noqa: E402
+
+METRIC = "mssvt_backbone_fwd_voxels_per_s"
+UNIT = "voxels/s"
+N_VOXELS = 150000
+POOL = 8  # distinct frames rotated through the timed loop: 8 x 40.8 MB = 326 MB > 126 MB L2
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index):
+        self.idx, self.proc = device_index, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, reasons = [], 0.0, set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = max(mx, float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        busy = [v for v in sm if v > 0.5 * mx] or sm
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def build_model(device):
+    from mssvt_b200.mssvt_backbone import MixedScaleSparseTransformer
+    cfg = s0_model_cfg()
+    torch.manual_seed(0)  # random-init weights of the S0 architecture (no checkpoints offline)
+    model = MixedScaleSparseTransformer(cfg, 64, list(S0_GRID), list(S0_VOXEL), list(S0_RANGE))
+    return cfg, model.to(device).eval()
+
+
+def algorithmic_bytes(kernel, n, w, pillars):
+    """Algorithmic HBM bytes per launch (DESIGN.md, section 'Kernels'); fp32, C = 64, S0."""
+    C4 = 64 * 4
+    table = {
+        # read xn rows once + maps, write the covered rows of `merged`
+        "mssvt_block_attention": n * C4 + w * (12 * 4 + 64 * 4 + 64 + 27 * 4 + 27 * 3 * 5) + n * 12 + n * C4,
+        # read x + merged + covered flag, write y
+        "mssvt_ffn": 3 * n * C4 + n,
+        "mssvt_layernorm": 2 * n * C4,
+        # read xn + xyz + rows map, write one row per pillar
+        "mssvt_compress_attention": n * C4 + n * 12 + pillars * 32 * 4 + pillars * C4,
+        # window rows in, compact maps out; probes hit the L2-resident 3.2 MB table
+        "mssvt_block_geometry": w * 16 + w * (12 * 4 + 27 * 4 + 64 * 4 + 64 + 27 * 3 * 5) + n,
+        "mssvt_window_partition": 16 * n + 16 * w + 8 * 400000 + 4 * n,
+        "mssvt_build_hash_table": 16 * n + 8 * n + 8 * 400000,
+    }
+    return table.get(kernel)
+
+
+def our_arm(args):
+    rank, world, local = dist_env()
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    from mssvt_b200 import _lib
+    _lib.load()
+    cfg, model = build_model(device)
+
+    # synthetic frames: POOL distinct frames per rank (seeds differ per rank: sharded by frame)
+    host = []
+    for i in range(POOL):
+        f, c = synth_frame(1000 * rank + i, N_VOXELS)
+        host.append((torch.from_numpy(f).pin_memory(), torch.from_numpy(c).pin_memory()))
+    dev = [(f.to(device), c.to(device).float()) for f, c in host]
+
+    def step(i):
+        f, c = dev[i % POOL]
+        return model({"voxel_features": f, "voxel_coords": c, "batch_size": 1})["encoded_spconv_tensor"]
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        for i in range(args.warmup):
+            out = step(i)
+        pillars = out.features.shape[0]
+        # ---- timed region: exactly K steps, device time, inputs resident in HBM
+        sampler = ClockSampler(local)
+        sampler.start()
+        launches0 = _lib.call("mssvt_launch_count")
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for i in range(args.steps):
+            step(args.warmup + i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = _lib.call("mssvt_launch_count") - launches0
+        clocks = sampler.stop()
+
+        # ---- e2e: module API from pinned host buffers, H2D + forward + D2H every step
+        out_feat = torch.empty((N_VOXELS, 64), dtype=torch.float32).pin_memory()
+        out_idx = torch.empty((N_VOXELS, 4), dtype=torch.int32).pin_memory()
+
+        def e2e_step(i):
+            f, c = host[i % POOL]
+            fd = f.to(device, non_blocking=True)
+            cd = c.to(device, non_blocking=True)
+            sp = model({"voxel_features": fd, "voxel_coords": cd, "batch_size": 1})["encoded_spconv_tensor"]
+            m = sp.features.shape[0]
+            out_feat[:m].copy_(sp.features, non_blocking=True)
+            out_idx[:m].copy_(sp.indices, non_blocking=True)
+            return m
+
+        for i in range(max(args.warmup, 3)):
+            e2e_step(i)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            m = e2e_step(i)
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        h2d = host[0][0].numel() * 4 + host[0][1].numel() * 4
+        d2h = m * 64 * 4 + m * 4 * 4
+
+        # ---- per-kernel breakdown (instrumented extra pass, not part of the timed region)
+        _lib.PROFILE = []
+        for i in range(args.steps):
+            step(args.warmup + i)
+        torch.cuda.synchronize()
+        per = {}
+        for name, a, b in _lib.PROFILE:
+            t = per.setdefault(name, [0.0, 0])
+            t[0] += a.elapsed_time(b)
+            t[1] += 1
+        _lib.PROFILE = None
+
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms, e2e_s], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_s = float(t[0]), float(t[1])
+    total_voxels = N_VOXELS * args.steps * world
+    value = total_voxels / (ms * 1e-3)
+    e2e_value = total_voxels / e2e_s
+
+    peaks, peak_kind = measured_peaks()
+    # dominant kernel of the step by accumulated device time
+    dom = max(per.items(), key=lambda kv: kv[1][0])
+    dom_name, (dom_ms, dom_n) = dom[0], dom[1]
+    w_est = int(0.26 * N_VOXELS)
+    abytes = algorithmic_bytes(dom_name, N_VOXELS, w_est, pillars)
+    avg_s = dom_ms / dom_n * 1e-3
+    achieved = abytes / avg_s / 1e9 if abytes else None
+    roofline = {"kernel": dom_name, "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"],
+                "unit": "GB/s", "frac": (achieved / peaks["hbm_gbs"]) if achieved else None,
+                "traffic": None, "peak_kind": peak_kind, "avg_launch_us": avg_s * 1e6,
+                "share_of_step": dom_ms / sum(v[0] for v in per.values()),
+                "algorithmic_bytes_per_launch": abytes}
+    breakdown = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps}
+                 for k, v in sorted(per.items(), key=lambda kv: -kv[1][0])}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "full MsSVT backbone forward (S0: 3 mixed-scale blocks 3^3/5^3 windows, 2+2 heads, "
+                               "K=32 + z-compress block), one synthetic Waymo-scale frame of 150000 voxels per GPU per "
+                               "step, C=64, hash 400000, batch 1; random-init weights (seed 0)",
+                   "voxels_per_frame": N_VOXELS, "frames_per_step": world, "sharding": "by frame, no collective",
+                   "l2": "inputs rotate through a pool of %d distinct frames (326 MB > 126 MB L2)" % POOL,
+                   "precision": "fp32 FFMA (features within 1e-4 of the fp32 reference)"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_s / args.steps * 1e3},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roofline,
+        "kernels": breakdown,
+        "output_rows": int(pillars),
+    }
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(budget_s=20.0)
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------- CPU arm
+
+def oracle_forward_fn():
+    from oracle import backbone as orc
+    from mssvt_b200.mssvt_backbone import MixedScaleSparseTransformer
+    cfg = s0_model_cfg()
+    torch.manual_seed(0)
+    model = MixedScaleSparseTransformer(cfg, 64, list(S0_GRID), list(S0_VOXEL), list(S0_RANGE))
+    state = {k: v.clone() for k, v in model.state_dict().items()}
+
+    def run(feats, coords):
+        with torch.no_grad():
+            return orc.backbone_forward(state, cfg, list(S0_GRID), list(S0_VOXEL), list(S0_RANGE), feats, coords, 1)
+    return run
+
+
+def cpu_baseline(budget_s=20.0):
+    """The CPU oracle (a port of the reference path: the reference has no CPU implementation) on
+    the host cores, all threads, one full 150 k-voxel frame per pass; passes until ~budget_s."""
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    run = oracle_forward_fn()
+    f, c = synth_frame(0, N_VOXELS)
+    f, c = torch.from_numpy(f), torch.from_numpy(c)
+    run(f, c)  # warm-up (MKL / OpenMP thread pools)
+    times = []
+    t_all = time.perf_counter()
+    while time.perf_counter() - t_all < budget_s and len(times) < 5:
+        t0 = time.perf_counter()
+        run(f, c)
+        times.append(time.perf_counter() - t0)
+    med = statistics.median(times)
+    return {"value": N_VOXELS / med, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d full-backbone passes over one 150000-voxel frame (median %.2f s/frame); "
+                      "PyTorch-CPU fp32 + OpenMP C kernels (oracle/)" % (len(times), med)}
+
+
+def reference_arm(args):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    run = oracle_forward_fn()
+    frames = []
+    for i in range(2):
+        f, c = synth_frame(i, N_VOXELS)
+        frames.append((torch.from_numpy(f), torch.from_numpy(c)))
+    steps = min(args.steps, 6)       # each step is one full frame (~5-15 s of CPU work)
+    warm = min(args.warmup, 1)
+    for i in range(warm):
+        run(*frames[i % 2])
+    t0 = time.perf_counter()
+    for i in range(steps):
+        run(*frames[i % 2])
+    dt = time.perf_counter() - t0
+    value = N_VOXELS * steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
+        "steps": steps, "warmup": warm, "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "full MsSVT backbone forward (S0), one synthetic 150000-voxel frame per step, "
+                               "CPU restatement of the reference path on the host cores (the reference itself is CUDA-only)",
+                   "voxels_per_frame": N_VOXELS},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%d steps of one full 150000-voxel frame" % steps},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        our_arm(args)
+
+
+if __name__ == "__main__":
+    main()

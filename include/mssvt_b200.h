@@ -35,6 +35,7 @@ extern "C" {
 
 const char *mssvt_version(void);
 int mssvt_last_cuda_error(void);
+long long mssvt_launch_count(void); /* kernels launched by this library since it was loaded */
 
 /* ---- utilities ------------------------------------------------------------------------- */
 

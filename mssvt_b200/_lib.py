@@ -45,10 +45,13 @@ _SIGNATURES = {
     "mssvt_sizeof_ffn_shape": [],
     "mssvt_last_cuda_error": [],
     "mssvt_version": [],
+    "mssvt_launch_count": [],
 }
-_RESTYPES = {"mssvt_window_partition_workspace_bytes": L, "mssvt_version": ctypes.c_char_p}
+_RESTYPES = {"mssvt_window_partition_workspace_bytes": L, "mssvt_version": ctypes.c_char_p,
+             "mssvt_launch_count": L}
 _NO_STATUS = {"mssvt_window_partition_workspace_bytes", "mssvt_fps_log2_block", "mssvt_version",
-              "mssvt_sizeof_attn_shape", "mssvt_sizeof_ffn_shape", "mssvt_last_cuda_error"}
+              "mssvt_sizeof_attn_shape", "mssvt_sizeof_ffn_shape", "mssvt_last_cuda_error",
+              "mssvt_launch_count"}
 _ERRORS = {-1: "invalid argument", -2: "CUDA launch/runtime error", -3: "workspace too small"}
 
 EXPORTS = tuple(_SIGNATURES)
@@ -95,10 +98,22 @@ def load():
     return lib
 
 
+# When set to a list, call() brackets every entry point with CUDA events on the current stream
+# and appends (name, start_event, end_event): bench.py's per-kernel breakdown.  None = off.
+PROFILE = None
+
+
 def call(name, *args):
     """Invoke an entry point; raise on a non-zero status."""
     fn = getattr(load(), name)
-    rc = fn(*args)
+    if PROFILE is not None and name not in _NO_STATUS:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args)
+        e1.record()
+        PROFILE.append((name, e0, e1))
+    else:
+        rc = fn(*args)
     if name in _NO_STATUS:
         return rc
     if rc != 0:

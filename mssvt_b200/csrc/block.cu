@@ -637,6 +637,7 @@ int mssvt_layernorm(int num_rows, const int *num_rows_dev, int C, const float *x
     if (num_rows < 0 || C <= 0 || C > 256) return MSSVT_ERR_INVALID;
     if (num_rows == 0) return MSSVT_OK;
     if (!x || !gamma || !beta || !y) return MSSVT_ERR_INVALID;
+    ++g_launches;
     k_layernorm<<<persistent_grid(num_rows, 8, 8), 256, 0, (cudaStream_t)stream>>>(
         num_rows, num_rows_dev, C, x, gamma, beta, eps, y);
     return check_launch();
@@ -663,6 +664,7 @@ int mssvt_block_attention(const void *shape, int shape_bytes, const float *param
     int per_sm = (int)(220 * 1024 / smem);
     per_sm = per_sm > 4 ? 4 : per_sm < 1 ? 1 : per_sm;
     int grid = persistent_grid(win_capacity, ATT_WARPS, per_sm, 1);
+    ++g_launches;
     k_block_attention<<<grid, ATT_WARPS * 32, smem, (cudaStream_t)stream>>>(
         S, params, win_capacity, win_count_total, (const int4 *)win_list, xn, xyz, q_row, k_row,
         k_mask, win1_row, nn_idx, nn_w, merged);
@@ -684,6 +686,7 @@ int mssvt_compress_attention(const void *shape, int shape_bytes, const float *pa
     int per_sm = (int)(220 * 1024 / smem);
     per_sm = per_sm > 4 ? 4 : per_sm < 1 ? 1 : per_sm;
     int grid = persistent_grid(win_capacity, ATT_WARPS, per_sm, 1);
+    ++g_launches;
     k_compress_attention<<<grid, ATT_WARPS * 32, smem, (cudaStream_t)stream>>>(
         S, params, win_capacity, win_count_total, (const int4 *)win_list, xn, xyz, k_row, out);
     return check_launch();
@@ -704,6 +707,7 @@ int mssvt_ffn(const void *shape, int shape_bytes, const float *params, int num_r
     int per_sm = (int)(220 * 1024 / smem);
     per_sm = per_sm > 2 ? 2 : per_sm < 1 ? 1 : per_sm;
     int grid = persistent_grid(num_rows, FFN_WARPS * FFN_ROWS, per_sm, 1);
+    ++g_launches;
     k_ffn<<<grid, FFN_WARPS * 32, smem, (cudaStream_t)stream>>>(S, params, num_rows, num_rows_dev, x,
                                                               merged, covered, y);
     return check_launch();
@@ -717,6 +721,7 @@ int mssvt_dense_scatter(int num_rows, const int *num_rows_dev, int batch_size, i
     if (e != cudaSuccess) { g_last_cuda_error = (int)e; return MSSVT_ERR_LAUNCH; }
     if (num_rows == 0) return MSSVT_OK;
     if (!features || !indices) return MSSVT_ERR_INVALID;
+    ++g_launches;
     k_dense_scatter<<<persistent_grid((long long)num_rows * C, 256, 8), 256, 0, s>>>(
         num_rows, num_rows_dev, C, D, H, W, features, (const int4 *)indices, out);
     return check_launch();

@@ -389,6 +389,7 @@ int mssvt_gather_two_window(int x_max, int y_max, int z_max, int x_ws, int y_ws,
     if (smem > 200 * 1024) return MSSVT_ERR_INVALID;
     cudaFuncSetAttribute(k_gather_lists, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int grid = persistent_grid(num_wins, GEO_WARPS, 8);
+    ++g_launches;
     k_gather_lists<<<grid, GEO_WARPS * 32, smem, (cudaStream_t)stream>>>(
         g, tabs, num_wins, (const int4 *)win_indices, (const int2 *)table, out);
     return check_launch();
@@ -454,6 +455,7 @@ int mssvt_block_geometry(int x_max, int y_max, int z_max, int x_ws, int y_ws, in
     if (smem > 200 * 1024) return MSSVT_ERR_INVALID;
     cudaFuncSetAttribute(k_block_geometry, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int grid = persistent_grid(win_capacity, GEO_WARPS, 6);
+    ++g_launches;
     k_block_geometry<<<grid, GEO_WARPS * 32, smem, s>>>(P, tabs, win_count_total,
                                                        (const int4 *)win_list, (const int2 *)table,
                                                        v_start, out);
@@ -476,6 +478,7 @@ int mssvt_window_rows(int x_max, int y_max, int z_max, int x_ws, int y_ws, int z
     size_t smem = (size_t)(num_win1 * 3 + GEO_WARPS * max_win1 * 2) * sizeof(int);
     if (smem > 200 * 1024) return MSSVT_ERR_INVALID;
     cudaFuncSetAttribute(k_window_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    ++g_launches;
     k_window_rows<<<persistent_grid(win_capacity, GEO_WARPS, 8), GEO_WARPS * 32, smem,
                     (cudaStream_t)stream>>>(g, tabs, win_count_total, (const int4 *)win_list,
                                             (const int2 *)table, v_start, k_row);

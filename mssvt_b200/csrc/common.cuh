@@ -14,6 +14,7 @@
 namespace mssvt {
 
 extern int g_last_cuda_error;
+extern long long g_launches;  // kernels launched by this library since load
 
 static inline int check_launch() {
     cudaError_t e = cudaGetLastError();

@@ -18,6 +18,7 @@
 namespace mssvt {
 
 int g_last_cuda_error = 0;
+long long g_launches = 0;
 
 // ------------------------------------------------------------------------------- fill
 
@@ -36,6 +37,7 @@ int fill_i32(int *p, size_t count, int value, cudaStream_t s) {
     size_t n16 = count / 4;
     int ntail = (int)(count % 4);
     int grid = persistent_grid((long long)(n16 ? n16 : 1), 256, 8);
+    ++g_launches;
     k_fill_i32x4<<<grid, 256, 0, s>>>((int4 *)p, n16, p + n16 * 4, ntail, value);
     return check_launch();
 }
@@ -234,6 +236,7 @@ using namespace mssvt;
 extern "C" {
 
 int mssvt_last_cuda_error(void) { return g_last_cuda_error; }
+long long mssvt_launch_count(void) { return g_launches; }
 
 const char *mssvt_version(void) { return "mssvt_b200 0.1 (sm_100a)"; }
 
@@ -250,6 +253,7 @@ int mssvt_build_hash_table(int x_max, int y_max, int z_max, int num_voxels, int 
     cudaStream_t s = (cudaStream_t)stream;
     int rc = fill_i32(table, (size_t)batch_size * hash_size * 2, MSSVT_EMPTY, s);
     if (rc || num_voxels == 0) return rc;
+    ++g_launches;
     k_hash_insert<<<div_up(num_voxels, 256), 256, 0, s>>>(
         x_max, y_max, z_max, num_voxels, hash_size, (const int4 *)v_indices, v_bs_cnt,
         (unsigned long long *)table);
@@ -261,6 +265,7 @@ int mssvt_hash_lookup(int hash_size, int num_queries, const int *batch_ids, cons
     if (num_queries < 0 || hash_size <= 0) return MSSVT_ERR_INVALID;
     if (num_queries == 0) return MSSVT_OK;
     if (!batch_ids || !keys || !table || !values) return MSSVT_ERR_INVALID;
+    ++g_launches;
     k_hash_lookup<<<div_up(num_queries, 256), 256, 0, (cudaStream_t)stream>>>(
         hash_size, num_queries, batch_ids, keys, (const int2 *)table, values);
     return check_launch();
@@ -271,6 +276,7 @@ int mssvt_voxel_world_coords(int num_voxels, const int *v_indices, const float *
     if (num_voxels < 0 || !voxel_size || !range_min) return MSSVT_ERR_INVALID;
     if (num_voxels == 0) return MSSVT_OK;
     if (!v_indices || !xyz) return MSSVT_ERR_INVALID;
+    ++g_launches;
     k_world_coords<<<div_up(num_voxels, 256), 256, 0, (cudaStream_t)stream>>>(
         num_voxels, (const int4 *)v_indices, voxel_size[0], voxel_size[1], voxel_size[2],
         range_min[0], range_min[1], range_min[2], xyz);
@@ -285,9 +291,11 @@ int mssvt_count_samples(int num_rows, int batch_size, const int *indices, int *c
     if (rc) return rc;
     if (num_rows) {
         if (!indices) return MSSVT_ERR_INVALID;
+        ++g_launches;
         k_count_samples<<<div_up(num_rows, 256), 256, 0, s>>>(num_rows, batch_size,
                                                               (const int4 *)indices, counts);
     }
+    ++g_launches;
     k_prefix_small<<<1, 32, 0, s>>>(batch_size, counts, start);
     return check_launch();
 }
@@ -316,12 +324,15 @@ int mssvt_window_partition(int x_wgs, int y_wgs, int z_wgs, int x_ws, int y_ws, 
     int *slot_of = (int *)workspace;
     int *block_counts = slot_of + num_voxels;
     int blocks = div_up(num_voxels, WIN_BLOCK);
+    ++g_launches;
     k_win_insert<<<div_up(num_voxels, 256), 256, 0, s>>>(x_wgs, y_wgs, z_wgs, x_ws, y_ws, z_ws,
                                                          num_voxels, hash_size,
                                                          (const int4 *)v_indices, table, slot_of);
+    ++g_launches;
     k_win_count<<<blocks, WIN_BLOCK, 0, s>>>(num_voxels, hash_size, batch_size,
                                              (const int4 *)v_indices, table, slot_of, block_counts,
                                              win_count);
+    ++g_launches;
     k_win_emit<<<blocks, WIN_BLOCK, 0, s>>>(x_ws, y_ws, z_ws, num_voxels, hash_size, batch_size,
                                             max_wins, list_capacity, (const int4 *)v_indices, table,
                                             slot_of, block_counts, win_count, (int4 *)win_list,

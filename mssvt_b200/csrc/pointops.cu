@@ -295,6 +295,7 @@ int mssvt_group_features(int B, int M, int C, int nsample, const float *features
     cudaFuncSetAttribute(k_group_features, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int per_sm = (int)(200 * 1024 / (smem + 1024));
     per_sm = per_sm > 8 ? 8 : per_sm < 1 ? 1 : per_sm;
+    ++g_launches;
     k_group_features<<<persistent_grid(M, 1, per_sm), GF_THREADS, smem, (cudaStream_t)stream>>>(
         B, M, C, nsample, features, features_batch_cnt, idx, idx_batch_cnt, out);
     return check_launch();
@@ -316,6 +317,7 @@ int mssvt_group_features_grad(int B, int M, int C, int N, int nsample, const flo
     cudaFuncSetAttribute(k_group_features_grad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int per_sm = (int)(200 * 1024 / (smem + 1024));
     per_sm = per_sm > 8 ? 8 : per_sm < 1 ? 1 : per_sm;
+    ++g_launches;
     k_group_features_grad<<<persistent_grid(M, 1, per_sm), GF_THREADS, smem, s>>>(
         B, M, C, nsample, grad_out, idx, idx_batch_cnt, features_batch_cnt, grad_features);
     return check_launch();
@@ -331,6 +333,7 @@ int mssvt_fps(int b, int n, int m, const float *dataset, float *temp, int *idxs,
     cudaStream_t s = (cudaStream_t)stream;
     if (n <= FPS_WARP_MAXN) {
         size_t smem = (size_t)FPS_WARPS * n * 4 * sizeof(float);
+        ++g_launches;
         k_fps_warp<<<persistent_grid(b, FPS_WARPS, 8), FPS_WARPS * 32, smem, s>>>(b, n, m, log2b,
                                                                                   dataset, idxs);
     } else {
@@ -339,6 +342,7 @@ int mssvt_fps(int b, int n, int m, const float *dataset, float *temp, int *idxs,
         if (!in_smem && !temp) return MSSVT_ERR_WORKSPACE;
         if (in_smem)
             cudaFuncSetAttribute(k_fps_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        ++g_launches;
         k_fps_cta<<<b, FPS_CTA, in_smem ? smem : 0, s>>>(n, m, log2b, in_smem, dataset, temp, idxs);
     }
     return check_launch();
@@ -350,6 +354,7 @@ int mssvt_gather_points(int b, int c, int n, int m, const float *points, const i
     long long total = (long long)b * c * m;
     if (total == 0) return MSSVT_OK;
     if (!points || !idx || !out) return MSSVT_ERR_INVALID;
+    ++g_launches;
     k_gather_points<<<persistent_grid(total, 256, 8), 256, 0, (cudaStream_t)stream>>>(b, c, n, m,
                                                                                       points, idx, out);
     return check_launch();
@@ -364,6 +369,7 @@ int mssvt_three_nn(int b, int n, int m, const float *unknown, const float *known
     for (int b0 = 0; b0 < b; b0 += 65535) {
         int bb = b - b0 < 65535 ? b - b0 : 65535;
         dim3 grid(div_up(n, 128), bb);
+        ++g_launches;
         k_three_nn<<<grid, 128, 0, (cudaStream_t)stream>>>(
             bb, n, m, unknown + (size_t)b0 * n * 3, known + (size_t)b0 * m * 3,
             dist2 + (size_t)b0 * n * 3, idx + (size_t)b0 * n * 3);
@@ -377,6 +383,7 @@ int mssvt_group_points(int b, int c, int n, int npoints, int nsample, const floa
     long long total = (long long)b * c * npoints * nsample;
     if (total == 0) return MSSVT_OK;
     if (!points || !idx || !out) return MSSVT_ERR_INVALID;
+    ++g_launches;
     k_group_points<<<persistent_grid(total, 256, 8), 256, 0, (cudaStream_t)stream>>>(
         b, c, n, npoints, nsample, points, idx, out);
     return check_launch();
@@ -394,6 +401,7 @@ int mssvt_group_points_grad(int b, int c, int n, int npoints, int nsample, const
     long long total = (long long)b * c * npoints * nsample;
     if (total == 0) return MSSVT_OK;
     if (!grad_out || !idx) return MSSVT_ERR_INVALID;
+    ++g_launches;
     k_group_points_grad<<<persistent_grid(total, 256, 8), 256, 0, s>>>(b, c, n, npoints, nsample,
                                                                       grad_out, idx, grad_points);
     return check_launch();

@@ -207,3 +207,9 @@ def test_gather_and_group_points_bit_exact():
     if HAVE_REF:
         assert torch.equal(ref.group_points(cuda(feats), cuda(idx3)).cpu(), want)
         assert torch.equal(ref.gather_operation(cuda(feats), cuda(idx)).cpu(), oops.gather_operation(feats, idx))
+
+
+def test_reference_kernels_were_present_on_this_box():
+    """oracle/_ref (the reference's own kernels, built unmodified in the build container) must
+    travel to the GPU box; without it the cross-checks above silently reduce to oracle-only."""
+    assert HAVE_REF, "oracle/_ref/libmssvt_ref.so missing: run `make -C oracle ref` where /root/reference exists"
