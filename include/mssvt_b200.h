@@ -134,6 +134,16 @@ int mssvt_group_points_grad(int b, int c, int n, int npoints, int nsample, const
 
 /* ---- fused entry points used by the backbone module ------------------------------------------ */
 
+/* Voxel lookup structure of the fused path (replaces the hash table there; the op-level API above
+ * keeps the reference's table): an occupancy bitmap with rank.  cells: (B * X * Y * ceil(Z/32), 2)
+ * int32 {bits, base}; vals: (N) per-sample voxel index at base + popcount(bits below z).  A lookup
+ * is one 8-byte load, plus one 4-byte load on a hit; no probing, no dependence on a hash size.
+ * workspace: ceil(mssvt_grid_index_words / 1024) + 1 int32. */
+long long mssvt_grid_index_words(int x_max, int y_max, int z_max, int batch_size);
+int mssvt_grid_index_build(int x_max, int y_max, int z_max, int num_voxels, int batch_size,
+                           const int *v_indices, const int *v_start, int *cells, int *vals,
+                           int *workspace, void *stream);
+
 /* Coordinate-only part of MixedScaleSparseTransformerBlock.forward (mssvt_backbone.py:213-258,
  * 264-269, 300-307) in one kernel, one warp per window, with no host synchronisation: the
  * number of windows is read from device memory (win_count_total) and bounds the work.
@@ -149,22 +159,23 @@ int mssvt_group_points_grad(int b, int c, int n, int npoints, int nsample, const
  *   fps_idx_tap (cap, 2K), counts_tap (cap, 4): optional raw FPS picks / list lengths (NULL ok)
  * voxel_size, range_min: 3 HOST floats each. */
 int mssvt_block_geometry(int x_max, int y_max, int z_max, int x_ws, int y_ws, int z_ws,
-                         int hash_size, int num_odd, int num_even, int num_win1, int num_win2,
+                         int num_odd, int num_even, int num_win1, int num_win2,
                          int max_win1, int max_win2, int key_num_sample, int cbs_pattern,
                          int use_interp, const float *voxel_size, const float *range_min,
                          const int *q_odd, const int *q_even, const int *q_win1, const int *q_win2,
                          int win_capacity, const int *win_count_total, const int *win_list,
-                         const int *table, const int *v_start, int num_voxels, int *q_row,
+                         const int *grid_cells, const int *grid_vals, const int *v_start,
+                         int num_voxels, int *q_row,
                          int *win1_row, int *k_row, unsigned char *k_mask, unsigned char *nn_idx,
                          float *nn_w, unsigned char *covered, int *fps_idx_tap, int *counts_tap,
                          void *stream);
 
 /* One-window gather of the compress block without host synchronisation (same table walk as
  * mssvt_gather_one_window): k_row (cap, max_win1) global feature rows, -1 padded. */
-int mssvt_window_rows(int x_max, int y_max, int z_max, int x_ws, int y_ws, int z_ws, int hash_size,
+int mssvt_window_rows(int x_max, int y_max, int z_max, int x_ws, int y_ws, int z_ws,
                       int num_win1, int max_win1, const int *q_win1, int win_capacity,
-                      const int *win_count_total, const int *win_list, const int *table,
-                      const int *v_start, int *k_row, void *stream);
+                      const int *win_count_total, const int *win_list, const int *grid_cells,
+                      const int *grid_vals, const int *v_start, int *k_row, void *stream);
 
 /* nn.LayerNorm(C) over rows (mssvt_backbone.py:210, 352); num_rows_dev (may be NULL) bounds the
  * row count from device memory. */

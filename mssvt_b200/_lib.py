@@ -34,8 +34,10 @@ _SIGNATURES = {
     "mssvt_three_nn": [I, I, I, P, P, P, P, P],
     "mssvt_group_points": [I, I, I, I, I, P, P, P, P],
     "mssvt_group_points_grad": [I, I, I, I, I, P, P, P, P],
-    "mssvt_block_geometry": [I] * 16 + [P] * 6 + [I, P, P, P, P, I] + [P] * 9 + [P],
-    "mssvt_window_rows": [I] * 9 + [P, I, P, P, P, P, P, P],
+    "mssvt_grid_index_words": [I, I, I, I],
+    "mssvt_grid_index_build": [I, I, I, I, I, P, P, P, P, P, P],
+    "mssvt_block_geometry": [I] * 15 + [P] * 6 + [I, P, P, P, P, P, I] + [P] * 9 + [P],
+    "mssvt_window_rows": [I] * 8 + [P, I, P, P, P, P, P, P, P],
     "mssvt_layernorm": [I, P, I, P, P, P, F, P, P],
     "mssvt_block_attention": [P, I, P, I] + [P] * 11 + [P],
     "mssvt_compress_attention": [P, I, P, I] + [P] * 6 + [P],
@@ -47,9 +49,9 @@ _SIGNATURES = {
     "mssvt_version": [],
     "mssvt_launch_count": [],
 }
-_RESTYPES = {"mssvt_window_partition_workspace_bytes": L, "mssvt_version": ctypes.c_char_p,
+_RESTYPES = {"mssvt_window_partition_workspace_bytes": L, "mssvt_grid_index_words": L, "mssvt_version": ctypes.c_char_p,
              "mssvt_launch_count": L}
-_NO_STATUS = {"mssvt_window_partition_workspace_bytes", "mssvt_fps_log2_block", "mssvt_version",
+_NO_STATUS = {"mssvt_window_partition_workspace_bytes", "mssvt_grid_index_words", "mssvt_fps_log2_block", "mssvt_version",
               "mssvt_sizeof_attn_shape", "mssvt_sizeof_ffn_shape", "mssvt_last_cuda_error",
               "mssvt_launch_count"}
 _ERRORS = {-1: "invalid argument", -2: "CUDA launch/runtime error", -3: "workspace too small"}

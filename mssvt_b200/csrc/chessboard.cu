@@ -45,15 +45,15 @@ __device__ __forceinline__ int off_z(int p) { return (int)(signed char)((p >> 16
 // Probe every offset for one window; lists land in shared memory in table order.
 // s_tab: total x 3 ints (concatenated tables); s_ind/s_off: per-warp list storage, list L at
 // list_at[L].  Returns the (capped) list lengths in cnt[].
+template <typename IDX>
 __device__ __forceinline__ void probe_window(const GatherShape &g, int4 win, const int *s_tab,
-                                             const int2 *__restrict__ table, int *s_ind, int *s_off,
+                                             const IDX &index, int *s_ind, int *s_off,
                                              const int list_at[4], int cnt[4], int &cx, int &cy,
                                              int &cz) {
     const int lane = threadIdx.x & 31;
     cz = win.y * g.z_ws + g.z_ws / 2;
     cy = win.z * g.y_ws + g.y_ws / 2;
     cx = win.w * g.x_ws + g.x_ws / 2;
-    const int2 *tab = table + (size_t)win.x * g.hash_size;
     const int e0 = g.seg[0], e1 = e0 + g.seg[1], e2 = e1 + g.seg[2], total = e2 + g.seg[3];
     cnt[0] = cnt[1] = cnt[2] = cnt[3] = 0;
     for (int base = 0; base < total; base += 32) {
@@ -64,7 +64,7 @@ __device__ __forceinline__ void probe_window(const GatherShape &g, int4 win, con
             int ox = s_tab[3 * q], oy = s_tab[3 * q + 1], oz = s_tab[3 * q + 2];
             int sx = cx + ox, sy = cy + oy, sz = cz + oz;
             if (!(sx >= g.x_max || sx < 0 || sy >= g.y_max || sy < 0 || sz >= g.z_max || sz < 0)) {
-                v = table_find(tab, g.hash_size, sx * g.y_max * g.z_max + sy * g.z_max + sz);
+                v = index.find(win.x, sx, sy, sz);
                 packed = pack_off(ox, oy, oz);
                 member = list_membership(q < e0 ? 0 : q < e1 ? 1 : q < e2 ? 2 : 3);
             }
@@ -119,9 +119,10 @@ k_gather_lists(GatherShape g, TablePtrs tabs, int num_wins, const int4 *__restri
     load_tables(g, tabs.p, s_tab);
     __syncthreads();
     int list_at[4] = {0, g.cap[0], g.cap[0] + g.cap[1], g.cap[0] + g.cap[1] + g.cap[2]};
+    const HashIdx index = {table, g.hash_size, g.y_max, g.z_max};
     for (int w = blockIdx.x * GEO_WARPS + warp; w < num_wins; w += gridDim.x * GEO_WARPS) {
         int cnt[4], cx, cy, cz;
-        probe_window(g, __ldg(win_list + w), s_tab, table, s_ind, s_off, list_at, cnt, cx, cy, cz);
+        probe_window(g, __ldg(win_list + w), s_tab, index, s_ind, s_off, list_at, cnt, cx, cy, cz);
 #pragma unroll
         for (int L = 0; L < 4; ++L) {
             const int cap = g.cap[L];
@@ -202,7 +203,7 @@ __device__ __forceinline__ void fps_list(const int *s_off, int cnt, int n, int l
 
 __global__ void __launch_bounds__(GEO_WARPS * 32)
 k_block_geometry(GeoParams P, TablePtrs tabs, const int *__restrict__ win_count_total,
-                 const int4 *__restrict__ win_list, const int2 *__restrict__ table,
+                 const int4 *__restrict__ win_list, GridIdx index,
                  const int *__restrict__ v_start, GeoOut out) {
     extern __shared__ int smem[];
     const GatherShape &g = P.g;
@@ -229,7 +230,7 @@ k_block_geometry(GeoParams P, TablePtrs tabs, const int *__restrict__ win_count_
     for (int w = blockIdx.x * GEO_WARPS + warp; w < num_wins; w += gridDim.x * GEO_WARPS) {
         int cnt[4], cx, cy, cz;
         const int4 win = __ldg(win_list + w);
-        probe_window(g, win, s_tab, table, s_ind, s_off, list_at, cnt, cx, cy, cz);
+        probe_window(g, win, s_tab, index, s_ind, s_off, list_at, cnt, cx, cy, cz);
         const int row0 = __ldg(v_start + win.x);
         if (out.counts && lane < 4)
             out.counts[4 * w + lane] = lane == 0 ? cnt[0] : lane == 1 ? cnt[1] : lane == 2 ? cnt[2] : cnt[3];
@@ -315,7 +316,7 @@ k_block_geometry(GeoParams P, TablePtrs tabs, const int *__restrict__ win_count_
 // one-window gather for the compress block, sync-free: global rows only, -1 padded
 __global__ void __launch_bounds__(GEO_WARPS * 32)
 k_window_rows(GatherShape g, TablePtrs tabs, const int *__restrict__ win_count_total,
-              const int4 *__restrict__ win_list, const int2 *__restrict__ table,
+              const int4 *__restrict__ win_list, GridIdx index,
               const int *__restrict__ v_start, int *__restrict__ k_row) {
     extern __shared__ int smem[];
     const int total = g.seg[2], cap = g.cap[2];
@@ -330,7 +331,7 @@ k_window_rows(GatherShape g, TablePtrs tabs, const int *__restrict__ win_count_t
     for (int w = blockIdx.x * GEO_WARPS + warp; w < num_wins; w += gridDim.x * GEO_WARPS) {
         int cnt[4], cx, cy, cz;
         const int4 win = __ldg(win_list + w);
-        probe_window(g, win, s_tab, table, s_ind, s_off, list_at, cnt, cx, cy, cz);
+        probe_window(g, win, s_tab, index, s_ind, s_off, list_at, cnt, cx, cy, cz);
         const int row0 = __ldg(v_start + win.x);
         for (int i = lane; i < cap; i += 32) k_row[(size_t)w * cap + i] = i < cnt[2] ? row0 + s_ind[i] : -1;
         __syncwarp();
@@ -409,22 +410,24 @@ int mssvt_gather_one_window(int x_max, int y_max, int z_max, int x_ws, int y_ws,
 // Fused per-window geometry of a two-window block.  All sizes that depend on the data stay on
 // the device (win_count_total), so there is no host synchronisation.
 int mssvt_block_geometry(int x_max, int y_max, int z_max, int x_ws, int y_ws, int z_ws,
-                         int hash_size, int num_odd, int num_even, int num_win1, int num_win2,
+                         int num_odd, int num_even, int num_win1, int num_win2,
                          int max_win1, int max_win2, int key_num_sample, int cbs_pattern,
                          int use_interp, const float *voxel_size, const float *range_min,
                          const int *q_odd, const int *q_even, const int *q_win1, const int *q_win2,
                          int win_capacity, const int *win_count_total, const int *win_list,
-                         const int *table, const int *v_start, int num_voxels, int *q_row,
+                         const int *grid_cells, const int *grid_vals, const int *v_start,
+                         int num_voxels, int *q_row,
                          int *win1_row, int *k_row, unsigned char *k_mask, unsigned char *nn_idx,
                          float *nn_w, unsigned char *covered, int *fps_idx_tap, int *counts_tap,
                          void *stream) {
     GeoParams P;
-    P.g = {x_max, y_max, z_max, x_ws, y_ws, z_ws, hash_size,
+    P.g = {x_max, y_max, z_max, x_ws, y_ws, z_ws, 1,
            {num_odd, num_even, num_win1, num_win2}, {num_odd, num_even, max_win1, max_win2}};
     if (!shape_ok(P.g) || key_num_sample <= 0 || key_num_sample > 256 || cbs_pattern < 0 ||
         cbs_pattern > 2 || max_win1 <= 0 || max_win2 <= 0 || win_capacity < 0)
         return MSSVT_ERR_INVALID;
-    if (!voxel_size || !range_min || !win_count_total || !win_list || !table || !v_start || !q_row ||
+    if (!voxel_size || !range_min || !win_count_total || !win_list || !grid_cells || !grid_vals ||
+        !v_start || !q_row ||
         !win1_row || !k_row || !k_mask || !covered)
         return MSSVT_ERR_INVALID;
     if (use_interp && (!nn_idx || !nn_w)) return MSSVT_ERR_INVALID;
@@ -456,32 +459,36 @@ int mssvt_block_geometry(int x_max, int y_max, int z_max, int x_ws, int y_ws, in
     cudaFuncSetAttribute(k_block_geometry, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int grid = persistent_grid(win_capacity, GEO_WARPS, 6);
     ++g_launches;
+    const int zw = (z_max + 31) / 32;
+    GridIdx index = {(const int2 *)grid_cells, grid_vals, y_max, zw, (long long)x_max * y_max * zw};
     k_block_geometry<<<grid, GEO_WARPS * 32, smem, s>>>(P, tabs, win_count_total,
-                                                       (const int4 *)win_list, (const int2 *)table,
-                                                       v_start, out);
+                                                       (const int4 *)win_list, index, v_start, out);
     (void)ext;
     return check_launch();
 }
 
 /* One-window gather of the compress block without host synchronisation: k_row (cap, max_win1)
  * global feature rows in table order, -1 padded. */
-int mssvt_window_rows(int x_max, int y_max, int z_max, int x_ws, int y_ws, int z_ws, int hash_size,
+int mssvt_window_rows(int x_max, int y_max, int z_max, int x_ws, int y_ws, int z_ws,
                       int num_win1, int max_win1, const int *q_win1, int win_capacity,
-                      const int *win_count_total, const int *win_list, const int *table,
-                      const int *v_start, int *k_row, void *stream) {
-    GatherShape g = {x_max, y_max, z_max, x_ws, y_ws, z_ws, hash_size, {0, 0, num_win1, 0},
+                      const int *win_count_total, const int *win_list, const int *grid_cells,
+                      const int *grid_vals, const int *v_start, int *k_row, void *stream) {
+    GatherShape g = {x_max, y_max, z_max, x_ws, y_ws, z_ws, 1, {0, 0, num_win1, 0},
                      {0, 0, max_win1, 0}};
     if (!shape_ok(g) || max_win1 <= 0 || win_capacity < 0) return MSSVT_ERR_INVALID;
     if (win_capacity == 0) return MSSVT_OK;
-    if (!q_win1 || !win_count_total || !win_list || !table || !v_start || !k_row) return MSSVT_ERR_INVALID;
+    if (!q_win1 || !win_count_total || !win_list || !grid_cells || !grid_vals || !v_start || !k_row)
+        return MSSVT_ERR_INVALID;
     TablePtrs tabs = {{nullptr, nullptr, q_win1, nullptr}};
     size_t smem = (size_t)(num_win1 * 3 + GEO_WARPS * max_win1 * 2) * sizeof(int);
     if (smem > 200 * 1024) return MSSVT_ERR_INVALID;
     cudaFuncSetAttribute(k_window_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int zw = (z_max + 31) / 32;
+    GridIdx index = {(const int2 *)grid_cells, grid_vals, y_max, zw, (long long)x_max * y_max * zw};
     ++g_launches;
     k_window_rows<<<persistent_grid(win_capacity, GEO_WARPS, 8), GEO_WARPS * 32, smem,
                     (cudaStream_t)stream>>>(g, tabs, win_count_total, (const int4 *)win_list,
-                                            (const int2 *)table, v_start, k_row);
+                                            index, v_start, k_row);
     return check_launch();
 }
 

@@ -49,6 +49,35 @@ __device__ __forceinline__ int table_find(const int2 *__restrict__ tab, int hash
     return MSSVT_EMPTY;
 }
 
+// ---- voxel lookup structures.  Both expose find(b, x, y, z) -> per-sample voxel index or -1.
+//
+// HashIdx: the reference's table (drop-in contract of the op-level API).
+struct HashIdx {
+    const int2 *table;
+    int hash_size, y_max, z_max;
+    __device__ __forceinline__ int find(int b, int x, int y, int z) const {
+        return table_find(table + (size_t)b * hash_size, hash_size, x * y_max * z_max + y * z_max + z);
+    }
+};
+
+// GridIdx: occupancy bitmap + rank, used by the fused path.  One int2 {bits, base} per 32 cells
+// of a z column; a hit costs one more load from `vals` at base + popcount(bits below z).  At most
+// two dependent loads, no probing loop, no clustering, and the 125 probes of a window touch only
+// 25 neighbouring words (the z neighbours of an offset share a word).  For the S0 grid the
+// structure is 1.75 MB + 4 N bytes: it lives in L2.
+struct GridIdx {
+    const int2 *cells;  // (B, x_max * y_max * zw)
+    const int *vals;    // (N) per-sample voxel index, grouped by word, ordered by z inside a word
+    int y_max, zw;      // zw = words per column = ceil(z_max / 32)
+    long long words_per_sample;
+    __device__ __forceinline__ int find(int b, int x, int y, int z) const {
+        int2 c = __ldg(cells + (size_t)b * words_per_sample + ((size_t)x * y_max + y) * zw + (z >> 5));
+        unsigned bit = 1u << (z & 31);
+        if (!((unsigned)c.x & bit)) return MSSVT_EMPTY;
+        return __ldg(vals + c.y + __popc((unsigned)c.x & (bit - 1u)));
+    }
+};
+
 __device__ __forceinline__ unsigned lanemask_lt() {
     unsigned m;
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));

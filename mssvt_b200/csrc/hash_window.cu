@@ -65,7 +65,10 @@ __global__ void k_hash_insert(int x_max, int y_max, int z_max, int num_voxels, i
     unsigned long long packed = (unsigned long long)(unsigned)key | ((unsigned long long)(unsigned)local << 32);
     int slot = (int)((unsigned)key % (unsigned)hash_size);
     for (int probes = 0; probes < hash_size; ++probes) {
-        unsigned long long prev = atomicCAS(tab + slot, ~0ull, packed);
+        // walk occupied slots with plain loads (keys never change once written); only an empty
+        // slot costs an atomic.  `k % H` clusters badly on voxel keys, so chains can be long.
+        unsigned long long prev = *((volatile unsigned long long *)(tab + slot));
+        if (prev == ~0ull) prev = atomicCAS(tab + slot, ~0ull, packed);
         if (prev == ~0ull) return;
         if ((int)(unsigned)(prev & 0xffffffffull) == key) {
             // duplicate coordinate: the reference lets the last writer win; sequential order
@@ -117,6 +120,85 @@ __global__ void k_prefix_small(int batch_size, const int *__restrict__ counts, i
         for (int b = 0; b < batch_size; ++b) { start[b] = s; s += counts[b]; }
         start[batch_size] = s;
     }
+}
+
+// ------------------------------------------------------------------------------- grid index
+// Occupancy bitmap + rank (GridIdx in common.cuh), built in four small passes:
+//   bits:  atomicOr one bit per voxel            scan: per-1024-word block popcount sums
+//   base:  exclusive prefix of the popcounts     vals: vals[base + rank] = per-sample voxel index
+
+__global__ void k_grid_bits(int x_max, int y_max, int z_max, int zw, long long words_per_sample,
+                            int num_voxels, const int4 *__restrict__ v_indices, int2 *__restrict__ cells) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= num_voxels) return;
+    int4 c = __ldg(v_indices + t);
+    int z = c.y, y = c.z, x = c.w;
+    if (x >= x_max || x < 0 || y < 0 || y >= y_max || z < 0 || z >= z_max) return;
+    atomicOr(&cells[(size_t)c.x * words_per_sample + ((size_t)x * y_max + y) * zw + (z >> 5)].x, 1 << (z & 31));
+}
+
+#define GRID_BLOCK 1024
+__global__ void __launch_bounds__(GRID_BLOCK)
+k_grid_block_sums(long long total_words, const int2 *__restrict__ cells, int *__restrict__ block_sums) {
+    __shared__ int s_warp[GRID_BLOCK / 32];
+    long long i = (long long)blockIdx.x * GRID_BLOCK + threadIdx.x;
+    int c = i < total_words ? __popc((unsigned)cells[i].x) : 0;
+    c = __reduce_add_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        int v = s_warp[threadIdx.x];
+        v = __reduce_add_sync(0xffffffffu, v);
+        if (threadIdx.x == 0) block_sums[blockIdx.x] = v;
+    }
+}
+
+__global__ void __launch_bounds__(GRID_BLOCK)
+k_grid_base(long long total_words, int2 *__restrict__ cells, const int *__restrict__ block_sums) {
+    __shared__ int s_warp[GRID_BLOCK / 32];
+    __shared__ int s_base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int part = 0;
+    for (int i = threadIdx.x; i < (int)blockIdx.x; i += GRID_BLOCK) part += block_sums[i];
+    part = __reduce_add_sync(0xffffffffu, part);
+    if (lane == 0) s_warp[warp] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int s = 0;
+        for (int i = 0; i < GRID_BLOCK / 32; ++i) s += s_warp[i];
+        s_base = s;
+    }
+    __syncthreads();
+    const int base = s_base;
+    __syncthreads();
+    long long i = (long long)blockIdx.x * GRID_BLOCK + threadIdx.x;
+    int c = i < total_words ? __popc((unsigned)cells[i].x) : 0;
+    // inclusive warp scan, then add the sums of the warps before
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int n = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += n;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    int before = 0;
+    for (int w = 0; w < warp; ++w) before += s_warp[w];
+    if (i < total_words) cells[i].y = base + before + incl - c;
+}
+
+__global__ void k_grid_vals(int x_max, int y_max, int z_max, int zw, long long words_per_sample,
+                            int num_voxels, const int4 *__restrict__ v_indices,
+                            const int *__restrict__ v_start, const int2 *__restrict__ cells,
+                            int *__restrict__ vals) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= num_voxels) return;
+    int4 c = __ldg(v_indices + t);
+    int z = c.y, y = c.z, x = c.w;
+    if (x >= x_max || x < 0 || y < 0 || y >= y_max || z < 0 || z >= z_max) return;
+    int2 cell = cells[(size_t)c.x * words_per_sample + ((size_t)x * y_max + y) * zw + (z >> 5)];
+    unsigned bit = 1u << (z & 31);
+    vals[cell.y + __popc((unsigned)cell.x & (bit - 1u))] = t - __ldg(v_start + c.x);
 }
 
 // ------------------------------------------------------------------------------- window partition
@@ -297,6 +379,39 @@ int mssvt_count_samples(int num_rows, int batch_size, const int *indices, int *c
     }
     ++g_launches;
     k_prefix_small<<<1, 32, 0, s>>>(batch_size, counts, start);
+    return check_launch();
+}
+
+/* Grid index of the fused path (GridIdx): cells (B * x*y*ceil(z/32), 2) int32, vals (N) int32.
+ * workspace: ceil(words / 1024) + 1 ints. */
+long long mssvt_grid_index_words(int x_max, int y_max, int z_max, int batch_size) {
+    return (long long)batch_size * x_max * y_max * ((z_max + 31) / 32);
+}
+
+int mssvt_grid_index_build(int x_max, int y_max, int z_max, int num_voxels, int batch_size,
+                           const int *v_indices, const int *v_start, int *cells, int *vals,
+                           int *workspace, void *stream) {
+    if (x_max <= 0 || y_max <= 0 || z_max <= 0 || batch_size <= 0 || num_voxels < 0 || !cells)
+        return MSSVT_ERR_INVALID;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int zw = (z_max + 31) / 32;
+    const long long wps = (long long)x_max * y_max * zw, total = wps * batch_size;
+    cudaError_t e = cudaMemsetAsync(cells, 0, (size_t)total * 8, s);
+    if (e != cudaSuccess) { g_last_cuda_error = (int)e; return MSSVT_ERR_LAUNCH; }
+    if (num_voxels == 0) return MSSVT_OK;
+    if (!v_indices || !v_start || !vals || !workspace) return MSSVT_ERR_INVALID;
+    const int blocks = div_up(total, GRID_BLOCK);
+    ++g_launches;
+    k_grid_bits<<<div_up(num_voxels, 256), 256, 0, s>>>(x_max, y_max, z_max, zw, wps, num_voxels,
+                                                        (const int4 *)v_indices, (int2 *)cells);
+    ++g_launches;
+    k_grid_block_sums<<<blocks, GRID_BLOCK, 0, s>>>(total, (const int2 *)cells, workspace);
+    ++g_launches;
+    k_grid_base<<<blocks, GRID_BLOCK, 0, s>>>(total, (int2 *)cells, workspace);
+    ++g_launches;
+    k_grid_vals<<<div_up(num_voxels, 256), 256, 0, s>>>(x_max, y_max, z_max, zw, wps, num_voxels,
+                                                        (const int4 *)v_indices, v_start,
+                                                        (const int2 *)cells, vals);
     return check_launch();
 }
 

@@ -239,12 +239,13 @@ class MixedScaleSparseTransformerBlock(nn.Module):
             "counts": torch.empty((cap, 4), **i32) if taps else None,
         }
         sx, sy, sz = (int(v) for v in sp_tensor.spatial_shape)
-        call("mssvt_block_geometry", sx, sy, sz, *self.win1_size, sp_tensor.hash_size,
+        cells, vals = sp_tensor.grid_index()
+        call("mssvt_block_geometry", sx, sy, sz, *self.win1_size,
              t['odd'].shape[0], t['even'].shape[0], t['win1'].shape[0], t['win2'].shape[0],
              self.max_num_win1, self.max_num_win2, K, self.cbs_pattern,
              int(bool(self.use_feature_interpolation)), host_floats(sp_tensor.voxel_size),
              host_floats(sp_tensor.point_cloud_range[0:3]), ptr(t['odd']), ptr(t['even']), ptr(t['win1']),
-             ptr(t['win2']), cap, ptr(g["total"]), ptr(win_list), ptr(sp_tensor.map_table), ptr(v_start),
+             ptr(t['win2']), cap, ptr(g["total"]), ptr(win_list), ptr(cells), ptr(vals), ptr(v_start),
              N, ptr(g["q_row"]), ptr(g["win1_row"]), ptr(g["k_row"]), ptr(g["k_mask"]), ptr(g["nn_idx"]),
              ptr(g["nn_w"]), ptr(g["covered"]), ptr(g["fps_idx"]), ptr(g["counts"]), stream())
         cache[key] = g
@@ -349,8 +350,9 @@ class MixedScaleSparseTransformerCompressBlock(MixedScaleSparseTransformerBlock)
         total = win_count[B:B + 1]
         k_row = torch.empty((cap, n1), dtype=torch.int32, device=dev)
         sx, sy, sz = (int(v) for v in sp_tensor.spatial_shape)
-        call("mssvt_window_rows", sx, sy, sz, *self.win1_size, sp_tensor.hash_size, t['win1'].shape[0],
-             n1, ptr(t['win1']), cap, ptr(total), ptr(win_list), ptr(sp_tensor.map_table), ptr(v_start),
+        cells, vals = sp_tensor.grid_index()
+        call("mssvt_window_rows", sx, sy, sz, *self.win1_size, t['win1'].shape[0],
+             n1, ptr(t['win1']), cap, ptr(total), ptr(win_list), ptr(cells), ptr(vals), ptr(v_start),
              ptr(k_row), stream())
         xn = self._layernorm1(x)
         S, buf = self._attn_descriptor(sp_tensor, 1, n1, n1)

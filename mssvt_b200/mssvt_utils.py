@@ -38,7 +38,24 @@ class SparseTensor(object):
         self.hash_size = hash_size
         self.gather_dict = gather_dict
         self._derived = {}                  # per-coordinate-set caches (counts, world xyz, geometry)
-        self.map_table = self.build_map_table() if map_table is None else map_table
+        self._map_table = map_table         # reference-contract hash table, built on first use
+
+    @property
+    def map_table(self):
+        """(B, hash_size, 2) table of the reference (mssvt_utils.py:31).  The fused blocks look
+        voxels up through grid_index() instead, so the table is only built when somebody asks
+        for it (e.g. to call mssvt_ops.gather_two_window_voxels)."""
+        if self._map_table is None:
+            self._map_table = self.build_map_table()
+        return self._map_table
+
+    @map_table.setter
+    def map_table(self, value):
+        self._map_table = value
+
+    @map_table.deleter
+    def map_table(self):
+        self._map_table = None
 
     # ---- coordinate-derived state, recomputed only when `indices` is replaced
     def _cache(self):
@@ -62,6 +79,22 @@ class SparseTensor(object):
                  host_floats(self.voxel_size), host_floats(self.point_cloud_range[0:3]), ptr(xyz), stream())
             c["xyz"] = xyz
         return c["xyz"]
+
+    def grid_index(self):
+        """(cells, vals): occupancy-bitmap + rank lookup structure of the fused path."""
+        c = self._cache()
+        if "grid" not in c:
+            x, y, z = (int(v) for v in self.spatial_shape)
+            dev = self.indices.device
+            words = call("mssvt_grid_index_words", x, y, z, self.batch_size)
+            cells = torch.empty((words, 2), dtype=torch.int32, device=dev)
+            vals = torch.empty(max(self.indices.shape[0], 1), dtype=torch.int32, device=dev)
+            work = torch.empty((words + 1023) // 1024 + 1, dtype=torch.int32, device=dev)
+            _, start = self.sample_counts()
+            call("mssvt_grid_index_build", x, y, z, self.indices.shape[0], self.batch_size,
+                 ptr(self.indices), ptr(start), ptr(cells), ptr(vals), ptr(work), stream())
+            c["grid"] = (cells, vals)
+        return c["grid"]
 
     @torch.no_grad()
     def build_map_table(self):
