@@ -42,6 +42,7 @@ _SIGNATURES = {
     "mssvt_block_attention": [P, I, P, I] + [P] * 11 + [P],
     "mssvt_compress_attention": [P, I, P, I] + [P] * 6 + [P],
     "mssvt_ffn": [P, I, P, I, P, P, P, P, P, P],
+    "mssvt_ffn_tc": [I, I, I, F] + [P] * 6 + [I, P, P, P, P, P, P],
     "mssvt_dense_scatter": [I, P, I, I, I, I, I, P, P, P, P],
     "mssvt_sizeof_attn_shape": [],
     "mssvt_sizeof_ffn_shape": [],

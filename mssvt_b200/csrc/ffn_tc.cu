@@ -1,0 +1,337 @@
+// ffn_tc.cu -- the block FFN on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a.
+//
+//   y = u + W2 relu(W1 LN(u) + b1) + b2         mssvt_backbone.py:337-340, 384-385
+//   u = covered ? merged + x : 2 x  (two-window block)   |   u = merged  (compress block)
+//
+// One CTA of 128 threads owns a tile of 128 rows; thread t = row t = TMEM lane t.
+//   1. each thread loads its row, builds u, LayerNorms it in registers and stores it, rounded to
+//      TF32, as the A operand in the canonical K-major no-swizzle UMMA layout
+//      (8-row x 16-byte core matrices: byte = chunk * LBO + (row / 8) * 128 + (row % 8) * 16);
+//   2. one thread issues C/8 tcgen05.mma.kind::tf32 (M = 128, N = F) -> D1 in TMEM columns [0, F);
+//   3. tcgen05.ld brings each row's D1 back, bias + ReLU, TF32 round, store as the A operand of the
+//      second GEMM (same layout, K = F);
+//   4. F/8 tcgen05.mma (M = 128, N = C) -> D2 in TMEM columns [F, F + C);
+//   5. tcgen05.ld, + b2 + u (still in registers), row store.
+// W1 / W2 (nn.Linear [out][in] = N x K, K-major) sit in shared memory in the same canonical
+// layout for the whole kernel.  Completion of the async MMAs is tracked with tcgen05.commit on
+// an mbarrier; generic-proxy shared stores are made visible with fence.proxy.async.
+//
+// Precision: TF32 operands (10-bit mantissa, round-to-nearest), fp32 accumulation in TMEM; the
+// residual stream u and the LayerNorm stay fp32.  Selected with precision = "tf32"; the exact
+// FFMA kernel in block.cu stays the default (tests state the tolerance for each).
+#include "block_common.cuh"
+
+namespace mssvt {
+
+#define TC_ROWS 128
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+// K-major, no swizzle.  LBO = byte stride between the two 16-byte K chunks of one MMA,
+// SBO = byte stride between 8-row core-matrix groups (cute/arch/mma_sm100_desc.hpp semantics).
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;  // descriptor version for sm_100
+    return d;                // base_offset 0, layout_type 0 (SWIZZLE_NONE)
+}
+
+// kind::tf32, fp32 accumulate, both operands K-major
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__device__ __forceinline__ void umma_commit(uint32_t mbar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar)
+                 : "memory");
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+
+// bounded wait: a mis-programmed MMA must not hang the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+    for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}\n"
+            : "=r"(done)
+            : "r"(mbar), "r"(parity)
+            : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+
+__device__ __forceinline__ float to_tf32(float v) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return __uint_as_float(r);
+}
+
+// 32 consecutive TMEM columns of this thread's lane
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// copy a row-major [n_rows][k] fp32 matrix (global) into the canonical K-major layout, TF32-rounded
+__device__ __forceinline__ void stage_operand(const float *__restrict__ src, int n_rows, int k, char *dst) {
+    const int chunks = k >> 2;
+    const uint32_t lbo = (uint32_t)n_rows * 16u;
+    for (int e = threadIdx.x; e < n_rows * chunks; e += blockDim.x) {
+        const int n = e / chunks, c = e - n * chunks;
+        float4 v = __ldg((const float4 *)(src + (size_t)n * k) + c);
+        v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w);
+        *(float4 *)(dst + (size_t)c * lbo + (n >> 3) * 128 + (n & 7) * 16) = v;
+    }
+}
+
+struct FfnTcParams {
+    int F, mode;            // hidden width; 0: u = merged, 1: u = covered ? merged + x : 2 x
+    float eps;
+    const float *w1, *b1;   // [F][C], [F]   (nn.Linear layout)
+    const float *w2, *b2;   // [C][F], [C]
+    const float *ln_g, *ln_b;
+};
+
+template <int C>
+__global__ void __launch_bounds__(TC_ROWS, 1)
+k_ffn_tc(FfnTcParams P, int n_cap, const int *__restrict__ n_dev, const float *__restrict__ x,
+         const float *__restrict__ merged, const unsigned char *__restrict__ covered,
+         float *__restrict__ y) {
+    extern __shared__ __align__(128) char smem_raw[];
+    const int F = P.F;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    // carve shared memory
+    char *sA = smem_raw;                          // [C/4][128][16 B]
+    char *sW1 = sA + TC_ROWS * C * 4;             // [C/4][F][16 B]
+    char *sW2 = sW1 + F * C * 4;                  // [F/4][C][16 B]
+    char *sH = sW2 + C * F * 4;                   // [F/4][128][16 B]
+    float *s_vec = (float *)(sH + TC_ROWS * F * 4);  // ln_g[C], ln_b[C], b1[F], b2[C]
+    uint64_t *s_bar = (uint64_t *)(s_vec + 3 * C + F);  // 2 mbarriers (8-byte aligned: C, F even)
+    uint32_t *s_tmem = (uint32_t *)(s_bar + 2);
+
+    stage_operand(P.w1, F, C, sW1);
+    stage_operand(P.w2, C, F, sW2);
+    for (int i = tid; i < C; i += TC_ROWS) {
+        s_vec[i] = __ldg(P.ln_g + i);
+        s_vec[C + i] = __ldg(P.ln_b + i);
+        s_vec[2 * C + F + i] = __ldg(P.b2 + i);
+    }
+    for (int i = tid; i < F; i += TC_ROWS) s_vec[2 * C + i] = __ldg(P.b1 + i);
+    const float *s_g = s_vec, *s_b = s_vec + C, *s_b1 = s_vec + 2 * C, *s_b2 = s_vec + 2 * C + F;
+
+    const uint32_t bar1 = smem_u32(s_bar), bar2 = smem_u32(s_bar + 1);
+    if (tid == 0) {
+        mbar_init(bar1, 1);
+        mbar_init(bar2, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // TMEM: F columns for D1 + C columns for D2, rounded up to a power of two >= 32
+    uint32_t tmem_cols = 32;
+    while (tmem_cols < (uint32_t)(F + C)) tmem_cols <<= 1;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)),
+                     "r"(tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // staged weights -> async proxy
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *s_tmem;
+    const uint32_t tmem_d1 = tmem_base, tmem_d2 = tmem_base + (uint32_t)F;
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;  // this warp's quarter of the 128 lanes
+
+    const uint32_t idesc1 = umma_idesc_tf32(TC_ROWS, F), idesc2 = umma_idesc_tf32(TC_ROWS, C);
+    const uint32_t a_lbo = TC_ROWS * 16, w1_lbo = (uint32_t)F * 16, w2_lbo = (uint32_t)C * 16;
+    const uint32_t sA_u = smem_u32(sA), sW1_u = smem_u32(sW1), sW2_u = smem_u32(sW2), sH_u = smem_u32(sH);
+
+    const int n = n_dev ? min(n_cap, __ldg(n_dev)) : n_cap;
+    const int tiles = (n + TC_ROWS - 1) / TC_ROWS;
+    uint32_t phase = 0;
+    const uint32_t my_row_off = (uint32_t)(tid >> 3) * 128u + (uint32_t)(tid & 7) * 16u;
+
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, phase ^= 1u) {
+        const int row = tile * TC_ROWS + tid;
+        const bool live = row < n;
+        // ---- 1. residual stream u (registers), LayerNorm, A operand
+        float u[C];
+        if (live) {
+            const float4 *mp = (const float4 *)(merged + (size_t)row * C);
+            if (P.mode == 0) {
+#pragma unroll
+                for (int c = 0; c < C / 4; ++c) {
+                    float4 v = __ldg(mp + c);
+                    u[4 * c] = v.x; u[4 * c + 1] = v.y; u[4 * c + 2] = v.z; u[4 * c + 3] = v.w;
+                }
+            } else {
+                const float4 *xp = (const float4 *)(x + (size_t)row * C);
+                const bool cov = covered[row] != 0;
+#pragma unroll
+                for (int c = 0; c < C / 4; ++c) {
+                    float4 v = __ldg(xp + c);
+                    float4 m = cov ? __ldg(mp + c) : v;
+                    u[4 * c] = m.x + v.x; u[4 * c + 1] = m.y + v.y; u[4 * c + 2] = m.z + v.z; u[4 * c + 3] = m.w + v.w;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < C; ++c) u[c] = 0.f;
+        }
+        float mean = 0.f;
+#pragma unroll
+        for (int c = 0; c < C; ++c) mean += u[c];
+        mean *= (1.0f / C);
+        float var = 0.f;
+#pragma unroll
+        for (int c = 0; c < C; ++c) { const float d = u[c] - mean; var = fmaf(d, d, var); }
+        const float rstd = rsqrtf(var * (1.0f / C) + P.eps);
+#pragma unroll
+        for (int c = 0; c < C / 4; ++c) {
+            float4 v;
+            v.x = to_tf32((u[4 * c] - mean) * rstd * s_g[4 * c] + s_b[4 * c]);
+            v.y = to_tf32((u[4 * c + 1] - mean) * rstd * s_g[4 * c + 1] + s_b[4 * c + 1]);
+            v.z = to_tf32((u[4 * c + 2] - mean) * rstd * s_g[4 * c + 2] + s_b[4 * c + 2]);
+            v.w = to_tf32((u[4 * c + 3] - mean) * rstd * s_g[4 * c + 3] + s_b[4 * c + 3]);
+            *(float4 *)(sA + (uint32_t)c * a_lbo + my_row_off) = v;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        // ---- 2. D1[128 x F] = A[128 x C] . W1^T, one K = 8 slice (two 16-byte chunks) per MMA
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int k = 0; k < C / 8; ++k) {
+                const uint64_t da = umma_smem_desc(sA_u + (uint32_t)k * 2u * a_lbo, a_lbo, 128);
+                const uint64_t db = umma_smem_desc(sW1_u + (uint32_t)k * 2u * w1_lbo, w1_lbo, 128);
+                umma_tf32(tmem_d1, da, db, idesc1, k > 0 ? 1u : 0u);
+            }
+            umma_commit(bar1);
+        }
+        mbar_wait(bar1, phase);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // ---- 3. hidden = relu(D1 + b1) -> A operand of the second GEMM
+        for (int c0 = 0; c0 < F; c0 += 32) {
+            float d[32];
+            tmem_ld32(tmem_d1 + lane_off + (uint32_t)c0, d);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                float4 v;
+                v.x = to_tf32(fmaxf(d[4 * q] + s_b1[c0 + 4 * q], 0.f));
+                v.y = to_tf32(fmaxf(d[4 * q + 1] + s_b1[c0 + 4 * q + 1], 0.f));
+                v.z = to_tf32(fmaxf(d[4 * q + 2] + s_b1[c0 + 4 * q + 2], 0.f));
+                v.w = to_tf32(fmaxf(d[4 * q + 3] + s_b1[c0 + 4 * q + 3], 0.f));
+                *(float4 *)(sH + (uint32_t)(c0 / 4 + q) * a_lbo + my_row_off) = v;
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        // ---- 4. D2[128 x C] = H[128 x F] . W2^T
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            for (int k = 0; k < F / 8; ++k) {
+                const uint64_t da = umma_smem_desc(sH_u + (uint32_t)k * 2u * a_lbo, a_lbo, 128);
+                const uint64_t db = umma_smem_desc(sW2_u + (uint32_t)k * 2u * w2_lbo, w2_lbo, 128);
+                umma_tf32(tmem_d2, da, db, idesc2, k > 0 ? 1u : 0u);
+            }
+            umma_commit(bar2);
+        }
+        mbar_wait(bar2, phase);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // ---- 5. y = u + D2 + b2
+#pragma unroll
+        for (int c0 = 0; c0 < C; c0 += 32) {
+            float d[32];
+            tmem_ld32(tmem_d2 + lane_off + (uint32_t)c0, d);
+            if (live) {
+                float4 *yp = (float4 *)(y + (size_t)row * C + c0);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    float4 v;
+                    v.x = u[c0 + 4 * q] + d[4 * q] + s_b2[c0 + 4 * q];
+                    v.y = u[c0 + 4 * q + 1] + d[4 * q + 1] + s_b2[c0 + 4 * q + 1];
+                    v.z = u[c0 + 4 * q + 2] + d[4 * q + 2] + s_b2[c0 + 4 * q + 2];
+                    v.w = u[c0 + 4 * q + 3] + d[4 * q + 3] + s_b2[c0 + 4 * q + 3];
+                    yp[q] = v;
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();  // TMEM and the operand tiles are free for the next tile
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols)
+                     : "memory");
+    }
+}
+
+}  // namespace mssvt
+
+using namespace mssvt;
+
+extern "C" {
+
+// Tensor-core FFN (TF32 operands, fp32 accumulate).  Weights in nn.Linear layout: w1 [F][C],
+// w2 [C][F].  Supported: C in {32, 64}, F a multiple of 32 with F + C <= 512 and the operand
+// tiles fitting in shared memory; returns MSSVT_ERR_INVALID otherwise (callers then use mssvt_ffn).
+int mssvt_ffn_tc(int C, int F, int mode, float eps, const float *ln_g, const float *ln_b, const float *w1,
+                 const float *b1, const float *w2, const float *b2, int num_rows, const int *num_rows_dev,
+                 const float *x, const float *merged, const unsigned char *covered, float *y, void *stream) {
+    if ((C != 32 && C != 64) || F <= 0 || (F & 31) || F + C > 512 || num_rows < 0) return MSSVT_ERR_INVALID;
+    if (num_rows == 0) return MSSVT_OK;
+    if (!ln_g || !ln_b || !w1 || !b1 || !w2 || !b2 || !merged || !y || (mode == 1 && (!x || !covered)))
+        return MSSVT_ERR_INVALID;
+    size_t smem = (size_t)TC_ROWS * C * 4 + 2 * (size_t)F * C * 4 + (size_t)TC_ROWS * F * 4 +
+                  (size_t)(3 * C + F) * 4 + 2 * 8 + 16 + 128;
+    if (smem > 227 * 1024) return MSSVT_ERR_INVALID;
+    FfnTcParams P = {F, mode, eps, w1, b1, w2, b2, ln_g, ln_b};
+    int tiles = (num_rows + TC_ROWS - 1) / TC_ROWS;
+    int grid = tiles < MSSVT_NUM_SMS ? tiles : MSSVT_NUM_SMS;
+    ++g_launches;
+    if (C == 64) {
+        cudaFuncSetAttribute(k_ffn_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_ffn_tc<64><<<grid, TC_ROWS, smem, (cudaStream_t)stream>>>(P, num_rows, num_rows_dev, x, merged, covered, y);
+    } else {
+        cudaFuncSetAttribute(k_ffn_tc<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_ffn_tc<32><<<grid, TC_ROWS, smem, (cudaStream_t)stream>>>(P, num_rows, num_rows_dev, x, merged, covered, y);
+    }
+    return check_launch();
+}
+
+}  // extern "C"

@@ -136,6 +136,9 @@ class MixedScaleSparseTransformerBlock(nn.Module):
             self.win1_size, self.win2_size, self.cbs_mode)
         self._attn_pack, self._ffn_pack = _ParamPack(), _ParamPack()
         self._tables_dev = {}
+        # "fp32": exact FFMA kernels everywhere (default).  "tf32": the FFN runs on the tcgen05
+        # tensor cores with TF32 operands (features within 2e-3 of the fp32 reference).
+        self.precision = (cfg.get("precision", "fp32") if hasattr(cfg, "get") else "fp32") or "fp32"
 
     # ---- init-time tables -------------------------------------------------------------------
     def get_vox_query_table(self, win1_size, win2_size=None, cbs_mode=None):
@@ -311,6 +314,13 @@ class MixedScaleSparseTransformerBlock(nn.Module):
     def _ffn(self, S, buf, n_rows, x, merged, covered):
         c_out = S.C_out if S.C_out else S.C
         y = torch.empty((n_rows, c_out), dtype=torch.float32, device=merged.device)
+        if (self.precision == "tf32" and S.C_out == 0 and S.C in (32, 64) and S.F % 32 == 0
+                and S.F + S.C <= 512 and (128 * S.C + 2 * S.F * S.C + 128 * S.F) * 4 < 220 * 1024):
+            # tensor-core path: TF32 operands on tcgen05, fp32 accumulate / LayerNorm / residual
+            call("mssvt_ffn_tc", S.C, S.F, S.mode, self.norm2.eps, ptr(self.norm2.weight), ptr(self.norm2.bias),
+                 ptr(self.linear1.weight), ptr(self.linear1.bias), ptr(self.linear2.weight),
+                 ptr(self.linear2.bias), n_rows, None, ptr(x), ptr(merged), ptr(covered), ptr(y), stream())
+            return y
         call("mssvt_ffn", ctypes.byref(S), ctypes.sizeof(S), ptr(buf), n_rows, None, ptr(x), ptr(merged),
              ptr(covered), ptr(y), stream())
         return y
@@ -410,6 +420,16 @@ class MixedScaleSparseTransformer(nn.Module):
                 raise NotImplementedError
             self.backbone.append(block)
         self.num_point_features = model_cfg.NUM_OUTPUT_FEATURES
+        self.set_precision(model_cfg.get('PRECISION', 'fp32'))
+
+    def set_precision(self, precision):
+        """'fp32' (exact FFMA kernels) or 'tf32' (FFN GEMMs on the tcgen05 tensor cores)."""
+        if precision not in ("fp32", "tf32"):
+            raise ValueError("precision must be 'fp32' or 'tf32'")
+        self.precision = precision
+        for block in self.backbone:
+            block.precision = precision
+        return self
 
     def forward(self, batch_dict):
         voxel_features, voxel_coords = batch_dict['voxel_features'], batch_dict['voxel_coords']

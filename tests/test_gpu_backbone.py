@@ -123,3 +123,55 @@ def test_full_size_frame_properties_150k():
     dense = a.dense()
     assert dense.shape == (1, 64, 1, 468, 468)
     assert torch.equal(dense[0, :, 0, a.indices[:, 2].long(), a.indices[:, 3].long()].t(), a.features)
+
+
+TF32_TOL = 2e-3  # relative to max|reference|: FFN GEMMs with TF32 operands on tcgen05, fp32 accumulate
+
+
+@pytest.mark.parametrize("n_rows,mode", [(1000, 1), (128, 0), (37, 1), (5000, 0)])
+def test_tensor_core_ffn_matches_fp32_ffn(n_rows, mode):
+    """mssvt_ffn_tc (tcgen05, TF32) against mssvt_ffn (FFMA, fp32) and a float64 PyTorch reference"""
+    import ctypes
+    from mssvt_b200._lib import call, ptr, stream
+    from mssvt_b200.config import block_cfg
+    from mssvt_b200.mssvt_backbone import MixedScaleSparseTransformerBlock
+    torch.manual_seed(n_rows)
+    cfg = block_cfg()
+    blk = MixedScaleSparseTransformerBlock(cfg, 64, 128, 64, [2, 2], drop_path=0.0, window_size=cfg.window_size,
+                                           cbs_pattern=1).cuda().eval()
+    with torch.no_grad():
+        blk.norm2.weight.add_(0.2 * torch.randn_like(blk.norm2.weight))
+        blk.norm2.bias.add_(0.2 * torch.randn_like(blk.norm2.bias))
+    x = torch.randn(n_rows, 64, device="cuda")
+    merged = torch.randn(n_rows, 64, device="cuda")
+    covered = (torch.rand(n_rows, device="cuda") < 0.7).to(torch.uint8)
+    u = merged if mode == 0 else torch.where(covered.bool()[:, None], merged + x, 2 * x)
+    with torch.no_grad():
+        ud = u.double()
+        h = torch.nn.functional.layer_norm(ud, (64,), blk.norm2.weight.double(), blk.norm2.bias.double(), blk.norm2.eps)
+        ref = ud + torch.nn.functional.linear(torch.relu(torch.nn.functional.linear(
+            h, blk.linear1.weight.double(), blk.linear1.bias.double())), blk.linear2.weight.double(), blk.linear2.bias.double())
+        S, buf = blk._ffn_descriptor(mode)
+        blk.precision = "fp32"
+        y32 = blk._ffn(S, buf, n_rows, x, merged, covered)
+        blk.precision = "tf32"
+        ytc = blk._ffn(S, buf, n_rows, x, merged, covered)
+    torch.cuda.synchronize()
+    scale = ref.abs().max().item()
+    assert (y32.double() - ref).abs().max().item() <= 1e-5 * scale
+    err = (ytc.double() - ref).abs().max().item()
+    assert err <= TF32_TOL * scale, (err, scale)
+    assert err > 0  # it really is a different arithmetic path
+
+
+@pytest.mark.parametrize("name", ["s0_b2_n1200"])
+def test_backbone_tf32_mode_within_stated_tolerance(name):
+    blob, cfg, state = load_golden(name)
+    cfg["PRECISION"] = "tf32"
+    feats, coords = torch.from_numpy(blob["voxel_features"]), torch.from_numpy(blob["voxel_coords"])
+    model, sp = run_product(cfg, state, blob["grid"], blob["pc_range"], feats, coords, int(blob["batch_size"]))
+    assert model.backbone[0].precision == "tf32"
+    assert torch.equal(sp.indices.cpu(), torch.from_numpy(blob["out_indices"]))  # indices stay bit-exact
+    ref = torch.from_numpy(blob["out_features"])
+    err = (sp.features.cpu() - ref).abs().max().item()
+    assert err <= TF32_TOL * ref.abs().max().item(), err
