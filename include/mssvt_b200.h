@@ -157,6 +157,10 @@ int mssvt_grid_index_build(int x_max, int y_max, int z_max, int num_voxels, int 
  *                             slots and normalised inverse-distance weights (use_interp only)
  *   covered  (num_voxels)     1 for every row the merge will overwrite (zeroed by this call)
  *   fps_idx_tap (cap, 2K), counts_tap (cap, 4): optional raw FPS picks / list lengths (NULL ok)
+ *   rep_row (cap, 2K), meta (cap, 4): optional (both or neither) compact form for the tensor-core
+ *                             window kernel: per scale the rows of the DISTINCT keys (unmasked slots
+ *                             in order, then one entry standing for all masked slots) and
+ *                             {#real queries, #win1 voxels, nrep0 | nmask0 << 8, nrep1 | nmask1 << 8}
  * voxel_size, range_min: 3 HOST floats each. */
 int mssvt_block_geometry(int x_max, int y_max, int z_max, int x_ws, int y_ws, int z_ws,
                          int num_odd, int num_even, int num_win1, int num_win2,
@@ -168,7 +172,7 @@ int mssvt_block_geometry(int x_max, int y_max, int z_max, int x_ws, int y_ws, in
                          int num_voxels, int *q_row,
                          int *win1_row, int *k_row, unsigned char *k_mask, unsigned char *nn_idx,
                          float *nn_w, unsigned char *covered, int *fps_idx_tap, int *counts_tap,
-                         void *stream);
+                         int *rep_row, int *meta, void *stream);
 
 /* One-window gather of the compress block without host synchronisation (same table walk as
  * mssvt_gather_one_window): k_row (cap, max_win1) global feature rows, -1 padded. */
@@ -192,6 +196,21 @@ int mssvt_block_attention(const void *shape, int shape_bytes, const float *param
                           const unsigned char *k_mask, const int *win1_row,
                           const unsigned char *nn_idx, const float *nn_w, float *merged,
                           void *stream);
+
+/* The same step, task-parallel with the K/V projection on the tcgen05 tensor cores (TF32 operands,
+ * fp32 everywhere else; mssvt_b200/csrc/attention_tc.cu).  Weights in nn.Module layout: pos_w
+ * [64][6], wq*/wp* [32][32], wkv* [64][32] for head groups 0 / 1; rep_row / meta from
+ * mssvt_block_geometry.  Supported: C = 64, two groups of 32 channels with 1, 2 or 4 heads each,
+ * nq <= 32, key_num_sample <= 127, cap1 <= 128; -1 otherwise. */
+int mssvt_block_attention_tc(int C, int heads_per_group, int nq, int key_num_sample, int cap1, int interp,
+                             float scale, const float *win_cell, const float *range_min,
+                             const float *pos_w, const float *pos_b, const float *wq0, const float *bq0,
+                             const float *wkv0, const float *bkv0, const float *wp0, const float *bp0,
+                             const float *wq1, const float *bq1, const float *wkv1, const float *bkv1,
+                             const float *wp1, const float *bp1, int win_capacity, const int *win_count_total,
+                             const int *win_list, const float *xn, const float *xyz, const int *q_row,
+                             const int *rep_row, const int *meta, const int *win1_row,
+                             const unsigned char *nn_idx, const float *nn_w, float *merged, void *stream);
 
 /* Attention of a one-window (compress) block (mssvt_backbone.py:361-383): out (cap, C). */
 int mssvt_compress_attention(const void *shape, int shape_bytes, const float *params,

@@ -162,6 +162,9 @@ struct GeoOut {
     unsigned char *covered; // (N) 1 = row is written by the merge (appears in a win1 list)
     int *fps_idx;     // (W, 2K) raw FPS picks, optional tap (may be null)
     int *counts;      // (W, 4) list lengths odd, even, win1, win2, optional tap (may be null)
+    int *rep_row;     // (W, 2K) per scale: rows of the DISTINCT keys (unmasked slots in order, then
+                      //         one entry standing for every masked slot), optional (may be null)
+    int *meta;        // (W, 4) {#real queries, #win1 voxels, nrep0 | nmask0 << 8, nrep1 | nmask1 << 8}
 };
 
 __device__ __forceinline__ unsigned bitrev(unsigned v, int bits) { return bits ? __brev(v) >> (32 - bits) : 0u; }
@@ -234,6 +237,10 @@ k_block_geometry(GeoParams P, TablePtrs tabs, const int *__restrict__ win_count_
         const int row0 = __ldg(v_start + win.x);
         if (out.counts && lane < 4)
             out.counts[4 * w + lane] = lane == 0 ? cnt[0] : lane == 1 ? cnt[1] : lane == 2 ? cnt[2] : cnt[3];
+        if (out.meta && lane == 0) {
+            out.meta[4 * (size_t)w + 0] = cnt[qL];
+            out.meta[4 * (size_t)w + 1] = cnt[2];
+        }
 
         // queries and win1 rows (global rows)
         for (int i = lane; i < nq; i += 32)
@@ -258,6 +265,28 @@ k_block_geometry(GeoParams P, TablePtrs tabs, const int *__restrict__ win_count_
                 out.k_row[(size_t)w * 2 * K + s * K + j] = row0 + max(v, 0);
                 out.k_mask[(size_t)w * 2 * K + s * K + j] = (j > 0 && f == 0) ? 1 : 0;
                 if (out.fps_idx) out.fps_idx[(size_t)w * 2 * K + s * K + j] = f;
+            }
+            if (out.rep_row) {
+                // distinct keys of this scale: all masked slots hold the same key (first voxel of
+                // the list, offset zeroed), so one entry with a multiplicity stands for them
+                int nrep = 0, nmask = 0, masked_row = -1;
+                for (int j0 = 0; j0 < K; j0 += 32) {
+                    const int j = j0 + lane;
+                    const int f = j < K ? s_pick[s * K + j] : 1;
+                    const int v = (j < K && f < cnt[L]) ? s_ind[list_at[L] + f] : -1;
+                    const int row = row0 + max(v, 0);
+                    const bool masked = j < K && j > 0 && f == 0, live = j < K && !masked;
+                    const unsigned mm = __ballot_sync(0xffffffffu, masked), lm = __ballot_sync(0xffffffffu, live);
+                    if (live) out.rep_row[(size_t)w * 2 * K + s * K + nrep + __popc(lm & lanemask_lt())] = row;
+                    if (mm && masked_row < 0) masked_row = __shfl_sync(0xffffffffu, row, __ffs(mm) - 1);
+                    nrep += __popc(lm);
+                    nmask += __popc(mm);
+                }
+                if (nmask > 0) {
+                    if (lane == 0) out.rep_row[(size_t)w * 2 * K + s * K + nrep] = masked_row;
+                    nrep += 1;
+                }
+                if (lane == 0) out.meta[4 * (size_t)w + 2 + s] = nrep | (nmask << 8);
             }
             __syncwarp();
         }
@@ -419,7 +448,7 @@ int mssvt_block_geometry(int x_max, int y_max, int z_max, int x_ws, int y_ws, in
                          int num_voxels, int *q_row,
                          int *win1_row, int *k_row, unsigned char *k_mask, unsigned char *nn_idx,
                          float *nn_w, unsigned char *covered, int *fps_idx_tap, int *counts_tap,
-                         void *stream) {
+                         int *rep_row, int *meta, void *stream) {
     GeoParams P;
     P.g = {x_max, y_max, z_max, x_ws, y_ws, z_ws, 1,
            {num_odd, num_even, num_win1, num_win2}, {num_odd, num_even, max_win1, max_win2}};
@@ -449,7 +478,8 @@ int mssvt_block_geometry(int x_max, int y_max, int z_max, int x_ws, int y_ws, in
     if (e != cudaSuccess) { g_last_cuda_error = (int)e; return MSSVT_ERR_LAUNCH; }
     if (win_capacity == 0) return MSSVT_OK;
     TablePtrs tabs = {{q_odd, q_even, q_win1, q_win2}};
-    GeoOut out = {q_row, win1_row, k_row, k_mask, nn_idx, nn_w, covered, fps_idx_tap, counts_tap};
+    if ((rep_row == nullptr) != (meta == nullptr)) return MSSVT_ERR_INVALID;
+    GeoOut out = {q_row, win1_row, k_row, k_mask, nn_idx, nn_w, covered, fps_idx_tap, counts_tap, rep_row, meta};
     int total = num_odd + num_even + num_win1 + num_win2;
     int caps = num_odd + num_even + max_win1 + max_win2;
     int nmax = max_win1 > max_win2 ? max_win1 : max_win2;

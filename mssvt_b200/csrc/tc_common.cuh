@@ -1,0 +1,135 @@
+// tc_common.cuh -- thin inline-PTX layer over the 5th-generation tensor cores (tcgen05 + TMEM).
+// Descriptor formats follow cute/arch/mma_sm100_desc.hpp of CUTLASS (read, not included).
+#pragma once
+#include <cstdio>
+#include "block_common.cuh"
+
+namespace mssvt {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+// K-major, no swizzle.  LBO = byte stride between the two 16-byte K chunks of one MMA,
+// SBO = byte stride between 8-row core-matrix groups (cute/arch/mma_sm100_desc.hpp semantics).
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;  // descriptor version for sm_100
+    return d;                // base_offset 0, layout_type 0 (SWIZZLE_NONE)
+}
+
+// kind::tf32, fp32 accumulate, both operands K-major
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__device__ __forceinline__ void umma_commit(uint32_t mbar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar)
+                 : "memory");
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+
+// bounded wait: a mis-programmed MMA must not hang the GPU.  try_wait suspends the thread for a
+// hardware-defined slice per call, so the bound is on wall time (%globaltimer), not on iterations:
+// after 100 ms the kernel reports where it is stuck and traps (-> cudaErrorLaunchFailure).
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+    unsigned long long t0 = 0;
+    for (uint32_t spin = 0;; ++spin) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}\n"
+            : "=r"(done)
+            : "r"(mbar), "r"(parity)
+            : "memory");
+        if (done) break;
+        if ((spin & 63u) == 63u) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 100000000ull) {
+                if ((threadIdx.x & 31) == 0)
+                    printf("mssvt_b200: mbarrier wait timed out (block %d, thread %d, parity %u)\n", blockIdx.x,
+                           threadIdx.x, parity);
+                __trap();
+            }
+        }
+    }
+    // lanes leave the wait loop at different times; the tcgen05.ld / fence instructions that follow
+    // are .sync.aligned (warp-collective), so reconverge explicitly
+    __syncwarp();
+}
+
+__device__ __forceinline__ float to_tf32(float v) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return __uint_as_float(r);
+}
+
+// 32 consecutive TMEM columns of this thread's lane
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
+    uint32_t r[32];
+    __syncwarp();
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// copy a row-major [n_rows][k] fp32 matrix (global) into the canonical K-major layout, TF32-rounded
+__device__ __forceinline__ void stage_operand(const float *__restrict__ src, int n_rows, int k, char *dst) {
+    const int chunks = k >> 2;
+    const uint32_t lbo = (uint32_t)n_rows * 16u;
+    for (int e = threadIdx.x; e < n_rows * chunks; e += blockDim.x) {
+        const int n = e / chunks, c = e - n * chunks;
+        float4 v = __ldg((const float4 *)(src + (size_t)n * k) + c);
+        v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w);
+        *(float4 *)(dst + (size_t)c * lbo + (n >> 3) * 128 + (n & 7) * 16) = v;
+    }
+}
+
+
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t cols) {  // one full warp
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {  // the same warp
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+}  // namespace mssvt

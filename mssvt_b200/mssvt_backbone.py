@@ -240,6 +240,8 @@ class MixedScaleSparseTransformerBlock(nn.Module):
             "covered": torch.empty(N, **u8),
             "fps_idx": torch.empty((cap, 2 * K), **i32) if taps else None,
             "counts": torch.empty((cap, 4), **i32) if taps else None,
+            "rep_row": torch.empty((cap, 2 * K), **i32),
+            "meta": torch.empty((cap, 4), **i32),
         }
         sx, sy, sz = (int(v) for v in sp_tensor.spatial_shape)
         cells, vals = sp_tensor.grid_index()
@@ -250,7 +252,8 @@ class MixedScaleSparseTransformerBlock(nn.Module):
              host_floats(sp_tensor.point_cloud_range[0:3]), ptr(t['odd']), ptr(t['even']), ptr(t['win1']),
              ptr(t['win2']), cap, ptr(g["total"]), ptr(win_list), ptr(cells), ptr(vals), ptr(v_start),
              N, ptr(g["q_row"]), ptr(g["win1_row"]), ptr(g["k_row"]), ptr(g["k_mask"]), ptr(g["nn_idx"]),
-             ptr(g["nn_w"]), ptr(g["covered"]), ptr(g["fps_idx"]), ptr(g["counts"]), stream())
+             ptr(g["nn_w"]), ptr(g["covered"]), ptr(g["fps_idx"]), ptr(g["counts"]), ptr(g["rep_row"]),
+             ptr(g["meta"]), stream())
         cache[key] = g
         return g
 
@@ -332,12 +335,29 @@ class MixedScaleSparseTransformerBlock(nn.Module):
             x = x.float().contiguous()
         g = self.geometry(sp_tensor)
         xn = self._layernorm1(x)
-        S, buf = self._attn_descriptor(sp_tensor, g["nq"], 2 * self.key_num_sample, self.max_num_win1)
         merged = torch.empty_like(x)  # only rows flagged in g["covered"] are written and read
-        call("mssvt_block_attention", ctypes.byref(S), ctypes.sizeof(S), ptr(buf), g["cap"],
-             ptr(g["total"]), ptr(g["win_list"]), ptr(xn), ptr(sp_tensor.world_coords()), ptr(g["q_row"]),
-             ptr(g["k_row"]), ptr(g["k_mask"]), ptr(g["win1_row"]), ptr(g["nn_idx"]), ptr(g["nn_w"]),
-             ptr(merged), stream())
+        a = self.ms_attn
+        if (self.precision == "tf32" and self.in_channels == 64 and a.scale_dims == [32, 32]
+                and a.num_heads[0] == a.num_heads[1] and a.num_heads[0] in (1, 2, 4) and g["nq"] <= 32
+                and self.key_num_sample <= 127 and self.max_num_win1 <= 128 and len(self.pos_proj) == 2):
+            # task-parallel kernel, K/V projection on the tcgen05 tensor cores (TF32 operands)
+            vs = sp_tensor.voxel_size
+            call("mssvt_block_attention_tc", 64, a.num_heads[0], g["nq"], self.key_num_sample, self.max_num_win1,
+                 int(bool(self.use_feature_interpolation)), a.scale,
+                 host_floats([vs[i] * self.win1_size[i] for i in range(3)]),
+                 host_floats(sp_tensor.point_cloud_range[0:3]), ptr(self.pos_proj[0].weight),
+                 ptr(self.pos_proj[0].bias), ptr(a.to_qs[0].weight), ptr(a.to_qs[0].bias), ptr(a.to_kvs[0].weight),
+                 ptr(a.to_kvs[0].bias), ptr(a.projs[0].weight), ptr(a.projs[0].bias), ptr(a.to_qs[1].weight),
+                 ptr(a.to_qs[1].bias), ptr(a.to_kvs[1].weight), ptr(a.to_kvs[1].bias), ptr(a.projs[1].weight),
+                 ptr(a.projs[1].bias), g["cap"], ptr(g["total"]), ptr(g["win_list"]), ptr(xn),
+                 ptr(sp_tensor.world_coords()), ptr(g["q_row"]), ptr(g["rep_row"]), ptr(g["meta"]),
+                 ptr(g["win1_row"]), ptr(g["nn_idx"]), ptr(g["nn_w"]), ptr(merged), stream())
+        else:
+            S, buf = self._attn_descriptor(sp_tensor, g["nq"], 2 * self.key_num_sample, self.max_num_win1)
+            call("mssvt_block_attention", ctypes.byref(S), ctypes.sizeof(S), ptr(buf), g["cap"],
+                 ptr(g["total"]), ptr(g["win_list"]), ptr(xn), ptr(sp_tensor.world_coords()), ptr(g["q_row"]),
+                 ptr(g["k_row"]), ptr(g["k_mask"]), ptr(g["win1_row"]), ptr(g["nn_idx"]), ptr(g["nn_w"]),
+                 ptr(merged), stream())
         F, fbuf = self._ffn_descriptor(mode=1)
         sp_tensor.features = self._ffn(F, fbuf, x.shape[0], x, merged, g["covered"])
         sp_tensor.gather_dict = None
