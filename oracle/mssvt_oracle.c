@@ -378,6 +378,15 @@ void orc_group_points_grad(int b, int c, int n, int npoints, int nsample, const 
         }
 }
 
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    extern void omp_set_num_threads(int);
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int orc_num_threads(void) {
 #ifdef _OPENMP
     extern int omp_get_max_threads(void);
