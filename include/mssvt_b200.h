@@ -52,6 +52,11 @@ int mssvt_count_samples(int num_rows, int batch_size, const int *indices, int *c
 int mssvt_voxel_world_coords(int num_voxels, const int *v_indices, const float *voxel_size,
                              const float *range_min, float *xyz, void *stream);
 
+/* dst[i] = sum_{j<i} src[j * stride] for i in [0, n], n = min(n_cap, *n_dev) read on the device
+ * (n_dev may be NULL).  dst: n_cap + 1 ints; workspace: ceil((n_cap + 1) / 1024) + 1 ints. */
+int mssvt_exclusive_scan(int n_cap, const int *n_dev, const int *src, int stride, int *dst, int *workspace,
+                         void *stream);
+
 /* ---- mssvt_ops_cuda replacements ---------------------------------------------------------- */
 
 /* build_mapping_with_hash_wrapper (ms_sparse_attention.cpp:23-35; kernel ..._gpu.cu:66-115).
@@ -197,11 +202,13 @@ int mssvt_block_attention(const void *shape, int shape_bytes, const float *param
                           const unsigned char *nn_idx, const float *nn_w, float *merged,
                           void *stream);
 
-/* The same step, task-parallel with the K/V projection on the tcgen05 tensor cores (TF32 operands,
- * fp32 everywhere else; mssvt_b200/csrc/attention_tc.cu).  Weights in nn.Module layout: pos_w
- * [64][6], wq*/wp* [32][32], wkv* [64][32] for head groups 0 / 1; rep_row / meta from
- * mssvt_block_geometry.  Supported: C = 64, two groups of 32 channels with 1, 2 or 4 heads each,
- * nq <= 32, key_num_sample <= 127, cap1 <= 128; -1 otherwise. */
+/* The same step, task-parallel (one thread per query / distinct key / voxel over the whole frame) with
+ * the K/V projection on the tcgen05 tensor cores (TF32 operands, fp32 everywhere else;
+ * mssvt_b200/csrc/attention_tc.cu: 4 kernels).  Weights in nn.Module layout: pos_w [64][6], wq*/wp*
+ * [32][32], wkv* [64][32] for head groups 0 / 1; rep_row / meta from mssvt_block_geometry; q_base =
+ * mssvt_exclusive_scan(meta[:, 0]) (win_capacity + 1 ints); scratch: 3 * num_voxels * 64 floats.
+ * Supported: C = 64, two groups of 32 channels with 1, 2 or 4 heads each, nq <= 32,
+ * key_num_sample <= 63, cap1 <= 128; -1 otherwise. */
 int mssvt_block_attention_tc(int C, int heads_per_group, int nq, int key_num_sample, int cap1, int interp,
                              float scale, const float *win_cell, const float *range_min,
                              const float *pos_w, const float *pos_b, const float *wq0, const float *bq0,
@@ -209,8 +216,9 @@ int mssvt_block_attention_tc(int C, int heads_per_group, int nq, int key_num_sam
                              const float *wq1, const float *bq1, const float *wkv1, const float *bkv1,
                              const float *wp1, const float *bp1, int win_capacity, const int *win_count_total,
                              const int *win_list, const float *xn, const float *xyz, const int *q_row,
-                             const int *rep_row, const int *meta, const int *win1_row,
-                             const unsigned char *nn_idx, const float *nn_w, float *merged, void *stream);
+                             const int *rep_row, const int *meta, const int *q_base, const int *win1_row,
+                             const unsigned char *nn_idx, const float *nn_w, int num_voxels, float *scratch,
+                             float *merged, void *stream);
 
 /* Attention of a one-window (compress) block (mssvt_backbone.py:361-383): out (cap, C). */
 int mssvt_compress_attention(const void *shape, int shape_bytes, const float *params,

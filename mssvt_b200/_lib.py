@@ -19,6 +19,7 @@ P, I, L, F = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_float
 _SIGNATURES = {
     "mssvt_fill_i32": [P, L, I, P],
     "mssvt_count_samples": [I, I, P, P, P, P],
+    "mssvt_exclusive_scan": [I, P, P, I, P, P, P],
     "mssvt_voxel_world_coords": [I, P, P, P, P, P],
     "mssvt_build_hash_table": [I, I, I, I, I, I, P, P, P, P],
     "mssvt_hash_lookup": [I, I, P, P, P, P, P],
@@ -40,7 +41,7 @@ _SIGNATURES = {
     "mssvt_window_rows": [I] * 8 + [P, I, P, P, P, P, P, P, P],
     "mssvt_layernorm": [I, P, I, P, P, P, F, P, P],
     "mssvt_block_attention": [P, I, P, I] + [P] * 11 + [P],
-    "mssvt_block_attention_tc": [I] * 6 + [F] + [P] * 16 + [I] + [P] * 11 + [P],
+    "mssvt_block_attention_tc": [I] * 6 + [F] + [P] * 16 + [I] + [P] * 11 + [I, P, P] + [P],
     "mssvt_compress_attention": [P, I, P, I] + [P] * 6 + [P],
     "mssvt_ffn": [P, I, P, I, P, P, P, P, P, P],
     "mssvt_ffn_tc": [I, I, I, F] + [P] * 6 + [I, P, P, P, P, P, P],

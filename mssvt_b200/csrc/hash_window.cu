@@ -122,6 +122,63 @@ __global__ void k_prefix_small(int batch_size, const int *__restrict__ counts, i
     }
 }
 
+// ------------------------------------------------------------------------------- strided scan
+// dst[i] = sum_{j < i} src[j * stride], dst[n] = total, for n = min(n_cap, *n_dev) read on the device
+// (two-level: 1024-element block sums, then prefix of the sums + in-block scan).
+
+__global__ void __launch_bounds__(1024)
+k_scan_block_sums(int n_cap, const int *__restrict__ n_dev, const int *__restrict__ src, int stride,
+                  int *__restrict__ block_sums) {
+    __shared__ int s_warp[32];
+    const int n = n_dev ? min(n_cap, __ldg(n_dev)) : n_cap;
+    const int i = blockIdx.x * 1024 + threadIdx.x;
+    int v = i < n ? __ldg(src + (size_t)i * stride) : 0;
+    v = __reduce_add_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        int t = s_warp[threadIdx.x];
+        t = __reduce_add_sync(0xffffffffu, t);
+        if (threadIdx.x == 0) block_sums[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(1024)
+k_scan_emit(int n_cap, const int *__restrict__ n_dev, const int *__restrict__ src, int stride,
+            const int *__restrict__ block_sums, int *__restrict__ dst) {
+    __shared__ int s_warp[32];
+    __shared__ int s_base;
+    const int n = n_dev ? min(n_cap, __ldg(n_dev)) : n_cap;
+    if (blockIdx.x * 1024 > n) return;  // (the block holding index n still writes the total)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int part = 0;
+    for (int b = threadIdx.x; b < (int)blockIdx.x; b += 1024) part += block_sums[b];
+    part = __reduce_add_sync(0xffffffffu, part);
+    if (lane == 0) s_warp[warp] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < 32; ++w) t += s_warp[w];
+        s_base = t;
+    }
+    __syncthreads();
+    const int base = s_base;
+    __syncthreads();
+    const int i = blockIdx.x * 1024 + threadIdx.x;
+    const int v = i < n ? __ldg(src + (size_t)i * stride) : 0;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    int before = 0;
+    for (int w = 0; w < warp; ++w) before += s_warp[w];
+    if (i <= n) dst[i] = base + before + incl - v;  // i == n: the total
+}
+
 // ------------------------------------------------------------------------------- grid index
 // Occupancy bitmap + rank (GridIdx in common.cuh), built in four small passes:
 //   bits:  atomicOr one bit per voxel            scan: per-1024-word block popcount sums
@@ -412,6 +469,20 @@ int mssvt_grid_index_build(int x_max, int y_max, int z_max, int num_voxels, int 
     k_grid_vals<<<div_up(num_voxels, 256), 256, 0, s>>>(x_max, y_max, z_max, zw, wps, num_voxels,
                                                         (const int4 *)v_indices, v_start,
                                                         (const int2 *)cells, vals);
+    return check_launch();
+}
+
+/* dst[i] = sum of src[j * stride] for j < i, i in [0, n]; n = min(n_cap, *n_dev) (n_dev may be NULL).
+ * dst holds n_cap + 1 ints, workspace ceil((n_cap + 1) / 1024) + 1 ints. */
+int mssvt_exclusive_scan(int n_cap, const int *n_dev, const int *src, int stride, int *dst, int *workspace,
+                         void *stream) {
+    if (n_cap < 0 || stride <= 0 || !dst || !workspace || (n_cap && !src)) return MSSVT_ERR_INVALID;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int blocks = div_up((long long)n_cap + 1, 1024);
+    ++g_launches;
+    k_scan_block_sums<<<blocks, 1024, 0, s>>>(n_cap, n_dev, src, stride, workspace);
+    ++g_launches;
+    k_scan_emit<<<blocks, 1024, 0, s>>>(n_cap, n_dev, src, stride, workspace, dst);
     return check_launch();
 }
 

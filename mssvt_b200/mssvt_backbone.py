@@ -242,6 +242,7 @@ class MixedScaleSparseTransformerBlock(nn.Module):
             "counts": torch.empty((cap, 4), **i32) if taps else None,
             "rep_row": torch.empty((cap, 2 * K), **i32),
             "meta": torch.empty((cap, 4), **i32),
+            "q_base": torch.empty(cap + 1, **i32),
         }
         sx, sy, sz = (int(v) for v in sp_tensor.spatial_shape)
         cells, vals = sp_tensor.grid_index()
@@ -254,6 +255,10 @@ class MixedScaleSparseTransformerBlock(nn.Module):
              N, ptr(g["q_row"]), ptr(g["win1_row"]), ptr(g["k_row"]), ptr(g["k_mask"]), ptr(g["nn_idx"]),
              ptr(g["nn_w"]), ptr(g["covered"]), ptr(g["fps_idx"]), ptr(g["counts"]), ptr(g["rep_row"]),
              ptr(g["meta"]), stream())
+        # compact query ids for the task-parallel kernels: q_base[w] = #real queries of windows < w
+        scan_ws = torch.empty((cap + 1 + 1023) // 1024 + 1, **i32)
+        call("mssvt_exclusive_scan", cap, ptr(g["total"]), ptr(g["meta"]), 4, ptr(g["q_base"]), ptr(scan_ws),
+             stream())
         cache[key] = g
         return g
 
@@ -339,7 +344,7 @@ class MixedScaleSparseTransformerBlock(nn.Module):
         a = self.ms_attn
         if (self.precision == "tf32" and self.in_channels == 64 and a.scale_dims == [32, 32]
                 and a.num_heads[0] == a.num_heads[1] and a.num_heads[0] in (1, 2, 4) and g["nq"] <= 32
-                and self.key_num_sample <= 127 and self.max_num_win1 <= 128 and len(self.pos_proj) == 2):
+                and self.key_num_sample <= 63 and self.max_num_win1 <= 128 and len(self.pos_proj) == 2):
             # task-parallel kernel, K/V projection on the tcgen05 tensor cores (TF32 operands)
             vs = sp_tensor.voxel_size
             call("mssvt_block_attention_tc", 64, a.num_heads[0], g["nq"], self.key_num_sample, self.max_num_win1,
@@ -351,7 +356,9 @@ class MixedScaleSparseTransformerBlock(nn.Module):
                  ptr(a.to_qs[1].bias), ptr(a.to_kvs[1].weight), ptr(a.to_kvs[1].bias), ptr(a.projs[1].weight),
                  ptr(a.projs[1].bias), g["cap"], ptr(g["total"]), ptr(g["win_list"]), ptr(xn),
                  ptr(sp_tensor.world_coords()), ptr(g["q_row"]), ptr(g["rep_row"]), ptr(g["meta"]),
-                 ptr(g["win1_row"]), ptr(g["nn_idx"]), ptr(g["nn_w"]), ptr(merged), stream())
+                 ptr(g["q_base"]), ptr(g["win1_row"]), ptr(g["nn_idx"]), ptr(g["nn_w"]), x.shape[0],
+                 ptr(torch.empty((3 * x.shape[0], 64), dtype=torch.float32, device=x.device)), ptr(merged),
+                 stream())
         else:
             S, buf = self._attn_descriptor(sp_tensor, g["nq"], 2 * self.key_num_sample, self.max_num_win1)
             call("mssvt_block_attention", ctypes.byref(S), ctypes.sizeof(S), ptr(buf), g["cap"],
