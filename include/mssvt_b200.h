@@ -166,6 +166,7 @@ int mssvt_grid_index_build(int x_max, int y_max, int z_max, int num_voxels, int 
  *                             window kernel: per scale the rows of the DISTINCT keys (unmasked slots
  *                             in order, then one entry standing for all masked slots) and
  *                             {#real queries, #win1 voxels, nrep0 | nmask0 << 8, nrep1 | nmask1 << 8}
+ *   vox_slot (num_voxels)     optional: w * max_win1 + i of the win1 slot holding each voxel, -1 if none
  * voxel_size, range_min: 3 HOST floats each. */
 int mssvt_block_geometry(int x_max, int y_max, int z_max, int x_ws, int y_ws, int z_ws,
                          int num_odd, int num_even, int num_win1, int num_win2,
@@ -177,7 +178,12 @@ int mssvt_block_geometry(int x_max, int y_max, int z_max, int x_ws, int y_ws, in
                          int num_voxels, int *q_row,
                          int *win1_row, int *k_row, unsigned char *k_mask, unsigned char *nn_idx,
                          float *nn_w, unsigned char *covered, int *fps_idx_tap, int *counts_tap,
-                         int *rep_row, int *meta, void *stream);
+                         int *rep_row, int *meta, int *vox_slot, void *stream);
+
+/* q_src[q_base[w] + s] = w * nq + s for every real query slot: inverse of the compact query numbering
+ * (q_base = mssvt_exclusive_scan over meta[:, 0]). */
+int mssvt_query_src(int win_capacity, const int *win_count_total, int nq, const int *meta, const int *q_base,
+                    int *q_src, void *stream);
 
 /* One-window gather of the compress block without host synchronisation (same table walk as
  * mssvt_gather_one_window): k_row (cap, max_win1) global feature rows, -1 padded. */
@@ -206,7 +212,8 @@ int mssvt_block_attention(const void *shape, int shape_bytes, const float *param
  * the K/V projection on the tcgen05 tensor cores (TF32 operands, fp32 everywhere else;
  * mssvt_b200/csrc/attention_tc.cu: 4 kernels).  Weights in nn.Module layout: pos_w [64][6], wq*/wp*
  * [32][32], wkv* [64][32] for head groups 0 / 1; rep_row / meta from mssvt_block_geometry; q_base =
- * mssvt_exclusive_scan(meta[:, 0]) (win_capacity + 1 ints); scratch: 3 * num_voxels * 64 floats.
+ * mssvt_exclusive_scan(meta[:, 0]) (win_capacity + 1 ints), q_src = mssvt_query_src, vox_slot from the
+ * geometry; scratch: 3 * num_voxels * 64 floats.
  * Supported: C = 64, two groups of 32 channels with 1, 2 or 4 heads each, nq <= 32,
  * key_num_sample <= 63, cap1 <= 128; -1 otherwise. */
 int mssvt_block_attention_tc(int C, int heads_per_group, int nq, int key_num_sample, int cap1, int interp,
@@ -216,15 +223,27 @@ int mssvt_block_attention_tc(int C, int heads_per_group, int nq, int key_num_sam
                              const float *wq1, const float *bq1, const float *wkv1, const float *bkv1,
                              const float *wp1, const float *bp1, int win_capacity, const int *win_count_total,
                              const int *win_list, const float *xn, const float *xyz, const int *q_row,
-                             const int *rep_row, const int *meta, const int *q_base, const int *win1_row,
-                             const unsigned char *nn_idx, const float *nn_w, int num_voxels, float *scratch,
-                             float *merged, void *stream);
+                             const int *rep_row, const int *meta, const int *q_base, const int *q_src,
+                             const int *vox_slot, const int *win1_row, const unsigned char *nn_idx,
+                             const float *nn_w, int num_voxels, float *scratch, float *merged, void *stream);
 
 /* Attention of a one-window (compress) block (mssvt_backbone.py:361-383): out (cap, C). */
 int mssvt_compress_attention(const void *shape, int shape_bytes, const float *params,
                              int win_capacity, const int *win_count_total, const int *win_list,
                              const float *xn, const float *xyz, const int *k_row, float *out,
                              void *stream);
+
+/* The same step, task-parallel with the second positional-embedding layer and the K/V projection on
+ * the tcgen05 tensor cores (mssvt_b200/csrc/compress_tc.cu: 3 kernels).  Weights in nn.Module layout:
+ * pos_w [64][6], pos2_w [64][64], wq / wp [64][64], wkv [128][64].  scratch: 2 * win_capacity * 64 floats.
+ * Supported: C = 64, one head group with 1, 2, 4 or 8 heads, two-layer pos_proj, n1 <= 127; -1 otherwise. */
+int mssvt_compress_attention_tc(int C, int heads, int n1, float scale, const float *win_cell,
+                                const float *range_min, const float *pos_w, const float *pos_b,
+                                const float *pos2_w, const float *pos2_b, const float *wq, const float *bq,
+                                const float *wkv, const float *bkv, const float *wp, const float *bp,
+                                int win_capacity, const int *win_count_total, const int *win_list,
+                                const float *xn, const float *xyz, const int *k_row, float *scratch, float *out,
+                                void *stream);
 
 /* residual + norm2 + linear1 / ReLU / linear2 + residual (+ out_linear)
  * (mssvt_backbone.py:337-343, 384-387).  `shape` is the FfnShape descriptor. */

@@ -37,12 +37,14 @@ _SIGNATURES = {
     "mssvt_group_points_grad": [I, I, I, I, I, P, P, P, P],
     "mssvt_grid_index_words": [I, I, I, I],
     "mssvt_grid_index_build": [I, I, I, I, I, P, P, P, P, P, P],
-    "mssvt_block_geometry": [I] * 15 + [P] * 6 + [I, P, P, P, P, P, I] + [P] * 11 + [P],
+    "mssvt_block_geometry": [I] * 15 + [P] * 6 + [I, P, P, P, P, P, I] + [P] * 12 + [P],
+    "mssvt_query_src": [I, P, I, P, P, P, P],
     "mssvt_window_rows": [I] * 8 + [P, I, P, P, P, P, P, P, P],
     "mssvt_layernorm": [I, P, I, P, P, P, F, P, P],
     "mssvt_block_attention": [P, I, P, I] + [P] * 11 + [P],
-    "mssvt_block_attention_tc": [I] * 6 + [F] + [P] * 16 + [I] + [P] * 11 + [I, P, P] + [P],
+    "mssvt_block_attention_tc": [I] * 6 + [F] + [P] * 16 + [I] + [P] * 13 + [I, P, P] + [P],
     "mssvt_compress_attention": [P, I, P, I] + [P] * 6 + [P],
+    "mssvt_compress_attention_tc": [I, I, I, F] + [P] * 12 + [I] + [P] * 7 + [P],
     "mssvt_ffn": [P, I, P, I, P, P, P, P, P, P],
     "mssvt_ffn_tc": [I, I, I, F] + [P] * 6 + [I, P, P, P, P, P, P],
     "mssvt_dense_scatter": [I, P, I, I, I, I, I, P, P, P, P],

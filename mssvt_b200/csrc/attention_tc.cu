@@ -30,7 +30,7 @@
 namespace mssvt {
 
 #define TCA_THREADS 128
-#define TCA_WB 32        // windows per batch (tile candidates)
+#define TCA_WB 16        // windows per batch (tile candidates)
 #define TCA_C 64
 #define TCA_SD 32
 #define TCA_VPITCH 36    // V row pitch in floats: 16-byte aligned, conflict-free for quarter warps
@@ -73,21 +73,24 @@ __device__ __forceinline__ float pos_embed8(const float *sPos, int c, float rx, 
     return fmaxf(a, 0.f);
 }
 
-// 8 interleaved outputs (oq, oq+4, ...) of a 32 -> 32 projection for one input row held in registers
+// 8 interleaved outputs (oq, oq+4, ...) of a 32 -> 32 projection for one input row held in registers;
+// the 8 accumulators are independent FMA chains
 __device__ __forceinline__ void proj8(const float *sW, const float *bias, const float *xin, int oq, float mul,
                                       float *dst) {
-#pragma unroll 2
-    for (int j = 0; j < 8; ++j) {
-        const int o = oq + 4 * j;
-        float a = bias[o];
+    float a[8];
 #pragma unroll
-        for (int i4 = 0; i4 < TCA_SD / 4; ++i4) {
-            const float4 wv = *(const float4 *)(sW + o * TCA_WPITCH + 4 * i4);
-            a = fmaf(wv.x, xin[4 * i4], a); a = fmaf(wv.y, xin[4 * i4 + 1], a);
-            a = fmaf(wv.z, xin[4 * i4 + 2], a); a = fmaf(wv.w, xin[4 * i4 + 3], a);
+    for (int j = 0; j < 8; ++j) a[j] = bias[oq + 4 * j];
+#pragma unroll
+    for (int i4 = 0; i4 < TCA_SD / 4; ++i4) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 wv = *(const float4 *)(sW + (oq + 4 * j) * TCA_WPITCH + 4 * i4);
+            a[j] = fmaf(wv.x, xin[4 * i4], a[j]); a[j] = fmaf(wv.y, xin[4 * i4 + 1], a[j]);
+            a[j] = fmaf(wv.z, xin[4 * i4 + 2], a[j]); a[j] = fmaf(wv.w, xin[4 * i4 + 3], a[j]);
         }
-        dst[o] = a * mul;
     }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dst[oq + 4 * j] = a[j] * mul;
 }
 
 // ------------------------------------------------------------------------------- queries
@@ -95,7 +98,7 @@ __device__ __forceinline__ void proj8(const float *sW, const float *bias, const 
 __global__ void __launch_bounds__(256)
 k_tca_query(TcAttnParams P, int win_cap, const int *__restrict__ win_count_total,
             const int4 *__restrict__ win_list, const float *__restrict__ xn, const float *__restrict__ xyz,
-            const int *__restrict__ q_row, const int *__restrict__ meta, const int *__restrict__ q_base,
+            const int *__restrict__ q_row, const int *__restrict__ q_base, const int *__restrict__ q_src,
             float *__restrict__ Qbuf) {
     __shared__ __align__(16) float sPos[64 * 8];
     __shared__ __align__(16) float sW[2 * TCA_WGRP];
@@ -105,13 +108,13 @@ k_tca_query(TcAttnParams P, int win_cap, const int *__restrict__ win_count_total
     for (int i = threadIdx.x; i < 64; i += blockDim.x) sB[i] = __ldg(P.bq[i >> 5] + (i & 31));
     __syncthreads();
     const int num_wins = min(win_cap, __ldg(win_count_total));
-    const long long total = (long long)num_wins * P.nq * 8;
+    const long long total = (long long)__ldg(q_base + num_wins) * 8;  // #real queries of the frame
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
          e += (long long)gridDim.x * blockDim.x) {
         const int part = (int)(e & 7), g = part >> 2, oq = part & 3;
-        const int qs = (int)(e >> 3), w = qs / P.nq, s = qs - w * P.nq;
-        if (s >= __ldg(meta + 4 * (size_t)w)) continue;  // padded query slot
-        const int row = __ldg(q_row + (size_t)w * P.nq + s);
+        const size_t qid = (size_t)(e >> 3);
+        const int src = __ldg(q_src + qid), w = src / P.nq;
+        const int row = __ldg(q_row + src);
         const int4 win = __ldg(win_list + w);
         const float cx = world_coord(win.w, P.win_cell[0], P.lo[0]);
         const float cy = world_coord(win.z, P.win_cell[1], P.lo[1]);
@@ -128,8 +131,7 @@ k_tca_query(TcAttnParams P, int win_cap, const int *__restrict__ win_count_total
             xin[4 * c4 + 2] = v.z + pos_embed8(sPos, g * TCA_SD + 4 * c4 + 2, rx, ry, rz, cx, cy, cz);
             xin[4 * c4 + 3] = v.w + pos_embed8(sPos, g * TCA_SD + 4 * c4 + 3, rx, ry, rz, cx, cy, cz);
         }
-        proj8(sW + g * TCA_WGRP, sB + g * TCA_SD, xin, oq, P.scale,
-              Qbuf + (size_t)(__ldg(q_base + w) + s) * TCA_C + g * TCA_SD);
+        proj8(sW + g * TCA_WGRP, sB + g * TCA_SD, xin, oq, P.scale, Qbuf + qid * TCA_C + g * TCA_SD);
     }
 }
 
@@ -262,9 +264,12 @@ k_tca_keys(TcAttnParams P, int win_cap, const int *__restrict__ win_count_total,
                     rz = __fsub_rn(__ldg(xyz + 3 * (size_t)row + 2), cz);
                 }
                 const float4 *src = (const float4 *)(xn + (size_t)row * TCA_C + g * TCA_SD);
-#pragma unroll 2
+                float4 xv[TCA_SD / 4];  // the whole 128-byte slice in flight at once
+#pragma unroll
+                for (int c4 = 0; c4 < TCA_SD / 4; ++c4) xv[c4] = __ldg(src + c4);
+#pragma unroll
                 for (int c4 = 0; c4 < TCA_SD / 4; ++c4) {
-                    const float4 v = __ldg(src + c4);
+                    const float4 v = xv[c4];
                     const int c = g * TCA_SD + 4 * c4;
                     float4 o;
                     o.x = to_tf32(v.x + pos_embed8(sPos, c, rx, ry, rz, cx, cy, cz));
@@ -389,24 +394,24 @@ k_tca_proj(TcAttnParams P, int win_cap, const int *__restrict__ win_count_total,
 // ------------------------------------------------------------------------------- merge
 
 __global__ void __launch_bounds__(256)
-k_tca_merge(TcAttnParams P, int win_cap, const int *__restrict__ win_count_total,
-            const int *__restrict__ meta, const int *__restrict__ q_base, const int *__restrict__ q_row,
-            const int *__restrict__ win1_row, const unsigned char *__restrict__ nn_idx,
-            const float *__restrict__ nn_w, const float *__restrict__ Pbuf, float *__restrict__ merged) {
+k_tca_merge(TcAttnParams P, int win_cap, const int *__restrict__ win_count_total, int num_voxels,
+            const int *__restrict__ meta, const int *__restrict__ q_base, const int *__restrict__ q_src,
+            const int *__restrict__ q_row, const int *__restrict__ vox_slot,
+            const unsigned char *__restrict__ nn_idx, const float *__restrict__ nn_w,
+            const float *__restrict__ Pbuf, float *__restrict__ merged) {
     const int num_wins = min(win_cap, __ldg(win_count_total));
-    const int per_win = P.interp ? P.cap1 : P.nq;
-    const long long total = (long long)num_wins * per_win * 4;
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
-         e += (long long)gridDim.x * blockDim.x) {
-        const int cq = (int)(e & 3);
-        const int vs = (int)(e >> 2), w = vs / per_win, i = vs - w * per_win;
-        const int4 m = __ldg((const int4 *)meta + w);
-        const int nqr = m.x, q0 = __ldg(q_base + w);
-        if (P.interp) {
-            if (i >= m.y) continue;  // padded win1 slot
-            const int row = __ldg(win1_row + (size_t)w * P.cap1 + i);
-            const unsigned char *ni = nn_idx + ((size_t)w * P.cap1 + i) * 3;
-            const float *nw = nn_w + ((size_t)w * P.cap1 + i) * 3;
+    if (P.interp) {
+        // thread = (voxel row, 16 channels): the voxel's win1 slot names its 3 nearest query slots
+        const long long total = (long long)num_voxels * 4;
+        for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+             e += (long long)gridDim.x * blockDim.x) {
+            const int cq = (int)(e & 3), row = (int)(e >> 2);
+            const int slot = __ldg(vox_slot + row);
+            if (slot < 0) continue;  // not in any win1 list: the FFN doubles the shortcut instead
+            const int w = slot / P.cap1;
+            const int nqr = __ldg(meta + 4 * (size_t)w), q0 = __ldg(q_base + w);
+            const unsigned char *ni = nn_idx + (size_t)slot * 3;
+            const float *nw = nn_w + (size_t)slot * 3;
             const int n0 = ni[0], n1 = ni[1], n2 = ni[2];
             // padded query slots (index >= #real queries) are zero rows in the reference
             const float4 *a0 = n0 < nqr ? (const float4 *)(Pbuf + (size_t)(q0 + n0) * TCA_C + 16 * cq) : nullptr;
@@ -426,10 +431,16 @@ k_tca_merge(TcAttnParams P, int win_cap, const int *__restrict__ win_count_total
                 y.w = __fadd_rn(__fadd_rn(__fmul_rn(p0.w, w0), __fmul_rn(p1.w, w1)), __fmul_rn(p2.w, w2));
                 dst[c4] = y;
             }
-        } else {
-            if (i >= nqr) continue;
-            const int row = __ldg(q_row + (size_t)w * P.nq + i);
-            const float4 *src = (const float4 *)(Pbuf + (size_t)(q0 + i) * TCA_C + 16 * cq);
+        }
+    } else {
+        // thread = (query, 16 channels): the query voxel takes its own projected row
+        const long long total = (long long)__ldg(q_base + num_wins) * 4;
+        for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+             e += (long long)gridDim.x * blockDim.x) {
+            const int cq = (int)(e & 3);
+            const size_t qid = (size_t)(e >> 2);
+            const int row = __ldg(q_row + __ldg(q_src + qid));
+            const float4 *src = (const float4 *)(Pbuf + qid * TCA_C + 16 * cq);
             float4 *dst = (float4 *)(merged + (size_t)row * TCA_C + 16 * cq);
 #pragma unroll
             for (int c4 = 0; c4 < 4; ++c4) dst[c4] = __ldg(src + c4);
@@ -463,18 +474,19 @@ int mssvt_block_attention_tc(int C, int heads_per_group, int nq, int key_num_sam
                              const float *wq1, const float *bq1, const float *wkv1, const float *bkv1,
                              const float *wp1, const float *bp1, int win_capacity, const int *win_count_total,
                              const int *win_list, const float *xn, const float *xyz, const int *q_row,
-                             const int *rep_row, const int *meta, const int *q_base, const int *win1_row,
-                             const unsigned char *nn_idx, const float *nn_w, int num_voxels, float *scratch,
-                             float *merged, void *stream) {
+                             const int *rep_row, const int *meta, const int *q_base, const int *q_src,
+                             const int *vox_slot, const int *win1_row, const unsigned char *nn_idx,
+                             const float *nn_w, int num_voxels, float *scratch, float *merged, void *stream) {
     if (C != 64 || (heads_per_group != 1 && heads_per_group != 2 && heads_per_group != 4) || nq <= 0 || nq > 32 ||
         key_num_sample <= 0 || key_num_sample > 63 || cap1 <= 0 || cap1 > 128 || win_capacity < 0 || num_voxels < 0)
         return MSSVT_ERR_INVALID;
     if (win_capacity == 0) return MSSVT_OK;
     if (!win_cell || !range_min || !pos_w || !pos_b || !wq0 || !bq0 || !wkv0 || !bkv0 || !wp0 || !bp0 || !wq1 ||
         !bq1 || !wkv1 || !bkv1 || !wp1 || !bp1 || !win_count_total || !win_list || !xn || !xyz || !q_row ||
-        !rep_row || !meta || !q_base || !scratch || !merged)
+        !rep_row || !meta || !q_base || !q_src || !scratch || !merged)
         return MSSVT_ERR_INVALID;
-    if (interp && (!win1_row || !nn_idx || !nn_w)) return MSSVT_ERR_INVALID;
+    if (interp && (!vox_slot || !nn_idx || !nn_w)) return MSSVT_ERR_INVALID;
+    (void)win1_row;
     TcAttnParams P;
     P.nq = nq; P.K = key_num_sample; P.cap1 = cap1; P.interp = interp ? 1 : 0;
     P.heads = heads_per_group; P.smax = nq * heads_per_group;
@@ -491,7 +503,7 @@ int mssvt_block_attention_tc(int C, int heads_per_group, int nq, int key_num_sam
     const int wide = MSSVT_NUM_SMS * 8;  // grid-stride kernels: 8 CTAs of 256 threads per SM
 
     ++g_launches;
-    k_tca_query<<<wide, 256, 0, s>>>(P, win_capacity, win_count_total, wl, xn, xyz, q_row, meta, q_base, Qbuf);
+    k_tca_query<<<wide, 256, 0, s>>>(P, win_capacity, win_count_total, wl, xn, xyz, q_row, q_base, q_src, Qbuf);
 
     int per_sm = (int)(227 * 1024 / (smem + 1024));
     per_sm = per_sm > 4 ? 4 : per_sm < 1 ? 1 : per_sm;  // 4 x 128 TMEM columns = all 512
@@ -511,8 +523,8 @@ int mssvt_block_attention_tc(int C, int heads_per_group, int nq, int key_num_sam
     ++g_launches;
     k_tca_proj<<<wide, 256, 0, s>>>(P, win_capacity, win_count_total, q_base, Obuf, Pbuf);
     ++g_launches;
-    k_tca_merge<<<wide, 256, 0, s>>>(P, win_capacity, win_count_total, meta, q_base, q_row, win1_row, nn_idx,
-                                     nn_w, Pbuf, merged);
+    k_tca_merge<<<wide, 256, 0, s>>>(P, win_capacity, win_count_total, num_voxels, meta, q_base, q_src, q_row,
+                                     vox_slot, nn_idx, nn_w, Pbuf, merged);
     return check_launch();
 }
 

@@ -165,6 +165,7 @@ struct GeoOut {
     int *rep_row;     // (W, 2K) per scale: rows of the DISTINCT keys (unmasked slots in order, then
                       //         one entry standing for every masked slot), optional (may be null)
     int *meta;        // (W, 4) {#real queries, #win1 voxels, nrep0 | nmask0 << 8, nrep1 | nmask1 << 8}
+    int *vox_slot;    // (N) w * cap1 + i of the win1 slot holding the voxel, -1 if none (optional)
 };
 
 __device__ __forceinline__ unsigned bitrev(unsigned v, int bits) { return bits ? __brev(v) >> (32 - bits) : 0u; }
@@ -249,6 +250,7 @@ k_block_geometry(GeoParams P, TablePtrs tabs, const int *__restrict__ win_count_
             int r = i < cnt[2] ? row0 + s_ind[list_at[2] + i] : -1;
             out.win1_row[(size_t)w * cap1 + i] = r;
             if (P.interp && r >= 0) out.covered[r] = 1;
+            if (out.vox_slot && r >= 0) out.vox_slot[r] = w * cap1 + i;
         }
         if (!P.interp)  // without interpolation the merge writes the query rows instead
             for (int i = lane; i < cnt[qL]; i += 32) out.covered[row0 + s_ind[list_at[qL] + i]] = 1;
@@ -367,6 +369,19 @@ k_window_rows(GatherShape g, TablePtrs tabs, const int *__restrict__ win_count_t
     }
 }
 
+// q_src[q_base[w] + s] = w * nq + s for every real query slot: inverse of the compact query numbering
+__global__ void k_query_src(int win_cap, const int *__restrict__ win_count_total, int nq,
+                            const int *__restrict__ meta, const int *__restrict__ q_base,
+                            int *__restrict__ q_src) {
+    const int num_wins = min(win_cap, __ldg(win_count_total));
+    const long long total = (long long)num_wins * nq;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        const int w = (int)(e / nq), sl = (int)(e - (long long)w * nq);
+        if (sl < __ldg(meta + 4 * (size_t)w)) q_src[__ldg(q_base + w) + sl] = (int)e;
+    }
+}
+
 }  // namespace mssvt
 
 using namespace mssvt;
@@ -448,7 +463,7 @@ int mssvt_block_geometry(int x_max, int y_max, int z_max, int x_ws, int y_ws, in
                          int num_voxels, int *q_row,
                          int *win1_row, int *k_row, unsigned char *k_mask, unsigned char *nn_idx,
                          float *nn_w, unsigned char *covered, int *fps_idx_tap, int *counts_tap,
-                         int *rep_row, int *meta, void *stream) {
+                         int *rep_row, int *meta, int *vox_slot, void *stream) {
     GeoParams P;
     P.g = {x_max, y_max, z_max, x_ws, y_ws, z_ws, 1,
            {num_odd, num_even, num_win1, num_win2}, {num_odd, num_even, max_win1, max_win2}};
@@ -479,7 +494,12 @@ int mssvt_block_geometry(int x_max, int y_max, int z_max, int x_ws, int y_ws, in
     if (win_capacity == 0) return MSSVT_OK;
     TablePtrs tabs = {{q_odd, q_even, q_win1, q_win2}};
     if ((rep_row == nullptr) != (meta == nullptr)) return MSSVT_ERR_INVALID;
-    GeoOut out = {q_row, win1_row, k_row, k_mask, nn_idx, nn_w, covered, fps_idx_tap, counts_tap, rep_row, meta};
+    GeoOut out = {q_row, win1_row, k_row, k_mask, nn_idx, nn_w, covered, fps_idx_tap, counts_tap, rep_row, meta,
+                  vox_slot};
+    if (vox_slot) {
+        e = cudaMemsetAsync(vox_slot, 0xff, (size_t)num_voxels * sizeof(int), s);
+        if (e != cudaSuccess) { g_last_cuda_error = (int)e; return MSSVT_ERR_LAUNCH; }
+    }
     int total = num_odd + num_even + num_win1 + num_win2;
     int caps = num_odd + num_even + max_win1 + max_win2;
     int nmax = max_win1 > max_win2 ? max_win1 : max_win2;
@@ -519,6 +539,18 @@ int mssvt_window_rows(int x_max, int y_max, int z_max, int x_ws, int y_ws, int z
     k_window_rows<<<persistent_grid(win_capacity, GEO_WARPS, 8), GEO_WARPS * 32, smem,
                     (cudaStream_t)stream>>>(g, tabs, win_count_total, (const int4 *)win_list,
                                             index, v_start, k_row);
+    return check_launch();
+}
+
+/* q_src[q_base[w] + s] = w * nq + s for every real query slot (inverse of the compact numbering). */
+int mssvt_query_src(int win_capacity, const int *win_count_total, int nq, const int *meta, const int *q_base,
+                    int *q_src, void *stream) {
+    if (win_capacity < 0 || nq <= 0) return MSSVT_ERR_INVALID;
+    if (win_capacity == 0) return MSSVT_OK;
+    if (!win_count_total || !meta || !q_base || !q_src) return MSSVT_ERR_INVALID;
+    ++g_launches;
+    k_query_src<<<persistent_grid((long long)win_capacity * nq, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+        win_capacity, win_count_total, nq, meta, q_base, q_src);
     return check_launch();
 }
 

@@ -243,6 +243,8 @@ class MixedScaleSparseTransformerBlock(nn.Module):
             "rep_row": torch.empty((cap, 2 * K), **i32),
             "meta": torch.empty((cap, 4), **i32),
             "q_base": torch.empty(cap + 1, **i32),
+            "q_src": torch.empty(max(N, 1), **i32),
+            "vox_slot": torch.empty(max(N, 1), **i32),
         }
         sx, sy, sz = (int(v) for v in sp_tensor.spatial_shape)
         cells, vals = sp_tensor.grid_index()
@@ -254,11 +256,12 @@ class MixedScaleSparseTransformerBlock(nn.Module):
              ptr(t['win2']), cap, ptr(g["total"]), ptr(win_list), ptr(cells), ptr(vals), ptr(v_start),
              N, ptr(g["q_row"]), ptr(g["win1_row"]), ptr(g["k_row"]), ptr(g["k_mask"]), ptr(g["nn_idx"]),
              ptr(g["nn_w"]), ptr(g["covered"]), ptr(g["fps_idx"]), ptr(g["counts"]), ptr(g["rep_row"]),
-             ptr(g["meta"]), stream())
+             ptr(g["meta"]), ptr(g["vox_slot"]), stream())
         # compact query ids for the task-parallel kernels: q_base[w] = #real queries of windows < w
         scan_ws = torch.empty((cap + 1 + 1023) // 1024 + 1, **i32)
         call("mssvt_exclusive_scan", cap, ptr(g["total"]), ptr(g["meta"]), 4, ptr(g["q_base"]), ptr(scan_ws),
              stream())
+        call("mssvt_query_src", cap, ptr(g["total"]), nq, ptr(g["meta"]), ptr(g["q_base"]), ptr(g["q_src"]), stream())
         cache[key] = g
         return g
 
@@ -356,7 +359,8 @@ class MixedScaleSparseTransformerBlock(nn.Module):
                  ptr(a.to_qs[1].bias), ptr(a.to_kvs[1].weight), ptr(a.to_kvs[1].bias), ptr(a.projs[1].weight),
                  ptr(a.projs[1].bias), g["cap"], ptr(g["total"]), ptr(g["win_list"]), ptr(xn),
                  ptr(sp_tensor.world_coords()), ptr(g["q_row"]), ptr(g["rep_row"]), ptr(g["meta"]),
-                 ptr(g["q_base"]), ptr(g["win1_row"]), ptr(g["nn_idx"]), ptr(g["nn_w"]), x.shape[0],
+                 ptr(g["q_base"]), ptr(g["q_src"]), ptr(g["vox_slot"]), ptr(g["win1_row"]), ptr(g["nn_idx"]),
+                 ptr(g["nn_w"]), x.shape[0],
                  ptr(torch.empty((3 * x.shape[0], 64), dtype=torch.float32, device=x.device)), ptr(merged),
                  stream())
         else:
@@ -392,10 +396,24 @@ class MixedScaleSparseTransformerCompressBlock(MixedScaleSparseTransformerBlock)
              n1, ptr(t['win1']), cap, ptr(total), ptr(win_list), ptr(cells), ptr(vals), ptr(v_start),
              ptr(k_row), stream())
         xn = self._layernorm1(x)
-        S, buf = self._attn_descriptor(sp_tensor, 1, n1, n1)
         attn = torch.empty((cap, self.in_channels), dtype=torch.float32, device=dev)
-        call("mssvt_compress_attention", ctypes.byref(S), ctypes.sizeof(S), ptr(buf), cap, ptr(total),
-             ptr(win_list), ptr(xn), ptr(sp_tensor.world_coords()), ptr(k_row), ptr(attn), stream())
+        a = self.ms_attn
+        if (self.precision == "tf32" and self.in_channels == 64 and a.num_head_groups == 1
+                and a.num_heads[0] in (1, 2, 4, 8) and len(self.pos_proj) == 4 and n1 <= 127):
+            # task-parallel kernels; second pos_proj layer and K/V projection on the tcgen05 tensor cores
+            vs = sp_tensor.voxel_size
+            scratch = torch.empty((2 * cap, 64), dtype=torch.float32, device=dev)
+            call("mssvt_compress_attention_tc", 64, a.num_heads[0], n1, a.scale,
+                 host_floats([vs[i] * self.win1_size[i] for i in range(3)]),
+                 host_floats(sp_tensor.point_cloud_range[0:3]), ptr(self.pos_proj[0].weight),
+                 ptr(self.pos_proj[0].bias), ptr(self.pos_proj[2].weight), ptr(self.pos_proj[2].bias),
+                 ptr(a.to_qs[0].weight), ptr(a.to_qs[0].bias), ptr(a.to_kvs[0].weight), ptr(a.to_kvs[0].bias),
+                 ptr(a.projs[0].weight), ptr(a.projs[0].bias), cap, ptr(total), ptr(win_list), ptr(xn),
+                 ptr(sp_tensor.world_coords()), ptr(k_row), ptr(scratch), ptr(attn), stream())
+        else:
+            S, buf = self._attn_descriptor(sp_tensor, 1, n1, n1)
+            call("mssvt_compress_attention", ctypes.byref(S), ctypes.sizeof(S), ptr(buf), cap, ptr(total),
+                 ptr(win_list), ptr(xn), ptr(sp_tensor.world_coords()), ptr(k_row), ptr(attn), stream())
         # the output has one row per non-empty window: the only host sync of the backbone
         counts = win_count.tolist()
         if counts[B + 1]:
