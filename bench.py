@@ -195,7 +195,17 @@ def our_arm(args):
                     ev.record(s_in)
                 staged[i] = (fd, cd, ev)
 
+            def drain(i, sp, done):
+                # result of step i to the host: row count (already on its way), then the rows
+                with torch.cuda.stream(s_out):
+                    s_out.wait_event(done)
+                    n = sp.features.shape[0]
+                    out_feat[i % 2][:n].copy_(sp.features, non_blocking=True)
+                    out_idx[i % 2][:n].copy_(sp.indices, non_blocking=True)
+                return n
+
             stage(0)
+            pending = None
             for i in range(steps):
                 if i + 1 < steps:
                     stage(i + 1)
@@ -203,16 +213,16 @@ def our_arm(args):
                 with torch.cuda.stream(s_comp):
                     s_comp.wait_event(ev)
                     sp = model({"voxel_features": fd, "voxel_coords": cd, "batch_size": 1})["encoded_spconv_tensor"]
+                    sp.prefetch_row_count()
                     done = torch.cuda.Event()
                     done.record(s_comp)
-                rows = sp.features.shape[0]
-                with torch.cuda.stream(s_out):
-                    s_out.wait_event(done)
-                    out_feat[i % 2][:rows].copy_(sp.features, non_blocking=True)
-                    out_idx[i % 2][:rows].copy_(sp.indices, non_blocking=True)
-                keep.append((fd, cd, sp))  # keep device buffers alive until their copies are done
-                if len(keep) > 3:
+                if pending is not None:      # step i is queued: now wait for step i-1's count and copy it out
+                    rows = drain(*pending)
+                pending = (i, sp, done)
+                keep.append((fd, cd, sp))    # keep device buffers alive until their copies are done
+                if len(keep) > 4:
                     keep.pop(0)
+            rows = drain(*pending)
             for st in (s_in, s_comp, s_out):
                 st.synchronize()
             return rows

@@ -322,7 +322,7 @@ class MixedScaleSparseTransformerBlock(nn.Module):
              ptr(self.norm1.bias), self.norm1.eps, ptr(xn), stream())
         return xn
 
-    def _ffn(self, S, buf, n_rows, x, merged, covered):
+    def _ffn(self, S, buf, n_rows, x, merged, covered, n_dev=None):
         c_out = S.C_out if S.C_out else S.C
         y = torch.empty((n_rows, c_out), dtype=torch.float32, device=merged.device)
         if (self.precision == "tf32" and S.C_out == 0 and S.C in (32, 64) and S.F % 32 == 0
@@ -330,9 +330,9 @@ class MixedScaleSparseTransformerBlock(nn.Module):
             # tensor-core path: TF32 operands on tcgen05, fp32 accumulate / LayerNorm / residual
             call("mssvt_ffn_tc", S.C, S.F, S.mode, self.norm2.eps, ptr(self.norm2.weight), ptr(self.norm2.bias),
                  ptr(self.linear1.weight), ptr(self.linear1.bias), ptr(self.linear2.weight),
-                 ptr(self.linear2.bias), n_rows, None, ptr(x), ptr(merged), ptr(covered), ptr(y), stream())
+                 ptr(self.linear2.bias), n_rows, ptr(n_dev), ptr(x), ptr(merged), ptr(covered), ptr(y), stream())
             return y
-        call("mssvt_ffn", ctypes.byref(S), ctypes.sizeof(S), ptr(buf), n_rows, None, ptr(x), ptr(merged),
+        call("mssvt_ffn", ctypes.byref(S), ctypes.sizeof(S), ptr(buf), n_rows, ptr(n_dev), ptr(x), ptr(merged),
              ptr(covered), ptr(y), stream())
         return y
 
@@ -414,21 +414,18 @@ class MixedScaleSparseTransformerCompressBlock(MixedScaleSparseTransformerBlock)
             S, buf = self._attn_descriptor(sp_tensor, 1, n1, n1)
             call("mssvt_compress_attention", ctypes.byref(S), ctypes.sizeof(S), ptr(buf), cap, ptr(total),
                  ptr(win_list), ptr(xn), ptr(sp_tensor.world_coords()), ptr(k_row), ptr(attn), stream())
-        # the output has one row per non-empty window: the only host sync of the backbone
-        counts = win_count.tolist()
-        if counts[B + 1]:
-            raise RuntimeError("compress block: %d windows exceed max_num_wins" % counts[B + 1])
-        W = counts[B]
+        # one output row per non-empty window; the count stays on the device (lazy slicing, see
+        # SparseTensor.set_lazy_rows): the forward never waits for the host
         F, fbuf = self._ffn_descriptor(mode=0)
-        new_features = self._ffn(F, fbuf, W, None, attn, None)
+        new_features = self._ffn(F, fbuf, cap, None, attn, None, n_dev=total)
         vs = sp_tensor.voxel_size
-        sp_tensor.features = new_features
-        sp_tensor.indices = win_list[:W]
+        sp_tensor.set_lazy_rows(new_features, win_list, total)
         sp_tensor.spatial_shape = grid
         sp_tensor.voxel_size = [vs[i] * self.win1_size[i] for i in range(3)]
         sp_tensor.gather_dict = None
         sp_tensor.map_table = win_table
-        sp_tensor._taps = {"k_row": k_row[:W], "attn": attn[:W]}
+        sp_tensor._window_overflow = win_count[B + 1:B + 2]
+        sp_tensor._taps = {"k_row": k_row, "attn": attn}
         return sp_tensor
 
 

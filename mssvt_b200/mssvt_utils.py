@@ -15,6 +15,18 @@ from . import mssvt_ops
 from ._lib import call, ptr, stream, host_floats
 
 
+_PINNED_RING = []
+
+
+def _pinned_pair():
+    """small ring of pinned int32[2] buffers for asynchronous row-count readbacks"""
+    if len(_PINNED_RING) < 16:
+        _PINNED_RING.append(torch.empty(2, dtype=torch.int32).pin_memory())
+        return _PINNED_RING[-1]
+    _PINNED_RING.append(_PINNED_RING.pop(0))
+    return _PINNED_RING[-1]
+
+
 def sample_counts(indices, batch_size):
     """(counts (B), start (B+1)) int32 on the device, no host sync."""
     counts = torch.empty(batch_size, dtype=torch.int32, device=indices.device)
@@ -29,8 +41,9 @@ class SparseTensor(object):
 
     def __init__(self, features, indices, spatial_shape, voxel_size, point_cloud_range, batch_size,
                  hash_size, map_table=None, gather_dict=None):
-        self.features = features            # (N, C), samples contiguous
-        self.indices = indices              # (N, 4) int32 [b, z, y, x]
+        self._lazy = None                   # (features_cap, indices_cap, count_dev) until first access
+        self._features = features           # (N, C), samples contiguous
+        self._indices = indices             # (N, 4) int32 [b, z, y, x]
         self.spatial_shape = spatial_shape  # [x, y, z]
         self.batch_size = batch_size
         self.voxel_size = voxel_size
@@ -39,6 +52,67 @@ class SparseTensor(object):
         self.gather_dict = gather_dict
         self._derived = {}                  # per-coordinate-set caches (counts, world xyz, geometry)
         self._map_table = map_table         # reference-contract hash table, built on first use
+
+    # A compress block produces one row per non-empty window; that count lives on the device.  The
+    # rows are kept at capacity and sliced to the exact count the first time somebody looks at
+    # .features / .indices (one 4-byte D2H copy), so the forward itself never waits for the host.
+    def set_lazy_rows(self, features_cap, indices_cap, count_dev):
+        self._lazy = (features_cap, indices_cap, count_dev)
+        self._features = self._indices = None
+        # the count is produced on the stream that is current now; whoever materialises later (maybe
+        # under another current stream) must wait for it
+        self._ready = torch.cuda.Event()
+        self._ready.record()
+        self._count_host = None
+
+    def prefetch_row_count(self):
+        """Start the 8-byte readback of (row count, dropped windows) without waiting for it, so that a
+        pipelined caller can queue the next frame before it looks at .features of this one."""
+        if self._lazy is not None and self._count_host is None:
+            host = _pinned_pair()
+            host[0:1].copy_(self._lazy[2], non_blocking=True)
+            dropped = getattr(self, "_window_overflow", None)
+            if dropped is not None:
+                host[1:2].copy_(dropped, non_blocking=True)
+            else:
+                host[1] = 0
+            self._count_host = host
+            self._ready = torch.cuda.Event()
+            self._ready.record()
+
+    def _materialise(self):
+        if self._lazy is not None:
+            f, i, count = self._lazy
+            self._ready.synchronize()
+            if self._count_host is not None:
+                n, n_dropped = int(self._count_host[0]), int(self._count_host[1])
+            else:
+                n = int(count.item())
+                dropped = getattr(self, "_window_overflow", None)
+                n_dropped = int(dropped.item()) if dropped is not None else 0
+            if n_dropped:
+                raise RuntimeError("compress block: %d windows exceed max_num_wins" % n_dropped)
+            self._features, self._indices, self._lazy = f[:n], i[:n], None
+
+    @property
+    def features(self):
+        self._materialise()
+        return self._features
+
+    @features.setter
+    def features(self, value):
+        self._materialise()
+        self._features = value
+
+    @property
+    def indices(self):
+        self._materialise()
+        return self._indices
+
+    @indices.setter
+    def indices(self, value):
+        self._materialise()
+        self._indices = value
 
     @property
     def map_table(self):
@@ -104,11 +178,14 @@ class SparseTensor(object):
 
     def dense(self, channels_first=True):
         x, y, z = (int(v) for v in self.spatial_shape)
-        feats = self.features.float().contiguous()
+        if self._lazy is not None:  # no host sync needed: the kernel reads the row count on the device
+            feats, idx, count = self._lazy
+        else:
+            feats, idx, count = self.features.float().contiguous(), self.indices, None
         C = feats.shape[1]
         out = torch.empty((self.batch_size, C, z, y, x), dtype=torch.float32, device=feats.device)
-        call("mssvt_dense_scatter", feats.shape[0], None, self.batch_size, C, z, y, x, ptr(feats),
-             ptr(self.indices), ptr(out), stream())
+        call("mssvt_dense_scatter", feats.shape[0], ptr(count), self.batch_size, C, z, y, x, ptr(feats),
+             ptr(idx), ptr(out), stream())
         return out if channels_first else out.permute(0, 2, 3, 4, 1).contiguous()
 
 
