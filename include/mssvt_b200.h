@@ -253,10 +253,13 @@ int mssvt_ffn(const void *shape, int shape_bytes, const float *params, int num_r
 
 /* The same FFN on the tcgen05 tensor cores: TF32 operands, fp32 accumulation in TMEM, LayerNorm and
  * the residual stream in fp32 (mssvt_b200/csrc/ffn_tc.cu).  Weights in nn.Linear layout, w1 [F][C],
- * w2 [C][F].  Supported shapes: C in {32, 64}, F % 32 == 0, F + C <= 512; -1 otherwise. */
+ * w2 [C][F].  Supported shapes: C in {32, 64}, F % 32 == 0, F + C <= 512; -1 otherwise.
+ * xn_next (optional, with next_ln_g / next_ln_b / next_eps): also writes LayerNorm(y) with the NEXT block's
+ * norm1 parameters, which saves that block its own LayerNorm pass over y. */
 int mssvt_ffn_tc(int C, int F, int mode, float eps, const float *ln_g, const float *ln_b, const float *w1,
                  const float *b1, const float *w2, const float *b2, int num_rows, const int *num_rows_dev,
-                 const float *x, const float *merged, const unsigned char *covered, float *y, void *stream);
+                 const float *x, const float *merged, const unsigned char *covered, float *y,
+                 const float *next_ln_g, const float *next_ln_b, float next_eps, float *xn_next, void *stream);
 
 /* SparseTensor.dense() (mssvt_utils.py:50-62): out (B, C, D, H, W), zero-filled then scattered */
 int mssvt_dense_scatter(int num_rows, const int *num_rows_dev, int batch_size, int C, int D, int H,

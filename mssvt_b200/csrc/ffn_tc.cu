@@ -31,13 +31,15 @@ struct FfnTcParams {
     const float *w1, *b1;   // [F][C], [F]   (nn.Linear layout)
     const float *w2, *b2;   // [C][F], [C]
     const float *ln_g, *ln_b;
+    const float *next_g, *next_b;  // optional: LayerNorm of the NEXT block (norm1), fused into the epilogue
+    float next_eps;
 };
 
 template <int C>
 __global__ void __launch_bounds__(TC_ROWS, 1)
 k_ffn_tc(FfnTcParams P, int n_cap, const int *__restrict__ n_dev, const float *__restrict__ x,
          const float *__restrict__ merged, const unsigned char *__restrict__ covered,
-         float *__restrict__ y) {
+         float *__restrict__ y, float *__restrict__ xn_next) {
     extern __shared__ __align__(128) char smem_raw[];
     const int F = P.F;
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -46,8 +48,8 @@ k_ffn_tc(FfnTcParams P, int n_cap, const int *__restrict__ n_dev, const float *_
     char *sW1 = sA + TC_ROWS * C * 4;             // [C/4][F][16 B]
     char *sW2 = sW1 + F * C * 4;                  // [F/4][C][16 B]
     char *sH = sW2 + C * F * 4;                   // [F/4][128][16 B]
-    float *s_vec = (float *)(sH + TC_ROWS * F * 4);  // ln_g[C], ln_b[C], b1[F], b2[C]
-    uint64_t *s_bar = (uint64_t *)(s_vec + 3 * C + F);  // 2 mbarriers (8-byte aligned: C, F even)
+    float *s_vec = (float *)(sH + TC_ROWS * F * 4);  // ln_g[C], ln_b[C], b1[F], b2[C], next_g[C], next_b[C]
+    uint64_t *s_bar = (uint64_t *)(s_vec + 5 * C + F);  // 2 mbarriers (8-byte aligned: C, F even)
     uint32_t *s_tmem = (uint32_t *)(s_bar + 2);
 
     stage_operand(P.w1, F, C, sW1);
@@ -56,9 +58,12 @@ k_ffn_tc(FfnTcParams P, int n_cap, const int *__restrict__ n_dev, const float *_
         s_vec[i] = __ldg(P.ln_g + i);
         s_vec[C + i] = __ldg(P.ln_b + i);
         s_vec[2 * C + F + i] = __ldg(P.b2 + i);
+        s_vec[3 * C + F + i] = P.next_g ? __ldg(P.next_g + i) : 1.f;
+        s_vec[4 * C + F + i] = P.next_b ? __ldg(P.next_b + i) : 0.f;
     }
     for (int i = tid; i < F; i += TC_ROWS) s_vec[2 * C + i] = __ldg(P.b1 + i);
     const float *s_g = s_vec, *s_b = s_vec + C, *s_b1 = s_vec + 2 * C, *s_b2 = s_vec + 2 * C + F;
+    const float *s_ng = s_vec + 3 * C + F, *s_nb = s_vec + 4 * C + F;
 
     const uint32_t bar1 = smem_u32(s_bar), bar2 = smem_u32(s_bar + 1);
     if (tid == 0) {
@@ -175,22 +180,34 @@ k_ffn_tc(FfnTcParams P, int n_cap, const int *__restrict__ n_dev, const float *_
         }
         mbar_wait(bar2, phase);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // ---- 5. y = u + D2 + b2
+        // ---- 5. y = u + D2 + b2 (in place in u), optionally xn_next = LayerNorm_next(y)
 #pragma unroll
         for (int c0 = 0; c0 < C; c0 += 32) {
             float d[32];
             tmem_ld32(tmem_d2 + lane_off + (uint32_t)c0, d);
-            if (live) {
-                float4 *yp = (float4 *)(y + (size_t)row * C + c0);
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    float4 v;
-                    v.x = u[c0 + 4 * q] + d[4 * q] + s_b2[c0 + 4 * q];
-                    v.y = u[c0 + 4 * q + 1] + d[4 * q + 1] + s_b2[c0 + 4 * q + 1];
-                    v.z = u[c0 + 4 * q + 2] + d[4 * q + 2] + s_b2[c0 + 4 * q + 2];
-                    v.w = u[c0 + 4 * q + 3] + d[4 * q + 3] + s_b2[c0 + 4 * q + 3];
-                    yp[q] = v;
-                }
+            for (int i = 0; i < 32; ++i) u[c0 + i] += d[i] + s_b2[c0 + i];
+        }
+        if (live) {
+            float4 *yp = (float4 *)(y + (size_t)row * C);
+#pragma unroll
+            for (int q = 0; q < C / 4; ++q) yp[q] = make_float4(u[4 * q], u[4 * q + 1], u[4 * q + 2], u[4 * q + 3]);
+            if (xn_next) {
+                float m2 = 0.f;
+#pragma unroll
+                for (int c = 0; c < C; ++c) m2 += u[c];
+                m2 *= (1.0f / C);
+                float v2 = 0.f;
+#pragma unroll
+                for (int c = 0; c < C; ++c) { const float dd = u[c] - m2; v2 = fmaf(dd, dd, v2); }
+                const float r2 = rsqrtf(v2 * (1.0f / C) + P.next_eps);
+                float4 *xp = (float4 *)(xn_next + (size_t)row * C);
+#pragma unroll
+                for (int q = 0; q < C / 4; ++q)
+                    xp[q] = make_float4((u[4 * q] - m2) * r2 * s_ng[4 * q] + s_nb[4 * q],
+                                        (u[4 * q + 1] - m2) * r2 * s_ng[4 * q + 1] + s_nb[4 * q + 1],
+                                        (u[4 * q + 2] - m2) * r2 * s_ng[4 * q + 2] + s_nb[4 * q + 2],
+                                        (u[4 * q + 3] - m2) * r2 * s_ng[4 * q + 3] + s_nb[4 * q + 3]);
             }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -210,24 +227,26 @@ extern "C" {
 // tiles fitting in shared memory; returns MSSVT_ERR_INVALID otherwise (callers then use mssvt_ffn).
 int mssvt_ffn_tc(int C, int F, int mode, float eps, const float *ln_g, const float *ln_b, const float *w1,
                  const float *b1, const float *w2, const float *b2, int num_rows, const int *num_rows_dev,
-                 const float *x, const float *merged, const unsigned char *covered, float *y, void *stream) {
+                 const float *x, const float *merged, const unsigned char *covered, float *y,
+                 const float *next_ln_g, const float *next_ln_b, float next_eps, float *xn_next, void *stream) {
     if ((C != 32 && C != 64) || F <= 0 || (F & 31) || F + C > 512 || num_rows < 0) return MSSVT_ERR_INVALID;
     if (num_rows == 0) return MSSVT_OK;
     if (!ln_g || !ln_b || !w1 || !b1 || !w2 || !b2 || !merged || !y || (mode == 1 && (!x || !covered)))
         return MSSVT_ERR_INVALID;
     size_t smem = (size_t)TC_ROWS * C * 4 + 2 * (size_t)F * C * 4 + (size_t)TC_ROWS * F * 4 +
-                  (size_t)(3 * C + F) * 4 + 2 * 8 + 16 + 128;
+                  (size_t)(5 * C + F) * 4 + 2 * 8 + 16 + 128;
     if (smem > 227 * 1024) return MSSVT_ERR_INVALID;
-    FfnTcParams P = {F, mode, eps, w1, b1, w2, b2, ln_g, ln_b};
+    if (xn_next && (!next_ln_g || !next_ln_b)) return MSSVT_ERR_INVALID;
+    FfnTcParams P = {F, mode, eps, w1, b1, w2, b2, ln_g, ln_b, next_ln_g, next_ln_b, next_eps};
     int tiles = (num_rows + TC_ROWS - 1) / TC_ROWS;
     int grid = tiles < MSSVT_NUM_SMS ? tiles : MSSVT_NUM_SMS;
     ++g_launches;
     if (C == 64) {
         cudaFuncSetAttribute(k_ffn_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_ffn_tc<64><<<grid, TC_ROWS, smem, (cudaStream_t)stream>>>(P, num_rows, num_rows_dev, x, merged, covered, y);
+        k_ffn_tc<64><<<grid, TC_ROWS, smem, (cudaStream_t)stream>>>(P, num_rows, num_rows_dev, x, merged, covered, y, xn_next);
     } else {
         cudaFuncSetAttribute(k_ffn_tc<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_ffn_tc<32><<<grid, TC_ROWS, smem, (cudaStream_t)stream>>>(P, num_rows, num_rows_dev, x, merged, covered, y);
+        k_ffn_tc<32><<<grid, TC_ROWS, smem, (cudaStream_t)stream>>>(P, num_rows, num_rows_dev, x, merged, covered, y, xn_next);
     }
     return check_launch();
 }

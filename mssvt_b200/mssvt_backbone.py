@@ -316,7 +316,10 @@ class MixedScaleSparseTransformerBlock(nn.Module):
         S.total_floats, S.eps = total, self.norm2.eps
         return S, buf
 
-    def _layernorm1(self, x):
+    def _layernorm1(self, x, sp_tensor=None):
+        pre = getattr(sp_tensor, "_xn_ready", None) if sp_tensor is not None else None
+        if pre is not None and pre[0] is x and pre[2] is self.norm1:
+            return pre[1]  # the previous block's FFN epilogue already applied this norm1
         xn = torch.empty_like(x)
         call("mssvt_layernorm", x.shape[0], None, x.shape[1], ptr(x), ptr(self.norm1.weight),
              ptr(self.norm1.bias), self.norm1.eps, ptr(xn), stream())
@@ -328,9 +331,18 @@ class MixedScaleSparseTransformerBlock(nn.Module):
         if (self.precision == "tf32" and S.C_out == 0 and S.C in (32, 64) and S.F % 32 == 0
                 and S.F + S.C <= 512 and (128 * S.C + 2 * S.F * S.C + 128 * S.F) * 4 < 220 * 1024):
             # tensor-core path: TF32 operands on tcgen05, fp32 accumulate / LayerNorm / residual
+            # the epilogue also applies the NEXT block's norm1 (if there is one of the same width), which
+            # saves that block a LayerNorm pass
+            nxt = self.__dict__.get("_next_norm1")
+            xn_next = None
+            if nxt is not None and nxt.normalized_shape == (c_out,) and n_dev is None:
+                xn_next = torch.empty_like(y)
             call("mssvt_ffn_tc", S.C, S.F, S.mode, self.norm2.eps, ptr(self.norm2.weight), ptr(self.norm2.bias),
                  ptr(self.linear1.weight), ptr(self.linear1.bias), ptr(self.linear2.weight),
-                 ptr(self.linear2.bias), n_rows, ptr(n_dev), ptr(x), ptr(merged), ptr(covered), ptr(y), stream())
+                 ptr(self.linear2.bias), n_rows, ptr(n_dev), ptr(x), ptr(merged), ptr(covered), ptr(y),
+                 ptr(nxt.weight) if xn_next is not None else None, ptr(nxt.bias) if xn_next is not None else None,
+                 nxt.eps if xn_next is not None else 0.0, ptr(xn_next), stream())
+            self.__dict__["_xn_for_next"] = (y, xn_next) if xn_next is not None else None
             return y
         call("mssvt_ffn", ctypes.byref(S), ctypes.sizeof(S), ptr(buf), n_rows, ptr(n_dev), ptr(x), ptr(merged),
              ptr(covered), ptr(y), stream())
@@ -342,7 +354,7 @@ class MixedScaleSparseTransformerBlock(nn.Module):
         if x.dtype != torch.float32 or not x.is_contiguous():
             x = x.float().contiguous()
         g = self.geometry(sp_tensor)
-        xn = self._layernorm1(x)
+        xn = self._layernorm1(x, sp_tensor)
         merged = torch.empty_like(x)  # only rows flagged in g["covered"] are written and read
         a = self.ms_attn
         if (self.precision == "tf32" and self.in_channels == 64 and a.scale_dims == [32, 32]
@@ -370,7 +382,10 @@ class MixedScaleSparseTransformerBlock(nn.Module):
                  ptr(g["k_row"]), ptr(g["k_mask"]), ptr(g["win1_row"]), ptr(g["nn_idx"]), ptr(g["nn_w"]),
                  ptr(merged), stream())
         F, fbuf = self._ffn_descriptor(mode=1)
+        self.__dict__["_xn_for_next"] = None
         sp_tensor.features = self._ffn(F, fbuf, x.shape[0], x, merged, g["covered"])
+        pre = self.__dict__.get("_xn_for_next")
+        sp_tensor._xn_ready = (pre[0], pre[1], self.__dict__["_next_norm1"]) if pre is not None else None
         sp_tensor.gather_dict = None
         return sp_tensor
 
@@ -395,7 +410,7 @@ class MixedScaleSparseTransformerCompressBlock(MixedScaleSparseTransformerBlock)
         call("mssvt_window_rows", sx, sy, sz, *self.win1_size, t['win1'].shape[0],
              n1, ptr(t['win1']), cap, ptr(total), ptr(win_list), ptr(cells), ptr(vals), ptr(v_start),
              ptr(k_row), stream())
-        xn = self._layernorm1(x)
+        xn = self._layernorm1(x, sp_tensor)
         attn = torch.empty((cap, self.in_channels), dtype=torch.float32, device=dev)
         a = self.ms_attn
         if (self.precision == "tf32" and self.in_channels == 64 and a.num_head_groups == 1
@@ -461,6 +476,8 @@ class MixedScaleSparseTransformer(nn.Module):
             else:
                 raise NotImplementedError
             self.backbone.append(block)
+        for blk, nxt in zip(self.backbone[:-1], self.backbone[1:]):
+            blk.__dict__["_next_norm1"] = nxt.norm1  # (plain dict entry: not a registered sub-module)
         self.num_point_features = model_cfg.NUM_OUTPUT_FEATURES
         self.set_precision(model_cfg.get('PRECISION', 'fp32'))
 

@@ -156,6 +156,15 @@ def test_tensor_core_ffn_matches_fp32_ffn(n_rows, mode):
         y32 = blk._ffn(S, buf, n_rows, x, merged, covered)
         blk.precision = "tf32"
         ytc = blk._ffn(S, buf, n_rows, x, merged, covered)
+        # fused epilogue: LayerNorm of the next block applied to y in the same kernel
+        nxt = torch.nn.LayerNorm(64).cuda()
+        nxt.weight.add_(0.3 * torch.randn_like(nxt.weight)); nxt.bias.add_(0.3 * torch.randn_like(nxt.bias))
+        blk.__dict__["_next_norm1"] = nxt
+        ytc2 = blk._ffn(S, buf, n_rows, x, merged, covered)
+        y_keep, xn_next = blk.__dict__["_xn_for_next"]
+        assert y_keep is ytc2 and torch.equal(ytc2, ytc)
+        want = torch.nn.functional.layer_norm(ytc2, (64,), nxt.weight, nxt.bias, nxt.eps)
+        assert (xn_next - want).abs().max().item() <= 1e-5 * want.abs().max().item()
     torch.cuda.synchronize()
     scale = ref.abs().max().item()
     assert (y32.double() - ref).abs().max().item() <= 1e-5 * scale
