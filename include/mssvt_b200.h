@@ -211,7 +211,7 @@ int mssvt_block_attention(const void *shape, int shape_bytes, const float *param
 /* The same step, task-parallel (one thread per query / distinct key / voxel over the whole frame) with
  * the K/V projection on the tcgen05 tensor cores (TF32 operands, fp32 everywhere else;
  * mssvt_b200/csrc/attention_tc.cu: 4 kernels).  Weights in nn.Module layout: pos_w [64][6], wq*/wp*
- * [32][32], wkv* [64][32] for head groups 0 / 1; rep_row / meta from mssvt_block_geometry; q_base =
+ * [32][32] for head groups 0 / 1, wkv* [64][32] packed by mssvt_pack_operand_tf32; rep_row / meta from mssvt_block_geometry; q_base =
  * mssvt_exclusive_scan(meta[:, 0]) (win_capacity + 1 ints), q_src = mssvt_query_src, vox_slot from the
  * geometry; scratch: 3 * num_voxels * 64 floats.
  * Supported: C = 64, two groups of 32 channels with 1, 2 or 4 heads each, nq <= 32,
@@ -235,7 +235,7 @@ int mssvt_compress_attention(const void *shape, int shape_bytes, const float *pa
 
 /* The same step, task-parallel with the second positional-embedding layer and the K/V projection on
  * the tcgen05 tensor cores (mssvt_b200/csrc/compress_tc.cu: 3 kernels).  Weights in nn.Module layout:
- * pos_w [64][6], pos2_w [64][64], wq / wp [64][64], wkv [128][64].  scratch: 2 * win_capacity * 64 floats.
+ * pos_w [64][6], wq / wp [64][64]; pos2_w [64][64] and wkv [128][64] packed by mssvt_pack_operand_tf32.  scratch: 2 * win_capacity * 64 floats.
  * Supported: C = 64, one head group with 1, 2, 4 or 8 heads, two-layer pos_proj, n1 <= 127; -1 otherwise. */
 int mssvt_compress_attention_tc(int C, int heads, int n1, float scale, const float *win_cell,
                                 const float *range_min, const float *pos_w, const float *pos_b,
@@ -251,13 +251,19 @@ int mssvt_ffn(const void *shape, int shape_bytes, const float *params, int num_r
               const int *num_rows_dev, const float *x, const float *merged,
               const unsigned char *covered, float *y, void *stream);
 
+/* Packs a weight matrix w [n_rows][k] (nn.Linear layout, out x in) for the tensor-core entry points:
+ * TF32 rounding + the K-major 8-row x 16-byte core-matrix layout tcgen05.mma reads from shared memory.
+ * packed: n_rows * k floats.  n_rows % 8 == 0 and k % 8 == 0.  Done once per weight (the kernels then
+ * stage it with plain asynchronous copies); arguments documented as "packed" below take this form. */
+int mssvt_pack_operand_tf32(const float *w, int n_rows, int k, float *packed, void *stream);
+
 /* The same FFN on the tcgen05 tensor cores: TF32 operands, fp32 accumulation in TMEM, LayerNorm and
- * the residual stream in fp32 (mssvt_b200/csrc/ffn_tc.cu).  Weights in nn.Linear layout, w1 [F][C],
- * w2 [C][F].  Supported shapes: C in {32, 64}, F % 32 == 0, F + C <= 512; -1 otherwise.
+ * the residual stream in fp32 (mssvt_b200/csrc/ffn_tc.cu).  w1 [F][C] and w2 [C][F] (nn.Linear layout) packed by
+ * mssvt_pack_operand_tf32.  Supported shapes: C in {32, 64}, F % 64 == 0, F + C <= 512; -1 otherwise.
  * xn_next (optional, with next_ln_g / next_ln_b / next_eps): also writes LayerNorm(y) with the NEXT block's
  * norm1 parameters, which saves that block its own LayerNorm pass over y. */
-int mssvt_ffn_tc(int C, int F, int mode, float eps, const float *ln_g, const float *ln_b, const float *w1,
-                 const float *b1, const float *w2, const float *b2, int num_rows, const int *num_rows_dev,
+int mssvt_ffn_tc(int C, int F, int mode, float eps, const float *ln_g, const float *ln_b, const float *w1_packed,
+                 const float *b1, const float *w2_packed, const float *b2, int num_rows, const int *num_rows_dev,
                  const float *x, const float *merged, const unsigned char *covered, float *y,
                  const float *next_ln_g, const float *next_ln_b, float next_eps, float *xn_next, void *stream);
 

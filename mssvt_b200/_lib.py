@@ -46,6 +46,7 @@ _SIGNATURES = {
     "mssvt_compress_attention": [P, I, P, I] + [P] * 6 + [P],
     "mssvt_compress_attention_tc": [I, I, I, F] + [P] * 12 + [I] + [P] * 7 + [P],
     "mssvt_ffn": [P, I, P, I, P, P, P, P, P, P],
+    "mssvt_pack_operand_tf32": [P, I, I, P, P],
     "mssvt_ffn_tc": [I, I, I, F] + [P] * 6 + [I, P, P, P, P, P, P, P, F, P, P],
     "mssvt_dense_scatter": [I, P, I, I, I, I, I, P, P, P, P],
     "mssvt_sizeof_attn_shape": [],

@@ -43,7 +43,7 @@ struct TcAttnParams {
     float win_cell[3], lo[3];
     const float *pos_w, *pos_b;                // [64][6], [64]   (Conv1d weight (64, 6, 1))
     const float *wq[2], *bq[2];                // [32][32], [32]
-    const float *wkv[2], *bkv[2];              // [64][32], [64]
+    const float *wkv[2], *bkv[2];              // [64][32] packed (mssvt_pack_operand_tf32), [64]
     const float *wp[2], *bp[2];                // [32][32], [32]
 };
 
@@ -171,8 +171,8 @@ k_tca_keys(TcAttnParams P, int win_cap, const int *__restrict__ win_count_total,
     uint64_t *sBar = (uint64_t *)(sTile + 8 + ((TCA_WB * 4 + 3 * (TCA_WB + 1) + 3 * TCA_THREADS + 8) & 1));
     uint32_t *sTmem = (uint32_t *)(sBar + 1);
 
-    stage_operand(P.wkv[0], 64, 32, sWkv);
-    stage_operand(P.wkv[1], 64, 32, sWkv + 64 * 32 * 4);
+    stage_packed(P.wkv[0], 64 * 32, sWkv);
+    stage_packed(P.wkv[1], 64 * 32, sWkv + 64 * 32 * 4);
     stage_pos_weights(P, sPos);
     for (int i = tid; i < 128; i += TCA_THREADS) sBkv[i] = __ldg(P.bkv[i >> 6] + (i & 63));
     const uint32_t bar = smem_u32(sBar);
@@ -279,6 +279,7 @@ k_tca_keys(TcAttnParams P, int win_cap, const int *__restrict__ win_count_total,
                     *(float4 *)(sA + (uint32_t)c4 * a_lbo + my_row_off) = o;
                 }
             }
+            stage_packed_wait();
             fence_async_smem();
             __syncthreads();
             // ---- D0 = A Wkv0^T (columns 0..63), D1 = A Wkv1^T (columns 64..127) on the tensor cores
@@ -462,7 +463,8 @@ using namespace mssvt;
 extern "C" {
 
 /* Tensor-core window attention of a two-window block (see the header of this file).  Weights in
- * their nn.Module layout: pos_w [64][6], wq/wp [32][32], wkv [64][32] per head group.  rep_row / meta:
+ * their nn.Module layout: pos_w [64][6], wq/wp [32][32] per head group; wkv [64][32] packed by
+ * mssvt_pack_operand_tf32.  rep_row / meta:
  * compact key lists of mssvt_block_geometry; q_base: mssvt_exclusive_scan of meta[:, 0] (win_capacity + 1
  * ints).  scratch: 3 * num_voxels * 64 floats (q, head outputs, projected rows of every real query).
  * Returns MSSVT_ERR_INVALID for shapes outside C = 64 / 2 x 32 channels / nq <= 32 / K <= 63 /

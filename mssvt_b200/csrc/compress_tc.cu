@@ -30,9 +30,9 @@ struct TccParams {
     float scale;
     float win_cell[3], lo[3];
     const float *pos_w, *pos_b;    // [64][6], [64]
-    const float *pos2_w, *pos2_b;  // [64][64], [64]
+    const float *pos2_w, *pos2_b;  // [64][64] packed (mssvt_pack_operand_tf32), [64]
     const float *wq, *bq;          // [64][64], [64]
-    const float *wkv, *bkv;        // [128][64], [128]
+    const float *wkv, *bkv;        // [128][64] packed, [128]
     const float *wp, *bp;          // [64][64], [64]
 };
 
@@ -132,8 +132,8 @@ k_tcc_keys(TccParams P, int win_cap, const int *__restrict__ win_count_total, co
     uint64_t *sBar = (uint64_t *)(sTile + 4 + ((2 * TCC_WB + 1 + 2 * TCC_THREADS + 4) & 1));
     uint32_t *sTmem = (uint32_t *)(sBar + 1);
 
-    stage_operand(P.pos2_w, 64, 64, sW2);
-    stage_operand(P.wkv, 128, 64, sWkv);
+    stage_packed(P.pos2_w, 64 * 64, sW2);
+    stage_packed(P.wkv, 128 * 64, sWkv);
     for (int i = tid; i < 64 * 8; i += TCC_THREADS) {
         const int c = i >> 3, k = i & 7;
         sPos[i] = k < 6 ? __ldg(P.pos_w + c * 6 + k) : k == 6 ? __ldg(P.pos_b + c) : 0.f;
@@ -233,6 +233,7 @@ k_tcc_keys(TccParams P, int win_cap, const int *__restrict__ win_count_total, co
                     *(float4 *)(sA + (uint32_t)c4 * a_lbo + my_row_off) = make_float4(o[0], o[1], o[2], o[3]);
                 }
             }
+            stage_packed_wait();
             fence_async_smem();
             __syncthreads();
             if (tid == 0) {  // D1 = A1 W2^T
@@ -385,7 +386,8 @@ using namespace mssvt;
 extern "C" {
 
 /* Tensor-core attention of a one-window (compress) block (see the header of this file).  Weights in
- * nn.Module layout: pos_w [64][6], pos2_w [64][64], wq / wp [64][64], wkv [128][64].  k_row: (cap, n1)
+ * nn.Module layout: pos_w [64][6], wq / wp [64][64]; pos2_w [64][64] and wkv [128][64] packed by
+ * mssvt_pack_operand_tf32.  k_row: (cap, n1)
  * global rows from mssvt_window_rows.  scratch: 2 * win_capacity * 64 floats.  out: (cap, 64).
  * Supported: C = 64, one head group with 1, 2, 4 or 8 heads, n1 <= 127; -1 otherwise. */
 int mssvt_compress_attention_tc(int C, int heads, int n1, float scale, const float *win_cell,

@@ -3,17 +3,20 @@
 //   y = u + W2 relu(W1 LN(u) + b1) + b2         mssvt_backbone.py:337-340, 384-385
 //   u = covered ? merged + x : 2 x  (two-window block)   |   u = merged  (compress block)
 //
-// One CTA of 128 threads owns a tile of 128 rows; thread t = row t = TMEM lane t.
+// One CTA of 256 threads owns a tile of 128 rows; threads t and t + 128 share row t = TMEM lane t
+// (one half of the channels each; row sums for the LayerNorms are exchanged through shared memory).
 //   1. each thread loads its row, builds u, LayerNorms it in registers and stores it, rounded to
 //      TF32, as the A operand in the canonical K-major no-swizzle UMMA layout
 //      (8-row x 16-byte core matrices: byte = chunk * LBO + (row / 8) * 128 + (row % 8) * 16);
 //   2. one thread issues C/8 tcgen05.mma.kind::tf32 (M = 128, N = F) -> D1 in TMEM columns [0, F);
-//   3. tcgen05.ld brings each row's D1 back, bias + ReLU, TF32 round, store as the A operand of the
-//      second GEMM (same layout, K = F);
-//   4. F/8 tcgen05.mma (M = 128, N = C) -> D2 in TMEM columns [F, F + C);
+//   3. tcgen05.ld brings each row's D1 back, bias + ReLU, TF32 round, tcgen05.st writes the hidden row
+//      back IN PLACE: TMEM columns [0, F) now hold the A operand of the second GEMM (lane = row,
+//      column = k), so the 128 x F hidden tile never touches shared memory;
+//   4. F/8 tcgen05.mma with A from TMEM (M = 128, N = C) -> D2 in TMEM columns [F, F + C);
 //   5. tcgen05.ld, + b2 + u (still in registers), row store.
 // W1 / W2 (nn.Linear [out][in] = N x K, K-major) sit in shared memory in the same canonical
-// layout for the whole kernel.  Completion of the async MMAs is tracked with tcgen05.commit on
+// layout for the whole kernel.  ~98 KB of shared memory and 256 TMEM columns per CTA: two CTAs per
+// SM, so one tile's loads and epilogue overlap the other's MMAs.  Completion of the async MMAs is tracked with tcgen05.commit on
 // an mbarrier; generic-proxy shared stores are made visible with fence.proxy.async.
 //
 // Precision: TF32 operands (10-bit mantissa, round-to-nearest), fp32 accumulation in TMEM; the
@@ -24,46 +27,50 @@
 namespace mssvt {
 
 #define TC_ROWS 128
+#define TC_THREADS 256   // two threads per row: warps w and w + 4 reach the same 32 TMEM lanes
 
 struct FfnTcParams {
     int F, mode;            // hidden width; 0: u = merged, 1: u = covered ? merged + x : 2 x
     float eps;
-    const float *w1, *b1;   // [F][C], [F]   (nn.Linear layout)
-    const float *w2, *b2;   // [C][F], [C]
+    const float *w1, *b1;   // [F][C] packed (mssvt_pack_operand_tf32), [F]
+    const float *w2, *b2;   // [C][F] packed, [C]
     const float *ln_g, *ln_b;
     const float *next_g, *next_b;  // optional: LayerNorm of the NEXT block (norm1), fused into the epilogue
     float next_eps;
 };
 
 template <int C>
-__global__ void __launch_bounds__(TC_ROWS, 1)
+__global__ void __launch_bounds__(TC_THREADS, 2)
 k_ffn_tc(FfnTcParams P, int n_cap, const int *__restrict__ n_dev, const float *__restrict__ x,
          const float *__restrict__ merged, const unsigned char *__restrict__ covered,
          float *__restrict__ y, float *__restrict__ xn_next) {
+    constexpr int CH = C / 2;  // channels per thread: two threads (warps w and w + 4) share a row
     extern __shared__ __align__(128) char smem_raw[];
-    const int F = P.F;
+    const int F = P.F, FH = F / 2;
     const int tid = threadIdx.x, warp = tid >> 5;
+    const int r = tid & (TC_ROWS - 1), half = tid >> 7;
     // carve shared memory
     char *sA = smem_raw;                          // [C/4][128][16 B]
     char *sW1 = sA + TC_ROWS * C * 4;             // [C/4][F][16 B]
     char *sW2 = sW1 + F * C * 4;                  // [F/4][C][16 B]
-    char *sH = sW2 + C * F * 4;                   // [F/4][128][16 B]
-    float *s_vec = (float *)(sH + TC_ROWS * F * 4);  // ln_g[C], ln_b[C], b1[F], b2[C], next_g[C], next_b[C]
-    uint64_t *s_bar = (uint64_t *)(s_vec + 5 * C + F);  // 2 mbarriers (8-byte aligned: C, F even)
+    float *s_vec = (float *)(sW2 + C * F * 4);    // ln_g[C], ln_b[C], b1[F], b2[C], next_g[C], next_b[C]
+    float *s_red = s_vec + 5 * C + F;             // [4][2][128] partial row sums of the two half-row threads
+    uint64_t *s_bar = (uint64_t *)(s_red + 8 * TC_ROWS);  // 2 mbarriers (8-byte aligned: C, F even)
     uint32_t *s_tmem = (uint32_t *)(s_bar + 2);
 
-    stage_operand(P.w1, F, C, sW1);
-    stage_operand(P.w2, C, F, sW2);
-    for (int i = tid; i < C; i += TC_ROWS) {
+    stage_packed(P.w1, F * C, sW1);
+    stage_packed(P.w2, C * F, sW2);
+    for (int i = tid; i < C; i += TC_THREADS) {
         s_vec[i] = __ldg(P.ln_g + i);
         s_vec[C + i] = __ldg(P.ln_b + i);
         s_vec[2 * C + F + i] = __ldg(P.b2 + i);
         s_vec[3 * C + F + i] = P.next_g ? __ldg(P.next_g + i) : 1.f;
         s_vec[4 * C + F + i] = P.next_b ? __ldg(P.next_b + i) : 0.f;
     }
-    for (int i = tid; i < F; i += TC_ROWS) s_vec[2 * C + i] = __ldg(P.b1 + i);
-    const float *s_g = s_vec, *s_b = s_vec + C, *s_b1 = s_vec + 2 * C, *s_b2 = s_vec + 2 * C + F;
-    const float *s_ng = s_vec + 3 * C + F, *s_nb = s_vec + 4 * C + F;
+    for (int i = tid; i < F; i += TC_THREADS) s_vec[2 * C + i] = __ldg(P.b1 + i);
+    const float *s_g = s_vec + half * CH, *s_b = s_vec + C + half * CH, *s_b1 = s_vec + 2 * C + half * FH;
+    const float *s_b2 = s_vec + 2 * C + F + half * CH;
+    const float *s_ng = s_vec + 3 * C + F + half * CH, *s_nb = s_vec + 4 * C + F + half * CH;
 
     const uint32_t bar1 = smem_u32(s_bar), bar2 = smem_u32(s_bar + 1);
     if (tid == 0) {
@@ -71,7 +78,7 @@ k_ffn_tc(FfnTcParams P, int n_cap, const int *__restrict__ n_dev, const float *_
         mbar_init(bar2, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    // TMEM: F columns for D1 + C columns for D2, rounded up to a power of two >= 32
+    // TMEM: F columns for D1 / hidden + C columns for D2, rounded up to a power of two >= 32
     uint32_t tmem_cols = 32;
     while (tmem_cols < (uint32_t)(F + C)) tmem_cols <<= 1;
     if (warp == 0) tmem_alloc(smem_u32(s_tmem), tmem_cols);
@@ -81,35 +88,37 @@ k_ffn_tc(FfnTcParams P, int n_cap, const int *__restrict__ n_dev, const float *_
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *s_tmem;
     const uint32_t tmem_d1 = tmem_base, tmem_d2 = tmem_base + (uint32_t)F;
-    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;  // this warp's quarter of the 128 lanes
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;  // a warp reaches TMEM lanes 32 (w % 4) ...
 
     const uint32_t idesc1 = umma_idesc_tf32(TC_ROWS, F), idesc2 = umma_idesc_tf32(TC_ROWS, C);
     const uint32_t a_lbo = TC_ROWS * 16, w1_lbo = (uint32_t)F * 16, w2_lbo = (uint32_t)C * 16;
-    const uint32_t sA_u = smem_u32(sA), sW1_u = smem_u32(sW1), sW2_u = smem_u32(sW2), sH_u = smem_u32(sH);
+    const uint32_t sA_u = smem_u32(sA), sW1_u = smem_u32(sW1), sW2_u = smem_u32(sW2);
 
     const int n = n_dev ? min(n_cap, __ldg(n_dev)) : n_cap;
     const int tiles = (n + TC_ROWS - 1) / TC_ROWS;
     uint32_t phase = 0;
-    const uint32_t my_row_off = (uint32_t)(tid >> 3) * 128u + (uint32_t)(tid & 7) * 16u;
+    const uint32_t my_row_off = (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u;
+    float *red_mine = s_red + half * TC_ROWS + r;
+    const float *red_other = s_red + (half ^ 1) * TC_ROWS + r;
 
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, phase ^= 1u) {
-        const int row = tile * TC_ROWS + tid;
+        const int row = tile * TC_ROWS + r;
         const bool live = row < n;
-        // ---- 1. residual stream u (registers), LayerNorm, A operand
-        float u[C];
+        // ---- 1. this thread's half of the residual row u (registers), LayerNorm, A operand
+        float u[CH];
         if (live) {
-            const float4 *mp = (const float4 *)(merged + (size_t)row * C);
+            const float4 *mp = (const float4 *)(merged + (size_t)row * C + half * CH);
             if (P.mode == 0) {
 #pragma unroll
-                for (int c = 0; c < C / 4; ++c) {
+                for (int c = 0; c < CH / 4; ++c) {
                     float4 v = __ldg(mp + c);
                     u[4 * c] = v.x; u[4 * c + 1] = v.y; u[4 * c + 2] = v.z; u[4 * c + 3] = v.w;
                 }
             } else {
-                const float4 *xp = (const float4 *)(x + (size_t)row * C);
+                const float4 *xp = (const float4 *)(x + (size_t)row * C + half * CH);
                 const bool cov = covered[row] != 0;
 #pragma unroll
-                for (int c = 0; c < C / 4; ++c) {
+                for (int c = 0; c < CH / 4; ++c) {
                     float4 v = __ldg(xp + c);
                     float4 m = cov ? __ldg(mp + c) : v;
                     u[4 * c] = m.x + v.x; u[4 * c + 1] = m.y + v.y; u[4 * c + 2] = m.z + v.z; u[4 * c + 3] = m.w + v.w;
@@ -117,25 +126,30 @@ k_ffn_tc(FfnTcParams P, int n_cap, const int *__restrict__ n_dev, const float *_
             }
         } else {
 #pragma unroll
-            for (int c = 0; c < C; ++c) u[c] = 0.f;
+            for (int c = 0; c < CH; ++c) u[c] = 0.f;
         }
-        float mean = 0.f;
+        float part = 0.f;
 #pragma unroll
-        for (int c = 0; c < C; ++c) mean += u[c];
-        mean *= (1.0f / C);
-        float var = 0.f;
+        for (int c = 0; c < CH; ++c) part += u[c];
+        red_mine[0] = part;
+        __syncthreads();
+        const float mean = (part + red_other[0]) * (1.0f / C);
+        part = 0.f;
 #pragma unroll
-        for (int c = 0; c < C; ++c) { const float d = u[c] - mean; var = fmaf(d, d, var); }
-        const float rstd = rsqrtf(var * (1.0f / C) + P.eps);
+        for (int c = 0; c < CH; ++c) { const float d = u[c] - mean; part = fmaf(d, d, part); }
+        red_mine[2 * TC_ROWS] = part;
+        __syncthreads();
+        const float rstd = rsqrtf((part + red_other[2 * TC_ROWS]) * (1.0f / C) + P.eps);
 #pragma unroll
-        for (int c = 0; c < C / 4; ++c) {
+        for (int c = 0; c < CH / 4; ++c) {
             float4 v;
             v.x = to_tf32((u[4 * c] - mean) * rstd * s_g[4 * c] + s_b[4 * c]);
             v.y = to_tf32((u[4 * c + 1] - mean) * rstd * s_g[4 * c + 1] + s_b[4 * c + 1]);
             v.z = to_tf32((u[4 * c + 2] - mean) * rstd * s_g[4 * c + 2] + s_b[4 * c + 2]);
             v.w = to_tf32((u[4 * c + 3] - mean) * rstd * s_g[4 * c + 3] + s_b[4 * c + 3]);
-            *(float4 *)(sA + (uint32_t)c * a_lbo + my_row_off) = v;
+            *(float4 *)(sA + (uint32_t)(half * (CH / 4) + c) * a_lbo + my_row_off) = v;
         }
+        stage_packed_wait();  // (first tile: the weight copies overlapped the loads and the LayerNorm)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
         // ---- 2. D1[128 x F] = A[128 x C] . W1^T, one K = 8 slice (two 16-byte chunks) per MMA
@@ -151,59 +165,64 @@ k_ffn_tc(FfnTcParams P, int n_cap, const int *__restrict__ n_dev, const float *_
         }
         mbar_wait(bar1, phase);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // ---- 3. hidden = relu(D1 + b1) -> A operand of the second GEMM
-        for (int c0 = 0; c0 < F; c0 += 32) {
+        // ---- 3. hidden = relu(D1 + b1), written back over D1: the A operand of the second GEMM
+        for (int c0 = 0; c0 < FH; c0 += 32) {
             float d[32];
-            tmem_ld32(tmem_d1 + lane_off + (uint32_t)c0, d);
+            const uint32_t col = tmem_d1 + lane_off + (uint32_t)(half * FH + c0);
+            tmem_ld32(col, d);
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                float4 v;
-                v.x = to_tf32(fmaxf(d[4 * q] + s_b1[c0 + 4 * q], 0.f));
-                v.y = to_tf32(fmaxf(d[4 * q + 1] + s_b1[c0 + 4 * q + 1], 0.f));
-                v.z = to_tf32(fmaxf(d[4 * q + 2] + s_b1[c0 + 4 * q + 2], 0.f));
-                v.w = to_tf32(fmaxf(d[4 * q + 3] + s_b1[c0 + 4 * q + 3], 0.f));
-                *(float4 *)(sH + (uint32_t)(c0 / 4 + q) * a_lbo + my_row_off) = v;
-            }
+            for (int i = 0; i < 32; ++i) d[i] = to_tf32(fmaxf(d[i] + s_b1[c0 + i], 0.f));
+            tmem_st32(col, d);
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        tmem_st_wait();
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
-        // ---- 4. D2[128 x C] = H[128 x F] . W2^T
+        // ---- 4. D2[128 x C] = H[128 x F] . W2^T, H read from TMEM
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             for (int k = 0; k < F / 8; ++k) {
-                const uint64_t da = umma_smem_desc(sH_u + (uint32_t)k * 2u * a_lbo, a_lbo, 128);
                 const uint64_t db = umma_smem_desc(sW2_u + (uint32_t)k * 2u * w2_lbo, w2_lbo, 128);
-                umma_tf32(tmem_d2, da, db, idesc2, k > 0 ? 1u : 0u);
+                umma_tf32_ts(tmem_d2, tmem_d1 + (uint32_t)k * 8u, db, idesc2, k > 0 ? 1u : 0u);
             }
             umma_commit(bar2);
         }
         mbar_wait(bar2, phase);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         // ---- 5. y = u + D2 + b2 (in place in u), optionally xn_next = LayerNorm_next(y)
-#pragma unroll
-        for (int c0 = 0; c0 < C; c0 += 32) {
+        {
             float d[32];
-            tmem_ld32(tmem_d2 + lane_off + (uint32_t)c0, d);
+            if constexpr (CH == 32) {
+                tmem_ld32(tmem_d2 + lane_off + (uint32_t)(half * 32), d);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) u[c0 + i] += d[i] + s_b2[c0 + i];
+                for (int i = 0; i < CH; ++i) u[i] += d[i] + s_b2[i];
+            } else {  // C = 32: both threads of a row read all 32 columns and keep their 16
+                tmem_ld32(tmem_d2 + lane_off, d);
+#pragma unroll
+                for (int i = 0; i < CH; ++i) u[i] += (half ? d[CH + i] : d[i]) + s_b2[i];
+            }
         }
         if (live) {
-            float4 *yp = (float4 *)(y + (size_t)row * C);
+            float4 *yp = (float4 *)(y + (size_t)row * C + half * CH);
 #pragma unroll
-            for (int q = 0; q < C / 4; ++q) yp[q] = make_float4(u[4 * q], u[4 * q + 1], u[4 * q + 2], u[4 * q + 3]);
-            if (xn_next) {
-                float m2 = 0.f;
+            for (int q = 0; q < CH / 4; ++q) yp[q] = make_float4(u[4 * q], u[4 * q + 1], u[4 * q + 2], u[4 * q + 3]);
+        }
+        if (xn_next) {  // (uniform over the CTA)
+            part = 0.f;
 #pragma unroll
-                for (int c = 0; c < C; ++c) m2 += u[c];
-                m2 *= (1.0f / C);
-                float v2 = 0.f;
+            for (int c = 0; c < CH; ++c) part += u[c];
+            red_mine[4 * TC_ROWS] = part;
+            __syncthreads();
+            const float m2 = (part + red_other[4 * TC_ROWS]) * (1.0f / C);
+            part = 0.f;
 #pragma unroll
-                for (int c = 0; c < C; ++c) { const float dd = u[c] - m2; v2 = fmaf(dd, dd, v2); }
-                const float r2 = rsqrtf(v2 * (1.0f / C) + P.next_eps);
-                float4 *xp = (float4 *)(xn_next + (size_t)row * C);
+            for (int c = 0; c < CH; ++c) { const float dd = u[c] - m2; part = fmaf(dd, dd, part); }
+            red_mine[6 * TC_ROWS] = part;
+            __syncthreads();
+            const float r2 = rsqrtf((part + red_other[6 * TC_ROWS]) * (1.0f / C) + P.next_eps);
+            if (live) {
+                float4 *xp = (float4 *)(xn_next + (size_t)row * C + half * CH);
 #pragma unroll
-                for (int q = 0; q < C / 4; ++q)
+                for (int q = 0; q < CH / 4; ++q)
                     xp[q] = make_float4((u[4 * q] - m2) * r2 * s_ng[4 * q] + s_nb[4 * q],
                                         (u[4 * q + 1] - m2) * r2 * s_ng[4 * q + 1] + s_nb[4 * q + 1],
                                         (u[4 * q + 2] - m2) * r2 * s_ng[4 * q + 2] + s_nb[4 * q + 2],
@@ -216,37 +235,63 @@ k_ffn_tc(FfnTcParams P, int n_cap, const int *__restrict__ n_dev, const float *_
     if (warp == 0) tmem_dealloc(tmem_base, tmem_cols);
 }
 
+// row-major [n_rows][k] fp32 -> canonical K-major UMMA layout (8-row x 16-byte core matrices), TF32-rounded
+__global__ void k_pack_operand_tf32(const float *__restrict__ src, int n_rows, int k, float *__restrict__ dst) {
+    const int chunks = k >> 2;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_rows * chunks) return;
+    const int n = e / chunks, c = e - n * chunks;
+    float4 v = __ldg((const float4 *)(src + (size_t)n * k) + c);
+    v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w);
+    *(float4 *)((char *)dst + (size_t)c * n_rows * 16 + (n >> 3) * 128 + (n & 7) * 16) = v;
+}
+
 }  // namespace mssvt
 
 using namespace mssvt;
 
 extern "C" {
 
-// Tensor-core FFN (TF32 operands, fp32 accumulate).  Weights in nn.Linear layout: w1 [F][C],
-// w2 [C][F].  Supported: C in {32, 64}, F a multiple of 32 with F + C <= 512 and the operand
+// Packs a weight matrix w [n_rows][k] (nn.Linear layout: out x in) for the tensor-core kernels: TF32
+// rounding + the K-major core-matrix layout tcgen05.mma reads from shared memory.  Done once per
+// weight; the *_tc entry points take the packed copies.  n_rows % 8 == 0, k % 8 == 0.
+int mssvt_pack_operand_tf32(const float *w, int n_rows, int k, float *packed, void *stream) {
+    if (!w || !packed || n_rows <= 0 || k <= 0 || (n_rows & 7) || (k & 7)) return MSSVT_ERR_INVALID;
+    const int n = n_rows * (k >> 2);
+    ++g_launches;
+    k_pack_operand_tf32<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, n_rows, k, packed);
+    return check_launch();
+}
+
+// Tensor-core FFN (TF32 operands, fp32 accumulate).  w1 [F][C] and w2 [C][F] (nn.Linear layout) packed
+// by mssvt_pack_operand_tf32.  Supported: C in {32, 64}, F a multiple of 64 with F + C <= 512 and the operand
 // tiles fitting in shared memory; returns MSSVT_ERR_INVALID otherwise (callers then use mssvt_ffn).
 int mssvt_ffn_tc(int C, int F, int mode, float eps, const float *ln_g, const float *ln_b, const float *w1,
                  const float *b1, const float *w2, const float *b2, int num_rows, const int *num_rows_dev,
                  const float *x, const float *merged, const unsigned char *covered, float *y,
                  const float *next_ln_g, const float *next_ln_b, float next_eps, float *xn_next, void *stream) {
-    if ((C != 32 && C != 64) || F <= 0 || (F & 31) || F + C > 512 || num_rows < 0) return MSSVT_ERR_INVALID;
+    if ((C != 32 && C != 64) || F <= 0 || (F & 63) || F + C > 512 || num_rows < 0) return MSSVT_ERR_INVALID;
     if (num_rows == 0) return MSSVT_OK;
     if (!ln_g || !ln_b || !w1 || !b1 || !w2 || !b2 || !merged || !y || (mode == 1 && (!x || !covered)))
         return MSSVT_ERR_INVALID;
-    size_t smem = (size_t)TC_ROWS * C * 4 + 2 * (size_t)F * C * 4 + (size_t)TC_ROWS * F * 4 +
-                  (size_t)(5 * C + F) * 4 + 2 * 8 + 16 + 128;
+    size_t smem = (size_t)TC_ROWS * C * 4 + 2 * (size_t)F * C * 4 + (size_t)(5 * C + F + 8 * TC_ROWS) * 4 + 2 * 8 + 16 + 128;
     if (smem > 227 * 1024) return MSSVT_ERR_INVALID;
     if (xn_next && (!next_ln_g || !next_ln_b)) return MSSVT_ERR_INVALID;
     FfnTcParams P = {F, mode, eps, w1, b1, w2, b2, ln_g, ln_b, next_ln_g, next_ln_b, next_eps};
     int tiles = (num_rows + TC_ROWS - 1) / TC_ROWS;
-    int grid = tiles < MSSVT_NUM_SMS ? tiles : MSSVT_NUM_SMS;
+    int tmem_cols = 32;
+    while (tmem_cols < F + C) tmem_cols <<= 1;
+    int per_sm = (int)(227 * 1024 / (smem + 1024));
+    if (per_sm > 512 / tmem_cols) per_sm = 512 / tmem_cols;
+    per_sm = per_sm > 2 ? 2 : per_sm < 1 ? 1 : per_sm;
+    int grid = tiles < MSSVT_NUM_SMS * per_sm ? tiles : MSSVT_NUM_SMS * per_sm;
     ++g_launches;
     if (C == 64) {
         cudaFuncSetAttribute(k_ffn_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_ffn_tc<64><<<grid, TC_ROWS, smem, (cudaStream_t)stream>>>(P, num_rows, num_rows_dev, x, merged, covered, y, xn_next);
+        k_ffn_tc<64><<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(P, num_rows, num_rows_dev, x, merged, covered, y, xn_next);
     } else {
         cudaFuncSetAttribute(k_ffn_tc<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_ffn_tc<32><<<grid, TC_ROWS, smem, (cudaStream_t)stream>>>(P, num_rows, num_rows_dev, x, merged, covered, y, xn_next);
+        k_ffn_tc<32><<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(P, num_rows, num_rows_dev, x, merged, covered, y, xn_next);
     }
     return check_launch();
 }

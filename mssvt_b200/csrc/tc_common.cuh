@@ -37,6 +37,18 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint
         : "memory");
 }
 
+// A operand read from TMEM (lane = row, one 32-bit column per K element), B from shared memory
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
 __device__ __forceinline__ void umma_commit(uint32_t mbar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar)
                  : "memory");
@@ -105,17 +117,35 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// copy a row-major [n_rows][k] fp32 matrix (global) into the canonical K-major layout, TF32-rounded
-__device__ __forceinline__ void stage_operand(const float *__restrict__ src, int n_rows, int k, char *dst) {
-    const int chunks = k >> 2;
-    const uint32_t lbo = (uint32_t)n_rows * 16u;
-    for (int e = threadIdx.x; e < n_rows * chunks; e += blockDim.x) {
-        const int n = e / chunks, c = e - n * chunks;
-        float4 v = __ldg((const float4 *)(src + (size_t)n * k) + c);
-        v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w);
-        *(float4 *)(dst + (size_t)c * lbo + (n >> 3) * 128 + (n & 7) * 16) = v;
-    }
+// store 32 consecutive TMEM columns of this thread's lane (completion: tmem_st_wait)
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float *v) {
+    __syncwarp();
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n" ::"r"(taddr),
+        "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+        "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+        "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+        "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])),
+        "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])),
+        "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])),
+        "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])),
+        "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
+        : "memory");
 }
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// Weight operands are packed ONCE (mssvt_pack_operand_tf32: canonical K-major layout, TF32-rounded) and
+// then only copied: asynchronous 16-byte copies global -> shared, no registers, no per-CTA conversion.
+// Call stage_packed_wait() before the fence.proxy.async / barrier that precedes the first MMA.
+__device__ __forceinline__ void stage_packed(const float *__restrict__ packed, int n_floats, char *dst) {
+    const uint32_t d = smem_u32(dst);
+    for (int o = threadIdx.x * 4; o < n_floats; o += blockDim.x * 4)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + (uint32_t)o * 4u), "l"(packed + o)
+                     : "memory");
+}
+__device__ __forceinline__ void stage_packed_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t cols) {  // one full warp

@@ -299,6 +299,20 @@ class MixedScaleSparseTransformerBlock(nn.Module):
             S.lo[i] = sp_tensor.point_cloud_range[i]
         return S, buf
 
+    def _packed(self, weight):
+        """tensor-core operand form of an nn.Linear / 1x1 Conv1d weight (TF32, K-major core matrices),
+        packed once and cached until the parameter is modified or moved"""
+        cache = self.__dict__.setdefault("_packed_ops", {})
+        key = id(weight)
+        tag = (weight.data_ptr(), weight._version)
+        hit = cache.get(key)
+        if hit is None or hit[0] != tag:
+            w2d = weight.detach().reshape(weight.shape[0], -1).float().contiguous()
+            out = torch.empty_like(w2d)
+            call("mssvt_pack_operand_tf32", ptr(w2d), w2d.shape[0], w2d.shape[1], ptr(out), stream())
+            hit = cache[key] = (tag, out)
+        return hit[1]
+
     def _ffn_descriptor(self, mode):
         named = [("ln_g", self.norm2.weight), ("ln_b", self.norm2.bias),
                  ("w1", self.linear1.weight.t()), ("b1", self.linear1.bias),
@@ -328,7 +342,7 @@ class MixedScaleSparseTransformerBlock(nn.Module):
     def _ffn(self, S, buf, n_rows, x, merged, covered, n_dev=None):
         c_out = S.C_out if S.C_out else S.C
         y = torch.empty((n_rows, c_out), dtype=torch.float32, device=merged.device)
-        if (self.precision == "tf32" and S.C_out == 0 and S.C in (32, 64) and S.F % 32 == 0
+        if (self.precision == "tf32" and S.C_out == 0 and S.C in (32, 64) and S.F % 64 == 0
                 and S.F + S.C <= 512 and (128 * S.C + 2 * S.F * S.C + 128 * S.F) * 4 < 220 * 1024):
             # tensor-core path: TF32 operands on tcgen05, fp32 accumulate / LayerNorm / residual
             # the epilogue also applies the NEXT block's norm1 (if there is one of the same width), which
@@ -338,8 +352,9 @@ class MixedScaleSparseTransformerBlock(nn.Module):
             if nxt is not None and nxt.normalized_shape == (c_out,) and n_dev is None:
                 xn_next = torch.empty_like(y)
             call("mssvt_ffn_tc", S.C, S.F, S.mode, self.norm2.eps, ptr(self.norm2.weight), ptr(self.norm2.bias),
-                 ptr(self.linear1.weight), ptr(self.linear1.bias), ptr(self.linear2.weight),
-                 ptr(self.linear2.bias), n_rows, ptr(n_dev), ptr(x), ptr(merged), ptr(covered), ptr(y),
+                 ptr(self._packed(self.linear1.weight)), ptr(self.linear1.bias),
+                 ptr(self._packed(self.linear2.weight)), ptr(self.linear2.bias), n_rows, ptr(n_dev), ptr(x),
+                 ptr(merged), ptr(covered), ptr(y),
                  ptr(nxt.weight) if xn_next is not None else None, ptr(nxt.bias) if xn_next is not None else None,
                  nxt.eps if xn_next is not None else 0.0, ptr(xn_next), stream())
             self.__dict__["_xn_for_next"] = (y, xn_next) if xn_next is not None else None
@@ -366,9 +381,10 @@ class MixedScaleSparseTransformerBlock(nn.Module):
                  int(bool(self.use_feature_interpolation)), a.scale,
                  host_floats([vs[i] * self.win1_size[i] for i in range(3)]),
                  host_floats(sp_tensor.point_cloud_range[0:3]), ptr(self.pos_proj[0].weight),
-                 ptr(self.pos_proj[0].bias), ptr(a.to_qs[0].weight), ptr(a.to_qs[0].bias), ptr(a.to_kvs[0].weight),
+                 ptr(self.pos_proj[0].bias), ptr(a.to_qs[0].weight), ptr(a.to_qs[0].bias),
+                 ptr(self._packed(a.to_kvs[0].weight)),
                  ptr(a.to_kvs[0].bias), ptr(a.projs[0].weight), ptr(a.projs[0].bias), ptr(a.to_qs[1].weight),
-                 ptr(a.to_qs[1].bias), ptr(a.to_kvs[1].weight), ptr(a.to_kvs[1].bias), ptr(a.projs[1].weight),
+                 ptr(a.to_qs[1].bias), ptr(self._packed(a.to_kvs[1].weight)), ptr(a.to_kvs[1].bias), ptr(a.projs[1].weight),
                  ptr(a.projs[1].bias), g["cap"], ptr(g["total"]), ptr(g["win_list"]), ptr(xn),
                  ptr(sp_tensor.world_coords()), ptr(g["q_row"]), ptr(g["rep_row"]), ptr(g["meta"]),
                  ptr(g["q_base"]), ptr(g["q_src"]), ptr(g["vox_slot"]), ptr(g["win1_row"]), ptr(g["nn_idx"]),
@@ -421,8 +437,9 @@ class MixedScaleSparseTransformerCompressBlock(MixedScaleSparseTransformerBlock)
             call("mssvt_compress_attention_tc", 64, a.num_heads[0], n1, a.scale,
                  host_floats([vs[i] * self.win1_size[i] for i in range(3)]),
                  host_floats(sp_tensor.point_cloud_range[0:3]), ptr(self.pos_proj[0].weight),
-                 ptr(self.pos_proj[0].bias), ptr(self.pos_proj[2].weight), ptr(self.pos_proj[2].bias),
-                 ptr(a.to_qs[0].weight), ptr(a.to_qs[0].bias), ptr(a.to_kvs[0].weight), ptr(a.to_kvs[0].bias),
+                 ptr(self.pos_proj[0].bias), ptr(self._packed(self.pos_proj[2].weight)), ptr(self.pos_proj[2].bias),
+                 ptr(a.to_qs[0].weight), ptr(a.to_qs[0].bias), ptr(self._packed(a.to_kvs[0].weight)),
+                 ptr(a.to_kvs[0].bias),
                  ptr(a.projs[0].weight), ptr(a.projs[0].bias), cap, ptr(total), ptr(win_list), ptr(xn),
                  ptr(sp_tensor.world_coords()), ptr(k_row), ptr(scratch), ptr(attn), stream())
         else:
