@@ -208,12 +208,22 @@ int mssvt_block_attention(const void *shape, int shape_bytes, const float *param
                           const unsigned char *nn_idx, const float *nn_w, float *merged,
                           void *stream);
 
+/* Tile plan of mssvt_block_attention_tc: packs consecutive windows of one scale into tiles of <= 128
+ * distinct keys.  A function of the geometry only (meta, q_base, win_list): made once per frame and shared
+ * by every block that runs over the same window lists.  Outputs (opaque, caller-allocated):
+ * tiles (2, win_capacity, 2) int, tile_count (2) int, win_rec (2, win_capacity, 4) int,
+ * win_ctr (win_capacity, 4) float. */
+int mssvt_attention_tiles(int heads_per_group, int nq, int key_num_sample, int win_capacity,
+                          const int *win_count_total, const int *win_list, const int *meta, const int *q_base,
+                          const float *win_cell, const float *range_min, int *tiles, int *tile_count,
+                          int *win_rec, float *win_ctr, void *stream);
+
 /* The same step, task-parallel (one thread per query / distinct key / voxel over the whole frame) with
  * the K/V projection on the tcgen05 tensor cores (TF32 operands, fp32 everywhere else;
  * mssvt_b200/csrc/attention_tc.cu: 4 kernels).  Weights in nn.Module layout: pos_w [64][6], wq*/wp*
  * [32][32] for head groups 0 / 1, wkv* [64][32] packed by mssvt_pack_operand_tf32; rep_row / meta from mssvt_block_geometry; q_base =
  * mssvt_exclusive_scan(meta[:, 0]) (win_capacity + 1 ints), q_src = mssvt_query_src, vox_slot from the
- * geometry; scratch: 3 * num_voxels * 64 floats.
+ * geometry; tiles / tile_count / win_rec / win_ctr = mssvt_attention_tiles; scratch: 3 * num_voxels * 64 floats.
  * Supported: C = 64, two groups of 32 channels with 1, 2 or 4 heads each, nq <= 32,
  * key_num_sample <= 63, cap1 <= 128; -1 otherwise. */
 int mssvt_block_attention_tc(int C, int heads_per_group, int nq, int key_num_sample, int cap1, int interp,
@@ -225,7 +235,8 @@ int mssvt_block_attention_tc(int C, int heads_per_group, int nq, int key_num_sam
                              const int *win_list, const float *xn, const float *xyz, const int *q_row,
                              const int *rep_row, const int *meta, const int *q_base, const int *q_src,
                              const int *vox_slot, const int *win1_row, const unsigned char *nn_idx,
-                             const float *nn_w, int num_voxels, float *scratch, float *merged, void *stream);
+                             const float *nn_w, const int *tiles, const int *tile_count, const int *win_rec,
+                             const float *win_ctr, int num_voxels, float *scratch, float *merged, void *stream);
 
 /* Attention of a one-window (compress) block (mssvt_backbone.py:361-383): out (cap, C). */
 int mssvt_compress_attention(const void *shape, int shape_bytes, const float *params,

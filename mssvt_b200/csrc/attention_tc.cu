@@ -4,21 +4,22 @@
 // warp walking through a window, every stage runs with one THREAD per task over the whole frame:
 //
 //   k_tca_query   thread = (query, head group, 8 outputs): q = (Wq (xn + posemb) + bq) * scale
-//   k_tca_keys    thread = distinct key of a window (both scales mixed, 128 per tile).  The thread
+//   k_tca_plan    once per frame geometry: packs consecutive windows of one scale into tiles of <= 128
+//                 distinct keys (windows without a real query are skipped), per-window offsets
+//   k_tca_keys    thread = distinct key of a window, 128 keys of ONE scale per tile.  The thread
 //                 gathers its 32-channel slice of the layer-normed row, adds the positional
 //                 embedding and stores the row, TF32-rounded, as row t of the A operand; one thread
-//                 issues 8 tcgen05.mma.kind::tf32 (M = 128, N = 64, K = 8): D0 = A Wkv0^T and
-//                 D1 = A Wkv1^T into 128 TMEM columns; tcgen05.ld hands every thread the 64 K|V
-//                 values of ITS key (TMEM lane = thread, columns of its scale).  Scores against the
-//                 window's queries, then softmax (with the multiplicity of the masked key) and AV
-//                 with one thread per (query, scale, head, quarter head).
+//                 issues 4 tcgen05.mma.kind::tf32 (M = 128, N = 64, K = 8): D = A Wkv^T into 64 TMEM
+//                 columns; tcgen05.ld hands every thread the 64 K|V values of ITS key (TMEM lane =
+//                 thread).  Scores against the window's queries, then softmax (with the multiplicity
+//                 of the masked key) and AV with one thread per (query, head, quarter head).
 //   k_tca_proj    thread = (query, head group, 8 outputs): output projection
 //   k_tca_merge   thread = (win1 voxel, 16 channels): 1/d blend of the 3 nearest query rows -> merged
 //
 // Queries are addressed by a compact id (q_base[w] + slot, an exclusive scan over the windows done
 // with the geometry), so the three intermediates (q, head outputs, projected rows) are dense
 // (#queries, 64) fp32 arrays that live in L2.  Compared with the warp-per-window kernel this executes
-// ~5x fewer warp instructions, has no lane redundancy on the small per-window matrices, keeps four
+// ~5x fewer warp instructions, has no lane redundancy on the small per-window matrices, keeps five
 // 128-thread CTAs per SM in flight, and the 2048 FMAs per key run on the tensor pipe.
 //
 // Supported shape (config S0 and relatives): C = 64, two head groups of 32 channels, 1/2/4 heads per
@@ -30,7 +31,9 @@
 namespace mssvt {
 
 #define TCA_THREADS 128
-#define TCA_WB 16        // windows per batch (tile candidates)
+#define TCA_TW 32        // windows per tile (at most)
+#define TCA_SBUD 2048    // score slots per tile: sum over its windows of #queries x #keys x heads
+#define TCA_PLAN_WB 64   // windows planned by one warp
 #define TCA_C 64
 #define TCA_SD 32
 #define TCA_VPITCH 36    // V row pitch in floats: 16-byte aligned, conflict-free for quarter warps
@@ -135,53 +138,117 @@ k_tca_query(TcAttnParams P, int win_cap, const int *__restrict__ win_count_total
     }
 }
 
+// ------------------------------------------------------------------------------- tile plan
+
+// A tile = consecutive windows of ONE scale whose distinct keys fill the 128 rows of an MMA.  The plan is
+// a function of the geometry only, so it is made once per frame and shared by every block that uses the
+// same window lists.  One warp plans TCA_PLAN_WB windows of one scale: lanes load 32 windows at a time,
+// the greedy cut is a 32-step scan over shuffled values (every lane runs it, lane i keeps step i).
+// Windows without a real query get no key tasks at all (nobody would read their K/V).
+__global__ void __launch_bounds__(256)
+k_tca_plan(int heads, int win_cap, const int *__restrict__ win_count_total, const int4 *__restrict__ win_list,
+           const int4 *__restrict__ meta, const int *__restrict__ q_base, float3 win_cell, float3 lo,
+           int2 *__restrict__ tiles, int *__restrict__ tile_count, int4 *__restrict__ win_rec,
+           float4 *__restrict__ win_ctr) {
+    const int num_wins = min(win_cap, __ldg(win_count_total));
+    const int lane = threadIdx.x & 31;
+    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int g = wid & 1, w0 = (wid >> 1) * TCA_PLAN_WB;
+    if (w0 >= num_wins) return;
+    const int w1 = min(w0 + TCA_PLAN_WB, num_wins);
+    int ts = w0, a = 0, aq = 0, as = 0, nw = 0;  // open tile: first window, key tasks, queries, score slots, windows
+    for (int wb = w0; wb < w1; wb += 32) {
+        const int w = wb + lane;
+        int nqr = 0, r = 0, mult = 0, qb = 0;
+        if (w < w1) {
+            const int4 m = __ldg(meta + w);
+            const int mm = g ? m.w : m.z;
+            nqr = m.x; r = nqr ? mm & 0xff : 0; mult = mm >> 8; qb = __ldg(q_base + w);
+            if (g == 0) {
+                const int4 win = __ldg(win_list + w);
+                win_ctr[w] = make_float4(world_coord(win.w, win_cell.x, lo.x), world_coord(win.z, win_cell.y, lo.y),
+                                         world_coord(win.y, win_cell.z, lo.z), 0.f);
+            }
+        }
+        int my_a = 0, my_aq = 0, my_as = 0;
+        const int n = min(32, w1 - wb);
+        for (int i = 0; i < n; ++i) {
+            const int ri = __shfl_sync(0xffffffffu, r, i), qi = __shfl_sync(0xffffffffu, nqr, i);
+            const int si = qi * ri * heads;
+            if (nw > 0 && (a + ri > TCA_THREADS || aq + qi > TCA_THREADS || as + si > TCA_SBUD || nw == TCA_TW)) {
+                if (lane == 0 && a > 0) tiles[(size_t)g * win_cap + atomicAdd(tile_count + g, 1)] = make_int2(ts, nw);
+                ts = wb + i; a = aq = as = nw = 0;
+            }
+            if (i == lane) { my_a = a; my_aq = aq; my_as = as; }
+            a += ri; aq += qi; as += si; ++nw;
+        }
+        if (w < w1)
+            win_rec[(size_t)g * win_cap + w] = make_int4(qb, nqr | (r << 8) | (mult << 16), my_a | (my_aq << 8) | (my_as << 16), 0);
+    }
+    if (lane == 0 && a > 0) tiles[(size_t)g * win_cap + atomicAdd(tile_count + g, 1)] = make_int2(ts, nw);
+}
+
 // ------------------------------------------------------------------------------- keys + attention
 
-struct TcaTile {
-    int ws, we, nQ, nT0, nT1;
-};
+// largest l in [0, n) with off[l] <= v (off[n] > v)
+__device__ __forceinline__ int tile_window(const int *off, int n, int v) {
+    int lo = 0, hi = n;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (off[mid] <= v) lo = mid; else hi = mid;
+    }
+    return lo;
+}
 
 template <int HEADS>
-__global__ void __launch_bounds__(TCA_THREADS, 4)
-k_tca_keys(TcAttnParams P, int win_cap, const int *__restrict__ win_count_total,
-           const int4 *__restrict__ win_list, const float *__restrict__ xn, const float *__restrict__ xyz,
-           const int *__restrict__ rep_row, const int *__restrict__ meta, const int *__restrict__ q_base,
-           const float *__restrict__ Qbuf, float *__restrict__ Obuf) {
+__global__ void __launch_bounds__(TCA_THREADS, 5)
+k_tca_keys(TcAttnParams P, int win_cap, const int2 *__restrict__ tiles, const int *__restrict__ tile_count,
+           const int4 *__restrict__ win_rec, const float4 *__restrict__ win_ctr, const float *__restrict__ xn,
+           const float *__restrict__ xyz, const int *__restrict__ rep_row, const float *__restrict__ Qbuf,
+           float *__restrict__ Obuf) {
     constexpr int HD = TCA_SD / HEADS;
     constexpr int DPT = HD / 4;  // channels per thread in the AV phase
     extern __shared__ __align__(128) char smem_raw[];
     const int tid = threadIdx.x, warp = tid >> 5;
-    const int K = P.K, smax = P.smax;
+    const int K = P.K;
 
-    // ---- shared memory: 16 KB weights + 18 KB A/V (aliased) + scores + bookkeeping = ~51 KB
-    char *sWkv = smem_raw;                                  // 2 x [64 x 32] canonical, TF32   16 KB
-    char *sA = sWkv + 2 * 64 * 32 * 4;                      // [128 x 32] canonical (16 KB) ...
+    // ---- every CTA works on one scale for its whole life (8 KB of weights instead of 16); the CTAs of the
+    //      two scales are interleaved over the grid in proportion to the tile counts
+    const int T0 = __ldg(tile_count), T1 = __ldg(tile_count + 1), G = gridDim.x, b = blockIdx.x;
+    int G0 = T0 == 0 ? 0 : T1 == 0 ? G : (int)(((long long)G * T0 + (T0 + T1) / 2) / (T0 + T1));
+    if (T0 > 0 && T1 > 0) G0 = min(max(G0, 1), G - 1);
+    const int c0b = (int)((long long)b * G0 / G), c0n = (int)((long long)(b + 1) * G0 / G);
+    const int g = c0n > c0b ? 0 : 1;
+    const int first = g ? b - c0b : c0b, stride = g ? G - G0 : G0, T = g ? T1 : T0;
+    tiles += (size_t)g * win_cap;
+    win_rec += (size_t)g * win_cap;
+
+    // ---- shared memory: 8 KB weights + 18 KB A/V (aliased) + 8 KB scores + bookkeeping = ~38 KB
+    char *sWkv = smem_raw;                                  // [64 x 32] canonical, TF32           8 KB
+    char *sA = sWkv + 64 * 32 * 4;                          // [128 x 32] canonical (16 KB) ...
     float *sV = (float *)sA;                                // ... reused as V [128][VPITCH] after the MMA
-    float *sPos = sV + TCA_THREADS * TCA_VPITCH;            // [64][8]
-    float *sBkv = sPos + 64 * 8;                            // [2][64]
-    float *sS = sBkv + 128;                                 // [128][smax] scores of each key task
-    float *sCtr = sS + TCA_THREADS * smax;                  // [WB][4] window centres
-    int *sMeta = (int *)(sCtr + TCA_WB * 4);                // [WB][4] {nqr, q_base, rep0, rep1}
-    int *sQoff = sMeta + TCA_WB * 4;                        // [WB + 1] prefix of real queries in the tile
-    int *sToff = sQoff + TCA_WB + 1;                        // [2][WB + 1] prefix of key tasks per scale
-    int *sQwin = sToff + 2 * (TCA_WB + 1);                  // [128] local window of each query of the tile
-    int *sTwin = sQwin + TCA_THREADS;                       // [128] local window of each key task
-    int *sTmult = sTwin + TCA_THREADS;                      // [128] multiplicity of each key task
-    int *sTile = sTmult + TCA_THREADS;                      // TcaTile + pad
-    uint64_t *sBar = (uint64_t *)(sTile + 8 + ((TCA_WB * 4 + 3 * (TCA_WB + 1) + 3 * TCA_THREADS + 8) & 1));
+    float *sPos = sV + TCA_THREADS * TCA_VPITCH;            // [32][8] (this scale's channels)
+    float *sBkv = sPos + 32 * 8;                            // [64]
+    float *sS = sBkv + 64;                                  // [SBUD] scores: window-major, [key][query][head]
+    float4 *sCtr = (float4 *)(sS + TCA_SBUD);               // [TW] window centres
+    int4 *sRec = (int4 *)(sCtr + TCA_TW);                   // [TW] {q_base, nqr | r << 8 | mult << 16, offsets}
+    int *sToff = (int *)(sRec + TCA_TW);                    // [TW + 1] first key task of each window
+    int *sQoff = sToff + TCA_TW + 1;                        // [TW + 1] first query of each window
+    uint64_t *sBar = (uint64_t *)(sQoff + TCA_TW + 1);      // (2 * (TW + 1) ints: 8-byte aligned)
     uint32_t *sTmem = (uint32_t *)(sBar + 1);
 
-    stage_packed(P.wkv[0], 64 * 32, sWkv);
-    stage_packed(P.wkv[1], 64 * 32, sWkv + 64 * 32 * 4);
-    stage_pos_weights(P, sPos);
-    for (int i = tid; i < 128; i += TCA_THREADS) sBkv[i] = __ldg(P.bkv[i >> 6] + (i & 63));
+    stage_packed(P.wkv[g], 64 * 32, sWkv);
+    for (int i = tid; i < 32 * 8; i += TCA_THREADS) {
+        const int c = g * TCA_SD + (i >> 3), k = i & 7;
+        sPos[i] = k < 6 ? __ldg(P.pos_w + c * 6 + k) : k == 6 ? __ldg(P.pos_b + c) : 0.f;
+    }
+    if (tid < 64) sBkv[tid] = __ldg(P.bkv[g] + tid);
     const uint32_t bar = smem_u32(sBar);
     if (tid == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0) tmem_alloc(smem_u32(sTmem), 128);
-    fence_async_smem();
+    if (warp == 0) tmem_alloc(smem_u32(sTmem), 64);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -193,177 +260,144 @@ k_tca_keys(TcAttnParams P, int win_cap, const int *__restrict__ win_count_total,
     const uint32_t my_row_off = (uint32_t)(tid >> 3) * 128u + (uint32_t)(tid & 7) * 16u;
     uint32_t phase = 0;
 
-    const int num_wins = min(win_cap, __ldg(win_count_total));
-    const int batches = (num_wins + TCA_WB - 1) / TCA_WB;
-    TcaTile *tile = (TcaTile *)sTile;
-
-    for (int batch = blockIdx.x; batch < batches; batch += gridDim.x) {
-        const int wb0 = batch * TCA_WB, nb = min(TCA_WB, num_wins - wb0);
-        __syncthreads();  // previous batch fully consumed
-        if (tid < nb) {
-            const int4 m = __ldg((const int4 *)meta + wb0 + tid);
-            sMeta[4 * tid] = m.x; sMeta[4 * tid + 1] = __ldg(q_base + wb0 + tid);
-            sMeta[4 * tid + 2] = m.z; sMeta[4 * tid + 3] = m.w;
-            const int4 win = __ldg(win_list + wb0 + tid);
-            sCtr[4 * tid] = world_coord(win.w, P.win_cell[0], P.lo[0]);
-            sCtr[4 * tid + 1] = world_coord(win.z, P.win_cell[1], P.lo[1]);
-            sCtr[4 * tid + 2] = world_coord(win.y, P.win_cell[2], P.lo[2]);
+    for (int t = first; t < T; t += stride) {
+        const int2 tl = __ldg(tiles + t);
+        const int nwin = tl.y;
+        if (tid < nwin) {
+            const int4 rec = __ldg(win_rec + tl.x + tid);
+            sRec[tid] = rec;
+            sCtr[tid] = __ldg(win_ctr + tl.x + tid);
+            sToff[tid] = rec.z & 0xff;
+            sQoff[tid] = (rec.z >> 8) & 0xff;
+            if (tid == nwin - 1) {
+                sToff[nwin] = (rec.z & 0xff) + ((rec.y >> 8) & 0xff);
+                sQoff[nwin] = ((rec.z >> 8) & 0xff) + (rec.y & 0xff);
+            }
         }
         __syncthreads();
-        int ws = 0;
-        while (ws < nb) {
-            // ---- tile = greedy prefix of the batch: <= 128 distinct keys (both scales), <= 128 queries
-            if (tid == 0) {
-                int we = ws, aq = 0, a0 = 0, a1 = 0;
-                while (we < nb) {
-                    const int nqr = sMeta[4 * we];
-                    const int r0 = sMeta[4 * we + 2] & 0xff, r1 = sMeta[4 * we + 3] & 0xff;
-                    // scale-1 tasks start at a warp boundary: tcgen05.ld takes ONE column address per warp
-                    if (we > ws && (aq + nqr > TCA_THREADS || ((a0 + r0 + 31) & ~31) + a1 + r1 > TCA_THREADS)) break;
-                    const int l = we - ws;
-                    sQoff[l] = aq; sToff[l] = a0; sToff[TCA_WB + 1 + l] = a1;
-                    aq += nqr; a0 += r0; a1 += r1;
-                    ++we;
-                }
-                const int l = we - ws;
-                sQoff[l] = aq; sToff[l] = a0; sToff[TCA_WB + 1 + l] = a1;
-                tile->ws = ws; tile->we = we; tile->nQ = aq; tile->nT0 = a0; tile->nT1 = a1;
-            }
-            __syncthreads();
-            const int t_ws = tile->ws, t_we = tile->we, nQ = tile->nQ, nT0 = tile->nT0, nT1 = tile->nT1;
-            const int R1 = (nT0 + 31) & ~31;  // first row of the scale-1 tasks (warp aligned)
-            const int nwin = t_we - t_ws;
-            // task -> window maps; key tasks: scale 0 of every window first, then scale 1
-            if (tid < nwin) {
-                for (int i = sQoff[tid]; i < sQoff[tid + 1]; ++i) sQwin[i] = tid;
-                for (int i = sToff[tid]; i < sToff[tid + 1]; ++i) sTwin[i] = tid;
-                for (int i = sToff[TCA_WB + 1 + tid]; i < sToff[TCA_WB + 1 + tid + 1]; ++i) sTwin[R1 + i] = tid;
-            }
-            __syncthreads();
+        const int nT = sToff[nwin], nQ = sQoff[nwin];
+        // the tile's query rows (contiguous ids) are read after the MMA: pull their 128-byte halves into L1 now
+        if (tid < nQ)
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(Qbuf + (size_t)(sRec[0].x + tid) * TCA_C + g * TCA_SD));
 
-            // ---- key task -> row t of the A operand
-            int l = 0, my_nqr = 0, my_q0 = 0;
-            const int g = tid >= R1 ? 1 : 0;  // uniform within a warp
-            const bool is_task = g ? tid - R1 < nT1 : tid < nT0;
-            bool masked = false;
-            if (is_task) {
-                l = sTwin[tid];
-                const int j = g ? tid - R1 - sToff[TCA_WB + 1 + l] : tid - sToff[l];
-                const int w = wb0 + t_ws + l;
-                const int m = sMeta[4 * (t_ws + l) + 2 + g];
-                masked = (m >> 8) > 0 && j == (m & 0xff) - 1;  // last distinct key stands for all masked slots
-                sTmult[tid] = masked ? (m >> 8) : 1;
-                my_nqr = sMeta[4 * (t_ws + l)];
-                my_q0 = sMeta[4 * (t_ws + l) + 1];
-                const int row = __ldg(rep_row + (size_t)w * 2 * K + g * K + j);
-                const float cx = sCtr[4 * (t_ws + l)], cy = sCtr[4 * (t_ws + l) + 1], cz = sCtr[4 * (t_ws + l) + 2];
-                float rx = 0.f, ry = 0.f, rz = 0.f;  // masked key: relative offset zeroed
-                if (!masked) {
-                    rx = __fsub_rn(__ldg(xyz + 3 * (size_t)row), cx);
-                    ry = __fsub_rn(__ldg(xyz + 3 * (size_t)row + 1), cy);
-                    rz = __fsub_rn(__ldg(xyz + 3 * (size_t)row + 2), cz);
-                }
-                const float4 *src = (const float4 *)(xn + (size_t)row * TCA_C + g * TCA_SD);
-                float4 xv[TCA_SD / 4];  // the whole 128-byte slice in flight at once
-#pragma unroll
-                for (int c4 = 0; c4 < TCA_SD / 4; ++c4) xv[c4] = __ldg(src + c4);
-#pragma unroll
-                for (int c4 = 0; c4 < TCA_SD / 4; ++c4) {
-                    const float4 v = xv[c4];
-                    const int c = g * TCA_SD + 4 * c4;
-                    float4 o;
-                    o.x = to_tf32(v.x + pos_embed8(sPos, c, rx, ry, rz, cx, cy, cz));
-                    o.y = to_tf32(v.y + pos_embed8(sPos, c + 1, rx, ry, rz, cx, cy, cz));
-                    o.z = to_tf32(v.z + pos_embed8(sPos, c + 2, rx, ry, rz, cx, cy, cz));
-                    o.w = to_tf32(v.w + pos_embed8(sPos, c + 3, rx, ry, rz, cx, cy, cz));
-                    *(float4 *)(sA + (uint32_t)c4 * a_lbo + my_row_off) = o;
-                }
+        // ---- key task -> row t of the A operand
+        const bool is_task = tid < nT;
+        int j = 0, nqr = 0, q0 = 0, soff = 0;
+        bool masked = false;
+        if (is_task) {
+            const int l = tile_window(sToff, nwin, tid);
+            const int4 rec = sRec[l];
+            j = tid - (rec.z & 0xff);
+            nqr = rec.y & 0xff; q0 = rec.x; soff = rec.z >> 16;
+            const int r = (rec.y >> 8) & 0xff, mult = rec.y >> 16;
+            masked = mult > 0 && j == r - 1;  // last distinct key stands for all masked slots
+            const int row = __ldg(rep_row + (size_t)(tl.x + l) * 2 * K + g * K + j);
+            const float4 ctr = sCtr[l];
+            float rx = 0.f, ry = 0.f, rz = 0.f;  // masked key: relative offset zeroed
+            if (!masked) {
+                rx = __fsub_rn(__ldg(xyz + 3 * (size_t)row), ctr.x);
+                ry = __fsub_rn(__ldg(xyz + 3 * (size_t)row + 1), ctr.y);
+                rz = __fsub_rn(__ldg(xyz + 3 * (size_t)row + 2), ctr.z);
             }
-            stage_packed_wait();
-            fence_async_smem();
-            __syncthreads();
-            // ---- D0 = A Wkv0^T (columns 0..63), D1 = A Wkv1^T (columns 64..127) on the tensor cores
-            if (tid == 0) {
-                tc_fence_after();
+            const float4 *src = (const float4 *)(xn + (size_t)row * TCA_C + g * TCA_SD);
+            float4 xv[TCA_SD / 4];  // the whole 128-byte slice in flight at once
 #pragma unroll
-                for (int gg = 0; gg < 2; ++gg)
+            for (int c4 = 0; c4 < TCA_SD / 4; ++c4) xv[c4] = __ldg(src + c4);
 #pragma unroll
-                    for (int k = 0; k < TCA_SD / 8; ++k) {
-                        const uint64_t da = umma_smem_desc(sA_u + (uint32_t)k * 2u * a_lbo, a_lbo, 128);
-                        const uint64_t db = umma_smem_desc(sWkv_u + (uint32_t)gg * 64u * 32u * 4u + (uint32_t)k * 2u * w_lbo,
-                                                           w_lbo, 128);
-                        umma_tf32(tmem_d + (uint32_t)gg * 64u, da, db, idesc, k > 0 ? 1u : 0u);
-                    }
-                umma_commit(bar);
+            for (int c4 = 0; c4 < TCA_SD / 4; ++c4) {
+                const float4 v = xv[c4];
+                float4 o;
+                o.x = to_tf32(v.x + pos_embed8(sPos, 4 * c4, rx, ry, rz, ctr.x, ctr.y, ctr.z));
+                o.y = to_tf32(v.y + pos_embed8(sPos, 4 * c4 + 1, rx, ry, rz, ctr.x, ctr.y, ctr.z));
+                o.z = to_tf32(v.z + pos_embed8(sPos, 4 * c4 + 2, rx, ry, rz, ctr.x, ctr.y, ctr.z));
+                o.w = to_tf32(v.w + pos_embed8(sPos, 4 * c4 + 3, rx, ry, rz, ctr.x, ctr.y, ctr.z));
+                *(float4 *)(sA + (uint32_t)c4 * a_lbo + my_row_off) = o;
             }
-            mbar_wait(bar, phase);
-            phase ^= 1u;
-            tc_fence_after();
-            // ---- this thread's key: K|V of its scale back from TMEM; scores against its window's queries
-            {
-                float kk[TCA_SD], vv[TCA_SD];
-                tmem_ld32(tmem_d + lane_off + (uint32_t)g * 64u, kk);
-                tmem_ld32(tmem_d + lane_off + (uint32_t)g * 64u + 32u, vv);
-                tc_fence_before();
-                __syncthreads();  // every thread has its K|V in registers: the A tile may become V
-                if (is_task) {
-                    const float *bk = sBkv + g * 64;
-#pragma unroll
-                    for (int i = 0; i < TCA_SD; ++i) { kk[i] += bk[i]; vv[i] += bk[TCA_SD + i]; }
-#pragma unroll
-                    for (int c4 = 0; c4 < TCA_SD / 4; ++c4)
-                        *(float4 *)(sV + tid * TCA_VPITCH + 4 * c4) =
-                            make_float4(vv[4 * c4], vv[4 * c4 + 1], vv[4 * c4 + 2], vv[4 * c4 + 3]);
-                    const float bias = masked ? -100.0f : 0.f;  // additive mask of the reference
-                    for (int s = 0; s < my_nqr; ++s) {
-                        const float4 *qv = (const float4 *)(Qbuf + (size_t)(my_q0 + s) * TCA_C + g * TCA_SD);
-#pragma unroll
-                        for (int h = 0; h < HEADS; ++h) {
-                            float a = 0.f;
-#pragma unroll
-                            for (int d4 = 0; d4 < HD / 4; ++d4) {
-                                const float4 q4 = __ldg(qv + h * (HD / 4) + d4);
-                                a = fmaf(q4.x, kk[h * HD + 4 * d4], a); a = fmaf(q4.y, kk[h * HD + 4 * d4 + 1], a);
-                                a = fmaf(q4.z, kk[h * HD + 4 * d4 + 2], a); a = fmaf(q4.w, kk[h * HD + 4 * d4 + 3], a);
-                            }
-                            sS[tid * smax + s * HEADS + h] = a + bias;
-                        }
-                    }
-                }
-            }
-            __syncthreads();
-            // ---- softmax over the window's distinct keys of a scale and AV,
-            //      thread = (query, scale, head, quarter of the head)
-            for (int e = tid; e < nQ * 2 * HEADS * 4; e += TCA_THREADS) {
-                const int dq = e & 3, qgh = e >> 2;
-                const int h = qgh % HEADS, qg = qgh / HEADS, gg = qg & 1, qt = qg >> 1;
-                const int lq = sQwin[qt], s = qt - sQoff[lq];
-                const int t0 = gg ? R1 + sToff[TCA_WB + 1 + lq] : sToff[lq];
-                const int t1 = gg ? R1 + sToff[TCA_WB + 1 + lq + 1] : sToff[lq + 1];
-                float mx = -3.0e38f;
-                for (int t = t0; t < t1; ++t) mx = fmaxf(mx, sS[t * smax + s * HEADS + h]);
-                float den = 0.f, acc[DPT];
-#pragma unroll
-                for (int d = 0; d < DPT; ++d) acc[d] = 0.f;
-                for (int t = t0; t < t1; ++t) {
-                    const float wgt = exp_neg(sS[t * smax + s * HEADS + h] - mx) * (float)sTmult[t];
-                    den += wgt;
-                    const float *vp = sV + t * TCA_VPITCH + h * HD + dq * DPT;
-#pragma unroll
-                    for (int d = 0; d < DPT; ++d) acc[d] = fmaf(wgt, vp[d], acc[d]);
-                }
-                const float inv = 1.0f / den;
-                float *dst = Obuf + (size_t)(sMeta[4 * (t_ws + lq) + 1] + s) * TCA_C + gg * TCA_SD + h * HD + dq * DPT;
-#pragma unroll
-                for (int d = 0; d < DPT; ++d) dst[d] = acc[d] * inv;
-            }
-            __syncthreads();
-            ws = t_we;
         }
+        stage_packed_wait();
+        fence_async_smem();
+        __syncthreads();
+        // ---- D = A Wkv^T: K in TMEM columns 0..31, V in 32..63
+        if (tid == 0) {
+            tc_fence_after();
+#pragma unroll
+            for (int k = 0; k < TCA_SD / 8; ++k) {
+                const uint64_t da = umma_smem_desc(sA_u + (uint32_t)k * 2u * a_lbo, a_lbo, 128);
+                const uint64_t db = umma_smem_desc(sWkv_u + (uint32_t)k * 2u * w_lbo, w_lbo, 128);
+                umma_tf32(tmem_d, da, db, idesc, k > 0 ? 1u : 0u);
+            }
+            umma_commit(bar);
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1u;
+        tc_fence_after();
+        // ---- this thread's key: K|V back from TMEM; scores against its window's queries
+        {
+            float kk[TCA_SD], vv[TCA_SD];
+            tmem_ld32(tmem_d + lane_off, kk);
+            tmem_ld32(tmem_d + lane_off + 32u, vv);
+            tc_fence_before();
+            __syncthreads();  // every thread has its K|V in registers: the A tile may become V
+            if (is_task) {
+#pragma unroll
+                for (int c4 = 0; c4 < TCA_SD / 4; ++c4)
+                    *(float4 *)(sV + tid * TCA_VPITCH + 4 * c4) =
+                        make_float4(vv[4 * c4] + sBkv[TCA_SD + 4 * c4], vv[4 * c4 + 1] + sBkv[TCA_SD + 4 * c4 + 1],
+                                    vv[4 * c4 + 2] + sBkv[TCA_SD + 4 * c4 + 2], vv[4 * c4 + 3] + sBkv[TCA_SD + 4 * c4 + 3]);
+#pragma unroll
+                for (int i = 0; i < TCA_SD; ++i) kk[i] += sBkv[i];
+                const float bias = masked ? -100.0f : 0.f;  // additive mask of the reference
+                float *srow = sS + soff + j * nqr * HEADS;
+                for (int s = 0; s < nqr; ++s) {
+                    const float4 *qv = (const float4 *)(Qbuf + (size_t)(q0 + s) * TCA_C + g * TCA_SD);
+#pragma unroll
+                    for (int h = 0; h < HEADS; ++h) {
+                        float a = 0.f;
+#pragma unroll
+                        for (int d4 = 0; d4 < HD / 4; ++d4) {
+                            const float4 q4 = __ldg(qv + h * (HD / 4) + d4);
+                            a = fmaf(q4.x, kk[h * HD + 4 * d4], a); a = fmaf(q4.y, kk[h * HD + 4 * d4 + 1], a);
+                            a = fmaf(q4.z, kk[h * HD + 4 * d4 + 2], a); a = fmaf(q4.w, kk[h * HD + 4 * d4 + 3], a);
+                        }
+                        srow[s * HEADS + h] = a + bias;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // ---- softmax over the window's distinct keys and AV, thread = (query, head, quarter of the head)
+        for (int e = tid; e < nQ * HEADS * 4; e += TCA_THREADS) {
+            const int dq = e & 3, qh = e >> 2;
+            const int h = qh % HEADS, qt = qh / HEADS;
+            const int lq = tile_window(sQoff, nwin, qt);
+            const int4 rec = sRec[lq];
+            const int s = qt - ((rec.z >> 8) & 0xff);
+            const int wq = rec.y & 0xff, r = (rec.y >> 8) & 0xff, mult = rec.y >> 16;
+            const float *sc = sS + (rec.z >> 16) + s * HEADS + h;  // + key * wq * HEADS
+            const int step = wq * HEADS;
+            float mx = -3.0e38f;
+            for (int k = 0; k < r; ++k) mx = fmaxf(mx, sc[k * step]);
+            float den = 0.f, acc[DPT];
+#pragma unroll
+            for (int d = 0; d < DPT; ++d) acc[d] = 0.f;
+            const float *vp = sV + (rec.z & 0xff) * TCA_VPITCH + h * HD + dq * DPT;
+            for (int k = 0; k < r; ++k) {
+                float wgt = exp_neg(sc[k * step] - mx);
+                if (k == r - 1 && mult > 0) wgt *= (float)mult;  // the masked key counts once per masked slot
+                den += wgt;
+#pragma unroll
+                for (int d = 0; d < DPT; ++d) acc[d] = fmaf(wgt, vp[k * TCA_VPITCH + d], acc[d]);
+            }
+            const float inv = 1.0f / den;
+            float *dst = Obuf + (size_t)(rec.x + s) * TCA_C + g * TCA_SD + h * HD + dq * DPT;
+#pragma unroll
+            for (int d = 0; d < DPT; ++d) dst[d] = acc[d] * inv;
+        }
+        __syncthreads();
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem_d, 128);
+    if (warp == 0) tmem_dealloc(tmem_d, 64);
 }
 
 // ------------------------------------------------------------------------------- output projection
@@ -449,11 +483,9 @@ k_tca_merge(TcAttnParams P, int win_cap, const int *__restrict__ win_count_total
     }
 }
 
-static size_t tca_keys_smem_bytes(int smax) {
-    size_t floats = TCA_THREADS * TCA_VPITCH + 64 * 8 + 128 + (size_t)TCA_THREADS * smax + TCA_WB * 4;
-    size_t ints = TCA_WB * 4 + 3 * (TCA_WB + 1) + 3 * TCA_THREADS + 8;
-    ints += ints & 1;  // keep the mbarrier 8-byte aligned
-    return 2 * 64 * 32 * 4 + (floats + ints) * 4 + 8 + 16 + 128;
+static size_t tca_keys_smem_bytes() {
+    return 64 * 32 * 4 + (size_t)(TCA_THREADS * TCA_VPITCH + 32 * 8 + 64 + TCA_SBUD) * 4 + TCA_TW * 32 +
+           2 * (TCA_TW + 1) * 4 + 8 + 16 + 128;
 }
 
 }  // namespace mssvt
@@ -462,11 +494,38 @@ using namespace mssvt;
 
 extern "C" {
 
+/* Tile plan of the tensor-core window attention: a function of the geometry (meta, q_base, win_list)
+ * only, made once and shared by every block / launch over the same window lists.
+ * tiles (2, win_capacity, 2) int, tile_count (2) int, win_rec (2, win_capacity, 4) int, win_ctr
+ * (win_capacity, 4) float: opaque to the caller. */
+int mssvt_attention_tiles(int heads_per_group, int nq, int key_num_sample, int win_capacity,
+                          const int *win_count_total, const int *win_list, const int *meta, const int *q_base,
+                          const float *win_cell, const float *range_min, int *tiles, int *tile_count,
+                          int *win_rec, float *win_ctr, void *stream) {
+    if (heads_per_group <= 0 || nq <= 0 || nq > 32 || key_num_sample <= 0 || key_num_sample > 63 ||
+        nq * (key_num_sample + 1) * heads_per_group > TCA_SBUD || win_capacity < 0)
+        return MSSVT_ERR_INVALID;
+    if (!win_count_total || !win_list || !meta || !q_base || !win_cell || !range_min || !tiles || !tile_count ||
+        !win_rec || !win_ctr)
+        return MSSVT_ERR_INVALID;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (cudaMemsetAsync(tile_count, 0, 2 * sizeof(int), s) != cudaSuccess) return MSSVT_ERR_LAUNCH;
+    if (win_capacity == 0) return MSSVT_OK;
+    const int warps = 2 * ((win_capacity + TCA_PLAN_WB - 1) / TCA_PLAN_WB);
+    ++g_launches;
+    k_tca_plan<<<(warps + 7) / 8, 256, 0, s>>>(heads_per_group, win_capacity, win_count_total, (const int4 *)win_list,
+                                               (const int4 *)meta, q_base,
+                                               make_float3(win_cell[0], win_cell[1], win_cell[2]),
+                                               make_float3(range_min[0], range_min[1], range_min[2]),
+                                               (int2 *)tiles, tile_count, (int4 *)win_rec, (float4 *)win_ctr);
+    return check_launch();
+}
+
 /* Tensor-core window attention of a two-window block (see the header of this file).  Weights in
  * their nn.Module layout: pos_w [64][6], wq/wp [32][32] per head group; wkv [64][32] packed by
- * mssvt_pack_operand_tf32.  rep_row / meta:
- * compact key lists of mssvt_block_geometry; q_base: mssvt_exclusive_scan of meta[:, 0] (win_capacity + 1
- * ints).  scratch: 3 * num_voxels * 64 floats (q, head outputs, projected rows of every real query).
+ * mssvt_pack_operand_tf32.  rep_row / meta: compact key lists of mssvt_block_geometry; q_base:
+ * mssvt_exclusive_scan of meta[:, 0] (win_capacity + 1 ints); tiles .. win_ctr: mssvt_attention_tiles.
+ * scratch: 3 * num_voxels * 64 floats (q, head outputs, projected rows of every real query).
  * Returns MSSVT_ERR_INVALID for shapes outside C = 64 / 2 x 32 channels / nq <= 32 / K <= 63 /
  * cap1 <= 128 (callers then use mssvt_block_attention). */
 int mssvt_block_attention_tc(int C, int heads_per_group, int nq, int key_num_sample, int cap1, int interp,
@@ -478,14 +537,16 @@ int mssvt_block_attention_tc(int C, int heads_per_group, int nq, int key_num_sam
                              const int *win_list, const float *xn, const float *xyz, const int *q_row,
                              const int *rep_row, const int *meta, const int *q_base, const int *q_src,
                              const int *vox_slot, const int *win1_row, const unsigned char *nn_idx,
-                             const float *nn_w, int num_voxels, float *scratch, float *merged, void *stream) {
+                             const float *nn_w, const int *tiles, const int *tile_count, const int *win_rec,
+                             const float *win_ctr, int num_voxels, float *scratch, float *merged, void *stream) {
     if (C != 64 || (heads_per_group != 1 && heads_per_group != 2 && heads_per_group != 4) || nq <= 0 || nq > 32 ||
-        key_num_sample <= 0 || key_num_sample > 63 || cap1 <= 0 || cap1 > 128 || win_capacity < 0 || num_voxels < 0)
+        key_num_sample <= 0 || key_num_sample > 63 || cap1 <= 0 || cap1 > 128 || win_capacity < 0 || num_voxels < 0 ||
+        nq * (key_num_sample + 1) * heads_per_group > TCA_SBUD)
         return MSSVT_ERR_INVALID;
     if (win_capacity == 0) return MSSVT_OK;
     if (!win_cell || !range_min || !pos_w || !pos_b || !wq0 || !bq0 || !wkv0 || !bkv0 || !wp0 || !bp0 || !wq1 ||
         !bq1 || !wkv1 || !bkv1 || !wp1 || !bp1 || !win_count_total || !win_list || !xn || !xyz || !q_row ||
-        !rep_row || !meta || !q_base || !q_src || !scratch || !merged)
+        !rep_row || !meta || !q_base || !q_src || !tiles || !tile_count || !win_rec || !win_ctr || !scratch || !merged)
         return MSSVT_ERR_INVALID;
     if (interp && (!vox_slot || !nn_idx || !nn_w)) return MSSVT_ERR_INVALID;
     (void)win1_row;
@@ -497,8 +558,7 @@ int mssvt_block_attention_tc(int C, int heads_per_group, int nq, int key_num_sam
     P.pos_w = pos_w; P.pos_b = pos_b;
     P.wq[0] = wq0; P.bq[0] = bq0; P.wkv[0] = wkv0; P.bkv[0] = bkv0; P.wp[0] = wp0; P.bp[0] = bp0;
     P.wq[1] = wq1; P.bq[1] = bq1; P.wkv[1] = wkv1; P.bkv[1] = bkv1; P.wp[1] = wp1; P.bp[1] = bp1;
-    const size_t smem = tca_keys_smem_bytes(P.smax);
-    if (smem > 227 * 1024) return MSSVT_ERR_INVALID;
+    const size_t smem = tca_keys_smem_bytes();
     float *Qbuf = scratch, *Obuf = scratch + (size_t)num_voxels * 64, *Pbuf = scratch + 2 * (size_t)num_voxels * 64;
     cudaStream_t s = (cudaStream_t)stream;
     const int4 *wl = (const int4 *)win_list;
@@ -508,15 +568,14 @@ int mssvt_block_attention_tc(int C, int heads_per_group, int nq, int key_num_sam
     k_tca_query<<<wide, 256, 0, s>>>(P, win_capacity, win_count_total, wl, xn, xyz, q_row, q_base, q_src, Qbuf);
 
     int per_sm = (int)(227 * 1024 / (smem + 1024));
-    per_sm = per_sm > 4 ? 4 : per_sm < 1 ? 1 : per_sm;  // 4 x 128 TMEM columns = all 512
-    const int batches = (win_capacity + TCA_WB - 1) / TCA_WB;
-    int grid = MSSVT_NUM_SMS * per_sm;
-    if (grid > batches) grid = batches;
+    per_sm = per_sm > 5 ? 5 : per_sm < 1 ? 1 : per_sm;  // (64 TMEM columns each)
+    const int grid = MSSVT_NUM_SMS * per_sm;
     ++g_launches;
 #define TCA_LAUNCH(H)                                                                                      \
     cudaFuncSetAttribute(k_tca_keys<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
-    k_tca_keys<H><<<grid, TCA_THREADS, smem, s>>>(P, win_capacity, win_count_total, wl, xn, xyz, rep_row,  \
-                                                  meta, q_base, Qbuf, Obuf)
+    k_tca_keys<H><<<grid, TCA_THREADS, smem, s>>>(P, win_capacity, (const int2 *)tiles, tile_count,         \
+                                                  (const int4 *)win_rec, (const float4 *)win_ctr, xn, xyz, \
+                                                  rep_row, Qbuf, Obuf)
     if (heads_per_group == 1) { TCA_LAUNCH(1); }
     else if (heads_per_group == 2) { TCA_LAUNCH(2); }
     else { TCA_LAUNCH(4); }

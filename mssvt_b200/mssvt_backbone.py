@@ -265,6 +265,22 @@ class MixedScaleSparseTransformerBlock(nn.Module):
         cache[key] = g
         return g
 
+    def _tile_plan(self, sp_tensor, g, heads):
+        """tile plan of the tensor-core attention: depends on the geometry only, cached with it"""
+        key = ("tiles", heads)
+        if key not in g:
+            cap, dev = g["cap"], g["meta"].device
+            i32 = dict(dtype=torch.int32, device=dev)
+            plan = (torch.empty((2, cap, 2), **i32), torch.empty(2, **i32), torch.empty((2, cap, 4), **i32),
+                    torch.empty((cap, 4), dtype=torch.float32, device=dev))
+            vs = sp_tensor.voxel_size
+            call("mssvt_attention_tiles", heads, g["nq"], self.key_num_sample, cap, ptr(g["total"]),
+                 ptr(g["win_list"]), ptr(g["meta"]), ptr(g["q_base"]),
+                 host_floats([vs[i] * self.win1_size[i] for i in range(3)]),
+                 host_floats(sp_tensor.point_cloud_range[0:3]), *(ptr(v) for v in plan), stream())
+            g[key] = plan
+        return g[key]
+
     def _attn_descriptor(self, sp_tensor, nq, nk_total, cap1):
         a = self.ms_attn
         G = a.num_head_groups
@@ -343,7 +359,7 @@ class MixedScaleSparseTransformerBlock(nn.Module):
         c_out = S.C_out if S.C_out else S.C
         y = torch.empty((n_rows, c_out), dtype=torch.float32, device=merged.device)
         if (self.precision == "tf32" and S.C_out == 0 and S.C in (32, 64) and S.F % 64 == 0
-                and S.F + S.C <= 512 and (128 * S.C + 2 * S.F * S.C + 128 * S.F) * 4 < 220 * 1024):
+                and S.F + S.C <= 512 and (128 * S.C + 2 * S.F * S.C) * 4 < 220 * 1024):
             # tensor-core path: TF32 operands on tcgen05, fp32 accumulate / LayerNorm / residual
             # the epilogue also applies the NEXT block's norm1 (if there is one of the same width), which
             # saves that block a LayerNorm pass
@@ -374,9 +390,11 @@ class MixedScaleSparseTransformerBlock(nn.Module):
         a = self.ms_attn
         if (self.precision == "tf32" and self.in_channels == 64 and a.scale_dims == [32, 32]
                 and a.num_heads[0] == a.num_heads[1] and a.num_heads[0] in (1, 2, 4) and g["nq"] <= 32
-                and self.key_num_sample <= 63 and self.max_num_win1 <= 128 and len(self.pos_proj) == 2):
+                and self.key_num_sample <= 63 and self.max_num_win1 <= 128 and len(self.pos_proj) == 2
+                and g["nq"] * (self.key_num_sample + 1) * a.num_heads[0] <= 2048):
             # task-parallel kernel, K/V projection on the tcgen05 tensor cores (TF32 operands)
             vs = sp_tensor.voxel_size
+            plan = self._tile_plan(sp_tensor, g, a.num_heads[0])
             call("mssvt_block_attention_tc", 64, a.num_heads[0], g["nq"], self.key_num_sample, self.max_num_win1,
                  int(bool(self.use_feature_interpolation)), a.scale,
                  host_floats([vs[i] * self.win1_size[i] for i in range(3)]),
@@ -388,7 +406,7 @@ class MixedScaleSparseTransformerBlock(nn.Module):
                  ptr(a.projs[1].bias), g["cap"], ptr(g["total"]), ptr(g["win_list"]), ptr(xn),
                  ptr(sp_tensor.world_coords()), ptr(g["q_row"]), ptr(g["rep_row"]), ptr(g["meta"]),
                  ptr(g["q_base"]), ptr(g["q_src"]), ptr(g["vox_slot"]), ptr(g["win1_row"]), ptr(g["nn_idx"]),
-                 ptr(g["nn_w"]), x.shape[0],
+                 ptr(g["nn_w"]), *(ptr(v) for v in plan), x.shape[0],
                  ptr(torch.empty((3 * x.shape[0], 64), dtype=torch.float32, device=x.device)), ptr(merged),
                  stream())
         else:
