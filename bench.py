@@ -183,7 +183,7 @@ def our_arm(args):
         out_idx = [torch.empty((N_VOXELS, 4), dtype=torch.int32).pin_memory() for _ in range(2)]
         s_in, s_comp, s_out = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
 
-        def e2e_run(steps):
+        def e2e_run(steps, stamps=None):
             staged, keep, rows = {}, [], 0
 
             def stage(i):
@@ -219,6 +219,8 @@ def our_arm(args):
                 if pending is not None:      # step i is queued: now wait for step i-1's count and copy it out
                     rows = drain(*pending)
                 pending = (i, sp, done)
+                if stamps is not None:
+                    stamps.append(time.perf_counter())
                 keep.append((fd, cd, sp))    # keep device buffers alive until their copies are done
                 if len(keep) > 4:
                     keep.pop(0)
@@ -227,12 +229,21 @@ def our_arm(args):
                 st.synchronize()
             return rows
 
-        e2e_run(max(args.warmup, 3))
-        barrier()
-        t0 = time.perf_counter()
-        m = e2e_run(args.steps)
-        barrier()
-        e2e_s = time.perf_counter() - t0
+        e2e_run(max(args.warmup, 8))  # (long enough for the caching allocator to reach its steady state)
+        # three timed passes of K steps each; the median is reported, all three are listed
+        e2e_samples = []
+        for _ in range(3):
+            barrier()
+            stamps = [time.perf_counter()]
+            m = e2e_run(args.steps, stamps)
+            barrier()
+            stamps.append(time.perf_counter())
+            e2e_samples.append(stamps[-1] - stamps[0])
+            gaps = sorted(((b - a) * 1e3, k) for k, (a, b) in enumerate(zip(stamps, stamps[1:])))[-3:]
+            print(f"[bench] e2e pass {len(e2e_samples)}: {e2e_samples[-1] * 1e3:.2f} ms for {args.steps} steps; "
+                  f"longest host gaps (ms, step): {gaps}", file=sys.stderr)
+        e2e_s = sorted(e2e_samples)[1]
+        e2e_passes = [round(v / args.steps * 1e3, 4) for v in e2e_samples]
         h2d = host[0][0].numel() * 4 + host[0][1].numel() * 4
         d2h = m * 64 * 4 + m * 4 * 4
 
@@ -297,10 +308,11 @@ def our_arm(args):
                    "voxels_per_frame": N_VOXELS, "frames_per_step": world, "sharding": "by frame, no collective",
                    "l2": "inputs rotate through a pool of %d distinct frames (326 MB > 126 MB L2)" % POOL,
                    "precision": ("fp32 FFMA kernels (features within 1e-4 of max|fp32 reference|)" if args.precision == "fp32"
-                                 else "FFN GEMMs on tcgen05 with TF32 operands / fp32 accumulate, rest fp32 "
+                                 else "projections and FFN GEMMs on tcgen05 with TF32 operands / fp32 accumulate, rest fp32 "
                                       "(features within 2e-3 of max|fp32 reference|)")},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_s / args.steps * 1e3},
+                "ms_per_step": e2e_s / args.steps * 1e3, "passes_ms_per_step": e2e_passes,
+                "note": "median of 3 passes of K steps each"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,

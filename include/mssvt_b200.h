@@ -220,18 +220,19 @@ int mssvt_attention_tiles(int heads_per_group, int nq, int key_num_sample, int w
 
 /* The same step, task-parallel (one thread per query / distinct key / voxel over the whole frame) with
  * the K/V projection on the tcgen05 tensor cores (TF32 operands, fp32 everywhere else;
- * mssvt_b200/csrc/attention_tc.cu: 4 kernels).  Weights in nn.Module layout: pos_w [64][6], wq*/wp*
- * [32][32] for head groups 0 / 1, wkv* [64][32] packed by mssvt_pack_operand_tf32; rep_row / meta from mssvt_block_geometry; q_base =
+ * mssvt_b200/csrc/attention_tc.cu: 4 kernels).  Weights: pos_w [64][6] (nn.Module layout); packed by
+ * mssvt_pack_operand_tf32: wkv* [64][32] per head group, wq_packed / wp_packed = the [64][64] block-diagonal
+ * matrix of the two groups' [32][32] weights; rep_row / meta from mssvt_block_geometry; q_base =
  * mssvt_exclusive_scan(meta[:, 0]) (win_capacity + 1 ints), q_src = mssvt_query_src, vox_slot from the
  * geometry; tiles / tile_count / win_rec / win_ctr = mssvt_attention_tiles; scratch: 3 * num_voxels * 64 floats.
  * Supported: C = 64, two groups of 32 channels with 1, 2 or 4 heads each, nq <= 32,
  * key_num_sample <= 63, cap1 <= 128; -1 otherwise. */
 int mssvt_block_attention_tc(int C, int heads_per_group, int nq, int key_num_sample, int cap1, int interp,
                              float scale, const float *win_cell, const float *range_min,
-                             const float *pos_w, const float *pos_b, const float *wq0, const float *bq0,
-                             const float *wkv0, const float *bkv0, const float *wp0, const float *bp0,
-                             const float *wq1, const float *bq1, const float *wkv1, const float *bkv1,
-                             const float *wp1, const float *bp1, int win_capacity, const int *win_count_total,
+                             const float *pos_w, const float *pos_b, const float *wq_packed, const float *bq0,
+                             const float *bq1, const float *wkv0, const float *bkv0, const float *wkv1,
+                             const float *bkv1, const float *wp_packed, const float *bp0, const float *bp1,
+                             int win_capacity, const int *win_count_total,
                              const int *win_list, const float *xn, const float *xyz, const int *q_row,
                              const int *rep_row, const int *meta, const int *q_base, const int *q_src,
                              const int *vox_slot, const int *win1_row, const unsigned char *nn_idx,
@@ -246,7 +247,7 @@ int mssvt_compress_attention(const void *shape, int shape_bytes, const float *pa
 
 /* The same step, task-parallel with the second positional-embedding layer and the K/V projection on
  * the tcgen05 tensor cores (mssvt_b200/csrc/compress_tc.cu: 3 kernels).  Weights in nn.Module layout:
- * pos_w [64][6], wq / wp [64][64]; pos2_w [64][64] and wkv [128][64] packed by mssvt_pack_operand_tf32.  scratch: 2 * win_capacity * 64 floats.
+ * pos_w [64][6]; packed by mssvt_pack_operand_tf32: wq / wp / pos2_w [64][64], wkv [128][64].  scratch: 2 * win_capacity * 64 floats.
  * Supported: C = 64, one head group with 1, 2, 4 or 8 heads, two-layer pos_proj, n1 <= 127; -1 otherwise. */
 int mssvt_compress_attention_tc(int C, int heads, int n1, float scale, const float *win_cell,
                                 const float *range_min, const float *pos_w, const float *pos_b,

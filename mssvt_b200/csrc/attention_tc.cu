@@ -3,7 +3,7 @@
 // attention.cu (mssvt_backbone.py:260-336, mssvt_utils.py:88-157), different mapping: instead of one
 // warp walking through a window, every stage runs with one THREAD per task over the whole frame:
 //
-//   k_tca_query   thread = (query, head group, 8 outputs): q = (Wq (xn + posemb) + bq) * scale
+//   k_tc_linear   (tc_linear.cuh) q = (Wq (xn + posemb) + bq) * scale for every real query, on tcgen05
 //   k_tca_plan    once per frame geometry: packs consecutive windows of one scale into tiles of <= 128
 //                 distinct keys (windows without a real query are skipped), per-window offsets
 //   k_tca_keys    thread = distinct key of a window, 128 keys of ONE scale per tile.  The thread
@@ -13,7 +13,7 @@
 //                 columns; tcgen05.ld hands every thread the 64 K|V values of ITS key (TMEM lane =
 //                 thread).  Scores against the window's queries, then softmax (with the multiplicity
 //                 of the masked key) and AV with one thread per (query, head, quarter head).
-//   k_tca_proj    thread = (query, head group, 8 outputs): output projection
+//   k_tc_linear   output projection of the head outputs, on tcgen05
 //   k_tca_merge   thread = (win1 voxel, 16 channels): 1/d blend of the 3 nearest query rows -> merged
 //
 // Queries are addressed by a compact id (q_base[w] + slot, an exclusive scan over the windows done
@@ -24,9 +24,9 @@
 //
 // Supported shape (config S0 and relatives): C = 64, two head groups of 32 channels, 1/2/4 heads per
 // group, nq <= 32, key_num_sample <= 63, max_num_win1 <= 128.  Everything else runs on
-// k_block_attention.  Precision: TF32 operands for K/V only; q, scores, softmax, AV, projections and
-// interpolation are fp32.
-#include "tc_common.cuh"
+// k_block_attention.  Precision: TF32 operands for the Q, K/V and output projections; positional embedding,
+// scores, softmax, AV and interpolation are fp32.
+#include "tc_linear.cuh"
 
 namespace mssvt {
 
@@ -37,17 +37,15 @@ namespace mssvt {
 #define TCA_C 64
 #define TCA_SD 32
 #define TCA_VPITCH 36    // V row pitch in floats: 16-byte aligned, conflict-free for quarter warps
-#define TCA_WPITCH 36    // projection-weight row pitch (see stage_proj_weights)
-#define TCA_WGRP (32 * TCA_WPITCH + 16)
 
 struct TcAttnParams {
     int nq, K, cap1, interp, heads, smax;      // smax = nq * heads: score slots per key task
     float scale;
     float win_cell[3], lo[3];
     const float *pos_w, *pos_b;                // [64][6], [64]   (Conv1d weight (64, 6, 1))
-    const float *wq[2], *bq[2];                // [32][32], [32]
+    const float *wq, *bq[2];                   // blockdiag(Wq0, Wq1) [64][64] packed, [32] x 2
     const float *wkv[2], *bkv[2];              // [64][32] packed (mssvt_pack_operand_tf32), [64]
-    const float *wp[2], *bp[2];                // [32][32], [32]
+    const float *wp, *bp[2];                   // blockdiag(Wp0, Wp1) [64][64] packed, [32] x 2
 };
 
 // [64][8] per channel: w0..w5, bias, 0
@@ -55,15 +53,6 @@ __device__ __forceinline__ void stage_pos_weights(const TcAttnParams &P, float *
     for (int i = threadIdx.x; i < 64 * 8; i += blockDim.x) {
         const int c = i >> 3, k = i & 7;
         sPos[i] = k < 6 ? __ldg(P.pos_w + c * 6 + k) : k == 6 ? __ldg(P.pos_b + c) : 0.f;
-    }
-}
-
-// 32x32 projection weights of both groups: row pitch 36 floats, groups 1168 floats apart, so that the
-// 8 (group, output-phase) rows read by the lanes of a warp fall into 8 different 16-byte bank groups
-__device__ __forceinline__ void stage_proj_weights(const float *w0, const float *w1, float *sW) {
-    for (int i = threadIdx.x; i < 2 * 32 * 32; i += blockDim.x) {
-        const int g = i >> 10, o = (i >> 5) & 31, k = i & 31;
-        sW[g * TCA_WGRP + o * TCA_WPITCH + k] = __ldg((g ? w1 : w0) + (i & 1023));
     }
 }
 
@@ -76,67 +65,48 @@ __device__ __forceinline__ float pos_embed8(const float *sPos, int c, float rx, 
     return fmaxf(a, 0.f);
 }
 
-// 8 interleaved outputs (oq, oq+4, ...) of a 32 -> 32 projection for one input row held in registers;
-// the 8 accumulators are independent FMA chains
-__device__ __forceinline__ void proj8(const float *sW, const float *bias, const float *xin, int oq, float mul,
-                                      float *dst) {
-    float a[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) a[j] = bias[oq + 4 * j];
-#pragma unroll
-    for (int i4 = 0; i4 < TCA_SD / 4; ++i4) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float4 wv = *(const float4 *)(sW + (oq + 4 * j) * TCA_WPITCH + 4 * i4);
-            a[j] = fmaf(wv.x, xin[4 * i4], a[j]); a[j] = fmaf(wv.y, xin[4 * i4 + 1], a[j]);
-            a[j] = fmaf(wv.z, xin[4 * i4 + 2], a[j]); a[j] = fmaf(wv.w, xin[4 * i4 + 3], a[j]);
-        }
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) dst[oq + 4 * j] = a[j] * mul;
-}
-
 // ------------------------------------------------------------------------------- queries
 
-__global__ void __launch_bounds__(256)
-k_tca_query(TcAttnParams P, int win_cap, const int *__restrict__ win_count_total,
-            const int4 *__restrict__ win_list, const float *__restrict__ xn, const float *__restrict__ xyz,
-            const int *__restrict__ q_row, const int *__restrict__ q_base, const int *__restrict__ q_src,
-            float *__restrict__ Qbuf) {
-    __shared__ __align__(16) float sPos[64 * 8];
-    __shared__ __align__(16) float sW[2 * TCA_WGRP];
-    __shared__ float sB[64];
-    stage_pos_weights(P, sPos);
-    stage_proj_weights(P.wq[0], P.wq[1], sW);
-    for (int i = threadIdx.x; i < 64; i += blockDim.x) sB[i] = __ldg(P.bq[i >> 5] + (i & 31));
-    __syncthreads();
-    const int num_wins = min(win_cap, __ldg(win_count_total));
-    const long long total = (long long)__ldg(q_base + num_wins) * 8;  // #real queries of the frame
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
-         e += (long long)gridDim.x * blockDim.x) {
-        const int part = (int)(e & 7), g = part >> 2, oq = part & 3;
-        const size_t qid = (size_t)(e >> 3);
-        const int src = __ldg(q_src + qid), w = src / P.nq;
+// rows of k_tc_linear for the query projection: compact query id -> layer-normed row + positional embedding
+struct TcaQueryRows {
+    int nq, win_cap;
+    float win_cell[3], lo[3];
+    const float *pos_w, *pos_b;
+    const int *win_count_total;
+    const int4 *win_list;
+    const float *xn, *xyz;
+    const int *q_row, *q_base, *q_src;
+    __device__ void init(float *sPos) const {
+        for (int i = threadIdx.x; i < 64 * 8; i += blockDim.x) {
+            const int c = i >> 3, k = i & 7;
+            sPos[i] = k < 6 ? __ldg(pos_w + c * 6 + k) : k == 6 ? __ldg(pos_b + c) : 0.f;
+        }
+    }
+    __device__ int rows() const { return __ldg(q_base + min(win_cap, __ldg(win_count_total))); }
+    __device__ void load(int qid, int half, const float *sPos, float *in) const {
+        const int src = __ldg(q_src + qid), w = src / nq;
         const int row = __ldg(q_row + src);
         const int4 win = __ldg(win_list + w);
-        const float cx = world_coord(win.w, P.win_cell[0], P.lo[0]);
-        const float cy = world_coord(win.z, P.win_cell[1], P.lo[1]);
-        const float cz = world_coord(win.y, P.win_cell[2], P.lo[2]);
+        const float cx = world_coord(win.w, win_cell[0], lo[0]);
+        const float cy = world_coord(win.z, win_cell[1], lo[1]);
+        const float cz = world_coord(win.y, win_cell[2], lo[2]);
         const float rx = __fsub_rn(__ldg(xyz + 3 * (size_t)row), cx);
         const float ry = __fsub_rn(__ldg(xyz + 3 * (size_t)row + 1), cy);
         const float rz = __fsub_rn(__ldg(xyz + 3 * (size_t)row + 2), cz);
-        float xin[TCA_SD];
+        const float4 *p = (const float4 *)(xn + (size_t)row * TCA_C + half * TCA_SD);
+        float4 xv[TCA_SD / 4];
+#pragma unroll
+        for (int c4 = 0; c4 < TCA_SD / 4; ++c4) xv[c4] = __ldg(p + c4);
 #pragma unroll
         for (int c4 = 0; c4 < TCA_SD / 4; ++c4) {
-            const float4 v = __ldg((const float4 *)(xn + (size_t)row * TCA_C + g * TCA_SD) + c4);
-            xin[4 * c4] = v.x + pos_embed8(sPos, g * TCA_SD + 4 * c4, rx, ry, rz, cx, cy, cz);
-            xin[4 * c4 + 1] = v.y + pos_embed8(sPos, g * TCA_SD + 4 * c4 + 1, rx, ry, rz, cx, cy, cz);
-            xin[4 * c4 + 2] = v.z + pos_embed8(sPos, g * TCA_SD + 4 * c4 + 2, rx, ry, rz, cx, cy, cz);
-            xin[4 * c4 + 3] = v.w + pos_embed8(sPos, g * TCA_SD + 4 * c4 + 3, rx, ry, rz, cx, cy, cz);
+            const int c = half * TCA_SD + 4 * c4;
+            in[4 * c4] = xv[c4].x + pos_embed8(sPos, c, rx, ry, rz, cx, cy, cz);
+            in[4 * c4 + 1] = xv[c4].y + pos_embed8(sPos, c + 1, rx, ry, rz, cx, cy, cz);
+            in[4 * c4 + 2] = xv[c4].z + pos_embed8(sPos, c + 2, rx, ry, rz, cx, cy, cz);
+            in[4 * c4 + 3] = xv[c4].w + pos_embed8(sPos, c + 3, rx, ry, rz, cx, cy, cz);
         }
-        proj8(sW + g * TCA_WGRP, sB + g * TCA_SD, xin, oq, P.scale, Qbuf + qid * TCA_C + g * TCA_SD);
     }
-}
+};
 
 // ------------------------------------------------------------------------------- tile plan
 
@@ -400,32 +370,6 @@ k_tca_keys(TcAttnParams P, int win_cap, const int2 *__restrict__ tiles, const in
     if (warp == 0) tmem_dealloc(tmem_d, 64);
 }
 
-// ------------------------------------------------------------------------------- output projection
-
-__global__ void __launch_bounds__(256)
-k_tca_proj(TcAttnParams P, int win_cap, const int *__restrict__ win_count_total,
-           const int *__restrict__ q_base, const float *__restrict__ Obuf, float *__restrict__ Pbuf) {
-    __shared__ __align__(16) float sW[2 * TCA_WGRP];
-    __shared__ float sB[64];
-    stage_proj_weights(P.wp[0], P.wp[1], sW);
-    for (int i = threadIdx.x; i < 64; i += blockDim.x) sB[i] = __ldg(P.bp[i >> 5] + (i & 31));
-    __syncthreads();
-    const int num_wins = min(win_cap, __ldg(win_count_total));
-    const long long total = (long long)__ldg(q_base + num_wins) * 8;  // #real queries of the frame
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
-         e += (long long)gridDim.x * blockDim.x) {
-        const int part = (int)(e & 7), g = part >> 2, oq = part & 3;
-        const size_t qid = (size_t)(e >> 3);
-        float xin[TCA_SD];
-#pragma unroll
-        for (int i4 = 0; i4 < TCA_SD / 4; ++i4) {
-            const float4 v = __ldg((const float4 *)(Obuf + qid * TCA_C + g * TCA_SD) + i4);
-            xin[4 * i4] = v.x; xin[4 * i4 + 1] = v.y; xin[4 * i4 + 2] = v.z; xin[4 * i4 + 3] = v.w;
-        }
-        proj8(sW + g * TCA_WGRP, sB + g * TCA_SD, xin, oq, 1.0f, Pbuf + qid * TCA_C + g * TCA_SD);
-    }
-}
-
 // ------------------------------------------------------------------------------- merge
 
 __global__ void __launch_bounds__(256)
@@ -522,18 +466,18 @@ int mssvt_attention_tiles(int heads_per_group, int nq, int key_num_sample, int w
 }
 
 /* Tensor-core window attention of a two-window block (see the header of this file).  Weights in
- * their nn.Module layout: pos_w [64][6], wq/wp [32][32] per head group; wkv [64][32] packed by
- * mssvt_pack_operand_tf32.  rep_row / meta: compact key lists of mssvt_block_geometry; q_base:
+ * their nn.Module layout: pos_w [64][6]; packed by mssvt_pack_operand_tf32: wkv [64][32] per head group,
+ * wq_packed / wp_packed = the [64][64] block-diagonal matrix of the two groups' [32][32] weights.  rep_row / meta: compact key lists of mssvt_block_geometry; q_base:
  * mssvt_exclusive_scan of meta[:, 0] (win_capacity + 1 ints); tiles .. win_ctr: mssvt_attention_tiles.
  * scratch: 3 * num_voxels * 64 floats (q, head outputs, projected rows of every real query).
  * Returns MSSVT_ERR_INVALID for shapes outside C = 64 / 2 x 32 channels / nq <= 32 / K <= 63 /
  * cap1 <= 128 (callers then use mssvt_block_attention). */
 int mssvt_block_attention_tc(int C, int heads_per_group, int nq, int key_num_sample, int cap1, int interp,
                              float scale, const float *win_cell, const float *range_min,
-                             const float *pos_w, const float *pos_b, const float *wq0, const float *bq0,
-                             const float *wkv0, const float *bkv0, const float *wp0, const float *bp0,
-                             const float *wq1, const float *bq1, const float *wkv1, const float *bkv1,
-                             const float *wp1, const float *bp1, int win_capacity, const int *win_count_total,
+                             const float *pos_w, const float *pos_b, const float *wq_packed, const float *bq0,
+                             const float *bq1, const float *wkv0, const float *bkv0, const float *wkv1,
+                             const float *bkv1, const float *wp_packed, const float *bp0, const float *bp1,
+                             int win_capacity, const int *win_count_total,
                              const int *win_list, const float *xn, const float *xyz, const int *q_row,
                              const int *rep_row, const int *meta, const int *q_base, const int *q_src,
                              const int *vox_slot, const int *win1_row, const unsigned char *nn_idx,
@@ -544,8 +488,8 @@ int mssvt_block_attention_tc(int C, int heads_per_group, int nq, int key_num_sam
         nq * (key_num_sample + 1) * heads_per_group > TCA_SBUD)
         return MSSVT_ERR_INVALID;
     if (win_capacity == 0) return MSSVT_OK;
-    if (!win_cell || !range_min || !pos_w || !pos_b || !wq0 || !bq0 || !wkv0 || !bkv0 || !wp0 || !bp0 || !wq1 ||
-        !bq1 || !wkv1 || !bkv1 || !wp1 || !bp1 || !win_count_total || !win_list || !xn || !xyz || !q_row ||
+    if (!win_cell || !range_min || !pos_w || !pos_b || !wq_packed || !bq0 || !wkv0 || !bkv0 || !wp_packed || !bp0 ||
+        !bq1 || !wkv1 || !bkv1 || !bp1 || !win_count_total || !win_list || !xn || !xyz || !q_row ||
         !rep_row || !meta || !q_base || !q_src || !tiles || !tile_count || !win_rec || !win_ctr || !scratch || !merged)
         return MSSVT_ERR_INVALID;
     if (interp && (!vox_slot || !nn_idx || !nn_w)) return MSSVT_ERR_INVALID;
@@ -556,16 +500,23 @@ int mssvt_block_attention_tc(int C, int heads_per_group, int nq, int key_num_sam
     P.scale = scale;
     for (int i = 0; i < 3; ++i) { P.win_cell[i] = win_cell[i]; P.lo[i] = range_min[i]; }
     P.pos_w = pos_w; P.pos_b = pos_b;
-    P.wq[0] = wq0; P.bq[0] = bq0; P.wkv[0] = wkv0; P.bkv[0] = bkv0; P.wp[0] = wp0; P.bp[0] = bp0;
-    P.wq[1] = wq1; P.bq[1] = bq1; P.wkv[1] = wkv1; P.bkv[1] = bkv1; P.wp[1] = wp1; P.bp[1] = bp1;
+    P.wq = wq_packed; P.bq[0] = bq0; P.wkv[0] = wkv0; P.bkv[0] = bkv0; P.wp = wp_packed; P.bp[0] = bp0;
+    P.bq[1] = bq1; P.wkv[1] = wkv1; P.bkv[1] = bkv1; P.bp[1] = bp1;
     const size_t smem = tca_keys_smem_bytes();
     float *Qbuf = scratch, *Obuf = scratch + (size_t)num_voxels * 64, *Pbuf = scratch + 2 * (size_t)num_voxels * 64;
     cudaStream_t s = (cudaStream_t)stream;
     const int4 *wl = (const int4 *)win_list;
     const int wide = MSSVT_NUM_SMS * 8;  // grid-stride kernels: 8 CTAs of 256 threads per SM
 
-    ++g_launches;
-    k_tca_query<<<wide, 256, 0, s>>>(P, win_capacity, win_count_total, wl, xn, xyz, q_row, q_base, q_src, Qbuf);
+    {
+        TcaQueryRows rows;
+        rows.nq = nq; rows.win_cap = win_capacity;
+        for (int i = 0; i < 3; ++i) { rows.win_cell[i] = win_cell[i]; rows.lo[i] = range_min[i]; }
+        rows.pos_w = pos_w; rows.pos_b = pos_b; rows.win_count_total = win_count_total; rows.win_list = wl;
+        rows.xn = xn; rows.xyz = xyz; rows.q_row = q_row; rows.q_base = q_base; rows.q_src = q_src;
+        const TclParams L = {wq_packed, bq0, bq1, scale};
+        tcl_launch(L, rows, num_voxels, Qbuf, s);
+    }
 
     int per_sm = (int)(227 * 1024 / (smem + 1024));
     per_sm = per_sm > 5 ? 5 : per_sm < 1 ? 1 : per_sm;  // (64 TMEM columns each)
@@ -581,8 +532,11 @@ int mssvt_block_attention_tc(int C, int heads_per_group, int nq, int key_num_sam
     else { TCA_LAUNCH(4); }
 #undef TCA_LAUNCH
 
-    ++g_launches;
-    k_tca_proj<<<wide, 256, 0, s>>>(P, win_capacity, win_count_total, q_base, Obuf, Pbuf);
+    {
+        const TclCopyRows rows = {Obuf, win_count_total, q_base, win_capacity};
+        const TclParams L = {wp_packed, bp0, bp1, 1.0f};
+        tcl_launch(L, rows, num_voxels, Pbuf, s);
+    }
     ++g_launches;
     k_tca_merge<<<wide, 256, 0, s>>>(P, win_capacity, win_count_total, num_voxels, meta, q_base, q_src, q_row,
                                      vox_slot, nn_idx, nn_w, Pbuf, merged);

@@ -3,7 +3,7 @@
 // Same mathematics as k_compress_attention in attention.cu
 // (MixedScaleSparseTransformerCompressBlock.forward, mssvt_backbone.py:361-383):
 //
-//   k_tcc_query   thread = (window, 8 outputs): q = (Wq maxpool(window rows incl. zero padding) + bq) * scale
+//   k_tc_linear   (tc_linear.cuh) q = (Wq maxpool(window rows incl. zero padding) + bq) * scale, on tcgen05
 //   k_tcc_keys    thread = key of a window: one per voxel + one "pad key" per window that has padded
 //                 slots (all padded slots carry the same key: zero feature, offset 0 - centre, mask -100,
 //                 multiplicity = #padded slots).  128 keys per tile:
@@ -11,11 +11,11 @@
 //                   A2 = xn + relu(D1 + b2)              -> 8 x tcgen05.mma  D2 = A2 Wkv^T       (N = 128)
 //                 K|V come back per thread through tcgen05.ld; scores against the window's query,
 //                 then softmax + AV with one thread per (window, head, quarter head).
-//   k_tcc_proj    thread = (window, 8 outputs): output projection -> one row per window
+//   k_tc_linear   output projection -> one row per window, on tcgen05
 //
 // Supported shape: C = 64, one head group (1, 2, 4 or 8 heads), two-layer pos_proj, max_num_win1 <= 127.
 // Everything else runs on k_compress_attention.  TF32 operands for the two tensor-core GEMMs only.
-#include "tc_common.cuh"
+#include "tc_linear.cuh"
 
 namespace mssvt {
 
@@ -23,7 +23,6 @@ namespace mssvt {
 #define TCC_WB 64        // windows per batch (tile candidates)
 #define TCC_C 64
 #define TCC_VPITCH 68    // V row pitch in floats (16-byte aligned, conflict-free for quarter warps)
-#define TCC_WPITCH 68    // 64 x 64 projection weight row pitch
 
 struct TccParams {
     int n1, heads;
@@ -31,72 +30,39 @@ struct TccParams {
     float win_cell[3], lo[3];
     const float *pos_w, *pos_b;    // [64][6], [64]
     const float *pos2_w, *pos2_b;  // [64][64] packed (mssvt_pack_operand_tf32), [64]
-    const float *wq, *bq;          // [64][64], [64]
+    const float *wq, *bq;          // [64][64] packed, [64]
     const float *wkv, *bkv;        // [128][64] packed, [128]
-    const float *wp, *bp;          // [64][64], [64]
+    const float *wp, *bp;          // [64][64] packed, [64]
 };
-
-// 64 x 64 weights with row pitch 68 floats: the 8 output-phase rows read by the lanes of a warp
-// (rows oq, oq + 8, ... for 8 values of oq) fall into different 16-byte bank groups
-__device__ __forceinline__ void stage_w64(const float *w, float *sW) {
-    for (int i = threadIdx.x; i < 64 * 64; i += blockDim.x) sW[(i >> 6) * TCC_WPITCH + (i & 63)] = __ldg(w + i);
-}
-
-// 8 interleaved outputs (oq, oq + 8, ...) of a 64 -> 64 projection for one input row in registers
-__device__ __forceinline__ void proj64x8(const float *sW, const float *bias, const float *xin, int oq, float mul,
-                                         float *dst) {
-    float a[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) a[j] = bias[oq + 8 * j];
-#pragma unroll
-    for (int i4 = 0; i4 < TCC_C / 4; ++i4) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float4 wv = *(const float4 *)(sW + (oq + 8 * j) * TCC_WPITCH + 4 * i4);
-            a[j] = fmaf(wv.x, xin[4 * i4], a[j]); a[j] = fmaf(wv.y, xin[4 * i4 + 1], a[j]);
-            a[j] = fmaf(wv.z, xin[4 * i4 + 2], a[j]); a[j] = fmaf(wv.w, xin[4 * i4 + 3], a[j]);
-        }
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) dst[oq + 8 * j] = a[j] * mul;
-}
 
 // ------------------------------------------------------------------------------- query
 
-__global__ void __launch_bounds__(256)
-k_tcc_query(TccParams P, int win_cap, const int *__restrict__ win_count_total, const float *__restrict__ xn,
-            const int *__restrict__ k_row, float *__restrict__ Qc) {
-    extern __shared__ __align__(16) float smq[];
-    float *sW = smq, *sB = smq + 64 * TCC_WPITCH;
-    stage_w64(P.wq, sW);
-    for (int i = threadIdx.x; i < 64; i += blockDim.x) sB[i] = __ldg(P.bq + i);
-    __syncthreads();
-    const int num_wins = min(win_cap, __ldg(win_count_total));
-    const long long total = (long long)num_wins * 8;
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
-         e += (long long)gridDim.x * blockDim.x) {
-        const int oq = (int)(e & 7);
-        const size_t w = (size_t)(e >> 3);
-        const int *kr = k_row + w * P.n1;
-        // channel-wise max over the n1 slots; padded slots contribute zeros (Q6)
-        float xin[TCC_C];
-        const bool full = __ldg(kr + P.n1 - 1) >= 0;
+// rows of k_tc_linear for the query projection: channel-wise max over the window's n1 slots; padded
+// slots contribute zeros (Q6)
+struct TccQueryRows {
+    int n1, win_cap;
+    const int *win_count_total, *k_row;
+    const float *xn;
+    __device__ void init(float *) const {}
+    __device__ int rows() const { return min(win_cap, __ldg(win_count_total)); }
+    __device__ void load(int w, int half, const float *, float *in) const {
+        const int *kr = k_row + (size_t)w * n1;
+        const bool full = __ldg(kr + n1 - 1) >= 0;
 #pragma unroll
-        for (int c = 0; c < TCC_C; ++c) xin[c] = full ? -3.0e38f : 0.f;
-        for (int t = 0; t < P.n1; ++t) {
+        for (int c = 0; c < 32; ++c) in[c] = full ? -3.0e38f : 0.f;
+        for (int t = 0; t < n1; ++t) {
             const int row = __ldg(kr + t);
             if (row < 0) break;  // real slots are compacted at the front
-            const float4 *src = (const float4 *)(xn + (size_t)row * TCC_C);
+            const float4 *src = (const float4 *)(xn + (size_t)row * TCC_C + half * 32);
 #pragma unroll
-            for (int c4 = 0; c4 < TCC_C / 4; ++c4) {
+            for (int c4 = 0; c4 < 8; ++c4) {
                 const float4 v = __ldg(src + c4);
-                xin[4 * c4] = fmaxf(xin[4 * c4], v.x); xin[4 * c4 + 1] = fmaxf(xin[4 * c4 + 1], v.y);
-                xin[4 * c4 + 2] = fmaxf(xin[4 * c4 + 2], v.z); xin[4 * c4 + 3] = fmaxf(xin[4 * c4 + 3], v.w);
+                in[4 * c4] = fmaxf(in[4 * c4], v.x); in[4 * c4 + 1] = fmaxf(in[4 * c4 + 1], v.y);
+                in[4 * c4 + 2] = fmaxf(in[4 * c4 + 2], v.z); in[4 * c4 + 3] = fmaxf(in[4 * c4 + 3], v.w);
             }
         }
-        proj64x8(sW, sB, xin, oq, P.scale, Qc + w * TCC_C);
     }
-}
+};
 
 // ------------------------------------------------------------------------------- keys + attention
 
@@ -346,32 +312,6 @@ k_tcc_keys(TccParams P, int win_cap, const int *__restrict__ win_count_total, co
     if (warp == 0) tmem_dealloc(tmem_base, 256);
 }
 
-// ------------------------------------------------------------------------------- output projection
-
-__global__ void __launch_bounds__(256)
-k_tcc_proj(TccParams P, int win_cap, const int *__restrict__ win_count_total, const float *__restrict__ Oc,
-           float *__restrict__ out) {
-    extern __shared__ __align__(16) float smq[];
-    float *sW = smq, *sB = smq + 64 * TCC_WPITCH;
-    stage_w64(P.wp, sW);
-    for (int i = threadIdx.x; i < 64; i += blockDim.x) sB[i] = __ldg(P.bp + i);
-    __syncthreads();
-    const int num_wins = min(win_cap, __ldg(win_count_total));
-    const long long total = (long long)num_wins * 8;
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
-         e += (long long)gridDim.x * blockDim.x) {
-        const int oq = (int)(e & 7);
-        const size_t w = (size_t)(e >> 3);
-        float xin[TCC_C];
-#pragma unroll
-        for (int c4 = 0; c4 < TCC_C / 4; ++c4) {
-            const float4 v = __ldg((const float4 *)(Oc + w * TCC_C) + c4);
-            xin[4 * c4] = v.x; xin[4 * c4 + 1] = v.y; xin[4 * c4 + 2] = v.z; xin[4 * c4 + 3] = v.w;
-        }
-        proj64x8(sW, sB, xin, oq, 1.0f, out + w * TCC_C);
-    }
-}
-
 static size_t tcc_keys_smem_bytes(int heads) {
     size_t floats = TCC_THREADS * TCC_VPITCH + 64 * 8 + 64 + 128 + (size_t)TCC_THREADS * heads + TCC_WB * 4;
     size_t ints = 2 * TCC_WB + 1 + 2 * TCC_THREADS + 4;
@@ -386,8 +326,8 @@ using namespace mssvt;
 extern "C" {
 
 /* Tensor-core attention of a one-window (compress) block (see the header of this file).  Weights in
- * nn.Module layout: pos_w [64][6], wq / wp [64][64]; pos2_w [64][64] and wkv [128][64] packed by
- * mssvt_pack_operand_tf32.  k_row: (cap, n1)
+ * nn.Module layout: pos_w [64][6]; packed by mssvt_pack_operand_tf32: wq / wp / pos2_w [64][64] and
+ * wkv [128][64].  k_row: (cap, n1)
  * global rows from mssvt_window_rows.  scratch: 2 * win_capacity * 64 floats.  out: (cap, 64).
  * Supported: C = 64, one head group with 1, 2, 4 or 8 heads, n1 <= 127; -1 otherwise. */
 int mssvt_compress_attention_tc(int C, int heads, int n1, float scale, const float *win_cell,
@@ -410,11 +350,11 @@ int mssvt_compress_attention_tc(int C, int heads, int n1, float scale, const flo
     P.wq = wq; P.bq = bq; P.wkv = wkv; P.bkv = bkv; P.wp = wp; P.bp = bp;
     float *Qc = scratch, *Oc = scratch + (size_t)win_capacity * 64;
     cudaStream_t s = (cudaStream_t)stream;
-    const int wide = MSSVT_NUM_SMS * 4;
-    const size_t smq = (64 * TCC_WPITCH + 64) * sizeof(float);
-
-    ++g_launches;
-    k_tcc_query<<<wide, 256, smq, s>>>(P, win_capacity, win_count_total, xn, k_row, Qc);
+    {
+        const TccQueryRows rows = {n1, win_capacity, win_count_total, k_row, xn};
+        const TclParams L = {wq, bq, nullptr, scale};
+        tcl_launch(L, rows, win_capacity, Qc, s);
+    }
 
     const size_t smem = tcc_keys_smem_bytes(heads);
     if (smem > 227 * 1024) return MSSVT_ERR_INVALID;
@@ -433,8 +373,11 @@ int mssvt_compress_attention_tc(int C, int heads, int n1, float scale, const flo
     else { TCC_LAUNCH(8); }
 #undef TCC_LAUNCH
 
-    ++g_launches;
-    k_tcc_proj<<<wide, 256, smq, s>>>(P, win_capacity, win_count_total, Oc, out);
+    {
+        const TclCopyRows rows = {Oc, win_count_total, nullptr, win_capacity};
+        const TclParams L = {wp, bp, nullptr, 1.0f};
+        tcl_launch(L, rows, win_capacity, out, s);
+    }
     return check_launch();
 }
 

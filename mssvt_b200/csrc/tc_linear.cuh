@@ -1,0 +1,141 @@
+// tc_linear.cuh -- out[r] = (W in[r] + b) * mul for 64-channel rows on the tcgen05 tensor cores.
+// The small projections of the attention blocks (queries, outputs) are row-wise 64 x 64 linear maps over
+// 10^4..10^5 rows; with one thread per (row, 8 outputs) on the FP32 pipe they are bound by the shared-memory
+// reads of the weights.  Here a CTA of 256 threads owns a tile of 128 rows (threads t and t + 128 share
+// row t: 32 channels each, both reach TMEM lane t); a PRODUCER functor builds the input row (gather,
+// positional embedding, max-pool ...), the thread stores it TF32-rounded as the A operand, one thread
+// issues 8 tcgen05.mma (M = 128, N = 64, K = 8) against the packed weight (mssvt_pack_operand_tf32; two
+// head groups = one block-diagonal 64 x 64 matrix) and every thread reads its 32 outputs back from TMEM.
+// 49 KB of shared memory and 64 TMEM columns per CTA: four CTAs per SM.
+#pragma once
+#include "tc_common.cuh"
+
+namespace mssvt {
+
+#define TCL_ROWS 128
+#define TCL_THREADS 256
+#define TCL_C 64
+
+struct TclParams {
+    const float *w_packed;  // [64][64] packed
+    const float *bias;      // [64] (bias_hi == nullptr) or [32] + bias_hi [32]
+    const float *bias_hi;
+    float mul;
+};
+
+static inline size_t tcl_smem_bytes() { return TCL_ROWS * TCL_C * 4 + TCL_C * TCL_C * 4 + TCL_C * 4 + 2048 + 8 + 16 + 128; }
+
+// Producer: struct with
+//   __device__ void init(float *s_extra)            cooperative, before the first barrier (s_extra: 2 KB)
+//   __device__ int rows() const                     number of rows (device-side count)
+//   __device__ void load(int row, int half, const float *s_extra, float *in /*[32]*/) const
+
+// rows copied from a dense (rows, 64) array; row count = min(cap, *count), optionally mapped through
+// an index array (count_map[n], e.g. a prefix sum)
+struct TclCopyRows {
+    const float *src;
+    const int *count, *count_map;
+    int cap;
+    __device__ void init(float *) const {}
+    __device__ int rows() const {
+        const int n = min(cap, __ldg(count));
+        return count_map ? __ldg(count_map + n) : n;
+    }
+    __device__ void load(int row, int half, const float *, float *in) const {
+        const float4 *p = (const float4 *)(src + (size_t)row * TCL_C + half * 32);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const float4 v = __ldg(p + c);
+            in[4 * c] = v.x; in[4 * c + 1] = v.y; in[4 * c + 2] = v.z; in[4 * c + 3] = v.w;
+        }
+    }
+};
+template <class Producer>
+__global__ void __launch_bounds__(TCL_THREADS, 4)
+k_tc_linear(TclParams P, Producer prod, float *__restrict__ out) {
+    extern __shared__ __align__(128) char smem_raw[];
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int r = tid & (TCL_ROWS - 1), half = tid >> 7;
+    char *sA = smem_raw;                           // [16][128][16 B]
+    char *sW = sA + TCL_ROWS * TCL_C * 4;          // [16][64][16 B]
+    float *sB = (float *)(sW + TCL_C * TCL_C * 4); // [64]
+    float *sExtra = sB + TCL_C;                    // producer scratch (2 KB)
+    uint64_t *sBar = (uint64_t *)(sExtra + 512);
+    uint32_t *sTmem = (uint32_t *)(sBar + 1);
+
+    stage_packed(P.w_packed, TCL_C * TCL_C, sW);
+    if (tid < TCL_C) sB[tid] = P.bias_hi && tid >= 32 ? __ldg(P.bias_hi + tid - 32) : __ldg(P.bias + tid);
+    prod.init(sExtra);
+    const uint32_t bar = smem_u32(sBar);
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) tmem_alloc(smem_u32(sTmem), 64);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = *sTmem;
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t idesc = umma_idesc_tf32(TCL_ROWS, TCL_C);
+    const uint32_t sA_u = smem_u32(sA), sW_u = smem_u32(sW);
+    const uint32_t a_lbo = TCL_ROWS * 16, w_lbo = TCL_C * 16;
+    const uint32_t my_row_off = (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u;
+    const int n = prod.rows();
+    const int tiles = (n + TCL_ROWS - 1) / TCL_ROWS;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, phase ^= 1u) {
+        const int row = tile * TCL_ROWS + r;
+        const bool live = row < n;
+        float in[32];
+        if (live) prod.load(row, half, sExtra, in);
+        else {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) in[c] = 0.f;
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+            *(float4 *)(sA + (uint32_t)(half * 8 + c) * a_lbo + my_row_off) =
+                make_float4(to_tf32(in[4 * c]), to_tf32(in[4 * c + 1]), to_tf32(in[4 * c + 2]), to_tf32(in[4 * c + 3]));
+        stage_packed_wait();
+        fence_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+#pragma unroll
+            for (int k = 0; k < TCL_C / 8; ++k)
+                umma_tf32(tmem_d, umma_smem_desc(sA_u + (uint32_t)k * 2u * a_lbo, a_lbo, 128),
+                          umma_smem_desc(sW_u + (uint32_t)k * 2u * w_lbo, w_lbo, 128), idesc, k > 0 ? 1u : 0u);
+            umma_commit(bar);
+        }
+        mbar_wait(bar, phase);
+        tc_fence_after();
+        float d[32];
+        tmem_ld32(tmem_d + lane_off + (uint32_t)(half * 32), d);
+        if (live) {
+            float4 *dst = (float4 *)(out + (size_t)row * TCL_C + half * 32);
+            const float *bb = sB + half * 32;
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                dst[q] = make_float4((d[4 * q] + bb[4 * q]) * P.mul, (d[4 * q + 1] + bb[4 * q + 1]) * P.mul,
+                                     (d[4 * q + 2] + bb[4 * q + 2]) * P.mul, (d[4 * q + 3] + bb[4 * q + 3]) * P.mul);
+        }
+        tc_fence_before();
+        __syncthreads();  // TMEM and the A tile are free for the next tile
+    }
+    if (warp == 0) tmem_dealloc(tmem_d, 64);
+}
+
+template <class Producer>
+static inline void tcl_launch(const TclParams &P, const Producer &prod, int row_capacity, float *out, cudaStream_t s) {
+    const size_t smem = tcl_smem_bytes();
+    int tiles = (row_capacity + TCL_ROWS - 1) / TCL_ROWS;
+    int grid = MSSVT_NUM_SMS * 4;
+    if (grid > tiles) grid = tiles;
+    if (grid < 1) return;
+    cudaFuncSetAttribute(k_tc_linear<Producer>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    ++g_launches;
+    k_tc_linear<Producer><<<grid, TCL_THREADS, smem, s>>>(P, prod, out);
+}
+
+}  // namespace mssvt

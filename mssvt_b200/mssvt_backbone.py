@@ -315,15 +315,17 @@ class MixedScaleSparseTransformerBlock(nn.Module):
             S.lo[i] = sp_tensor.point_cloud_range[i]
         return S, buf
 
-    def _packed(self, weight):
+    def _packed(self, *weights):
         """tensor-core operand form of an nn.Linear / 1x1 Conv1d weight (TF32, K-major core matrices),
-        packed once and cached until the parameter is modified or moved"""
+        packed once and cached until the parameter is modified or moved; several weights = their
+        block-diagonal matrix (one GEMM for all head groups)"""
         cache = self.__dict__.setdefault("_packed_ops", {})
-        key = id(weight)
-        tag = (weight.data_ptr(), weight._version)
+        key = tuple(id(w) for w in weights)
+        tag = tuple((w.data_ptr(), w._version) for w in weights)
         hit = cache.get(key)
         if hit is None or hit[0] != tag:
-            w2d = weight.detach().reshape(weight.shape[0], -1).float().contiguous()
+            mats = [w.detach().reshape(w.shape[0], -1).float() for w in weights]
+            w2d = (mats[0] if len(mats) == 1 else torch.block_diag(*mats)).contiguous()
             out = torch.empty_like(w2d)
             call("mssvt_pack_operand_tf32", ptr(w2d), w2d.shape[0], w2d.shape[1], ptr(out), stream())
             hit = cache[key] = (tag, out)
@@ -399,10 +401,10 @@ class MixedScaleSparseTransformerBlock(nn.Module):
                  int(bool(self.use_feature_interpolation)), a.scale,
                  host_floats([vs[i] * self.win1_size[i] for i in range(3)]),
                  host_floats(sp_tensor.point_cloud_range[0:3]), ptr(self.pos_proj[0].weight),
-                 ptr(self.pos_proj[0].bias), ptr(a.to_qs[0].weight), ptr(a.to_qs[0].bias),
-                 ptr(self._packed(a.to_kvs[0].weight)),
-                 ptr(a.to_kvs[0].bias), ptr(a.projs[0].weight), ptr(a.projs[0].bias), ptr(a.to_qs[1].weight),
-                 ptr(a.to_qs[1].bias), ptr(self._packed(a.to_kvs[1].weight)), ptr(a.to_kvs[1].bias), ptr(a.projs[1].weight),
+                 ptr(self.pos_proj[0].bias), ptr(self._packed(a.to_qs[0].weight, a.to_qs[1].weight)),
+                 ptr(a.to_qs[0].bias), ptr(a.to_qs[1].bias), ptr(self._packed(a.to_kvs[0].weight)),
+                 ptr(a.to_kvs[0].bias), ptr(self._packed(a.to_kvs[1].weight)), ptr(a.to_kvs[1].bias),
+                 ptr(self._packed(a.projs[0].weight, a.projs[1].weight)), ptr(a.projs[0].bias),
                  ptr(a.projs[1].bias), g["cap"], ptr(g["total"]), ptr(g["win_list"]), ptr(xn),
                  ptr(sp_tensor.world_coords()), ptr(g["q_row"]), ptr(g["rep_row"]), ptr(g["meta"]),
                  ptr(g["q_base"]), ptr(g["q_src"]), ptr(g["vox_slot"]), ptr(g["win1_row"]), ptr(g["nn_idx"]),
@@ -456,9 +458,9 @@ class MixedScaleSparseTransformerCompressBlock(MixedScaleSparseTransformerBlock)
                  host_floats([vs[i] * self.win1_size[i] for i in range(3)]),
                  host_floats(sp_tensor.point_cloud_range[0:3]), ptr(self.pos_proj[0].weight),
                  ptr(self.pos_proj[0].bias), ptr(self._packed(self.pos_proj[2].weight)), ptr(self.pos_proj[2].bias),
-                 ptr(a.to_qs[0].weight), ptr(a.to_qs[0].bias), ptr(self._packed(a.to_kvs[0].weight)),
+                 ptr(self._packed(a.to_qs[0].weight)), ptr(a.to_qs[0].bias), ptr(self._packed(a.to_kvs[0].weight)),
                  ptr(a.to_kvs[0].bias),
-                 ptr(a.projs[0].weight), ptr(a.projs[0].bias), cap, ptr(total), ptr(win_list), ptr(xn),
+                 ptr(self._packed(a.projs[0].weight)), ptr(a.projs[0].bias), cap, ptr(total), ptr(win_list), ptr(xn),
                  ptr(sp_tensor.world_coords()), ptr(k_row), ptr(scratch), ptr(attn), stream())
         else:
             S, buf = self._attn_descriptor(sp_tensor, 1, n1, n1)
