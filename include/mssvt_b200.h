@@ -247,8 +247,8 @@ int mssvt_compress_attention(const void *shape, int shape_bytes, const float *pa
 
 /* The same step, task-parallel with the second positional-embedding layer and the K/V projection on
  * the tcgen05 tensor cores (mssvt_b200/csrc/compress_tc.cu: 3 kernels).  Weights in nn.Module layout:
- * pos_w [64][6]; packed by mssvt_pack_operand_tf32: wq / wp / pos2_w [64][64], wkv [128][64].  scratch: 2 * win_capacity * 64 floats.
- * Supported: C = 64, one head group with 1, 2, 4 or 8 heads, two-layer pos_proj, n1 <= 127; -1 otherwise. */
+ * pos_w [64][6]; packed by mssvt_pack_operand_tf32: wq / wp / pos2_w [64][64], wkv [128][64].  scratch: 4 * win_capacity * 64 floats.
+ * Supported: C = 64, one head group with 2, 4 or 8 heads, two-layer pos_proj, n1 <= 127; -1 otherwise. */
 int mssvt_compress_attention_tc(int C, int heads, int n1, float scale, const float *win_cell,
                                 const float *range_min, const float *pos_w, const float *pos_b,
                                 const float *pos2_w, const float *pos2_b, const float *wq, const float *bq,

@@ -450,10 +450,10 @@ class MixedScaleSparseTransformerCompressBlock(MixedScaleSparseTransformerBlock)
         attn = torch.empty((cap, self.in_channels), dtype=torch.float32, device=dev)
         a = self.ms_attn
         if (self.precision == "tf32" and self.in_channels == 64 and a.num_head_groups == 1
-                and a.num_heads[0] in (1, 2, 4, 8) and len(self.pos_proj) == 4 and n1 <= 127):
+                and a.num_heads[0] in (2, 4, 8) and len(self.pos_proj) == 4 and n1 <= 127):
             # task-parallel kernels; second pos_proj layer and K/V projection on the tcgen05 tensor cores
             vs = sp_tensor.voxel_size
-            scratch = torch.empty((2 * cap, 64), dtype=torch.float32, device=dev)
+            scratch = torch.empty((4 * cap, 64), dtype=torch.float32, device=dev)
             call("mssvt_compress_attention_tc", 64, a.num_heads[0], n1, a.scale,
                  host_floats([vs[i] * self.win1_size[i] for i in range(3)]),
                  host_floats(sp_tensor.point_cloud_range[0:3]), ptr(self.pos_proj[0].weight),
