@@ -176,30 +176,63 @@ __device__ __forceinline__ unsigned bitrev(unsigned v, int bits) { return bits ?
 // one minimising (bit_reverse(k mod B), k).  Offsets are small integers, so the
 // fp32 distances of the reference are exact and integer arithmetic gives identical results.
 // key = dist << 20 | (B-1-bitrev(k mod B)) << 10 | (1023-k)  ->  one redux.sync per pick.
+//
+// All padded slots sit at the same point, so they always carry the same distance and only the one with
+// the best tie order can ever win: they are folded into ONE candidate (dist d_pad, key tie_pad), and the
+// per-pick scan covers the cnt real slots only.  With cnt <= 32 (the usual case) a lane keeps its slot's
+// offset, tie key and running distance in registers.
+__device__ __forceinline__ unsigned fps_tie(int k, int B, int log2b) {
+    return ((unsigned)(B - 1) - bitrev((unsigned)k & (B - 1), log2b)) << 10 | (unsigned)(1023 - k);
+}
+
 __device__ __forceinline__ void fps_list(const int *s_off, int cnt, int n, int log2b, int K,
                                          int *s_min, int *s_pick) {
     const int lane = threadIdx.x & 31;
     const int B = 1 << log2b;
-    for (int k = lane; k < n; k += 32) s_min[k] = 0x7fffffff;
+    unsigned tie_pad = 0;  // best tie key among the padded slots [cnt, n); 0 = there is none
+    for (int k = cnt + lane; k < n; k += 32) tie_pad = max(tie_pad, fps_tie(k, B, log2b));
+    tie_pad = __reduce_max_sync(0xffffffffu, tie_pad);
+    int d_pad = 0xfff;  // (keys hold 12 bits of distance: squared offsets of a few cells)
     if (lane == 0) s_pick[0] = 0;
-    __syncwarp();
     int old = 0, j = 1;
-    for (; j < K; ++j) {
-        int po = old < cnt ? s_off[old] : 0;
-        int ox = off_x(po), oy = off_y(po), oz = off_z(po);
-        unsigned best = 0;
-        for (int k = lane; k < n; k += 32) {
-            int p = k < cnt ? s_off[k] : 0;
-            int dx = off_x(p) - ox, dy = off_y(p) - oy, dz = off_z(p) - oz;
-            int d = min(s_min[k], dx * dx + dy * dy + dz * dz);
-            s_min[k] = d;
-            unsigned tie = ((unsigned)(B - 1) - bitrev((unsigned)k & (B - 1), log2b)) << 10 | (unsigned)(1023 - k);
-            best = max(best, ((unsigned)d << 20) | tie);
+    if (cnt <= 32) {
+        const int p = lane < cnt ? s_off[lane] : 0;
+        const int px = off_x(p), py = off_y(p), pz = off_z(p);
+        const unsigned tie = fps_tie(lane, B, log2b);
+        int d = 0xfff;
+        for (; j < K; ++j) {
+            const int po = __shfl_sync(0xffffffffu, p, old & 31);  // (old >= cnt: a padded slot, offset 0)
+            const int ox = old < cnt ? off_x(po) : 0, oy = old < cnt ? off_y(po) : 0, oz = old < cnt ? off_z(po) : 0;
+            const int dx = px - ox, dy = py - oy, dz = pz - oz;
+            d = min(d, dx * dx + dy * dy + dz * dz);
+            d_pad = min(d_pad, ox * ox + oy * oy + oz * oz);
+            unsigned best = lane < cnt ? ((unsigned)d << 20) | tie : 0u;
+            if (tie_pad) best = max(best, ((unsigned)d_pad << 20) | tie_pad);
+            best = __reduce_max_sync(0xffffffffu, best);
+            if ((best >> 20) == 0) break;  // every slot coincides with a pick: index 0 from here on
+            old = 1023 - (int)(best & 1023u);
+            if (lane == 0) s_pick[j] = old;
         }
-        best = __reduce_max_sync(0xffffffffu, best);
-        if ((best >> 20) == 0) break;  // every slot coincides with a pick: index 0 from here on
-        old = 1023 - (int)(best & 1023u);
-        if (lane == 0) s_pick[j] = old;
+    } else {
+        for (int k = lane; k < cnt; k += 32) s_min[k] = 0xfff;
+        __syncwarp();
+        for (; j < K; ++j) {
+            const int po = old < cnt ? s_off[old] : 0;
+            const int ox = off_x(po), oy = off_y(po), oz = off_z(po);
+            d_pad = min(d_pad, ox * ox + oy * oy + oz * oz);
+            unsigned best = tie_pad ? ((unsigned)d_pad << 20) | tie_pad : 0u;
+            for (int k = lane; k < cnt; k += 32) {
+                const int p = s_off[k];
+                const int dx = off_x(p) - ox, dy = off_y(p) - oy, dz = off_z(p) - oz;
+                const int d = min(s_min[k], dx * dx + dy * dy + dz * dz);
+                s_min[k] = d;
+                best = max(best, ((unsigned)d << 20) | fps_tie(k, B, log2b));
+            }
+            best = __reduce_max_sync(0xffffffffu, best);
+            if ((best >> 20) == 0) break;
+            old = 1023 - (int)(best & 1023u);
+            if (lane == 0) s_pick[j] = old;
+        }
     }
     for (int r = j + lane; r < K; r += 32) s_pick[r] = 0;
     __syncwarp();
