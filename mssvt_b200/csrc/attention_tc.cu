@@ -272,7 +272,7 @@ k_tca_keys(TcAttnParams P, int win_cap, const int2 *__restrict__ tiles, const in
             const float4 *src = (const float4 *)(xn + (size_t)row * TCA_C + g * TCA_SD);
             float4 xv[TCA_SD / 4];  // the whole 128-byte slice in flight at once
 #pragma unroll
-            for (int c4 = 0; c4 < TCA_SD / 4; ++c4) xv[c4] = __ldg(src + c4);
+            for (int c4 = 0; c4 < TCA_SD / 4; ++c4) xv[c4] = ldg_stream(src + c4);
 #pragma unroll
             for (int c4 = 0; c4 < TCA_SD / 4; ++c4) {
                 const float4 v = xv[c4];

@@ -27,6 +27,11 @@
 namespace mssvt {
 
 #define TC_ROWS 128
+#ifdef MSSVT_TRACE
+#define TRACE(i) do { if (tid == 0 && blockIdx.x == 0 && tile == (int)blockIdx.x + (int)gridDim.x) tr[i] = clock64(); } while (0)
+#else
+#define TRACE(i) do {} while (0)
+#endif
 #define TC_THREADS 256   // two threads per row: warps w and w + 4 reach the same 32 TMEM lanes
 
 struct FfnTcParams {
@@ -100,37 +105,87 @@ k_ffn_tc(FfnTcParams P, int n_cap, const int *__restrict__ n_dev, const float *_
     const uint32_t my_row_off = (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u;
     float *red_mine = s_red + half * TC_ROWS + r;
     const float *red_other = s_red + (half ^ 1) * TC_ROWS + r;
+    // warp-private staging inside the A tile (free between the second GEMM of a tile and the A stores of
+    // the next): 32 half-rows of CH floats, 16-byte chunks XOR-swizzled by the row -> conflict-free both ways
+    constexpr int CPR = CH / 4, RPI = 32 / CPR;  // chunks per half-row, rows per warp instruction
+    const int lane = tid & 31;
+    char *stg = sA + warp * (32 * CH * 4);
+    const int st_row = lane / CPR, st_ch = lane % CPR;
+    int tile_row0 = 0;  // first row of the warp's 32 rows in the current tile
+    auto stage_in = [&](const float *__restrict__ src, float4 *dst) {
+        float4 v[CPR];
+#pragma unroll
+        for (int i = 0; i < CPR; ++i) {
+            const int rr = RPI * i + st_row, grow = tile_row0 + rr;
+            v[i] = grow < n ? __ldg((const float4 *)(src + (size_t)grow * C + half * CH) + st_ch)
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < CPR; ++i) {
+            const int rr = RPI * i + st_row;
+            *(float4 *)(stg + rr * (CH * 4) + ((st_ch ^ (rr & (CPR - 1))) << 4)) = v[i];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < CPR; ++q) dst[q] = *(const float4 *)(stg + lane * (CH * 4) + ((q ^ (lane & (CPR - 1))) << 4));
+        __syncwarp();
+    };
+    auto stage_out = [&](float *__restrict__ dst, const float4 *src) {
+#pragma unroll
+        for (int q = 0; q < CPR; ++q) *(float4 *)(stg + lane * (CH * 4) + ((q ^ (lane & (CPR - 1))) << 4)) = src[q];
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < CPR; ++i) {
+            const int rr = RPI * i + st_row, grow = tile_row0 + rr;
+            if (grow < n)
+                *((float4 *)(dst + (size_t)grow * C + half * CH) + st_ch) =
+                    *(const float4 *)(stg + rr * (CH * 4) + ((st_ch ^ (rr & (CPR - 1))) << 4));
+        }
+        __syncwarp();
+    };
 
+#ifdef MSSVT_TRACE
+    long long tr[12] = {0};
+#endif
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, phase ^= 1u) {
+        TRACE(0);
         const int row = tile * TC_ROWS + r;
         const bool live = row < n;
-        // ---- 1. this thread's half of the residual row u (registers), LayerNorm, A operand
+        tile_row0 = tile * TC_ROWS + (warp & 3) * 32;
+        {   // the next tile's rows: start them on their way from HBM to L2 now, a whole tile time ahead
+            const int nrow = row + (int)gridDim.x * TC_ROWS;
+            if (nrow < n) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(merged + (size_t)nrow * C + half * CH));
+                if (P.mode != 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(x + (size_t)nrow * C + half * CH));
+            }
+        }
+        // ---- 1. this thread's half of the residual row u (registers), LayerNorm, A operand.
+        //      Global rows move through a warp-private staging area so that every load / store
+        //      instruction of a warp covers whole 128-byte lines (RPI rows x CH floats), not 32 rows
         float u[CH];
-        if (live) {
-            const float4 *mp = (const float4 *)(merged + (size_t)row * C + half * CH);
+        {
+            float4 mv[CH / 4];
+            stage_in(merged, mv);
             if (P.mode == 0) {
 #pragma unroll
                 for (int c = 0; c < CH / 4; ++c) {
-                    float4 v = __ldg(mp + c);
-                    u[4 * c] = v.x; u[4 * c + 1] = v.y; u[4 * c + 2] = v.z; u[4 * c + 3] = v.w;
+                    u[4 * c] = mv[c].x; u[4 * c + 1] = mv[c].y; u[4 * c + 2] = mv[c].z; u[4 * c + 3] = mv[c].w;
                 }
             } else {
-                const float4 *xp = (const float4 *)(x + (size_t)row * C + half * CH);
-                const bool cov = covered[row] != 0;
+                float4 xv[CH / 4];
+                stage_in(x, xv);
+                const bool cov = live && covered[row] != 0;  // (uncovered rows of merged are never written)
 #pragma unroll
                 for (int c = 0; c < CH / 4; ++c) {
-                    float4 v = __ldg(xp + c);
-                    float4 m = cov ? __ldg(mp + c) : v;
+                    const float4 v = xv[c], m = cov ? mv[c] : v;
                     u[4 * c] = m.x + v.x; u[4 * c + 1] = m.y + v.y; u[4 * c + 2] = m.z + v.z; u[4 * c + 3] = m.w + v.w;
                 }
             }
-        } else {
-#pragma unroll
-            for (int c = 0; c < CH; ++c) u[c] = 0.f;
         }
         float part = 0.f;
 #pragma unroll
         for (int c = 0; c < CH; ++c) part += u[c];
+        TRACE(1);
         red_mine[0] = part;
         __syncthreads();
         const float mean = (part + red_other[0]) * (1.0f / C);
@@ -152,6 +207,7 @@ k_ffn_tc(FfnTcParams P, int n_cap, const int *__restrict__ n_dev, const float *_
         stage_packed_wait();  // (first tile: the weight copies overlapped the loads and the LayerNorm)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
+        TRACE(2);
         // ---- 2. D1[128 x F] = A[128 x C] . W1^T, one K = 8 slice (two 16-byte chunks) per MMA
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -163,7 +219,9 @@ k_ffn_tc(FfnTcParams P, int n_cap, const int *__restrict__ n_dev, const float *_
             }
             umma_commit(bar1);
         }
+        TRACE(3);
         mbar_wait(bar1, phase);
+        TRACE(4);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         // ---- 3. hidden = relu(D1 + b1), written back over D1: the A operand of the second GEMM
         for (int c0 = 0; c0 < FH; c0 += 32) {
@@ -175,8 +233,10 @@ k_ffn_tc(FfnTcParams P, int n_cap, const int *__restrict__ n_dev, const float *_
             tmem_st32(col, d);
         }
         tmem_st_wait();
+        TRACE(5);
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
+        TRACE(6);
         // ---- 4. D2[128 x C] = H[128 x F] . W2^T, H read from TMEM
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -186,7 +246,9 @@ k_ffn_tc(FfnTcParams P, int n_cap, const int *__restrict__ n_dev, const float *_
             }
             umma_commit(bar2);
         }
+        TRACE(7);
         mbar_wait(bar2, phase);
+        TRACE(8);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         // ---- 5. y = u + D2 + b2 (in place in u), optionally xn_next = LayerNorm_next(y)
         {
@@ -201,10 +263,11 @@ k_ffn_tc(FfnTcParams P, int n_cap, const int *__restrict__ n_dev, const float *_
                 for (int i = 0; i < CH; ++i) u[i] += (half ? d[CH + i] : d[i]) + s_b2[i];
             }
         }
-        if (live) {
-            float4 *yp = (float4 *)(y + (size_t)row * C + half * CH);
+        {
+            float4 o[CH / 4];
 #pragma unroll
-            for (int q = 0; q < CH / 4; ++q) yp[q] = make_float4(u[4 * q], u[4 * q + 1], u[4 * q + 2], u[4 * q + 3]);
+            for (int q = 0; q < CH / 4; ++q) o[q] = make_float4(u[4 * q], u[4 * q + 1], u[4 * q + 2], u[4 * q + 3]);
+            stage_out(y, o);
         }
         if (xn_next) {  // (uniform over the CTA)
             part = 0.f;
@@ -219,19 +282,25 @@ k_ffn_tc(FfnTcParams P, int n_cap, const int *__restrict__ n_dev, const float *_
             red_mine[6 * TC_ROWS] = part;
             __syncthreads();
             const float r2 = rsqrtf((part + red_other[6 * TC_ROWS]) * (1.0f / C) + P.next_eps);
-            if (live) {
-                float4 *xp = (float4 *)(xn_next + (size_t)row * C + half * CH);
+            float4 o[CH / 4];
 #pragma unroll
-                for (int q = 0; q < CH / 4; ++q)
-                    xp[q] = make_float4((u[4 * q] - m2) * r2 * s_ng[4 * q] + s_nb[4 * q],
-                                        (u[4 * q + 1] - m2) * r2 * s_ng[4 * q + 1] + s_nb[4 * q + 1],
-                                        (u[4 * q + 2] - m2) * r2 * s_ng[4 * q + 2] + s_nb[4 * q + 2],
-                                        (u[4 * q + 3] - m2) * r2 * s_ng[4 * q + 3] + s_nb[4 * q + 3]);
-            }
+            for (int q = 0; q < CH / 4; ++q)
+                o[q] = make_float4((u[4 * q] - m2) * r2 * s_ng[4 * q] + s_nb[4 * q],
+                                   (u[4 * q + 1] - m2) * r2 * s_ng[4 * q + 1] + s_nb[4 * q + 1],
+                                   (u[4 * q + 2] - m2) * r2 * s_ng[4 * q + 2] + s_nb[4 * q + 2],
+                                   (u[4 * q + 3] - m2) * r2 * s_ng[4 * q + 3] + s_nb[4 * q + 3]);
+            stage_out(xn_next, o);
         }
+        TRACE(9);
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();  // TMEM and the operand tiles are free for the next tile
+        TRACE(10);
     }
+#ifdef MSSVT_TRACE
+    if (tid == 0 && blockIdx.x == 0 && tr[10])
+        printf("ffn tile: load+sum %lld | LN+A+sync %lld | issue1 %lld | wait1 %lld | epi1 %lld | sync %lld | issue2 %lld | wait2 %lld | epi2+store %lld | sync %lld | total %lld clk\n",
+               tr[1] - tr[0], tr[2] - tr[1], tr[3] - tr[2], tr[4] - tr[3], tr[5] - tr[4], tr[6] - tr[5], tr[7] - tr[6], tr[8] - tr[7], tr[9] - tr[8], tr[10] - tr[9], tr[10] - tr[0]);
+#endif
     if (warp == 0) tmem_dealloc(tmem_base, tmem_cols);
 }
 
