@@ -83,28 +83,22 @@ struct TcaQueryRows {
         }
     }
     __device__ int rows() const { return __ldg(q_base + min(win_cap, __ldg(win_count_total))); }
-    __device__ void load(int qid, int half, const float *sPos, float *in) const {
-        const int src = __ldg(q_src + qid), w = src / nq;
-        const int row = __ldg(q_row + src);
+    struct Ctx { float rx, ry, rz, cx, cy, cz; };
+    __device__ const float4 *src(int qid, int half, Ctx &c) const {
+        const int s = __ldg(q_src + qid), w = s / nq;
+        const int row = __ldg(q_row + s);
         const int4 win = __ldg(win_list + w);
-        const float cx = world_coord(win.w, win_cell[0], lo[0]);
-        const float cy = world_coord(win.z, win_cell[1], lo[1]);
-        const float cz = world_coord(win.y, win_cell[2], lo[2]);
-        const float rx = __fsub_rn(__ldg(xyz + 3 * (size_t)row), cx);
-        const float ry = __fsub_rn(__ldg(xyz + 3 * (size_t)row + 1), cy);
-        const float rz = __fsub_rn(__ldg(xyz + 3 * (size_t)row + 2), cz);
-        const float4 *p = (const float4 *)(xn + (size_t)row * TCA_C + half * TCA_SD);
-        float4 xv[TCA_SD / 4];
+        c.cx = world_coord(win.w, win_cell[0], lo[0]);
+        c.cy = world_coord(win.z, win_cell[1], lo[1]);
+        c.cz = world_coord(win.y, win_cell[2], lo[2]);
+        c.rx = __fsub_rn(__ldg(xyz + 3 * (size_t)row), c.cx);
+        c.ry = __fsub_rn(__ldg(xyz + 3 * (size_t)row + 1), c.cy);
+        c.rz = __fsub_rn(__ldg(xyz + 3 * (size_t)row + 2), c.cz);
+        return (const float4 *)(xn + (size_t)row * TCA_C + half * TCA_SD);
+    }
+    __device__ void finish(const Ctx &c, int half, const float *sPos, float *in) const {
 #pragma unroll
-        for (int c4 = 0; c4 < TCA_SD / 4; ++c4) xv[c4] = __ldg(p + c4);
-#pragma unroll
-        for (int c4 = 0; c4 < TCA_SD / 4; ++c4) {
-            const int c = half * TCA_SD + 4 * c4;
-            in[4 * c4] = xv[c4].x + pos_embed8(sPos, c, rx, ry, rz, cx, cy, cz);
-            in[4 * c4 + 1] = xv[c4].y + pos_embed8(sPos, c + 1, rx, ry, rz, cx, cy, cz);
-            in[4 * c4 + 2] = xv[c4].z + pos_embed8(sPos, c + 2, rx, ry, rz, cx, cy, cz);
-            in[4 * c4 + 3] = xv[c4].w + pos_embed8(sPos, c + 3, rx, ry, rz, cx, cy, cz);
-        }
+        for (int i = 0; i < TCA_SD; ++i) in[i] += pos_embed8(sPos, half * TCA_SD + i, c.rx, c.ry, c.rz, c.cx, c.cy, c.cz);
     }
 };
 
@@ -254,6 +248,9 @@ k_tca_keys(TcAttnParams P, int win_cap, const int2 *__restrict__ tiles, const in
         const bool is_task = tid < nT;
         int j = 0, nqr = 0, q0 = 0, soff = 0;
         bool masked = false;
+        float rx = 0.f, ry = 0.f, rz = 0.f;  // masked key: relative offset zeroed
+        float4 ctr = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 *src = nullptr;
         if (is_task) {
             const int l = tile_window(sToff, nwin, tid);
             const int4 rec = sRec[l];
@@ -262,26 +259,30 @@ k_tca_keys(TcAttnParams P, int win_cap, const int2 *__restrict__ tiles, const in
             const int r = (rec.y >> 8) & 0xff, mult = rec.y >> 16;
             masked = mult > 0 && j == r - 1;  // last distinct key stands for all masked slots
             const int row = __ldg(rep_row + (size_t)(tl.x + l) * 2 * K + g * K + j);
-            const float4 ctr = sCtr[l];
-            float rx = 0.f, ry = 0.f, rz = 0.f;  // masked key: relative offset zeroed
+            ctr = sCtr[l];
             if (!masked) {
                 rx = __fsub_rn(__ldg(xyz + 3 * (size_t)row), ctr.x);
                 ry = __fsub_rn(__ldg(xyz + 3 * (size_t)row + 1), ctr.y);
                 rz = __fsub_rn(__ldg(xyz + 3 * (size_t)row + 2), ctr.z);
             }
-            const float4 *src = (const float4 *)(xn + (size_t)row * TCA_C + g * TCA_SD);
-            float4 xv[TCA_SD / 4];  // the whole 128-byte slice in flight at once
+            src = (const float4 *)(xn + (size_t)row * TCA_C + g * TCA_SD);
+        }
+        {
+            // the warp gathers its 32 rows together (8 lanes per 128-byte slice) through the A tile's memory
+            float4 xv[TCA_SD / 4];
+            warp_rows_load(sA + warp * 4096, src, xv);
+            __syncthreads();  // every warp is done with its staging area: the A tile may be written
+            if (is_task) {
 #pragma unroll
-            for (int c4 = 0; c4 < TCA_SD / 4; ++c4) xv[c4] = ldg_stream(src + c4);
-#pragma unroll
-            for (int c4 = 0; c4 < TCA_SD / 4; ++c4) {
-                const float4 v = xv[c4];
-                float4 o;
-                o.x = to_tf32(v.x + pos_embed8(sPos, 4 * c4, rx, ry, rz, ctr.x, ctr.y, ctr.z));
-                o.y = to_tf32(v.y + pos_embed8(sPos, 4 * c4 + 1, rx, ry, rz, ctr.x, ctr.y, ctr.z));
-                o.z = to_tf32(v.z + pos_embed8(sPos, 4 * c4 + 2, rx, ry, rz, ctr.x, ctr.y, ctr.z));
-                o.w = to_tf32(v.w + pos_embed8(sPos, 4 * c4 + 3, rx, ry, rz, ctr.x, ctr.y, ctr.z));
-                *(float4 *)(sA + (uint32_t)c4 * a_lbo + my_row_off) = o;
+                for (int c4 = 0; c4 < TCA_SD / 4; ++c4) {
+                    const float4 v = xv[c4];
+                    float4 o;
+                    o.x = to_tf32(v.x + pos_embed8(sPos, 4 * c4, rx, ry, rz, ctr.x, ctr.y, ctr.z));
+                    o.y = to_tf32(v.y + pos_embed8(sPos, 4 * c4 + 1, rx, ry, rz, ctr.x, ctr.y, ctr.z));
+                    o.z = to_tf32(v.z + pos_embed8(sPos, 4 * c4 + 2, rx, ry, rz, ctr.x, ctr.y, ctr.z));
+                    o.w = to_tf32(v.w + pos_embed8(sPos, 4 * c4 + 3, rx, ry, rz, ctr.x, ctr.y, ctr.z));
+                    *(float4 *)(sA + (uint32_t)c4 * a_lbo + my_row_off) = o;
+                }
             }
         }
         stage_packed_wait();

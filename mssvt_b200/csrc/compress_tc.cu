@@ -208,18 +208,27 @@ k_tcc_keys(TccParams P, const int2 *__restrict__ tiles, const int *__restrict__ 
         const bool is_task = r < nT;
         int l = 0, row = -1;
         bool pad = false;
+        float rx = 0.f, ry = 0.f, rz = 0.f;
+        float4 ctr = make_float4(0.f, 0.f, 0.f, 0.f);
         if (is_task) {
             l = tcc_tile_window(sToff, nwin, r);
             const int j = r - sToff[l];
             pad = j >= sCnt[l];
-            const float4 ctr = sCtr[l];
+            ctr = sCtr[l];
             float px = 0.f, py = 0.f, pz = 0.f;  // padded slots: grouped coordinate 0 -> offset 0 - centre
             if (!pad) {
                 row = __ldg(k_row + (size_t)(tl.x + l) * n1 + j);
                 px = __ldg(xyz + 3 * (size_t)row); py = __ldg(xyz + 3 * (size_t)row + 1);
                 pz = __ldg(xyz + 3 * (size_t)row + 2);
             }
-            const float rx = __fsub_rn(px, ctr.x), ry = __fsub_rn(py, ctr.y), rz = __fsub_rn(pz, ctr.z);
+            rx = __fsub_rn(px, ctr.x); ry = __fsub_rn(py, ctr.y); rz = __fsub_rn(pz, ctr.z);
+        }
+        // the feature rows (needed after the first MMA) are gathered now, 8 lanes per 128-byte half row,
+        // through the A tile's memory (pad key: zero feature)
+        float4 f[8];
+        warp_rows_load(sA + warp * 4096, is_task && !pad ? (const float4 *)(xn + (size_t)row * TCC_C + 32 * half) : nullptr, f);
+        __syncthreads();  // every warp is done with its staging area: the A tile may be written
+        if (is_task) {
 #pragma unroll 4
             for (int c4 = 0; c4 < 8; ++c4) {
                 float o[4];
@@ -245,14 +254,6 @@ k_tcc_keys(TccParams P, const int2 *__restrict__ tiles, const int *__restrict__ 
                 umma_tf32(tmem_d1, umma_smem_desc(sA_u + (uint32_t)k * 2u * a_lbo, a_lbo, 128),
                           umma_smem_desc(sW2_u + (uint32_t)k * 2u * w2_lbo, w2_lbo, 128), idesc1, k > 0 ? 1u : 0u);
             umma_commit(bar);
-        }
-        // the feature row is needed right after the MMA: fetch it while the tensor core works
-        float4 f[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) f[q] = make_float4(0.f, 0.f, 0.f, 0.f);  // pad key: zero feature
-        if (is_task && !pad) {
-#pragma unroll
-            for (int q = 0; q < 8; ++q) f[q] = __ldg((const float4 *)(xn + (size_t)row * TCC_C + 32 * half) + q);
         }
         mbar_wait(bar, phase);
         phase ^= 1u;

@@ -162,6 +162,43 @@ __device__ __forceinline__ float4 ldg_stream(const float4 *p) {
     return v;
 }
 
+// ---- warp-cooperative row transfer.  With one thread per row, a warp-wide 16-byte load touches 32
+// different 128-byte lines and the L1 tag stage (one line per cycle) becomes the bound.  Here the 32
+// lanes fetch 4 rows x 128 bytes per instruction (8 lanes per row), park them in a warp-private 4 KB
+// staging area (16-byte chunks XOR-swizzled by the row: conflict-free both ways) and every lane then
+// reads its own row back.  my_src / my_dst: the 128-byte segment of this lane's row (nullptr = no row).
+__device__ __forceinline__ void warp_rows_load(char *stg, const float4 *my_src, float4 *dst /*[8]*/) {
+    const int lane = threadIdx.x & 31, st_row = lane >> 3, st_ch = lane & 7;
+    float4 v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float4 *p = (const float4 *)__shfl_sync(0xffffffffu, (unsigned long long)my_src, 4 * i + st_row);
+        v[i] = p ? __ldg(p + st_ch) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int rr = 4 * i + st_row;
+        *(float4 *)(stg + rr * 128 + ((st_ch ^ (rr & 7)) << 4)) = v[i];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 8; ++q) dst[q] = *(const float4 *)(stg + lane * 128 + ((q ^ (lane & 7)) << 4));
+    __syncwarp();
+}
+__device__ __forceinline__ void warp_rows_store(char *stg, float4 *my_dst, const float4 *src /*[8]*/) {
+    const int lane = threadIdx.x & 31, st_row = lane >> 3, st_ch = lane & 7;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) *(float4 *)(stg + lane * 128 + ((q ^ (lane & 7)) << 4)) = src[q];
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int rr = 4 * i + st_row;
+        float4 *p = (float4 *)__shfl_sync(0xffffffffu, (unsigned long long)my_dst, rr);
+        if (p) p[st_ch] = *(const float4 *)(stg + rr * 128 + ((st_ch ^ (rr & 7)) << 4));
+    }
+    __syncwarp();
+}
+
 // Weight operands are packed ONCE (mssvt_pack_operand_tf32: canonical K-major layout, TF32-rounded) and
 // then only copied: asynchronous 16-byte copies global -> shared, no registers, no per-CTA conversion.
 // Call stage_packed_wait() before the fence.proxy.async / barrier that precedes the first MMA.

@@ -28,12 +28,14 @@ static inline size_t tcl_smem_bytes() { return TCL_ROWS * TCL_C * 4 + TCL_C * TC
 // Producer: struct with
 //   __device__ void init(float *s_extra)            cooperative, before the first barrier (s_extra: 2 KB)
 //   __device__ int rows() const                     number of rows (device-side count)
-//   __device__ void load(int row, int half, const float *s_extra, float *in /*[32]*/) const
+//   struct Ctx;                                      per-row context carried from src() to finish()
+//   __device__ const float4 *src(int row, int half, Ctx &) const     128-byte segment holding the row's 32 inputs
+//   __device__ void finish(const Ctx &, int half, const float *s_extra, float *in /*[32]*/) const   in-place fix-up
 
 // rows copied from a dense (rows, 64) array; row count = min(cap, *count), optionally mapped through
 // an index array (count_map[n], e.g. a prefix sum)
 struct TclCopyRows {
-    const float *src;
+    const float *rows_in;
     const int *count, *count_map;
     int cap;
     __device__ void init(float *) const {}
@@ -41,14 +43,11 @@ struct TclCopyRows {
         const int n = min(cap, __ldg(count));
         return count_map ? __ldg(count_map + n) : n;
     }
-    __device__ void load(int row, int half, const float *, float *in) const {
-        const float4 *p = (const float4 *)(src + (size_t)row * TCL_C + half * 32);
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            const float4 v = __ldg(p + c);
-            in[4 * c] = v.x; in[4 * c + 1] = v.y; in[4 * c + 2] = v.z; in[4 * c + 3] = v.w;
-        }
+    struct Ctx {};
+    __device__ const float4 *src(int row, int half, Ctx &) const {
+        return (const float4 *)(rows_in + (size_t)row * TCL_C + half * 32);
     }
+    __device__ void finish(const Ctx &, int, const float *, float *) const {}
 };
 template <class Producer>
 __global__ void __launch_bounds__(TCL_THREADS, 4)
@@ -81,6 +80,7 @@ k_tc_linear(TclParams P, Producer prod, float *__restrict__ out) {
     const uint32_t sA_u = smem_u32(sA), sW_u = smem_u32(sW);
     const uint32_t a_lbo = TCL_ROWS * 16, w_lbo = TCL_C * 16;
     const uint32_t my_row_off = (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u;
+    char *stg = sA + warp * 4096;  // warp-private staging (inside the A tile, see the barriers below)
     const int n = prod.rows();
     const int tiles = (n + TCL_ROWS - 1) / TCL_ROWS;
     uint32_t phase = 0;
@@ -88,11 +88,16 @@ k_tc_linear(TclParams P, Producer prod, float *__restrict__ out) {
         const int row = tile * TCL_ROWS + r;
         const bool live = row < n;
         float in[32];
-        if (live) prod.load(row, half, sExtra, in);
-        else {
+        {
+            typename Producer::Ctx ctx;
+            const float4 *my_src = live ? prod.src(row, half, ctx) : nullptr;
+            float4 v[8];
+            warp_rows_load(stg, my_src, v);
 #pragma unroll
-            for (int c = 0; c < 32; ++c) in[c] = 0.f;
+            for (int c = 0; c < 8; ++c) { in[4 * c] = v[c].x; in[4 * c + 1] = v[c].y; in[4 * c + 2] = v[c].z; in[4 * c + 3] = v[c].w; }
+            if (live) prod.finish(ctx, half, sExtra, in);
         }
+        __syncthreads();  // the staging areas alias the A tile: every warp is done reading before A is written
 #pragma unroll
         for (int c = 0; c < 8; ++c)
             *(float4 *)(sA + (uint32_t)(half * 8 + c) * a_lbo + my_row_off) =
@@ -112,13 +117,15 @@ k_tc_linear(TclParams P, Producer prod, float *__restrict__ out) {
         tc_fence_after();
         float d[32];
         tmem_ld32(tmem_d + lane_off + (uint32_t)(half * 32), d);
-        if (live) {
-            float4 *dst = (float4 *)(out + (size_t)row * TCL_C + half * 32);
+        {
             const float *bb = sB + half * 32;
+            float4 o[8];
 #pragma unroll
             for (int q = 0; q < 8; ++q)
-                dst[q] = make_float4((d[4 * q] + bb[4 * q]) * P.mul, (d[4 * q + 1] + bb[4 * q + 1]) * P.mul,
-                                     (d[4 * q + 2] + bb[4 * q + 2]) * P.mul, (d[4 * q + 3] + bb[4 * q + 3]) * P.mul);
+                o[q] = make_float4((d[4 * q] + bb[4 * q]) * P.mul, (d[4 * q + 1] + bb[4 * q + 1]) * P.mul,
+                                   (d[4 * q + 2] + bb[4 * q + 2]) * P.mul, (d[4 * q + 3] + bb[4 * q + 3]) * P.mul);
+            // (the MMA has consumed the A tile: its memory serves as the staging area again)
+            warp_rows_store(stg, live ? (float4 *)(out + (size_t)row * TCL_C + half * 32) : nullptr, o);
         }
         tc_fence_before();
         __syncthreads();  // TMEM and the A tile are free for the next tile
