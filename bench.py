@@ -119,12 +119,22 @@ def algorithmic_bytes(kernel, n, w, pillars):
         "mssvt_layernorm": 2 * n * C4,
         # read xn + xyz + rows map, write one row per pillar
         "mssvt_compress_attention": n * C4 + n * 12 + pillars * 32 * 4 + pillars * C4,
+        "mssvt_compress_attention_tc": n * C4 + n * 12 + pillars * 32 * 4 + pillars * C4,
         # window rows in, compact maps out; probes hit the L2-resident 3.2 MB table
         "mssvt_block_geometry": w * 16 + w * (12 * 4 + 27 * 4 + 64 * 4 + 64 + 27 * 3 * 5) + n,
         "mssvt_window_partition": 16 * n + 16 * w + 8 * 400000 + 4 * n,
         "mssvt_build_hash_table": 16 * n + 8 * n + 8 * 400000,
     }
     return table.get(kernel)
+
+
+# DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per launch of an entry point, summed over its
+# kernels, from the ncu --set full capture summarised in profiles/r01_ncu_summary.md (section r01n;
+# N = 150 k; ncu flushes caches between kernels, so this is the cold-cache figure)
+MEASURED_TRAFFIC = {
+    "mssvt_block_attention_tc": int((20.164 + 0.010 + 60.632 + 3.090 + 16.533 + 0.0 + 28.210 + 1.183) * 1e6),
+    "mssvt_ffn_tc": int((77.180 + 29.050) * 1e6),
+}
 
 
 def our_arm(args):
@@ -291,7 +301,7 @@ def our_arm(args):
     achieved = abytes / avg_s / 1e9 if abytes else None
     roofline = {"kernel": dom_name, "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"],
                 "unit": "GB/s", "frac": (achieved / peaks["hbm_gbs"]) if achieved else None,
-                "traffic": None, "peak_kind": peak_kind, "avg_launch_us": avg_s * 1e6,
+                "traffic": MEASURED_TRAFFIC.get(dom_name), "peak_kind": peak_kind, "avg_launch_us": avg_s * 1e6,
                 "share_of_step": dom_ms / sum(v[0] for v in per.values()),
                 "algorithmic_bytes_per_launch": abytes}
     breakdown = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps}
