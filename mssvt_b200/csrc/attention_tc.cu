@@ -31,6 +31,11 @@
 namespace mssvt {
 
 #define TCA_THREADS 128
+#ifdef MSSVT_TRACE
+#define KTRACE(i) do { if (tid == 0 && blockIdx.x == gridDim.x - 1 && t == first + 2 * stride) tr[i] = clock64(); } while (0)
+#else
+#define KTRACE(i) do {} while (0)
+#endif
 #define TCA_TW 32        // windows per tile (at most)
 #define TCA_SBUD 2048    // score slots per tile: sum over its windows of #queries x #keys x heads
 #define TCA_PLAN_WB 64   // windows planned by one warp
@@ -224,8 +229,17 @@ k_tca_keys(TcAttnParams P, int win_cap, const int2 *__restrict__ tiles, const in
     const uint32_t my_row_off = (uint32_t)(tid >> 3) * 128u + (uint32_t)(tid & 7) * 16u;
     uint32_t phase = 0;
 
+#ifdef MSSVT_TRACE
+    long long tr[12] = {0};
+#endif
+    int2 tl_next = first < T ? __ldg(tiles + first) : make_int2(0, 0);
     for (int t = first; t < T; t += stride) {
-        const int2 tl = __ldg(tiles + t);
+        KTRACE(0);
+        // the tile record is fetched one tile ahead; the next tile's window records and key lists are
+        // pulled into L1 while this tile's MMA runs, so that the chain tile -> windows -> key rows ->
+        // features starts from cached lines
+        const int2 tl = tl_next;
+        if (t + stride < T) tl_next = __ldg(tiles + t + stride);
         const int nwin = tl.y;
         if (tid < nwin) {
             const int4 rec = __ldg(win_rec + tl.x + tid);
@@ -239,10 +253,10 @@ k_tca_keys(TcAttnParams P, int win_cap, const int2 *__restrict__ tiles, const in
             }
         }
         __syncthreads();
+        KTRACE(1);
         const int nT = sToff[nwin], nQ = sQoff[nwin];
         // the tile's query rows (contiguous ids) are read after the MMA: pull their 128-byte halves into L1 now
-        if (tid < nQ)
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(Qbuf + (size_t)(sRec[0].x + tid) * TCA_C + g * TCA_SD));
+        if (tid < nQ) prefetch_l1(Qbuf + (size_t)(sRec[0].x + tid) * TCA_C + g * TCA_SD);
 
         // ---- key task -> row t of the A operand
         const bool is_task = tid < nT;
@@ -260,18 +274,21 @@ k_tca_keys(TcAttnParams P, int win_cap, const int2 *__restrict__ tiles, const in
             masked = mult > 0 && j == r - 1;  // last distinct key stands for all masked slots
             const int row = __ldg(rep_row + (size_t)(tl.x + l) * 2 * K + g * K + j);
             ctr = sCtr[l];
-            if (!masked) {
-                rx = __fsub_rn(__ldg(xyz + 3 * (size_t)row), ctr.x);
-                ry = __fsub_rn(__ldg(xyz + 3 * (size_t)row + 1), ctr.y);
-                rz = __fsub_rn(__ldg(xyz + 3 * (size_t)row + 2), ctr.z);
+            if (!masked) {  // (coordinates and features travel together: the subtraction waits below)
+                rx = __ldg(xyz + 3 * (size_t)row); ry = __ldg(xyz + 3 * (size_t)row + 1);
+                rz = __ldg(xyz + 3 * (size_t)row + 2);
             }
             src = (const float4 *)(xn + (size_t)row * TCA_C + g * TCA_SD);
         }
         {
             // the warp gathers its 32 rows together (8 lanes per 128-byte slice) through the A tile's memory
             float4 xv[TCA_SD / 4];
-            warp_rows_load(sA + warp * 4096, src, xv);
-            __syncthreads();  // every warp is done with its staging area: the A tile may be written
+            KTRACE(2);
+            warp_rows_load<true>(sA + warp * 4096, src, xv);
+            if (is_task && !masked) { rx = __fsub_rn(rx, ctr.x); ry = __fsub_rn(ry, ctr.y); rz = __fsub_rn(rz, ctr.z); }
+            KTRACE(3);
+            __syncthreads();
+            KTRACE(4);  // every warp is done with its staging area: the A tile may be written
             if (is_task) {
 #pragma unroll
                 for (int c4 = 0; c4 < TCA_SD / 4; ++c4) {
@@ -285,9 +302,11 @@ k_tca_keys(TcAttnParams P, int win_cap, const int2 *__restrict__ tiles, const in
                 }
             }
         }
+        KTRACE(5);
         stage_packed_wait();
         fence_async_smem();
         __syncthreads();
+        KTRACE(6);
         // ---- D = A Wkv^T: K in TMEM columns 0..31, V in 32..63
         if (tid == 0) {
             tc_fence_after();
@@ -299,7 +318,14 @@ k_tca_keys(TcAttnParams P, int win_cap, const int2 *__restrict__ tiles, const in
             }
             umma_commit(bar);
         }
+        if (t + stride < T) {  // next tile: window records (16 B each), centres, key lists (K ints per window)
+            if (tid < tl_next.y) prefetch_l1(rep_row + (size_t)(tl_next.x + tid) * 2 * K + g * K);
+            else if (tid < tl_next.y + (tl_next.y + 7) / 8 + 1) prefetch_l1(win_rec + tl_next.x + 8 * (tid - tl_next.y));
+            else if (tid < tl_next.y + 2 * ((tl_next.y + 7) / 8 + 1))
+                prefetch_l1(win_ctr + tl_next.x + 8 * (tid - tl_next.y - (tl_next.y + 7) / 8 - 1));
+        }
         mbar_wait(bar, phase);
+        KTRACE(7);
         phase ^= 1u;
         tc_fence_after();
         // ---- this thread's key: K|V back from TMEM; scores against its window's queries
@@ -310,13 +336,13 @@ k_tca_keys(TcAttnParams P, int win_cap, const int2 *__restrict__ tiles, const in
             tc_fence_before();
             __syncthreads();  // every thread has its K|V in registers: the A tile may become V
             if (is_task) {
+                // Biases: q.(k + bk) shifts every score of a query by the same q.bk, which the softmax
+                // cancels, so bk is dropped; sum_i p_i (v_i + bv) = sum_i p_i v_i + bv, so bv is added once
+                // per output below instead of once per key here.
 #pragma unroll
                 for (int c4 = 0; c4 < TCA_SD / 4; ++c4)
                     *(float4 *)(sV + tid * TCA_VPITCH + 4 * c4) =
-                        make_float4(vv[4 * c4] + sBkv[TCA_SD + 4 * c4], vv[4 * c4 + 1] + sBkv[TCA_SD + 4 * c4 + 1],
-                                    vv[4 * c4 + 2] + sBkv[TCA_SD + 4 * c4 + 2], vv[4 * c4 + 3] + sBkv[TCA_SD + 4 * c4 + 3]);
-#pragma unroll
-                for (int i = 0; i < TCA_SD; ++i) kk[i] += sBkv[i];
+                        make_float4(vv[4 * c4], vv[4 * c4 + 1], vv[4 * c4 + 2], vv[4 * c4 + 3]);
                 const float bias = masked ? -100.0f : 0.f;  // additive mask of the reference
                 float *srow = sS + soff + j * nqr * HEADS;
                 for (int s = 0; s < nqr; ++s) {
@@ -335,7 +361,9 @@ k_tca_keys(TcAttnParams P, int win_cap, const int2 *__restrict__ tiles, const in
                 }
             }
         }
+        KTRACE(8);
         __syncthreads();
+        KTRACE(9);
         // ---- softmax over the window's distinct keys and AV, thread = (query, head, quarter of the head)
         for (int e = tid; e < nQ * HEADS * 4; e += TCA_THREADS) {
             const int dq = e & 3, qh = e >> 2;
@@ -361,11 +389,19 @@ k_tca_keys(TcAttnParams P, int win_cap, const int2 *__restrict__ tiles, const in
             }
             const float inv = 1.0f / den;
             float *dst = Obuf + (size_t)(rec.x + s) * TCA_C + g * TCA_SD + h * HD + dq * DPT;
+            const float *bv = sBkv + TCA_SD + h * HD + dq * DPT;
 #pragma unroll
-            for (int d = 0; d < DPT; ++d) dst[d] = acc[d] * inv;
+            for (int d = 0; d < DPT; ++d) dst[d] = fmaf(acc[d], inv, bv[d]);
         }
+        KTRACE(10);
         __syncthreads();
+        KTRACE(11);
     }
+#ifdef MSSVT_TRACE
+    if (tid == 0 && blockIdx.x == gridDim.x - 1 && tr[11])
+        printf("keys tile g%d: header %lld | search+idx %lld | gather %lld | sync %lld | posemb+A %lld | sync %lld | mma %lld | tmem+scores %lld | sync %lld | softmax+AV %lld | sync %lld | total %lld clk\n", g,
+               tr[1] - tr[0], tr[2] - tr[1], tr[3] - tr[2], tr[4] - tr[3], tr[5] - tr[4], tr[6] - tr[5], tr[7] - tr[6], tr[8] - tr[7], tr[9] - tr[8], tr[10] - tr[9], tr[11] - tr[10], tr[11] - tr[0]);
+#endif
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem_d, 64);

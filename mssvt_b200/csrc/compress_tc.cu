@@ -302,23 +302,23 @@ k_tcc_keys(TccParams P, const int2 *__restrict__ tiles, const int *__restrict__ 
             __syncthreads();  // all K|V are in registers: the A tile may become V
             if (is_task) {
                 const float4 *qv = (const float4 *)(Qc + (size_t)(tl.x + l) * TCC_C + 32 * half);
-                const float *bk = sBkv + 32 * half, *bv = sBkv + 64 + 32 * half;
+                // (biases: the K bias shifts all scores of the query equally -> cancelled by the softmax;
+                //  the V bias is added once per output below)
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                     const float4 q4 = __ldg(qv + q);
                     const int h = (4 * q) / HD;
-                    sc[h] = fmaf(q4.x, d[4 * q] + bk[4 * q], sc[h]);
-                    sc[h] = fmaf(q4.y, d[4 * q + 1] + bk[4 * q + 1], sc[h]);
-                    sc[h] = fmaf(q4.z, d[4 * q + 2] + bk[4 * q + 2], sc[h]);
-                    sc[h] = fmaf(q4.w, d[4 * q + 3] + bk[4 * q + 3], sc[h]);
+                    sc[h] = fmaf(q4.x, d[4 * q], sc[h]);
+                    sc[h] = fmaf(q4.y, d[4 * q + 1], sc[h]);
+                    sc[h] = fmaf(q4.z, d[4 * q + 2], sc[h]);
+                    sc[h] = fmaf(q4.w, d[4 * q + 3], sc[h]);
                 }
 #pragma unroll
                 for (int h = 0; h < HH; ++h) sS[r * HEADS + half * HH + h] = sc[h] + (pad ? -100.0f : 0.f);
 #pragma unroll
                 for (int c4 = 0; c4 < 8; ++c4)
                     *(float4 *)(sV + r * TCC_VPITCH + 32 * half + 4 * c4) =
-                        make_float4(vv[4 * c4] + bv[4 * c4], vv[4 * c4 + 1] + bv[4 * c4 + 1],
-                                    vv[4 * c4 + 2] + bv[4 * c4 + 2], vv[4 * c4 + 3] + bv[4 * c4 + 3]);
+                        make_float4(vv[4 * c4], vv[4 * c4 + 1], vv[4 * c4 + 2], vv[4 * c4 + 3]);
             }
         }
         __syncthreads();
@@ -343,8 +343,9 @@ k_tcc_keys(TccParams P, const int2 *__restrict__ tiles, const int *__restrict__ 
             }
             const float inv = 1.0f / den;
             float *dst = Oc + (size_t)(tl.x + lw) * TCC_C + h * HD + dq * DPT;
+            const float *bv = sBkv + 64 + h * HD + dq * DPT;
 #pragma unroll
-            for (int d = 0; d < DPT; ++d) dst[d] = acc[d] * inv;
+            for (int d = 0; d < DPT; ++d) dst[d] = fmaf(acc[d], inv, bv[d]);
         }
         __syncthreads();
     }

@@ -167,13 +167,14 @@ __device__ __forceinline__ float4 ldg_stream(const float4 *p) {
 // lanes fetch 4 rows x 128 bytes per instruction (8 lanes per row), park them in a warp-private 4 KB
 // staging area (16-byte chunks XOR-swizzled by the row: conflict-free both ways) and every lane then
 // reads its own row back.  my_src / my_dst: the 128-byte segment of this lane's row (nullptr = no row).
+template <bool STREAM = false>  // STREAM: do not allocate the rows in L1 (they are used once per tile)
 __device__ __forceinline__ void warp_rows_load(char *stg, const float4 *my_src, float4 *dst /*[8]*/) {
     const int lane = threadIdx.x & 31, st_row = lane >> 3, st_ch = lane & 7;
     float4 v[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const float4 *p = (const float4 *)__shfl_sync(0xffffffffu, (unsigned long long)my_src, 4 * i + st_row);
-        v[i] = p ? __ldg(p + st_ch) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[i] = !p ? make_float4(0.f, 0.f, 0.f, 0.f) : STREAM ? ldg_stream(p + st_ch) : __ldg(p + st_ch);
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -198,6 +199,8 @@ __device__ __forceinline__ void warp_rows_store(char *stg, float4 *my_dst, const
     }
     __syncwarp();
 }
+
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // Weight operands are packed ONCE (mssvt_pack_operand_tf32: canonical K-major layout, TF32-rounded) and
 // then only copied: asynchronous 16-byte copies global -> shared, no registers, no per-CTA conversion.
