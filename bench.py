@@ -334,7 +334,7 @@ def our_arm(args):
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(budget_s=20.0)
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
@@ -410,10 +410,22 @@ def reference_arm(args):
                          "sample": "%d steps of one full 150000-voxel frame" % steps},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
+
+
+_RESULT = None  # the real stdout; fd 1 itself is pointed at stderr while the benchmark runs
+
+
+def emit(line):
+    print(json.dumps(line), file=_RESULT or sys.stdout, flush=True)
 
 
 def main():
+    # ONE JSON line on stdout: libraries that write to fd 1 (NCCL's version banner, ...) go to stderr
+    global _RESULT
+    sys.stdout.flush()
+    _RESULT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
