@@ -1,0 +1,93 @@
+"""BASELINE config 5: MsSVT backbone train step (forward + backward + AdamW) on synthetic frames,
+one frame per GPU per step, DDP gradient all-reduce over NCCL when launched under torchrun.
+
+    python benchmarks/train_step.py [--steps 10] [--warmup 3] [--voxels 150000] [--amp]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \
+        --master-port 29533 benchmarks/train_step.py --amp
+
+Training runs the autograd path of the blocks: index maps from the fused geometry kernels, row gathers
+through mssvt_group_features / mssvt_group_features_grad, dense math in torch (bf16 autocast with --amp).
+Loss = mean of the squared `.dense()` output (synthetic).  Prints one JSON line.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from mssvt_b200.config import s0_model_cfg  # noqa: E402
+from mssvt_b200.mssvt_backbone import MixedScaleSparseTransformer  # noqa: E402
+from mssvt_b200.synth import S0_GRID, S0_RANGE, S0_VOXEL, synth_frame  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--voxels", type=int, default=150000)
+    ap.add_argument("--amp", action="store_true", help="bf16 autocast for the dense math")
+    args = ap.parse_args()
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    torch.manual_seed(0)
+    model = MixedScaleSparseTransformer(s0_model_cfg(), 64, list(S0_GRID), list(S0_VOXEL), list(S0_RANGE)).to(dev)
+    model.train()
+    net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local]) if world > 1 else model
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4)
+    frames = []
+    for i in range(4):
+        f, c = synth_frame(1000 * rank + i, args.voxels)
+        frames.append((torch.from_numpy(f).to(dev), torch.from_numpy(c).to(dev)))
+
+    def step(i):
+        f, c = frames[i % len(frames)]
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=args.amp):
+            sp = net({"voxel_features": f, "voxel_coords": c, "batch_size": 1})["encoded_spconv_tensor"]
+            loss = (sp.dense().float() ** 2).mean()
+        loss.backward()
+        opt.step()
+        return loss
+
+    for i in range(args.warmup):
+        step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for i in range(args.steps):
+        loss = step(args.warmup + i)
+    e1.record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    ms = e0.elapsed_time(e1) / args.steps
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    if rank == 0:
+        print(json.dumps({"metric": "mssvt_backbone_train_step_ms", "value": ms, "unit": "ms/step", "n_gpus": world,
+                          "steps": args.steps, "warmup": args.warmup, "higher_is_better": False,
+                          "voxels_per_s": args.voxels * world / (ms * 1e-3), "wall_ms_per_step": wall / args.steps * 1e3,
+                          "dtype": "bf16 autocast" if args.amp else "fp32", "loss": float(loss),
+                          "config": {"workload": "S0 backbone fwd+bwd+AdamW, one synthetic %d-voxel frame per GPU per "
+                                                 "step, loss = mean(dense()^2), DDP all-reduce when world > 1" % args.voxels}}),
+              file=out, flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

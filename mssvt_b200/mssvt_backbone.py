@@ -25,7 +25,7 @@ from .mssvt_utils import MixedScaleAttention, SparseTensor, sample_counts
 
 class DropPath(nn.Module):
     """Stochastic depth (timm.models.layers.DropPath, used at mssvt_backbone.py:4, 42): identity
-    in eval mode, which is the only mode the fused path runs in."""
+    in eval mode (the fused kernels); active on the autograd path in training mode."""
 
     def __init__(self, drop_prob=0.0):
         super().__init__()
@@ -191,13 +191,82 @@ class MixedScaleSparseTransformerBlock(nn.Module):
             out['vox_ind_' + n], out['vox_mask_' + n], out['vox_coord_' + n] = outs[i], outs[i] < 0, outs[4 + i]
         return out
 
-    # ---- fused path --------------------------------------------------------------------------
-    def _check_mode(self):
-        if self.training and torch.is_grad_enabled():
-            raise RuntimeError(
-                "mssvt_b200: the fused backbone runs inference only in this release (call .eval() "
-                "and torch.no_grad()); the backward kernels are the next hot-path row "
-                "(SURVEY.md 8(f) rank 2).")
+    # ---- training path / fused inference path -------------------------------------------------
+    def _differentiable(self, x):
+        """Training (or any call that needs gradients) takes the autograd path: geometry from the fused
+        kernels, feature gathers through mssvt_group_features / mssvt_group_features_grad, dense math
+        in torch.  Inference takes the fused kernels."""
+        return torch.is_grad_enabled() and (self.training or x.requires_grad)
+
+    def _window_centres(self, sp_tensor, win_list):
+        vs, lo = sp_tensor.voxel_size, sp_tensor.point_cloud_range
+        cell = win_list.new_tensor([vs[i] * self.win1_size[i] for i in range(3)], dtype=torch.float32)
+        origin = win_list.new_tensor(list(lo[0:3]), dtype=torch.float32)
+        # [b, z, y, x] -> (x, y, z), same arithmetic order as world_coord() in csrc/common.cuh
+        return ((win_list[:, [3, 2, 1]].float() + 0.5) * cell + origin).unsqueeze(-1)   # (W, 3, 1)
+
+    def _pos_embed(self, pos):
+        """pos_proj (Conv1d k=1 + ReLU [x2], mssvt_backbone.py:43-54) on (W, 6, n) as plain matmuls: cuDNN
+        would run the 1x1 convolutions in TF32 by default, the matmul path stays fp32"""
+        y = pos.transpose(1, 2)                                              # (W, n, 6)
+        for layer in self.pos_proj:
+            y = torch.relu(y) if isinstance(layer, nn.ReLU) else \
+                torch.nn.functional.linear(y, layer.weight[:, :, 0], layer.bias)
+        return y.transpose(1, 2)                                             # (W, C, n)
+
+    def _ffn_autograd(self, u):
+        act = self.linear2(self.dropout1(self.activation(self.linear1(self.norm2(u)))))
+        y = u + self.drop_path(self.dropout1(act))
+        return self.out_linear(y) if hasattr(self, 'out_linear') else y
+
+    def _forward_autograd(self, sp_tensor):
+        """mssvt_backbone.py:201-346 as an autograd graph.  Index maps (windows, chessboard lists, FPS
+        keys, masks, three-NN) come from mssvt_block_geometry and carry no gradient; every row gather is
+        GroupingOperation (our CUDA forward + scatter-add backward) over global rows."""
+        x = sp_tensor.features.float().contiguous()
+        N, C = x.shape
+        g = self.geometry(sp_tensor)
+        W = int(g["total"].item())
+        dev = x.device
+        cnt_n = torch.tensor([N], dtype=torch.int32, device=dev)
+        cnt_w = torch.tensor([W], dtype=torch.int32, device=dev)
+        group = lambda feats, rows: mssvt_ops.grouping_operation(feats, cnt_n, rows, cnt_w)   # (W, c, ns)
+        q_row, k_row = g["q_row"][:W].contiguous(), g["k_row"][:W].contiguous()
+        q_mask, k_mask = q_row < 0, g["k_mask"][:W].bool()
+        xn = self.norm1(x)
+        xyz = sp_tensor.world_coords()
+        centre = self._window_centres(sp_tensor, g["win_list"][:W])
+        with torch.no_grad():
+            q_rel = (group(xyz, q_row) - centre) * (~q_mask).unsqueeze(1)
+            k_rel = (group(xyz, k_row) - centre) * (~k_mask).unsqueeze(1)   # masked keys: offset zeroed
+            q_pos = torch.cat((q_rel, centre.expand_as(q_rel)), 1)
+            k_pos = torch.cat((k_rel, centre.expand_as(k_rel)), 1)
+        q_fea = group(xn, q_row) + self._pos_embed(q_pos)                     # (W, C, nq)
+        k_fea = group(xn, k_row) + self._pos_embed(k_pos)                     # (W, C, 2K)
+        attn = self.ms_attn(q_fea.permute(0, 2, 1), k_fea.permute(0, 2, 1), batch_first=True,
+                            query_mask=q_mask, key_masks=k_mask)             # (W, nq, C)
+        # merge back to voxels: every covered voxel owns exactly one win1 slot (vox_slot)
+        slot = g["vox_slot"][:N].long()
+        cov = slot >= 0
+        sl = slot.clamp(min=0)
+        if self.use_feature_interpolation:
+            w_of = sl // self.max_num_win1
+            nn_idx = g["nn_idx"][:W].reshape(-1, 3)[sl].long()               # (N, 3) query slots
+            nn_w = g["nn_w"][:W].reshape(-1, 3)[sl]                          # (N, 3)
+            picked = attn[w_of.unsqueeze(1), nn_idx]                         # (N, 3, C); padded queries: zero rows
+            merged_cov = (picked * nn_w.unsqueeze(-1)).sum(1)
+        else:
+            q_slot = torch.full((N,), -1, dtype=torch.long, device=dev)
+            flat = q_row.reshape(-1).long()
+            ok = flat >= 0
+            q_slot[flat[ok]] = torch.arange(flat.numel(), device=dev)[ok]
+            cov = q_slot >= 0
+            merged_cov = attn.reshape(-1, C)[q_slot.clamp(min=0)]
+        merged = torch.where(cov.unsqueeze(1), merged_cov, x)               # Q5: uncovered rows keep x
+        u = self.drop_path(merged) + x
+        sp_tensor.features = self._ffn_autograd(u)
+        sp_tensor.gather_dict = None
+        return sp_tensor
 
     def _windows(self, sp_tensor):
         """window list of this block's win1 grid, cached on the tensor per window size"""
@@ -382,7 +451,8 @@ class MixedScaleSparseTransformerBlock(nn.Module):
         return y
 
     def forward(self, sp_tensor, block_idx=None, recycle_dict=None):
-        self._check_mode()
+        if self._differentiable(sp_tensor.features):
+            return self._forward_autograd(sp_tensor)
         x = sp_tensor.features
         if x.dtype != torch.float32 or not x.is_contiguous():
             x = x.float().contiguous()
@@ -429,9 +499,38 @@ class MixedScaleSparseTransformerBlock(nn.Module):
 class MixedScaleSparseTransformerCompressBlock(MixedScaleSparseTransformerBlock):
     """mssvt_backbone.py:349-398: one query per window, output re-indexed to the window grid."""
 
+    def _forward_autograd_compress(self, sp_tensor, x, k_row, grid, win_list, win_table, win_count):
+        """training path (see MixedScaleSparseTransformerBlock._forward_autograd)"""
+        B, N, dev = sp_tensor.batch_size, x.shape[0], x.device
+        W, dropped = (int(v) for v in win_count[B:B + 2].tolist())
+        if dropped:
+            raise RuntimeError("compress block: %d windows exceed max_num_wins" % dropped)
+        cnt_n = torch.tensor([N], dtype=torch.int32, device=dev)
+        cnt_w = torch.tensor([W], dtype=torch.int32, device=dev)
+        group = lambda feats, rows: mssvt_ops.grouping_operation(feats, cnt_n, rows, cnt_w)
+        k_row = k_row[:W].contiguous()
+        k_mask = k_row < 0
+        xn = self.norm1(x)
+        centre = self._window_centres(sp_tensor, win_list[:W])
+        with torch.no_grad():
+            k_rel = group(sp_tensor.world_coords(), k_row) - centre          # Q6: padded slots sit at 0 - centre
+            k_pos = torch.cat((k_rel, centre.expand_as(k_rel)), 1)
+        k_fea = group(xn, k_row)                                             # (W, C, n1), zeros at padding
+        q_fea = k_fea.max(dim=-1)[0].unsqueeze(0)                            # Q6: the max sees the zero padding
+        k_fea = k_fea + self._pos_embed(k_pos)
+        attn = self.ms_attn(q_fea, k_fea.permute(2, 0, 1), key_masks=k_mask).squeeze(0)    # (W, C)
+        vs = sp_tensor.voxel_size
+        sp_tensor.features = self._ffn_autograd(attn)
+        sp_tensor.indices = win_list[:W]
+        sp_tensor.spatial_shape = grid
+        sp_tensor.voxel_size = [vs[i] * self.win1_size[i] for i in range(3)]
+        sp_tensor.gather_dict = None
+        sp_tensor.map_table = win_table
+        return sp_tensor
+
     def forward(self, sp_tensor, block_idx=None, recycle_dict=None):
-        self._check_mode()
         x = sp_tensor.features
+        differentiable = self._differentiable(x)
         if x.dtype != torch.float32 or not x.is_contiguous():
             x = x.float().contiguous()
         dev, B = x.device, sp_tensor.batch_size
@@ -446,6 +545,8 @@ class MixedScaleSparseTransformerCompressBlock(MixedScaleSparseTransformerBlock)
         call("mssvt_window_rows", sx, sy, sz, *self.win1_size, t['win1'].shape[0],
              n1, ptr(t['win1']), cap, ptr(total), ptr(win_list), ptr(cells), ptr(vals), ptr(v_start),
              ptr(k_row), stream())
+        if differentiable:
+            return self._forward_autograd_compress(sp_tensor, x, k_row, grid, win_list, win_table, win_count)
         xn = self._layernorm1(x, sp_tensor)
         attn = torch.empty((cap, self.in_channels), dtype=torch.float32, device=dev)
         a = self.ms_attn

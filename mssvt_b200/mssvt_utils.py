@@ -183,6 +183,12 @@ class SparseTensor(object):
         else:
             feats, idx, count = self.features.float().contiguous(), self.indices, None
         C = feats.shape[1]
+        if torch.is_grad_enabled() and feats.requires_grad:
+            # training: the scatter has to stay in the autograd graph (index_put; backward = row gather)
+            out = feats.new_zeros((self.batch_size, z, y, x, C))
+            i = idx.long()
+            out = out.index_put((i[:, 0], i[:, 1], i[:, 2], i[:, 3]), feats)
+            return out.permute(0, 4, 1, 2, 3) if channels_first else out
         out = torch.empty((self.batch_size, C, z, y, x), dtype=torch.float32, device=feats.device)
         call("mssvt_dense_scatter", feats.shape[0], ptr(count), self.batch_size, C, z, y, x, ptr(feats),
              ptr(idx), ptr(out), stream())
@@ -211,8 +217,35 @@ class MixedScaleAttention(nn.Module):
         self.proj_drop = nn.Dropout(dropout)
         self.dropout = dropout
 
-    def forward(self, *args, **kwargs):
-        raise RuntimeError(
-            "MixedScaleAttention is evaluated inside the fused window kernels "
-            "(mssvt_block_attention / mssvt_compress_attention); call the enclosing "
-            "MixedScaleSparseTransformerBlock instead. There is no dense PyTorch path.")
+    def forward(self, query, keys, batch_first=False, query_mask=None, key_masks=None):
+        """Differentiable dense form (mssvt_utils.py:88-157), used by the TRAINING path of the blocks;
+        inference runs the same mathematics inside the fused window kernels (mssvt_block_attention[_tc] /
+        mssvt_compress_attention[_tc]) and never comes through here.  query (b, nq, C), keys (b, G * nk, C)
+        when batch_first; head group g reads channel slice g of the queries and key chunk g only; key_masks
+        (b, G * nk) bool (True = masked, additive -100 like the reference); padded queries give zero rows."""
+        if not query.is_cuda:
+            raise RuntimeError("mssvt_b200 runs on CUDA tensors only; there is no CPU path")
+        if not batch_first:
+            query, keys = query.transpose(1, 0), keys.transpose(1, 0)
+        b, nq, _ = query.shape
+        nk = keys.shape[1] // self.num_head_groups
+        outs, c0 = [], 0
+        for g, heads in enumerate(self.num_heads):
+            c1 = self.group_c_idx[g]
+            q = self.to_qs[g](query[:, :, c0:c1]).reshape(b, nq, heads, self.per_head_dim).permute(0, 2, 1, 3)
+            kv = self.to_kvs[g](keys[:, g * nk:(g + 1) * nk, c0:c1])
+            kv = kv.reshape(b, nk, 2, heads, self.per_head_dim).permute(2, 0, 3, 1, 4)
+            k, v = kv[0], kv[1]
+            c0 = c1
+            attn = (q * self.scale) @ k.transpose(-2, -1)                      # (b, heads, nq, nk)
+            if key_masks is not None:
+                km = key_masks[:, g * nk:(g + 1) * nk]
+                attn = attn + (km.to(attn.dtype) * -100.0).view(b, 1, 1, nk)
+                attn = torch.softmax(attn, dim=-1)
+            attn = self.attn_drop(attn)
+            x = (attn @ v).transpose(1, 2).reshape(b, nq, -1)
+            outs.append(self.proj_drop(self.projs[g](x)))
+        out = torch.cat(outs, dim=-1)
+        if query_mask is not None:
+            out = out * (~query_mask).unsqueeze(-1).to(out.dtype)
+        return out if batch_first else out.transpose(1, 0)

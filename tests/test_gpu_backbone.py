@@ -184,3 +184,93 @@ def test_backbone_tf32_mode_within_stated_tolerance(name):
     ref = torch.from_numpy(blob["out_features"])
     err = (sp.features.cpu() - ref).abs().max().item()
     assert err <= TF32_TOL * ref.abs().max().item(), err
+
+
+def test_height_compression_consumes_the_backbone_output():
+    """map_to_bev mirror (height_compression.py:31-51): dense() -> (B, C*D, H, W), stride passed on"""
+    from mssvt_b200.config import AttrDict
+    from mssvt_b200.height_compression import HeightCompression
+    blob, cfg, state = load_golden("s0_b2_n1200")
+    feats, coords = torch.from_numpy(blob["voxel_features"]), torch.from_numpy(blob["voxel_coords"])
+    model = MixedScaleSparseTransformer(cfg, feats.shape[1], list(blob["grid"]), list(S0_VOXEL), list(blob["pc_range"]))
+    model.load_state_dict(state, strict=True)
+    model = model.cuda().eval()
+    bev = HeightCompression(AttrDict(NUM_BEV_FEATURES=64, COMPRESS_LAYER_NUMS=0)).cuda().eval()
+    with torch.no_grad():
+        out = bev(model({"voxel_features": feats.cuda(), "voxel_coords": coords.cuda().float(),
+                         "batch_size": int(blob["batch_size"])}))
+    sf = out["spatial_features"]
+    sp = out["encoded_spconv_tensor"]
+    B, (X, Y, Z) = int(blob["batch_size"]), [int(v) for v in sp.spatial_shape]
+    assert sf.shape == (B, 64 * Z, Y, X) and out["spatial_features_stride"] == 1
+    ref = torch.zeros((B, 64, Z, Y, X))
+    idx = torch.from_numpy(blob["out_indices"]).long()
+    ref[idx[:, 0], :, idx[:, 1], idx[:, 2], idx[:, 3]] = torch.from_numpy(blob["out_features"])
+    err = (sf.cpu().view(B, 64, Z, Y, X) - ref).abs().max().item()
+    assert err <= FEATURE_TOL * ref.abs().max().item(), err
+    bev3 = HeightCompression(AttrDict(NUM_BEV_FEATURES=64 * Z)).cuda().eval()   # default 3-layer conv stack
+    with torch.no_grad():
+        assert bev3(out)["spatial_features"].shape == sf.shape
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_training_path_forward_matches_reference_golden(name):
+    """the autograd (training) path computes the same features as the fused inference kernels / the reference"""
+    blob, cfg, state = load_golden(name)
+    feats, coords = torch.from_numpy(blob["voxel_features"]), torch.from_numpy(blob["voxel_coords"])
+    model = MixedScaleSparseTransformer(cfg, feats.shape[1], list(blob["grid"]), list(S0_VOXEL), list(blob["pc_range"]))
+    model.load_state_dict(state, strict=True)
+    model = model.cuda().eval()          # eval: DropPath / Dropout are identities, gradients still flow
+    x = feats.cuda().requires_grad_(True)
+    sp = model({"voxel_features": x, "voxel_coords": coords.cuda().float(),
+                "batch_size": int(blob["batch_size"])})["encoded_spconv_tensor"]
+    assert sp.features.requires_grad
+    assert torch.equal(sp.indices.cpu(), torch.from_numpy(blob["out_indices"]))
+    ref = torch.from_numpy(blob["out_features"])
+    err = (sp.features.detach().cpu() - ref).abs().max().item()
+    assert err <= FEATURE_TOL * ref.abs().max().item(), (err, ref.abs().max().item())
+    dense = sp.dense()
+    assert dense.requires_grad and dense.shape[1] == ref.shape[1]
+    (dense ** 2).mean().backward()
+    assert x.grad is not None and torch.isfinite(x.grad).all() and x.grad.abs().max() > 0
+    for n, p in model.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), n
+
+
+def test_training_path_gradients_cuda_gather_backward_vs_autograd_indexing(monkeypatch):
+    """Same graph twice: row gathers through GroupingOperation (mssvt_group_features /
+    mssvt_group_features_grad, the CUDA scatter-add) and through plain torch indexing (autograd's own
+    backward).  Input and parameter gradients must agree (fp32 atomics: order-dependent rounding only)."""
+    from mssvt_b200 import mssvt_ops
+    blob, cfg, state = load_golden("s0_b2_n1200")
+    feats, coords = torch.from_numpy(blob["voxel_features"]), torch.from_numpy(blob["voxel_coords"])
+
+    def run():
+        model = MixedScaleSparseTransformer(cfg, feats.shape[1], list(blob["grid"]), list(S0_VOXEL),
+                                            list(blob["pc_range"]))
+        model.load_state_dict(state, strict=True)
+        model = model.cuda().train()
+        for m in model.modules():            # deterministic: no stochastic depth / dropout
+            if isinstance(m, torch.nn.Dropout):
+                m.p = 0.0
+            if hasattr(m, "drop_prob"):
+                m.drop_prob = 0.0
+        x = feats.cuda().requires_grad_(True)
+        sp = model({"voxel_features": x, "voxel_coords": coords.cuda().float(),
+                    "batch_size": int(blob["batch_size"])})["encoded_spconv_tensor"]
+        (sp.features ** 2).sum().backward()
+        return x.grad.clone(), {n: p.grad.clone() for n, p in model.named_parameters()}
+
+    gx, gp = run()
+
+    def torch_gather(features, features_batch_cnt, idx, idx_batch_cnt):
+        pad = torch.cat([features, features.new_zeros(1, features.shape[1])], 0)
+        rows = torch.where(idx < 0, torch.full_like(idx, features.shape[0]), idx).long()
+        return pad[rows].permute(0, 2, 1)                      # (M, C, ns)
+
+    monkeypatch.setattr(mssvt_ops, "grouping_operation", torch_gather)
+    rx, rp = run()
+    assert (gx - rx).abs().max().item() <= 1e-4 * rx.abs().max().item()
+    for n in rp:
+        scale = rp[n].abs().max().item()
+        assert (gp[n] - rp[n]).abs().max().item() <= 1e-4 * max(scale, 1e-6), n
