@@ -193,8 +193,11 @@ def our_arm(args):
         out_idx = [torch.empty((N_VOXELS, 4), dtype=torch.int32).pin_memory() for _ in range(2)]
         s_in, s_comp, s_out = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
 
+        gpu_spans = []
+
         def e2e_run(steps, stamps=None):
             staged, keep, rows = {}, [], 0
+            gpu_spans.clear()
 
             def stage(i):
                 f, c = host[i % POOL]
@@ -222,10 +225,15 @@ def our_arm(args):
                 fd, cd, ev = staged.pop(i)
                 with torch.cuda.stream(s_comp):
                     s_comp.wait_event(ev)
+                    if stamps is not None:
+                        g0 = torch.cuda.Event(enable_timing=True)
+                        g0.record(s_comp)
                     sp = model({"voxel_features": fd, "voxel_coords": cd, "batch_size": 1})["encoded_spconv_tensor"]
                     sp.prefetch_row_count()
-                    done = torch.cuda.Event()
+                    done = torch.cuda.Event(enable_timing=stamps is not None)
                     done.record(s_comp)
+                    if stamps is not None:
+                        gpu_spans.append((g0, done))
                 if pending is not None:      # step i is queued: now wait for step i-1's count and copy it out
                     rows = drain(*pending)
                 pending = (i, sp, done)
@@ -250,6 +258,10 @@ def our_arm(args):
             stamps.append(time.perf_counter())
             e2e_samples.append(stamps[-1] - stamps[0])
             gaps = sorted(((b - a) * 1e3, k) for k, (a, b) in enumerate(zip(stamps, stamps[1:])))[-3:]
+            busy = [a.elapsed_time(b) for a, b in gpu_spans]
+            idle = [gpu_spans[k][1].elapsed_time(gpu_spans[k + 1][0]) for k in range(len(gpu_spans) - 1)]
+            print(f"[bench] e2e pass: forward on the compute stream {statistics.mean(busy):.3f} ms/step, "
+                  f"idle between forwards {statistics.mean(idle):.3f} ms/step", file=sys.stderr)
             print(f"[bench] e2e pass {len(e2e_samples)}: {e2e_samples[-1] * 1e3:.2f} ms for {args.steps} steps; "
                   f"longest host gaps (ms, step): {gaps}", file=sys.stderr)
         e2e_s = sorted(e2e_samples)[1]

@@ -46,7 +46,7 @@ def main():
             step(i)
         pr.disable()
         torch.cuda.synchronize()
-        pstats.Stats(pr).sort_stats("cumulative").print_stats(28)
+        pstats.Stats(pr).sort_stats("tottime").print_stats(22)
 
 
 if __name__ == "__main__":

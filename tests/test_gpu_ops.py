@@ -213,3 +213,65 @@ def test_reference_kernels_were_present_on_this_box():
     """oracle/_ref (the reference's own kernels, built unmodified in the build container) must
     travel to the GPU box; without it the cross-checks above silently reduce to oracle-only."""
     assert HAVE_REF, "oracle/_ref/libmssvt_ref.so missing: run `make -C oracle ref` where /root/reference exists"
+
+
+@pytest.mark.parametrize("rows,k", [(64, 32), (128, 64), (8, 8)])
+def test_pack_operand_tf32_layout_and_rounding(rows, k):
+    """mssvt_pack_operand_tf32: K-major 8-row x 16-byte core matrices (chunk c of row n at byte
+    c * rows * 16 + (n / 8) * 128 + (n % 8) * 16), values rounded to TF32 (round to nearest, ties away)"""
+    from mssvt_b200._lib import call, ptr, stream
+    torch.manual_seed(rows)
+    w = torch.randn(rows, k)
+    out = torch.empty(rows * k, device="cuda")
+    call("mssvt_pack_operand_tf32", ptr(w.cuda().contiguous()), rows, k, ptr(out), stream())
+    bits = w.numpy().view(np.uint32).astype(np.uint64)
+    tf32 = (((bits + 0x1000) & 0xFFFFE000) & 0xFFFFFFFF).astype(np.uint32).view(np.float32)
+    want = np.zeros(rows * k, np.float32)
+    for n in range(rows):
+        for c in range(k // 4):
+            at = (c * rows * 16 + (n // 8) * 128 + (n % 8) * 16) // 4
+            want[at:at + 4] = tf32[n, 4 * c:4 * c + 4]
+    assert np.array_equal(out.cpu().numpy(), want)
+
+
+def test_attention_tile_plan_invariants():
+    """mssvt_attention_tiles: per scale, every window with a real query lies in exactly one tile; a tile
+    holds <= 128 key tasks, <= 128 queries, <= 32 windows, <= 2048 score slots; offsets are prefix sums"""
+    from mssvt_b200.config import block_cfg
+    from mssvt_b200.mssvt_backbone import MixedScaleSparseTransformerBlock
+    from mssvt_b200.mssvt_utils import SparseTensor
+    from mssvt_b200.synth import S0_RANGE, S0_VOXEL
+    cfg = block_cfg()
+    blk = MixedScaleSparseTransformerBlock(cfg, 64, 128, 64, [2, 2], drop_path=0.0, window_size=cfg.window_size,
+                                           cbs_pattern=1).cuda().eval()
+    feats, coords = synth_frame(5, 30000, crop=0.45)
+    sp = SparseTensor(features=torch.from_numpy(feats).cuda(), indices=torch.from_numpy(coords).cuda(),
+                      spatial_shape=list(S0_GRID), voxel_size=list(S0_VOXEL), point_cloud_range=list(S0_RANGE),
+                      batch_size=1, hash_size=400000, map_table=None, gather_dict=None)
+    g = blk.geometry(sp)
+    tiles, tile_count, win_rec, win_ctr = (t.cpu() for t in blk._tile_plan(sp, g, 2))
+    W = int(g["total"].item())
+    meta, q_base = g["meta"][:W].cpu(), g["q_base"][:W + 1].cpu()
+    heads = 2
+    for s in range(2):
+        nqr = meta[:, 0]
+        nrep = torch.where(nqr > 0, meta[:, 2 + s] & 0xff, torch.zeros_like(nqr))
+        rec = win_rec[s, :W]
+        assert torch.equal(rec[:, 0], q_base[:W])
+        assert torch.equal(rec[:, 1] & 0xff, nqr) and torch.equal((rec[:, 1] >> 8) & 0xff, nrep)
+        seen = torch.zeros(W, dtype=torch.int32)
+        for t in range(int(tile_count[s])):
+            ws, nw = (int(v) for v in tiles[s, t])
+            assert 0 < nw <= 32 and ws + nw <= W
+            seen[ws:ws + nw] += 1
+            r, q = nrep[ws:ws + nw], nqr[ws:ws + nw]
+            assert int(r.sum()) <= 128 and int(q.sum()) <= 128 and int((r * q).sum()) * heads <= 2048
+            off = rec[ws:ws + nw, 2]
+            zero = torch.zeros(1, dtype=r.dtype)
+            assert torch.equal(off & 0xff, torch.cat([zero, r.cumsum(0)[:-1]]).int())
+            assert torch.equal((off >> 8) & 0xff, torch.cat([zero, q.cumsum(0)[:-1]]).int())
+            assert torch.equal(off >> 16, torch.cat([zero, (r * q * heads).cumsum(0)[:-1]]).int())
+        assert bool((seen[nrep > 0] == 1).all()) and int(seen.max()) <= 1
+    cell = torch.tensor([S0_VOXEL[i] * 3 for i in range(3)])
+    want = (g["win_list"][:W].cpu()[:, [3, 2, 1]].float() + 0.5) * cell + torch.tensor(S0_RANGE[:3])
+    assert torch.allclose(win_ctr[:W, :3], want, atol=1e-5)
