@@ -274,3 +274,59 @@ def test_training_path_gradients_cuda_gather_backward_vs_autograd_indexing(monke
     for n in rp:
         scale = rp[n].abs().max().item()
         assert (gp[n] - rp[n]).abs().max().item() <= 1e-4 * max(scale, 1e-6), n
+
+
+def test_tf32_mode_vs_live_oracle_20k_and_fp32_mode_150k():
+    """tensor-core mode at BASELINE config 1 size against the CPU oracle, and at config 2 size against
+    the exact-fp32 kernels of the same library (the oracle takes seconds per 150 k frame)"""
+    feats, coords = synth_frame(3, 20000, crop=0.38)
+    feats, coords = torch.from_numpy(feats), torch.from_numpy(coords)
+    cfg = s0_model_cfg()
+    torch.manual_seed(0)
+    model = MixedScaleSparseTransformer(cfg, 64, list(S0_GRID), list(S0_VOXEL), list(S0_RANGE))
+    state = {k: v.clone() for k, v in model.state_dict().items()}
+    with torch.no_grad():
+        want = orc.backbone_forward(state, cfg, list(S0_GRID), list(S0_VOXEL), list(S0_RANGE), feats, coords, 1)
+    model = model.cuda().eval()
+    model.set_precision("tf32")
+    run = lambda f, c: model({"voxel_features": f.cuda(), "voxel_coords": c.cuda().float(),
+                              "batch_size": 1})["encoded_spconv_tensor"]
+    with torch.no_grad():
+        sp = run(feats, coords)
+    assert torch.equal(sp.indices.cpu(), want.indices)
+    err = (sp.features.cpu() - want.features).abs().max().item()
+    assert err <= TF32_TOL * want.features.abs().max().item(), err
+    # full-size frame: both modes of the library on the same input
+    feats, coords = synth_frame(4, 150000)
+    feats, coords = torch.from_numpy(feats), torch.from_numpy(coords)
+    with torch.no_grad():
+        tc = run(feats, coords)
+        tc_feat, tc_idx = tc.features.clone(), tc.indices.clone()
+        model.set_precision("fp32")
+        ex = run(feats, coords)
+    assert torch.equal(tc_idx, ex.indices)
+    err = (tc_feat - ex.features).abs().max().item()
+    assert err <= TF32_TOL * ex.features.abs().max().item(), err
+    assert err > 0
+
+
+@pytest.mark.parametrize("n", [1, 37, 300])
+def test_tiny_frames_in_both_modes(n):
+    """a handful of voxels: single windows, tiles with one task, grids smaller than the SM count"""
+    feats, coords = synth_frame(11, n, crop=0.05)
+    feats, coords = torch.from_numpy(feats), torch.from_numpy(coords)
+    cfg = s0_model_cfg()
+    torch.manual_seed(0)
+    model = MixedScaleSparseTransformer(cfg, 64, list(S0_GRID), list(S0_VOXEL), list(S0_RANGE))
+    state = {k: v.clone() for k, v in model.state_dict().items()}
+    with torch.no_grad():
+        want = orc.backbone_forward(state, cfg, list(S0_GRID), list(S0_VOXEL), list(S0_RANGE), feats, coords, 1)
+    model = model.cuda().eval()
+    for precision, tol in (("fp32", FEATURE_TOL), ("tf32", TF32_TOL)):
+        model.set_precision(precision)
+        with torch.no_grad():
+            sp = model({"voxel_features": feats.cuda(), "voxel_coords": coords.cuda().float(),
+                        "batch_size": 1})["encoded_spconv_tensor"]
+        assert torch.equal(sp.indices.cpu(), want.indices)
+        err = (sp.features.cpu() - want.features).abs().max().item()
+        assert err <= tol * want.features.abs().max().item(), (precision, err)
