@@ -180,6 +180,8 @@ k_tca_keys(TcAttnParams P, int win_cap, const int2 *__restrict__ tiles, const in
     extern __shared__ __align__(128) char smem_raw[];
     const int tid = threadIdx.x, warp = tid >> 5;
     const int K = P.K;
+    pdl_launch_dependents();
+    pdl_wait();  // (the scale of this CTA, hence its weights, depends on the tile counts: nothing to do before)
 
     // ---- every CTA works on one scale for its whole life (8 KB of weights instead of 16); the CTAs of the
     //      two scales are interleaved over the grid in proportion to the tile counts
@@ -415,6 +417,8 @@ k_tca_merge(TcAttnParams P, int win_cap, const int *__restrict__ win_count_total
             const int *__restrict__ q_row, const int *__restrict__ vox_slot,
             const unsigned char *__restrict__ nn_idx, const float *__restrict__ nn_w,
             const float *__restrict__ Pbuf, float *__restrict__ merged) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int num_wins = min(win_cap, __ldg(win_count_total));
     if (P.interp) {
         // thread = (voxel row, 16 channels): the voxel's win1 slot names its 3 nearest query slots
@@ -561,9 +565,8 @@ int mssvt_block_attention_tc(int C, int heads_per_group, int nq, int key_num_sam
     ++g_launches;
 #define TCA_LAUNCH(H)                                                                                      \
     cudaFuncSetAttribute(k_tca_keys<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
-    k_tca_keys<H><<<grid, TCA_THREADS, smem, s>>>(P, win_capacity, (const int2 *)tiles, tile_count,         \
-                                                  (const int4 *)win_rec, (const float4 *)win_ctr, xn, xyz, \
-                                                  rep_row, Qbuf, Obuf)
+    launch_pdl(k_tca_keys<H>, dim3(grid), dim3(TCA_THREADS), smem, s, P, win_capacity, (const int2 *)tiles,   \
+               tile_count, (const int4 *)win_rec, (const float4 *)win_ctr, xn, xyz, rep_row, Qbuf, Obuf)
     if (heads_per_group == 1) { TCA_LAUNCH(1); }
     else if (heads_per_group == 2) { TCA_LAUNCH(2); }
     else { TCA_LAUNCH(4); }
@@ -575,8 +578,8 @@ int mssvt_block_attention_tc(int C, int heads_per_group, int nq, int key_num_sam
         tcl_launch(L, rows, num_voxels, Pbuf, s);
     }
     ++g_launches;
-    k_tca_merge<<<wide, 256, 0, s>>>(P, win_capacity, win_count_total, num_voxels, meta, q_base, q_src, q_row,
-                                     vox_slot, nn_idx, nn_w, Pbuf, merged);
+    launch_pdl(k_tca_merge, dim3(wide), dim3(256), 0, s, P, win_capacity, win_count_total, num_voxels, meta, q_base,
+               q_src, q_row, vox_slot, nn_idx, nn_w, Pbuf, merged);
     return check_launch();
 }
 

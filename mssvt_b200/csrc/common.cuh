@@ -29,6 +29,29 @@ static inline int div_up(long long a, long long b) { return (int)((a + b - 1) / 
 
 // grid for a grid-stride kernel: enough CTAs to cover `items`, capped at `waves` full waves of
 // the 148 SMs times the resident CTAs per SM.
+// ---- programmatic dependent launch (PDL).  A kernel launched with launch_pdl() may become resident while
+// its predecessor in the stream is still draining: its CTAs run their prologue (stage packed weights,
+// barriers, TMEM allocation -- nothing the predecessor writes) and then block in pdl_wait() until the
+// predecessor has completed and its writes are visible.  Every kernel of such a chain calls
+// pdl_launch_dependents() first thing, which lets the successor start as soon as all CTAs of this grid
+// are running.  This removes the launch gap and the tail idle time between the ~45 kernels of a frame.
+// RULE: in a kernel launched with launch_pdl(), every read of data that is not a static parameter
+// (weights, biases) comes after pdl_wait().
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                              Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 static inline int persistent_grid(long long items, int per_cta, int ctas_per_sm, int waves = 4) {
     long long need = (items + per_cta - 1) / per_cta;
     long long cap = (long long)MSSVT_NUM_SMS * ctas_per_sm * waves;

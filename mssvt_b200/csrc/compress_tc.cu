@@ -88,6 +88,8 @@ k_tcc_plan(int n1, int win_cap, const int *__restrict__ win_count_total, const i
 __global__ void __launch_bounds__(256)
 k_tcc_pool(int n1, int win_cap, const int *__restrict__ win_count_total, const int *__restrict__ win_rec,
            const int *__restrict__ k_row, const float *__restrict__ xn, float *__restrict__ pooled) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int num_wins = min(win_cap, __ldg(win_count_total));
     const long long total = (long long)num_wins * 16;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
@@ -141,6 +143,7 @@ k_tcc_keys(TccParams P, const int2 *__restrict__ tiles, const int *__restrict__ 
     constexpr int HD = TCC_C / HEADS;
     constexpr int DPT = HD / 4;
     constexpr int HH = HEADS / 2;  // heads per thread
+    pdl_launch_dependents();
     extern __shared__ __align__(128) char smem_raw[];
     const int tid = threadIdx.x, warp = tid >> 5;
     const int r = tid & (TCC_ROWS - 1), half = tid >> 7;
@@ -185,6 +188,7 @@ k_tcc_keys(TccParams P, const int2 *__restrict__ tiles, const int *__restrict__ 
     const uint32_t a_lbo = TCC_ROWS * 16, w2_lbo = 64 * 16, wkv_lbo = 128 * 16;
     const uint32_t my_row_off = (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u;
     uint32_t phase = 0;
+    pdl_wait();  // (everything above touched static parameters only)
     const int T = __ldg(tile_count);
 
     for (int t = blockIdx.x; t < T; t += gridDim.x) {
@@ -403,7 +407,8 @@ int mssvt_compress_attention_tc(int C, int heads, int n1, float scale, const flo
                                                     make_float3(range_min[0], range_min[1], range_min[2]), tiles,
                                                     tile_count, win_rec, win_ctr);
     ++g_launches;
-    k_tcc_pool<<<MSSVT_NUM_SMS * 8, 256, 0, s>>>(n1, win_capacity, win_count_total, win_rec, k_row, xn, pooled);
+    launch_pdl(k_tcc_pool, dim3(MSSVT_NUM_SMS * 8), dim3(256), 0, s, n1, win_capacity, win_count_total, (const int *)win_rec,
+               k_row, xn, pooled);
     {
         const TclCopyRows rows = {pooled, win_count_total, nullptr, win_capacity};
         const TclParams L = {wq, bq, nullptr, scale};
@@ -417,7 +422,8 @@ int mssvt_compress_attention_tc(int C, int heads, int n1, float scale, const flo
     ++g_launches;
 #define TCC_LAUNCH(H)                                                                                     \
     cudaFuncSetAttribute(k_tcc_keys<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
-    k_tcc_keys<H><<<grid, TCC_THREADS, smem, s>>>(P, tiles, tile_count, win_rec, win_ctr, xn, xyz, k_row, Qc, Oc)
+    launch_pdl(k_tcc_keys<H>, dim3(grid), dim3(TCC_THREADS), smem, s, P, (const int2 *)tiles, (const int *)tile_count,   \
+               (const int *)win_rec, (const float4 *)win_ctr, xn, xyz, k_row, (const float *)Qc, Oc)
     if (heads == 2) { TCC_LAUNCH(2); }
     else if (heads == 4) { TCC_LAUNCH(4); }
     else { TCC_LAUNCH(8); }

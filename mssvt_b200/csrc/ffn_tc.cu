@@ -51,6 +51,7 @@ k_ffn_tc(FfnTcParams P, int n_cap, const int *__restrict__ n_dev, const float *_
          float *__restrict__ y, float *__restrict__ xn_next) {
     constexpr int CH = C / 2;  // channels per thread: two threads (warps w and w + 4) share a row
     extern __shared__ __align__(128) char smem_raw[];
+    pdl_launch_dependents();
     const int F = P.F, FH = F / 2;
     const int tid = threadIdx.x, warp = tid >> 5;
     const int r = tid & (TC_ROWS - 1), half = tid >> 7;
@@ -99,6 +100,7 @@ k_ffn_tc(FfnTcParams P, int n_cap, const int *__restrict__ n_dev, const float *_
     const uint32_t a_lbo = TC_ROWS * 16, w1_lbo = (uint32_t)F * 16, w2_lbo = (uint32_t)C * 16;
     const uint32_t sA_u = smem_u32(sA), sW1_u = smem_u32(sW1), sW2_u = smem_u32(sW2);
 
+    pdl_wait();  // (everything above touched static parameters only)
     const int n = n_dev ? min(n_cap, __ldg(n_dev)) : n_cap;
     const int tiles = (n + TC_ROWS - 1) / TC_ROWS;
     uint32_t phase = 0;
@@ -357,10 +359,12 @@ int mssvt_ffn_tc(int C, int F, int mode, float eps, const float *ln_g, const flo
     ++g_launches;
     if (C == 64) {
         cudaFuncSetAttribute(k_ffn_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_ffn_tc<64><<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(P, num_rows, num_rows_dev, x, merged, covered, y, xn_next);
+        launch_pdl(k_ffn_tc<64>, dim3(grid), dim3(TC_THREADS), smem, (cudaStream_t)stream, P, num_rows, num_rows_dev, x,
+                   merged, covered, y, xn_next);
     } else {
         cudaFuncSetAttribute(k_ffn_tc<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_ffn_tc<32><<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(P, num_rows, num_rows_dev, x, merged, covered, y, xn_next);
+        launch_pdl(k_ffn_tc<32>, dim3(grid), dim3(TC_THREADS), smem, (cudaStream_t)stream, P, num_rows, num_rows_dev, x,
+                   merged, covered, y, xn_next);
     }
     return check_launch();
 }

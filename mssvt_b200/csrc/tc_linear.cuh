@@ -53,6 +53,7 @@ template <class Producer>
 __global__ void __launch_bounds__(TCL_THREADS, 4)
 k_tc_linear(TclParams P, Producer prod, float *__restrict__ out) {
     extern __shared__ __align__(128) char smem_raw[];
+    pdl_launch_dependents();
     const int tid = threadIdx.x, warp = tid >> 5;
     const int r = tid & (TCL_ROWS - 1), half = tid >> 7;
     char *sA = smem_raw;                           // [16][128][16 B]
@@ -81,6 +82,7 @@ k_tc_linear(TclParams P, Producer prod, float *__restrict__ out) {
     const uint32_t a_lbo = TCL_ROWS * 16, w_lbo = TCL_C * 16;
     const uint32_t my_row_off = (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u;
     char *stg = sA + warp * 4096;  // warp-private staging (inside the A tile, see the barriers below)
+    pdl_wait();  // (everything above touched static parameters only)
     const int n = prod.rows();
     const int tiles = (n + TCL_ROWS - 1) / TCL_ROWS;
     uint32_t phase = 0;
@@ -142,7 +144,7 @@ static inline void tcl_launch(const TclParams &P, const Producer &prod, int row_
     if (grid < 1) return;
     cudaFuncSetAttribute(k_tc_linear<Producer>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     ++g_launches;
-    k_tc_linear<Producer><<<grid, TCL_THREADS, smem, s>>>(P, prod, out);
+    launch_pdl(k_tc_linear<Producer>, dim3(grid), dim3(TCL_THREADS), smem, s, P, prod, out);
 }
 
 }  // namespace mssvt
