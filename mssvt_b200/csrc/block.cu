@@ -64,6 +64,8 @@ k_layernorm(int n_cap, const int *__restrict__ n_dev, int C, const float *__rest
 __global__ void __launch_bounds__(256)
 k_layernorm64(int n_cap, const int *__restrict__ n_dev, const float *__restrict__ x,
               const float *__restrict__ gamma, const float *__restrict__ beta, float eps, float *__restrict__ y) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int n = n_dev ? min(n_cap, __ldg(n_dev)) : n_cap;
     const int lane = threadIdx.x & 31, sub = lane >> 4, c4 = lane & 15;
     const int warps = (gridDim.x * blockDim.x) >> 5;
@@ -198,7 +200,7 @@ int mssvt_layernorm(int num_rows, const int *num_rows_dev, int C, const float *x
     if (!x || !gamma || !beta || !y) return MSSVT_ERR_INVALID;
     ++g_launches;
     if (C == 64)
-        k_layernorm64<<<persistent_grid(num_rows, 64, 8), 256, 0, (cudaStream_t)stream>>>(
+        launch_pdl(k_layernorm64, dim3(persistent_grid(num_rows, 64, 8)), dim3(256), 0, (cudaStream_t)stream, 
             num_rows, num_rows_dev, x, gamma, beta, eps, y);
     else
         k_layernorm<<<persistent_grid(num_rows, 8, 8), 256, 0, (cudaStream_t)stream>>>(

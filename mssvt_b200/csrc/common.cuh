@@ -35,8 +35,12 @@ static inline int div_up(long long a, long long b) { return (int)((a + b - 1) / 
 // predecessor has completed and its writes are visible.  Every kernel of such a chain calls
 // pdl_launch_dependents() first thing, which lets the successor start as soon as all CTAs of this grid
 // are running.  This removes the launch gap and the tail idle time between the ~45 kernels of a frame.
-// RULE: in a kernel launched with launch_pdl(), every read of data that is not a static parameter
-// (weights, biases) comes after pdl_wait().
+// RULES: (1) in a kernel launched with launch_pdl(), every read of data that is not a static parameter
+// (weights, biases) comes after pdl_wait().  (2) The L1 of an SM is not invalidated between the early start
+// of the dependent's CTAs and their pdl_wait(), so a dependent must not read -- through L1-cached loads
+// (__ldg / const __restrict__) -- addresses that the predecessor both reads and writes (its own loads may have
+// left stale lines in that L1).  The feature-kernel chain satisfies this (every kernel only writes its
+// outputs); the hash / window / scan kernels, which read and update the same tables, are launched normally.
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
