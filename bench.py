@@ -156,10 +156,22 @@ def our_arm(args):
         f, c = synth_frame(1000 * rank + i, N_VOXELS)
         host.append((torch.from_numpy(f).pin_memory(), torch.from_numpy(c).pin_memory()))
     dev = [(f.to(device), c.to(device).float()) for f, c in host]
+    dev_idx = [c.to(device) for _, c in host]          # int32 coordinates: the graphs bind to these buffers
 
-    def step(i):
+    def eager_step(i):
         f, c = dev[i % POOL]
         return model({"voxel_features": f, "voxel_coords": c, "batch_size": 1})["encoded_spconv_tensor"]
+
+    # --launch graph (default): the forward of every resident frame is captured once into a CUDA graph bound
+    # to that frame's buffers; a step is one cudaGraphLaunch replaying all of its kernels (geometry included)
+    graphs = None
+    if args.launch == "graph":
+        with torch.no_grad():
+            graphs = [model.capture({"voxel_features": dev[i][0], "voxel_coords": dev_idx[i], "batch_size": 1})
+                      for i in range(POOL)]
+
+    def step(i):
+        return graphs[i % POOL].replay() if graphs is not None else eager_step(i)
 
     def barrier():
         if world > 1:
@@ -184,7 +196,20 @@ def our_arm(args):
         barrier()
         ms = e0.elapsed_time(e1)
         launches = _lib.call("mssvt_launch_count") - launches0
+        if graphs is not None:
+            launches = sum(graphs[(args.warmup + i) % POOL].launches for i in range(args.steps))
         clocks = sampler.stop()
+        # the same K steps launched kernel by kernel from Python, for the record
+        x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for i in range(3):
+            eager_step(i)
+        barrier()
+        x0.record()
+        for i in range(args.steps):
+            eager_step(args.warmup + i)
+        x1.record()
+        barrier()
+        eager_ms = x0.elapsed_time(x1) / args.steps
 
         # ---- e2e: module API from pinned HOST buffers; every step copies its inputs host -> device and
         #      its result (features + indices of the output tensor) device -> host.  Three streams:
@@ -194,16 +219,34 @@ def our_arm(args):
         s_in, s_comp, s_out = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
 
         gpu_spans = []
+        # graph launch: a ring of three captured forwards with their own static input / output buffers, so
+        # that the H2D of step i+1 and the D2H of step i-1 never touch the buffers step i is using
+        slots = []
+        if graphs is not None:
+            for r in range(3):
+                fb, cb = dev[r][0].clone(), dev_idx[r].clone()
+                slots.append({"f": fb, "c": cb, "done": None, "drained": None,
+                              "g": model.capture({"voxel_features": fb, "voxel_coords": cb, "batch_size": 1})})
 
         def e2e_run(steps, stamps=None):
             staged, keep, rows = {}, [], 0
             gpu_spans.clear()
+            for sl in slots:
+                sl["done"] = sl["drained"] = None
 
             def stage(i):
                 f, c = host[i % POOL]
                 with torch.cuda.stream(s_in):
-                    fd = f.to(device, non_blocking=True)
-                    cd = c.to(device, non_blocking=True)
+                    if slots:
+                        sl = slots[i % 3]
+                        if sl["done"] is not None:
+                            s_in.wait_event(sl["done"])      # step i-3 has consumed the slot's inputs
+                        sl["f"].copy_(f, non_blocking=True)
+                        sl["c"].copy_(c, non_blocking=True)
+                        fd, cd = sl["f"], sl["c"]
+                    else:
+                        fd = f.to(device, non_blocking=True)
+                        cd = c.to(device, non_blocking=True)
                     ev = torch.cuda.Event()
                     ev.record(s_in)
                 staged[i] = (fd, cd, ev)
@@ -215,6 +258,9 @@ def our_arm(args):
                     n = sp.features.shape[0]
                     out_feat[i % 2][:n].copy_(sp.features, non_blocking=True)
                     out_idx[i % 2][:n].copy_(sp.indices, non_blocking=True)
+                    if slots:
+                        slots[i % 3]["drained"] = torch.cuda.Event()
+                        slots[i % 3]["drained"].record(s_out)
                 return n
 
             stage(0)
@@ -225,13 +271,20 @@ def our_arm(args):
                 fd, cd, ev = staged.pop(i)
                 with torch.cuda.stream(s_comp):
                     s_comp.wait_event(ev)
+                    if slots and slots[i % 3]["drained"] is not None:
+                        s_comp.wait_event(slots[i % 3]["drained"])   # step i-3's rows have left the slot
                     if stamps is not None:
                         g0 = torch.cuda.Event(enable_timing=True)
                         g0.record(s_comp)
-                    sp = model({"voxel_features": fd, "voxel_coords": cd, "batch_size": 1})["encoded_spconv_tensor"]
+                    if slots:
+                        sp = slots[i % 3]["g"].replay()
+                    else:
+                        sp = model({"voxel_features": fd, "voxel_coords": cd, "batch_size": 1})["encoded_spconv_tensor"]
                     sp.prefetch_row_count()
                     done = torch.cuda.Event(enable_timing=stamps is not None)
                     done.record(s_comp)
+                    if slots:
+                        slots[i % 3]["done"] = done
                     if stamps is not None:
                         gpu_spans.append((g0, done))
                 if pending is not None:      # step i is queued: now wait for step i-1's count and copy it out
@@ -272,7 +325,7 @@ def our_arm(args):
         # ---- per-kernel breakdown (instrumented extra pass, not part of the timed region)
         _lib.PROFILE = []
         for i in range(args.steps):
-            step(args.warmup + i)
+            eager_step(args.warmup + i)
         torch.cuda.synchronize()
         per = {}
         for name, a, b in _lib.PROFILE:
@@ -286,12 +339,12 @@ def our_arm(args):
     model.set_precision(other)
     with torch.no_grad():
         for i in range(3):
-            step(i)
+            eager_step(i)
         o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         o0.record()
         for i in range(max(args.steps // 2, 3)):
-            step(i)
+            eager_step(i)
         o1.record()
         torch.cuda.synchronize()
     other_ms = o0.elapsed_time(o1) / max(args.steps // 2, 3)
@@ -329,6 +382,10 @@ def our_arm(args):
                                "step, C=64, hash 400000, batch 1; random-init weights (seed 0)",
                    "voxels_per_frame": N_VOXELS, "frames_per_step": world, "sharding": "by frame, no collective",
                    "l2": "inputs rotate through a pool of %d distinct frames (326 MB > 126 MB L2)" % POOL,
+                   "launch": ("one CUDA graph replay per forward (captured once per resident frame; every replay runs "
+                              "all kernels of the frame, geometry included)" if args.launch == "graph"
+                              else "eager: kernel by kernel from Python"),
+                   "eager_ms_per_step": round(eager_ms, 4),
                    "precision": ("fp32 FFMA kernels (features within 1e-4 of max|fp32 reference|)" if args.precision == "fp32"
                                  else "projections and FFN GEMMs on tcgen05 with TF32 operands / fp32 accumulate, rest fp32 "
                                       "(features within 2e-3 of max|fp32 reference|)")},
@@ -444,6 +501,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--launch", default="graph", choices=["graph", "eager"],
+                    help="graph (default): every forward is one CUDA-graph replay; eager: kernel by kernel from Python")
     ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32"],
                     help="tf32 (default): K/V projection and FFN GEMMs on the tcgen05 tensor cores with TF32 "
                          "operands, everything else fp32 (features within 2e-3 of the fp32 reference); "

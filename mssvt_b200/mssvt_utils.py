@@ -61,8 +61,10 @@ class SparseTensor(object):
         self._features = self._indices = None
         # the count is produced on the stream that is current now; whoever materialises later (maybe
         # under another current stream) must wait for it
-        self._ready = torch.cuda.Event()
-        self._ready.record()
+        self._ready = None
+        if not torch.cuda.is_current_stream_capturing():   # (a captured forward is re-armed by GraphedForward)
+            self._ready = torch.cuda.Event()
+            self._ready.record()
         self._count_host = None
 
     def prefetch_row_count(self):
@@ -83,7 +85,8 @@ class SparseTensor(object):
     def _materialise(self):
         if self._lazy is not None:
             f, i, count = self._lazy
-            self._ready.synchronize()
+            if self._ready is not None:
+                self._ready.synchronize()
             if self._count_host is not None:
                 n, n_dropped = int(self._count_host[0]), int(self._count_host[1])
             else:

@@ -330,3 +330,28 @@ def test_tiny_frames_in_both_modes(n):
         assert torch.equal(sp.indices.cpu(), want.indices)
         err = (sp.features.cpu() - want.features).abs().max().item()
         assert err <= tol * want.features.abs().max().item(), (precision, err)
+
+
+def test_cuda_graph_replay_matches_eager_forward():
+    """MixedScaleSparseTransformer.capture: the graph, replayed on new contents of its static input buffers,
+    gives exactly the eager results (both precision modes use the same kernels either way)"""
+    cfg = s0_model_cfg()
+    cfg["PRECISION"] = "tf32"
+    torch.manual_seed(0)
+    model = MixedScaleSparseTransformer(cfg, 64, list(S0_GRID), list(S0_VOXEL), list(S0_RANGE)).cuda().eval()
+    frames = [synth_frame(20 + i, 6000, crop=0.2) for i in range(3)]
+    f0 = torch.from_numpy(frames[0][0]).cuda()
+    c0 = torch.from_numpy(frames[0][1]).cuda()
+    graphed = model.capture({"voxel_features": f0, "voxel_coords": c0, "batch_size": 1})
+    assert graphed.launches > 20
+    for feats, coords in frames[1:] + frames[:1]:
+        f, c = torch.from_numpy(feats).cuda(), torch.from_numpy(coords).cuda()
+        with torch.no_grad():
+            want = model({"voxel_features": f, "voxel_coords": c, "batch_size": 1})["encoded_spconv_tensor"]
+            want_f, want_i = want.features.clone(), want.indices.clone()
+        f0.copy_(f)
+        c0.copy_(c)
+        got = graphed.replay()
+        assert torch.equal(got.indices, want_i) and torch.equal(got.features, want_f)
+        dense = got.dense()
+        assert dense.shape == (1, 64, 1, 468, 468) and torch.isfinite(dense).all()
