@@ -245,17 +245,27 @@ int mssvt_compress_attention(const void *shape, int shape_bytes, const float *pa
                              const float *xn, const float *xyz, const int *k_row, float *out,
                              void *stream);
 
+/* Tile plan of mssvt_compress_attention_tc: #real slots per window, tiles of <= 128 key tasks, window
+ * centres.  A function of the window rows (coordinates) only, so it can run ahead of / concurrently with the
+ * feature kernels.  Outputs (opaque, caller-allocated): tiles (win_capacity, 2) int, tile_count (1) int,
+ * win_rec (win_capacity) int, win_ctr (win_capacity, 4) float. */
+int mssvt_compress_tiles(int n1, int win_capacity, const int *win_count_total, const int *win_list,
+                         const int *k_row, const float *win_cell, const float *range_min, int *tiles,
+                         int *tile_count, int *win_rec, float *win_ctr, void *stream);
+
 /* The same step, task-parallel with the second positional-embedding layer and the K/V projection on
- * the tcgen05 tensor cores (mssvt_b200/csrc/compress_tc.cu: 3 kernels).  Weights in nn.Module layout:
- * pos_w [64][6]; packed by mssvt_pack_operand_tf32: wq / wp / pos2_w [64][64], wkv [128][64].  scratch: 4 * win_capacity * 64 floats.
+ * the tcgen05 tensor cores (mssvt_b200/csrc/compress_tc.cu).  Weights: pos_w [64][6] (nn.Module layout);
+ * packed by mssvt_pack_operand_tf32: wq / wp / pos2_w [64][64], wkv [128][64].  tiles .. win_ctr:
+ * mssvt_compress_tiles.  scratch: 3 * win_capacity * 64 floats.
  * Supported: C = 64, one head group with 2, 4 or 8 heads, two-layer pos_proj, n1 <= 127; -1 otherwise. */
 int mssvt_compress_attention_tc(int C, int heads, int n1, float scale, const float *win_cell,
                                 const float *range_min, const float *pos_w, const float *pos_b,
                                 const float *pos2_w, const float *pos2_b, const float *wq, const float *bq,
                                 const float *wkv, const float *bkv, const float *wp, const float *bp,
                                 int win_capacity, const int *win_count_total, const int *win_list,
-                                const float *xn, const float *xyz, const int *k_row, float *scratch, float *out,
-                                void *stream);
+                                const float *xn, const float *xyz, const int *k_row, const int *tiles,
+                                const int *tile_count, const int *win_rec, const float *win_ctr, float *scratch,
+                                float *out, void *stream);
 
 /* residual + norm2 + linear1 / ReLU / linear2 + residual (+ out_linear)
  * (mssvt_backbone.py:337-343, 384-387).  `shape` is the FfnShape descriptor. */

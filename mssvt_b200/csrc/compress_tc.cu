@@ -369,43 +369,59 @@ using namespace mssvt;
 
 extern "C" {
 
+/* Tile plan of mssvt_compress_attention_tc: #real slots per window, tiles of <= 128 key tasks, window
+ * centres.  A function of the window rows only (coordinates), so it can be made ahead of / concurrently
+ * with the feature kernels.  tiles (win_capacity, 2) int, tile_count (1) int, win_rec (win_capacity) int,
+ * win_ctr (win_capacity, 4) float: opaque, caller-allocated. */
+int mssvt_compress_tiles(int n1, int win_capacity, const int *win_count_total, const int *win_list,
+                         const int *k_row, const float *win_cell, const float *range_min, int *tiles,
+                         int *tile_count, int *win_rec, float *win_ctr, void *stream) {
+    if (n1 <= 0 || n1 > 127 || win_capacity < 0) return MSSVT_ERR_INVALID;
+    if (!win_count_total || !win_list || !k_row || !win_cell || !range_min || !tiles || !tile_count || !win_rec ||
+        !win_ctr)
+        return MSSVT_ERR_INVALID;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (cudaMemsetAsync(tile_count, 0, sizeof(int), s) != cudaSuccess) return MSSVT_ERR_LAUNCH;
+    if (win_capacity == 0) return MSSVT_OK;
+    const int plan_warps = (win_capacity + TCC_PLAN_WB - 1) / TCC_PLAN_WB;
+    ++g_launches;
+    k_tcc_plan<<<(plan_warps + 7) / 8, 256, 0, s>>>(n1, win_capacity, win_count_total, (const int4 *)win_list, k_row,
+                                                    make_float3(win_cell[0], win_cell[1], win_cell[2]),
+                                                    make_float3(range_min[0], range_min[1], range_min[2]),
+                                                    (int2 *)tiles, tile_count, win_rec, (float4 *)win_ctr);
+    return check_launch();
+}
+
 /* Tensor-core attention of a one-window (compress) block (see the header of this file).  Weights in
  * nn.Module layout: pos_w [64][6]; packed by mssvt_pack_operand_tf32: wq / wp / pos2_w [64][64] and
- * wkv [128][64].  k_row: (cap, n1)
- * global rows from mssvt_window_rows.  scratch: 4 * win_capacity * 64 floats.  out: (cap, 64).
+ * wkv [128][64].  k_row: (cap, n1) global rows from mssvt_window_rows; tiles .. win_ctr: mssvt_compress_tiles.
+ * scratch: 3 * win_capacity * 64 floats.  out: (cap, 64).
  * Supported: C = 64, one head group with 2, 4 or 8 heads, n1 <= 127; -1 otherwise. */
 int mssvt_compress_attention_tc(int C, int heads, int n1, float scale, const float *win_cell,
                                 const float *range_min, const float *pos_w, const float *pos_b,
                                 const float *pos2_w, const float *pos2_b, const float *wq, const float *bq,
                                 const float *wkv, const float *bkv, const float *wp, const float *bp,
                                 int win_capacity, const int *win_count_total, const int *win_list,
-                                const float *xn, const float *xyz, const int *k_row, float *scratch, float *out,
-                                void *stream) {
+                                const float *xn, const float *xyz, const int *k_row, const int *tiles_in,
+                                const int *tile_count, const int *win_rec, const float *win_ctr_in, float *scratch,
+                                float *out, void *stream) {
     if (C != 64 || (heads != 2 && heads != 4 && heads != 8) || n1 <= 0 || n1 > 127 || win_capacity < 0)
         return MSSVT_ERR_INVALID;
     if (win_capacity == 0) return MSSVT_OK;
     if (!win_cell || !range_min || !pos_w || !pos_b || !pos2_w || !pos2_b || !wq || !bq || !wkv || !bkv || !wp || !bp ||
-        !win_count_total || !win_list || !xn || !xyz || !k_row || !scratch || !out)
+        !win_count_total || !win_list || !xn || !xyz || !k_row || !tiles_in || !tile_count || !win_rec || !win_ctr_in ||
+        !scratch || !out)
         return MSSVT_ERR_INVALID;
     TccParams P;
     P.n1 = n1; P.heads = heads; P.scale = scale;
     for (int i = 0; i < 3; ++i) { P.win_cell[i] = win_cell[i]; P.lo[i] = range_min[i]; }
     P.pos_w = pos_w; P.pos_b = pos_b; P.pos2_w = pos2_w; P.pos2_b = pos2_b;
     P.wq = wq; P.bq = bq; P.wkv = wkv; P.bkv = bkv; P.wp = wp; P.bp = bp;
-    // scratch: Qc | Oc | pooled | plan (tile_count, tiles, win_rec, win_ctr)
+    // scratch: Qc | Oc | pooled
     float *Qc = scratch, *Oc = scratch + (size_t)win_capacity * 64, *pooled = scratch + 2 * (size_t)win_capacity * 64;
-    float4 *win_ctr = (float4 *)(scratch + 3 * (size_t)win_capacity * 64);
-    int2 *tiles = (int2 *)(win_ctr + win_capacity);
-    int *win_rec = (int *)(tiles + win_capacity);
-    int *tile_count = win_rec + win_capacity;
+    const float4 *win_ctr = (const float4 *)win_ctr_in;
+    const int2 *tiles = (const int2 *)tiles_in;
     cudaStream_t s = (cudaStream_t)stream;
-    if (cudaMemsetAsync(tile_count, 0, sizeof(int), s) != cudaSuccess) return MSSVT_ERR_LAUNCH;
-    const int plan_warps = (win_capacity + TCC_PLAN_WB - 1) / TCC_PLAN_WB;
-    ++g_launches;
-    k_tcc_plan<<<(plan_warps + 7) / 8, 256, 0, s>>>(n1, win_capacity, win_count_total, (const int4 *)win_list, k_row,
-                                                    make_float3(win_cell[0], win_cell[1], win_cell[2]),
-                                                    make_float3(range_min[0], range_min[1], range_min[2]), tiles,
-                                                    tile_count, win_rec, win_ctr);
     ++g_launches;
     launch_pdl(k_tcc_pool, dim3(MSSVT_NUM_SMS * 8), dim3(256), 0, s, n1, win_capacity, win_count_total, (const int *)win_rec,
                k_row, xn, pooled);
@@ -422,8 +438,8 @@ int mssvt_compress_attention_tc(int C, int heads, int n1, float scale, const flo
     ++g_launches;
 #define TCC_LAUNCH(H)                                                                                     \
     cudaFuncSetAttribute(k_tcc_keys<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
-    launch_pdl(k_tcc_keys<H>, dim3(grid), dim3(TCC_THREADS), smem, s, P, (const int2 *)tiles, (const int *)tile_count,   \
-               (const int *)win_rec, (const float4 *)win_ctr, xn, xyz, k_row, (const float *)Qc, Oc)
+    launch_pdl(k_tcc_keys<H>, dim3(grid), dim3(TCC_THREADS), smem, s, P, tiles, tile_count, win_rec, win_ctr, xn, xyz,   \
+               k_row, (const float *)Qc, Oc)
     if (heads == 2) { TCC_LAUNCH(2); }
     else if (heads == 4) { TCC_LAUNCH(4); }
     else { TCC_LAUNCH(8); }

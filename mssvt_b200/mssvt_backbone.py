@@ -420,7 +420,11 @@ class MixedScaleSparseTransformerBlock(nn.Module):
     def _layernorm1(self, x, sp_tensor=None):
         pre = getattr(sp_tensor, "_xn_ready", None) if sp_tensor is not None else None
         if pre is not None and pre[0] is x and pre[2] is self.norm1:
-            return pre[1]  # the previous block's FFN epilogue already applied this norm1
+            ev = getattr(sp_tensor, "_xn_event", None)
+            if ev is not None:                   # computed on the side stream (first block)
+                torch.cuda.current_stream().wait_event(ev)
+                sp_tensor._xn_event = None
+            return pre[1]  # the previous block's FFN epilogue (or the side stream) already applied this norm1
         xn = torch.empty_like(x)
         call("mssvt_layernorm", x.shape[0], None, x.shape[1], ptr(x), ptr(self.norm1.weight),
              ptr(self.norm1.bias), self.norm1.eps, ptr(xn), stream())
@@ -528,12 +532,20 @@ class MixedScaleSparseTransformerCompressBlock(MixedScaleSparseTransformerBlock)
         sp_tensor.map_table = win_table
         return sp_tensor
 
-    def forward(self, sp_tensor, block_idx=None, recycle_dict=None):
-        x = sp_tensor.features
-        differentiable = self._differentiable(x)
-        if x.dtype != torch.float32 or not x.is_contiguous():
-            x = x.float().contiguous()
-        dev, B = x.device, sp_tensor.batch_size
+    def _tc_supported(self):
+        a = self.ms_attn
+        return (self.precision == "tf32" and self.in_channels == 64 and a.num_head_groups == 1
+                and a.num_heads[0] in (2, 4, 8) and len(self.pos_proj) == 4 and self.max_num_win1 <= 127)
+
+    def prepare(self, sp_tensor):
+        """Coordinate-only part of the block: pillar window list, window rows, tile plan.  Cached on the
+        tensor per coordinate set, so it can be issued early (on a side stream, see
+        MixedScaleSparseTransformer.forward) and is picked up by forward()."""
+        cache = sp_tensor._cache()
+        key = ("rows", tuple(self.win1_size), self.max_num_win1, self.max_num_wins, self._tc_supported())
+        if key in cache:
+            return cache[key]
+        dev, B = sp_tensor.indices.device, sp_tensor.batch_size
         grid, win_list, win_table, win_count = self._windows(sp_tensor)
         cap, n1 = win_list.shape[0], self.max_num_win1
         t = self._tables(dev)
@@ -545,16 +557,40 @@ class MixedScaleSparseTransformerCompressBlock(MixedScaleSparseTransformerBlock)
         call("mssvt_window_rows", sx, sy, sz, *self.win1_size, t['win1'].shape[0],
              n1, ptr(t['win1']), cap, ptr(total), ptr(win_list), ptr(cells), ptr(vals), ptr(v_start),
              ptr(k_row), stream())
+        plan = None
+        if self._tc_supported():
+            i32 = dict(dtype=torch.int32, device=dev)
+            plan = (torch.empty((cap, 2), **i32), torch.empty(1, **i32), torch.empty(cap, **i32),
+                    torch.empty((cap, 4), dtype=torch.float32, device=dev))
+            vs = sp_tensor.voxel_size
+            call("mssvt_compress_tiles", n1, cap, ptr(total), ptr(win_list), ptr(k_row),
+                 host_floats([vs[i] * self.win1_size[i] for i in range(3)]),
+                 host_floats(sp_tensor.point_cloud_range[0:3]), *(ptr(v) for v in plan), stream())
+        cache[key] = (grid, win_list, win_table, win_count, k_row, plan)
+        return cache[key]
+
+    def forward(self, sp_tensor, block_idx=None, recycle_dict=None):
+        x = sp_tensor.features
+        differentiable = self._differentiable(x)
+        if x.dtype != torch.float32 or not x.is_contiguous():
+            x = x.float().contiguous()
+        dev, B = x.device, sp_tensor.batch_size
+        grid, win_list, win_table, win_count, k_row, plan = self.prepare(sp_tensor)
+        cap, n1 = win_list.shape[0], self.max_num_win1
+        total = win_count[B:B + 1]
+        join = getattr(sp_tensor, "_prepare_event", None)
+        if join is not None:                     # prepared on a side stream: everything below needs it
+            torch.cuda.current_stream().wait_event(join)
+            sp_tensor._prepare_event = None
         if differentiable:
             return self._forward_autograd_compress(sp_tensor, x, k_row, grid, win_list, win_table, win_count)
         xn = self._layernorm1(x, sp_tensor)
         attn = torch.empty((cap, self.in_channels), dtype=torch.float32, device=dev)
         a = self.ms_attn
-        if (self.precision == "tf32" and self.in_channels == 64 and a.num_head_groups == 1
-                and a.num_heads[0] in (2, 4, 8) and len(self.pos_proj) == 4 and n1 <= 127):
+        if plan is not None:
             # task-parallel kernels; second pos_proj layer and K/V projection on the tcgen05 tensor cores
             vs = sp_tensor.voxel_size
-            scratch = torch.empty((4 * cap, 64), dtype=torch.float32, device=dev)
+            scratch = torch.empty((3 * cap, 64), dtype=torch.float32, device=dev)
             call("mssvt_compress_attention_tc", 64, a.num_heads[0], n1, a.scale,
                  host_floats([vs[i] * self.win1_size[i] for i in range(3)]),
                  host_floats(sp_tensor.point_cloud_range[0:3]), ptr(self.pos_proj[0].weight),
@@ -562,7 +598,7 @@ class MixedScaleSparseTransformerCompressBlock(MixedScaleSparseTransformerBlock)
                  ptr(self._packed(a.to_qs[0].weight)), ptr(a.to_qs[0].bias), ptr(self._packed(a.to_kvs[0].weight)),
                  ptr(a.to_kvs[0].bias),
                  ptr(self._packed(a.projs[0].weight)), ptr(a.projs[0].bias), cap, ptr(total), ptr(win_list), ptr(xn),
-                 ptr(sp_tensor.world_coords()), ptr(k_row), ptr(scratch), ptr(attn), stream())
+                 ptr(sp_tensor.world_coords()), ptr(k_row), *(ptr(v) for v in plan), ptr(scratch), ptr(attn), stream())
         else:
             S, buf = self._attn_descriptor(sp_tensor, 1, n1, n1)
             call("mssvt_compress_attention", ctypes.byref(S), ctypes.sizeof(S), ptr(buf), cap, ptr(total),
@@ -643,10 +679,40 @@ class MixedScaleSparseTransformer(nn.Module):
             features=voxel_features, indices=indices.contiguous(), spatial_shape=list(self.grid_size),
             voxel_size=list(self.voxel_size), point_cloud_range=list(self.point_cloud_range),
             batch_size=batch_size, hash_size=self.hash_size, map_table=None, gather_dict=None)
+        self._fork_side_work(sp_tensor)
         for i, attention_block in enumerate(self.backbone):
             sp_tensor = attention_block(sp_tensor, block_idx=i)
         batch_dict.update({'encoded_spconv_tensor': sp_tensor, 'encoded_spconv_tensor_stride': 1})
         return batch_dict
+
+    def _fork_side_work(self, sp_tensor):
+        """Inference only: work that does not sit on the critical path of the first blocks runs on a side
+        stream (a parallel branch when the forward is captured into a CUDA graph): the first block's
+        LayerNorm (features only) next to the coordinate-only geometry, and the compress block's window
+        list / window rows / tile plan next to the attention blocks."""
+        first = self.backbone[0]
+        x = sp_tensor.features
+        if first._differentiable(x) or x.dtype != torch.float32 or not x.is_contiguous() or len(self.backbone) < 2:
+            return
+        last = self.backbone[-1]
+        main = torch.cuda.current_stream()
+        side = self.__dict__.get("_side_stream")
+        if side is None or side.device != x.device:
+            side = self.__dict__["_side_stream"] = torch.cuda.Stream(device=x.device)
+        # shared by both branches: made on the main stream before the fork
+        sp_tensor.sample_counts(), sp_tensor.grid_index(), sp_tensor.world_coords()
+        fork = torch.cuda.Event()
+        fork.record(main)
+        with torch.cuda.stream(side):
+            side.wait_event(fork)
+            xn = first._layernorm1(x)
+            sp_tensor._xn_ready, sp_tensor._xn_event = (x, xn, first.norm1), torch.cuda.Event()
+            sp_tensor._xn_event.record(side)
+            if isinstance(last, MixedScaleSparseTransformerCompressBlock) and \
+                    all(not isinstance(b, MixedScaleSparseTransformerCompressBlock) for b in self.backbone[:-1]):
+                last.prepare(sp_tensor)               # (the blocks before it keep the voxel coordinates)
+                sp_tensor._prepare_event = torch.cuda.Event()
+                sp_tensor._prepare_event.record(side)
 
 
 class GraphedForward:
