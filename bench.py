@@ -162,16 +162,47 @@ def our_arm(args):
         f, c = dev[i % POOL]
         return model({"voxel_features": f, "voxel_coords": c, "batch_size": 1})["encoded_spconv_tensor"]
 
-    # --launch graph (default): the forward of every resident frame is captured once into a CUDA graph bound
-    # to that frame's buffers; a step is one cudaGraphLaunch replaying all of its kernels (geometry included)
+    # --launch graph (default): the forward of every resident frame is captured once into a CUDA graph bound to
+    # that frame's buffers; a step is one cudaGraphLaunch replaying all kernels of the frame, geometry included.
+    # --launch pipelined: two graphs per frame, the coordinate-only part (voxel index, window lists, chessboard /
+    # FPS geometry, tile plans) and the feature kernels; the coordinate graph of frame i + 1 runs on a second
+    # stream while frame i is in its feature graph (frame-level software pipelining; every step still executes
+    # one coordinate pass and one feature pass inside the timed region).  Measured: no gain over "graph" --
+    # the feature kernels already fill the register files, the two passes only share the SMs.
     graphs = None
-    if args.launch == "graph":
+    if args.launch != "eager":
         with torch.no_grad():
-            graphs = [model.capture({"voxel_features": dev[i][0], "voxel_coords": dev_idx[i], "batch_size": 1})
-                      for i in range(POOL)]
+            graphs = [model.capture({"voxel_features": dev[i][0], "voxel_coords": dev_idx[i], "batch_size": 1},
+                                    split=args.launch == "pipelined") for i in range(POOL)]
+    s_prep = torch.cuda.Stream()
+    ev_prep, ev_feat = [None] * POOL, [None] * POOL
 
-    def step(i):
-        return graphs[i % POOL].replay() if graphs is not None else eager_step(i)
+    def serial_steps(first, count):
+        for i in range(first, first + count):
+            out = graphs[i % POOL].replay() if graphs is not None else eager_step(i)
+        return out
+
+    def prepare_ahead(i):
+        k = i % POOL
+        with torch.cuda.stream(s_prep):
+            if ev_feat[k] is not None:
+                s_prep.wait_event(ev_feat[k])         # the frame's buffers are free again
+            graphs[k].replay_prepare()
+            ev_prep[k] = torch.cuda.Event()
+            ev_prep[k].record(s_prep)
+
+    def pipelined_steps(first, count):
+        """steps first .. first + count - 1; the coordinate pass of step `first` must already be queued"""
+        main = torch.cuda.current_stream()
+        for i in range(first, first + count):
+            prepare_ahead(i + 1)
+            k = i % POOL
+            main.wait_event(ev_prep[k])
+            out = graphs[k].replay_features()
+            ev_feat[k] = torch.cuda.Event()
+            ev_feat[k].record(main)
+        main.wait_event(ev_prep[(first + count) % POOL])   # the count-th coordinate pass belongs to the region
+        return out
 
     def barrier():
         if world > 1:
@@ -179,37 +210,42 @@ def our_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def timed(run, first, count):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        run(first, count)
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1)
+
     with torch.no_grad():
-        for i in range(args.warmup):
-            out = step(i)
+        pipelined = args.launch == "pipelined"
+        if pipelined:
+            prepare_ahead(0)
+            out = pipelined_steps(0, args.warmup)
+        else:
+            out = serial_steps(0, args.warmup)
         pillars = out.features.shape[0]
         # ---- timed region: exactly K steps, device time, inputs resident in HBM
         sampler = ClockSampler(local)
         sampler.start()
         launches0 = _lib.call("mssvt_launch_count")
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        e0.record()
-        for i in range(args.steps):
-            step(args.warmup + i)
-        e1.record()
-        barrier()
-        ms = e0.elapsed_time(e1)
+        ms = timed(pipelined_steps if pipelined else serial_steps, args.warmup, args.steps)
         launches = _lib.call("mssvt_launch_count") - launches0
         if graphs is not None:
             launches = sum(graphs[(args.warmup + i) % POOL].launches for i in range(args.steps))
         clocks = sampler.stop()
-        # the same K steps launched kernel by kernel from Python, for the record
-        x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        # for the record: the same K steps (a) as one graph replay per forward on one stream
+        serial_ms = timed(serial_steps, args.warmup, args.steps) / args.steps if graphs is not None else None
+        # (b) launched kernel by kernel from Python
         for i in range(3):
             eager_step(i)
-        barrier()
-        x0.record()
-        for i in range(args.steps):
-            eager_step(args.warmup + i)
-        x1.record()
-        barrier()
-        eager_ms = x0.elapsed_time(x1) / args.steps
+        def eager_steps(first, count):
+            for i in range(first, first + count):
+                eager_step(i)
+
+        eager_ms = timed(eager_steps, args.warmup, args.steps) / args.steps
 
         # ---- e2e: module API from pinned HOST buffers; every step copies its inputs host -> device and
         #      its result (features + indices of the output tensor) device -> host.  Three streams:
@@ -226,7 +262,8 @@ def our_arm(args):
             for r in range(3):
                 fb, cb = dev[r][0].clone(), dev_idx[r].clone()
                 slots.append({"f": fb, "c": cb, "done": None, "drained": None,
-                              "g": model.capture({"voxel_features": fb, "voxel_coords": cb, "batch_size": 1})})
+                              "g": model.capture({"voxel_features": fb, "voxel_coords": cb, "batch_size": 1},
+                                                 split=pipelined)})
 
         def e2e_run(steps, stamps=None):
             staged, keep, rows = {}, [], 0
@@ -249,6 +286,12 @@ def our_arm(args):
                         cd = c.to(device, non_blocking=True)
                     ev = torch.cuda.Event()
                     ev.record(s_in)
+                if slots and pipelined:          # the frame's coordinate pass follows its H2D copy at once
+                    with torch.cuda.stream(s_prep):
+                        s_prep.wait_event(ev)
+                        slots[i % 3]["g"].replay_prepare()
+                        ev = torch.cuda.Event()
+                        ev.record(s_prep)
                 staged[i] = (fd, cd, ev)
 
             def drain(i, sp, done):
@@ -277,7 +320,7 @@ def our_arm(args):
                         g0 = torch.cuda.Event(enable_timing=True)
                         g0.record(s_comp)
                     if slots:
-                        sp = slots[i % 3]["g"].replay()
+                        sp = slots[i % 3]["g"].replay_features() if pipelined else slots[i % 3]["g"].replay()
                     else:
                         sp = model({"voxel_features": fd, "voxel_coords": cd, "batch_size": 1})["encoded_spconv_tensor"]
                     sp.prefetch_row_count()
@@ -382,9 +425,14 @@ def our_arm(args):
                                "step, C=64, hash 400000, batch 1; random-init weights (seed 0)",
                    "voxels_per_frame": N_VOXELS, "frames_per_step": world, "sharding": "by frame, no collective",
                    "l2": "inputs rotate through a pool of %d distinct frames (326 MB > 126 MB L2)" % POOL,
-                   "launch": ("one CUDA graph replay per forward (captured once per resident frame; every replay runs "
-                              "all kernels of the frame, geometry included)" if args.launch == "graph"
-                              else "eager: kernel by kernel from Python"),
+                   "launch": {"pipelined": "CUDA graphs captured once per resident frame; frame-level software pipelining: "
+                                           "the coordinate-only graph (voxel index, windows, chessboard/FPS geometry, tile "
+                                           "plans) of frame i+1 runs on a second stream while frame i is in its feature "
+                                           "graph; every step executes one coordinate pass and one feature pass",
+                              "graph": "one CUDA graph replay per forward (captured once per resident frame; every replay "
+                                       "runs all kernels of the frame, geometry included)",
+                              "eager": "kernel by kernel from Python"}[args.launch],
+                   "serial_graph_ms_per_step": None if serial_ms is None else round(serial_ms, 4),
                    "eager_ms_per_step": round(eager_ms, 4),
                    "precision": ("fp32 FFMA kernels (features within 1e-4 of max|fp32 reference|)" if args.precision == "fp32"
                                  else "projections and FFN GEMMs on tcgen05 with TF32 operands / fp32 accumulate, rest fp32 "
@@ -501,8 +549,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--launch", default="graph", choices=["graph", "eager"],
-                    help="graph (default): every forward is one CUDA-graph replay; eager: kernel by kernel from Python")
+    ap.add_argument("--launch", default="graph", choices=["graph", "pipelined", "eager"],
+                    help="graph (default): one CUDA-graph replay per forward; pipelined: coordinate-only graph of frame "
+                         "i + 1 overlapped with the feature graph of frame i; eager: kernel by kernel from Python")
     ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32"],
                     help="tf32 (default): K/V projection and FFN GEMMs on the tcgen05 tensor cores with TF32 "
                          "operands, everything else fp32 (features within 2e-3 of the fp32 reference); "

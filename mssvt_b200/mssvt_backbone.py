@@ -334,6 +334,22 @@ class MixedScaleSparseTransformerBlock(nn.Module):
         cache[key] = g
         return g
 
+    def _tc_supported(self, nq):
+        """shape family of the tensor-core window attention (mssvt_block_attention_tc)"""
+        a = self.ms_attn
+        return (self.precision == "tf32" and self.in_channels == 64 and a.scale_dims == [32, 32]
+                and a.num_heads[0] == a.num_heads[1] and a.num_heads[0] in (1, 2, 4) and nq <= 32
+                and self.key_num_sample <= 63 and self.max_num_win1 <= 128 and len(self.pos_proj) == 2
+                and nq * (self.key_num_sample + 1) * a.num_heads[0] <= 2048)
+
+    def prepare(self, sp_tensor):
+        """Coordinate-only part of the block (window list, chessboard / FPS geometry, tile plan); cached on
+        the tensor per coordinate set and picked up by forward()."""
+        g = self.geometry(sp_tensor)
+        if self._tc_supported(g["nq"]):
+            self._tile_plan(sp_tensor, g, self.ms_attn.num_heads[0])
+        return g
+
     def _tile_plan(self, sp_tensor, g, heads):
         """tile plan of the tensor-core attention: depends on the geometry only, cached with it"""
         key = ("tiles", heads)
@@ -464,10 +480,7 @@ class MixedScaleSparseTransformerBlock(nn.Module):
         xn = self._layernorm1(x, sp_tensor)
         merged = torch.empty_like(x)  # only rows flagged in g["covered"] are written and read
         a = self.ms_attn
-        if (self.precision == "tf32" and self.in_channels == 64 and a.scale_dims == [32, 32]
-                and a.num_heads[0] == a.num_heads[1] and a.num_heads[0] in (1, 2, 4) and g["nq"] <= 32
-                and self.key_num_sample <= 63 and self.max_num_win1 <= 128 and len(self.pos_proj) == 2
-                and g["nq"] * (self.key_num_sample + 1) * a.num_heads[0] <= 2048):
+        if self._tc_supported(g["nq"]):
             # task-parallel kernel, K/V projection on the tcgen05 tensor cores (TF32 operands)
             vs = sp_tensor.voxel_size
             plan = self._tile_plan(sp_tensor, g, a.num_heads[0])
@@ -664,10 +677,30 @@ class MixedScaleSparseTransformer(nn.Module):
             block.precision = precision
         return self
 
-    def capture(self, batch_dict, warmup=2):
-        """CUDA-graph capture of the inference forward for frames of this size; see GraphedForward."""
+    def capture(self, batch_dict, warmup=2, split=False):
+        """CUDA-graph capture of the inference forward for frames of this size; see GraphedForward.
+        split=True captures the coordinate-only part and the feature part as two graphs, so that a
+        pipelined caller can run the first one for frame i + 1 while frame i is in the second."""
         return GraphedForward(self, batch_dict['voxel_features'], batch_dict['voxel_coords'],
-                              batch_dict['batch_size'], warmup)
+                              batch_dict['batch_size'], warmup, split)
+
+    def _sparse_tensor(self, voxel_features, indices, batch_size):
+        return SparseTensor(
+            features=voxel_features, indices=indices, spatial_shape=list(self.grid_size),
+            voxel_size=list(self.voxel_size), point_cloud_range=list(self.point_cloud_range),
+            batch_size=batch_size, hash_size=self.hash_size, map_table=None, gather_dict=None)
+
+    def prepare(self, sp_tensor):
+        """Everything of the forward that depends on the voxel coordinates only -- voxel index, window lists,
+        chessboard / FPS geometry, tile plans, pillar rows: about a quarter of the frame time.  Results are
+        cached on the tensor (per coordinate set); forward() on a tensor with the same coordinate buffer
+        reuses them and launches the feature kernels only."""
+        sp_tensor.sample_counts(), sp_tensor.grid_index(), sp_tensor.world_coords()
+        for block in self.backbone:
+            block.prepare(sp_tensor)
+            if isinstance(block, MixedScaleSparseTransformerCompressBlock):
+                break                                 # (coordinates change here: nothing further to prepare)
+        return sp_tensor._derived
 
     def forward(self, batch_dict):
         voxel_features, voxel_coords = batch_dict['voxel_features'], batch_dict['voxel_coords']
@@ -675,11 +708,12 @@ class MixedScaleSparseTransformer(nn.Module):
         if not voxel_features.is_cuda:
             raise RuntimeError("MixedScaleSparseTransformer runs on CUDA tensors only; there is no CPU path")
         indices = voxel_coords if voxel_coords.dtype == torch.int32 else voxel_coords.int()
-        sp_tensor = SparseTensor(
-            features=voxel_features, indices=indices.contiguous(), spatial_shape=list(self.grid_size),
-            voxel_size=list(self.voxel_size), point_cloud_range=list(self.point_cloud_range),
-            batch_size=batch_size, hash_size=self.hash_size, map_table=None, gather_dict=None)
-        self._fork_side_work(sp_tensor)
+        sp_tensor = self._sparse_tensor(voxel_features, indices.contiguous(), batch_size)
+        prepared = batch_dict.get('mssvt_prepared')   # optional: result of prepare() for these coordinates
+        if prepared is not None:
+            sp_tensor._derived = prepared
+        else:
+            self._fork_side_work(sp_tensor)
         for i, attention_block in enumerate(self.backbone):
             sp_tensor = attention_block(sp_tensor, block_idx=i)
         batch_dict.update({'encoded_spconv_tensor': sp_tensor, 'encoded_spconv_tensor_stride': 1})
@@ -728,7 +762,7 @@ class GraphedForward:
     own capture or the eager forward.  Outputs live in graph-owned buffers that the next replay overwrites.
     """
 
-    def __init__(self, model, voxel_features, voxel_coords, batch_size, warmup=2):
+    def __init__(self, model, voxel_features, voxel_coords, batch_size, warmup=2, split=False):
         if model.training or voxel_features.requires_grad:
             raise RuntimeError("GraphedForward captures the inference forward (model.eval(), no gradients)")
         if voxel_coords.dtype != torch.int32 or not voxel_coords.is_contiguous():
@@ -745,18 +779,45 @@ class GraphedForward:
                     run()
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
-            self.graph = torch.cuda.CUDAGraph()
             before = call("mssvt_launch_count")
-            with torch.cuda.graph(self.graph):
-                sp = run()
+            self.prepare_graph = None
+            if split:
+                # graph 1: coordinate-only work, results (graph-owned buffers) kept in `derived`;
+                # graph 2: the feature kernels, reading them
+                self.prepare_graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.prepare_graph):
+                    derived = model.prepare(model._sparse_tensor(None, voxel_coords, batch_size))
+                self._derived = derived
+                self.graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph, pool=self.prepare_graph.pool()):
+                    sp = model({"voxel_features": voxel_features, "voxel_coords": voxel_coords,
+                                "batch_size": batch_size, "mssvt_prepared": derived})["encoded_spconv_tensor"]
+            else:
+                self.graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph):
+                    sp = run()
             self.launches = int(call("mssvt_launch_count") - before)   # kernels per replay
         self._template = sp                     # keeps the graph-owned output / geometry buffers alive
         self._lazy = sp._lazy
         self._overflow = getattr(sp, "_window_overflow", None)
 
+    def replay_prepare(self):
+        """split capture only: the coordinate-only graph (may run a frame ahead, on another stream, as long
+        as the previous replay_features() of THIS object has finished with the buffers)"""
+        self.prepare_graph.replay()
+
+    def replay_features(self):
+        """split capture only: the feature graph; needs the replay_prepare() of the same frame"""
+        return self._replay_main()
+
     def replay(self):
         """Launch the captured forward on the current stream; returns the output tensor (lazy rows: no
         host sync until .features / .indices are read; .dense() never syncs)."""
+        if self.prepare_graph is not None:
+            self.prepare_graph.replay()
+        return self._replay_main()
+
+    def _replay_main(self):
         self.graph.replay()
         t = self._template
         sp = SparseTensor(features=None, indices=None, spatial_shape=t.spatial_shape, voxel_size=t.voxel_size,

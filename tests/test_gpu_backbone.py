@@ -332,9 +332,10 @@ def test_tiny_frames_in_both_modes(n):
         assert err <= tol * want.features.abs().max().item(), (precision, err)
 
 
-def test_cuda_graph_replay_matches_eager_forward():
-    """MixedScaleSparseTransformer.capture: the graph, replayed on new contents of its static input buffers,
-    gives exactly the eager results (both precision modes use the same kernels either way)"""
+@pytest.mark.parametrize("split", [False, True])
+def test_cuda_graph_replay_matches_eager_forward(split):
+    """MixedScaleSparseTransformer.capture: the graph (or the coordinate graph + feature graph pair), replayed
+    on new contents of its static input buffers, gives exactly the eager results"""
     cfg = s0_model_cfg()
     cfg["PRECISION"] = "tf32"
     torch.manual_seed(0)
@@ -342,8 +343,8 @@ def test_cuda_graph_replay_matches_eager_forward():
     frames = [synth_frame(20 + i, 6000, crop=0.2) for i in range(3)]
     f0 = torch.from_numpy(frames[0][0]).cuda()
     c0 = torch.from_numpy(frames[0][1]).cuda()
-    graphed = model.capture({"voxel_features": f0, "voxel_coords": c0, "batch_size": 1})
-    assert graphed.launches > 20
+    graphed = model.capture({"voxel_features": f0, "voxel_coords": c0, "batch_size": 1}, split=split)
+    assert graphed.launches > 20 and (graphed.prepare_graph is not None) == split
     for feats, coords in frames[1:] + frames[:1]:
         f, c = torch.from_numpy(feats).cuda(), torch.from_numpy(coords).cuda()
         with torch.no_grad():
@@ -351,7 +352,15 @@ def test_cuda_graph_replay_matches_eager_forward():
             want_f, want_i = want.features.clone(), want.indices.clone()
         f0.copy_(f)
         c0.copy_(c)
-        got = graphed.replay()
+        if split:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                graphed.replay_prepare()           # coordinate pass on another stream, then the feature pass
+            torch.cuda.current_stream().wait_stream(side)
+            got = graphed.replay_features()
+        else:
+            got = graphed.replay()
         assert torch.equal(got.indices, want_i) and torch.equal(got.features, want_f)
         dense = got.dense()
         assert dense.shape == (1, 64, 1, 468, 468) and torch.isfinite(dense).all()
