@@ -137,8 +137,37 @@ MEASURED_TRAFFIC = {
 }
 
 
+def bind_to_gpu_numa_node(local):
+    """Pin this rank (and therefore its pinned host buffers: first touch) to the NUMA node its GPU hangs off,
+    so that host <-> device copies of the 8 ranks do not cross the socket interconnect.  Best effort."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(local)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:           # nvml pads the domain to 8 hex digits, sysfs uses 4
+            bus = bus[4:]
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception as e:  # noqa: BLE001
+        print("[bench] NUMA binding skipped: %r" % (e,), file=sys.stderr)
+    return None
+
+
 def our_arm(args):
     rank, world, local = dist_env()
+    numa = bind_to_gpu_numa_node(local)
+    print("[bench] rank %d: GPU %d, NUMA node %s, %d CPUs" % (rank, local, numa, len(os.sched_getaffinity(0))),
+          file=sys.stderr)
     if world > 1:
         import torch.distributed as dist
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
