@@ -1,3 +1,5 @@
+"""Max / RMS error of both precision modes against the CPU oracle on two synthetic frames (test infrastructure:
+imports oracle/).  usage: python tests/precision_probe.py"""
 import sys, torch
 sys.path.insert(0, ".")
 from oracle import backbone as orc
