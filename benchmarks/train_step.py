@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--voxels", type=int, default=150000)
     ap.add_argument("--amp", action="store_true", help="bf16 autocast for the dense math")
+    ap.add_argument("--tf32", action="store_true", help="allow TF32 tensor-core matmuls in torch (default: fp32 SIMT)")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -39,6 +40,7 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
+    torch.backends.cuda.matmul.allow_tf32 = bool(args.tf32)
     torch.manual_seed(0)
     model = MixedScaleSparseTransformer(s0_model_cfg(), 64, list(S0_GRID), list(S0_VOXEL), list(S0_RANGE)).to(dev)
     model.train()
@@ -81,7 +83,7 @@ def main():
         print(json.dumps({"metric": "mssvt_backbone_train_step_ms", "value": ms, "unit": "ms/step", "n_gpus": world,
                           "steps": args.steps, "warmup": args.warmup, "higher_is_better": False,
                           "voxels_per_s": args.voxels * world / (ms * 1e-3), "wall_ms_per_step": wall / args.steps * 1e3,
-                          "dtype": "bf16 autocast" if args.amp else "fp32", "loss": float(loss),
+                          "dtype": "bf16 autocast" if args.amp else "tf32 matmuls" if args.tf32 else "fp32", "loss": float(loss),
                           "config": {"workload": "S0 backbone fwd+bwd+AdamW, one synthetic %d-voxel frame per GPU per "
                                                  "step, loss = mean(dense()^2), DDP all-reduce when world > 1" % args.voxels}}),
               file=out, flush=True)

@@ -253,7 +253,8 @@ class MixedScaleSparseTransformerBlock(nn.Module):
             w_of = sl // self.max_num_win1
             nn_idx = g["nn_idx"][:W].reshape(-1, 3)[sl].long()               # (N, 3) query slots
             nn_w = g["nn_w"][:W].reshape(-1, 3)[sl]                          # (N, 3)
-            picked = attn[w_of.unsqueeze(1), nn_idx]                         # (N, 3, C); padded queries: zero rows
+            flat = (w_of.unsqueeze(1) * attn.shape[1] + nn_idx).reshape(-1)  # rows of the (W * nq, C) view
+            picked = attn.reshape(-1, C).index_select(0, flat).view(N, 3, C)  # padded queries: zero rows
             merged_cov = (picked * nn_w.unsqueeze(-1)).sum(1)
         else:
             q_slot = torch.full((N,), -1, dtype=torch.long, device=dev)
@@ -261,7 +262,7 @@ class MixedScaleSparseTransformerBlock(nn.Module):
             ok = flat >= 0
             q_slot[flat[ok]] = torch.arange(flat.numel(), device=dev)[ok]
             cov = q_slot >= 0
-            merged_cov = attn.reshape(-1, C)[q_slot.clamp(min=0)]
+            merged_cov = attn.reshape(-1, C).index_select(0, q_slot.clamp(min=0))
         merged = torch.where(cov.unsqueeze(1), merged_cov, x)               # Q5: uncovered rows keep x
         u = self.drop_path(merged) + x
         sp_tensor.features = self._ffn_autograd(u)
