@@ -46,48 +46,55 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md): NVML polled from a thread
+    every millisecond (the timed region is ~20 ms: `nvidia-smi -lms` does not even start in that time)."""
 
     def __init__(self, device_index):
-        self.idx, self.proc = device_index, None
+        self.idx, self.samples, self.reasons, self.max_mhz = device_index, [], set(), None
+        self._stop, self._thread, self._err = False, None, None
+
+    def _run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self._physical_index(nv))
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            names = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+            while not self._stop:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                mask = int(get_reasons(h))
+                self.reasons.update(n for n, bit in names.items() if mask & bit)
+                time.sleep(0.001)
+        except Exception as e:  # noqa: BLE001
+            self._err = repr(e)
+
+    def _physical_index(self, nv):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if self.idx < len(ids) and ids[self.idx].isdigit():
+                return int(ids[self.idx])
+        return self.idx
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-        except OSError:
-            self.proc = None
+        import threading
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
+        time.sleep(0.01)       # let NVML initialise before the timed region opens
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            out, _ = self.proc.communicate(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-            out, _ = self.proc.communicate()
-        sm, mx, reasons = [], 0.0, set()
-        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for line in out.strip().splitlines():
-            f = [x.strip() for x in line.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1]))
-                mx = max(mx, float(f[2]))
-            except ValueError:
-                continue
-            for n, v in zip(names, f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        busy = [v for v in sm if v > 0.5 * mx] or sm
-        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": mx or None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        self._stop = True
+        if self._thread is not None:
+            self._thread.join(timeout=2)
+        sm = self.samples
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml unavailable: %s" % self._err],
+                    "samples": 0}
+        busy = [v for v in sm if self.max_mhz and v > 0.5 * self.max_mhz] or sm
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(sm)}
 
 
 def dist_env():
@@ -200,9 +207,14 @@ def our_arm(args):
     # the feature kernels already fill the register files, the two passes only share the SMs.
     graphs = None
     if args.launch != "eager":
-        with torch.no_grad():
-            graphs = [model.capture({"voxel_features": dev[i][0], "voxel_coords": dev_idx[i], "batch_size": 1},
-                                    split=args.launch == "pipelined") for i in range(POOL)]
+        try:
+            with torch.no_grad():
+                graphs = [model.capture({"voxel_features": dev[i][0], "voxel_coords": dev_idx[i], "batch_size": 1},
+                                        split=args.launch == "pipelined") for i in range(POOL)]
+        except Exception as e:  # noqa: BLE001 -- a capture problem must not cost the measurement
+            print("[bench] CUDA graph capture failed (%r): falling back to --launch eager" % (e,), file=sys.stderr)
+            graphs, args.launch = None, "eager"
+            torch.cuda.synchronize()
     s_prep = torch.cuda.Stream()
     ev_prep, ev_feat = [None] * POOL, [None] * POOL
 
