@@ -102,6 +102,22 @@ def main():
             f = feats[:, :C].contiguous()
             dt = timed(lambda: mssvt_ops.grouping_operation(f, cnt, idx, wcnt), flush=flush)
             rows.append(("K/V feature gather C=%d ns=32" % C, n, 4 * W * 32 + 4 * C * valid + 4 * C * W * 32, dt))
+    # (iv) DynamicVFE: points -> voxels (bitmap + scan voxelisation, PFN, per-voxel max); N = points here
+    from mssvt_b200.config import AttrDict
+    from mssvt_b200.dynamic_vfe import DynamicVFE
+    vfe = DynamicVFE(AttrDict(NUM_FILTERS=[64]), 5, list(S0_VOXEL), list(S0_GRID), list(S0_RANGE)).to(dev).eval()
+    words = S0_GRID[0] * S0_GRID[1]
+    for n in (180000, 1000000):
+        g = torch.Generator().manual_seed(n)
+        centres = torch.rand((n // 30, 3), generator=g) * torch.tensor([140.0, 140.0, 5.0]) + torch.tensor([-70.0, -70.0, -1.9])
+        xyz = centres[torch.randint(0, n // 30, (n,), generator=g)] + (torch.rand((n, 3), generator=g) - 0.5) * torch.tensor([2.0, 2.0, 0.8])
+        pts = torch.cat([torch.zeros(n, 1), xyz, torch.rand((n, 2), generator=g)], 1).to(dev)
+        batch = {"points": pts, "batch_size": 1}
+        v = vfe(dict(batch))["voxel_features"].shape[0]
+        dt = timed(lambda: vfe(dict(batch)), flush=flush)
+        # points read twice (voxelise, PFN), bitmap + counts + scan, per-voxel sums, per-voxel output rows
+        rows.append(("DynamicVFE points -> %d voxels (voxelise + PFN 11->64 + max, incl. one host sync)" % v, n,
+                     2 * 24 * n + 4 * n + 5 * 4 * words + 16 * v + 16 * v + 4 * 64 * v, dt))
     lines = ["| kernel | N voxels | algorithmic MB | time us | GB/s | of measured HBM peak (%.0f GB/s) |" % peak,
              "|---|---:|---:|---:|---:|---:|"]
     for name, n, b, dt in rows:

@@ -296,6 +296,35 @@ int mssvt_dense_scatter(int num_rows, const int *num_rows_dev, int batch_size, i
 int mssvt_sizeof_attn_shape(void);
 int mssvt_sizeof_ffn_shape(void);
 
+/* ---- DynamicVFE (pcdet/models/backbones_3d/vfe/dynamic_vfe.py:71-130): the producer of voxel_features /
+ * voxel_coords.  Inference (eval-mode BatchNorm). */
+
+/* words of the occupancy bitmap used by mssvt_vfe_voxelize: batch * gx * gy * ceil(gz / 32) */
+long long mssvt_vfe_bitmap_words(int batch_size, int gx, int gy, int gz);
+
+/* Dynamic voxelisation (dynamic_vfe.py:85-93, 111-116; replaces torch.unique(sorted, return_inverse)).
+ * points (P, point_stride) fp32 rows [batch, x, y, z, ...].  Scratch (int): bitmap (words), counts (words),
+ * base (words + 1), scan_workspace ((words + 1) / 1024 + 2).  Outputs: point_voxel (P) voxel row of every
+ * point or -1 (outside the range); voxel_coords (P, 4) [b, z, y, x], rows [0, num_voxels) in ascending
+ * (b, x, y, z) key order (the order of torch.unique); num_voxels = base[words] stays on the device;
+ * xyz_sum (P, 4), optional: per-voxel (sum x, sum y, sum z, #points) for the cluster centre. */
+int mssvt_vfe_voxelize(int num_points, const float *points, int point_stride, int batch_size, int gx, int gy,
+                       int gz, const float *voxel_size, const float *range_min, int *bitmap, int *counts,
+                       int *base, int *scan_workspace, int *point_voxel, int *voxel_coords, float *xyz_sum,
+                       void *stream);
+
+/* Point-feature network + per-voxel max (dynamic_vfe.py:95-108, 124-130; replaces torch_scatter.scatter_mean /
+ * scatter_max and the Linear + BatchNorm1d + ReLU stack).  The caller folds each eval-mode BatchNorm1d into
+ * its Linear.  One or two layers: w0 (c0, in0), b0 (c0); w1 (c1, 2 * c0), b1 (c1), or c1 = 0.
+ * in0 = num_point_features + 3 (cluster centre) + 3 (voxel centre) + 1 (distance) as enabled, <= 20.
+ * centre_offset = voxel_size / 2 + range_min.  scratch: voxel_capacity * c0 floats (two layers only).
+ * out (voxel_capacity, c_last); rows >= num_voxels are zero. */
+int mssvt_vfe_features(int num_points, const float *points, int point_stride, int num_point_features,
+                       int with_cluster_center, int with_voxel_center, int with_distance, const float *voxel_size,
+                       const float *range_min, const float *centre_offset, const int *point_voxel,
+                       const float *xyz_sum, int voxel_capacity, const float *w0, const float *b0, int c0,
+                       const float *w1, const float *b1, int c1, float *scratch, float *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -53,13 +53,17 @@ _SIGNATURES = {
     "mssvt_dense_scatter": [I, P, I, I, I, I, I, P, P, P, P],
     "mssvt_sizeof_attn_shape": [],
     "mssvt_sizeof_ffn_shape": [],
+    "mssvt_vfe_bitmap_words": [I, I, I, I],
+    "mssvt_vfe_voxelize": [I, P, I, I, I, I, I] + [P] * 9 + [P],
+    "mssvt_vfe_features": [I, P, I, I, I, I, I] + [P] * 5 + [I, P, P, I, P, P, I, P, P] + [P],
     "mssvt_last_cuda_error": [],
     "mssvt_version": [],
     "mssvt_launch_count": [],
 }
 _RESTYPES = {"mssvt_window_partition_workspace_bytes": L, "mssvt_grid_index_words": L, "mssvt_version": ctypes.c_char_p,
+             "mssvt_vfe_bitmap_words": L,
              "mssvt_launch_count": L}
-_NO_STATUS = {"mssvt_window_partition_workspace_bytes", "mssvt_grid_index_words", "mssvt_fps_log2_block", "mssvt_version",
+_NO_STATUS = {"mssvt_window_partition_workspace_bytes", "mssvt_grid_index_words", "mssvt_vfe_bitmap_words", "mssvt_fps_log2_block", "mssvt_version",
               "mssvt_sizeof_attn_shape", "mssvt_sizeof_ffn_shape", "mssvt_last_cuda_error",
               "mssvt_launch_count"}
 _ERRORS = {-1: "invalid argument", -2: "CUDA launch/runtime error", -3: "workspace too small"}
