@@ -7,9 +7,9 @@
 //                                                       the row of its voxel in the sorted unique list; no sort
 //   torch_scatter.scatter_mean(xyz) :98                 atomicAdd of (x, y, z, 1) per point
 //   PFN: Linear + BatchNorm1d + ReLU :124-130           BatchNorm (eval) folded into the linear layer by the
-//                                                       caller; weights in shared memory, 32 points per CTA pass
+//                                                       caller; one warp per point, lane = output channel
 //   torch_scatter.scatter_max :108, :128                atomicMax on the int view (values are >= 0 after ReLU)
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace mssvt {
 
@@ -81,9 +81,9 @@ __global__ void k_vfe_coords(VfeGrid G, long long words, const unsigned *__restr
 }
 
 // ---- point-feature network -----------------------------------------------------------------------------
-#define VFE_PTS 32        // points per CTA pass
-#define VFE_THREADS 128   // thread = (point, quarter of the outputs)
+#define VFE_WARPS 8
 #define VFE_MAX_IN 20     // raw point features + 3 + 3 + 1
+#define VFE_OPL 4         // outputs per lane: layer widths up to 128
 
 struct VfeFeat {
     int n, stride, nfeat, cluster, centre, dist, in0, c0, c1;   // c1 = 0: one layer
@@ -91,76 +91,179 @@ struct VfeFeat {
     const float *w0, *b0, *w1, *b1;                             // BatchNorm already folded in
 };
 
-// LAYER 0: out = max over the voxel's points of relu(W0 x + b0);  LAYER 1: x1 = [relu(W0 x + b0), vmax0[voxel]],
-// out = max of relu(W1 x1 + b1)
+// One warp per point, lane = output channel (o = lane + 32 k): the first layer's weights live in registers,
+// a point's output row is written / max-reduced as one contiguous segment.
+// LAYER 0: out = max over the voxel's points of relu(W0 x + b0);
+// LAYER 1: x1 = [relu(W0 x + b0), vmax0[voxel]], out = max of relu(W1 x1 + b1)   (W1 rows in shared memory)
 template <int LAYER>
-__global__ void __launch_bounds__(VFE_THREADS)
+__global__ void __launch_bounds__(VFE_WARPS * 32)
 k_vfe_pfn(VfeFeat F, const float *__restrict__ points, const int *__restrict__ point_voxel,
           const float *__restrict__ xyz_sum, const float *__restrict__ vmax0, float *__restrict__ out) {
     extern __shared__ float sm[];
-    const int in1 = 2 * F.c0;
-    float *sW0 = sm;                                     // [c0][in0]
-    float *sB0 = sW0 + F.c0 * F.in0;                     // [c0]
-    float *sW1 = sB0 + F.c0;                             // [c1][in1]        (LAYER 1)
-    float *sB1 = sW1 + (LAYER ? F.c1 * in1 : 0);         // [c1]
-    float *sX = sB1 + (LAYER ? F.c1 : 0);                // [PTS][in0 + 1]
-    float *sY = sX + VFE_PTS * (F.in0 + 1);              // [PTS][in1 + 1]   (LAYER 1)
-    for (int i = threadIdx.x; i < F.c0 * F.in0; i += VFE_THREADS) sW0[i] = __ldg(F.w0 + i);
-    for (int i = threadIdx.x; i < F.c0; i += VFE_THREADS) sB0[i] = __ldg(F.b0 + i);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int in1 = 2 * F.c0, pitch1 = in1 + 1;
+    float *sW1 = sm;                                              // [c1][in1 + 1]   (LAYER 1)
+    float *sY = sW1 + (LAYER ? F.c1 * pitch1 : 0) + warp * in1;   // [warps][in1]    (LAYER 1)
     if (LAYER) {
-        for (int i = threadIdx.x; i < F.c1 * in1; i += VFE_THREADS) sW1[i] = __ldg(F.w1 + i);
-        for (int i = threadIdx.x; i < F.c1; i += VFE_THREADS) sB1[i] = __ldg(F.b1 + i);
-    }
-    const int pl = threadIdx.x & (VFE_PTS - 1), part = threadIdx.x / VFE_PTS;   // 4 parts
-    for (int p0 = blockIdx.x * VFE_PTS; p0 < F.n; p0 += gridDim.x * VFE_PTS) {
+        for (int i = threadIdx.x; i < F.c1 * in1; i += blockDim.x) sW1[(i / in1) * pitch1 + i % in1] = __ldg(F.w1 + i);
         __syncthreads();
-        const int p = p0 + pl;
-        const int v = p < F.n ? __ldg(point_voxel + p) : -1;
-        if (part == 0 && v >= 0) {   // input features of the point (dynamic_vfe.py:95-107)
-            const float *pt = points + (size_t)p * F.stride;
-            float *x = sX + pl * (F.in0 + 1);
-            int at = 0;
-            for (int i = 0; i < F.nfeat; ++i) x[at++] = pt[1 + i];
+    }
+    float w[VFE_OPL][VFE_MAX_IN], bias[VFE_OPL];
+#pragma unroll
+    for (int k = 0; k < VFE_OPL; ++k) {
+        const int o = lane + 32 * k;
+        bias[k] = o < F.c0 ? __ldg(F.b0 + o) : 0.f;
+#pragma unroll
+        for (int i = 0; i < VFE_MAX_IN; ++i) w[k][i] = (o < F.c0 && i < F.in0) ? __ldg(F.w0 + o * F.in0 + i) : 0.f;
+    }
+    const int warps = gridDim.x * VFE_WARPS;
+    for (int p = blockIdx.x * VFE_WARPS + warp; p < F.n; p += warps) {
+        const int v = __ldg(point_voxel + p);
+        if (v < 0) continue;
+        // input features of the point (dynamic_vfe.py:95-107); every lane builds the same small vector
+        const float *pt = points + (size_t)p * F.stride;
+        float x[VFE_MAX_IN];
+#pragma unroll
+        for (int i = 0; i < VFE_MAX_IN; ++i) x[i] = 0.f;
+        int at = 0;
+        for (int i = 0; i < F.nfeat; ++i) x[at++] = __ldg(pt + 1 + i);
+        const float px = x[0], py = x[1], pz = x[2];
+        float cnt = 0.f;
+        if (xyz_sum) {
+            const float4 s = __ldg((const float4 *)(xyz_sum + 4 * (size_t)v));
+            cnt = s.w;
             if (F.cluster) {
-                const float4 s = *(const float4 *)(xyz_sum + 4 * (size_t)v);
-                const float cnt = fmaxf(s.w, 1.0f);
-                x[at++] = __fsub_rn(pt[1], __fdiv_rn(s.x, cnt));
-                x[at++] = __fsub_rn(pt[2], __fdiv_rn(s.y, cnt));
-                x[at++] = __fsub_rn(pt[3], __fdiv_rn(s.z, cnt));
+                const float c = fmaxf(s.w, 1.0f);
+                x[at++] = __fsub_rn(px, __fdiv_rn(s.x, c)); x[at++] = __fsub_rn(py, __fdiv_rn(s.y, c));
+                x[at++] = __fsub_rn(pz, __fdiv_rn(s.z, c));
+            }
+        }
+        if (F.centre) {
+            const float q[3] = {px, py, pz};
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                const float c = floorf(__fdiv_rn(__fsub_rn(q[d], F.lo[d]), F.vs[d]));
+                x[at++] = __fsub_rn(q[d], __fadd_rn(__fmul_rn(c, F.vs[d]), F.off[d]));
+            }
+        }
+        if (F.dist) x[at++] = __fsqrt_rn(px * px + py * py + pz * pz);
+        const bool alone = cnt == 1.0f;   // a voxel with a single point needs no atomic
+        float y[VFE_OPL];
+#pragma unroll
+        for (int k = 0; k < VFE_OPL; ++k) {
+            float a = bias[k];
+#pragma unroll
+            for (int i = 0; i < VFE_MAX_IN; ++i) a = fmaf(w[k][i], x[i], a);
+            y[k] = fmaxf(a, 0.f);
+        }
+        if (!LAYER) {
+#pragma unroll
+            for (int k = 0; k < VFE_OPL; ++k) {
+                const int o = lane + 32 * k;
+                if (o < F.c0) {
+                    if (alone) out[(size_t)v * F.c0 + o] = y[k];
+                    else atomicMax((int *)out + (size_t)v * F.c0 + o, __float_as_int(y[k]));   // y >= 0: int order = float order
+                }
+            }
+        } else {
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < VFE_OPL; ++k) {
+                const int o = lane + 32 * k;
+                if (o < F.c0) { sY[o] = y[k]; sY[F.c0 + o] = __ldg(vmax0 + (size_t)v * F.c0 + o); }
+            }
+            __syncwarp();
+            for (int o = lane; o < F.c1; o += 32) {
+                float a = __ldg(F.b1 + o);
+                const float *wr = sW1 + o * pitch1;
+                for (int i = 0; i < in1; ++i) a = fmaf(wr[i], sY[i], a);
+                a = fmaxf(a, 0.f);
+                if (alone) out[(size_t)v * F.c1 + o] = a;
+                else atomicMax((int *)out + (size_t)v * F.c1 + o, __float_as_int(a));
+            }
+        }
+    }
+}
+
+// First layer, thread = point: the point's features are built once, its outputs are computed 32 at a time
+// against weights in shared memory (rows padded to a multiple of 4 inputs: 16-byte broadcast loads), and a
+// chunk of 32 outputs = 128 bytes of the voxel's row leaves through the warp-cooperative row store
+// (tc_common.cuh) when the voxel holds a single point, through atomicMax otherwise.
+__global__ void __launch_bounds__(VFE_WARPS * 32)
+k_vfe_pfn0(VfeFeat F, const float *__restrict__ points, const int *__restrict__ point_voxel,
+           const float *__restrict__ xyz_sum, float *__restrict__ out) {
+    extern __shared__ __align__(16) float sm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int pitch = (F.in0 + 3) & ~3;                       // <= VFE_MAX_IN
+    float *sW = sm;                                           // [c0][pitch], zero padded
+    float *sB = sW + F.c0 * pitch;                            // [c0]
+    char *stg = (char *)(sB + ((F.c0 + 3) & ~3)) + warp * 4096;
+    for (int i = threadIdx.x; i < F.c0 * pitch; i += blockDim.x) {
+        const int o = i / pitch, k = i - o * pitch;
+        sW[i] = k < F.in0 ? __ldg(F.w0 + o * F.in0 + k) : 0.f;
+    }
+    for (int i = threadIdx.x; i < F.c0; i += blockDim.x) sB[i] = __ldg(F.b0 + i);
+    __syncthreads();
+    const int stride_pts = gridDim.x * blockDim.x;
+    for (int p0 = blockIdx.x * blockDim.x + warp * 32; p0 < F.n; p0 += stride_pts) {   // (warp-uniform loop)
+        const int p = p0 + lane;
+        const int v = p < F.n ? __ldg(point_voxel + p) : -1;
+        float x[VFE_MAX_IN];
+#pragma unroll
+        for (int i = 0; i < VFE_MAX_IN; ++i) x[i] = 0.f;
+        bool alone = false;
+        if (v >= 0) {   // input features of the point (dynamic_vfe.py:95-107)
+            const float *pt = points + (size_t)p * F.stride;
+            const float px = __ldg(pt + 1), py = __ldg(pt + 2), pz = __ldg(pt + 3);
+            int at = 0;
+#pragma unroll
+            for (int i = 0; i < VFE_MAX_IN - 7; ++i)
+                if (i < F.nfeat) x[at++] = __ldg(pt + 1 + i);
+            if (xyz_sum) {
+                const float4 s = __ldg((const float4 *)(xyz_sum + 4 * (size_t)v));
+                alone = s.w == 1.0f;
+                if (F.cluster) {
+                    const float c = fmaxf(s.w, 1.0f);
+                    x[at++] = __fsub_rn(px, __fdiv_rn(s.x, c)); x[at++] = __fsub_rn(py, __fdiv_rn(s.y, c));
+                    x[at++] = __fsub_rn(pz, __fdiv_rn(s.z, c));
+                }
             }
             if (F.centre) {
+                const float q[3] = {px, py, pz};
 #pragma unroll
                 for (int d = 0; d < 3; ++d) {
-                    const float c = floorf(__fdiv_rn(__fsub_rn(pt[1 + d], F.lo[d]), F.vs[d]));
-                    x[at++] = __fsub_rn(pt[1 + d], __fadd_rn(__fmul_rn(c, F.vs[d]), F.off[d]));
+                    const float c = floorf(__fdiv_rn(__fsub_rn(q[d], F.lo[d]), F.vs[d]));
+                    x[at++] = __fsub_rn(q[d], __fadd_rn(__fmul_rn(c, F.vs[d]), F.off[d]));
                 }
             }
-            if (F.dist) x[at++] = __fsqrt_rn(pt[1] * pt[1] + pt[2] * pt[2] + pt[3] * pt[3]);
+            if (F.dist) x[at++] = __fsqrt_rn(px * px + py * py + pz * pz);
         }
-        __syncthreads();
-        if (v >= 0) {   // layer 0: this thread's quarter of the c0 outputs
-            const float *x = sX + pl * (F.in0 + 1);
-            for (int o = part; o < F.c0; o += VFE_THREADS / VFE_PTS) {
-                float a = sB0[o];
-                for (int i = 0; i < F.in0; ++i) a = fmaf(sW0[o * F.in0 + i], x[i], a);
-                a = fmaxf(a, 0.f);
-                if (LAYER) {
-                    sY[pl * (in1 + 1) + o] = a;
-                    sY[pl * (in1 + 1) + F.c0 + o] = __ldg(vmax0 + (size_t)v * F.c0 + o);
-                } else {
-                    atomicMax((int *)out + (size_t)v * F.c0 + o, __float_as_int(a));   // a >= 0: int order = float order
+        for (int c = 0; c < F.c0; c += 32) {   // 32 outputs = one 128-byte segment of the voxel's row
+            float4 y[8];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                float a = 0.f;
+                if (c + j < F.c0) {
+                    a = sB[c + j];
+                    const float4 *wr = (const float4 *)(sW + (c + j) * pitch);
+#pragma unroll
+                    for (int i4 = 0; i4 < VFE_MAX_IN / 4; ++i4)
+                        if (4 * i4 < pitch) {
+                            const float4 wv = wr[i4];
+                            a = fmaf(wv.x, x[4 * i4], a); a = fmaf(wv.y, x[4 * i4 + 1], a);
+                            a = fmaf(wv.z, x[4 * i4 + 2], a); a = fmaf(wv.w, x[4 * i4 + 3], a);
+                        }
+                    a = fmaxf(a, 0.f);
                 }
+                ((float *)y)[j] = a;
             }
-        }
-        if (LAYER) {
-            __syncthreads();
-            if (v >= 0) {
-                const float *y = sY + pl * (in1 + 1);
-                for (int o = part; o < F.c1; o += VFE_THREADS / VFE_PTS) {
-                    float a = sB1[o];
-                    for (int i = 0; i < in1; ++i) a = fmaf(sW1[o * in1 + i], y[i], a);
-                    atomicMax((int *)out + (size_t)v * F.c1 + o, __float_as_int(fmaxf(a, 0.f)));
-                }
+            const bool full = c + 32 <= F.c0;
+            float *row = v >= 0 ? out + (size_t)v * F.c0 + c : nullptr;
+            warp_rows_store(stg, (full && alone) ? (float4 *)row : nullptr, y);
+            if (row && !(full && alone)) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (c + j < F.c0) atomicMax((int *)row + j, __float_as_int(((float *)y)[j]));   // y >= 0
             }
         }
     }
@@ -241,28 +344,28 @@ int mssvt_vfe_features(int num_points, const float *points, int point_stride, in
                  with_distance ? 1 : 0, in0, c0, c1,
                  {voxel_size[0], voxel_size[1], voxel_size[2]}, {range_min[0], range_min[1], range_min[2]},
                  {centre_offset[0], centre_offset[1], centre_offset[2]}, w0, b0, w1, b1};
-    const int grid = persistent_grid(num_points, VFE_PTS, 8);
-    const size_t sm0 = (size_t)(c0 * in0 + c0 + VFE_PTS * (in0 + 1)) * 4;
+    if (c0 > 32 * VFE_OPL || c1 > 32 * VFE_OPL) return MSSVT_ERR_INVALID;
+    const int grid = persistent_grid(num_points, VFE_WARPS, 8);
+    const int grid0 = persistent_grid(num_points, VFE_WARPS * 32, 8);
+    const size_t sm0 = (size_t)(c0 * ((in0 + 3) & ~3) + ((c0 + 3) & ~3)) * 4 + VFE_WARPS * 4096;
+    if (sm0 > 200 * 1024 || (c0 & 3)) return MSSVT_ERR_INVALID;
+    cudaFuncSetAttribute(k_vfe_pfn0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm0);
     if (!c1) {
-        if (sm0 > 200 * 1024) return MSSVT_ERR_INVALID;
-        cudaFuncSetAttribute(k_vfe_pfn<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm0);
         ++g_launches;
-        k_vfe_pfn<0><<<grid, VFE_THREADS, sm0, s>>>(F, points, point_voxel, xyz_sum, nullptr, out);
+        k_vfe_pfn0<<<grid0, VFE_WARPS * 32, sm0, s>>>(F, points, point_voxel, xyz_sum, out);
         return check_launch();
     }
     // two layers: pass 1 = per-voxel max of layer 0 (scratch), pass 2 recomputes layer 0 and applies layer 1
     if (cudaMemsetAsync(scratch, 0, (size_t)voxel_capacity * c0 * 4, s) != cudaSuccess) return MSSVT_ERR_LAUNCH;
     VfeFeat F0 = F;
     F0.c1 = 0;
-    if (sm0 > 200 * 1024) return MSSVT_ERR_INVALID;
-    cudaFuncSetAttribute(k_vfe_pfn<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm0);
     ++g_launches;
-    k_vfe_pfn<0><<<grid, VFE_THREADS, sm0, s>>>(F0, points, point_voxel, xyz_sum, nullptr, scratch);
-    const size_t sm1 = sm0 + (size_t)(c1 * 2 * c0 + c1 + VFE_PTS * (2 * c0 + 1)) * 4;
+    k_vfe_pfn0<<<grid0, VFE_WARPS * 32, sm0, s>>>(F0, points, point_voxel, xyz_sum, scratch);
+    const size_t sm1 = (size_t)(c1 * (2 * c0 + 1) + VFE_WARPS * 2 * c0) * 4;
     if (sm1 > 200 * 1024) return MSSVT_ERR_INVALID;
     cudaFuncSetAttribute(k_vfe_pfn<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1);
     ++g_launches;
-    k_vfe_pfn<1><<<grid, VFE_THREADS, sm1, s>>>(F, points, point_voxel, xyz_sum, scratch, out);
+    k_vfe_pfn<1><<<grid, VFE_WARPS * 32, sm1, s>>>(F, points, point_voxel, xyz_sum, scratch, out);
     return check_launch();
 }
 

@@ -69,7 +69,7 @@ class DynamicVFE(nn.Module):
         bitmap, counts, base = torch.empty(words, **i32), torch.empty(words, **i32), torch.empty(words + 1, **i32)
         work = torch.empty((words + 1) // 1024 + 2, **i32)
         point_voxel, coords = torch.empty(max(P, 1), **i32), torch.empty((max(P, 1), 4), **i32)
-        xyz_sum = torch.empty((max(P, 1), 4), dtype=torch.float32, device=dev) if self.with_cluster_center else None
+        xyz_sum = torch.empty((max(P, 1), 4), dtype=torch.float32, device=dev)   # (also: #points per voxel)
         vs, lo = host_floats(self.voxel_size), host_floats(self.point_cloud_range[0:3])
         call("mssvt_vfe_voxelize", P, ptr(points), stride, B, gx, gy, gz, vs, lo, ptr(bitmap), ptr(counts), ptr(base),
              ptr(work), ptr(point_voxel), ptr(coords), ptr(xyz_sum), stream())
