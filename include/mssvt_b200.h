@@ -282,12 +282,17 @@ int mssvt_pack_operand_tf32(const float *w, int n_rows, int k, float *packed, vo
 /* The same FFN on the tcgen05 tensor cores: TF32 operands, fp32 accumulation in TMEM, LayerNorm and
  * the residual stream in fp32 (mssvt_b200/csrc/ffn_tc.cu).  w1 [F][C] and w2 [C][F] (nn.Linear layout) packed by
  * mssvt_pack_operand_tf32.  Supported shapes: C in {32, 64}, F % 64 == 0, F + C <= 512; -1 otherwise.
+ * mode 2 (C = 64): the three-NN interpolation + merge of mssvt_block_attention_tc happens on the way in --
+ * `merged` is not read; vox_slot / meta / q_base / nn_idx / nn_w are the geometry maps, `projected` the projected
+ * query rows (scratch + 2 * num_voxels * 64 of that call), cap1 = max_num_win1.  Otherwise those 7 are ignored.
  * xn_next (optional, with next_ln_g / next_ln_b / next_eps): also writes LayerNorm(y) with the NEXT block's
  * norm1 parameters, which saves that block its own LayerNorm pass over y. */
 int mssvt_ffn_tc(int C, int F, int mode, float eps, const float *ln_g, const float *ln_b, const float *w1_packed,
                  const float *b1, const float *w2_packed, const float *b2, int num_rows, const int *num_rows_dev,
                  const float *x, const float *merged, const unsigned char *covered, float *y,
-                 const float *next_ln_g, const float *next_ln_b, float next_eps, float *xn_next, void *stream);
+                 const float *next_ln_g, const float *next_ln_b, float next_eps, float *xn_next,
+                 const int *vox_slot, const int *meta, const int *q_base, const unsigned char *nn_idx,
+                 const float *nn_w, const float *projected, int cap1, void *stream);
 
 /* SparseTensor.dense() (mssvt_utils.py:50-62): out (B, C, D, H, W), zero-filled then scattered */
 int mssvt_dense_scatter(int num_rows, const int *num_rows_dev, int batch_size, int C, int D, int H,

@@ -510,7 +510,9 @@ int mssvt_attention_tiles(int heads_per_group, int nq, int key_num_sample, int w
  * their nn.Module layout: pos_w [64][6]; packed by mssvt_pack_operand_tf32: wkv [64][32] per head group,
  * wq_packed / wp_packed = the [64][64] block-diagonal matrix of the two groups' [32][32] weights.  rep_row / meta: compact key lists of mssvt_block_geometry; q_base:
  * mssvt_exclusive_scan of meta[:, 0] (win_capacity + 1 ints); tiles .. win_ctr: mssvt_attention_tiles.
- * scratch: 3 * num_voxels * 64 floats (q, head outputs, projected rows of every real query).
+ * scratch: 3 * num_voxels * 64 floats (q, head outputs, projected rows of every real query).  merged may be
+ * NULL when interp is set: the blend of the projected rows (scratch + 2 * num_voxels * 64) is then left to
+ * mssvt_ffn_tc in mode 2.
  * Returns MSSVT_ERR_INVALID for shapes outside C = 64 / 2 x 32 channels / nq <= 32 / K <= 63 /
  * cap1 <= 128 (callers then use mssvt_block_attention). */
 int mssvt_block_attention_tc(int C, int heads_per_group, int nq, int key_num_sample, int cap1, int interp,
@@ -531,7 +533,8 @@ int mssvt_block_attention_tc(int C, int heads_per_group, int nq, int key_num_sam
     if (win_capacity == 0) return MSSVT_OK;
     if (!win_cell || !range_min || !pos_w || !pos_b || !wq_packed || !bq0 || !wkv0 || !bkv0 || !wp_packed || !bp0 ||
         !bq1 || !wkv1 || !bkv1 || !bp1 || !win_count_total || !win_list || !xn || !xyz || !q_row ||
-        !rep_row || !meta || !q_base || !q_src || !tiles || !tile_count || !win_rec || !win_ctr || !scratch || !merged)
+        !rep_row || !meta || !q_base || !q_src || !tiles || !tile_count || !win_rec || !win_ctr || !scratch ||
+        (!merged && !interp))
         return MSSVT_ERR_INVALID;
     if (interp && (!vox_slot || !nn_idx || !nn_w)) return MSSVT_ERR_INVALID;
     (void)win1_row;
@@ -577,6 +580,7 @@ int mssvt_block_attention_tc(int C, int heads_per_group, int nq, int key_num_sam
         const TclParams L = {wp_packed, bp0, bp1, 1.0f};
         tcl_launch(L, rows, num_voxels, Pbuf, s);
     }
+    if (!merged) return check_launch();  // interpolation + merge left to mssvt_ffn_tc (mode 2)
     ++g_launches;
     launch_pdl(k_tca_merge, dim3(wide), dim3(256), 0, s, P, win_capacity, win_count_total, num_voxels, meta, q_base,
                q_src, q_row, vox_slot, nn_idx, nn_w, Pbuf, merged);

@@ -42,6 +42,12 @@ struct FfnTcParams {
     const float *ln_g, *ln_b;
     const float *next_g, *next_b;  // optional: LayerNorm of the NEXT block (norm1), fused into the epilogue
     float next_eps;
+    // mode 2: the three-NN feature interpolation + merge of the window attention (k_tca_merge) happens here,
+    // on the way in: merged[row] = sum_i w_i * P[q_base[w] + nn_i] is never written to memory
+    const int *vox_slot, *meta, *q_base;
+    const unsigned char *nn_idx;
+    const float *nn_w, *pbuf;
+    int cap1;
 };
 
 template <int C>
@@ -157,7 +163,7 @@ k_ffn_tc(FfnTcParams P, int n_cap, const int *__restrict__ n_dev, const float *_
         {   // the next tile's rows: start them on their way from HBM to L2 now, a whole tile time ahead
             const int nrow = row + (int)gridDim.x * TC_ROWS;
             if (nrow < n) {
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(merged + (size_t)nrow * C + half * CH));
+                if (P.mode != 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(merged + (size_t)nrow * C + half * CH));
                 if (P.mode != 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(x + (size_t)nrow * C + half * CH));
             }
         }
@@ -167,7 +173,46 @@ k_ffn_tc(FfnTcParams P, int n_cap, const int *__restrict__ n_dev, const float *_
         float u[CH];
         {
             float4 mv[CH / 4];
-            stage_in(merged, mv);
+            bool cov = false;
+            if constexpr (C == 64) {
+                if (P.mode == 2) {
+                    // the voxel's win1 slot names its 3 nearest query slots; their projected rows are fetched
+                    // warp-cooperatively and blended in the reference's order (same arithmetic as k_tca_merge)
+                    const float *p0 = nullptr, *p1 = nullptr, *p2 = nullptr;
+                    float w0 = 0.f, w1 = 0.f, w2 = 0.f;
+                    const int slot = live ? __ldg(P.vox_slot + row) : -1;
+                    if (slot >= 0) {
+                        cov = true;
+                        const int w = slot / P.cap1;
+                        const int nqr = __ldg(P.meta + 4 * (size_t)w), q0 = __ldg(P.q_base + w);
+                        const unsigned char *ni = P.nn_idx + (size_t)slot * 3;
+                        const float *nw = P.nn_w + (size_t)slot * 3;
+                        const int n0 = ni[0], n1 = ni[1], n2 = ni[2];
+                        // padded query slots (index >= #real queries) are zero rows in the reference
+                        if (n0 < nqr) p0 = P.pbuf + (size_t)(q0 + n0) * 64 + half * 32;
+                        if (n1 < nqr) p1 = P.pbuf + (size_t)(q0 + n1) * 64 + half * 32;
+                        if (n2 < nqr) p2 = P.pbuf + (size_t)(q0 + n2) * 64 + half * 32;
+                        w0 = __ldg(nw); w1 = __ldg(nw + 1); w2 = __ldg(nw + 2);
+                    }
+                    float4 v[8];
+                    warp_rows_load(stg, (const float4 *)p0, mv);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        mv[q] = make_float4(__fmul_rn(mv[q].x, w0), __fmul_rn(mv[q].y, w0), __fmul_rn(mv[q].z, w0),
+                                            __fmul_rn(mv[q].w, w0));
+                    warp_rows_load(stg, (const float4 *)p1, v);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        mv[q] = make_float4(__fadd_rn(mv[q].x, __fmul_rn(v[q].x, w1)), __fadd_rn(mv[q].y, __fmul_rn(v[q].y, w1)),
+                                            __fadd_rn(mv[q].z, __fmul_rn(v[q].z, w1)), __fadd_rn(mv[q].w, __fmul_rn(v[q].w, w1)));
+                    warp_rows_load(stg, (const float4 *)p2, v);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        mv[q] = make_float4(__fadd_rn(mv[q].x, __fmul_rn(v[q].x, w2)), __fadd_rn(mv[q].y, __fmul_rn(v[q].y, w2)),
+                                            __fadd_rn(mv[q].z, __fmul_rn(v[q].z, w2)), __fadd_rn(mv[q].w, __fmul_rn(v[q].w, w2)));
+                }
+            }
+            if (P.mode != 2) stage_in(merged, mv);
             if (P.mode == 0) {
 #pragma unroll
                 for (int c = 0; c < CH / 4; ++c) {
@@ -176,7 +221,7 @@ k_ffn_tc(FfnTcParams P, int n_cap, const int *__restrict__ n_dev, const float *_
             } else {
                 float4 xv[CH / 4];
                 stage_in(x, xv);
-                const bool cov = live && covered[row] != 0;  // (uncovered rows of merged are never written)
+                if (P.mode == 1) cov = live && covered[row] != 0;  // (uncovered rows of merged are never written)
 #pragma unroll
                 for (int c = 0; c < CH / 4; ++c) {
                     const float4 v = xv[c], m = cov ? mv[c] : v;
@@ -340,15 +385,21 @@ int mssvt_pack_operand_tf32(const float *w, int n_rows, int k, float *packed, vo
 int mssvt_ffn_tc(int C, int F, int mode, float eps, const float *ln_g, const float *ln_b, const float *w1,
                  const float *b1, const float *w2, const float *b2, int num_rows, const int *num_rows_dev,
                  const float *x, const float *merged, const unsigned char *covered, float *y,
-                 const float *next_ln_g, const float *next_ln_b, float next_eps, float *xn_next, void *stream) {
+                 const float *next_ln_g, const float *next_ln_b, float next_eps, float *xn_next,
+                 const int *vox_slot, const int *meta, const int *q_base, const unsigned char *nn_idx,
+                 const float *nn_w, const float *projected, int cap1, void *stream) {
     if ((C != 32 && C != 64) || F <= 0 || (F & 63) || F + C > 512 || num_rows < 0) return MSSVT_ERR_INVALID;
     if (num_rows == 0) return MSSVT_OK;
-    if (!ln_g || !ln_b || !w1 || !b1 || !w2 || !b2 || !merged || !y || (mode == 1 && (!x || !covered)))
+    if (mode < 0 || mode > 2 || !ln_g || !ln_b || !w1 || !b1 || !w2 || !b2 || !y || (mode != 2 && !merged) ||
+        (mode == 1 && (!x || !covered)))
+        return MSSVT_ERR_INVALID;
+    if (mode == 2 && (C != 64 || !x || !vox_slot || !meta || !q_base || !nn_idx || !nn_w || !projected || cap1 <= 0))
         return MSSVT_ERR_INVALID;
     size_t smem = (size_t)TC_ROWS * C * 4 + 2 * (size_t)F * C * 4 + (size_t)(5 * C + F + 8 * TC_ROWS) * 4 + 2 * 8 + 16 + 128;
     if (smem > 227 * 1024) return MSSVT_ERR_INVALID;
     if (xn_next && (!next_ln_g || !next_ln_b)) return MSSVT_ERR_INVALID;
-    FfnTcParams P = {F, mode, eps, w1, b1, w2, b2, ln_g, ln_b, next_ln_g, next_ln_b, next_eps};
+    FfnTcParams P = {F, mode, eps, w1, b1, w2, b2, ln_g, ln_b, next_ln_g, next_ln_b, next_eps,
+                     vox_slot, meta, q_base, nn_idx, nn_w, projected, cap1};
     int tiles = (num_rows + TC_ROWS - 1) / TC_ROWS;
     int tmem_cols = 32;
     while (tmem_cols < F + C) tmem_cols <<= 1;

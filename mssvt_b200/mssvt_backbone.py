@@ -447,9 +447,15 @@ class MixedScaleSparseTransformerBlock(nn.Module):
              ptr(self.norm1.bias), self.norm1.eps, ptr(xn), stream())
         return xn
 
-    def _ffn(self, S, buf, n_rows, x, merged, covered, n_dev=None):
+    def _ffn_tc_supported(self, S):
+        return (self.precision == "tf32" and S.C_out == 0 and S.C in (32, 64) and S.F % 64 == 0
+                and S.F + S.C <= 512 and (128 * S.C + 2 * S.F * S.C) * 4 < 220 * 1024)
+
+    def _ffn(self, S, buf, n_rows, x, merged, covered, n_dev=None, merge_src=None):
+        """merge_src = (vox_slot, meta, q_base, nn_idx, nn_w, projected rows, cap1): the interpolation + merge
+        of the window attention is done by the FFN kernel on the way in (`merged` is not used)"""
         c_out = S.C_out if S.C_out else S.C
-        y = torch.empty((n_rows, c_out), dtype=torch.float32, device=merged.device)
+        y = torch.empty((n_rows, c_out), dtype=torch.float32, device=x.device if x is not None else merged.device)
         if (self.precision == "tf32" and S.C_out == 0 and S.C in (32, 64) and S.F % 64 == 0
                 and S.F + S.C <= 512 and (128 * S.C + 2 * S.F * S.C) * 4 < 220 * 1024):
             # tensor-core path: TF32 operands on tcgen05, fp32 accumulate / LayerNorm / residual
@@ -459,14 +465,16 @@ class MixedScaleSparseTransformerBlock(nn.Module):
             xn_next = None
             if nxt is not None and nxt.normalized_shape == (c_out,) and n_dev is None:
                 xn_next = torch.empty_like(y)
-            call("mssvt_ffn_tc", S.C, S.F, S.mode, self.norm2.eps, ptr(self.norm2.weight), ptr(self.norm2.bias),
+            ms = merge_src or (None,) * 6 + (0,)
+            call("mssvt_ffn_tc", S.C, S.F, 2 if merge_src else S.mode, self.norm2.eps, ptr(self.norm2.weight), ptr(self.norm2.bias),
                  ptr(self._packed(self.linear1.weight)), ptr(self.linear1.bias),
                  ptr(self._packed(self.linear2.weight)), ptr(self.linear2.bias), n_rows, ptr(n_dev), ptr(x),
                  ptr(merged), ptr(covered), ptr(y),
                  ptr(nxt.weight) if xn_next is not None else None, ptr(nxt.bias) if xn_next is not None else None,
-                 nxt.eps if xn_next is not None else 0.0, ptr(xn_next), stream())
+                 nxt.eps if xn_next is not None else 0.0, ptr(xn_next), *(ptr(t) for t in ms[:6]), ms[6], stream())
             self.__dict__["_xn_for_next"] = (y, xn_next) if xn_next is not None else None
             return y
+        assert merge_src is None
         call("mssvt_ffn", ctypes.byref(S), ctypes.sizeof(S), ptr(buf), n_rows, ptr(n_dev), ptr(x), ptr(merged),
              ptr(covered), ptr(y), stream())
         return y
@@ -479,12 +487,18 @@ class MixedScaleSparseTransformerBlock(nn.Module):
             x = x.float().contiguous()
         g = self.geometry(sp_tensor)
         xn = self._layernorm1(x, sp_tensor)
-        merged = torch.empty_like(x)  # only rows flagged in g["covered"] are written and read
         a = self.ms_attn
+        F, fbuf = self._ffn_descriptor(mode=1)
+        merge_src = None
+        # tensor-core path with interpolation: the FFN kernel blends the projected query rows itself
+        fuse_merge = (self._tc_supported(g["nq"]) and self.use_feature_interpolation and self.in_channels == 64
+                      and self._ffn_tc_supported(F))
+        merged = None if fuse_merge else torch.empty_like(x)  # only rows flagged in g["covered"] are written and read
         if self._tc_supported(g["nq"]):
             # task-parallel kernel, K/V projection on the tcgen05 tensor cores (TF32 operands)
             vs = sp_tensor.voxel_size
             plan = self._tile_plan(sp_tensor, g, a.num_heads[0])
+            scratch = torch.empty((3 * x.shape[0], 64), dtype=torch.float32, device=x.device)
             call("mssvt_block_attention_tc", 64, a.num_heads[0], g["nq"], self.key_num_sample, self.max_num_win1,
                  int(bool(self.use_feature_interpolation)), a.scale,
                  host_floats([vs[i] * self.win1_size[i] for i in range(3)]),
@@ -496,18 +510,18 @@ class MixedScaleSparseTransformerBlock(nn.Module):
                  ptr(a.projs[1].bias), g["cap"], ptr(g["total"]), ptr(g["win_list"]), ptr(xn),
                  ptr(sp_tensor.world_coords()), ptr(g["q_row"]), ptr(g["rep_row"]), ptr(g["meta"]),
                  ptr(g["q_base"]), ptr(g["q_src"]), ptr(g["vox_slot"]), ptr(g["win1_row"]), ptr(g["nn_idx"]),
-                 ptr(g["nn_w"]), *(ptr(v) for v in plan), x.shape[0],
-                 ptr(torch.empty((3 * x.shape[0], 64), dtype=torch.float32, device=x.device)), ptr(merged),
-                 stream())
+                 ptr(g["nn_w"]), *(ptr(v) for v in plan), x.shape[0], ptr(scratch), ptr(merged), stream())
+            if fuse_merge:
+                merge_src = (g["vox_slot"], g["meta"], g["q_base"], g["nn_idx"], g["nn_w"], scratch[2 * x.shape[0]:],
+                             self.max_num_win1)
         else:
             S, buf = self._attn_descriptor(sp_tensor, g["nq"], 2 * self.key_num_sample, self.max_num_win1)
             call("mssvt_block_attention", ctypes.byref(S), ctypes.sizeof(S), ptr(buf), g["cap"],
                  ptr(g["total"]), ptr(g["win_list"]), ptr(xn), ptr(sp_tensor.world_coords()), ptr(g["q_row"]),
                  ptr(g["k_row"]), ptr(g["k_mask"]), ptr(g["win1_row"]), ptr(g["nn_idx"]), ptr(g["nn_w"]),
                  ptr(merged), stream())
-        F, fbuf = self._ffn_descriptor(mode=1)
         self.__dict__["_xn_for_next"] = None
-        sp_tensor.features = self._ffn(F, fbuf, x.shape[0], x, merged, g["covered"])
+        sp_tensor.features = self._ffn(F, fbuf, x.shape[0], x, merged, g["covered"], merge_src=merge_src)
         pre = self.__dict__.get("_xn_for_next")
         sp_tensor._xn_ready = (pre[0], pre[1], self.__dict__["_next_norm1"]) if pre is not None else None
         sp_tensor.gather_dict = None
