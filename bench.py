@@ -119,8 +119,11 @@ def algorithmic_bytes(kernel, n, w, pillars):
     table = {
         # read xn rows once + maps, write the covered rows of `merged`
         "mssvt_block_attention": n * C4 + w * (12 * 4 + 64 * 4 + 64 + 27 * 4 + 27 * 3 * 5) + n * 12 + n * C4,
-        "mssvt_block_attention_tc": n * C4 + w * (12 * 4 + 64 * 4 + 16 + 27 * 4 + 27 * 3 * 5) + n * 12 + n * C4,
-        "mssvt_ffn_tc": 3 * n * C4 + n,
+        # read xn rows once + compact maps + coordinates, write the projected row of every real query (~N / 2)
+        "mssvt_block_attention_tc": n * C4 + w * (12 * 4 + 64 * 4 + 16) + n * 12 + (n // 2) * C4,
+        # the tensor-core FFN with the interpolation + merge on the way in: x, three projected rows per covered
+        # voxel out of the L2-resident (N / 2, 64) array (counted once), maps; writes y and the next LayerNorm
+        "mssvt_ffn_tc": n * C4 + (n // 2) * C4 + n * (4 + 3 + 12) + 2 * n * C4,
         # read x + merged + covered flag, write y
         "mssvt_ffn": 3 * n * C4 + n,
         "mssvt_layernorm": 2 * n * C4,
@@ -136,11 +139,11 @@ def algorithmic_bytes(kernel, n, w, pillars):
 
 
 # DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per launch of an entry point, summed over its
-# kernels, from the ncu --set full capture summarised in profiles/r01_ncu_summary.md (section r01n;
-# N = 150 k; ncu flushes caches between kernels, so this is the cold-cache figure)
+# kernels, from the ncu launch list summarised in profiles/r01w_launches_summary.md (N = 150 k; ncu flushes
+# caches between kernels, so this is the cold-cache figure)
 MEASURED_TRAFFIC = {
-    "mssvt_block_attention_tc": int((20.164 + 0.010 + 60.632 + 3.090 + 16.533 + 0.0 + 28.210 + 1.183) * 1e6),
-    "mssvt_ffn_tc": int((77.180 + 29.050) * 1e6),
+    "mssvt_block_attention_tc": int((60.4 + 192.4 + 82.9 * 3 / 5) / 3 * 1e6),   # query + keys + projection, per block
+    "mssvt_ffn_tc": int(291.1 / 4 * 1e6),
 }
 
 
