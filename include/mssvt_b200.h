@@ -228,7 +228,7 @@ int mssvt_attention_tiles(int heads_per_group, int nq, int key_num_sample, int w
  * Supported: C = 64, two groups of 32 channels with 1, 2 or 4 heads each, nq <= 32,
  * key_num_sample <= 63, cap1 <= 128; -1 otherwise. */
 int mssvt_block_attention_tc(int C, int heads_per_group, int nq, int key_num_sample, int cap1, int interp,
-                             float scale, const float *win_cell, const float *range_min,
+                             int terms, float scale, const float *win_cell, const float *range_min,
                              const float *pos_w, const float *pos_b, const float *wq_packed, const float *bq0,
                              const float *bq1, const float *wkv0, const float *bkv0, const float *wkv1,
                              const float *bkv1, const float *wp_packed, const float *bp0, const float *bp1,
@@ -258,7 +258,7 @@ int mssvt_compress_tiles(int n1, int win_capacity, const int *win_count_total, c
  * packed by mssvt_pack_operand_tf32: wq / wp / pos2_w [64][64], wkv [128][64].  tiles .. win_ctr:
  * mssvt_compress_tiles.  scratch: 3 * win_capacity * 64 floats.
  * Supported: C = 64, one head group with 2, 4 or 8 heads, two-layer pos_proj, n1 <= 127; -1 otherwise. */
-int mssvt_compress_attention_tc(int C, int heads, int n1, float scale, const float *win_cell,
+int mssvt_compress_attention_tc(int C, int heads, int n1, int terms, float scale, const float *win_cell,
                                 const float *range_min, const float *pos_w, const float *pos_b,
                                 const float *pos2_w, const float *pos2_b, const float *wq, const float *bq,
                                 const float *wkv, const float *bkv, const float *wp, const float *bp,
@@ -275,9 +275,12 @@ int mssvt_ffn(const void *shape, int shape_bytes, const float *params, int num_r
 
 /* Packs a weight matrix w [n_rows][k] (nn.Linear layout, out x in) for the tensor-core entry points:
  * TF32 rounding + the K-major 8-row x 16-byte core-matrix layout tcgen05.mma reads from shared memory.
- * packed: n_rows * k floats.  n_rows % 8 == 0 and k % 8 == 0.  Done once per weight (the kernels then
+ * terms = 1: plain TF32, packed = n_rows * k floats.  terms = 3 ("3xTF32"): w = w_hi + w_lo with w_hi =
+ * tf32(w), w_lo = tf32(w - w_hi), packed = [hi | lo] = 2 * n_rows * k floats; the *_tc entry points called with
+ * terms = 3 split their activations the same way and issue A_hi W_hi + A_lo W_hi + A_hi W_lo per K step:
+ * fp32-grade results (~1e-6 relative) from the TF32 tensor pipe.  n_rows % 8 == 0 and k % 8 == 0.  Done once per weight (the kernels then
  * stage it with plain asynchronous copies); arguments documented as "packed" below take this form. */
-int mssvt_pack_operand_tf32(const float *w, int n_rows, int k, float *packed, void *stream);
+int mssvt_pack_operand_tf32(const float *w, int n_rows, int k, int terms, float *packed, void *stream);
 
 /* The same FFN on the tcgen05 tensor cores: TF32 operands, fp32 accumulation in TMEM, LayerNorm and
  * the residual stream in fp32 (mssvt_b200/csrc/ffn_tc.cu).  w1 [F][C] and w2 [C][F] (nn.Linear layout) packed by
@@ -287,7 +290,7 @@ int mssvt_pack_operand_tf32(const float *w, int n_rows, int k, float *packed, vo
  * query rows (scratch + 2 * num_voxels * 64 of that call), cap1 = max_num_win1.  Otherwise those 7 are ignored.
  * xn_next (optional, with next_ln_g / next_ln_b / next_eps): also writes LayerNorm(y) with the NEXT block's
  * norm1 parameters, which saves that block its own LayerNorm pass over y. */
-int mssvt_ffn_tc(int C, int F, int mode, float eps, const float *ln_g, const float *ln_b, const float *w1_packed,
+int mssvt_ffn_tc(int C, int F, int mode, int terms, float eps, const float *ln_g, const float *ln_b, const float *w1_packed,
                  const float *b1, const float *w2_packed, const float *b2, int num_rows, const int *num_rows_dev,
                  const float *x, const float *merged, const unsigned char *covered, float *y,
                  const float *next_ln_g, const float *next_ln_b, float next_eps, float *xn_next,

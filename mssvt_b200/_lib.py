@@ -43,13 +43,13 @@ _SIGNATURES = {
     "mssvt_layernorm": [I, P, I, P, P, P, F, P, P],
     "mssvt_block_attention": [P, I, P, I] + [P] * 11 + [P],
     "mssvt_attention_tiles": [I] * 4 + [P] * 10 + [P],
-    "mssvt_block_attention_tc": [I] * 6 + [F] + [P] * 14 + [I] + [P] * 17 + [I, P, P] + [P],
+    "mssvt_block_attention_tc": [I] * 7 + [F] + [P] * 14 + [I] + [P] * 17 + [I, P, P] + [P],
     "mssvt_compress_attention": [P, I, P, I] + [P] * 6 + [P],
     "mssvt_compress_tiles": [I, I] + [P] * 9 + [P],
-    "mssvt_compress_attention_tc": [I, I, I, F] + [P] * 12 + [I] + [P] * 11 + [P],
+    "mssvt_compress_attention_tc": [I, I, I, I, F] + [P] * 12 + [I] + [P] * 11 + [P],
     "mssvt_ffn": [P, I, P, I, P, P, P, P, P, P],
-    "mssvt_pack_operand_tf32": [P, I, I, P, P],
-    "mssvt_ffn_tc": [I, I, I, F] + [P] * 6 + [I, P, P, P, P, P, P, P, F, P] + [P] * 6 + [I, P],
+    "mssvt_pack_operand_tf32": [P, I, I, I, P, P],
+    "mssvt_ffn_tc": [I, I, I, I, F] + [P] * 6 + [I, P, P, P, P, P, P, P, F, P] + [P] * 6 + [I, P],
     "mssvt_dense_scatter": [I, P, I, I, I, I, I, P, P, P, P],
     "mssvt_sizeof_attn_shape": [],
     "mssvt_sizeof_ffn_shape": [],

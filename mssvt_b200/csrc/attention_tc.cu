@@ -169,8 +169,8 @@ __device__ __forceinline__ int tile_window(const int *off, int n, int v) {
     return lo;
 }
 
-template <int HEADS>
-__global__ void __launch_bounds__(TCA_THREADS, 5)
+template <int HEADS, int TERMS>
+__global__ void __launch_bounds__(TCA_THREADS, TERMS == 3 ? 3 : 5)
 k_tca_keys(TcAttnParams P, int win_cap, const int2 *__restrict__ tiles, const int *__restrict__ tile_count,
            const int4 *__restrict__ win_rec, const float4 *__restrict__ win_ctr, const float *__restrict__ xn,
            const float *__restrict__ xyz, const int *__restrict__ rep_row, const float *__restrict__ Qbuf,
@@ -195,10 +195,13 @@ k_tca_keys(TcAttnParams P, int win_cap, const int2 *__restrict__ tiles, const in
     win_rec += (size_t)g * win_cap;
 
     // ---- shared memory: 8 KB weights + 18 KB A/V (aliased) + 8 KB scores + bookkeeping = ~38 KB
-    char *sWkv = smem_raw;                                  // [64 x 32] canonical, TF32           8 KB
-    char *sA = sWkv + 64 * 32 * 4;                          // [128 x 32] canonical (16 KB) ...
+    constexpr int NT = TERMS == 3 ? 2 : 1;                  // operand tiles: hi [, lo] (3xTF32, tc_common.cuh)
+    constexpr int A_TILE = TCA_THREADS * TCA_SD * 4;        // 16 KB
+    constexpr int A_REGION = NT * A_TILE > TCA_THREADS * TCA_VPITCH * 4 ? NT * A_TILE : TCA_THREADS * TCA_VPITCH * 4;
+    char *sWkv = smem_raw;                                  // NT x [64 x 32] canonical, TF32      8 KB each
+    char *sA = sWkv + NT * 64 * 32 * 4;                     // NT x [128 x 32] canonical (16 KB each) ...
     float *sV = (float *)sA;                                // ... reused as V [128][VPITCH] after the MMA
-    float *sPos = sV + TCA_THREADS * TCA_VPITCH;            // [32][8] (this scale's channels)
+    float *sPos = (float *)(sA + A_REGION);                 // [32][8] (this scale's channels)
     float *sBkv = sPos + 32 * 8;                            // [64]
     float *sS = sBkv + 64;                                  // [SBUD] scores: window-major, [key][query][head]
     float4 *sCtr = (float4 *)(sS + TCA_SBUD);               // [TW] window centres
@@ -208,7 +211,7 @@ k_tca_keys(TcAttnParams P, int win_cap, const int2 *__restrict__ tiles, const in
     uint64_t *sBar = (uint64_t *)(sQoff + TCA_TW + 1);      // (2 * (TW + 1) ints: 8-byte aligned)
     uint32_t *sTmem = (uint32_t *)(sBar + 1);
 
-    stage_packed(P.wkv[g], 64 * 32, sWkv);
+    stage_packed(P.wkv[g], NT * 64 * 32, sWkv);
     for (int i = tid; i < 32 * 8; i += TCA_THREADS) {
         const int c = g * TCA_SD + (i >> 3), k = i & 7;
         sPos[i] = k < 6 ? __ldg(P.pos_w + c * 6 + k) : k == 6 ? __ldg(P.pos_b + c) : 0.f;
@@ -295,12 +298,14 @@ k_tca_keys(TcAttnParams P, int win_cap, const int2 *__restrict__ tiles, const in
 #pragma unroll
                 for (int c4 = 0; c4 < TCA_SD / 4; ++c4) {
                     const float4 v = xv[c4];
-                    float4 o;
-                    o.x = to_tf32(v.x + pos_embed8(sPos, 4 * c4, rx, ry, rz, ctr.x, ctr.y, ctr.z));
-                    o.y = to_tf32(v.y + pos_embed8(sPos, 4 * c4 + 1, rx, ry, rz, ctr.x, ctr.y, ctr.z));
-                    o.z = to_tf32(v.z + pos_embed8(sPos, 4 * c4 + 2, rx, ry, rz, ctr.x, ctr.y, ctr.z));
-                    o.w = to_tf32(v.w + pos_embed8(sPos, 4 * c4 + 3, rx, ry, rz, ctr.x, ctr.y, ctr.z));
-                    *(float4 *)(sA + (uint32_t)c4 * a_lbo + my_row_off) = o;
+                    float4 o, hi, lo;
+                    o.x = v.x + pos_embed8(sPos, 4 * c4, rx, ry, rz, ctr.x, ctr.y, ctr.z);
+                    o.y = v.y + pos_embed8(sPos, 4 * c4 + 1, rx, ry, rz, ctr.x, ctr.y, ctr.z);
+                    o.z = v.z + pos_embed8(sPos, 4 * c4 + 2, rx, ry, rz, ctr.x, ctr.y, ctr.z);
+                    o.w = v.w + pos_embed8(sPos, 4 * c4 + 3, rx, ry, rz, ctr.x, ctr.y, ctr.z);
+                    split_tf32(o, hi, lo);
+                    *(float4 *)(sA + (uint32_t)c4 * a_lbo + my_row_off) = hi;
+                    if (TERMS == 3) *(float4 *)(sA + A_TILE + (uint32_t)c4 * a_lbo + my_row_off) = lo;
                 }
             }
         }
@@ -313,11 +318,9 @@ k_tca_keys(TcAttnParams P, int win_cap, const int2 *__restrict__ tiles, const in
         if (tid == 0) {
             tc_fence_after();
 #pragma unroll
-            for (int k = 0; k < TCA_SD / 8; ++k) {
-                const uint64_t da = umma_smem_desc(sA_u + (uint32_t)k * 2u * a_lbo, a_lbo, 128);
-                const uint64_t db = umma_smem_desc(sWkv_u + (uint32_t)k * 2u * w_lbo, w_lbo, 128);
-                umma_tf32(tmem_d, da, db, idesc, k > 0 ? 1u : 0u);
-            }
+            for (int k = 0; k < TCA_SD / 8; ++k)
+                umma_step<TERMS>(tmem_d, sA_u + (uint32_t)k * 2u * a_lbo, a_lbo, A_TILE,
+                                 sWkv_u + (uint32_t)k * 2u * w_lbo, w_lbo, 64 * 32 * 4, idesc, k == 0);
             umma_commit(bar);
         }
         if (t + stride < T) {  // next tile: window records (16 B each), centres, key lists (K ints per window)
@@ -468,8 +471,11 @@ k_tca_merge(TcAttnParams P, int win_cap, const int *__restrict__ win_count_total
     }
 }
 
-static size_t tca_keys_smem_bytes() {
-    return 64 * 32 * 4 + (size_t)(TCA_THREADS * TCA_VPITCH + 32 * 8 + 64 + TCA_SBUD) * 4 + TCA_TW * 32 +
+static size_t tca_keys_smem_bytes(int terms) {
+    const size_t nt = terms == 3 ? 2 : 1;
+    size_t a_region = nt * TCA_THREADS * TCA_SD * 4;
+    if (a_region < (size_t)TCA_THREADS * TCA_VPITCH * 4) a_region = (size_t)TCA_THREADS * TCA_VPITCH * 4;
+    return nt * 64 * 32 * 4 + a_region + (size_t)(32 * 8 + 64 + TCA_SBUD) * 4 + TCA_TW * 32 +
            2 * (TCA_TW + 1) * 4 + 8 + 16 + 128;
 }
 
@@ -516,7 +522,7 @@ int mssvt_attention_tiles(int heads_per_group, int nq, int key_num_sample, int w
  * Returns MSSVT_ERR_INVALID for shapes outside C = 64 / 2 x 32 channels / nq <= 32 / K <= 63 /
  * cap1 <= 128 (callers then use mssvt_block_attention). */
 int mssvt_block_attention_tc(int C, int heads_per_group, int nq, int key_num_sample, int cap1, int interp,
-                             float scale, const float *win_cell, const float *range_min,
+                             int terms, float scale, const float *win_cell, const float *range_min,
                              const float *pos_w, const float *pos_b, const float *wq_packed, const float *bq0,
                              const float *bq1, const float *wkv0, const float *bkv0, const float *wkv1,
                              const float *bkv1, const float *wp_packed, const float *bp0, const float *bp1,
@@ -528,7 +534,7 @@ int mssvt_block_attention_tc(int C, int heads_per_group, int nq, int key_num_sam
                              const float *win_ctr, int num_voxels, float *scratch, float *merged, void *stream) {
     if (C != 64 || (heads_per_group != 1 && heads_per_group != 2 && heads_per_group != 4) || nq <= 0 || nq > 32 ||
         key_num_sample <= 0 || key_num_sample > 63 || cap1 <= 0 || cap1 > 128 || win_capacity < 0 || num_voxels < 0 ||
-        nq * (key_num_sample + 1) * heads_per_group > TCA_SBUD)
+        nq * (key_num_sample + 1) * heads_per_group > TCA_SBUD || (terms != 1 && terms != 3))
         return MSSVT_ERR_INVALID;
     if (win_capacity == 0) return MSSVT_OK;
     if (!win_cell || !range_min || !pos_w || !pos_b || !wq_packed || !bq0 || !wkv0 || !bkv0 || !wp_packed || !bp0 ||
@@ -546,7 +552,7 @@ int mssvt_block_attention_tc(int C, int heads_per_group, int nq, int key_num_sam
     P.pos_w = pos_w; P.pos_b = pos_b;
     P.wq = wq_packed; P.bq[0] = bq0; P.wkv[0] = wkv0; P.bkv[0] = bkv0; P.wp = wp_packed; P.bp[0] = bp0;
     P.bq[1] = bq1; P.wkv[1] = wkv1; P.bkv[1] = bkv1; P.bp[1] = bp1;
-    const size_t smem = tca_keys_smem_bytes();
+    const size_t smem = tca_keys_smem_bytes(terms);
     float *Qbuf = scratch, *Obuf = scratch + (size_t)num_voxels * 64, *Pbuf = scratch + 2 * (size_t)num_voxels * 64;
     cudaStream_t s = (cudaStream_t)stream;
     const int4 *wl = (const int4 *)win_list;
@@ -559,26 +565,32 @@ int mssvt_block_attention_tc(int C, int heads_per_group, int nq, int key_num_sam
         rows.pos_w = pos_w; rows.pos_b = pos_b; rows.win_count_total = win_count_total; rows.win_list = wl;
         rows.xn = xn; rows.xyz = xyz; rows.q_row = q_row; rows.q_base = q_base; rows.q_src = q_src;
         const TclParams L = {wq_packed, bq0, bq1, scale};
-        tcl_launch(L, rows, num_voxels, Qbuf, s);
+        tcl_launch(L, rows, num_voxels, Qbuf, s, terms);
     }
 
     int per_sm = (int)(227 * 1024 / (smem + 1024));
-    per_sm = per_sm > 5 ? 5 : per_sm < 1 ? 1 : per_sm;  // (64 TMEM columns each)
+    per_sm = per_sm > (terms == 3 ? 3 : 5) ? (terms == 3 ? 3 : 5) : per_sm < 1 ? 1 : per_sm;  // (64 TMEM columns each)
     const int grid = MSSVT_NUM_SMS * per_sm;
     ++g_launches;
-#define TCA_LAUNCH(H)                                                                                      \
-    cudaFuncSetAttribute(k_tca_keys<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
-    launch_pdl(k_tca_keys<H>, dim3(grid), dim3(TCA_THREADS), smem, s, P, win_capacity, (const int2 *)tiles,   \
+#define TCA_LAUNCH(H, T)                                                                                   \
+    cudaFuncSetAttribute(k_tca_keys<H, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
+    launch_pdl(k_tca_keys<H, T>, dim3(grid), dim3(TCA_THREADS), smem, s, P, win_capacity, (const int2 *)tiles, \
                tile_count, (const int4 *)win_rec, (const float4 *)win_ctr, xn, xyz, rep_row, Qbuf, Obuf)
-    if (heads_per_group == 1) { TCA_LAUNCH(1); }
-    else if (heads_per_group == 2) { TCA_LAUNCH(2); }
-    else { TCA_LAUNCH(4); }
+    if (terms == 3) {
+        if (heads_per_group == 1) { TCA_LAUNCH(1, 3); }
+        else if (heads_per_group == 2) { TCA_LAUNCH(2, 3); }
+        else { TCA_LAUNCH(4, 3); }
+    } else {
+        if (heads_per_group == 1) { TCA_LAUNCH(1, 1); }
+        else if (heads_per_group == 2) { TCA_LAUNCH(2, 1); }
+        else { TCA_LAUNCH(4, 1); }
+    }
 #undef TCA_LAUNCH
 
     {
         const TclCopyRows rows = {Obuf, win_count_total, q_base, win_capacity};
         const TclParams L = {wp_packed, bp0, bp1, 1.0f};
-        tcl_launch(L, rows, num_voxels, Pbuf, s);
+        tcl_launch(L, rows, num_voxels, Pbuf, s, terms);
     }
     if (!merged) return check_launch();  // interpolation + merge left to mssvt_ffn_tc (mode 2)
     ++g_launches;

@@ -134,8 +134,8 @@ __device__ __forceinline__ int tcc_tile_window(const int *off, int n, int v) {
 
 // 256 threads per tile of 128 key tasks: threads t and t + 128 share task row t = TMEM lane t and own one
 // half of the channels / of the heads each (HEADS >= 2)
-template <int HEADS>
-__global__ void __launch_bounds__(TCC_THREADS, 2)
+template <int HEADS, int TERMS>
+__global__ void __launch_bounds__(TCC_THREADS, TERMS == 3 ? 1 : 2)
 k_tcc_keys(TccParams P, const int2 *__restrict__ tiles, const int *__restrict__ tile_count,
            const int *__restrict__ win_rec, const float4 *__restrict__ win_ctr, const float *__restrict__ xn,
            const float *__restrict__ xyz, const int *__restrict__ k_row, const float *__restrict__ Qc,
@@ -149,11 +149,14 @@ k_tcc_keys(TccParams P, const int2 *__restrict__ tiles, const int *__restrict__ 
     const int r = tid & (TCC_ROWS - 1), half = tid >> 7;
     const int n1 = P.n1;
 
-    char *sW2 = smem_raw;                                   // [64 x 64] canonical TF32    16 KB
-    char *sWkv = sW2 + 64 * 64 * 4;                         // [128 x 64] canonical TF32   32 KB
-    char *sA = sWkv + 128 * 64 * 4;                         // [128 x 64] canonical (32 KB) ...
+    constexpr int NT = TERMS == 3 ? 2 : 1;                  // operand tiles: hi [, lo] (3xTF32, tc_common.cuh)
+    constexpr int A_TILE = TCC_ROWS * TCC_C * 4;            // 32 KB
+    constexpr int A_REGION = NT * A_TILE > TCC_ROWS * TCC_VPITCH * 4 ? NT * A_TILE : TCC_ROWS * TCC_VPITCH * 4;
+    char *sW2 = smem_raw;                                   // NT x [64 x 64] canonical TF32    16 KB each
+    char *sWkv = sW2 + NT * 64 * 64 * 4;                    // NT x [128 x 64] canonical TF32   32 KB each
+    char *sA = sWkv + NT * 128 * 64 * 4;                    // NT x [128 x 64] canonical (32 KB each) ...
     float *sV = (float *)sA;                                // ... reused as V [128][VPITCH] (34 KB)
-    float *sPos = sV + TCC_ROWS * TCC_VPITCH;               // [64][8]
+    float *sPos = (float *)(sA + A_REGION);                 // [64][8]
     float *sB2 = sPos + 64 * 8;                             // [64]
     float *sBkv = sB2 + 64;                                 // [128]
     float *sS = sBkv + 128;                                 // [128][HEADS] scores
@@ -163,8 +166,8 @@ k_tcc_keys(TccParams P, const int2 *__restrict__ tiles, const int *__restrict__ 
     uint64_t *sBar = (uint64_t *)(sToff + TCC_TW + 2);
     uint32_t *sTmem = (uint32_t *)(sBar + 1);
 
-    stage_packed(P.pos2_w, 64 * 64, sW2);
-    stage_packed(P.wkv, 128 * 64, sWkv);
+    stage_packed(P.pos2_w, NT * 64 * 64, sW2);
+    stage_packed(P.wkv, NT * 128 * 64, sWkv);
     for (int i = tid; i < 64 * 8; i += TCC_THREADS) {
         const int c = i >> 3, k = i & 7;
         sPos[i] = k < 6 ? __ldg(P.pos_w + c * 6 + k) : k == 6 ? __ldg(P.pos_b + c) : 0.f;
@@ -243,9 +246,12 @@ k_tcc_keys(TccParams P, const int2 *__restrict__ tiles, const int *__restrict__ 
                     float a = wb.z;
                     a = fmaf(wa.x, rx, a); a = fmaf(wa.y, ry, a); a = fmaf(wa.z, rz, a);
                     a = fmaf(wa.w, ctr.x, a); a = fmaf(wb.x, ctr.y, a); a = fmaf(wb.y, ctr.z, a);
-                    o[k] = to_tf32(fmaxf(a, 0.f));
+                    o[k] = fmaxf(a, 0.f);
                 }
-                *(float4 *)(sA + (uint32_t)(8 * half + c4) * a_lbo + my_row_off) = make_float4(o[0], o[1], o[2], o[3]);
+                float4 hi, lo;
+                split_tf32(make_float4(o[0], o[1], o[2], o[3]), hi, lo);
+                *(float4 *)(sA + (uint32_t)(8 * half + c4) * a_lbo + my_row_off) = hi;
+                if (TERMS == 3) *(float4 *)(sA + A_TILE + (uint32_t)(8 * half + c4) * a_lbo + my_row_off) = lo;
             }
         }
         stage_packed_wait();
@@ -255,8 +261,8 @@ k_tcc_keys(TccParams P, const int2 *__restrict__ tiles, const int *__restrict__ 
             tc_fence_after();
 #pragma unroll
             for (int k = 0; k < TCC_C / 8; ++k)
-                umma_tf32(tmem_d1, umma_smem_desc(sA_u + (uint32_t)k * 2u * a_lbo, a_lbo, 128),
-                          umma_smem_desc(sW2_u + (uint32_t)k * 2u * w2_lbo, w2_lbo, 128), idesc1, k > 0 ? 1u : 0u);
+                umma_step<TERMS>(tmem_d1, sA_u + (uint32_t)k * 2u * a_lbo, a_lbo, A_TILE,
+                                 sW2_u + (uint32_t)k * 2u * w2_lbo, w2_lbo, 64 * 64 * 4, idesc1, k == 0);
             umma_commit(bar);
         }
         mbar_wait(bar, phase);
@@ -270,12 +276,14 @@ k_tcc_keys(TccParams P, const int2 *__restrict__ tiles, const int *__restrict__ 
                 const float *b2 = sB2 + 32 * half;
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
-                    float4 v;
-                    v.x = to_tf32(f[q].x + fmaxf(d[4 * q] + b2[4 * q], 0.f));
-                    v.y = to_tf32(f[q].y + fmaxf(d[4 * q + 1] + b2[4 * q + 1], 0.f));
-                    v.z = to_tf32(f[q].z + fmaxf(d[4 * q + 2] + b2[4 * q + 2], 0.f));
-                    v.w = to_tf32(f[q].w + fmaxf(d[4 * q + 3] + b2[4 * q + 3], 0.f));
-                    *(float4 *)(sA + (uint32_t)(8 * half + q) * a_lbo + my_row_off) = v;
+                    float4 v, hi, lo;
+                    v.x = f[q].x + fmaxf(d[4 * q] + b2[4 * q], 0.f);
+                    v.y = f[q].y + fmaxf(d[4 * q + 1] + b2[4 * q + 1], 0.f);
+                    v.z = f[q].z + fmaxf(d[4 * q + 2] + b2[4 * q + 2], 0.f);
+                    v.w = f[q].w + fmaxf(d[4 * q + 3] + b2[4 * q + 3], 0.f);
+                    split_tf32(v, hi, lo);
+                    *(float4 *)(sA + (uint32_t)(8 * half + q) * a_lbo + my_row_off) = hi;
+                    if (TERMS == 3) *(float4 *)(sA + A_TILE + (uint32_t)(8 * half + q) * a_lbo + my_row_off) = lo;
                 }
             }
         }
@@ -286,8 +294,8 @@ k_tcc_keys(TccParams P, const int2 *__restrict__ tiles, const int *__restrict__ 
             tc_fence_after();
 #pragma unroll
             for (int k = 0; k < TCC_C / 8; ++k)
-                umma_tf32(tmem_d2, umma_smem_desc(sA_u + (uint32_t)k * 2u * a_lbo, a_lbo, 128),
-                          umma_smem_desc(sWkv_u + (uint32_t)k * 2u * wkv_lbo, wkv_lbo, 128), idesc2, k > 0 ? 1u : 0u);
+                umma_step<TERMS>(tmem_d2, sA_u + (uint32_t)k * 2u * a_lbo, a_lbo, A_TILE,
+                                 sWkv_u + (uint32_t)k * 2u * wkv_lbo, wkv_lbo, 128 * 64 * 4, idesc2, k == 0);
             umma_commit(bar);
         }
         mbar_wait(bar, phase);
@@ -358,8 +366,11 @@ k_tcc_keys(TccParams P, const int2 *__restrict__ tiles, const int *__restrict__ 
     if (warp == 0) tmem_dealloc(tmem_base, 256);
 }
 
-static size_t tcc_keys_smem_bytes(int heads) {
-    return 64 * 64 * 4 + 128 * 64 * 4 + (size_t)(TCC_ROWS * TCC_VPITCH + 64 * 8 + 64 + 128 + TCC_ROWS * heads) * 4 +
+static size_t tcc_keys_smem_bytes(int heads, int terms) {
+    const size_t nt = terms == 3 ? 2 : 1;
+    size_t a_region = nt * TCC_ROWS * TCC_C * 4;
+    if (a_region < (size_t)TCC_ROWS * TCC_VPITCH * 4) a_region = (size_t)TCC_ROWS * TCC_VPITCH * 4;
+    return nt * (64 * 64 * 4 + 128 * 64 * 4) + a_region + (size_t)(64 * 8 + 64 + 128 + TCC_ROWS * heads) * 4 +
            TCC_TW * 16 + (2 * TCC_TW + 2) * 4 + 8 + 16 + 128;
 }
 
@@ -397,7 +408,7 @@ int mssvt_compress_tiles(int n1, int win_capacity, const int *win_count_total, c
  * wkv [128][64].  k_row: (cap, n1) global rows from mssvt_window_rows; tiles .. win_ctr: mssvt_compress_tiles.
  * scratch: 3 * win_capacity * 64 floats.  out: (cap, 64).
  * Supported: C = 64, one head group with 2, 4 or 8 heads, n1 <= 127; -1 otherwise. */
-int mssvt_compress_attention_tc(int C, int heads, int n1, float scale, const float *win_cell,
+int mssvt_compress_attention_tc(int C, int heads, int n1, int terms, float scale, const float *win_cell,
                                 const float *range_min, const float *pos_w, const float *pos_b,
                                 const float *pos2_w, const float *pos2_b, const float *wq, const float *bq,
                                 const float *wkv, const float *bkv, const float *wp, const float *bp,
@@ -405,7 +416,8 @@ int mssvt_compress_attention_tc(int C, int heads, int n1, float scale, const flo
                                 const float *xn, const float *xyz, const int *k_row, const int *tiles_in,
                                 const int *tile_count, const int *win_rec, const float *win_ctr_in, float *scratch,
                                 float *out, void *stream) {
-    if (C != 64 || (heads != 2 && heads != 4 && heads != 8) || n1 <= 0 || n1 > 127 || win_capacity < 0)
+    if (C != 64 || (heads != 2 && heads != 4 && heads != 8) || n1 <= 0 || n1 > 127 || win_capacity < 0 ||
+        (terms != 1 && terms != 3))
         return MSSVT_ERR_INVALID;
     if (win_capacity == 0) return MSSVT_OK;
     if (!win_cell || !range_min || !pos_w || !pos_b || !pos2_w || !pos2_b || !wq || !bq || !wkv || !bkv || !wp || !bp ||
@@ -428,27 +440,33 @@ int mssvt_compress_attention_tc(int C, int heads, int n1, float scale, const flo
     {
         const TclCopyRows rows = {pooled, win_count_total, nullptr, win_capacity};
         const TclParams L = {wq, bq, nullptr, scale};
-        tcl_launch(L, rows, win_capacity, Qc, s);
+        tcl_launch(L, rows, win_capacity, Qc, s, terms);
     }
 
-    const size_t smem = tcc_keys_smem_bytes(heads);
+    const size_t smem = tcc_keys_smem_bytes(heads, terms);
     if (smem > 227 * 1024) return MSSVT_ERR_INVALID;
     const int per_sm = smem <= 110 * 1024 ? 2 : 1;  // 2 x 256 TMEM columns = all 512
     const int grid = MSSVT_NUM_SMS * per_sm;
     ++g_launches;
-#define TCC_LAUNCH(H)                                                                                     \
-    cudaFuncSetAttribute(k_tcc_keys<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
-    launch_pdl(k_tcc_keys<H>, dim3(grid), dim3(TCC_THREADS), smem, s, P, tiles, tile_count, win_rec, win_ctr, xn, xyz,   \
-               k_row, (const float *)Qc, Oc)
-    if (heads == 2) { TCC_LAUNCH(2); }
-    else if (heads == 4) { TCC_LAUNCH(4); }
-    else { TCC_LAUNCH(8); }
+#define TCC_LAUNCH(H, T)                                                                                  \
+    cudaFuncSetAttribute(k_tcc_keys<H, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
+    launch_pdl(k_tcc_keys<H, T>, dim3(grid), dim3(TCC_THREADS), smem, s, P, tiles, tile_count, win_rec, win_ctr, xn, \
+               xyz, k_row, (const float *)Qc, Oc)
+    if (terms == 3) {
+        if (heads == 2) { TCC_LAUNCH(2, 3); }
+        else if (heads == 4) { TCC_LAUNCH(4, 3); }
+        else { TCC_LAUNCH(8, 3); }
+    } else {
+        if (heads == 2) { TCC_LAUNCH(2, 1); }
+        else if (heads == 4) { TCC_LAUNCH(4, 1); }
+        else { TCC_LAUNCH(8, 1); }
+    }
 #undef TCC_LAUNCH
 
     {
         const TclCopyRows rows = {Oc, win_count_total, nullptr, win_capacity};
         const TclParams L = {wp, bp, nullptr, 1.0f};
-        tcl_launch(L, rows, win_capacity, out, s);
+        tcl_launch(L, rows, win_capacity, out, s, terms);
     }
     return check_launch();
 }

@@ -202,6 +202,30 @@ __device__ __forceinline__ void warp_rows_store(char *stg, float4 *my_dst, const
 
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
+// ---- "3xTF32": a = a_hi + a_lo with a_hi = tf32(a), a_lo = tf32(a - a_hi) (and the same for the weights);
+// A W^T ~= A_hi W_hi^T + A_lo W_hi^T + A_hi W_lo^T with fp32 accumulation carries ~21 mantissa bits -- fp32-grade
+// results (measured ~1e-6 relative) from the TF32 tensor pipe at three MMAs per K step.  Kernels are
+// templated on TERMS (1: plain TF32, 3: split operands); operand tiles come in (hi, lo) pairs, packed weights
+// as [hi | lo] (mssvt_pack_operand_tf32 with terms = 3).
+__device__ __forceinline__ void split_tf32(float v, float &hi, float &lo) {
+    hi = to_tf32(v);
+    lo = to_tf32(v - hi);
+}
+__device__ __forceinline__ void split_tf32(const float4 &v, float4 &hi, float4 &lo) {
+    split_tf32(v.x, hi.x, lo.x); split_tf32(v.y, hi.y, lo.y); split_tf32(v.z, hi.z, lo.z); split_tf32(v.w, hi.w, lo.w);
+}
+// one K = 8 step of D (+)= A B^T from shared-memory operands, TERMS MMAs; *_lo = byte offset of the lo tile
+template <int TERMS>
+__device__ __forceinline__ void umma_step(uint32_t d, uint32_t a_addr, uint32_t a_lbo, uint32_t a_lo, uint32_t b_addr,
+                                          uint32_t b_lbo, uint32_t b_lo, uint32_t idesc, bool first) {
+    const uint64_t ah = umma_smem_desc(a_addr, a_lbo, 128), bh = umma_smem_desc(b_addr, b_lbo, 128);
+    umma_tf32(d, ah, bh, idesc, first ? 0u : 1u);
+    if (TERMS == 3) {
+        umma_tf32(d, umma_smem_desc(a_addr + a_lo, a_lbo, 128), bh, idesc, 1u);
+        umma_tf32(d, ah, umma_smem_desc(b_addr + b_lo, b_lbo, 128), idesc, 1u);
+    }
+}
+
 // Weight operands are packed ONCE (mssvt_pack_operand_tf32: canonical K-major layout, TF32-rounded) and
 // then only copied: asynchronous 16-byte copies global -> shared, no registers, no per-CTA conversion.
 // Call stage_packed_wait() before the fence.proxy.async / barrier that precedes the first MMA.

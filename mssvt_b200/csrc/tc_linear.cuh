@@ -23,7 +23,9 @@ struct TclParams {
     float mul;
 };
 
-static inline size_t tcl_smem_bytes() { return TCL_ROWS * TCL_C * 4 + TCL_C * TCL_C * 4 + TCL_C * 4 + 2048 + 8 + 16 + 128; }
+static inline size_t tcl_smem_bytes(int terms) {
+    return (size_t)(terms == 3 ? 2 : 1) * (TCL_ROWS * TCL_C * 4 + TCL_C * TCL_C * 4) + TCL_C * 4 + 2048 + 8 + 16 + 128;
+}
 
 // Producer: struct with
 //   __device__ void init(float *s_extra)            cooperative, before the first barrier (s_extra: 2 KB)
@@ -49,21 +51,22 @@ struct TclCopyRows {
     }
     __device__ void finish(const Ctx &, int, const float *, float *) const {}
 };
-template <class Producer>
-__global__ void __launch_bounds__(TCL_THREADS, 4)
+template <class Producer, int TERMS>
+__global__ void __launch_bounds__(TCL_THREADS, TERMS == 3 ? 2 : 4)
 k_tc_linear(TclParams P, Producer prod, float *__restrict__ out) {
+    constexpr int NT = TERMS == 3 ? 2 : 1;     // operand tiles: hi [, lo]
     extern __shared__ __align__(128) char smem_raw[];
     pdl_launch_dependents();
     const int tid = threadIdx.x, warp = tid >> 5;
     const int r = tid & (TCL_ROWS - 1), half = tid >> 7;
-    char *sA = smem_raw;                           // [16][128][16 B]
-    char *sW = sA + TCL_ROWS * TCL_C * 4;          // [16][64][16 B]
-    float *sB = (float *)(sW + TCL_C * TCL_C * 4); // [64]
+    char *sA = smem_raw;                           // NT x [16][128][16 B]
+    char *sW = sA + NT * TCL_ROWS * TCL_C * 4;     // NT x [16][64][16 B]
+    float *sB = (float *)(sW + NT * TCL_C * TCL_C * 4); // [64]
     float *sExtra = sB + TCL_C;                    // producer scratch (2 KB)
     uint64_t *sBar = (uint64_t *)(sExtra + 512);
     uint32_t *sTmem = (uint32_t *)(sBar + 1);
 
-    stage_packed(P.w_packed, TCL_C * TCL_C, sW);
+    stage_packed(P.w_packed, NT * TCL_C * TCL_C, sW);
     if (tid < TCL_C) sB[tid] = P.bias_hi && tid >= 32 ? __ldg(P.bias_hi + tid - 32) : __ldg(P.bias + tid);
     prod.init(sExtra);
     const uint32_t bar = smem_u32(sBar);
@@ -101,9 +104,12 @@ k_tc_linear(TclParams P, Producer prod, float *__restrict__ out) {
         }
         __syncthreads();  // the staging areas alias the A tile: every warp is done reading before A is written
 #pragma unroll
-        for (int c = 0; c < 8; ++c)
-            *(float4 *)(sA + (uint32_t)(half * 8 + c) * a_lbo + my_row_off) =
-                make_float4(to_tf32(in[4 * c]), to_tf32(in[4 * c + 1]), to_tf32(in[4 * c + 2]), to_tf32(in[4 * c + 3]));
+        for (int c = 0; c < 8; ++c) {
+            float4 hi, lo;
+            split_tf32(make_float4(in[4 * c], in[4 * c + 1], in[4 * c + 2], in[4 * c + 3]), hi, lo);
+            *(float4 *)(sA + (uint32_t)(half * 8 + c) * a_lbo + my_row_off) = hi;
+            if (TERMS == 3) *(float4 *)(sA + TCL_ROWS * TCL_C * 4 + (uint32_t)(half * 8 + c) * a_lbo + my_row_off) = lo;
+        }
         stage_packed_wait();
         fence_async_smem();
         __syncthreads();
@@ -111,8 +117,8 @@ k_tc_linear(TclParams P, Producer prod, float *__restrict__ out) {
             tc_fence_after();
 #pragma unroll
             for (int k = 0; k < TCL_C / 8; ++k)
-                umma_tf32(tmem_d, umma_smem_desc(sA_u + (uint32_t)k * 2u * a_lbo, a_lbo, 128),
-                          umma_smem_desc(sW_u + (uint32_t)k * 2u * w_lbo, w_lbo, 128), idesc, k > 0 ? 1u : 0u);
+                umma_step<TERMS>(tmem_d, sA_u + (uint32_t)k * 2u * a_lbo, a_lbo, TCL_ROWS * TCL_C * 4,
+                                 sW_u + (uint32_t)k * 2u * w_lbo, w_lbo, TCL_C * TCL_C * 4, idesc, k == 0);
             umma_commit(bar);
         }
         mbar_wait(bar, phase);
@@ -135,16 +141,24 @@ k_tc_linear(TclParams P, Producer prod, float *__restrict__ out) {
     if (warp == 0) tmem_dealloc(tmem_d, 64);
 }
 
-template <class Producer>
-static inline void tcl_launch(const TclParams &P, const Producer &prod, int row_capacity, float *out, cudaStream_t s) {
-    const size_t smem = tcl_smem_bytes();
+template <class Producer, int TERMS>
+static inline void tcl_launch_t(const TclParams &P, const Producer &prod, int row_capacity, float *out, cudaStream_t s) {
+    const size_t smem = tcl_smem_bytes(TERMS);
     int tiles = (row_capacity + TCL_ROWS - 1) / TCL_ROWS;
-    int grid = MSSVT_NUM_SMS * 4;
+    int grid = MSSVT_NUM_SMS * (TERMS == 3 ? 2 : 4);
     if (grid > tiles) grid = tiles;
     if (grid < 1) return;
-    cudaFuncSetAttribute(k_tc_linear<Producer>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_tc_linear<Producer, TERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     ++g_launches;
-    launch_pdl(k_tc_linear<Producer>, dim3(grid), dim3(TCL_THREADS), smem, s, P, prod, out);
+    launch_pdl(k_tc_linear<Producer, TERMS>, dim3(grid), dim3(TCL_THREADS), smem, s, P, prod, out);
+}
+
+// terms = 1: TF32 operands; terms = 3: split operands (w_packed = [hi | lo])
+template <class Producer>
+static inline void tcl_launch(const TclParams &P, const Producer &prod, int row_capacity, float *out, cudaStream_t s,
+                              int terms = 1) {
+    if (terms == 3) tcl_launch_t<Producer, 3>(P, prod, row_capacity, out, s);
+    else tcl_launch_t<Producer, 1>(P, prod, row_capacity, out, s);
 }
 
 }  // namespace mssvt

@@ -16,7 +16,7 @@ for seed, n, crop in ((0, 4000, 0.17), (3, 20000, 0.38)):
     with torch.no_grad():
         want = orc.backbone_forward(state, cfg, list(S0_GRID), list(S0_VOXEL), list(S0_RANGE), feats, coords, 1)
     model = model.cuda().eval()
-    for prec in ("fp32", "tf32"):
+    for prec in ("fp32", "tf32x3", "tf32"):
         model.set_precision(prec)
         with torch.no_grad():
             sp = model({"voxel_features": feats.cuda(), "voxel_coords": coords.cuda().float(), "batch_size": 1})["encoded_spconv_tensor"]

@@ -33,9 +33,12 @@ def to_local(rows, win_b, v_start):
     return torch.where(rows >= 0, rows - base, rows)
 
 
+@pytest.mark.parametrize("precision", ["fp32", "tf32x3"])
 @pytest.mark.parametrize("name", GOLDEN_CASES)
-def test_backbone_matches_reference_golden(name):
+def test_backbone_matches_reference_golden(name, precision):
+    """both fp32-grade modes: FFMA kernels and split-operand tensor-core kernels (the default)"""
     blob, cfg, state = load_golden(name)
+    cfg["PRECISION"] = precision
     feats, coords = torch.from_numpy(blob["voxel_features"]), torch.from_numpy(blob["voxel_coords"])
     model, sp = run_product(cfg, state, blob["grid"], blob["pc_range"], feats, coords, int(blob["batch_size"]))
     assert torch.equal(sp.indices.cpu(), torch.from_numpy(blob["out_indices"]))
@@ -311,7 +314,7 @@ def test_tf32_mode_vs_live_oracle_20k_and_fp32_mode_150k():
 
 
 @pytest.mark.parametrize("n", [1, 37, 300])
-def test_tiny_frames_in_both_modes(n):
+def test_tiny_frames_in_every_mode(n):
     """a handful of voxels: single windows, tiles with one task, grids smaller than the SM count"""
     feats, coords = synth_frame(11, n, crop=0.05)
     feats, coords = torch.from_numpy(feats), torch.from_numpy(coords)
@@ -322,7 +325,7 @@ def test_tiny_frames_in_both_modes(n):
     with torch.no_grad():
         want = orc.backbone_forward(state, cfg, list(S0_GRID), list(S0_VOXEL), list(S0_RANGE), feats, coords, 1)
     model = model.cuda().eval()
-    for precision, tol in (("fp32", FEATURE_TOL), ("tf32", TF32_TOL)):
+    for precision, tol in (("fp32", FEATURE_TOL), ("tf32x3", FEATURE_TOL), ("tf32", TF32_TOL)):
         model.set_precision(precision)
         with torch.no_grad():
             sp = model({"voxel_features": feats.cuda(), "voxel_coords": coords.cuda().float(),
@@ -364,3 +367,31 @@ def test_cuda_graph_replay_matches_eager_forward(split):
         assert torch.equal(got.indices, want_i) and torch.equal(got.features, want_f)
         dense = got.dense()
         assert dense.shape == (1, 64, 1, 468, 468) and torch.isfinite(dense).all()
+
+
+@pytest.mark.parametrize("name", ["s0_b2_n1200"])
+def test_backbone_tf32x3_mode_meets_the_fp32_tolerance(name):
+    """split-operand tensor-core mode (3xTF32): same kernels as tf32, fp32-grade results"""
+    blob, cfg, state = load_golden(name)
+    cfg["PRECISION"] = "tf32x3"
+    feats, coords = torch.from_numpy(blob["voxel_features"]), torch.from_numpy(blob["voxel_coords"])
+    model, sp = run_product(cfg, state, blob["grid"], blob["pc_range"], feats, coords, int(blob["batch_size"]))
+    assert model.backbone[0].precision == "tf32x3"
+    assert torch.equal(sp.indices.cpu(), torch.from_numpy(blob["out_indices"]))
+    ref = torch.from_numpy(blob["out_features"])
+    err = (sp.features.cpu() - ref).abs().max().item()
+    assert err <= FEATURE_TOL * ref.abs().max().item(), err
+    # and on a 20 k-voxel frame against the tf32 and fp32 modes of the library
+    torch.manual_seed(0)
+    model = MixedScaleSparseTransformer(s0_model_cfg(), 64, list(S0_GRID), list(S0_VOXEL), list(S0_RANGE)).cuda().eval()
+    f, c = synth_frame(9, 20000, crop=0.38)
+    f, c = torch.from_numpy(f).cuda(), torch.from_numpy(c).cuda()
+    outs = {}
+    for mode in ("fp32", "tf32x3", "tf32"):
+        model.set_precision(mode)
+        with torch.no_grad():
+            outs[mode] = model({"voxel_features": f, "voxel_coords": c, "batch_size": 1})["encoded_spconv_tensor"].features.clone()
+    scale = outs["fp32"].abs().max().item()
+    e3 = (outs["tf32x3"] - outs["fp32"]).abs().max().item() / scale
+    e1 = (outs["tf32"] - outs["fp32"]).abs().max().item() / scale
+    assert e3 <= 2e-5 and e3 < 0.1 * e1, (e3, e1)

@@ -222,16 +222,29 @@ def test_pack_operand_tf32_layout_and_rounding(rows, k):
     from mssvt_b200._lib import call, ptr, stream
     torch.manual_seed(rows)
     w = torch.randn(rows, k)
+    def rna(a):   # cvt.rna.tf32.f32: round to nearest, ties away, 10 explicit mantissa bits
+        bits = a.view(np.uint32).astype(np.uint64)
+        return (((bits + 0x1000) & 0xFFFFE000) & 0xFFFFFFFF).astype(np.uint32).view(np.float32)
+
+    def layout(m):
+        want = np.zeros(rows * k, np.float32)
+        for n in range(rows):
+            for c in range(k // 4):
+                at = (c * rows * 16 + (n // 8) * 128 + (n % 8) * 16) // 4
+                want[at:at + 4] = m[n, 4 * c:4 * c + 4]
+        return want
+
+    hi = rna(w.numpy())
     out = torch.empty(rows * k, device="cuda")
-    call("mssvt_pack_operand_tf32", ptr(w.cuda().contiguous()), rows, k, ptr(out), stream())
-    bits = w.numpy().view(np.uint32).astype(np.uint64)
-    tf32 = (((bits + 0x1000) & 0xFFFFE000) & 0xFFFFFFFF).astype(np.uint32).view(np.float32)
-    want = np.zeros(rows * k, np.float32)
-    for n in range(rows):
-        for c in range(k // 4):
-            at = (c * rows * 16 + (n // 8) * 128 + (n % 8) * 16) // 4
-            want[at:at + 4] = tf32[n, 4 * c:4 * c + 4]
-    assert np.array_equal(out.cpu().numpy(), want)
+    call("mssvt_pack_operand_tf32", ptr(w.cuda().contiguous()), rows, k, 1, ptr(out), stream())
+    assert np.array_equal(out.cpu().numpy(), layout(hi))
+    # terms = 3: [hi | lo] with lo = tf32(w - hi); hi + lo reproduces w to ~2^-21
+    out3 = torch.empty(2 * rows * k, device="cuda")
+    call("mssvt_pack_operand_tf32", ptr(w.cuda().contiguous()), rows, k, 3, ptr(out3), stream())
+    got = out3.cpu().numpy()
+    lo = rna((w.numpy() - hi).astype(np.float32))
+    assert np.array_equal(got[:rows * k], layout(hi)) and np.array_equal(got[rows * k:], layout(lo))
+    assert np.abs(hi + lo - w.numpy()).max() <= 2.0 ** -20 * np.abs(w.numpy()).max()
 
 
 def test_attention_tile_plan_invariants():
