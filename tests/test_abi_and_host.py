@@ -91,3 +91,30 @@ def test_synthetic_frames_are_deterministic_unique_and_sorted():
     key = ((c1[:, 0].astype(np.int64) * 468 + c1[:, 3]) * 468 + c1[:, 2]) * 32 + c1[:, 1]
     assert (np.diff(key) > 0).all()  # unique, ordered by (b, x, y, z), samples contiguous
     assert c1[:, 1].max() < 32 and c1[:, 2].max() < 468 and c1[:, 3].max() < 468 and c1.min() >= 0
+
+
+def test_precision_modes_and_module_mirrors_on_cpu():
+    """host logic that needs no GPU: precision switch, state-dict names of the producer / consumer mirrors"""
+    import torch
+    from mssvt_b200.config import AttrDict, s0_model_cfg
+    from mssvt_b200.dynamic_vfe import DynamicVFE
+    from mssvt_b200.height_compression import HeightCompression
+    from mssvt_b200.mssvt_backbone import MixedScaleSparseTransformer
+    from mssvt_b200.synth import S0_GRID, S0_RANGE, S0_VOXEL
+    model = MixedScaleSparseTransformer(s0_model_cfg(), 64, list(S0_GRID), list(S0_VOXEL), list(S0_RANGE))
+    assert model.precision == "tf32x3" and all(b.precision == "tf32x3" for b in model.backbone)
+    for mode in ("fp32", "tf32", "tf32x3"):
+        assert model.set_precision(mode).backbone[-1].precision == mode
+    with pytest.raises(ValueError):
+        model.set_precision("bf16")
+    assert model.backbone[0]._terms() == 3 and model.set_precision("tf32").backbone[0]._terms() == 1
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):   # no CPU path, also for the graph capture
+        model.eval()({"voxel_features": torch.zeros(1, 64), "voxel_coords": torch.zeros(1, 4), "batch_size": 1})
+    vfe = DynamicVFE(AttrDict(NUM_FILTERS=[32, 64]), 5, list(S0_VOXEL), list(S0_GRID), list(S0_RANGE))
+    keys = set(vfe.state_dict())
+    assert {"pfn.0.0.weight", "pfn.0.1.running_var", "pfn.1.0.bias"} <= keys   # dynamic_vfe.py:57-66 names
+    assert vfe.pfn[0][0].in_features == 11 and vfe.pfn[1][0].in_features == 64 and vfe.get_output_feature_dim() == 64
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        vfe.eval()({"points": torch.zeros(3, 6), "batch_size": 1})
+    bev = HeightCompression(AttrDict(NUM_BEV_FEATURES=64))
+    assert [k for k in bev.state_dict() if k.endswith("weight")][0] == "compress_layers.0.weight"
