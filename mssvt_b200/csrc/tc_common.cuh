@@ -60,7 +60,7 @@ __device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
 
 // bounded wait: a mis-programmed MMA must not hang the GPU.  try_wait suspends the thread for a
 // hardware-defined slice per call, so the bound is on wall time (%globaltimer), not on iterations:
-// after 100 ms the kernel reports where it is stuck and traps (-> cudaErrorLaunchFailure).
+// after 2 s the kernel reports where it is stuck and traps (-> cudaErrorLaunchFailure).
 __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
     unsigned long long t0 = 0;
     for (uint32_t spin = 0;; ++spin) {
@@ -79,7 +79,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
             unsigned long long now;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
             if (t0 == 0) t0 = now;
-            else if (now - t0 > 100000000ull) {
+            else if (now - t0 > 2000000000ull) {
                 if ((threadIdx.x & 31) == 0)
                     printf("mssvt_b200: mbarrier wait timed out (block %d, thread %d, parity %u)\n", blockIdx.x,
                            threadIdx.x, parity);
