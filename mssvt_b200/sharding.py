@@ -37,3 +37,134 @@ def aggregate_throughput(units_this_rank, seconds_this_rank, device="cpu"):
     total = sum_over_ranks(units_this_rank, device)
     slowest = max_over_ranks(seconds_this_rank, device)
     return total / slowest
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Window-set sharding of ONE large frame (second row; north star: "by window sets within a
+# large frame").  Domain decomposition instead of an all-gather: the frame is cut into x-slabs whose borders
+# are window-aligned, every rank runs the unmodified kernels on its slab plus a halo as wide as the larger
+# window sticks out of the smaller one (1 voxel for 3^3 / 5^3), and after every attention block only the halo
+# rows are exchanged with the two neighbours (point-to-point, ~1 % of the rows).  The windows of an owned voxel
+# and the key candidates of those windows lie inside slab + halo, so owned rows are computed exactly as on one
+# GPU; rows in the halo are recomputed by their owner and overwritten by the exchange.
+# One more row travels: the reference lets FPS pick a padded slot, and that key aliases voxel 0 of the sample
+# ((-1 + 0.1).int() == 0, quirk Q1) WITHOUT being masked, so every window with padding may read the features of
+# the sample's first voxel.  Each rank therefore keeps the first voxel of every sample in its local frame (it
+# stays local row 0 of the sample) and refreshes it from its owner after every block.
+
+
+class SlabPlan:
+    """x-slab decomposition of one frame.  Every rank holds the full coordinate list (inputs are replicated),
+    so all index lists are derived locally and neighbours agree on sizes and row order without a handshake."""
+
+    def __init__(self, coords, win_x, halo, rank, world, grid_x=None):
+        """coords (N, 4) int [b, z, y, x]; win_x: x extent of the window grid the slab borders align to;
+        halo: voxels a slab needs beyond its borders; grid_x: x extent of the voxel grid (saves a host sync)"""
+        x = coords[:, 3]
+        n = x.shape[0]
+        if grid_x is None:
+            grid_x = int(x.max().item()) + 1 if n else 1
+        hist = torch.bincount(x, minlength=grid_x)
+        cum = torch.cumsum(hist, 0)
+        # equal voxel counts, borders on multiples of win_x; one readback for all cuts
+        targets = torch.tensor([n * r // world for r in range(1, world)], device=cum.device, dtype=cum.dtype)
+        cuts = (torch.searchsorted(cum, targets) + 1).tolist() if world > 1 else []
+        bounds = [0]
+        for cut in cuts:
+            bounds.append(max(bounds[-1], (cut + win_x // 2) // win_x * win_x))
+        bounds.append(hist.shape[0] + win_x)
+        self.bounds, self.rank, self.world, self.halo = bounds, rank, world, halo
+        lo, hi = bounds[rank], bounds[rank + 1]
+        self.lo, self.hi = lo, hi
+        # slab + halo is one x range; plus the first voxel of every sample (samples are contiguous and ordered)
+        sel = (x >= (lo - halo if rank > 0 else lo)) & (x < (hi + halo if rank < world - 1 else hi))
+        nb = int(coords[-1, 0].item()) + 1 if n else 0
+        starts = torch.searchsorted(coords[:, 0].contiguous(), torch.arange(nb, device=x.device, dtype=coords.dtype))
+        sel[starts] = True
+        first = torch.zeros_like(sel)
+        first[starts] = True
+        self.local_rows = torch.nonzero(sel).squeeze(1)                      # ascending: global row order kept
+        xl = x[self.local_rows]
+        fl = first[self.local_rows]
+        none = torch.zeros_like(fl)
+        # rows of the LOCAL tensor: what the neighbours need from me, where their rows land here, what I own,
+        # the samples' first voxels -- six masks, one nonzero, one readback of the six counts
+        masks = torch.stack([
+            (xl >= lo) & (xl < lo + halo) if rank > 0 else none,
+            (xl >= hi - halo) & (xl < hi) if rank < world - 1 else none,
+            (xl >= lo - halo) & (xl < lo) if rank > 0 else none,
+            (xl >= hi) & (xl < hi + halo) if rank < world - 1 else none,
+            (xl >= lo) & (xl < hi),
+            fl])
+        nz = torch.nonzero(masks)[:, 1]
+        counts = masks.sum(1).tolist()
+        parts = torch.split(nz, counts)
+        self.send_left, self.send_right, self.recv_left, self.recv_right, self.owned_local, self.alias_local = parts
+        self.alias_mine = ((xl >= lo) & (xl < hi))[self.alias_local]          # which first voxels this rank owns
+
+    def exchange(self, features, group=None):
+        """overwrite the halo rows of `features` (n_local, C) with the owners' values"""
+        if self.world == 1:
+            return features
+        ops, bufs = [], []
+        for peer, send_idx, recv_idx in ((self.rank - 1, self.send_left, self.recv_left),
+                                         (self.rank + 1, self.send_right, self.recv_right)):
+            if peer < 0 or peer >= self.world:
+                continue
+            out = features.index_select(0, send_idx).contiguous()
+            buf = features.new_empty((recv_idx.shape[0], features.shape[1]))
+            ops += [dist.P2POp(dist.isend, out, peer, group), dist.P2POp(dist.irecv, buf, peer, group)]
+            bufs.append((recv_idx, buf, out))
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+        for recv_idx, buf, _ in bufs:
+            features.index_copy_(0, recv_idx, buf)
+        # the samples' first voxels: exactly one rank contributes a non-zero row, the sum is that row
+        alias = features.index_select(0, self.alias_local) * self.alias_mine.unsqueeze(1).to(features.dtype)
+        dist.all_reduce(alias, group=group)
+        features.index_copy_(0, self.alias_local, alias)
+        return features
+
+
+def sharded_backbone_forward(model, voxel_features, voxel_coords, batch_size, rank, world, group=None, marks=None):
+    """One frame over `world` ranks.  Inputs are the FULL frame on every rank; returns (features, indices) of
+    the output rows this rank owns (the pillars of its slab), identical to the corresponding rows of the
+    single-GPU forward.  Inference only."""
+    from .mssvt_backbone import MixedScaleSparseTransformerCompressBlock as Compress
+
+    def mark(name):                    # optional stage timeline: (name, CUDA event) pairs appended to `marks`
+        if marks is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            marks.append((name, ev))
+
+    mark("start")
+    coords = voxel_coords if voxel_coords.dtype == torch.int32 else voxel_coords.int()
+    blocks = list(model.backbone)
+    win_x = max(int(b.win1_size[0]) for b in blocks)
+    halo = max([(int(b.win2_size[0]) - int(b.win1_size[0]) + 1) // 2 for b in blocks if b.win2_size is not None] + [0])
+    plan = SlabPlan(coords, win_x, halo, rank, world, grid_x=int(model.grid_size[0]))
+    sp = model._sparse_tensor(voxel_features.index_select(0, plan.local_rows).contiguous(),
+                              coords.index_select(0, plan.local_rows).contiguous(), batch_size)
+    mark("plan + local frame")
+    with torch.no_grad():
+        for i, block in enumerate(blocks):
+            sp = block(sp, block_idx=i)
+            mark("block %d" % i)
+            if isinstance(block, Compress):
+                break
+            plan.exchange(sp.features, group)
+            pre = getattr(sp, "_xn_ready", None)
+            if pre is not None:            # the next block's LayerNorm rows ride along (written by the FFN epilogue)
+                plan.exchange(pre[1], group)
+            mark("exchange %d" % i)
+        feats, idx = sp.features, sp.indices
+        if isinstance(blocks[-1], Compress):
+            wx = int(blocks[-1].win1_size[0])   # output rows are windows of the compress grid
+            keep = (idx[:, 3].long() * wx >= plan.lo) & (idx[:, 3].long() * wx < plan.hi)
+        else:
+            keep = torch.zeros(feats.shape[0], dtype=torch.bool, device=feats.device)
+            keep[plan.owned_local] = True
+        out = feats[keep], idx[keep], plan
+        mark("owned rows")
+        return out

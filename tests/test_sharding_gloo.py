@@ -54,3 +54,51 @@ def test_frames_are_partitioned_and_time_is_max_over_ranks():
 def test_single_process_is_identity():
     assert frames_for_rank(5, 0, 1) == [0, 1, 2, 3, 4]
     assert max_over_ranks(3.5) == 3.5
+
+
+# ---- window-set (x-slab) sharding of one frame: plan + halo exchange over gloo -----------------------------
+
+def _slab_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from mssvt_b200.sharding import SlabPlan
+    from mssvt_b200.synth import synth_frame
+    _, coords = synth_frame(3, 6000, crop=0.25)
+    coords = torch.from_numpy(coords)
+    plan = SlabPlan(coords, 3, 1, rank, world)
+    # "features" = global row id in every channel, owned rows marked with the owner's rank in channel 1;
+    # halo rows start as garbage and must come back holding the owner's values
+    feats = torch.full((plan.local_rows.shape[0], 4), -1.0)
+    feats[plan.owned_local, 0] = plan.local_rows[plan.owned_local].float()
+    feats[plan.owned_local, 1] = float(rank)
+    plan.exchange(feats)
+    x = coords[plan.local_rows, 3]
+    ok_rows = bool((feats[:, 0] == plan.local_rows.float()).all())          # (incl. the sample's first voxel)
+    owner = torch.bucketize(x, torch.tensor(plan.bounds[1:-1]), right=True).float()
+    ok_owner = bool((feats[:, 1] == owner).all()) and int(plan.local_rows[plan.alias_local[0]]) == 0
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (plan.bounds, int(plan.owned_local.shape[0]), ok_rows, ok_owner,
+                                      int(plan.recv_left.shape[0] + plan.recv_right.shape[0])))
+    if rank == 0:
+        out.put((gathered, coords.shape[0]))
+    dist.destroy_process_group()
+
+
+def test_slab_plan_and_halo_exchange_world3():
+    world = 3
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_slab_worker, args=(r, world, port, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    gathered, n = out.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(g[0] == gathered[0][0] for g in gathered)            # every rank derives the same borders
+    assert all(b % 3 == 0 for b in gathered[0][0][1:-1])            # window-aligned
+    assert sum(g[1] for g in gathered) == n                         # every voxel owned exactly once
+    assert all(g[2] and g[3] for g in gathered)                     # halo rows hold their owners' values
+    assert all(g[4] > 0 for g in gathered)
