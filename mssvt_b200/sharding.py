@@ -57,11 +57,16 @@ class SlabPlan:
     """x-slab decomposition of one frame.  Every rank holds the full coordinate list (inputs are replicated),
     so all index lists are derived locally and neighbours agree on sizes and row order without a handshake."""
 
-    def __init__(self, coords, win_x, halo, rank, world, grid_x=None):
+    def __init__(self, coords, win_x, halo, rank, world, grid_x=None, sorted_single_sample=False):
         """coords (N, 4) int [b, z, y, x]; win_x: x extent of the window grid the slab borders align to;
-        halo: voxels a slab needs beyond its borders; grid_x: x extent of the voxel grid (saves a host sync)"""
+        halo: voxels a slab needs beyond its borders; grid_x: x extent of the voxel grid (saves a host sync);
+        sorted_single_sample: the caller guarantees ONE sample whose rows ascend in x (the order DynamicVFE /
+        torch.unique produce): every row set below is then a contiguous range found by binary search"""
         x = coords[:, 3]
         n = x.shape[0]
+        if sorted_single_sample and n and world > 1:
+            self._init_sorted(x, n, win_x, halo, rank, world, grid_x)
+            return
         if grid_x is None:
             grid_x = int(x.max().item()) + 1 if n else 1
         hist = torch.bincount(x, minlength=grid_x)
@@ -102,6 +107,35 @@ class SlabPlan:
         self.send_left, self.send_right, self.recv_left, self.recv_right, self.owned_local, self.alias_local = parts
         self.alias_mine = ((xl >= lo) & (xl < hi))[self.alias_local]          # which first voxels this rank owns
 
+    def _init_sorted(self, x, n, win_x, halo, rank, world, grid_x):
+        dev = x.device
+        pick = torch.tensor([n * r // world for r in range(1, world)], device=dev)
+        cuts = (x[pick] + 1).tolist()                                   # read-back 1: the quantile columns
+        bounds = [0]
+        for cut in cuts:
+            bounds.append(max(bounds[-1], (cut + win_x // 2) // win_x * win_x))
+        bounds.append((grid_x if grid_x is not None else int(x[-1].item()) + 1) + win_x)
+        self.bounds, self.rank, self.world, self.halo = bounds, rank, world, halo
+        lo, hi = bounds[rank], bounds[rank + 1]
+        self.lo, self.hi = lo, hi
+        has_l, has_r = rank > 0, rank < world - 1
+        marks = torch.tensor([lo - halo if has_l else lo, lo, lo + halo, hi - halo, hi, hi + halo if has_r else hi],
+                             device=dev, dtype=x.dtype)
+        p = torch.searchsorted(x.contiguous(), marks).tolist()          # read-back 2: six row positions
+        start, end = p[0], p[5]
+        extra = 1 if start > 0 else 0                                   # the sample's first voxel rides in front
+        rows = torch.arange(start, end, device=dev)
+        self.local_rows = torch.cat([rows.new_zeros(1), rows]) if extra else rows
+        rng = lambda a, b: torch.arange(a - start + extra, b - start + extra, device=dev)
+        none = rows[:0]
+        self.send_left = rng(p[1], min(p[2], p[4])) if has_l else none
+        self.send_right = rng(max(p[3], p[1]), p[4]) if has_r else none
+        self.recv_left = rng(p[0], p[1]) if has_l else none
+        self.recv_right = rng(p[4], p[5]) if has_r else none
+        self.owned_local = rng(p[1], p[4])
+        self.alias_local = rows.new_zeros(1)
+        self.alias_mine = torch.tensor([p[1] == 0 and p[4] > 0], device=dev)
+
     def exchange(self, features, group=None):
         """overwrite the halo rows of `features` (n_local, C) with the owners' values"""
         if self.world == 1:
@@ -126,10 +160,12 @@ class SlabPlan:
         return features
 
 
-def sharded_backbone_forward(model, voxel_features, voxel_coords, batch_size, rank, world, group=None, marks=None):
+def sharded_backbone_forward(model, voxel_features, voxel_coords, batch_size, rank, world, group=None, marks=None,
+                             sorted_by_x=False):
     """One frame over `world` ranks.  Inputs are the FULL frame on every rank; returns (features, indices) of
     the output rows this rank owns (the pillars of its slab), identical to the corresponding rows of the
-    single-GPU forward.  Inference only."""
+    single-GPU forward.  Inference only.  sorted_by_x: the caller guarantees rows ascending in x within the
+    (single) sample, which makes the slab plan two binary searches instead of passes over all voxels."""
     from .mssvt_backbone import MixedScaleSparseTransformerCompressBlock as Compress
 
     def mark(name):                    # optional stage timeline: (name, CUDA event) pairs appended to `marks`
@@ -143,7 +179,8 @@ def sharded_backbone_forward(model, voxel_features, voxel_coords, batch_size, ra
     blocks = list(model.backbone)
     win_x = max(int(b.win1_size[0]) for b in blocks)
     halo = max([(int(b.win2_size[0]) - int(b.win1_size[0]) + 1) // 2 for b in blocks if b.win2_size is not None] + [0])
-    plan = SlabPlan(coords, win_x, halo, rank, world, grid_x=int(model.grid_size[0]))
+    plan = SlabPlan(coords, win_x, halo, rank, world, grid_x=int(model.grid_size[0]),
+                    sorted_single_sample=bool(sorted_by_x) and batch_size == 1)
     sp = model._sparse_tensor(voxel_features.index_select(0, plan.local_rows).contiguous(),
                               coords.index_select(0, plan.local_rows).contiguous(), batch_size)
     mark("plan + local frame")

@@ -102,3 +102,23 @@ def test_slab_plan_and_halo_exchange_world3():
     assert sum(g[1] for g in gathered) == n                         # every voxel owned exactly once
     assert all(g[2] and g[3] for g in gathered)                     # halo rows hold their owners' values
     assert all(g[4] > 0 for g in gathered)
+
+
+def test_slab_plan_sorted_fast_path_equals_generic_path():
+    """frames whose rows ascend in x (the order DynamicVFE / torch.unique produce): the plan from two binary
+    searches is the plan from the passes over all voxels"""
+    from mssvt_b200.sharding import SlabPlan
+    from mssvt_b200.synth import synth_frame
+    for seed, n, crop in ((3, 20000, 0.4), (5, 3000, 0.2)):
+        _, c = synth_frame(seed, n, crop=crop)
+        c = torch.from_numpy(c)
+        assert bool((c[1:, 3] >= c[:-1, 3]).all())
+        for world in (2, 3, 5):
+            for r in range(world):
+                a = SlabPlan(c, 3, 1, r, world, grid_x=468)
+                b = SlabPlan(c, 3, 1, r, world, grid_x=468, sorted_single_sample=True)
+                assert a.bounds == b.bounds
+                for name in ("local_rows", "send_left", "send_right", "recv_left", "recv_right", "owned_local",
+                             "alias_local"):
+                    assert torch.equal(getattr(a, name), getattr(b, name)), (seed, world, r, name)
+                assert a.alias_mine.tolist() == b.alias_mine.tolist()
