@@ -784,7 +784,9 @@ class GraphedForward:
 
     A graph is bound to its input buffers: `voxel_features` (N, C) fp32 and `voxel_coords` (N, 4) int32 are
     STATIC -- write the next frame into them (same N) and call replay().  Frames of another size need their
-    own capture or the eager forward.  Outputs live in graph-owned buffers that the next replay overwrites.
+    own capture or the eager forward, and so does a change of the precision mode or of the weights' storage
+    (the graph holds the kernels and packed-weight pointers of the capture).  Outputs live in graph-owned
+    buffers that the next replay overwrites.
     """
 
     def __init__(self, model, voxel_features, voxel_coords, batch_size, warmup=2, split=False):
