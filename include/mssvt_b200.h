@@ -75,9 +75,10 @@ int mssvt_hash_lookup(int hash_size, int num_queries, const int *batch_ids, cons
  *   win_list  (list_capacity, 4) rows [b, wz, wy, wx] of all samples concatenated, numbered by
  *             first occurrence in voxel order (the reference numbers by atomicAdd arrival);
  *   table     (batch_size, hash_size, 2) window key -> per-sample row id, filled by this call;
- *   win_count (batch_size + 2): per-sample window counts, [B] = total, [B+1] = windows dropped
- *             because they exceed max_wins per sample or list_capacity (the reference writes
- *             out of bounds in that case);
+ *   win_count (batch_size + 2): per-sample window counts (before any clamping), [B] = rows in
+ *             win_list = kept windows (a sample keeps its first max_wins windows, kept windows of
+ *             all samples are contiguous, at most list_capacity rows), [B+1] = windows dropped
+ *             (the reference writes out of bounds in that case);
  *   workspace: mssvt_window_partition_workspace_bytes(num_voxels) bytes of scratch. */
 long long mssvt_window_partition_workspace_bytes(int num_voxels);
 int mssvt_window_partition(int x_wgs, int y_wgs, int z_wgs, int x_ws, int y_ws, int z_ws,
@@ -152,7 +153,7 @@ int mssvt_grid_index_build(int x_max, int y_max, int z_max, int num_voxels, int 
 /* Coordinate-only part of MixedScaleSparseTransformerBlock.forward (mssvt_backbone.py:213-258,
  * 264-269, 300-307) in one kernel, one warp per window, with no host synchronisation: the
  * number of windows is read from device memory (win_count_total) and bounds the work.
- * Outputs per window w < *win_count_total (rows beyond are untouched):
+ * Outputs per window w < min(win_capacity, *win_count_total) (rows beyond are untouched):
  *   q_row    (cap, nq)        global feature row of each query slot (-1 pad); nq = |odd| / |even|
  *                             / max_win1 for cbs_pattern 1 / 0 / 2
  *   win1_row (cap, max_win1)  global row of each win1 voxel (-1 pad)

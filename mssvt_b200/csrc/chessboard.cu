@@ -239,7 +239,7 @@ __device__ __forceinline__ void fps_list(const int *s_off, int cnt, int n, int l
 }
 
 __global__ void __launch_bounds__(GEO_WARPS * 32)
-k_block_geometry(GeoParams P, TablePtrs tabs, const int *__restrict__ win_count_total,
+k_block_geometry(GeoParams P, TablePtrs tabs, int win_cap, const int *__restrict__ win_count_total,
                  const int4 *__restrict__ win_list, GridIdx index,
                  const int *__restrict__ v_start, GeoOut out) {
     extern __shared__ int smem[];
@@ -262,7 +262,7 @@ k_block_geometry(GeoParams P, TablePtrs tabs, const int *__restrict__ win_count_
     __syncthreads();
     const int list_at[4] = {0, g.cap[0], g.cap[0] + g.cap[1], g.cap[0] + g.cap[1] + g.cap[2]};
     const int qL = P.pattern == 0 ? 1 : P.pattern == 1 ? 0 : 2;
-    const int num_wins = __ldg(win_count_total);
+    const int num_wins = min(win_cap, __ldg(win_count_total));  // never past the caller's allocations
 
     for (int w = blockIdx.x * GEO_WARPS + warp; w < num_wins; w += gridDim.x * GEO_WARPS) {
         int cnt[4], cx, cy, cz;
@@ -379,7 +379,7 @@ k_block_geometry(GeoParams P, TablePtrs tabs, const int *__restrict__ win_count_
 
 // one-window gather for the compress block, sync-free: global rows only, -1 padded
 __global__ void __launch_bounds__(GEO_WARPS * 32)
-k_window_rows(GatherShape g, TablePtrs tabs, const int *__restrict__ win_count_total,
+k_window_rows(GatherShape g, TablePtrs tabs, int win_cap, const int *__restrict__ win_count_total,
               const int4 *__restrict__ win_list, GridIdx index,
               const int *__restrict__ v_start, int *__restrict__ k_row) {
     extern __shared__ int smem[];
@@ -391,7 +391,7 @@ k_window_rows(GatherShape g, TablePtrs tabs, const int *__restrict__ win_count_t
     load_tables(g, tabs.p, s_tab);
     __syncthreads();
     const int list_at[4] = {0, 0, 0, 0};
-    const int num_wins = __ldg(win_count_total);
+    const int num_wins = min(win_cap, __ldg(win_count_total));  // never past the caller's allocations
     for (int w = blockIdx.x * GEO_WARPS + warp; w < num_wins; w += gridDim.x * GEO_WARPS) {
         int cnt[4], cx, cy, cz;
         const int4 win = __ldg(win_list + w);
@@ -544,7 +544,7 @@ int mssvt_block_geometry(int x_max, int y_max, int z_max, int x_ws, int y_ws, in
     ++g_launches;
     const int zw = (z_max + 31) / 32;
     GridIdx index = {(const int2 *)grid_cells, grid_vals, y_max, zw, (long long)x_max * y_max * zw};
-    k_block_geometry<<<grid, GEO_WARPS * 32, smem, s>>>(P, tabs, win_count_total,
+    k_block_geometry<<<grid, GEO_WARPS * 32, smem, s>>>(P, tabs, win_capacity, win_count_total,
                                                        (const int4 *)win_list, index, v_start, out);
     (void)ext;
     return check_launch();
@@ -570,7 +570,7 @@ int mssvt_window_rows(int x_max, int y_max, int z_max, int x_ws, int y_ws, int z
     GridIdx index = {(const int2 *)grid_cells, grid_vals, y_max, zw, (long long)x_max * y_max * zw};
     ++g_launches;
     k_window_rows<<<persistent_grid(win_capacity, GEO_WARPS, 8), GEO_WARPS * 32, smem,
-                    (cudaStream_t)stream>>>(g, tabs, win_count_total, (const int4 *)win_list,
+                    (cudaStream_t)stream>>>(g, tabs, win_capacity, win_count_total, (const int4 *)win_list,
                                             index, v_start, k_row);
     return check_launch();
 }

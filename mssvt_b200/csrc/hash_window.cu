@@ -357,15 +357,30 @@ k_win_emit(int x_ws, int y_ws, int z_ws, int num_voxels, int hash_size, int batc
     if (!opens) return;
     int rank = base + before + __popc(ball & lanemask_lt());
     int4 c = __ldg(v_indices + t);
-    int first_row = 0;
-    for (int i = 0; i < c.x; ++i) first_row += win_count[i];
-    int local = rank - first_row;
-    if (local >= max_wins || rank >= list_capacity) {
+    // A sample keeps its first max_wins windows; the kept windows of all samples are COMPACTED (no holes
+    // between samples when one overflows), and the list holds list_capacity rows at most.
+    int first_row = 0, first_kept = 0;
+    for (int i = 0; i < c.x; ++i) {
+        int n = win_count[i];
+        first_row += n;
+        first_kept += min(n, max_wins);
+    }
+    int local = rank - first_row, row = first_kept + local;
+    if (local >= max_wins || row >= list_capacity) {
         atomicAdd(overflow, 1);
         return;
     }
-    win_list[rank] = make_int4(c.x, c.y / z_ws, c.z / y_ws, c.w / x_ws);
+    win_list[row] = make_int4(c.x, c.y / z_ws, c.z / y_ws, c.w / x_ws);
     table[((size_t)c.x * hash_size + slot) * 2 + 1] = local;
+}
+
+// win_count[B] (all openers, written by k_win_count) -> number of rows actually in the list, so that every
+// consumer's loop bound is the kept count; the per-sample entries keep the raw counts.
+__global__ void k_win_clamp_total(int batch_size, int max_wins, int list_capacity, int *__restrict__ win_count) {
+    if (threadIdx.x || blockIdx.x) return;
+    int kept = 0;
+    for (int i = 0; i < batch_size; ++i) kept += min(win_count[i], max_wins);
+    win_count[batch_size] = min(kept, list_capacity);
 }
 
 }  // namespace mssvt
@@ -491,7 +506,8 @@ long long mssvt_window_partition_workspace_bytes(int num_voxels) {
     return ((long long)num_voxels + blocks + 8) * 4;
 }
 
-// win_count: (batch_size + 2) int32 -> per-sample counts, [B] total, [B+1] rows that did not fit
+// win_count: (batch_size + 2) int32 -> per-sample counts (before clamping), [B] rows in the list (kept windows,
+// compacted), [B+1] windows that did not fit (max_wins per sample / list_capacity)
 int mssvt_window_partition(int x_wgs, int y_wgs, int z_wgs, int x_ws, int y_ws, int z_ws,
                            int num_voxels, int max_wins, int hash_size, int batch_size,
                            int list_capacity, const int *v_indices, int *win_list, int *table,
@@ -523,6 +539,8 @@ int mssvt_window_partition(int x_wgs, int y_wgs, int z_wgs, int x_ws, int y_ws, 
                                             max_wins, list_capacity, (const int4 *)v_indices, table,
                                             slot_of, block_counts, win_count, (int4 *)win_list,
                                             win_count + batch_size + 1);
+    ++g_launches;
+    k_win_clamp_total<<<1, 32, 0, s>>>(batch_size, max_wins, list_capacity, win_count);
     return check_launch();
 }
 

@@ -225,7 +225,9 @@ class MixedScaleSparseTransformerBlock(nn.Module):
         x = sp_tensor.features.float().contiguous()
         N, C = x.shape
         g = self.geometry(sp_tensor)
-        W = int(g["total"].item())
+        W, dropped = (int(v) for v in g["win_count"][sp_tensor.batch_size:sp_tensor.batch_size + 2].tolist())
+        if dropped:
+            raise RuntimeError("window partition: %d windows exceed max_num_wins" % dropped)
         dev = x.device
         cnt_n = torch.tensor([N], dtype=torch.int32, device=dev)
         cnt_w = torch.tensor([W], dtype=torch.int32, device=dev)
@@ -407,7 +409,8 @@ class MixedScaleSparseTransformerBlock(nn.Module):
     def _packed(self, *weights):
         """tensor-core operand form of an nn.Linear / 1x1 Conv1d weight (TF32, K-major core matrices),
         packed once and cached until the parameter is modified or moved; several weights = their
-        block-diagonal matrix (one GEMM for all head groups)"""
+        block-diagonal matrix (one GEMM for all head groups).  A stale entry is re-packed IN PLACE (same
+        buffer), so a captured CUDA graph that holds the buffer's address sees the new weights."""
         cache = self.__dict__.setdefault("_packed_ops", {})
         terms = self._terms()
         key = tuple(id(w) for w in weights) + (terms,)
@@ -416,10 +419,28 @@ class MixedScaleSparseTransformerBlock(nn.Module):
         if hit is None or hit[0] != tag:
             mats = [w.detach().reshape(w.shape[0], -1).float() for w in weights]
             w2d = (mats[0] if len(mats) == 1 else torch.block_diag(*mats)).contiguous()
-            out = w2d.new_empty((2 if terms == 3 else 1,) + tuple(w2d.shape))   # [hi | lo] for 3xTF32
+            shape = (2 if terms == 3 else 1,) + tuple(w2d.shape)        # [hi | lo] for 3xTF32
+            out = hit[1] if hit is not None and tuple(hit[1].shape) == shape and hit[1].device == w2d.device \
+                else w2d.new_empty(shape)
             call("mssvt_pack_operand_tf32", ptr(w2d), w2d.shape[0], w2d.shape[1], terms, ptr(out), stream())
-            hit = cache[key] = (tag, out)
+            hit = cache[key] = (tag, out, weights)
         return hit[1]
+
+    def repack_stale(self):
+        """Re-pack (in place) every cached operand whose parameter was modified in place since it was packed
+        (optimizer step, load_state_dict, EMA); returns False if a parameter's STORAGE moved, which a
+        captured graph cannot follow."""
+        same_storage = True
+        for key, (tag, out, weights) in list(self.__dict__.get("_packed_ops", {}).items()):
+            now = tuple((w.data_ptr(), w._version) for w in weights)
+            if now != tag:
+                same_storage &= all(a[0] == b[0] for a, b in zip(now, tag))
+                terms = key[-1]
+                mats = [w.detach().reshape(w.shape[0], -1).float() for w in weights]
+                w2d = (mats[0] if len(mats) == 1 else torch.block_diag(*mats)).contiguous()
+                call("mssvt_pack_operand_tf32", ptr(w2d), w2d.shape[0], w2d.shape[1], terms, ptr(out), stream())
+                self._packed_ops[key] = (now, out, weights)
+        return same_storage
 
     def _ffn_descriptor(self, mode):
         named = [("ln_g", self.norm2.weight), ("ln_b", self.norm2.bias),
@@ -492,6 +513,8 @@ class MixedScaleSparseTransformerBlock(nn.Module):
         if x.dtype != torch.float32 or not x.is_contiguous():
             x = x.float().contiguous()
         g = self.geometry(sp_tensor)
+        B = sp_tensor.batch_size
+        sp_tensor.note_window_overflow(g["win_count"][B + 1:B + 2])
         xn = self._layernorm1(x, sp_tensor)
         a = self.ms_attn
         F, fbuf = self._ffn_descriptor(mode=1)
@@ -647,7 +670,7 @@ class MixedScaleSparseTransformerCompressBlock(MixedScaleSparseTransformerBlock)
         sp_tensor.voxel_size = [vs[i] * self.win1_size[i] for i in range(3)]
         sp_tensor.gather_dict = None
         sp_tensor.map_table = win_table
-        sp_tensor._window_overflow = win_count[B + 1:B + 2]
+        sp_tensor.note_window_overflow(win_count[B + 1:B + 2])
         sp_tensor._taps = {"k_row": k_row, "attn": attn}
         return sp_tensor
 
@@ -689,14 +712,16 @@ class MixedScaleSparseTransformer(nn.Module):
         self.num_point_features = model_cfg.NUM_OUTPUT_FEATURES
         self.set_precision(model_cfg.get('PRECISION', 'tf32x3'))
 
+    PRECISIONS = ("fp32", "tf32", "tf32x3")
+
     def set_precision(self, precision):
         """'tf32x3' (default): every projection and the FFN on the tcgen05 tensor cores with split operands
         (3xTF32): fp32-grade results (within 1e-4 of the fp32 reference, measured 1.5e-6) at three MMAs per K
         step.  'tf32': the same kernels with plain TF32 operands (within 2e-3, measured 6.7e-4), fastest.
         'fp32': FFMA kernels, no tensor cores (within 1e-4, measured 6e-7).  Shapes the tensor-core kernels do
         not cover run on the FFMA kernels in every mode."""
-        if precision not in ("fp32", "tf32", "tf32x3"):
-            raise ValueError("precision must be 'fp32', 'tf32' or 'tf32x3'")
+        if precision not in self.PRECISIONS:
+            raise ValueError("precision must be one of %s" % (self.PRECISIONS,))
         self.precision = precision
         for block in self.backbone:
             block.precision = precision
@@ -741,6 +766,7 @@ class MixedScaleSparseTransformer(nn.Module):
             self._fork_side_work(sp_tensor)
         for i, attention_block in enumerate(self.backbone):
             sp_tensor = attention_block(sp_tensor, block_idx=i)
+        sp_tensor._overflow_armed = True      # dropped windows are reported at the first look at the rows
         batch_dict.update({'encoded_spconv_tensor': sp_tensor, 'encoded_spconv_tensor_stride': 1})
         return batch_dict
 
@@ -762,14 +788,35 @@ class MixedScaleSparseTransformer(nn.Module):
         sp_tensor.sample_counts(), sp_tensor.grid_index(), sp_tensor.world_coords()
         fork = torch.cuda.Event()
         fork.record(main)
+        capturing = torch.cuda.is_current_stream_capturing()
+
+        def hand_over(obj):
+            # tensors allocated under the side stream are consumed on `main`: tell the caching allocator, so that
+            # a later forward driven from ANOTHER stream cannot be handed their blocks while `main` still reads
+            # them (inside a graph capture the pool is private and the graph's own edges order the reuse)
+            if capturing:
+                return
+            if isinstance(obj, torch.Tensor):
+                if obj.is_cuda:
+                    obj.record_stream(main)
+            elif isinstance(obj, (list, tuple)):
+                for o in obj:
+                    hand_over(o)
+            elif isinstance(obj, dict):
+                for o in obj.values():
+                    hand_over(o)
+
         with torch.cuda.stream(side):
             side.wait_event(fork)
             xn = first._layernorm1(x)
+            hand_over(xn)
             sp_tensor._xn_ready, sp_tensor._xn_event = (x, xn, first.norm1), torch.cuda.Event()
             sp_tensor._xn_event.record(side)
             if isinstance(last, MixedScaleSparseTransformerCompressBlock) and \
                     all(not isinstance(b, MixedScaleSparseTransformerCompressBlock) for b in self.backbone[:-1]):
+                known = set(sp_tensor._cache().keys())
                 last.prepare(sp_tensor)               # (the blocks before it keep the voxel coordinates)
+                hand_over([v for k, v in sp_tensor._cache().items() if k not in known])
                 sp_tensor._prepare_event = torch.cuda.Event()
                 sp_tensor._prepare_event.record(side)
 
@@ -784,9 +831,11 @@ class GraphedForward:
 
     A graph is bound to its input buffers: `voxel_features` (N, C) fp32 and `voxel_coords` (N, 4) int32 are
     STATIC -- write the next frame into them (same N) and call replay().  Frames of another size need their
-    own capture or the eager forward, and so does a change of the precision mode or of the weights' storage
-    (the graph holds the kernels and packed-weight pointers of the capture).  Outputs live in graph-owned
-    buffers that the next replay overwrites.
+    own capture or the eager forward, and so does a change of the precision mode or of a parameter's STORAGE
+    (the graph holds the kernels and the parameter / packed-weight pointers of the capture; replay raises).
+    In-place parameter updates (optimizer step, load_state_dict, EMA) are followed: replay() re-packs the
+    tensor-core weight copies in place first.  Outputs live in graph-owned buffers that the next replay
+    overwrites.
     """
 
     def __init__(self, model, voxel_features, voxel_coords, batch_size, warmup=2, split=False):
@@ -825,8 +874,9 @@ class GraphedForward:
                     sp = run()
             self.launches = int(call("mssvt_launch_count") - before)   # kernels per replay
         self._template = sp                     # keeps the graph-owned output / geometry buffers alive
+        self._param_tag = self._tag()
         self._lazy = sp._lazy
-        self._overflow = getattr(sp, "_window_overflow", None)
+        self._overflow = list(sp.__dict__.get("_overflow_flags") or [])
 
     def replay_prepare(self):
         """split capture only: the coordinate-only graph (may run a frame ahead, on another stream, as long
@@ -844,15 +894,31 @@ class GraphedForward:
             self.prepare_graph.replay()
         return self._replay_main()
 
+    def _tag(self):
+        return tuple((p.data_ptr(), p._version) for p in self.model.parameters())
+
+    def _refresh_weights(self):
+        """The graph reads biases / LayerNorm parameters through their own pointers and the GEMM weights through
+        packed copies: after an in-place update of the parameters the copies are re-packed in place (same
+        addresses); parameters whose storage was replaced cannot be followed by the captured pointers."""
+        tag = self._tag()
+        if tag != self._param_tag:
+            if len(tag) != len(self._param_tag) or any(a[0] != b[0] for a, b in zip(tag, self._param_tag)):
+                raise RuntimeError("GraphedForward: a parameter's storage changed since the capture; capture again")
+            for block in self.model.backbone:
+                block.repack_stale()
+            self._param_tag = tag
+
     def _replay_main(self):
+        self._refresh_weights()
         self.graph.replay()
         t = self._template
         sp = SparseTensor(features=None, indices=None, spatial_shape=t.spatial_shape, voxel_size=t.voxel_size,
                           point_cloud_range=t.point_cloud_range, batch_size=t.batch_size, hash_size=t.hash_size,
                           map_table=None, gather_dict=None)
+        sp._overflow_flags, sp._overflow_armed = list(self._overflow), True
         if self._lazy is not None:
             sp.set_lazy_rows(*self._lazy)
-            sp._window_overflow = self._overflow
         else:                                   # (no compress block: rows are the input voxels)
             sp._features, sp._indices = t._features, t._indices
         return sp

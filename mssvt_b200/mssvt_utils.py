@@ -15,16 +15,29 @@ from . import mssvt_ops
 from ._lib import call, ptr, stream, host_floats
 
 
-_PINNED_RING = []
+class _PinnedPairs:
+    """Pinned int32[2] buffers for asynchronous (row count, dropped windows) readbacks.  A buffer is handed
+    out again only after the event recorded behind its last copy has completed, so any number of
+    un-materialised outputs may be in flight (each keeps its own buffer until it is read)."""
+
+    def __init__(self):
+        self.free, self.busy = [], []
+
+    def get(self):
+        still = []
+        for buf, ev in self.busy:
+            if ev is None or ev.query():
+                self.free.append(buf)
+            else:
+                still.append((buf, ev))
+        self.busy = still
+        return self.free.pop() if self.free else torch.empty(2, dtype=torch.int32).pin_memory()
+
+    def release(self, buf, event):
+        self.busy.append((buf, event))
 
 
-def _pinned_pair():
-    """small ring of pinned int32[2] buffers for asynchronous row-count readbacks"""
-    if len(_PINNED_RING) < 16:
-        _PINNED_RING.append(torch.empty(2, dtype=torch.int32).pin_memory())
-        return _PINNED_RING[-1]
-    _PINNED_RING.append(_PINNED_RING.pop(0))
-    return _PINNED_RING[-1]
+_PINNED = _PinnedPairs()
 
 
 def sample_counts(indices, batch_size):
@@ -51,6 +64,7 @@ class SparseTensor(object):
         self.hash_size = hash_size
         self.gather_dict = gather_dict
         self._derived = {}                  # per-coordinate-set caches (counts, world xyz, geometry)
+        self._count_host = self._ready = None
         self._map_table = map_table         # reference-contract hash table, built on first use
 
     # A compress block produces one row per non-empty window; that count lives on the device.  The
@@ -67,13 +81,30 @@ class SparseTensor(object):
             self._ready.record()
         self._count_host = None
 
+    def note_window_overflow(self, flag):
+        """flag: device int32[1], number of windows a window partition had to drop (max_num_wins per sample /
+        list capacity).  The kernels stay memory-safe (dropped windows simply get no attention); the error is
+        raised at the next point where the host looks at the tensor anyway (.features / .indices,
+        prefetch_row_count + check_window_overflow), never by an extra synchronisation in the forward."""
+        flags = self.__dict__.setdefault("_overflow_flags", [])
+        if not any(f.data_ptr() == flag.data_ptr() for f in flags):
+            flags.append(flag)
+            self._overflow_host = None
+
+    def _overflow_total_dev(self):
+        flags = self.__dict__.get("_overflow_flags") or []
+        if not flags:
+            return None
+        return flags[0] if len(flags) == 1 else torch.stack([f.reshape(()) for f in flags]).sum().reshape(1).int()
+
     def prefetch_row_count(self):
         """Start the 8-byte readback of (row count, dropped windows) without waiting for it, so that a
         pipelined caller can queue the next frame before it looks at .features of this one."""
-        if self._lazy is not None and self._count_host is None:
-            host = _pinned_pair()
-            host[0:1].copy_(self._lazy[2], non_blocking=True)
-            dropped = getattr(self, "_window_overflow", None)
+        if self._count_host is None and (self._lazy is not None or self.__dict__.get("_overflow_flags")):
+            host = _PINNED.get()
+            if self._lazy is not None:
+                host[0:1].copy_(self._lazy[2], non_blocking=True)
+            dropped = self._overflow_total_dev()
             if dropped is not None:
                 host[1:2].copy_(dropped, non_blocking=True)
             else:
@@ -82,24 +113,47 @@ class SparseTensor(object):
             self._ready = torch.cuda.Event()
             self._ready.record()
 
+    def check_window_overflow(self):
+        """Raise if any window partition of the forward that produced this tensor dropped windows (one
+        4-byte readback, or none after prefetch_row_count)."""
+        if self.__dict__.get("_overflow_host") is None:
+            if self._count_host is not None:
+                if self._ready is not None:
+                    self._ready.synchronize()
+                self._overflow_host = int(self._count_host[1])
+            else:
+                dropped = self._overflow_total_dev()
+                self._overflow_host = int(dropped.item()) if dropped is not None else 0
+        if self._overflow_host:
+            raise RuntimeError("window partition: %d windows exceed max_num_wins (or the window list capacity); "
+                               "their voxels received no attention" % self._overflow_host)
+
     def _materialise(self):
         if self._lazy is not None:
             f, i, count = self._lazy
             if self._ready is not None:
                 self._ready.synchronize()
             if self._count_host is not None:
-                n, n_dropped = int(self._count_host[0]), int(self._count_host[1])
+                n = int(self._count_host[0])
+                self._overflow_host = int(self._count_host[1])
+                _PINNED.release(self._count_host, self._ready)
+                self._count_host = None
             else:
                 n = int(count.item())
-                dropped = getattr(self, "_window_overflow", None)
-                n_dropped = int(dropped.item()) if dropped is not None else 0
-            if n_dropped:
-                raise RuntimeError("compress block: %d windows exceed max_num_wins" % n_dropped)
             self._features, self._indices, self._lazy = f[:n], i[:n], None
+            self.check_window_overflow()
+
+    def _armed_check(self):
+        # armed by MixedScaleSparseTransformer.forward when it hands the tensor out: the first look at the rows
+        # from outside also reports dropped windows (inside the forward nothing synchronises)
+        if self.__dict__.get("_overflow_armed") and not torch.cuda.is_current_stream_capturing():
+            self._overflow_armed = False
+            self.check_window_overflow()
 
     @property
     def features(self):
         self._materialise()
+        self._armed_check()
         return self._features
 
     @features.setter
@@ -110,6 +164,7 @@ class SparseTensor(object):
     @property
     def indices(self):
         self._materialise()
+        self._armed_check()
         return self._indices
 
     @indices.setter

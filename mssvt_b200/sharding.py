@@ -4,6 +4,8 @@ Frames are independent end to end (per-sample hash / grid index, per-sample wind
 backbone shards by frame with NO data-path collective: rank r of `world` takes frames
 r, r + world, ... .  torch.distributed is only used for the barrier around a timed region and the
 max-over-ranks reduction of the measured time (NCCL on GPUs, gloo in the CPU tests)."""
+import math
+
 import torch
 import torch.distributed as dist
 
@@ -78,6 +80,7 @@ class SlabPlan:
         for cut in cuts:
             bounds.append(max(bounds[-1], (cut + win_x // 2) // win_x * win_x))
         bounds.append(hist.shape[0] + win_x)
+        self._check_bounds(bounds, halo, world)
         self.bounds, self.rank, self.world, self.halo = bounds, rank, world, halo
         lo, hi = bounds[rank], bounds[rank + 1]
         self.lo, self.hi = lo, hi
@@ -107,6 +110,14 @@ class SlabPlan:
         self.send_left, self.send_right, self.recv_left, self.recv_right, self.owned_local, self.alias_local = parts
         self.alias_mine = ((xl >= lo) & (xl < hi))[self.alias_local]          # which first voxels this rank owns
 
+    @staticmethod
+    def _check_bounds(bounds, halo, world):
+        """every rank derives the same bounds, so every rank raises together: a slab narrower than the halo
+        (or empty) would make the send / receive row sets of neighbours disagree"""
+        if world > 1 and any(b - a < max(halo, 1) for a, b in zip(bounds, bounds[1:])):
+            raise ValueError("one-frame sharding: a slab is narrower than the halo (%d voxels) -- slab borders %s; "
+                             "use fewer ranks for this frame" % (halo, bounds))
+
     def _init_sorted(self, x, n, win_x, halo, rank, world, grid_x):
         dev = x.device
         pick = torch.tensor([n * r // world for r in range(1, world)], device=dev)
@@ -115,6 +126,7 @@ class SlabPlan:
         for cut in cuts:
             bounds.append(max(bounds[-1], (cut + win_x // 2) // win_x * win_x))
         bounds.append((grid_x if grid_x is not None else int(x[-1].item()) + 1) + win_x)
+        self._check_bounds(bounds, halo, world)
         self.bounds, self.rank, self.world, self.halo = bounds, rank, world, halo
         lo, hi = bounds[rank], bounds[rank + 1]
         self.lo, self.hi = lo, hi
@@ -128,8 +140,8 @@ class SlabPlan:
         self.local_rows = torch.cat([rows.new_zeros(1), rows]) if extra else rows
         rng = lambda a, b: torch.arange(a - start + extra, b - start + extra, device=dev)
         none = rows[:0]
-        self.send_left = rng(p[1], min(p[2], p[4])) if has_l else none
-        self.send_right = rng(max(p[3], p[1]), p[4]) if has_r else none
+        self.send_left = rng(p[1], p[2]) if has_l else none
+        self.send_right = rng(p[3], p[4]) if has_r else none
         self.recv_left = rng(p[0], p[1]) if has_l else none
         self.recv_right = rng(p[4], p[5]) if has_r else none
         self.owned_local = rng(p[1], p[4])
@@ -177,7 +189,10 @@ def sharded_backbone_forward(model, voxel_features, voxel_coords, batch_size, ra
     mark("start")
     coords = voxel_coords if voxel_coords.dtype == torch.int32 else voxel_coords.int()
     blocks = list(model.backbone)
-    win_x = max(int(b.win1_size[0]) for b in blocks)
+    # slab borders must lie on the window grid of EVERY block: the least common multiple of the x extents
+    win_x = 1
+    for b in blocks:
+        win_x = math.lcm(win_x, int(b.win1_size[0]))
     halo = max([(int(b.win2_size[0]) - int(b.win1_size[0]) + 1) // 2 for b in blocks if b.win2_size is not None] + [0])
     plan = SlabPlan(coords, win_x, halo, rank, world, grid_x=int(model.grid_size[0]),
                     sorted_single_sample=bool(sorted_by_x) and batch_size == 1)

@@ -118,3 +118,44 @@ def test_precision_modes_and_module_mirrors_on_cpu():
         vfe.eval()({"points": torch.zeros(3, 6), "batch_size": 1})
     bev = HeightCompression(AttrDict(NUM_BEV_FEATURES=64))
     assert [k for k in bev.state_dict() if k.endswith("weight")][0] == "compress_layers.0.weight"
+
+
+def test_drop_path_stochastic_branch():
+    """timm DropPath (mssvt_backbone.py:4, 42): per-row Bernoulli(keep) mask scaled by 1/keep in
+    training mode, identity in eval mode and at drop_prob 0"""
+    from mssvt_b200.mssvt_backbone import DropPath
+    torch.manual_seed(0)
+    x = torch.randn(20000, 8) + 3.0
+    dp = DropPath(0.3)
+    dp.eval()
+    assert dp(x) is x
+    dp.train()
+    y = dp(x)
+    dropped = (y == 0).all(1)
+    kept = ~dropped
+    assert abs(dropped.float().mean().item() - 0.3) < 0.02          # whole rows are dropped
+    assert torch.allclose(y[kept], x[kept] / 0.7)                   # survivors are rescaled
+    assert abs(y.mean().item() - x.mean().item()) < 0.05            # expectation is preserved
+    assert DropPath(0.0).train()(x) is x
+    # the backbone assigns linspace(0, 0.3, n_blocks - 1) by block position, nothing to the compress block
+    model = MixedScaleSparseTransformer(s0_model_cfg(), 64, list(S0_GRID), list(S0_VOXEL), list(S0_RANGE))
+    rates = [getattr(b.drop_path, "drop_prob", 0.0) for b in model.backbone]
+    assert rates[0] == 0.0 and abs(rates[1] - 0.15) < 1e-6 and abs(rates[2] - 0.3) < 1e-6 and rates[3] == 0.0
+
+
+def test_slab_plan_aligns_to_every_window_grid_and_rejects_narrow_slabs():
+    """one-frame sharding: borders on the lcm of the blocks' window extents; a slab narrower than the halo would
+    make neighbours disagree on the exchanged row sets, so it is refused up front (same error on every rank)"""
+    from mssvt_b200.sharding import SlabPlan
+    rng = np.random.default_rng(0)
+    x = np.sort(rng.integers(0, 120, 4000)).astype(np.int32)
+    coords = torch.from_numpy(np.stack([np.zeros_like(x), x % 7, x % 11, x], 1))
+    for sorted_flag in (False, True):
+        plans = [SlabPlan(coords, 6, 1, r, 3, grid_x=120, sorted_single_sample=sorted_flag) for r in range(3)]
+        assert all(p.bounds == plans[0].bounds for p in plans)
+        assert all(b % 6 == 0 for b in plans[0].bounds[:-1])
+        for a, b in zip(plans, plans[1:]):                      # neighbours agree on the exchanged row counts
+            assert a.send_right.numel() == b.recv_left.numel() and b.send_left.numel() == a.recv_right.numel()
+    narrow = torch.from_numpy(np.stack([np.zeros(64, np.int32)] * 3 + [np.arange(64, dtype=np.int32) % 2], 1))
+    with pytest.raises(ValueError, match="narrower than the halo"):
+        SlabPlan(narrow, 2, 3, 0, 4, grid_x=2)

@@ -1,0 +1,153 @@
+"""GPU: parity AT THE HEADLINE CONFIGURATION (BASELINE config 2: one 150 k-voxel S0 frame) against the CPU
+oracle run live on the same frame -- every precision mode, the eager forward and the CUDA-graph replay the
+benchmark times, with the chessboard patterns (1, 1, 1) and (1, 0, 2) -- plus the corners round 1 left without
+a direct test: with_bs_cnt / with_coords, window overflow (max_num_wins below the real window
+count) and in-place weight updates under a captured graph.
+
+Bars: indices bit-exact; features within 1e-4 * max|ref| (fp32, tf32x3), 2e-3 (tf32) and
+2e-2 with RMS <= 5e-3 (bf16)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import backbone as orc
+from mssvt_b200.config import s0_model_cfg
+from mssvt_b200.mssvt_backbone import MixedScaleSparseTransformer
+from mssvt_b200.synth import S0_GRID, S0_RANGE, S0_VOXEL, synth_frame
+
+pytestmark = pytest.mark.gpu
+
+MODES = (("fp32", 1e-4, None), ("tf32x3", 1e-4, None), ("tf32", 2e-3, None), ("bf16", 2e-2, 5e-3))
+
+
+def build(cfg):
+    torch.manual_seed(0)
+    model = MixedScaleSparseTransformer(cfg, 64, list(S0_GRID), list(S0_VOXEL), list(S0_RANGE))
+    state = {k: v.clone() for k, v in model.state_dict().items()}
+    return model, state
+
+
+def check(sp, want, tol, rms_tol, what):
+    assert torch.equal(sp.indices.cpu(), want.indices), what + ": output indices differ from the oracle"
+    got = sp.features.cpu()
+    scale = want.features.abs().max().item()
+    err = (got - want.features).abs().max().item()
+    assert err <= tol * scale, "%s: max|d| %.3e > %.1e * %.3f" % (what, err, tol, scale)
+    if rms_tol is not None:
+        rms = (got - want.features).pow(2).mean().sqrt().item()
+        assert rms <= rms_tol * scale, "%s: rms %.3e" % (what, rms)
+    return err / scale
+
+
+@pytest.mark.parametrize("patterns", [(1, 1, 1), (1, 0, 2)])
+def test_150k_frame_every_mode_eager_and_graph_vs_live_oracle(patterns):
+    feats, coords = synth_frame(0, 150000)
+    feats, coords = torch.from_numpy(feats), torch.from_numpy(coords)
+    cfg = s0_model_cfg(cbs_patterns=patterns)
+    model, state = build(cfg)
+    with torch.no_grad():
+        want = orc.backbone_forward(state, cfg, list(S0_GRID), list(S0_VOXEL), list(S0_RANGE), feats, coords, 1)
+    model = model.cuda().eval()
+    f, c = feats.cuda(), coords.cuda()
+    for mode, tol, rms_tol in MODES:
+        if mode not in model.PRECISIONS:
+            continue
+        model.set_precision(mode)
+        with torch.no_grad():
+            sp = model({"voxel_features": f, "voxel_coords": c.float(), "batch_size": 1})["encoded_spconv_tensor"]
+        e_eager = check(sp, want, tol, rms_tol, "%s eager %s" % (mode, patterns))
+        eager_feats = sp.features.clone()
+        graphed = model.capture({"voxel_features": f.clone(), "voxel_coords": c.clone(), "batch_size": 1})
+        graphed.replay()
+        sp = graphed.replay()
+        check(sp, want, tol, rms_tol, "%s graph %s" % (mode, patterns))
+        assert torch.equal(sp.features, eager_feats), "%s: graph replay differs from the eager forward" % mode
+        print("150k %s %s: max|d|/max|ref| = %.2e" % (patterns, mode, e_eager))
+        del graphed
+
+
+def test_with_bs_cnt_and_with_coords_direct():
+    """SURVEY 8 a8 (mssvt_backbone.py:124-137): mssvt_count_samples / mssvt_voxel_world_coords, bit-exact"""
+    _, coords = synth_frame(5, 3000, batch_size=3, crop=0.3)
+    coords = torch.from_numpy(coords)
+    model, _ = build(s0_model_cfg())
+    blk = model.backbone[0]
+    cnt = blk.with_bs_cnt(coords.cuda(), 3)
+    assert torch.equal(cnt.cpu(), orc.per_sample_count(coords, 3))
+    xyz = blk.with_coords(coords.cuda(), list(S0_RANGE), list(S0_VOXEL))
+    assert torch.equal(xyz.cpu(), orc.world_coords(coords, list(S0_RANGE), list(S0_VOXEL)))
+    # a batch with an empty sample in the middle, and the window-grid variant (window centres)
+    c2 = coords[coords[:, 0] != 1].contiguous()
+    assert torch.equal(blk.with_bs_cnt(c2.cuda(), 3).cpu(), orc.per_sample_count(c2, 3))
+    win = [S0_VOXEL[i] * 3 for i in range(3)]
+    wc = torch.stack([coords[:, 0], coords[:, 1] // 3, coords[:, 2] // 3, coords[:, 3] // 3], 1).contiguous()
+    assert torch.equal(blk.with_coords(wc.cuda(), list(S0_RANGE), win).cpu(),
+                       orc.world_coords(wc, list(S0_RANGE), win))
+
+
+@pytest.mark.parametrize("mode", ["fp32", "tf32x3"])
+def test_window_overflow_is_memory_safe_and_reported(mode):
+    """max_num_wins below the real window count (the reference writes out of bounds there): the kernels keep
+    the first max_num_wins windows, stay inside their allocations, and the error surfaces at the first look
+    at the output rows -- for the attention blocks as well as for the compress block"""
+    feats, coords = synth_frame(2, 6000, batch_size=2, crop=0.2)
+    f, c = torch.from_numpy(feats).cuda(), torch.from_numpy(coords).cuda()
+    cfg = s0_model_cfg()
+    cfg["PRECISION"] = mode
+    model, _ = build(cfg)
+    model = model.cuda().eval()
+    with torch.no_grad():
+        ok = model({"voxel_features": f, "voxel_coords": c.float(), "batch_size": 2})["encoded_spconv_tensor"]
+        ok_feats = ok.features.clone()
+        for blocks in ([0, 1, 2], [3]):
+            for i, b in enumerate(model.backbone):
+                b.max_num_wins = 100 if i in blocks else 90000
+            out = model({"voxel_features": f, "voxel_coords": c.float(), "batch_size": 2})["encoded_spconv_tensor"]
+            dense = out.dense()                        # no host sync, must not fault
+            torch.cuda.synchronize()
+            assert torch.isfinite(dense).all()
+            with pytest.raises(RuntimeError, match="max_num_wins"):
+                out.features
+        for b in model.backbone:
+            b.max_num_wins = 90000
+        again = model({"voxel_features": f, "voxel_coords": c.float(), "batch_size": 2})["encoded_spconv_tensor"]
+        assert torch.equal(again.features, ok_feats)   # nothing was corrupted by the overflowing runs
+
+
+def test_overflowing_window_list_is_compacted():
+    """two samples, the first one overflows: the kept windows of both samples are contiguous in the list"""
+    from mssvt_b200 import mssvt_ops
+    _, coords = synth_frame(3, 4000, batch_size=2, crop=0.2)
+    c = torch.from_numpy(coords).cuda()
+    grid = [S0_GRID[i] // 3 for i in range(3)]
+    full, _, cnt = mssvt_ops.window_partition_device([3, 3, 3], 90000, 2, 400000, grid, c)
+    n0, n1, total, dropped = cnt.tolist()
+    assert dropped == 0 and total == n0 + n1
+    keep = 50
+    part, _, cnt2 = mssvt_ops.window_partition_device([3, 3, 3], keep, 2, 400000, grid, c)
+    m0, m1, total2, dropped2 = cnt2.tolist()
+    assert (m0, m1) == (n0, n1) and total2 == 2 * keep and dropped2 == n0 + n1 - 2 * keep
+    assert torch.equal(part[:keep], full[:keep]) and torch.equal(part[keep:2 * keep], full[n0:n0 + keep])
+
+
+def test_graph_replay_follows_in_place_weight_updates():
+    """the captured graph reads the GEMM weights through packed copies: after an in-place parameter update the
+    replay re-packs them in place and matches the eager forward; a parameter whose storage moved raises"""
+    feats, coords = synth_frame(21, 5000, crop=0.2)
+    f, c = torch.from_numpy(feats).cuda(), torch.from_numpy(coords).cuda()
+    cfg = s0_model_cfg()
+    model, _ = build(cfg)
+    model = model.cuda().eval()
+    graphed = model.capture({"voxel_features": f, "voxel_coords": c, "batch_size": 1})
+    before = graphed.replay().features.clone()
+    with torch.no_grad():
+        for p in model.parameters():
+            p.mul_(1.05)
+        got = graphed.replay().features.clone()
+        want = model({"voxel_features": f, "voxel_coords": c, "batch_size": 1})["encoded_spconv_tensor"].features
+        assert torch.equal(got, want) and not torch.equal(got, before)
+        assert torch.equal(graphed.replay().features, want)     # and the eager call in between broke nothing
+        lin = model.backbone[0].linear1
+        lin.weight = torch.nn.Parameter(lin.weight.clone())
+    with pytest.raises(RuntimeError, match="storage"):
+        graphed.replay()
