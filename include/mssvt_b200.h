@@ -219,24 +219,27 @@ int mssvt_attention_tiles(int heads_per_group, int nq, int key_num_sample, int w
                           const float *win_cell, const float *range_min, int *tiles, int *tile_count,
                           int *win_rec, float *win_ctr, void *stream);
 
-/* The same step, task-parallel (one thread per query / distinct key / voxel over the whole frame) with
- * the K/V projection on the tcgen05 tensor cores (TF32 operands, fp32 everywhere else;
- * mssvt_b200/csrc/attention_tc.cu: 4 kernels).  Weights: pos_w [64][6] (nn.Module layout); packed by
- * mssvt_pack_operand_tf32: wkv* [64][32] per head group, wq_packed / wp_packed = the [64][64] block-diagonal
- * matrix of the two groups' [32][32] weights; rep_row / meta from mssvt_block_geometry; q_base =
- * mssvt_exclusive_scan(meta[:, 0]) (win_capacity + 1 ints), q_src = mssvt_query_src, vox_slot from the
- * geometry; tiles / tile_count / win_rec / win_ctr = mssvt_attention_tiles; scratch: 3 * num_voxels * 64 floats.
+/* The same step (mssvt_backbone.py:260-336 + mssvt_utils.py:88-157) as ONE tile kernel on the tcgen05 tensor
+ * cores (mssvt_b200/csrc/attention_tc.cu): per tile of <= 128 rows (distinct keys + real queries of consecutive
+ * windows of one head group) the positional embedding (Conv1d 6 -> C), the [K | V | Q] projection and the
+ * output projection run as tcgen05.mma (TF32 operands, or split 3xTF32 with terms = 3; fp32 accumulate);
+ * scores, softmax and AV of the tiny per-window matrices run on the FP32 pipe.
+ * Weights packed by mssvt_pack_operand_tf32: wpos_packed = [pos_w | pos_b | 0] as a [64][8] matrix, ALWAYS
+ * packed with terms = 3; wkvq0 / wkvq1 = per head group the [96][32] matrix [Wk; Wv; scale * Wq]; wp0 / wp1 = the
+ * group's [32][32] output projection (packed with `terms`); bq / bkv / bp: the nn.Linear biases.
+ * rep_row / meta from mssvt_block_geometry; q_base = mssvt_exclusive_scan(meta[:, 0]) (win_capacity + 1 ints),
+ * q_src = mssvt_query_src, vox_slot from the geometry; tiles / tile_count / win_rec / win_ctr =
+ * mssvt_attention_tiles; scratch: 3 * num_voxels * 64 floats (projected query rows in the last third).
  * Supported: C = 64, two groups of 32 channels with 1, 2 or 4 heads each, nq <= 32,
  * key_num_sample <= 63, cap1 <= 128; -1 otherwise. */
 int mssvt_block_attention_tc(int C, int heads_per_group, int nq, int key_num_sample, int cap1, int interp,
-                             int terms, float scale, const float *win_cell, const float *range_min,
-                             const float *pos_w, const float *pos_b, const float *wq_packed, const float *bq0,
-                             const float *bq1, const float *wkv0, const float *bkv0, const float *wkv1,
-                             const float *bkv1, const float *wp_packed, const float *bp0, const float *bp1,
-                             int win_capacity, const int *win_count_total,
-                             const int *win_list, const float *xn, const float *xyz, const int *q_row,
+                             int terms, float scale, const float *wpos_packed, const float *wkvq0,
+                             const float *wkvq1, const float *wp0, const float *wp1, const float *bq0,
+                             const float *bq1, const float *bkv0, const float *bkv1, const float *bp0,
+                             const float *bp1, int win_capacity, const int *win_count_total,
+                             const float *xn, const float *xyz, const int *q_row,
                              const int *rep_row, const int *meta, const int *q_base, const int *q_src,
-                             const int *vox_slot, const int *win1_row, const unsigned char *nn_idx,
+                             const int *vox_slot, const unsigned char *nn_idx,
                              const float *nn_w, const int *tiles, const int *tile_count, const int *win_rec,
                              const float *win_ctr, int num_voxels, float *scratch, float *merged, void *stream);
 

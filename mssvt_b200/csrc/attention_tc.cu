@@ -1,31 +1,38 @@
-// attention_tc.cu -- window attention of a two-window MsSVT block, task-parallel, with the K/V
-// projection on the tcgen05 tensor cores (sm_100a).  Same mathematics as k_block_attention in
-// attention.cu (mssvt_backbone.py:260-336, mssvt_utils.py:88-157), different mapping: instead of one
-// warp walking through a window, every stage runs with one THREAD per task over the whole frame:
+// attention_tc.cu -- window attention of a two-window MsSVT block as ONE tile kernel on the tcgen05 tensor
+// cores (sm_100a).  Same mathematics as k_block_attention in attention.cu (mssvt_backbone.py:260-336,
+// mssvt_utils.py:88-157), different mapping: every stage runs with one THREAD per row over the whole frame.
 //
-//   k_tc_linear   (tc_linear.cuh) q = (Wq (xn + posemb) + bq) * scale for every real query, on tcgen05
-//   k_tca_plan    once per frame geometry: packs consecutive windows of one scale into tiles of <= 128
-//                 distinct keys (windows without a real query are skipped), per-window offsets
-//   k_tca_keys    thread = distinct key of a window, 128 keys of ONE scale per tile.  The thread
-//                 gathers its 32-channel slice of the layer-normed row, adds the positional
-//                 embedding and stores the row, TF32-rounded, as row t of the A operand; one thread
-//                 issues 4 tcgen05.mma.kind::tf32 (M = 128, N = 64, K = 8): D = A Wkv^T into 64 TMEM
-//                 columns; tcgen05.ld hands every thread the 64 K|V values of ITS key (TMEM lane =
-//                 thread).  Scores against the window's queries, then softmax (with the multiplicity
-//                 of the masked key) and AV with one thread per (query, head, quarter head).
-//   k_tc_linear   output projection of the head outputs, on tcgen05
-//   k_tca_merge   thread = (win1 voxel, 16 channels): 1/d blend of the 3 nearest query rows -> merged
+//   k_tca_plan    once per frame geometry: packs consecutive windows of one scale into tiles of <= 128 ROWS
+//                 (the windows' distinct keys, then their real queries), per-window offsets
+//   k_tca_tile    thread = row of a tile of ONE scale (head group).  Per tile, five steps, four of them GEMMs
+//                 with M = 128 (lane = row) on tcgen05:
+//                 1. pos = [rel | centre | 1 | 0] (8 values, split hi / lo) -> shared memory; MMA 1 (K = 8,
+//                    always 3xTF32): the positional-embedding layer Conv1d(6 -> C) of every row -> TMEM
+//                 2. tcgen05.ld, ReLU, + the gathered 32-channel slice of the layer-normed row, TF32 round,
+//                    tcgen05.st IN PLACE: TMEM now holds the A operand of MMA 2 (A from TMEM, N = 96):
+//                    [K | V | Q * scale] = A [Wk; Wv; scale Wq]^T -- key rows use K | V, query rows use Q
+//                 3. scores q.k of every (key, query of its window, head) on the FP32 pipe from registers /
+//                    shared memory, additive -100 for the key that stands for the masked slots
+//                 4. softmax over the window's distinct keys (with the multiplicity of the masked key) and AV
+//                    with one thread per (query, head, quarter head); head outputs -> A operand in shared
+//                    memory; MMA 3: the output projection of the group (N = 32)
+//                 5. tcgen05.ld, + bias, projected query rows -> (#queries, 64) array
+//   k_tca_merge   (only without interpolation; with it the blend lives in mssvt_ffn_tc mode 2)
 //
-// Queries are addressed by a compact id (q_base[w] + slot, an exclusive scan over the windows done
-// with the geometry), so the three intermediates (q, head outputs, projected rows) are dense
-// (#queries, 64) fp32 arrays that live in L2.  Compared with the warp-per-window kernel this executes
-// ~5x fewer warp instructions, has no lane redundancy on the small per-window matrices, keeps five
-// 128-thread CTAs per SM in flight, and the 2048 FMAs per key run on the tensor pipe.
+// The per-window matrices are tiny (2.3 real queries x 6.5 / 16 distinct keys on a 150 k-voxel frame, 3.9 M
+// score triples per block): QK^T and AV stay on the FP32 pipe, where they cost ~8 us per block when packed
+// without divergence.  As tcgen05 tiles (M = 128 lanes = queries of ~10 windows, block-diagonal mask) they need
+// 128 x HEADS more TMEM columns per tile for the 4 x lane redundancy of the diagonal blocks -> one CTA per SM
+// instead of four, two more MMA round trips per tile, and the same number of exp / mask instructions; see
+// DESIGN.md section 5.  What DOES pay on the tensor cores are the three per-row linear maps above.
+//
+// Queries are addressed by a compact id (q_base[w] + slot, an exclusive scan over the windows done with the
+// geometry); the projected rows form a dense (#queries, 64) fp32 array that lives in L2.
 //
 // Supported shape (config S0 and relatives): C = 64, two head groups of 32 channels, 1/2/4 heads per
 // group, nq <= 32, key_num_sample <= 63, max_num_win1 <= 128.  Everything else runs on
-// k_block_attention.  Precision: TF32 operands for the Q, K/V and output projections; positional embedding,
-// scores, softmax, AV and interpolation are fp32.
+// k_block_attention.  Precision: TF32 (or split 3xTF32) operands for the positional embedding, the K / V / Q
+// and output projections; scores, softmax, AV and interpolation are fp32.
 #include "tc_linear.cuh"
 
 namespace mssvt {
@@ -38,82 +45,27 @@ namespace mssvt {
 #endif
 #define TCA_TW 32        // windows per tile (at most)
 #define TCA_SBUD 2048    // score slots per tile: sum over its windows of #queries x #keys x heads
+#define TCA_QMAX 48      // queries per tile (rows of the output-projection operand)
 #define TCA_PLAN_WB 64   // windows planned by one warp
 #define TCA_C 64
 #define TCA_SD 32
-#define TCA_VPITCH 36    // V row pitch in floats: 16-byte aligned, conflict-free for quarter warps
 
 struct TcAttnParams {
-    int nq, K, cap1, interp, heads, smax;      // smax = nq * heads: score slots per key task
+    int nq, K, cap1, interp, heads;
+    const float *wpos;                         // [64][8] = [pos_w | pos_b | 0], packed with terms = 3 ([hi | lo])
+    const float *wkvq[2];                      // per group [96][32] = [Wk; Wv; scale * Wq], packed (terms)
+    const float *wp[2];                        // per group [32][32] output projection, packed (terms)
+    const float *bq[2], *bkv[2], *bp[2];       // [32], [64], [32] per group
     float scale;
-    float win_cell[3], lo[3];
-    const float *pos_w, *pos_b;                // [64][6], [64]   (Conv1d weight (64, 6, 1))
-    const float *wq, *bq[2];                   // blockdiag(Wq0, Wq1) [64][64] packed, [32] x 2
-    const float *wkv[2], *bkv[2];              // [64][32] packed (mssvt_pack_operand_tf32), [64]
-    const float *wp, *bp[2];                   // blockdiag(Wp0, Wp1) [64][64] packed, [32] x 2
-};
-
-// [64][8] per channel: w0..w5, bias, 0
-__device__ __forceinline__ void stage_pos_weights(const TcAttnParams &P, float *sPos) {
-    for (int i = threadIdx.x; i < 64 * 8; i += blockDim.x) {
-        const int c = i >> 3, k = i & 7;
-        sPos[i] = k < 6 ? __ldg(P.pos_w + c * 6 + k) : k == 6 ? __ldg(P.pos_b + c) : 0.f;
-    }
-}
-
-__device__ __forceinline__ float pos_embed8(const float *sPos, int c, float rx, float ry, float rz, float cx,
-                                            float cy, float cz) {
-    const float4 wa = *(const float4 *)(sPos + c * 8), wb = *(const float4 *)(sPos + c * 8 + 4);
-    float a = wb.z;
-    a = fmaf(wa.x, rx, a); a = fmaf(wa.y, ry, a); a = fmaf(wa.z, rz, a);
-    a = fmaf(wa.w, cx, a); a = fmaf(wb.x, cy, a); a = fmaf(wb.y, cz, a);
-    return fmaxf(a, 0.f);
-}
-
-// ------------------------------------------------------------------------------- queries
-
-// rows of k_tc_linear for the query projection: compact query id -> layer-normed row + positional embedding
-struct TcaQueryRows {
-    int nq, win_cap;
-    float win_cell[3], lo[3];
-    const float *pos_w, *pos_b;
-    const int *win_count_total;
-    const int4 *win_list;
-    const float *xn, *xyz;
-    const int *q_row, *q_base, *q_src;
-    __device__ void init(float *sPos) const {
-        for (int i = threadIdx.x; i < 64 * 8; i += blockDim.x) {
-            const int c = i >> 3, k = i & 7;
-            sPos[i] = k < 6 ? __ldg(pos_w + c * 6 + k) : k == 6 ? __ldg(pos_b + c) : 0.f;
-        }
-    }
-    __device__ int rows() const { return __ldg(q_base + min(win_cap, __ldg(win_count_total))); }
-    struct Ctx { float rx, ry, rz, cx, cy, cz; };
-    __device__ const float4 *src(int qid, int half, Ctx &c) const {
-        const int s = __ldg(q_src + qid), w = s / nq;
-        const int row = __ldg(q_row + s);
-        const int4 win = __ldg(win_list + w);
-        c.cx = world_coord(win.w, win_cell[0], lo[0]);
-        c.cy = world_coord(win.z, win_cell[1], lo[1]);
-        c.cz = world_coord(win.y, win_cell[2], lo[2]);
-        c.rx = __fsub_rn(__ldg(xyz + 3 * (size_t)row), c.cx);
-        c.ry = __fsub_rn(__ldg(xyz + 3 * (size_t)row + 1), c.cy);
-        c.rz = __fsub_rn(__ldg(xyz + 3 * (size_t)row + 2), c.cz);
-        return (const float4 *)(xn + (size_t)row * TCA_C + half * TCA_SD);
-    }
-    __device__ void finish(const Ctx &c, int half, const float *sPos, float *in) const {
-#pragma unroll
-        for (int i = 0; i < TCA_SD; ++i) in[i] += pos_embed8(sPos, half * TCA_SD + i, c.rx, c.ry, c.rz, c.cx, c.cy, c.cz);
-    }
 };
 
 // ------------------------------------------------------------------------------- tile plan
 
-// A tile = consecutive windows of ONE scale whose distinct keys fill the 128 rows of an MMA.  The plan is
-// a function of the geometry only, so it is made once per frame and shared by every block that uses the
-// same window lists.  One warp plans TCA_PLAN_WB windows of one scale: lanes load 32 windows at a time,
-// the greedy cut is a 32-step scan over shuffled values (every lane runs it, lane i keeps step i).
-// Windows without a real query get no key tasks at all (nobody would read their K/V).
+// A tile = consecutive windows of ONE scale whose rows -- distinct keys + real queries -- fill the 128 rows of
+// an MMA.  The plan is a function of the geometry only, so it is made once per frame and shared by every block
+// that uses the same window lists.  One warp plans TCA_PLAN_WB windows of one scale: lanes load 32 windows at
+// a time, the greedy cut is a 32-step scan over shuffled values (every lane runs it, lane i keeps step i).
+// Windows without a real query get no rows at all (nobody would read their K/V).
 __global__ void __launch_bounds__(256)
 k_tca_plan(int heads, int win_cap, const int *__restrict__ win_count_total, const int4 *__restrict__ win_list,
            const int4 *__restrict__ meta, const int *__restrict__ q_base, float3 win_cell, float3 lo,
@@ -125,7 +77,7 @@ k_tca_plan(int heads, int win_cap, const int *__restrict__ win_count_total, cons
     const int g = wid & 1, w0 = (wid >> 1) * TCA_PLAN_WB;
     if (w0 >= num_wins) return;
     const int w1 = min(w0 + TCA_PLAN_WB, num_wins);
-    int ts = w0, a = 0, aq = 0, as = 0, nw = 0;  // open tile: first window, key tasks, queries, score slots, windows
+    int ts = w0, a = 0, aq = 0, as = 0, nw = 0;  // open tile: first window, key rows, query rows, score slots, windows
     for (int wb = w0; wb < w1; wb += 32) {
         const int w = wb + lane;
         int nqr = 0, r = 0, mult = 0, qb = 0;
@@ -144,7 +96,7 @@ k_tca_plan(int heads, int win_cap, const int *__restrict__ win_count_total, cons
         for (int i = 0; i < n; ++i) {
             const int ri = __shfl_sync(0xffffffffu, r, i), qi = __shfl_sync(0xffffffffu, nqr, i);
             const int si = qi * ri * heads;
-            if (nw > 0 && (a + ri > TCA_THREADS || aq + qi > TCA_THREADS || as + si > TCA_SBUD || nw == TCA_TW)) {
+            if (nw > 0 && (a + aq + ri + qi > TCA_THREADS || aq + qi > TCA_QMAX || as + si > TCA_SBUD || nw == TCA_TW)) {
                 if (lane == 0 && a > 0) tiles[(size_t)g * win_cap + atomicAdd(tile_count + g, 1)] = make_int2(ts, nw);
                 ts = wb + i; a = aq = as = nw = 0;
             }
@@ -157,34 +109,88 @@ k_tca_plan(int heads, int win_cap, const int *__restrict__ win_count_total, cons
     if (lane == 0 && a > 0) tiles[(size_t)g * win_cap + atomicAdd(tile_count + g, 1)] = make_int2(ts, nw);
 }
 
-// ------------------------------------------------------------------------------- keys + attention
+// ------------------------------------------------------------------------------- the tile kernel
 
-// largest l in [0, n) with off[l] <= v (off[n] > v)
-__device__ __forceinline__ int tile_window(const int *off, int n, int v) {
+// shared-memory carve-up of k_tca_tile (bytes); NT = operand tiles per matrix: hi [, lo]
+struct TcaSmem {
+    int wpos, wkvq, wp, apos, ao, rows, hdr, misc, total;
+    __host__ __device__ explicit TcaSmem(int nt) {
+        wpos = 0;                                  // [hi | lo] x [2 chunks][32][16 B]                    2 KB
+        wkvq = wpos + 2048;                        // nt x [8 chunks][96][16 B]                          12 KB each
+        wp = wkvq + nt * 96 * 32 * 4;              // nt x [8 chunks][32][16 B]                           4 KB each
+        apos = wp + nt * 32 * 32 * 4;              // [hi | lo] x [2 chunks][128][16 B]; later the scores  8 KB
+        ao = apos + 8192;                          // nt x [QMAX / 8][8 chunks][8][16 B]                   8 KB each
+        rows = ao + nt * TCA_QMAX * TCA_SD * 4;    // gather staging, later V / Q rows [128][32]          16 KB
+        hdr = rows + TCA_THREADS * TCA_SD * 4;     // (the MMA reads 128 rows of `ao`: it runs into `rows`)
+        misc = hdr + 2 * TCA_TW * 32;              // 2 x {window records [TW] int4, window centres [TW] float4}
+        total = misc + 128 * 4 + TCA_QMAX * 4 + 8 + 16 + 128;   // biases, sQwin, barrier
+    }
+};
+
+// window records of a tile: offsets of the key rows / query rows are packed in rec.z (see k_tca_plan)
+__device__ __forceinline__ int rec_koff(const int4 &r) { return r.z & 0xff; }
+__device__ __forceinline__ int rec_qoff(const int4 &r) { return (r.z >> 8) & 0xff; }
+// largest l in [0, n) whose offset (bits [shift, shift + 8) of rec.z) is <= v
+__device__ __forceinline__ int tile_window(const int4 *rec, int n, int shift, int v) {
     int lo = 0, hi = n;
     while (hi - lo > 1) {
         const int mid = (lo + hi) >> 1;
-        if (off[mid] <= v) lo = mid; else hi = mid;
+        if (((rec[mid].z >> shift) & 0xff) <= v) lo = mid; else hi = mid;
     }
     return lo;
 }
 
+__device__ __forceinline__ float ex2_fast(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// 8 lanes per 128-byte slice: the warp copies the rows of its 32 lanes (my_src: this lane's row, nullptr = none)
+// asynchronously into its 4 KB staging area (16-byte chunks XOR-swizzled by the row)
+__device__ __forceinline__ void warp_rows_copy_async(char *stg, const float4 *my_src) {
+    const int lane = threadIdx.x & 31, st_row = lane >> 3, st_ch = lane & 7;
+    const uint32_t base = smem_u32(stg);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int rr = 4 * i + st_row;
+        const float4 *p = (const float4 *)__shfl_sync(0xffffffffu, (unsigned long long)my_src, rr);
+        if (p) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(base + (uint32_t)(rr * 128 + ((st_ch ^ (rr & 7)) << 4))),
+                            "l"(p + st_ch) : "memory");
+    }
+}
+
+// Software pipeline over the tiles of a CTA.  The loads of a tile form a chain of dependent global accesses
+// (tile record -> window records -> row ids -> coordinates + feature rows, ~3 L2 latencies); every link of
+// tile i + 1 is issued one phase of tile i ahead of its use and lands in shared memory (cp.async) or in a few
+// registers, so that a tile starts with its operands on the way:
+//     window records of i + 1: cp.async while tile i builds its positional operand
+//     row ids of i + 1:        loaded while MMA 2 of tile i runs
+//     feature rows of i + 1:   cp.async into the staging area once tile i is done with it (after softmax / AV)
 template <int HEADS, int TERMS>
-__global__ void __launch_bounds__(TCA_THREADS, TERMS == 3 ? 3 : 5)
-k_tca_keys(TcAttnParams P, int win_cap, const int2 *__restrict__ tiles, const int *__restrict__ tile_count,
+__global__ void __launch_bounds__(TCA_THREADS, TERMS == 3 ? 3 : 4)
+k_tca_tile(TcAttnParams P, int win_cap, const int2 *__restrict__ tiles, const int *__restrict__ tile_count,
            const int4 *__restrict__ win_rec, const float4 *__restrict__ win_ctr, const float *__restrict__ xn,
-           const float *__restrict__ xyz, const int *__restrict__ rep_row, const float *__restrict__ Qbuf,
-           float *__restrict__ Obuf) {
+           const float *__restrict__ xyz, const int *__restrict__ rep_row, const int *__restrict__ q_row,
+           float *__restrict__ Pbuf) {
     constexpr int HD = TCA_SD / HEADS;
-    constexpr int DPT = HD / 4;  // channels per thread in the AV phase
+    constexpr int NT = TERMS == 3 ? 2 : 1;       // operand tiles: hi [, lo] (3xTF32, tc_common.cuh)
+    // TMEM: 128 columns; the 3xTF32 kernel takes 32 more (low half of the A operand) as a SECOND allocation:
+    // 160 columns per CTA keep three CTAs on an SM, one 256-column allocation would allow two
     extern __shared__ __align__(128) char smem_raw[];
     const int tid = threadIdx.x, warp = tid >> 5;
-    const int K = P.K;
+    const int K = P.K, nq = P.nq;
+#ifdef MSSVT_TRACE
+    const long long t_entry = clock64();
+#endif
     pdl_launch_dependents();
     pdl_wait();  // (the scale of this CTA, hence its weights, depends on the tile counts: nothing to do before)
+#ifdef MSSVT_TRACE
+    const long long t_pdl = clock64();
+#endif
 
-    // ---- every CTA works on one scale for its whole life (8 KB of weights instead of 16); the CTAs of the
-    //      two scales are interleaved over the grid in proportion to the tile counts
+    // ---- every CTA works on one scale (head group) for its whole life; the CTAs of the two scales are
+    //      interleaved over the grid in proportion to the tile counts
     const int T0 = __ldg(tile_count), T1 = __ldg(tile_count + 1), G = gridDim.x, b = blockIdx.x;
     int G0 = T0 == 0 ? 0 : T1 == 0 ? G : (int)(((long long)G * T0 + (T0 + T1) / 2) / (T0 + T1));
     if (T0 > 0 && T1 > 0) G0 = min(max(G0, 1), G - 1);
@@ -194,222 +200,387 @@ k_tca_keys(TcAttnParams P, int win_cap, const int2 *__restrict__ tiles, const in
     tiles += (size_t)g * win_cap;
     win_rec += (size_t)g * win_cap;
 
-    // ---- shared memory: 8 KB weights + 18 KB A/V (aliased) + 8 KB scores + bookkeeping = ~38 KB
-    constexpr int NT = TERMS == 3 ? 2 : 1;                  // operand tiles: hi [, lo] (3xTF32, tc_common.cuh)
-    constexpr int A_TILE = TCA_THREADS * TCA_SD * 4;        // 16 KB
-    constexpr int A_REGION = NT * A_TILE > TCA_THREADS * TCA_VPITCH * 4 ? NT * A_TILE : TCA_THREADS * TCA_VPITCH * 4;
-    char *sWkv = smem_raw;                                  // NT x [64 x 32] canonical, TF32      8 KB each
-    char *sA = sWkv + NT * 64 * 32 * 4;                     // NT x [128 x 32] canonical (16 KB each) ...
-    float *sV = (float *)sA;                                // ... reused as V [128][VPITCH] after the MMA
-    float *sPos = (float *)(sA + A_REGION);                 // [32][8] (this scale's channels)
-    float *sBkv = sPos + 32 * 8;                            // [64]
-    float *sS = sBkv + 64;                                  // [SBUD] scores: window-major, [key][query][head]
-    float4 *sCtr = (float4 *)(sS + TCA_SBUD);               // [TW] window centres
-    int4 *sRec = (int4 *)(sCtr + TCA_TW);                   // [TW] {q_base, nqr | r << 8 | mult << 16, offsets}
-    int *sToff = (int *)(sRec + TCA_TW);                    // [TW + 1] first key task of each window
-    int *sQoff = sToff + TCA_TW + 1;                        // [TW + 1] first query of each window
-    uint64_t *sBar = (uint64_t *)(sQoff + TCA_TW + 1);      // (2 * (TW + 1) ints: 8-byte aligned)
+    const TcaSmem L(NT);
+    char *sWpos = smem_raw + L.wpos, *sWkvq = smem_raw + L.wkvq, *sWp = smem_raw + L.wp;
+    char *sApos = smem_raw + L.apos, *sAO = smem_raw + L.ao, *sRows = smem_raw + L.rows;
+    float *sS = (float *)sApos;                             // [SBUD] scores: window-major, [key][query][head]
+    char *sHdr = smem_raw + L.hdr;                          // 2 x {int4 rec[TW], float4 ctr[TW]}
+    float *sBias = (float *)(smem_raw + L.misc);            // [32] bq * scale, [32] bv, [32] bp (+ pad)
+    int *sQwin = (int *)(sBias + 128);                      // [QMAX] window of each query of the tile
+    uint64_t *sBar = (uint64_t *)(sQwin + TCA_QMAX);
     uint32_t *sTmem = (uint32_t *)(sBar + 1);
+    char *stg = sRows + warp * 4096;                        // this warp's staging area
 
-    stage_packed(P.wkv[g], NT * 64 * 32, sWkv);
-    for (int i = tid; i < 32 * 8; i += TCA_THREADS) {
-        const int c = g * TCA_SD + (i >> 3), k = i & 7;
-        sPos[i] = k < 6 ? __ldg(P.pos_w + c * 6 + k) : k == 6 ? __ldg(P.pos_b + c) : 0.f;
+    // weights of this scale: asynchronous 16-byte copies, waited for before the first MMA
+    {
+        const uint32_t d = smem_u32(sWpos);
+        // packed [64][8] hi | lo: plane = chunk * 1024 + row * 16 (+ 2048 for lo); this scale's rows g*32 ..
+        for (int i = tid; i < 128; i += TCA_THREADS) {   // i = (hl, chunk, row)
+            const int hl = i >> 6, ch = (i >> 5) & 1, n = i & 31;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + (uint32_t)(hl * 1024 + ch * 512 + n * 16)),
+                         "l"((const char *)P.wpos + hl * 2048 + ch * 1024 + (g * 32 + n) * 16) : "memory");
+        }
     }
-    if (tid < 64) sBkv[tid] = __ldg(P.bkv[g] + tid);
+    stage_packed(P.wkvq[g], NT * 96 * 32, sWkvq);
+    stage_packed(P.wp[g], NT * 32 * 32, sWp);
+    if (tid < 32) {
+        sBias[tid] = __ldg(P.bq[g] + tid) * P.scale;
+        sBias[32 + tid] = __ldg(P.bkv[g] + 32 + tid);
+        sBias[64 + tid] = __ldg(P.bp[g] + tid);
+    }
     const uint32_t bar = smem_u32(sBar);
     if (tid == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0) tmem_alloc(smem_u32(sTmem), 64);
+#ifdef MSSVT_TRACE
+    const long long t_stage = clock64();
+#endif
+    if (warp == 0) {
+        tmem_alloc(smem_u32(sTmem), 128, TERMS != 3);
+        if (TERMS == 3) tmem_alloc(smem_u32(sTmem + 1), 32);
+    }
+#ifdef MSSVT_TRACE
+    const long long t_alloc = clock64();
+#endif
+
+    // header of a tile (window records + centres) -> buffer `buf`, asynchronously
+    auto header_async = [&](int2 tl, int buf) {
+        if (tid < tl.y) {
+            const uint32_t d = smem_u32(sHdr + buf * (TCA_TW * 32));
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d + (uint32_t)tid * 16u), "l"(win_rec + tl.x + tid) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d + (uint32_t)(TCA_TW * 16 + tid * 16)), "l"(win_ctr + tl.x + tid) : "memory");
+        }
+    };
+    // role of this thread's row in a tile whose header is in shared memory: kind 1 = distinct key of window l,
+    // 2 = real query of window l, 0 = idle; -> global feature row (issued load)
+    auto role = [&](int2 tl, const int4 *rec, int &kind, int &l, int &row) {
+        const int4 last = rec[tl.y - 1];
+        const int nT = rec_koff(last) + ((last.y >> 8) & 0xff), nQ = rec_qoff(last) + (last.y & 0xff);
+        kind = tid < nT ? 1 : tid < nT + nQ ? 2 : 0;
+        l = 0; row = 0;
+        if (kind == 1) {
+            l = tile_window(rec, tl.y, 0, tid);
+            row = __ldg(rep_row + (size_t)(tl.x + l) * 2 * K + g * K + (tid - rec_koff(rec[l])));
+        } else if (kind == 2) {
+            l = tile_window(rec, tl.y, 8, tid - nT);
+            row = __ldg(q_row + (size_t)(tl.x + l) * nq + (tid - nT - rec_qoff(rec[l])));
+        }
+    };
+
+    int2 tl = first < T ? __ldg(tiles + first) : make_int2(0, 0);
+    int2 tl_next = first + stride < T ? __ldg(tiles + first + stride) : make_int2(0, 0);
+    if (first < T) header_async(tl, 0);
+    stage_packed_wait();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_d = *sTmem;
+#ifdef MSSVT_TRACE
+    if (tid == 0 && (blockIdx.x % 97) == 0)
+        printf("tile kernel prologue (block %d): pdl wait %lld | stage issue %lld | tmem alloc %lld | copies + sync %lld clk\n",
+               blockIdx.x, t_pdl - t_entry, t_stage - t_pdl, t_alloc - t_stage, clock64() - t_alloc);
+#endif
+    const uint32_t tm = *sTmem;                              // cols [0,32): pos -> A1 -> projection, [32,128): K|V|Q
     const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
-    const uint32_t idesc = umma_idesc_tf32(128, 64);
-    const uint32_t sA_u = smem_u32(sA), sWkv_u = smem_u32(sWkv);
-    const uint32_t a_lbo = TCA_THREADS * 16, w_lbo = 64 * 16;
-    const uint32_t my_row_off = (uint32_t)(tid >> 3) * 128u + (uint32_t)(tid & 7) * 16u;
+    const uint32_t tm_a = tm, tm_k = tm + 32u, tm_v = tm + 64u, tm_q = tm + 96u;
+    const uint32_t tm_alo = TERMS == 3 ? sTmem[1] : 0u;
+    const uint32_t id_n32 = umma_idesc_tf32(128, 32), id_n96 = umma_idesc_tf32(128, 96);
+    const uint32_t sWpos_u = smem_u32(sWpos), sWkvq_u = smem_u32(sWkvq), sWp_u = smem_u32(sWp);
+    const uint32_t sApos_u = smem_u32(sApos), sAO_u = smem_u32(sAO);
+    const uint32_t row_off = (uint32_t)(tid >> 3) * 128u + (uint32_t)(tid & 7) * 16u;   // canonical 8-row groups
     uint32_t phase = 0;
 
-#ifdef MSSVT_TRACE
-    long long tr[12] = {0};
-#endif
-    int2 tl_next = first < T ? __ldg(tiles + first) : make_int2(0, 0);
-    for (int t = first; t < T; t += stride) {
-        KTRACE(0);
-        // the tile record is fetched one tile ahead; the next tile's window records and key lists are
-        // pulled into L1 while this tile's MMA runs, so that the chain tile -> windows -> key rows ->
-        // features starts from cached lines
-        const int2 tl = tl_next;
-        if (t + stride < T) tl_next = __ldg(tiles + t + stride);
-        const int nwin = tl.y;
-        if (tid < nwin) {
-            const int4 rec = __ldg(win_rec + tl.x + tid);
-            sRec[tid] = rec;
-            sCtr[tid] = __ldg(win_ctr + tl.x + tid);
-            sToff[tid] = rec.z & 0xff;
-            sQoff[tid] = (rec.z >> 8) & 0xff;
-            if (tid == nwin - 1) {
-                sToff[nwin] = (rec.z & 0xff) + ((rec.y >> 8) & 0xff);
-                sQoff[nwin] = ((rec.z >> 8) & 0xff) + (rec.y & 0xff);
-            }
-        }
-        __syncthreads();
-        KTRACE(1);
-        const int nT = sToff[nwin], nQ = sQoff[nwin];
-        // the tile's query rows (contiguous ids) are read after the MMA: pull their 128-byte halves into L1 now
-        if (tid < nQ) prefetch_l1(Qbuf + (size_t)(sRec[0].x + tid) * TCA_C + g * TCA_SD);
+    // pipeline prologue: role, coordinates and feature row of the first tile
+    int kind = 0, l = 0, row = 0;
+    float px = 0.f, py = 0.f, pz = 0.f;
+    if (first < T) {
+        role(tl, (const int4 *)sHdr, kind, l, row);
+        if (kind) { px = __ldg(xyz + 3 * (size_t)row); py = __ldg(xyz + 3 * (size_t)row + 1); pz = __ldg(xyz + 3 * (size_t)row + 2); }
+        warp_rows_copy_async(stg, kind ? (const float4 *)(xn + (size_t)row * TCA_C + g * TCA_SD) : nullptr);
+    }
 
-        // ---- key task -> row t of the A operand
-        const bool is_task = tid < nT;
-        int j = 0, nqr = 0, q0 = 0, soff = 0;
+#ifdef MSSVT_TRACE
+    long long tr[16] = {0};
+#endif
+    int buf = 0;
+    for (int t = first; t < T; t += stride, buf ^= 1) {
+        KTRACE(0);
+        const int4 *sRec = (const int4 *)(sHdr + buf * (TCA_TW * 32));
+        const float4 *sCtr = (const float4 *)(sRec + TCA_TW);
+        const int nwin = tl.y;
+        const bool more = t + stride < T;
+        if (more) header_async(tl_next, buf ^ 1);            // the next tile's window records: on their way now
+        const int2 tl_after = t + 2 * stride < T ? __ldg(tiles + t + 2 * stride) : make_int2(0, 0);
+        const int4 last = sRec[nwin - 1];
+        const int nT = rec_koff(last) + ((last.y >> 8) & 0xff), nQ = rec_qoff(last) + (last.y & 0xff);
+        const bool is_key = kind == 1, is_query = kind == 2;
+        int j = 0, nqr = 0, soff = 0, qrow0 = 0;
         bool masked = false;
-        float rx = 0.f, ry = 0.f, rz = 0.f;  // masked key: relative offset zeroed
-        float4 ctr = make_float4(0.f, 0.f, 0.f, 0.f);
-        const float4 *src = nullptr;
-        if (is_task) {
-            const int l = tile_window(sToff, nwin, tid);
-            const int4 rec = sRec[l];
-            j = tid - (rec.z & 0xff);
-            nqr = rec.y & 0xff; q0 = rec.x; soff = rec.z >> 16;
-            const int r = (rec.y >> 8) & 0xff, mult = rec.y >> 16;
-            masked = mult > 0 && j == r - 1;  // last distinct key stands for all masked slots
-            const int row = __ldg(rep_row + (size_t)(tl.x + l) * 2 * K + g * K + j);
-            ctr = sCtr[l];
-            if (!masked) {  // (coordinates and features travel together: the subtraction waits below)
-                rx = __ldg(xyz + 3 * (size_t)row); ry = __ldg(xyz + 3 * (size_t)row + 1);
-                rz = __ldg(xyz + 3 * (size_t)row + 2);
-            }
-            src = (const float4 *)(xn + (size_t)row * TCA_C + g * TCA_SD);
-        }
         {
-            // the warp gathers its 32 rows together (8 lanes per 128-byte slice) through the A tile's memory
-            float4 xv[TCA_SD / 4];
-            KTRACE(2);
-            warp_rows_load<true>(sA + warp * 4096, src, xv);
-            if (is_task && !masked) { rx = __fsub_rn(rx, ctr.x); ry = __fsub_rn(ry, ctr.y); rz = __fsub_rn(rz, ctr.z); }
-            KTRACE(3);
-            __syncthreads();
-            KTRACE(4);  // every warp is done with its staging area: the A tile may be written
-            if (is_task) {
-#pragma unroll
-                for (int c4 = 0; c4 < TCA_SD / 4; ++c4) {
-                    const float4 v = xv[c4];
-                    float4 o, hi, lo;
-                    o.x = v.x + pos_embed8(sPos, 4 * c4, rx, ry, rz, ctr.x, ctr.y, ctr.z);
-                    o.y = v.y + pos_embed8(sPos, 4 * c4 + 1, rx, ry, rz, ctr.x, ctr.y, ctr.z);
-                    o.z = v.z + pos_embed8(sPos, 4 * c4 + 2, rx, ry, rz, ctr.x, ctr.y, ctr.z);
-                    o.w = v.w + pos_embed8(sPos, 4 * c4 + 3, rx, ry, rz, ctr.x, ctr.y, ctr.z);
-                    split_tf32(o, hi, lo);
-                    *(float4 *)(sA + (uint32_t)c4 * a_lbo + my_row_off) = hi;
-                    if (TERMS == 3) *(float4 *)(sA + A_TILE + (uint32_t)c4 * a_lbo + my_row_off) = lo;
+            // ---- 1. positional-embedding input [rel | centre | 1 | 0], split hi / lo, canonical K-major [128][8]
+            float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1 = p0;
+            if (kind) {
+                const int4 rec = sRec[l];
+                const float4 ctr = sCtr[l];
+                if (is_key) {
+                    j = tid - rec_koff(rec);
+                    nqr = rec.y & 0xff; soff = rec.z >> 16; qrow0 = nT + rec_qoff(rec);
+                    const int r = (rec.y >> 8) & 0xff, mult = rec.y >> 16;
+                    masked = mult > 0 && j == r - 1;  // last distinct key stands for all masked slots
                 }
+                else sQwin[tid - nT] = l;
+                // masked key: relative offset zeroed
+                p0 = masked ? make_float4(0.f, 0.f, 0.f, ctr.x)
+                            : make_float4(__fsub_rn(px, ctr.x), __fsub_rn(py, ctr.y), __fsub_rn(pz, ctr.z), ctr.x);
+                p1 = make_float4(ctr.y, ctr.z, 1.f, 0.f);
             }
+            float4 hi, lo;
+            split_tf32(p0, hi, lo);
+            *(float4 *)(sApos + row_off) = hi;
+            *(float4 *)(sApos + 4096 + row_off) = lo;
+            split_tf32(p1, hi, lo);
+            *(float4 *)(sApos + 2048 + row_off) = hi;
+            *(float4 *)(sApos + 4096 + 2048 + row_off) = lo;
         }
-        KTRACE(5);
-        stage_packed_wait();
         fence_async_smem();
         __syncthreads();
-        KTRACE(6);
-        // ---- D = A Wkv^T: K in TMEM columns 0..31, V in 32..63
+        KTRACE(1);
+        if (tid == 0) {
+            tc_fence_after();
+            const uint64_t ah = umma_smem_desc(sApos_u, 2048, 128), al = umma_smem_desc(sApos_u + 4096u, 2048, 128);
+            const uint64_t wh = umma_smem_desc(sWpos_u, 512, 128), wl = umma_smem_desc(sWpos_u + 1024u, 512, 128);
+            umma_tf32(tm_a, ah, wh, id_n32, 0u);
+            umma_tf32(tm_a, al, wh, id_n32, 1u);
+            umma_tf32(tm_a, ah, wl, id_n32, 1u);
+            umma_commit(bar);
+        }
+        // the warp's 32 feature rows (copied by its own lanes) have landed, and so has the next header
+        float4 xv[TCA_SD / 4];
+        stage_packed_wait();
+        __syncwarp();
+        {
+            const int lane = tid & 31;
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                xv[q] = kind ? *(const float4 *)(stg + lane * 128 + ((q ^ (lane & 7)) << 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        KTRACE(2);
+        mbar_wait(bar, phase);
+        phase ^= 1u;
+        tc_fence_after();
+        KTRACE(3);
+        {
+            // ---- 2. A1 = xn slice + relu(pos), TF32, written back over the accumulator (A operand from TMEM)
+            float d[TCA_SD];
+            tmem_ld32(tm_a + lane_off, d);
+            if (TERMS == 3) {
+                float lo[TCA_SD];
+#pragma unroll
+                for (int c4 = 0; c4 < TCA_SD / 4; ++c4) {
+                    split_tf32(xv[c4].x + fmaxf(d[4 * c4], 0.f), d[4 * c4], lo[4 * c4]);
+                    split_tf32(xv[c4].y + fmaxf(d[4 * c4 + 1], 0.f), d[4 * c4 + 1], lo[4 * c4 + 1]);
+                    split_tf32(xv[c4].z + fmaxf(d[4 * c4 + 2], 0.f), d[4 * c4 + 2], lo[4 * c4 + 2]);
+                    split_tf32(xv[c4].w + fmaxf(d[4 * c4 + 3], 0.f), d[4 * c4 + 3], lo[4 * c4 + 3]);
+                }
+                tmem_st32(tm_alo + lane_off, lo);
+            } else {
+#pragma unroll
+                for (int c4 = 0; c4 < TCA_SD / 4; ++c4) {
+                    d[4 * c4] = to_tf32(xv[c4].x + fmaxf(d[4 * c4], 0.f));
+                    d[4 * c4 + 1] = to_tf32(xv[c4].y + fmaxf(d[4 * c4 + 1], 0.f));
+                    d[4 * c4 + 2] = to_tf32(xv[c4].z + fmaxf(d[4 * c4 + 2], 0.f));
+                    d[4 * c4 + 3] = to_tf32(xv[c4].w + fmaxf(d[4 * c4 + 3], 0.f));
+                }
+            }
+            tmem_st32(tm_a + lane_off, d);
+            tmem_st_wait();
+        }
+        tc_fence_before();
+        __syncthreads();   // (also: every thread's header copies are complete -> the next header is visible)
+        KTRACE(4);
+        // ---- [K | V | Q] = A1 [Wk; Wv; scale Wq]^T: K in TMEM columns 32..63, V in 64..95, Q in 96..127
         if (tid == 0) {
             tc_fence_after();
 #pragma unroll
-            for (int k = 0; k < TCA_SD / 8; ++k)
-                umma_step<TERMS>(tmem_d, sA_u + (uint32_t)k * 2u * a_lbo, a_lbo, A_TILE,
-                                 sWkv_u + (uint32_t)k * 2u * w_lbo, w_lbo, 64 * 32 * 4, idesc, k == 0);
+            for (int k = 0; k < TCA_SD / 8; ++k) {
+                const uint64_t wh = umma_smem_desc(sWkvq_u + (uint32_t)k * 2u * 1536u, 1536, 128);
+                umma_tf32_ts(tm_k, tm_a + (uint32_t)k * 8u, wh, id_n96, k > 0 ? 1u : 0u);
+                if (TERMS == 3) {
+                    umma_tf32_ts(tm_k, tm_alo + (uint32_t)k * 8u, wh, id_n96, 1u);
+                    umma_tf32_ts(tm_k, tm_a + (uint32_t)k * 8u,
+                                 umma_smem_desc(sWkvq_u + 96u * 32u * 4u + (uint32_t)k * 2u * 1536u, 1536, 128), id_n96, 1u);
+                }
+            }
             umma_commit(bar);
         }
-        if (t + stride < T) {  // next tile: window records (16 B each), centres, key lists (K ints per window)
-            if (tid < tl_next.y) prefetch_l1(rep_row + (size_t)(tl_next.x + tid) * 2 * K + g * K);
-            else if (tid < tl_next.y + (tl_next.y + 7) / 8 + 1) prefetch_l1(win_rec + tl_next.x + 8 * (tid - tl_next.y));
-            else if (tid < tl_next.y + 2 * ((tl_next.y + 7) / 8 + 1))
-                prefetch_l1(win_ctr + tl_next.x + 8 * (tid - tl_next.y - (tl_next.y + 7) / 8 - 1));
-        }
+        // while the MMA runs: role and feature row id of this thread in the NEXT tile
+        int n_kind = 0, n_l = 0, n_row = 0;
+        if (more) role(tl_next, (const int4 *)(sHdr + (buf ^ 1) * (TCA_TW * 32)), n_kind, n_l, n_row);
         mbar_wait(bar, phase);
-        KTRACE(7);
         phase ^= 1u;
         tc_fence_after();
-        // ---- this thread's key: K|V back from TMEM; scores against its window's queries
+        KTRACE(5);
+        // ---- rows back from TMEM: V of the key rows and Q (+ bias) of the query rows -> shared memory (16-byte
+        //      chunks XOR-swizzled by the row), K of this thread's key stays in registers.  Biases: q.(k + bk)
+        //      shifts every score of a query by the same q.bk, which the softmax cancels, so bk is dropped;
+        //      sum_i p_i (v_i + bv) = sum_i p_i v_i + bv, so bv is added once per output below.
+        float kk[TCA_SD];
         {
-            float kk[TCA_SD], vv[TCA_SD];
-            tmem_ld32(tmem_d + lane_off, kk);
-            tmem_ld32(tmem_d + lane_off + 32u, vv);
-            tc_fence_before();
-            __syncthreads();  // every thread has its K|V in registers: the A tile may become V
-            if (is_task) {
-                // Biases: q.(k + bk) shifts every score of a query by the same q.bk, which the softmax
-                // cancels, so bk is dropped; sum_i p_i (v_i + bv) = sum_i p_i v_i + bv, so bv is added once
-                // per output below instead of once per key here.
+            const int w_lo = warp * 32, w_hi = w_lo + 32;
+            const bool warp_keys = w_lo < nT, warp_queries = w_hi > nT && w_lo < nT + nQ;   // (warp-uniform)
+            float4 *my = (float4 *)(sRows + tid * 128);
+            const int sw = tid & 7;
+            if (warp_keys) {
+                float vv[TCA_SD];
+                tmem_ld32(tm_v + lane_off, vv);
+                if (is_key) {
 #pragma unroll
-                for (int c4 = 0; c4 < TCA_SD / 4; ++c4)
-                    *(float4 *)(sV + tid * TCA_VPITCH + 4 * c4) =
-                        make_float4(vv[4 * c4], vv[4 * c4 + 1], vv[4 * c4 + 2], vv[4 * c4 + 3]);
-                const float bias = masked ? -100.0f : 0.f;  // additive mask of the reference
-                float *srow = sS + soff + j * nqr * HEADS;
-                for (int s = 0; s < nqr; ++s) {
-                    const float4 *qv = (const float4 *)(Qbuf + (size_t)(q0 + s) * TCA_C + g * TCA_SD);
+                    for (int c4 = 0; c4 < TCA_SD / 4; ++c4)
+                        my[c4 ^ sw] = make_float4(vv[4 * c4], vv[4 * c4 + 1], vv[4 * c4 + 2], vv[4 * c4 + 3]);
+                }
+            }
+            if (warp_queries) {
+                float qq[TCA_SD];
+                tmem_ld32(tm_q + lane_off, qq);
+                if (is_query) {
 #pragma unroll
-                    for (int h = 0; h < HEADS; ++h) {
-                        float a = 0.f;
+                    for (int c4 = 0; c4 < TCA_SD / 4; ++c4)
+                        my[c4 ^ sw] = make_float4(qq[4 * c4] + sBias[4 * c4], qq[4 * c4 + 1] + sBias[4 * c4 + 1],
+                                                  qq[4 * c4 + 2] + sBias[4 * c4 + 2], qq[4 * c4 + 3] + sBias[4 * c4 + 3]);
+                }
+            }
+            if (warp_keys) tmem_ld32(tm_k + lane_off, kk);
+        }
+        tc_fence_before();
+        __syncthreads();
+        KTRACE(6);
+        // ---- 3. scores of this thread's key against the queries of its window
+        if (is_key) {
+            const float bias = masked ? -100.0f : 0.f;  // additive mask of the reference
+            float *srow = sS + soff + j * nqr * HEADS;
+            for (int s = 0; s < nqr; ++s) {
+                const int qr = qrow0 + s;
+                const float4 *qv = (const float4 *)(sRows + qr * 128);
+                const int qsw = qr & 7;
 #pragma unroll
-                        for (int d4 = 0; d4 < HD / 4; ++d4) {
-                            const float4 q4 = __ldg(qv + h * (HD / 4) + d4);
-                            a = fmaf(q4.x, kk[h * HD + 4 * d4], a); a = fmaf(q4.y, kk[h * HD + 4 * d4 + 1], a);
-                            a = fmaf(q4.z, kk[h * HD + 4 * d4 + 2], a); a = fmaf(q4.w, kk[h * HD + 4 * d4 + 3], a);
-                        }
-                        srow[s * HEADS + h] = a + bias;
+                for (int h = 0; h < HEADS; ++h) {
+                    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+                    for (int d4 = 0; d4 < HD / 4; ++d4) {
+                        const float4 q4 = qv[(h * (HD / 4) + d4) ^ qsw];
+                        a0 = fmaf(q4.x, kk[h * HD + 4 * d4], a0); a1 = fmaf(q4.y, kk[h * HD + 4 * d4 + 1], a1);
+                        a0 = fmaf(q4.z, kk[h * HD + 4 * d4 + 2], a0); a1 = fmaf(q4.w, kk[h * HD + 4 * d4 + 3], a1);
                     }
+                    srow[s * HEADS + h] = a0 + a1 + bias;
                 }
             }
         }
-        KTRACE(8);
         __syncthreads();
-        KTRACE(9);
-        // ---- softmax over the window's distinct keys and AV, thread = (query, head, quarter of the head)
-        for (int e = tid; e < nQ * HEADS * 4; e += TCA_THREADS) {
-            const int dq = e & 3, qh = e >> 2;
-            const int h = qh % HEADS, qt = qh / HEADS;
-            const int lq = tile_window(sQoff, nwin, qt);
-            const int4 rec = sRec[lq];
-            const int s = qt - ((rec.z >> 8) & 0xff);
+        KTRACE(7);
+        // ---- 4. softmax over the window's distinct keys and AV, thread = (query, head, half of the head);
+        //      head outputs (+ bv) -> rows of the output-projection operand (canonical K-major, 8-row groups of
+        //      8 chunks: byte = (q / 8) * 1024 + chunk * 128 + (q % 8) * 16)
+        for (int e = tid; e < nQ * HEADS * 2; e += TCA_THREADS) {
+            constexpr int DPT = HD / 2;   // channels per thread (16 / 8 / 4)
+            const int half = e & 1, qh = e >> 1;
+            const int h = qh % HEADS, qs = qh / HEADS;
+            const int4 rec = sRec[sQwin[qs]];
+            const int s = qs - rec_qoff(rec);
             const int wq = rec.y & 0xff, r = (rec.y >> 8) & 0xff, mult = rec.y >> 16;
             const float *sc = sS + (rec.z >> 16) + s * HEADS + h;  // + key * wq * HEADS
             const int step = wq * HEADS;
             float mx = -3.0e38f;
             for (int k = 0; k < r; ++k) mx = fmaxf(mx, sc[k * step]);
+            mx *= 1.4426950408889634f;
             float den = 0.f, acc[DPT];
 #pragma unroll
             for (int d = 0; d < DPT; ++d) acc[d] = 0.f;
-            const float *vp = sV + (rec.z & 0xff) * TCA_VPITCH + h * HD + dq * DPT;
+            const int ch0 = (h * HD + half * DPT) >> 2, k0 = rec_koff(rec);   // first 16-byte chunk, first key row
             for (int k = 0; k < r; ++k) {
-                float wgt = exp_neg(sc[k * step] - mx);
+                float wgt = ex2_fast(fmaf(sc[k * step], 1.4426950408889634f, -mx));
                 if (k == r - 1 && mult > 0) wgt *= (float)mult;  // the masked key counts once per masked slot
                 den += wgt;
+                const int kr = k0 + k;
+                const float4 *vp = (const float4 *)(sRows + kr * 128);
 #pragma unroll
-                for (int d = 0; d < DPT; ++d) acc[d] = fmaf(wgt, vp[k * TCA_VPITCH + d], acc[d]);
+                for (int d4 = 0; d4 < DPT / 4; ++d4) {
+                    const float4 v = vp[(ch0 + d4) ^ (kr & 7)];
+                    acc[4 * d4] = fmaf(wgt, v.x, acc[4 * d4]); acc[4 * d4 + 1] = fmaf(wgt, v.y, acc[4 * d4 + 1]);
+                    acc[4 * d4 + 2] = fmaf(wgt, v.z, acc[4 * d4 + 2]); acc[4 * d4 + 3] = fmaf(wgt, v.w, acc[4 * d4 + 3]);
+                }
             }
             const float inv = 1.0f / den;
-            float *dst = Obuf + (size_t)(rec.x + s) * TCA_C + g * TCA_SD + h * HD + dq * DPT;
-            const float *bv = sBkv + TCA_SD + h * HD + dq * DPT;
+            char *dst = sAO + (qs >> 3) * 1024 + (qs & 7) * 16 + ch0 * 128;
+            const float *bv = sBias + 32 + 4 * ch0;
 #pragma unroll
-            for (int d = 0; d < DPT; ++d) dst[d] = fmaf(acc[d], inv, bv[d]);
+            for (int d4 = 0; d4 < DPT / 4; ++d4) {
+                float4 hi, lo;
+                split_tf32(make_float4(fmaf(acc[4 * d4], inv, bv[4 * d4]), fmaf(acc[4 * d4 + 1], inv, bv[4 * d4 + 1]),
+                                       fmaf(acc[4 * d4 + 2], inv, bv[4 * d4 + 2]), fmaf(acc[4 * d4 + 3], inv, bv[4 * d4 + 3])), hi, lo);
+                *(float4 *)(dst + d4 * 128) = hi;
+                if (TERMS == 3) *(float4 *)(dst + TCA_QMAX * TCA_SD * 4 + d4 * 128) = lo;
+            }
         }
-        KTRACE(10);
+        fence_async_smem();
         __syncthreads();
-        KTRACE(11);
+        KTRACE(8);
+        // ---- output projection of the group: rows = the tile's queries
+        if (tid == 0) {
+            tc_fence_after();
+#pragma unroll
+            for (int k = 0; k < TCA_SD / 8; ++k) {
+                const uint64_t ah = umma_smem_desc(sAO_u + (uint32_t)k * 256u, 128, 1024);
+                const uint64_t wh = umma_smem_desc(sWp_u + (uint32_t)k * 1024u, 512, 128);
+                umma_tf32(tm_a, ah, wh, id_n32, k > 0 ? 1u : 0u);
+                if (TERMS == 3) {
+                    umma_tf32(tm_a, umma_smem_desc(sAO_u + TCA_QMAX * TCA_SD * 4 + (uint32_t)k * 256u, 128, 1024), wh, id_n32, 1u);
+                    umma_tf32(tm_a, ah, umma_smem_desc(sWp_u + 32u * 32u * 4u + (uint32_t)k * 1024u, 512, 128), id_n32, 1u);
+                }
+            }
+            umma_commit(bar);
+        }
+        // the V / Q rows are consumed: the staging area takes the feature rows of the next tile
+        float nx = 0.f, ny = 0.f, nz = 0.f;
+        asm volatile("" : "+r"(n_row));   // (keeps every use of the row id -- address arithmetic included -- down here:
+                                          //  its load was issued a phase ago and must not be waited for up there)
+        if (more) {
+            if (n_kind) { nx = __ldg(xyz + 3 * (size_t)n_row); ny = __ldg(xyz + 3 * (size_t)n_row + 1); nz = __ldg(xyz + 3 * (size_t)n_row + 2); }
+            warp_rows_copy_async(stg, n_kind ? (const float4 *)(xn + (size_t)n_row * TCA_C + g * TCA_SD) : nullptr);
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1u;
+        tc_fence_after();
+        KTRACE(9);
+        // ---- 5. projected rows of the tile's queries (contiguous compact ids) -> (#queries, 64) array
+        if (warp * 32 < nQ) {   // (warp-uniform)
+            float d[TCA_SD];
+            tmem_ld32(tm_a + lane_off, d);
+            if (tid < nQ) {
+                float4 *dst = (float4 *)(Pbuf + (size_t)(sRec[0].x + tid) * TCA_C + g * TCA_SD);
+#pragma unroll
+                for (int c4 = 0; c4 < TCA_SD / 4; ++c4)
+                    dst[c4] = make_float4(d[4 * c4] + sBias[64 + 4 * c4], d[4 * c4 + 1] + sBias[64 + 4 * c4 + 1],
+                                          d[4 * c4 + 2] + sBias[64 + 4 * c4 + 2], d[4 * c4 + 3] + sBias[64 + 4 * c4 + 3]);
+            }
+        }
+        tc_fence_before();
+        __syncthreads();
+        KTRACE(10);
+        kind = n_kind; l = n_l; row = n_row; px = nx; py = ny; pz = nz;
+        tl = tl_next; tl_next = tl_after;
     }
 #ifdef MSSVT_TRACE
-    if (tid == 0 && blockIdx.x == gridDim.x - 1 && tr[11])
-        printf("keys tile g%d: header %lld | search+idx %lld | gather %lld | sync %lld | posemb+A %lld | sync %lld | mma %lld | tmem+scores %lld | sync %lld | softmax+AV %lld | sync %lld | total %lld clk\n", g,
-               tr[1] - tr[0], tr[2] - tr[1], tr[3] - tr[2], tr[4] - tr[3], tr[5] - tr[4], tr[6] - tr[5], tr[7] - tr[6], tr[8] - tr[7], tr[9] - tr[8], tr[10] - tr[9], tr[11] - tr[10], tr[11] - tr[0]);
+    if (tid == 0 && blockIdx.x == gridDim.x - 1 && tr[10])
+        printf("tile g%d: pos+sync %lld | rows in %lld | mma1 wait %lld | A1+sync %lld | roles(next)+mma2 %lld | unload+sync %lld | scores+sync %lld | softmax+AV+sync %lld | gather(next)+mma3 %lld | out+sync %lld | total %lld clk\n", g,
+               tr[1] - tr[0], tr[2] - tr[1], tr[3] - tr[2], tr[4] - tr[3], tr[5] - tr[4], tr[6] - tr[5], tr[7] - tr[6], tr[8] - tr[7], tr[9] - tr[8], tr[10] - tr[9], tr[10] - tr[0]);
 #endif
+    stage_packed_wait();
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem_d, 64);
+    if (warp == 0) {
+        tmem_dealloc(tm, 128);
+        if (TERMS == 3) tmem_dealloc(tm_alo, 32);
+    }
 }
 
 // ------------------------------------------------------------------------------- merge
@@ -471,14 +642,6 @@ k_tca_merge(TcAttnParams P, int win_cap, const int *__restrict__ win_count_total
     }
 }
 
-static size_t tca_keys_smem_bytes(int terms) {
-    const size_t nt = terms == 3 ? 2 : 1;
-    size_t a_region = nt * TCA_THREADS * TCA_SD * 4;
-    if (a_region < (size_t)TCA_THREADS * TCA_VPITCH * 4) a_region = (size_t)TCA_THREADS * TCA_VPITCH * 4;
-    return nt * 64 * 32 * 4 + a_region + (size_t)(32 * 8 + 64 + TCA_SBUD) * 4 + TCA_TW * 32 +
-           2 * (TCA_TW + 1) * 4 + 8 + 16 + 128;
-}
-
 }  // namespace mssvt
 
 using namespace mssvt;
@@ -512,24 +675,24 @@ int mssvt_attention_tiles(int heads_per_group, int nq, int key_num_sample, int w
     return check_launch();
 }
 
-/* Tensor-core window attention of a two-window block (see the header of this file).  Weights in
- * their nn.Module layout: pos_w [64][6]; packed by mssvt_pack_operand_tf32: wkv [64][32] per head group,
- * wq_packed / wp_packed = the [64][64] block-diagonal matrix of the two groups' [32][32] weights.  rep_row / meta: compact key lists of mssvt_block_geometry; q_base:
- * mssvt_exclusive_scan of meta[:, 0] (win_capacity + 1 ints); tiles .. win_ctr: mssvt_attention_tiles.
- * scratch: 3 * num_voxels * 64 floats (q, head outputs, projected rows of every real query).  merged may be
- * NULL when interp is set: the blend of the projected rows (scratch + 2 * num_voxels * 64) is then left to
- * mssvt_ffn_tc in mode 2.
+/* Tensor-core window attention of a two-window block (see the header of this file).  Weights packed by
+ * mssvt_pack_operand_tf32: wpos_packed = [pos_w | pos_b | 0] as a [64][8] matrix, ALWAYS packed with terms = 3;
+ * wkvq0 / wkvq1 = per head group the [96][32] matrix [Wk; Wv; scale * Wq]; wp0 / wp1 = the group's [32][32]
+ * output projection (packed with `terms`).  bq / bkv / bp: the nn.Linear biases ([32], [64], [32] per group).
+ * rep_row / meta: compact key lists of mssvt_block_geometry; q_base: mssvt_exclusive_scan of meta[:, 0]
+ * (win_capacity + 1 ints); tiles .. win_ctr: mssvt_attention_tiles.  scratch: 3 * num_voxels * 64 floats; the
+ * projected row of every real query lands in scratch + 2 * num_voxels * 64.  merged may be NULL when interp is
+ * set: the blend of the projected rows is then left to mssvt_ffn_tc in mode 2.
  * Returns MSSVT_ERR_INVALID for shapes outside C = 64 / 2 x 32 channels / nq <= 32 / K <= 63 /
  * cap1 <= 128 (callers then use mssvt_block_attention). */
 int mssvt_block_attention_tc(int C, int heads_per_group, int nq, int key_num_sample, int cap1, int interp,
-                             int terms, float scale, const float *win_cell, const float *range_min,
-                             const float *pos_w, const float *pos_b, const float *wq_packed, const float *bq0,
-                             const float *bq1, const float *wkv0, const float *bkv0, const float *wkv1,
-                             const float *bkv1, const float *wp_packed, const float *bp0, const float *bp1,
-                             int win_capacity, const int *win_count_total,
-                             const int *win_list, const float *xn, const float *xyz, const int *q_row,
+                             int terms, float scale, const float *wpos_packed, const float *wkvq0,
+                             const float *wkvq1, const float *wp0, const float *wp1, const float *bq0,
+                             const float *bq1, const float *bkv0, const float *bkv1, const float *bp0,
+                             const float *bp1, int win_capacity, const int *win_count_total,
+                             const float *xn, const float *xyz, const int *q_row,
                              const int *rep_row, const int *meta, const int *q_base, const int *q_src,
-                             const int *vox_slot, const int *win1_row, const unsigned char *nn_idx,
+                             const int *vox_slot, const unsigned char *nn_idx,
                              const float *nn_w, const int *tiles, const int *tile_count, const int *win_rec,
                              const float *win_ctr, int num_voxels, float *scratch, float *merged, void *stream) {
     if (C != 64 || (heads_per_group != 1 && heads_per_group != 2 && heads_per_group != 4) || nq <= 0 || nq > 32 ||
@@ -537,45 +700,31 @@ int mssvt_block_attention_tc(int C, int heads_per_group, int nq, int key_num_sam
         nq * (key_num_sample + 1) * heads_per_group > TCA_SBUD || (terms != 1 && terms != 3))
         return MSSVT_ERR_INVALID;
     if (win_capacity == 0) return MSSVT_OK;
-    if (!win_cell || !range_min || !pos_w || !pos_b || !wq_packed || !bq0 || !wkv0 || !bkv0 || !wp_packed || !bp0 ||
-        !bq1 || !wkv1 || !bkv1 || !bp1 || !win_count_total || !win_list || !xn || !xyz || !q_row ||
-        !rep_row || !meta || !q_base || !q_src || !tiles || !tile_count || !win_rec || !win_ctr || !scratch ||
-        (!merged && !interp))
+    if (!wpos_packed || !wkvq0 || !wkvq1 || !wp0 || !wp1 || !bq0 || !bq1 || !bkv0 || !bkv1 || !bp0 || !bp1 ||
+        !win_count_total || !xn || !xyz || !q_row || !rep_row || !meta || !q_base || !q_src || !tiles ||
+        !tile_count || !win_rec || !win_ctr || !scratch || (!merged && !interp))
         return MSSVT_ERR_INVALID;
     if (interp && (!vox_slot || !nn_idx || !nn_w)) return MSSVT_ERR_INVALID;
-    (void)win1_row;
     TcAttnParams P;
-    P.nq = nq; P.K = key_num_sample; P.cap1 = cap1; P.interp = interp ? 1 : 0;
-    P.heads = heads_per_group; P.smax = nq * heads_per_group;
+    P.nq = nq; P.K = key_num_sample; P.cap1 = cap1; P.interp = interp ? 1 : 0; P.heads = heads_per_group;
     P.scale = scale;
-    for (int i = 0; i < 3; ++i) { P.win_cell[i] = win_cell[i]; P.lo[i] = range_min[i]; }
-    P.pos_w = pos_w; P.pos_b = pos_b;
-    P.wq = wq_packed; P.bq[0] = bq0; P.wkv[0] = wkv0; P.bkv[0] = bkv0; P.wp = wp_packed; P.bp[0] = bp0;
-    P.bq[1] = bq1; P.wkv[1] = wkv1; P.bkv[1] = bkv1; P.bp[1] = bp1;
-    const size_t smem = tca_keys_smem_bytes(terms);
-    float *Qbuf = scratch, *Obuf = scratch + (size_t)num_voxels * 64, *Pbuf = scratch + 2 * (size_t)num_voxels * 64;
+    P.wpos = wpos_packed;
+    P.wkvq[0] = wkvq0; P.wkvq[1] = wkvq1; P.wp[0] = wp0; P.wp[1] = wp1;
+    P.bq[0] = bq0; P.bq[1] = bq1; P.bkv[0] = bkv0; P.bkv[1] = bkv1; P.bp[0] = bp0; P.bp[1] = bp1;
+    const size_t smem = (size_t)TcaSmem(terms == 3 ? 2 : 1).total;
+    float *Pbuf = scratch + 2 * (size_t)num_voxels * 64;
     cudaStream_t s = (cudaStream_t)stream;
-    const int4 *wl = (const int4 *)win_list;
     const int wide = MSSVT_NUM_SMS * 8;  // grid-stride kernels: 8 CTAs of 256 threads per SM
 
-    {
-        TcaQueryRows rows;
-        rows.nq = nq; rows.win_cap = win_capacity;
-        for (int i = 0; i < 3; ++i) { rows.win_cell[i] = win_cell[i]; rows.lo[i] = range_min[i]; }
-        rows.pos_w = pos_w; rows.pos_b = pos_b; rows.win_count_total = win_count_total; rows.win_list = wl;
-        rows.xn = xn; rows.xyz = xyz; rows.q_row = q_row; rows.q_base = q_base; rows.q_src = q_src;
-        const TclParams L = {wq_packed, bq0, bq1, scale};
-        tcl_launch(L, rows, num_voxels, Qbuf, s, terms);
-    }
-
     int per_sm = (int)(227 * 1024 / (smem + 1024));
-    per_sm = per_sm > (terms == 3 ? 3 : 5) ? (terms == 3 ? 3 : 5) : per_sm < 1 ? 1 : per_sm;  // (64 TMEM columns each)
+    const int tmem_limit = terms == 3 ? 3 : 4;   // 160 / 128 TMEM columns each
+    per_sm = per_sm > tmem_limit ? tmem_limit : per_sm < 1 ? 1 : per_sm;
     const int grid = MSSVT_NUM_SMS * per_sm;
     ++g_launches;
 #define TCA_LAUNCH(H, T)                                                                                   \
-    cudaFuncSetAttribute(k_tca_keys<H, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
-    launch_pdl(k_tca_keys<H, T>, dim3(grid), dim3(TCA_THREADS), smem, s, P, win_capacity, (const int2 *)tiles, \
-               tile_count, (const int4 *)win_rec, (const float4 *)win_ctr, xn, xyz, rep_row, Qbuf, Obuf)
+    cudaFuncSetAttribute(k_tca_tile<H, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
+    launch_pdl(k_tca_tile<H, T>, dim3(grid), dim3(TCA_THREADS), smem, s, P, win_capacity, (const int2 *)tiles, \
+               tile_count, (const int4 *)win_rec, (const float4 *)win_ctr, xn, xyz, rep_row, q_row, Pbuf)
     if (terms == 3) {
         if (heads_per_group == 1) { TCA_LAUNCH(1, 3); }
         else if (heads_per_group == 2) { TCA_LAUNCH(2, 3); }
@@ -586,12 +735,6 @@ int mssvt_block_attention_tc(int C, int heads_per_group, int nq, int key_num_sam
         else { TCA_LAUNCH(4, 1); }
     }
 #undef TCA_LAUNCH
-
-    {
-        const TclCopyRows rows = {Obuf, win_count_total, q_base, win_capacity};
-        const TclParams L = {wp_packed, bp0, bp1, 1.0f};
-        tcl_launch(L, rows, num_voxels, Pbuf, s, terms);
-    }
     if (!merged) return check_launch();  // interpolation + merge left to mssvt_ffn_tc (mode 2)
     ++g_launches;
     launch_pdl(k_tca_merge, dim3(wide), dim3(256), 0, s, P, win_capacity, win_count_total, num_voxels, meta, q_base,

@@ -62,29 +62,41 @@ __device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
 // hardware-defined slice per call, so the bound is on wall time (%globaltimer), not on iterations:
 // after 2 s the kernel reports where it is stuck and traps (-> cudaErrorLaunchFailure).
 __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+    // try_wait suspends the thread for a hardware-defined slice per attempt.  Measured alternatives: a
+    // suspend-time hint (every blocking wait of the 3xTF32 kernels then slept for the whole hint) and polling
+    // with test_wait (no gain for the tile kernel, slower FFN: eight polling warps take issue slots from the
+    // epilogue of the other CTA).
     unsigned long long t0 = 0;
-    for (uint32_t spin = 0;; ++spin) {
+    for (;;) {
         uint32_t done;
         asm volatile(
             "{\n\t"
             ".reg .pred p;\n\t"
+            ".reg .u32 n;\n\t"
+            "mov.u32 n, 256;\n\t"
+            "MBAR_TRY:\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "@p bra MBAR_DONE;\n\t"
+            "sub.u32 n, n, 1;\n\t"
+            "setp.ne.u32 p, n, 0;\n\t"
+            "@p bra MBAR_TRY;\n\t"
+            "setp.ne.u32 p, n, 0;\n\t"
+            "MBAR_DONE:\n\t"
             "selp.u32 %0, 1, 0, p;\n\t"
             "}\n"
             : "=r"(done)
             : "r"(mbar), "r"(parity)
             : "memory");
         if (done) break;
-        if ((spin & 63u) == 63u) {
-            unsigned long long now;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-            if (t0 == 0) t0 = now;
-            else if (now - t0 > 2000000000ull) {
-                if ((threadIdx.x & 31) == 0)
-                    printf("mssvt_b200: mbarrier wait timed out (block %d, thread %d, parity %u)\n", blockIdx.x,
-                           threadIdx.x, parity);
-                __trap();
-            }
+        // bounded: a mis-programmed MMA must not hang the GPU; after 2 s report and trap
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > 2000000000ull) {
+            if ((threadIdx.x & 31) == 0)
+                printf("mssvt_b200: mbarrier wait timed out (block %d, thread %d, parity %u)\n", blockIdx.x,
+                       threadIdx.x, parity);
+            __trap();
         }
     }
     // lanes leave the wait loop at different times; the tcgen05.ld / fence instructions that follow
@@ -238,11 +250,13 @@ __device__ __forceinline__ void stage_packed(const float *__restrict__ packed, i
 __device__ __forceinline__ void stage_packed_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 
-__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t cols) {  // one full warp
+// one full warp; `last`: this CTA allocates nothing more (the permit is given back, so that other CTAs of the SM
+// do not queue behind it)
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t cols, bool last = true) {
     __syncwarp();
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(cols)
                  : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (last) asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {  // the same warp
     __syncwarp();

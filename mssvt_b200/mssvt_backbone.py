@@ -406,41 +406,42 @@ class MixedScaleSparseTransformerBlock(nn.Module):
         """1: TF32 operands; 3: split operands ("3xTF32", fp32-grade results on the tensor cores)"""
         return 3 if self.precision == "tf32x3" else 1
 
-    def _packed(self, *weights):
-        """tensor-core operand form of an nn.Linear / 1x1 Conv1d weight (TF32, K-major core matrices),
-        packed once and cached until the parameter is modified or moved; several weights = their
-        block-diagonal matrix (one GEMM for all head groups).  A stale entry is re-packed IN PLACE (same
-        buffer), so a captured CUDA graph that holds the buffer's address sees the new weights."""
+    @staticmethod
+    def _block_diag(*mats):
+        return mats[0] if len(mats) == 1 else torch.block_diag(*mats)
+
+    def _packed(self, *weights, build=None, name="", terms=None):
+        """tensor-core operand form of nn.Linear / 1x1 Conv1d weights (TF32, K-major core matrices), packed once
+        and cached until a parameter is modified or moved.  `build` maps the 2-D fp32 views of `weights` to the
+        matrix to pack (default: their block-diagonal matrix = one GEMM for all head groups).  A stale entry is
+        re-packed IN PLACE (same buffer), so a captured CUDA graph that holds the buffer's address sees the new
+        weights."""
         cache = self.__dict__.setdefault("_packed_ops", {})
-        terms = self._terms()
-        key = tuple(id(w) for w in weights) + (terms,)
+        terms = self._terms() if terms is None else terms
+        key = tuple(id(w) for w in weights) + (name, terms)
         tag = tuple((w.data_ptr(), w._version) for w in weights)
         hit = cache.get(key)
         if hit is None or hit[0] != tag:
-            mats = [w.detach().reshape(w.shape[0], -1).float() for w in weights]
-            w2d = (mats[0] if len(mats) == 1 else torch.block_diag(*mats)).contiguous()
-            shape = (2 if terms == 3 else 1,) + tuple(w2d.shape)        # [hi | lo] for 3xTF32
-            out = hit[1] if hit is not None and tuple(hit[1].shape) == shape and hit[1].device == w2d.device \
-                else w2d.new_empty(shape)
-            call("mssvt_pack_operand_tf32", ptr(w2d), w2d.shape[0], w2d.shape[1], terms, ptr(out), stream())
-            hit = cache[key] = (tag, out, weights)
+            hit = cache[key] = (tag, self._pack_into(hit[1] if hit is not None else None, weights, build, terms),
+                                weights, build)
         return hit[1]
+
+    def _pack_into(self, out, weights, build, terms):
+        mats = [w.detach().reshape(w.shape[0], -1).float() for w in weights]
+        w2d = (build or self._block_diag)(*mats).contiguous()
+        shape = (2 if terms == 3 else 1,) + tuple(w2d.shape)            # [hi | lo] for 3xTF32
+        if out is None or tuple(out.shape) != shape or out.device != w2d.device:
+            out = w2d.new_empty(shape)
+        call("mssvt_pack_operand_tf32", ptr(w2d), w2d.shape[0], w2d.shape[1], terms, ptr(out), stream())
+        return out
 
     def repack_stale(self):
         """Re-pack (in place) every cached operand whose parameter was modified in place since it was packed
-        (optimizer step, load_state_dict, EMA); returns False if a parameter's STORAGE moved, which a
-        captured graph cannot follow."""
-        same_storage = True
-        for key, (tag, out, weights) in list(self.__dict__.get("_packed_ops", {}).items()):
+        (optimizer step, load_state_dict, EMA)."""
+        for key, (tag, out, weights, build) in list(self.__dict__.get("_packed_ops", {}).items()):
             now = tuple((w.data_ptr(), w._version) for w in weights)
             if now != tag:
-                same_storage &= all(a[0] == b[0] for a, b in zip(now, tag))
-                terms = key[-1]
-                mats = [w.detach().reshape(w.shape[0], -1).float() for w in weights]
-                w2d = (mats[0] if len(mats) == 1 else torch.block_diag(*mats)).contiguous()
-                call("mssvt_pack_operand_tf32", ptr(w2d), w2d.shape[0], w2d.shape[1], terms, ptr(out), stream())
-                self._packed_ops[key] = (now, out, weights)
-        return same_storage
+                self._packed_ops[key] = (now, self._pack_into(out, weights, build, key[-1]), weights, build)
 
     def _ffn_descriptor(self, mode):
         named = [("ln_g", self.norm2.weight), ("ln_b", self.norm2.bias),
@@ -524,22 +525,24 @@ class MixedScaleSparseTransformerBlock(nn.Module):
                       and self._ffn_tc_supported(F))
         merged = None if fuse_merge else torch.empty_like(x)  # only rows flagged in g["covered"] are written and read
         if self._tc_supported(g["nq"]):
-            # task-parallel kernel, K/V projection on the tcgen05 tensor cores (TF32 operands)
-            vs = sp_tensor.voxel_size
+            # tile kernel: positional embedding, K | V | Q projection and output projection on tcgen05
             plan = self._tile_plan(sp_tensor, g, a.num_heads[0])
             scratch = torch.empty((3 * x.shape[0], 64), dtype=torch.float32, device=x.device)
+            scale = a.scale
+            pos = self.pos_proj[0]
+            wpos = self._packed(pos.weight, pos.bias, name="pos", terms=3, build=lambda w, b: torch.cat(
+                (w, b.reshape(-1, 1), torch.zeros_like(b).reshape(-1, 1)), 1))
+            wkvq = [self._packed(a.to_kvs[i].weight, a.to_qs[i].weight, name="kvq",
+                                 build=lambda kv, q: torch.cat((kv, q * scale), 0)) for i in range(2)]
+            wp = [self._packed(a.projs[i].weight) for i in range(2)]
             call("mssvt_block_attention_tc", 64, a.num_heads[0], g["nq"], self.key_num_sample, self.max_num_win1,
-                 int(bool(self.use_feature_interpolation)), self._terms(), a.scale,
-                 host_floats([vs[i] * self.win1_size[i] for i in range(3)]),
-                 host_floats(sp_tensor.point_cloud_range[0:3]), ptr(self.pos_proj[0].weight),
-                 ptr(self.pos_proj[0].bias), ptr(self._packed(a.to_qs[0].weight, a.to_qs[1].weight)),
-                 ptr(a.to_qs[0].bias), ptr(a.to_qs[1].bias), ptr(self._packed(a.to_kvs[0].weight)),
-                 ptr(a.to_kvs[0].bias), ptr(self._packed(a.to_kvs[1].weight)), ptr(a.to_kvs[1].bias),
-                 ptr(self._packed(a.projs[0].weight, a.projs[1].weight)), ptr(a.projs[0].bias),
-                 ptr(a.projs[1].bias), g["cap"], ptr(g["total"]), ptr(g["win_list"]), ptr(xn),
-                 ptr(sp_tensor.world_coords()), ptr(g["q_row"]), ptr(g["rep_row"]), ptr(g["meta"]),
-                 ptr(g["q_base"]), ptr(g["q_src"]), ptr(g["vox_slot"]), ptr(g["win1_row"]), ptr(g["nn_idx"]),
-                 ptr(g["nn_w"]), *(ptr(v) for v in plan), x.shape[0], ptr(scratch), ptr(merged), stream())
+                 int(bool(self.use_feature_interpolation)), self._terms(), scale, ptr(wpos), ptr(wkvq[0]),
+                 ptr(wkvq[1]), ptr(wp[0]), ptr(wp[1]), ptr(a.to_qs[0].bias), ptr(a.to_qs[1].bias),
+                 ptr(a.to_kvs[0].bias), ptr(a.to_kvs[1].bias), ptr(a.projs[0].bias), ptr(a.projs[1].bias),
+                 g["cap"], ptr(g["total"]), ptr(xn), ptr(sp_tensor.world_coords()), ptr(g["q_row"]),
+                 ptr(g["rep_row"]), ptr(g["meta"]), ptr(g["q_base"]), ptr(g["q_src"]), ptr(g["vox_slot"]),
+                 ptr(g["nn_idx"]), ptr(g["nn_w"]), *(ptr(v) for v in plan), x.shape[0], ptr(scratch), ptr(merged),
+                 stream())
             if fuse_merge:
                 merge_src = (g["vox_slot"], g["meta"], g["q_base"], g["nn_idx"], g["nn_w"], scratch[2 * x.shape[0]:],
                              self.max_num_win1)
