@@ -29,7 +29,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 from mssvt_b200.config import s0_model_cfg  # noqa: E402
-from mssvt_b200.synth import S0_GRID, S0_RANGE, S0_VOXEL, synth_frame  # noqa: E402
+from mssvt_b200.synth import S0_GRID, S0_RANGE, S0_VOXEL, synth_frame, synth_points  # noqa: E402
 
 METRIC = "mssvt_backbone_fwd_voxels_per_s"
 UNIT = "voxels/s"
@@ -228,7 +228,7 @@ class Arm:
         f, c = self.dev[i % POOL]
         return self.model({"voxel_features": f, "voxel_coords": c, "batch_size": 1})["encoded_spconv_tensor"]
 
-    def measure(self, precision, e2e_passes=3, sample_clocks=False):
+    def measure(self, precision, e2e_passes=3, sample_clocks=False, with_points=False):
         """One full measurement in `precision`: K graph-replayed steps on resident frames (device time), the same
         through the module API from pinned host buffers (e2e), the per-entry-point breakdown and rooflines."""
         args, model, device = self.args, self.model, self.device
@@ -269,6 +269,7 @@ class Arm:
             eager_ms = self.timed(lambda a, n: [self.eager_step(i) for i in range(a, a + n)], args.warmup,
                                   args.steps) / args.steps
             e2e_s, e2e_list, rows = self.e2e(graphs is not None, e2e_passes)
+            pts = self.e2e(graphs is not None, e2e_passes, from_points=True) if with_points else None
             # per-entry-point breakdown (instrumented extra pass, not part of the timed region)
             self.lib.PROFILE = []
             for i in range(args.steps):
@@ -285,6 +286,15 @@ class Arm:
         from mssvt_b200.sharding import max_over_ranks
         ms, e2e_s = max_over_ranks(ms, device), max_over_ranks(e2e_s, device)
         total_voxels = N_VOXELS * args.steps * self.world
+        if pts is not None:
+            pts_s = max_over_ranks(pts[0], device)
+            out["e2e_points"] = {
+                "value": total_voxels / pts_s, "unit": UNIT, "h2d_bytes_per_step": self.points[0].numel() * 4,
+                "d2h_bytes_per_step": pts[2] * 64 * 4 + pts[2] * 4 * 4, "ms_per_step": pts_s / args.steps * 1e3,
+                "passes_ms_per_step": pts[1],
+                "pipeline": "pinned raw points (180000 x 6 fp32) -> H2D -> DynamicVFE (64 channels; its voxel count is the "
+                            "one host sync) -> backbone -> HeightCompression (dense BEV, stays on the device) -> D2H of "
+                            "the sparse output rows; median of %d passes of K steps" % len(pts[1])}
         peaks, peak_kind = measured_peaks()
         traffic = kernel_traffic().get(precision, {})
         w_est = int(0.26 * N_VOXELS)
@@ -317,12 +327,32 @@ class Arm:
             "note": PRECISION_NOTE[precision]})
         return out
 
-    def e2e(self, graph, passes):
+    def points_pipeline(self):
+        """DynamicVFE (one PFN layer, 64 channels) in front and HeightCompression (plain dense scatter) behind the
+        backbone, and pinned raw point clouds whose voxelisation is exactly the POOL frames' coordinates"""
+        if not hasattr(self, "vfe"):
+            from mssvt_b200.config import AttrDict
+            from mssvt_b200.dynamic_vfe import DynamicVFE
+            from mssvt_b200.height_compression import HeightCompression
+            torch.manual_seed(1)
+            self.vfe = DynamicVFE(AttrDict(NUM_FILTERS=[64]), 5, list(S0_VOXEL), list(S0_GRID), list(S0_RANGE)).to(self.device).eval()
+            self.bev = HeightCompression(AttrDict(NUM_BEV_FEATURES=64, COMPRESS_LAYER_NUMS=0)).to(self.device).eval()
+            self.points = [torch.from_numpy(synth_points(1000 * self.rank + i, N_VOXELS)).pin_memory() for i in range(POOL)]
+        return self.vfe, self.bev, self.points
+
+    def e2e(self, graph, passes, from_points=False):
         """module API from pinned HOST buffers; every step copies its inputs host -> device and its result (features
         + indices of the output tensor) device -> host.  Three streams: the H2D of step i+1 and the D2H of step
         i-1 overlap the forward of step i; with graphs, a ring of three captured forwards with their own static
-        input / output buffers, so that the copies never touch the buffers the running step is using."""
+        input / output buffers, so that the copies never touch the buffers the running step is using.
+        from_points: the step starts from the RAW POINT CLOUD (4.3 MB instead of 40.8 MB of voxel features):
+        H2D of the points, DynamicVFE (the one host sync of the pipeline: the voxel count, as in the reference's
+        torch.unique), backbone, HeightCompression (dense BEV, stays on the device for the 2-D backbone), D2H of
+        the sparse output rows."""
         args, model, device, host = self.args, self.model, self.device, self.host
+        if from_points:
+            vfe, bev, points = self.points_pipeline()
+            pts_dev = [torch.empty_like(points[0], device=device) for _ in range(3)]
         out_feat = [torch.empty((N_VOXELS, 64), dtype=torch.float32).pin_memory() for _ in range(2)]
         out_idx = [torch.empty((N_VOXELS, 4), dtype=torch.int32).pin_memory() for _ in range(2)]
         s_in, s_comp, s_out = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
@@ -342,7 +372,13 @@ class Arm:
             def stage(i):
                 f, c = host[i % POOL]
                 with torch.cuda.stream(s_in):
-                    if slots:
+                    if from_points:
+                        sl = slots[i % 3] if slots else None
+                        if sl is not None and sl["done"] is not None:
+                            s_in.wait_event(sl["done"])
+                        pts_dev[i % 3].copy_(points[i % POOL], non_blocking=True)
+                        fd, cd = pts_dev[i % 3], None
+                    elif slots:
                         sl = slots[i % 3]
                         if sl["done"] is not None:
                             s_in.wait_event(sl["done"])      # step i-3 has consumed the slot's inputs
@@ -381,7 +417,17 @@ class Arm:
                     if stamps is not None:
                         g0 = torch.cuda.Event(enable_timing=True)
                         g0.record(s_comp)
-                    if slots:
+                    if from_points:
+                        vox = vfe({"points": fd, "batch_size": 1})          # (host sync: the voxel count)
+                        if slots and vox["voxel_features"].shape[0] == N_VOXELS:
+                            slots[i % 3]["f"].copy_(vox["voxel_features"])
+                            slots[i % 3]["c"].copy_(vox["voxel_coords"])
+                            sp = slots[i % 3]["g"].replay()
+                        else:
+                            sp = model({"voxel_features": vox["voxel_features"], "voxel_coords": vox["voxel_coords"],
+                                        "batch_size": 1})["encoded_spconv_tensor"]
+                        keep_bev = bev({"encoded_spconv_tensor": sp, "encoded_spconv_tensor_stride": 1})["spatial_features"]
+                    elif slots:
                         sp = slots[i % 3]["g"].replay()
                     else:
                         sp = model({"voxel_features": fd, "voxel_coords": cd, "batch_size": 1})["encoded_spconv_tensor"]
@@ -397,7 +443,7 @@ class Arm:
                 pending = (i, sp, done)
                 if stamps is not None:
                     stamps.append(time.perf_counter())
-                keep.append((fd, cd, sp))    # keep device buffers alive until their copies are done
+                keep.append((fd, cd, sp, keep_bev if from_points else None))    # keep device buffers alive until their copies are done
                 if len(keep) > 4:
                     keep.pop(0)
             rows = drain(*pending)
@@ -416,10 +462,42 @@ class Arm:
             samples.append(stamps[-1] - stamps[0])
             busy = [a.elapsed_time(b) for a, b in gpu_spans]
             idle = [gpu_spans[j][1].elapsed_time(gpu_spans[j + 1][0]) for j in range(len(gpu_spans) - 1)]
-            print(f"[bench] e2e pass {k + 1}: {samples[-1] * 1e3:.2f} ms for {args.steps} steps; forward on the compute "
+            print(f"[bench] e2e{'_points' if from_points else ''} pass {k + 1}: {samples[-1] * 1e3:.2f} ms for {args.steps} steps; forward on the compute "
                   f"stream {statistics.mean(busy):.3f} ms/step, idle between forwards {statistics.mean(idle):.3f} ms/step",
                   file=sys.stderr)
         return sorted(samples)[len(samples) // 2], [round(v / args.steps * 1e3, 4) for v in samples], rows
+
+    def host_link_probe(self, mb=64, reps=8):
+        """What the host <-> device path of this box gives every rank WHEN ALL RANKS COPY AT ONCE (barrier-bracketed,
+        pinned memory, one direction at a time, then both): names the limiter of the e2e numbers at N > 1."""
+        import torch.distributed as dist
+        n = mb * (1 << 20) // 4
+        h_in, h_out = torch.empty(n, dtype=torch.float32).pin_memory(), torch.empty(n, dtype=torch.float32).pin_memory()
+        d_in, d_out = torch.empty(n, dtype=torch.float32, device=self.device), torch.ones(n, dtype=torch.float32, device=self.device)
+        s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+        res = {}
+        for name in ("h2d", "d2h", "both"):
+            for timed in (False, True):
+                self.barrier()
+                t0 = time.perf_counter()
+                for _ in range(reps):
+                    if name in ("h2d", "both"):
+                        with torch.cuda.stream(s1):
+                            d_in.copy_(h_in, non_blocking=True)
+                    if name in ("d2h", "both"):
+                        with torch.cuda.stream(s2):
+                            h_out.copy_(d_out, non_blocking=True)
+                s1.synchronize(); s2.synchronize()
+                self.barrier()
+                dt = time.perf_counter() - t0
+            gbs = reps * n * 4 / dt / 1e9
+            t = torch.tensor([gbs], dtype=torch.float64, device=self.device)
+            if self.world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            res[name + "_gbs_per_rank"] = round(float(t[0]) / self.world, 2)
+            res[name + "_gbs_all_ranks"] = round(float(t[0]), 2)
+        res["note"] = "%d MiB pinned copies, %d back to back, all %d ranks at once; 'both' = each direction's rate while the other runs" % (mb, reps, self.world)
+        return res
 
     def parity(self, want, modes):
         """The frame the CPU oracle just ran (seed 0, 150 k voxels), through the GPU arm in every mode -- eager and
@@ -465,7 +543,7 @@ def our_arm(args):
     torch.cuda.set_device(local)
     arm = Arm(args, rank, world, local)
     others = [m for m in arm.model.PRECISIONS if m not in (args.precision, "fp32")] if args.modes else []
-    head = arm.measure(args.precision, e2e_passes=3, sample_clocks=True)
+    head = arm.measure(args.precision, e2e_passes=3, sample_clocks=True, with_points=True)
     modes = {}
     for m in others:     # the other tensor-core modes: same frames, same K steps, graph-timed, e2e (one pass), rooflines
         r = arm.measure(m, e2e_passes=1)
@@ -485,9 +563,10 @@ def our_arm(args):
                               "eager": "kernel by kernel from Python"}[args.launch],
                    "eager_ms_per_step": round(head["eager_ms_per_step"], 4),
                    "precision": head["note"]},
-        "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "clocks": head.get("clocks"),
+        "e2e": head["e2e"], "e2e_points": head.get("e2e_points"), "gpu_launches": head["gpu_launches"], "clocks": head.get("clocks"),
         "roofline": head["roofline"], "kernels": head["kernels"], "output_rows": head["output_rows"],
         "modes": modes,
+        "host_link": arm.host_link_probe(),
     }
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:

@@ -70,3 +70,23 @@ def synth_frame(seed, n_target, batch_size=1, channels=64, grid=S0_GRID, voxel=S
     feats = np.random.default_rng(seed + 7919).standard_normal((coords.shape[0], channels),
                                                                 dtype=np.float32)
     return feats, coords
+
+
+def synth_points(seed, n_voxels, extra=0.2, batch_size=1, point_features=5, grid=S0_GRID, voxel=S0_VOXEL,
+                 pc_range=S0_RANGE, crop=1.0):
+    """A raw point cloud whose voxelisation is exactly the frame synth_frame(seed, n_voxels) is built on: one
+    point inside every occupied voxel plus `extra` * n_voxels more in randomly chosen occupied voxels, shuffled.
+    -> points (P, 1 + point_features) float32 [batch_idx, x, y, z, intensity, elongation, ...] as DynamicVFE
+    takes them (pcdet/models/backbones_3d/vfe/dynamic_vfe.py:71-92), P = batch_size * n_voxels * (1 + extra)."""
+    out = []
+    for b in range(batch_size):
+        rng = np.random.default_rng(seed + b + 104729)
+        keys = synth_coords(seed + b, n_voxels, grid, voxel, pc_range, crop)
+        keys = np.concatenate([keys, rng.choice(keys, size=int(extra * n_voxels))])
+        rng.shuffle(keys)
+        cell = np.stack([keys // (grid[2] * grid[1]), (keys // grid[2]) % grid[1], keys % grid[2]], 1)
+        # strictly inside the voxel, away from its faces (the voxel of a point must not depend on rounding)
+        xyz = (cell + rng.uniform(0.05, 0.95, cell.shape)) * np.asarray(voxel) + np.asarray(pc_range[:3])
+        rest = rng.random((len(keys), point_features - 3))
+        out.append(np.concatenate([np.full((len(keys), 1), b), xyz, rest], 1))
+    return np.concatenate(out, 0).astype(np.float32)
