@@ -79,8 +79,31 @@ def main():
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+    # the same steps without the gradient all-reduce (DDP no_sync): the difference is what the NCCL all-reduce
+    # costs after overlap with the backward pass
+    ms_nosync = None
+    if world > 1:
+        import contextlib
+        with net.no_sync():
+            for i in range(2):
+                step(i)
+            torch.cuda.synchronize()
+            dist.barrier()
+            n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n0.record()
+            for i in range(args.steps):
+                step(args.warmup + i)
+            n1.record()
+            torch.cuda.synchronize()
+        t = torch.tensor([n0.elapsed_time(n1) / args.steps], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_nosync = float(t.item())
     if rank == 0:
+        grad_bytes = sum(p.numel() for p in model.parameters()) * 4
         print(json.dumps({"metric": "mssvt_backbone_train_step_ms", "value": ms, "unit": "ms/step", "n_gpus": world,
+                          "ms_per_step_without_allreduce": ms_nosync,
+                          "allreduce_share": None if ms_nosync is None else max(0.0, (ms - ms_nosync) / ms),
+                          "gradient_bytes": grad_bytes,
                           "steps": args.steps, "warmup": args.warmup, "higher_is_better": False,
                           "voxels_per_s": args.voxels * world / (ms * 1e-3), "wall_ms_per_step": wall / args.steps * 1e3,
                           "dtype": "bf16 autocast" if args.amp else "tf32 matmuls" if args.tf32 else "fp32", "loss": float(loss),
