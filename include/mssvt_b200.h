@@ -179,7 +179,19 @@ int mssvt_block_geometry(int x_max, int y_max, int z_max, int x_ws, int y_ws, in
                          int num_voxels, int *q_row,
                          int *win1_row, int *k_row, unsigned char *k_mask, unsigned char *nn_idx,
                          float *nn_w, unsigned char *covered, int *fps_idx_tap, int *counts_tap,
-                         int *rep_row, int *meta, int *vox_slot, void *stream);
+                         int *rep_row, int *meta, int *vox_slot, int *odd_row, int *even_row, void *stream);
+
+/* The pattern-dependent part of the block geometry (query rows, #real queries, three-NN + weights;
+ * mssvt_backbone.py:220-234, 300-307) for ANOTHER cbs_pattern, from the outputs of one mssvt_block_geometry call
+ * over the same windows: src_row = the list that serves as the query set -- odd_row (cap, |odd|) for pattern 1,
+ * even_row (cap, |even|) for pattern 0 (both optional outputs of mssvt_block_geometry: global rows, -1 padded) or
+ * win1_row for pattern 2 -- with nq entries per window; meta_in = that call's meta; xyz = mssvt_voxel_world_coords.
+ * Writes q_row (cap, nq), meta_out (cap, 4) (entry 0 = #real queries of THIS pattern, the rest copied) and, with
+ * use_interp, nn_idx / nn_w (cap, max_win1, 3).  Bit-identical to a direct call with that pattern; the chessboard
+ * probes and both FPS passes are not repeated (blocks that differ only in cbs_pattern share them). */
+int mssvt_block_queries(int nq, int max_win1, int use_interp, int win_capacity, const int *win_count_total,
+                        const int *src_row, const int *win1_row, const int *meta_in, const float *xyz, int *q_row,
+                        int *meta_out, unsigned char *nn_idx, float *nn_w, void *stream);
 
 /* q_src[q_base[w] + s] = w * nq + s for every real query slot: inverse of the compact query numbering
  * (q_base = mssvt_exclusive_scan over meta[:, 0]). */

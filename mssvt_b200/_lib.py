@@ -37,7 +37,8 @@ _SIGNATURES = {
     "mssvt_group_points_grad": [I, I, I, I, I, P, P, P, P],
     "mssvt_grid_index_words": [I, I, I, I],
     "mssvt_grid_index_build": [I, I, I, I, I, P, P, P, P, P, P],
-    "mssvt_block_geometry": [I] * 15 + [P] * 6 + [I, P, P, P, P, P, I] + [P] * 12 + [P],
+    "mssvt_block_geometry": [I] * 15 + [P] * 6 + [I, P, P, P, P, P, I] + [P] * 14 + [P],
+    "mssvt_block_queries": [I] * 4 + [P] * 9 + [P],
     "mssvt_query_src": [I, P, I, P, P, P, P],
     "mssvt_window_rows": [I] * 8 + [P, I, P, P, P, P, P, P, P],
     "mssvt_layernorm": [I, P, I, P, P, P, F, P, P],

@@ -166,6 +166,8 @@ struct GeoOut {
                       //         one entry standing for every masked slot), optional (may be null)
     int *meta;        // (W, 4) {#real queries, #win1 voxels, nrep0 | nmask0 << 8, nrep1 | nmask1 << 8}
     int *vox_slot;    // (N) w * cap1 + i of the win1 slot holding the voxel, -1 if none (optional)
+    int *odd_row;     // (W, cap[0]) / (W, cap[1]): global rows of the odd / even chessboard lists, -1 pad (optional:
+    int *even_row;    //  what mssvt_block_queries needs to serve another cbs_pattern from this geometry)
 };
 
 __device__ __forceinline__ unsigned bitrev(unsigned v, int bits) { return bits ? __brev(v) >> (32 - bits) : 0u; }
@@ -238,6 +240,32 @@ __device__ __forceinline__ void fps_list(const int *s_off, int cnt, int n, int l
     __syncwarp();
 }
 
+// three nearest of nq known points (padding sits at the origin, quirk Q4) for one win1 voxel, and the normalised
+// 1/d weights: three_nn_kernel_fast (interpolate_gpu.cu:16-59) + mssvt_backbone.py:305-307
+__device__ __forceinline__ void three_nn_slot(float ux, float uy, float uz, const float *s_known, int nq,
+                                              unsigned char *oi, float *ow) {
+    const float INF = __int_as_float(0x7f800000);
+    float b1 = INF, b2 = INF, b3 = INF;
+    int i1 = 0, i2 = 0, i3 = 0;
+    for (int k = 0; k < nq; ++k) {
+        float dx = __fsub_rn(ux, s_known[3 * k]);
+        float dy = __fsub_rn(uy, s_known[3 * k + 1]);
+        float dz = __fsub_rn(uz, s_known[3 * k + 2]);
+        // nvcc's contraction of the reference expression (SASS of oracle/_ref):
+        float d = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+        if (d < b1) { b3 = b2; i3 = i2; b2 = b1; i2 = i1; b1 = d; i1 = k; }
+        else if (d < b2) { b3 = b2; i3 = i2; b2 = d; i2 = k; }
+        else if (d < b3) { b3 = d; i3 = k; }
+    }
+    // dist = sqrt(d2); w = 1 / clamp(dist, 1e-10); w /= sum(w)  (mssvt_backbone.py:305-307)
+    float w1 = __fdiv_rn(1.0f, fmaxf(__fsqrt_rn(b1), 1e-10f));
+    float w2 = __fdiv_rn(1.0f, fmaxf(__fsqrt_rn(b2), 1e-10f));
+    float w3 = __fdiv_rn(1.0f, fmaxf(__fsqrt_rn(b3), 1e-10f));
+    float sum = __fadd_rn(__fadd_rn(w1, w2), w3);
+    oi[0] = (unsigned char)i1; oi[1] = (unsigned char)i2; oi[2] = (unsigned char)i3;
+    ow[0] = __fdiv_rn(w1, sum); ow[1] = __fdiv_rn(w2, sum); ow[2] = __fdiv_rn(w3, sum);
+}
+
 __global__ void __launch_bounds__(GEO_WARPS * 32)
 k_block_geometry(GeoParams P, TablePtrs tabs, int win_cap, const int *__restrict__ win_count_total,
                  const int4 *__restrict__ win_list, GridIdx index,
@@ -279,6 +307,12 @@ k_block_geometry(GeoParams P, TablePtrs tabs, int win_cap, const int *__restrict
         // queries and win1 rows (global rows)
         for (int i = lane; i < nq; i += 32)
             out.q_row[(size_t)w * nq + i] = i < cnt[qL] ? row0 + s_ind[list_at[qL] + i] : -1;
+        if (out.odd_row)
+            for (int i = lane; i < g.cap[0]; i += 32)
+                out.odd_row[(size_t)w * g.cap[0] + i] = i < cnt[0] ? row0 + s_ind[list_at[0] + i] : -1;
+        if (out.even_row)
+            for (int i = lane; i < g.cap[1]; i += 32)
+                out.even_row[(size_t)w * g.cap[1] + i] = i < cnt[1] ? row0 + s_ind[list_at[1] + i] : -1;
         for (int i = lane; i < cap1; i += 32) {
             int r = i < cnt[2] ? row0 + s_ind[list_at[2] + i] : -1;
             out.win1_row[(size_t)w * cap1 + i] = r;
@@ -348,29 +382,59 @@ k_block_geometry(GeoParams P, TablePtrs tabs, int win_cap, const int *__restrict
                     continue;
                 }
                 int p = s_off[list_at[2] + i];
-                float ux = world_coord(cx + off_x(p), P.cell[0], P.lo[0]);
-                float uy = world_coord(cy + off_y(p), P.cell[1], P.lo[1]);
-                float uz = world_coord(cz + off_z(p), P.cell[2], P.lo[2]);
-                const float INF = __int_as_float(0x7f800000);
-                float b1 = INF, b2 = INF, b3 = INF;
-                int i1 = 0, i2 = 0, i3 = 0;
-                for (int k = 0; k < nq; ++k) {
-                    float dx = __fsub_rn(ux, s_known[3 * k]);
-                    float dy = __fsub_rn(uy, s_known[3 * k + 1]);
-                    float dz = __fsub_rn(uz, s_known[3 * k + 2]);
-                    // nvcc's contraction of the reference expression (SASS of oracle/_ref):
-                    float d = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
-                    if (d < b1) { b3 = b2; i3 = i2; b2 = b1; i2 = i1; b1 = d; i1 = k; }
-                    else if (d < b2) { b3 = b2; i3 = i2; b2 = d; i2 = k; }
-                    else if (d < b3) { b3 = d; i3 = k; }
+                three_nn_slot(world_coord(cx + off_x(p), P.cell[0], P.lo[0]), world_coord(cy + off_y(p), P.cell[1], P.lo[1]),
+                              world_coord(cz + off_z(p), P.cell[2], P.lo[2]), s_known, nq, oi, ow);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// The pattern-dependent part of the block geometry, from the lists another pattern's mssvt_block_geometry call
+// left behind: query rows, #real queries (meta[0]; the key entries of meta are copied), three-NN + weights.
+// One warp per window.  src_row: (W, nq) the chessboard list that serves as the query set (odd / even / win1
+// rows).  Voxel centres come from the xyz array, which holds the very world_coord() values k_block_geometry
+// derives from the cell indices, so indices and weights are bit-identical to a direct call.
+__global__ void __launch_bounds__(GEO_WARPS * 32)
+k_block_queries(int nq, int cap1, int interp, int win_cap, const int *__restrict__ win_count_total,
+                const int *__restrict__ src_row, const int *__restrict__ win1_row, const int4 *__restrict__ meta_in,
+                const float *__restrict__ xyz, int *__restrict__ q_row, int4 *__restrict__ meta_out,
+                unsigned char *__restrict__ nn_idx, float *__restrict__ nn_w) {
+    extern __shared__ int smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float *s_known = (float *)smem + warp * 3 * nq;
+    const int num_wins = min(win_cap, __ldg(win_count_total));
+    for (int w = blockIdx.x * GEO_WARPS + warp; w < num_wins; w += gridDim.x * GEO_WARPS) {
+        int nqr = 0;
+        for (int k0 = 0; k0 < nq; k0 += 32) {
+            const int k = k0 + lane;
+            const int row = k < nq ? __ldg(src_row + (size_t)w * nq + k) : -1;
+            if (k < nq) {
+                q_row[(size_t)w * nq + k] = row;
+                float x = 0.f, y = 0.f, z = 0.f;       // padded queries sit at the world origin (Q4)
+                if (row >= 0) { x = __ldg(xyz + 3 * (size_t)row); y = __ldg(xyz + 3 * (size_t)row + 1); z = __ldg(xyz + 3 * (size_t)row + 2); }
+                s_known[3 * k] = x; s_known[3 * k + 1] = y; s_known[3 * k + 2] = z;
+            }
+            nqr += __popc(__ballot_sync(0xffffffffu, row >= 0));
+        }
+        if (lane == 0) {
+            int4 m = __ldg(meta_in + w);
+            m.x = nqr;
+            meta_out[w] = m;
+        }
+        __syncwarp();
+        if (interp) {
+            for (int i = lane; i < cap1; i += 32) {
+                unsigned char *oi = nn_idx + ((size_t)w * cap1 + i) * 3;
+                float *ow = nn_w + ((size_t)w * cap1 + i) * 3;
+                const int row = __ldg(win1_row + (size_t)w * cap1 + i);
+                if (row < 0) {
+                    oi[0] = oi[1] = oi[2] = 0;
+                    ow[0] = ow[1] = ow[2] = 0.f;
+                    continue;
                 }
-                // dist = sqrt(d2); w = 1 / clamp(dist, 1e-10); w /= sum(w)  (mssvt_backbone.py:305-307)
-                float w1 = __fdiv_rn(1.0f, fmaxf(__fsqrt_rn(b1), 1e-10f));
-                float w2 = __fdiv_rn(1.0f, fmaxf(__fsqrt_rn(b2), 1e-10f));
-                float w3 = __fdiv_rn(1.0f, fmaxf(__fsqrt_rn(b3), 1e-10f));
-                float sum = __fadd_rn(__fadd_rn(w1, w2), w3);
-                oi[0] = (unsigned char)i1; oi[1] = (unsigned char)i2; oi[2] = (unsigned char)i3;
-                ow[0] = __fdiv_rn(w1, sum); ow[1] = __fdiv_rn(w2, sum); ow[2] = __fdiv_rn(w3, sum);
+                three_nn_slot(__ldg(xyz + 3 * (size_t)row), __ldg(xyz + 3 * (size_t)row + 1), __ldg(xyz + 3 * (size_t)row + 2),
+                              s_known, nq, oi, ow);
             }
         }
         __syncwarp();
@@ -496,7 +560,7 @@ int mssvt_block_geometry(int x_max, int y_max, int z_max, int x_ws, int y_ws, in
                          int num_voxels, int *q_row,
                          int *win1_row, int *k_row, unsigned char *k_mask, unsigned char *nn_idx,
                          float *nn_w, unsigned char *covered, int *fps_idx_tap, int *counts_tap,
-                         int *rep_row, int *meta, int *vox_slot, void *stream) {
+                         int *rep_row, int *meta, int *vox_slot, int *odd_row, int *even_row, void *stream) {
     GeoParams P;
     P.g = {x_max, y_max, z_max, x_ws, y_ws, z_ws, 1,
            {num_odd, num_even, num_win1, num_win2}, {num_odd, num_even, max_win1, max_win2}};
@@ -528,7 +592,7 @@ int mssvt_block_geometry(int x_max, int y_max, int z_max, int x_ws, int y_ws, in
     TablePtrs tabs = {{q_odd, q_even, q_win1, q_win2}};
     if ((rep_row == nullptr) != (meta == nullptr)) return MSSVT_ERR_INVALID;
     GeoOut out = {q_row, win1_row, k_row, k_mask, nn_idx, nn_w, covered, fps_idx_tap, counts_tap, rep_row, meta,
-                  vox_slot};
+                  vox_slot, odd_row, even_row};
     if (vox_slot) {
         e = cudaMemsetAsync(vox_slot, 0xff, (size_t)num_voxels * sizeof(int), s);
         if (e != cudaSuccess) { g_last_cuda_error = (int)e; return MSSVT_ERR_LAUNCH; }
@@ -547,6 +611,28 @@ int mssvt_block_geometry(int x_max, int y_max, int z_max, int x_ws, int y_ws, in
     k_block_geometry<<<grid, GEO_WARPS * 32, smem, s>>>(P, tabs, win_capacity, win_count_total,
                                                        (const int4 *)win_list, index, v_start, out);
     (void)ext;
+    return check_launch();
+}
+
+/* Pattern-dependent part of the block geometry for ANOTHER cbs_pattern, from the outputs of one
+ * mssvt_block_geometry call over the same windows (mssvt_backbone.py:220-234, 300-307): src_row = the list that
+ * serves as the query set -- odd_row (pattern 1), even_row (pattern 0) or win1_row (pattern 2), nq entries per
+ * window; meta_in = that call's meta.  Writes q_row (cap, nq), meta_out (cap, 4) (entry 0 = #real queries of THIS
+ * pattern, the rest copied) and, with use_interp, nn_idx / nn_w (cap, max_win1, 3).  Results are bit-identical
+ * to a direct mssvt_block_geometry call with that pattern; the chessboard probes and both FPS passes are not
+ * repeated. */
+int mssvt_block_queries(int nq, int max_win1, int use_interp, int win_capacity, const int *win_count_total,
+                        const int *src_row, const int *win1_row, const int *meta_in, const float *xyz, int *q_row,
+                        int *meta_out, unsigned char *nn_idx, float *nn_w, void *stream) {
+    if (nq <= 0 || nq > 255 || max_win1 <= 0 || win_capacity < 0) return MSSVT_ERR_INVALID;
+    if (win_capacity == 0) return MSSVT_OK;
+    if (!win_count_total || !src_row || !win1_row || !meta_in || !xyz || !q_row || !meta_out) return MSSVT_ERR_INVALID;
+    if (use_interp && (!nn_idx || !nn_w)) return MSSVT_ERR_INVALID;
+    const size_t smem = (size_t)GEO_WARPS * 3 * nq * sizeof(float);
+    ++g_launches;
+    k_block_queries<<<persistent_grid(win_capacity, GEO_WARPS, 8), GEO_WARPS * 32, smem, (cudaStream_t)stream>>>(
+        nq, max_win1, use_interp ? 1 : 0, win_capacity, win_count_total, src_row, win1_row, (const int4 *)meta_in, xyz,
+        q_row, (int4 *)meta_out, nn_idx, nn_w);
     return check_launch();
 }
 

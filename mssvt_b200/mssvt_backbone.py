@@ -283,51 +283,76 @@ class MixedScaleSparseTransformerBlock(nn.Module):
         return cache[key]
 
     def geometry(self, sp_tensor, taps=False):
-        """Coordinate-only part of the block (windows, chessboard lists, FPS keys, masks, three-NN),
-        computed once per (coordinates, window configuration) and cached on the tensor."""
+        """Coordinate-only part of the block (windows, chessboard lists, FPS keys, masks, three-NN), computed once
+        per (coordinates, window configuration) and cached on the tensor.  Blocks that differ only in cbs_pattern
+        share the expensive part -- chessboard probes, both FPS passes, key lists -- through one
+        mssvt_block_geometry call; every further pattern costs one mssvt_block_queries launch (query rows,
+        three-NN) plus its compact query numbering."""
         cache = sp_tensor._cache()
-        key = ("geo", tuple(self.win1_size), tuple(self.win2_size), self.max_num_win1, self.max_num_win2,
-               self.key_num_sample, self.cbs_pattern, bool(self.use_feature_interpolation), bool(taps))
+        interp = bool(self.use_feature_interpolation)
+        base = (tuple(self.win1_size), tuple(self.win2_size), self.max_num_win1, self.max_num_win2,
+                self.key_num_sample, interp, self.max_num_wins)
+        key = ("geo", base, self.cbs_pattern, bool(taps))
         if key in cache:
             return cache[key]
-        grid, win_list, _, win_count = self._windows(sp_tensor)
         dev = sp_tensor.indices.device
         N, B, K = sp_tensor.indices.shape[0], sp_tensor.batch_size, self.key_num_sample
-        cap = win_list.shape[0]
         nq = {0: self.max_num_even, 1: self.max_num_odd, 2: self.max_num_win1}[self.cbs_pattern]
-        t = self._tables(dev)
-        _, v_start = sp_tensor.sample_counts()
         i32 = dict(dtype=torch.int32, device=dev)
         u8 = dict(dtype=torch.uint8, device=dev)
-        g = {
-            "win_list": win_list, "win_count": win_count, "total": win_count[B:B + 1], "cap": cap, "nq": nq,
-            "q_row": torch.empty((cap, nq), **i32),
-            "win1_row": torch.empty((cap, self.max_num_win1), **i32),
-            "k_row": torch.empty((cap, 2 * K), **i32),
-            "k_mask": torch.empty((cap, 2 * K), **u8),
-            "nn_idx": torch.empty((cap, self.max_num_win1, 3), **u8) if self.use_feature_interpolation else None,
-            "nn_w": torch.empty((cap, self.max_num_win1, 3), dtype=torch.float32, device=dev)
-            if self.use_feature_interpolation else None,
-            "covered": torch.empty(N, **u8),
-            "fps_idx": torch.empty((cap, 2 * K), **i32) if taps else None,
-            "counts": torch.empty((cap, 4), **i32) if taps else None,
-            "rep_row": torch.empty((cap, 2 * K), **i32),
-            "meta": torch.empty((cap, 4), **i32),
-            "q_base": torch.empty(cap + 1, **i32),
-            "q_src": torch.empty(max(N, 1), **i32),
-            "vox_slot": torch.empty(max(N, 1), **i32),
-        }
-        sx, sy, sz = (int(v) for v in sp_tensor.spatial_shape)
-        cells, vals = sp_tensor.grid_index()
-        call("mssvt_block_geometry", sx, sy, sz, *self.win1_size,
-             t['odd'].shape[0], t['even'].shape[0], t['win1'].shape[0], t['win2'].shape[0],
-             self.max_num_win1, self.max_num_win2, K, self.cbs_pattern,
-             int(bool(self.use_feature_interpolation)), host_floats(sp_tensor.voxel_size),
-             host_floats(sp_tensor.point_cloud_range[0:3]), ptr(t['odd']), ptr(t['even']), ptr(t['win1']),
-             ptr(t['win2']), cap, ptr(g["total"]), ptr(win_list), ptr(cells), ptr(vals), ptr(v_start),
-             N, ptr(g["q_row"]), ptr(g["win1_row"]), ptr(g["k_row"]), ptr(g["k_mask"]), ptr(g["nn_idx"]),
-             ptr(g["nn_w"]), ptr(g["covered"]), ptr(g["fps_idx"]), ptr(g["counts"]), ptr(g["rep_row"]),
-             ptr(g["meta"]), ptr(g["vox_slot"]), stream())
+        shared = cache.get(("geo-shared", base)) if interp and not taps else None
+        if shared is not None:
+            # another pattern over the same windows: only the query-dependent maps are new
+            cap = shared["cap"]
+            g = dict(shared)
+            g.update({"nq": nq, "q_row": torch.empty((cap, nq), **i32), "meta": torch.empty((cap, 4), **i32),
+                      "nn_idx": torch.empty((cap, self.max_num_win1, 3), **u8),
+                      "nn_w": torch.empty((cap, self.max_num_win1, 3), dtype=torch.float32, device=dev),
+                      "q_base": torch.empty(cap + 1, **i32), "q_src": torch.empty(max(N, 1), **i32)})
+            for k in [k for k in g if isinstance(k, tuple)]:
+                del g[k]                                   # (tile plans belong to the other pattern's numbering)
+            src = {0: shared["even_row"], 1: shared["odd_row"], 2: shared["win1_row"]}[self.cbs_pattern]
+            call("mssvt_block_queries", nq, self.max_num_win1, 1, cap, ptr(g["total"]), ptr(src), ptr(g["win1_row"]),
+                 ptr(shared["meta"]), ptr(sp_tensor.world_coords()), ptr(g["q_row"]), ptr(g["meta"]), ptr(g["nn_idx"]),
+                 ptr(g["nn_w"]), stream())
+        else:
+            grid, win_list, _, win_count = self._windows(sp_tensor)
+            cap = win_list.shape[0]
+            t = self._tables(dev)
+            _, v_start = sp_tensor.sample_counts()
+            share = interp and not taps and len(self.__dict__.get("_geo_patterns", ())) > 1
+            g = {
+                "win_list": win_list, "win_count": win_count, "total": win_count[B:B + 1], "cap": cap, "nq": nq,
+                "q_row": torch.empty((cap, nq), **i32),
+                "win1_row": torch.empty((cap, self.max_num_win1), **i32),
+                "k_row": torch.empty((cap, 2 * K), **i32),
+                "k_mask": torch.empty((cap, 2 * K), **u8),
+                "nn_idx": torch.empty((cap, self.max_num_win1, 3), **u8) if interp else None,
+                "nn_w": torch.empty((cap, self.max_num_win1, 3), dtype=torch.float32, device=dev) if interp else None,
+                "covered": torch.empty(N, **u8),
+                "fps_idx": torch.empty((cap, 2 * K), **i32) if taps else None,
+                "counts": torch.empty((cap, 4), **i32) if taps else None,
+                "rep_row": torch.empty((cap, 2 * K), **i32),
+                "meta": torch.empty((cap, 4), **i32),
+                "q_base": torch.empty(cap + 1, **i32),
+                "q_src": torch.empty(max(N, 1), **i32),
+                "vox_slot": torch.empty(max(N, 1), **i32),
+                "odd_row": torch.empty((cap, self.max_num_odd), **i32) if share else None,
+                "even_row": torch.empty((cap, self.max_num_even), **i32) if share else None,
+            }
+            sx, sy, sz = (int(v) for v in sp_tensor.spatial_shape)
+            cells, vals = sp_tensor.grid_index()
+            call("mssvt_block_geometry", sx, sy, sz, *self.win1_size,
+                 t['odd'].shape[0], t['even'].shape[0], t['win1'].shape[0], t['win2'].shape[0],
+                 self.max_num_win1, self.max_num_win2, K, self.cbs_pattern,
+                 int(interp), host_floats(sp_tensor.voxel_size),
+                 host_floats(sp_tensor.point_cloud_range[0:3]), ptr(t['odd']), ptr(t['even']), ptr(t['win1']),
+                 ptr(t['win2']), cap, ptr(g["total"]), ptr(win_list), ptr(cells), ptr(vals), ptr(v_start),
+                 N, ptr(g["q_row"]), ptr(g["win1_row"]), ptr(g["k_row"]), ptr(g["k_mask"]), ptr(g["nn_idx"]),
+                 ptr(g["nn_w"]), ptr(g["covered"]), ptr(g["fps_idx"]), ptr(g["counts"]), ptr(g["rep_row"]),
+                 ptr(g["meta"]), ptr(g["vox_slot"]), ptr(g["odd_row"]), ptr(g["even_row"]), stream())
+            if share:
+                cache[("geo-shared", base)] = g
         # compact query ids for the task-parallel kernels: q_base[w] = #real queries of windows < w
         scan_ws = torch.empty((cap + 1 + 1023) // 1024 + 1, **i32)
         call("mssvt_exclusive_scan", cap, ptr(g["total"]), ptr(g["meta"]), 4, ptr(g["q_base"]), ptr(scan_ws),
@@ -712,6 +737,14 @@ class MixedScaleSparseTransformer(nn.Module):
             self.backbone.append(block)
         for blk, nxt in zip(self.backbone[:-1], self.backbone[1:]):
             blk.__dict__["_next_norm1"] = nxt.norm1  # (plain dict entry: not a registered sub-module)
+        # blocks that differ only in cbs_pattern share one chessboard / FPS pass (see Block.geometry)
+        groups = {}
+        for blk in self.backbone:
+            if type(blk) is MixedScaleSparseTransformerBlock:
+                sig = (tuple(blk.win1_size), tuple(blk.win2_size), blk.max_num_win1, blk.max_num_win2, blk.key_num_sample,
+                       bool(blk.use_feature_interpolation))
+                groups.setdefault(sig, set()).add(blk.cbs_pattern)
+                blk.__dict__["_geo_patterns"] = groups[sig]
         self.num_point_features = model_cfg.NUM_OUTPUT_FEATURES
         self.set_precision(model_cfg.get('PRECISION', 'tf32x3'))
 
