@@ -298,6 +298,11 @@ int mssvt_ffn(const void *shape, int shape_bytes, const float *params, int num_r
  * stage it with plain asynchronous copies); arguments documented as "packed" below take this form. */
 int mssvt_pack_operand_tf32(const float *w, int n_rows, int k, int terms, float *packed, void *stream);
 
+/* The bf16 form (precision mode "bf16": tcgen05.mma.kind::f16 with bf16 operands, fp32 accumulate): packed holds
+ * n_rows * k bf16 in the same K-major core-matrix layout (16-byte chunks of 8 elements).  n_rows % 8 == 0,
+ * k % 16 == 0.  mssvt_ffn_tc and mssvt_block_attention_tc take these copies when called with terms = 0. */
+int mssvt_pack_operand_bf16(const float *w, int n_rows, int k, void *packed, void *stream);
+
 /* The same FFN on the tcgen05 tensor cores: TF32 operands, fp32 accumulation in TMEM, LayerNorm and
  * the residual stream in fp32 (mssvt_b200/csrc/ffn_tc.cu).  w1 [F][C] and w2 [C][F] (nn.Linear layout) packed by
  * mssvt_pack_operand_tf32.  Supported shapes: C in {32, 64}, F % 64 == 0, F + C <= 512; -1 otherwise.

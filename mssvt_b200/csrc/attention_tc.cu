@@ -114,13 +114,14 @@ k_tca_plan(int heads, int win_cap, const int *__restrict__ win_count_total, cons
 // shared-memory carve-up of k_tca_tile (bytes); NT = operand tiles per matrix: hi [, lo]
 struct TcaSmem {
     int wpos, wkvq, wp, apos, ao, rows, hdr, misc, total;
-    __host__ __device__ explicit TcaSmem(int nt) {
+    // nt = operand tiles per matrix (hi [, lo]); eb = bytes per operand element (4: TF32, 2: bf16)
+    __host__ __device__ explicit TcaSmem(int nt, int eb = 4) {
         wpos = 0;                                  // [hi | lo] x [2 chunks][32][16 B]                    2 KB
-        wkvq = wpos + 2048;                        // nt x [8 chunks][96][16 B]                          12 KB each
-        wp = wkvq + nt * 96 * 32 * 4;              // nt x [8 chunks][32][16 B]                           4 KB each
-        apos = wp + nt * 32 * 32 * 4;              // [hi | lo] x [2 chunks][128][16 B]; later the scores  8 KB
-        ao = apos + 8192;                          // nt x [QMAX / 8][8 chunks][8][16 B]                   8 KB each
-        rows = ao + nt * TCA_QMAX * TCA_SD * 4;    // gather staging, later V / Q rows [128][32]          16 KB
+        wkvq = wpos + 2048;                        // nt x [chunks][96][16 B]                    12 KB each (TF32)
+        wp = wkvq + nt * 96 * 32 * eb;             // nt x [chunks][32][16 B]                     4 KB each (TF32)
+        apos = wp + nt * 32 * 32 * eb;             // [hi | lo] x [2 chunks][128][16 B]; later the scores  8 KB
+        ao = apos + 8192;                          // nt x [QMAX / 8][chunks][8][16 B]            6 KB each (TF32)
+        rows = ao + nt * TCA_QMAX * TCA_SD * eb;   // gather staging, later V / Q rows [128][32]          16 KB
         hdr = rows + TCA_THREADS * TCA_SD * 4;     // (the MMA reads 128 rows of `ao`: it runs into `rows`)
         misc = hdr + 2 * TCA_TW * 32;              // 2 x {window records [TW] int4, window centres [TW] float4}
         total = misc + 128 * 4 + TCA_QMAX * 4 + 8 + 16 + 128;   // biases, sQwin, barrier
@@ -175,6 +176,8 @@ k_tca_tile(TcAttnParams P, int win_cap, const int2 *__restrict__ tiles, const in
            float *__restrict__ Pbuf) {
     constexpr int HD = TCA_SD / HEADS;
     constexpr int NT = TERMS == 3 ? 2 : 1;       // operand tiles: hi [, lo] (3xTF32, tc_common.cuh)
+    constexpr bool BF = TERMS == 0;              // bf16 operands (kind::f16) for the K|V|Q and output projections
+    constexpr int EB = BF ? 2 : 4;
     // TMEM: 128 columns; the 3xTF32 kernel takes 32 more (low half of the A operand) as a SECOND allocation:
     // 160 columns per CTA keep three CTAs on an SM, one 256-column allocation would allow two
     extern __shared__ __align__(128) char smem_raw[];
@@ -200,7 +203,7 @@ k_tca_tile(TcAttnParams P, int win_cap, const int2 *__restrict__ tiles, const in
     tiles += (size_t)g * win_cap;
     win_rec += (size_t)g * win_cap;
 
-    const TcaSmem L(NT);
+    const TcaSmem L(NT, EB);
     char *sWpos = smem_raw + L.wpos, *sWkvq = smem_raw + L.wkvq, *sWp = smem_raw + L.wp;
     char *sApos = smem_raw + L.apos, *sAO = smem_raw + L.ao, *sRows = smem_raw + L.rows;
     float *sS = (float *)sApos;                             // [SBUD] scores: window-major, [key][query][head]
@@ -221,8 +224,8 @@ k_tca_tile(TcAttnParams P, int win_cap, const int2 *__restrict__ tiles, const in
                          "l"((const char *)P.wpos + hl * 2048 + ch * 1024 + (g * 32 + n) * 16) : "memory");
         }
     }
-    stage_packed(P.wkvq[g], NT * 96 * 32, sWkvq);
-    stage_packed(P.wp[g], NT * 32 * 32, sWp);
+    stage_packed(P.wkvq[g], NT * 96 * 32 * EB / 4, sWkvq);
+    stage_packed(P.wp[g], NT * 32 * 32 * EB / 4, sWp);
     if (tid < 32) {
         sBias[tid] = __ldg(P.bq[g] + tid) * P.scale;
         sBias[32 + tid] = __ldg(P.bkv[g] + 32 + tid);
@@ -284,7 +287,8 @@ k_tca_tile(TcAttnParams P, int win_cap, const int2 *__restrict__ tiles, const in
     const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
     const uint32_t tm_a = tm, tm_k = tm + 32u, tm_v = tm + 64u, tm_q = tm + 96u;
     const uint32_t tm_alo = TERMS == 3 ? sTmem[1] : 0u;
-    const uint32_t id_n32 = umma_idesc_tf32(128, 32), id_n96 = umma_idesc_tf32(128, 96);
+    const uint32_t id_n32 = umma_idesc_tf32(128, 32), id_n96 = BF ? umma_idesc_bf16(128, 96) : umma_idesc_tf32(128, 96);
+    const uint32_t id_p32 = BF ? umma_idesc_bf16(128, 32) : id_n32;   // output projection
     const uint32_t sWpos_u = smem_u32(sWpos), sWkvq_u = smem_u32(sWkvq), sWp_u = smem_u32(sWp);
     const uint32_t sApos_u = smem_u32(sApos), sAO_u = smem_u32(sAO);
     const uint32_t row_off = (uint32_t)(tid >> 3) * 128u + (uint32_t)(tid & 7) * 16u;   // canonical 8-row groups
@@ -373,7 +377,16 @@ k_tca_tile(TcAttnParams P, int win_cap, const int2 *__restrict__ tiles, const in
             // ---- 2. A1 = xn slice + relu(pos), TF32, written back over the accumulator (A operand from TMEM)
             float d[TCA_SD];
             tmem_ld32(tm_a + lane_off, d);
-            if (TERMS == 3) {
+            if constexpr (BF) {
+                // packed bf16 pairs: channel k in column k / 2 (16 columns, in place over the accumulator)
+                uint32_t w[TCA_SD / 2];
+#pragma unroll
+                for (int c4 = 0; c4 < TCA_SD / 4; ++c4) {
+                    w[2 * c4] = pack_bf16x2(xv[c4].x + fmaxf(d[4 * c4], 0.f), xv[c4].y + fmaxf(d[4 * c4 + 1], 0.f));
+                    w[2 * c4 + 1] = pack_bf16x2(xv[c4].z + fmaxf(d[4 * c4 + 2], 0.f), xv[c4].w + fmaxf(d[4 * c4 + 3], 0.f));
+                }
+                tmem_st16(tm_a + lane_off, w);
+            } else if (TERMS == 3) {
                 float lo[TCA_SD];
 #pragma unroll
                 for (int c4 = 0; c4 < TCA_SD / 4; ++c4) {
@@ -392,7 +405,7 @@ k_tca_tile(TcAttnParams P, int win_cap, const int2 *__restrict__ tiles, const in
                     d[4 * c4 + 3] = to_tf32(xv[c4].w + fmaxf(d[4 * c4 + 3], 0.f));
                 }
             }
-            tmem_st32(tm_a + lane_off, d);
+            if constexpr (!BF) tmem_st32(tm_a + lane_off, d);
             tmem_st_wait();
         }
         tc_fence_before();
@@ -401,6 +414,12 @@ k_tca_tile(TcAttnParams P, int win_cap, const int2 *__restrict__ tiles, const in
         // ---- [K | V | Q] = A1 [Wk; Wv; scale Wq]^T: K in TMEM columns 32..63, V in 64..95, Q in 96..127
         if (tid == 0) {
             tc_fence_after();
+            if constexpr (BF) {
+#pragma unroll
+                for (int k = 0; k < TCA_SD / 16; ++k)   // K = 16 per MMA: 8 packed A columns, two 16-byte B chunks
+                    umma_bf16_ts(tm_k, tm_a + (uint32_t)k * 8u, umma_smem_desc(sWkvq_u + (uint32_t)k * 2u * 1536u, 1536, 128),
+                                 id_n96, k > 0 ? 1u : 0u);
+            } else
 #pragma unroll
             for (int k = 0; k < TCA_SD / 8; ++k) {
                 const uint64_t wh = umma_smem_desc(sWkvq_u + (uint32_t)k * 2u * 1536u, 1536, 128);
@@ -510,8 +529,20 @@ k_tca_tile(TcAttnParams P, int win_cap, const int2 *__restrict__ tiles, const in
                 }
             }
             const float inv = 1.0f / den;
-            char *dst = sAO + (qs >> 3) * 1024 + (qs & 7) * 16 + ch0 * 128;
             const float *bv = sBias + 32 + 4 * ch0;
+            if constexpr (BF) {
+                // bf16 operand rows: 8-row groups of 4 chunks of 8 elements, byte = (q / 8) * 512 + chunk * 128 + (q % 8) * 16
+                const int c0 = 4 * ch0;
+                char *dst = sAO + (qs >> 3) * 512 + (qs & 7) * 16 + (c0 >> 3) * 128 + (c0 & 7) * 2;
+#pragma unroll
+                for (int d = 0; d < DPT; d += 2) {
+                    const int c = c0 + d;      // (pairs never straddle a chunk: c0 and DPT are multiples of 4)
+                    *(uint32_t *)(dst + ((c >> 3) - (c0 >> 3)) * 128 + ((c & 7) - (c0 & 7)) * 2) =
+                        pack_bf16x2(fmaf(acc[d], inv, bv[d]), fmaf(acc[d + 1], inv, bv[d + 1]));
+                }
+                continue;
+            }
+            char *dst = sAO + (qs >> 3) * 1024 + (qs & 7) * 16 + ch0 * 128;
 #pragma unroll
             for (int d4 = 0; d4 < DPT / 4; ++d4) {
                 float4 hi, lo;
@@ -527,6 +558,12 @@ k_tca_tile(TcAttnParams P, int win_cap, const int2 *__restrict__ tiles, const in
         // ---- output projection of the group: rows = the tile's queries
         if (tid == 0) {
             tc_fence_after();
+            if constexpr (BF) {
+#pragma unroll
+                for (int k = 0; k < TCA_SD / 16; ++k)
+                    umma_bf16(tm_a, umma_smem_desc(sAO_u + (uint32_t)k * 256u, 128, 512),
+                              umma_smem_desc(sWp_u + (uint32_t)k * 1024u, 512, 128), id_p32, k > 0 ? 1u : 0u);
+            } else
 #pragma unroll
             for (int k = 0; k < TCA_SD / 8; ++k) {
                 const uint64_t ah = umma_smem_desc(sAO_u + (uint32_t)k * 256u, 128, 1024);
@@ -697,7 +734,7 @@ int mssvt_block_attention_tc(int C, int heads_per_group, int nq, int key_num_sam
                              const float *win_ctr, int num_voxels, float *scratch, float *merged, void *stream) {
     if (C != 64 || (heads_per_group != 1 && heads_per_group != 2 && heads_per_group != 4) || nq <= 0 || nq > 32 ||
         key_num_sample <= 0 || key_num_sample > 63 || cap1 <= 0 || cap1 > 128 || win_capacity < 0 || num_voxels < 0 ||
-        nq * (key_num_sample + 1) * heads_per_group > TCA_SBUD || (terms != 1 && terms != 3))
+        nq * (key_num_sample + 1) * heads_per_group > TCA_SBUD || (terms != 0 && terms != 1 && terms != 3))
         return MSSVT_ERR_INVALID;
     if (win_capacity == 0) return MSSVT_OK;
     if (!wpos_packed || !wkvq0 || !wkvq1 || !wp0 || !wp1 || !bq0 || !bq1 || !bkv0 || !bkv1 || !bp0 || !bp1 ||
@@ -711,7 +748,7 @@ int mssvt_block_attention_tc(int C, int heads_per_group, int nq, int key_num_sam
     P.wpos = wpos_packed;
     P.wkvq[0] = wkvq0; P.wkvq[1] = wkvq1; P.wp[0] = wp0; P.wp[1] = wp1;
     P.bq[0] = bq0; P.bq[1] = bq1; P.bkv[0] = bkv0; P.bkv[1] = bkv1; P.bp[0] = bp0; P.bp[1] = bp1;
-    const size_t smem = (size_t)TcaSmem(terms == 3 ? 2 : 1).total;
+    const size_t smem = (size_t)TcaSmem(terms == 3 ? 2 : 1, terms == 0 ? 2 : 4).total;
     float *Pbuf = scratch + 2 * (size_t)num_voxels * 64;
     cudaStream_t s = (cudaStream_t)stream;
     const int wide = MSSVT_NUM_SMS * 8;  // grid-stride kernels: 8 CTAs of 256 threads per SM
@@ -725,7 +762,11 @@ int mssvt_block_attention_tc(int C, int heads_per_group, int nq, int key_num_sam
     cudaFuncSetAttribute(k_tca_tile<H, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
     launch_pdl(k_tca_tile<H, T>, dim3(grid), dim3(TCA_THREADS), smem, s, P, win_capacity, (const int2 *)tiles, \
                tile_count, (const int4 *)win_rec, (const float4 *)win_ctr, xn, xyz, rep_row, q_row, Pbuf)
-    if (terms == 3) {
+    if (terms == 0) {
+        if (heads_per_group == 1) { TCA_LAUNCH(1, 0); }
+        else if (heads_per_group == 2) { TCA_LAUNCH(2, 0); }
+        else { TCA_LAUNCH(4, 0); }
+    } else if (terms == 3) {
         if (heads_per_group == 1) { TCA_LAUNCH(1, 3); }
         else if (heads_per_group == 2) { TCA_LAUNCH(2, 3); }
         else { TCA_LAUNCH(4, 3); }

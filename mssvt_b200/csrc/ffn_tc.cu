@@ -50,6 +50,8 @@ struct FfnTcParams {
     int cap1;
 };
 
+// TERMS: 1 = TF32 operands, 3 = split operands (3xTF32), 0 = bf16 operands (kind::f16; half the operand bytes,
+// the hidden tile packed two per TMEM column)
 template <int C, int TERMS>
 __global__ void __launch_bounds__(TC_THREADS, TERMS == 3 ? 1 : 2)
 k_ffn_tc(FfnTcParams P, int n_cap, const int *__restrict__ n_dev, const float *__restrict__ x,
@@ -63,16 +65,18 @@ k_ffn_tc(FfnTcParams P, int n_cap, const int *__restrict__ n_dev, const float *_
     const int r = tid & (TC_ROWS - 1), half = tid >> 7;
     // carve shared memory
     constexpr int NT = TERMS == 3 ? 2 : 1;        // operand tiles: hi [, lo] (3xTF32, see tc_common.cuh)
-    char *sA = smem_raw;                          // NT x [C/4][128][16 B]
-    char *sW1 = sA + NT * TC_ROWS * C * 4;        // NT x [C/4][F][16 B]
-    char *sW2 = sW1 + NT * F * C * 4;             // NT x [F/4][C][16 B]
-    float *s_vec = (float *)(sW2 + NT * C * F * 4);    // ln_g[C], ln_b[C], b1[F], b2[C], next_g[C], next_b[C]
+    constexpr bool BF = TERMS == 0;               // bf16 operands
+    constexpr int EB = BF ? 2 : 4;                // bytes per operand element
+    char *sA = smem_raw;                          // NT x [chunks][128][16 B] (at least the 32 KB staging area)
+    char *sW1 = sA + (BF ? TC_ROWS * C * 4 : NT * TC_ROWS * C * 4);   // NT x [chunks][F][16 B]
+    char *sW2 = sW1 + NT * F * C * EB;            // NT x [chunks][C][16 B]
+    float *s_vec = (float *)(sW2 + NT * C * F * EB);   // ln_g[C], ln_b[C], b1[F], b2[C], next_g[C], next_b[C]
     float *s_red = s_vec + 5 * C + F;             // [4][2][128] partial row sums of the two half-row threads
     uint64_t *s_bar = (uint64_t *)(s_red + 8 * TC_ROWS);  // 2 mbarriers (8-byte aligned: C, F even)
     uint32_t *s_tmem = (uint32_t *)(s_bar + 2);
 
-    stage_packed(P.w1, NT * F * C, sW1);
-    stage_packed(P.w2, NT * C * F, sW2);
+    stage_packed(P.w1, NT * F * C * EB / 4, sW1);
+    stage_packed(P.w2, NT * C * F * EB / 4, sW2);
     for (int i = tid; i < C; i += TC_THREADS) {
         s_vec[i] = __ldg(P.ln_g + i);
         s_vec[C + i] = __ldg(P.ln_b + i);
@@ -93,7 +97,7 @@ k_ffn_tc(FfnTcParams P, int n_cap, const int *__restrict__ n_dev, const float *_
     }
     // TMEM: F columns for D1 / hidden + C columns for D2, rounded up to a power of two >= 32
     uint32_t tmem_cols = 32;
-    while (tmem_cols < (uint32_t)(F + C + (TERMS == 3 ? F : 0))) tmem_cols <<= 1;
+    while (tmem_cols < (uint32_t)(F + C + (TERMS == 3 ? F : BF ? F / 2 : 0))) tmem_cols <<= 1;
     if (warp == 0) tmem_alloc(smem_u32(s_tmem), tmem_cols);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // staged weights -> async proxy
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -101,10 +105,12 @@ k_ffn_tc(FfnTcParams P, int n_cap, const int *__restrict__ n_dev, const float *_
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *s_tmem;
     const uint32_t tmem_d1 = tmem_base, tmem_d2 = tmem_base + (uint32_t)F;
-    const uint32_t tmem_hlo = tmem_base + (uint32_t)(F + C);   // (TERMS == 3) low part of the hidden tile
+    const uint32_t tmem_hlo = tmem_base + (uint32_t)(F + C);   // (TERMS == 3) low part of the hidden tile;
+                                                               // (bf16) the packed hidden tile, F / 2 columns
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;  // a warp reaches TMEM lanes 32 (w % 4) ...
 
-    const uint32_t idesc1 = umma_idesc_tf32(TC_ROWS, F), idesc2 = umma_idesc_tf32(TC_ROWS, C);
+    const uint32_t idesc1 = BF ? umma_idesc_bf16(TC_ROWS, F) : umma_idesc_tf32(TC_ROWS, F);
+    const uint32_t idesc2 = BF ? umma_idesc_bf16(TC_ROWS, C) : umma_idesc_tf32(TC_ROWS, C);
     const uint32_t a_lbo = TC_ROWS * 16, w1_lbo = (uint32_t)F * 16, w2_lbo = (uint32_t)C * 16;
     const uint32_t sA_u = smem_u32(sA), sW1_u = smem_u32(sW1), sW2_u = smem_u32(sW2);
 
@@ -244,16 +250,30 @@ k_ffn_tc(FfnTcParams P, int n_cap, const int *__restrict__ n_dev, const float *_
         red_mine[2 * TC_ROWS] = part;
         __syncthreads();
         const float rstd = rsqrtf((part + red_other[2 * TC_ROWS]) * (1.0f / C) + P.eps);
+        if constexpr (BF) {
+            // 16-byte chunks of 8 bf16: chunk = channel / 8
 #pragma unroll
-        for (int c = 0; c < CH / 4; ++c) {
-            float4 v, hi, lo;
-            v.x = (u[4 * c] - mean) * rstd * s_g[4 * c] + s_b[4 * c];
-            v.y = (u[4 * c + 1] - mean) * rstd * s_g[4 * c + 1] + s_b[4 * c + 1];
-            v.z = (u[4 * c + 2] - mean) * rstd * s_g[4 * c + 2] + s_b[4 * c + 2];
-            v.w = (u[4 * c + 3] - mean) * rstd * s_g[4 * c + 3] + s_b[4 * c + 3];
-            split_tf32(v, hi, lo);
-            *(float4 *)(sA + (uint32_t)(half * (CH / 4) + c) * a_lbo + my_row_off) = hi;
-            if (TERMS == 3) *(float4 *)(sA + TC_ROWS * C * 4 + (uint32_t)(half * (CH / 4) + c) * a_lbo + my_row_off) = lo;
+            for (int c = 0; c < CH / 8; ++c) {
+                uint32_t w[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int i = 8 * c + 2 * q;
+                    w[q] = pack_bf16x2((u[i] - mean) * rstd * s_g[i] + s_b[i], (u[i + 1] - mean) * rstd * s_g[i + 1] + s_b[i + 1]);
+                }
+                *(uint4 *)(sA + (uint32_t)(half * (CH / 8) + c) * a_lbo + my_row_off) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < CH / 4; ++c) {
+                float4 v, hi, lo;
+                v.x = (u[4 * c] - mean) * rstd * s_g[4 * c] + s_b[4 * c];
+                v.y = (u[4 * c + 1] - mean) * rstd * s_g[4 * c + 1] + s_b[4 * c + 1];
+                v.z = (u[4 * c + 2] - mean) * rstd * s_g[4 * c + 2] + s_b[4 * c + 2];
+                v.w = (u[4 * c + 3] - mean) * rstd * s_g[4 * c + 3] + s_b[4 * c + 3];
+                split_tf32(v, hi, lo);
+                *(float4 *)(sA + (uint32_t)(half * (CH / 4) + c) * a_lbo + my_row_off) = hi;
+                if (TERMS == 3) *(float4 *)(sA + TC_ROWS * C * 4 + (uint32_t)(half * (CH / 4) + c) * a_lbo + my_row_off) = lo;
+            }
         }
         stage_packed_wait();  // (first tile: the weight copies overlapped the loads and the LayerNorm)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -262,10 +282,17 @@ k_ffn_tc(FfnTcParams P, int n_cap, const int *__restrict__ n_dev, const float *_
         // ---- 2. D1[128 x F] = A[128 x C] . W1^T, one K = 8 slice (two 16-byte chunks) per MMA
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if constexpr (BF) {
 #pragma unroll
-            for (int k = 0; k < C / 8; ++k)
-                umma_step<TERMS>(tmem_d1, sA_u + (uint32_t)k * 2u * a_lbo, a_lbo, TC_ROWS * C * 4,
-                                 sW1_u + (uint32_t)k * 2u * w1_lbo, w1_lbo, (uint32_t)(F * C * 4), idesc1, k == 0);
+                for (int k = 0; k < C / 16; ++k)       // K = 16 per MMA: two 16-byte chunks of 8 elements
+                    umma_bf16(tmem_d1, umma_smem_desc(sA_u + (uint32_t)k * 2u * a_lbo, a_lbo, 128),
+                              umma_smem_desc(sW1_u + (uint32_t)k * 2u * w1_lbo, w1_lbo, 128), idesc1, k > 0 ? 1u : 0u);
+            } else {
+#pragma unroll
+                for (int k = 0; k < C / 8; ++k)
+                    umma_step<TERMS>(tmem_d1, sA_u + (uint32_t)k * 2u * a_lbo, a_lbo, TC_ROWS * C * 4,
+                                     sW1_u + (uint32_t)k * 2u * w1_lbo, w1_lbo, (uint32_t)(F * C * 4), idesc1, k == 0);
+            }
             umma_commit(bar1);
         }
         TRACE(3);
@@ -277,6 +304,15 @@ k_ffn_tc(FfnTcParams P, int n_cap, const int *__restrict__ n_dev, const float *_
             float d[32];
             const uint32_t col = tmem_d1 + lane_off + (uint32_t)(half * FH + c0);
             tmem_ld32(col, d);
+            if constexpr (BF) {
+                // relu(D1 + b1) as packed bf16 pairs: hidden element k lives in column k / 2 of the packed tile
+                uint32_t w[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    w[i] = pack_bf16x2(fmaxf(d[2 * i] + s_b1[c0 + 2 * i], 0.f), fmaxf(d[2 * i + 1] + s_b1[c0 + 2 * i + 1], 0.f));
+                tmem_st16(tmem_hlo + lane_off + (uint32_t)((half * FH + c0) / 2), w);
+                continue;
+            }
             if (TERMS == 3) {
                 float lo[32];
 #pragma unroll
@@ -296,6 +332,11 @@ k_ffn_tc(FfnTcParams P, int n_cap, const int *__restrict__ n_dev, const float *_
         // ---- 4. D2[128 x C] = H[128 x F] . W2^T, H read from TMEM
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if constexpr (BF) {
+                for (int k = 0; k < F / 16; ++k)       // A: 8 packed columns per K = 16 step
+                    umma_bf16_ts(tmem_d2, tmem_hlo + (uint32_t)k * 8u,
+                                 umma_smem_desc(sW2_u + (uint32_t)k * 2u * w2_lbo, w2_lbo, 128), idesc2, k > 0 ? 1u : 0u);
+            } else
             for (int k = 0; k < F / 8; ++k) {
                 const uint64_t db = umma_smem_desc(sW2_u + (uint32_t)k * 2u * w2_lbo, w2_lbo, 128);
                 umma_tf32_ts(tmem_d2, tmem_d1 + (uint32_t)k * 8u, db, idesc2, k > 0 ? 1u : 0u);
@@ -380,11 +421,32 @@ __global__ void k_pack_operand_tf32(const float *__restrict__ src, int n_rows, i
     if (terms == 3) *(float4 *)(at + (size_t)n_rows * k * 4) = lo;   // second tile: the low parts
 }
 
+// row-major [n_rows][k] fp32 -> canonical K-major UMMA layout of bf16 (8-row x 16-byte core matrices = 8 elements)
+__global__ void k_pack_operand_bf16(const float *__restrict__ src, int n_rows, int k, uint4 *__restrict__ dst) {
+    const int chunks = k >> 3;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_rows * chunks) return;
+    const int n = e / chunks, c = e - n * chunks;
+    const float4 a = __ldg((const float4 *)(src + (size_t)n * k) + 2 * c), b = __ldg((const float4 *)(src + (size_t)n * k) + 2 * c + 1);
+    char *at = (char *)dst + (size_t)c * n_rows * 16 + (n >> 3) * 128 + (n & 7) * 16;
+    *(uint4 *)at = make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
+}
+
 }  // namespace mssvt
 
 using namespace mssvt;
 
 extern "C" {
+
+// The bf16 form of mssvt_pack_operand_tf32 (precision mode "bf16", tcgen05.mma.kind::f16): packed holds
+// n_rows * k bf16 (2 bytes each).  n_rows % 8 == 0, k % 16 == 0.
+int mssvt_pack_operand_bf16(const float *w, int n_rows, int k, void *packed, void *stream) {
+    if (!w || !packed || n_rows <= 0 || k <= 0 || (n_rows & 7) || (k & 15)) return MSSVT_ERR_INVALID;
+    const int n = n_rows * (k >> 3);
+    ++g_launches;
+    k_pack_operand_bf16<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, n_rows, k, (uint4 *)packed);
+    return check_launch();
+}
 
 // Packs a weight matrix w [n_rows][k] (nn.Linear layout: out x in) for the tensor-core kernels: TF32
 // rounding + the K-major core-matrix layout tcgen05.mma reads from shared memory.  Done once per
@@ -398,8 +460,8 @@ int mssvt_pack_operand_tf32(const float *w, int n_rows, int k, int terms, float 
     return check_launch();
 }
 
-// Tensor-core FFN (TF32 operands, fp32 accumulate).  w1 [F][C] and w2 [C][F] (nn.Linear layout) packed
-// by mssvt_pack_operand_tf32.  Supported: C in {32, 64}, F a multiple of 64 with F + C <= 512 and the operand
+// Tensor-core FFN (fp32 accumulate; terms 1: TF32 operands, 3: split 3xTF32 operands, 0: bf16 operands).  w1 [F][C]
+// and w2 [C][F] (nn.Linear layout) packed by mssvt_pack_operand_tf32 (terms 1 / 3) or mssvt_pack_operand_bf16 (terms 0).  Supported: C in {32, 64}, F a multiple of 64 with F + C <= 512 and the operand
 // tiles fitting in shared memory; returns MSSVT_ERR_INVALID otherwise (callers then use mssvt_ffn).
 int mssvt_ffn_tc(int C, int F, int mode, int terms, float eps, const float *ln_g, const float *ln_b, const float *w1,
                  const float *b1, const float *w2, const float *b2, int num_rows, const int *num_rows_dev,
@@ -407,8 +469,8 @@ int mssvt_ffn_tc(int C, int F, int mode, int terms, float eps, const float *ln_g
                  const float *next_ln_g, const float *next_ln_b, float next_eps, float *xn_next,
                  const int *vox_slot, const int *meta, const int *q_base, const unsigned char *nn_idx,
                  const float *nn_w, const float *projected, int cap1, void *stream) {
-    if ((C != 32 && C != 64) || F <= 0 || (F & 63) || F + C + (terms == 3 ? F : 0) > 512 || num_rows < 0 ||
-        (terms != 1 && terms != 3))
+    if ((C != 32 && C != 64) || F <= 0 || (F & 63) || F + C + (terms == 3 ? F : terms == 0 ? F / 2 : 0) > 512 || num_rows < 0 ||
+        (terms != 0 && terms != 1 && terms != 3))
         return MSSVT_ERR_INVALID;
     if (num_rows == 0) return MSSVT_OK;
     if (mode < 0 || mode > 2 || !ln_g || !ln_b || !w1 || !b1 || !w2 || !b2 || !y || (mode != 2 && !merged) ||
@@ -418,13 +480,15 @@ int mssvt_ffn_tc(int C, int F, int mode, int terms, float eps, const float *ln_g
         return MSSVT_ERR_INVALID;
     const int nt = terms == 3 ? 2 : 1;
     size_t smem = nt * ((size_t)TC_ROWS * C * 4 + 2 * (size_t)F * C * 4) + (size_t)(5 * C + F + 8 * TC_ROWS) * 4 + 2 * 8 + 16 + 128;
+    if (terms == 0)  // bf16 operands: the A region keeps the size of the fp32 staging area, the weights halve
+        smem = (size_t)TC_ROWS * C * 4 + 2 * (size_t)F * C * 2 + (size_t)(5 * C + F + 8 * TC_ROWS) * 4 + 2 * 8 + 16 + 128;
     if (smem > 227 * 1024) return MSSVT_ERR_INVALID;
     if (xn_next && (!next_ln_g || !next_ln_b)) return MSSVT_ERR_INVALID;
     FfnTcParams P = {F, mode, eps, w1, b1, w2, b2, ln_g, ln_b, next_ln_g, next_ln_b, next_eps,
                      vox_slot, meta, q_base, nn_idx, nn_w, projected, cap1};
     int tiles = (num_rows + TC_ROWS - 1) / TC_ROWS;
     int tmem_cols = 32;
-    while (tmem_cols < F + C + (terms == 3 ? F : 0)) tmem_cols <<= 1;
+    while (tmem_cols < F + C + (terms == 3 ? F : terms == 0 ? F / 2 : 0)) tmem_cols <<= 1;
     int per_sm = (int)(227 * 1024 / (smem + 1024));
     if (per_sm > 512 / tmem_cols) per_sm = 512 / tmem_cols;
     per_sm = per_sm > 2 ? 2 : per_sm < 1 ? 1 : per_sm;
@@ -434,7 +498,9 @@ int mssvt_ffn_tc(int C, int F, int mode, int terms, float eps, const float *ln_g
     cudaFuncSetAttribute(k_ffn_tc<CC, TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
     launch_pdl(k_ffn_tc<CC, TT>, dim3(grid), dim3(TC_THREADS), smem, (cudaStream_t)stream, P, num_rows,        \
                num_rows_dev, x, merged, covered, y, xn_next)
-    if (C == 64 && terms == 3) { FFN_TC_LAUNCH(64, 3); }
+    if (C == 64 && terms == 0) { FFN_TC_LAUNCH(64, 0); }
+    else if (terms == 0) { FFN_TC_LAUNCH(32, 0); }
+    else if (C == 64 && terms == 3) { FFN_TC_LAUNCH(64, 3); }
     else if (C == 64) { FFN_TC_LAUNCH(64, 1); }
     else if (terms == 3) { FFN_TC_LAUNCH(32, 3); }
     else { FFN_TC_LAUNCH(32, 1); }

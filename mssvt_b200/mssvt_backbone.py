@@ -23,6 +23,9 @@ from ._lib import AttnShape, FfnShape, call, ptr, stream, host_floats
 from .mssvt_utils import MixedScaleAttention, SparseTensor, sample_counts
 
 
+TC_MODES = ("tf32", "tf32x3", "bf16")     # precision modes that run on the tcgen05 kernels
+
+
 class DropPath(nn.Module):
     """Stochastic depth (timm.models.layers.DropPath, used at mssvt_backbone.py:4, 42): identity
     in eval mode (the fused kernels); active on the autograd path in training mode."""
@@ -364,7 +367,7 @@ class MixedScaleSparseTransformerBlock(nn.Module):
     def _tc_supported(self, nq):
         """shape family of the tensor-core window attention (mssvt_block_attention_tc)"""
         a = self.ms_attn
-        return (self.precision in ("tf32", "tf32x3") and self.in_channels == 64 and a.scale_dims == [32, 32]
+        return (self.precision in TC_MODES and self.in_channels == 64 and a.scale_dims == [32, 32]
                 and a.num_heads[0] == a.num_heads[1] and a.num_heads[0] in (1, 2, 4) and nq <= 32
                 and self.key_num_sample <= 63 and self.max_num_win1 <= 128 and len(self.pos_proj) == 2
                 and nq * (self.key_num_sample + 1) * a.num_heads[0] <= 2048)
@@ -428,8 +431,9 @@ class MixedScaleSparseTransformerBlock(nn.Module):
         return S, buf
 
     def _terms(self):
-        """1: TF32 operands; 3: split operands ("3xTF32", fp32-grade results on the tensor cores)"""
-        return 3 if self.precision == "tf32x3" else 1
+        """operand form of the tensor-core kernels -- 1: TF32; 3: split TF32 ("3xTF32", fp32-grade results);
+        0: bf16 (tcgen05.mma.kind::f16)"""
+        return {"tf32x3": 3, "bf16": 0}.get(self.precision, 1)
 
     @staticmethod
     def _block_diag(*mats):
@@ -455,9 +459,13 @@ class MixedScaleSparseTransformerBlock(nn.Module):
         mats = [w.detach().reshape(w.shape[0], -1).float() for w in weights]
         w2d = (build or self._block_diag)(*mats).contiguous()
         shape = (2 if terms == 3 else 1,) + tuple(w2d.shape)            # [hi | lo] for 3xTF32
-        if out is None or tuple(out.shape) != shape or out.device != w2d.device:
-            out = w2d.new_empty(shape)
-        call("mssvt_pack_operand_tf32", ptr(w2d), w2d.shape[0], w2d.shape[1], terms, ptr(out), stream())
+        dtype = torch.bfloat16 if terms == 0 else torch.float32
+        if out is None or tuple(out.shape) != shape or out.device != w2d.device or out.dtype != dtype:
+            out = torch.empty(shape, dtype=dtype, device=w2d.device)
+        if terms == 0:
+            call("mssvt_pack_operand_bf16", ptr(w2d), w2d.shape[0], w2d.shape[1], ptr(out), stream())
+        else:
+            call("mssvt_pack_operand_tf32", ptr(w2d), w2d.shape[0], w2d.shape[1], terms, ptr(out), stream())
         return out
 
     def repack_stale(self):
@@ -499,18 +507,17 @@ class MixedScaleSparseTransformerBlock(nn.Module):
         return xn
 
     def _ffn_tc_supported(self, S):
-        return (self.precision in ("tf32", "tf32x3") and S.C_out == 0 and S.C in (32, 64) and S.F % 64 == 0
-                and S.F * (2 if self._terms() == 3 else 1) + S.C <= 512
-                and (128 * S.C + 2 * S.F * S.C) * 4 * (2 if self._terms() == 3 else 1) < 220 * 1024)
+        t = self._terms()
+        return (self.precision in TC_MODES and S.C_out == 0 and S.C in (32, 64) and S.F % 64 == 0
+                and S.F * (2 if t == 3 else 1) + S.C + (S.F // 2 if t == 0 else 0) <= 512     # TMEM columns
+                and (128 * S.C + 2 * S.F * S.C) * 4 * (2 if t == 3 else 1) < 220 * 1024)      # shared memory
 
     def _ffn(self, S, buf, n_rows, x, merged, covered, n_dev=None, merge_src=None):
         """merge_src = (vox_slot, meta, q_base, nn_idx, nn_w, projected rows, cap1): the interpolation + merge
         of the window attention is done by the FFN kernel on the way in (`merged` is not used)"""
         c_out = S.C_out if S.C_out else S.C
         y = torch.empty((n_rows, c_out), dtype=torch.float32, device=x.device if x is not None else merged.device)
-        if (self.precision in ("tf32", "tf32x3") and S.C_out == 0 and S.C in (32, 64) and S.F % 64 == 0
-                and S.F * (2 if self._terms() == 3 else 1) + S.C <= 512
-                and (128 * S.C + 2 * S.F * S.C) * 4 * (2 if self._terms() == 3 else 1) < 220 * 1024):
+        if self._ffn_tc_supported(S):
             # tensor-core path: TF32 operands on tcgen05, fp32 accumulate / LayerNorm / residual
             # the epilogue also applies the NEXT block's norm1 (if there is one of the same width), which
             # saves that block a LayerNorm pass
@@ -617,9 +624,14 @@ class MixedScaleSparseTransformerCompressBlock(MixedScaleSparseTransformerBlock)
         sp_tensor.map_table = win_table
         return sp_tensor
 
+    def _attn_terms(self):
+        """the compress attention kernels have no bf16 form: in bf16 mode they run with TF32 operands (its FFN
+        does run in bf16)"""
+        return 1 if self.precision == "bf16" else self._terms()
+
     def _tc_supported(self):
         a = self.ms_attn
-        return (self.precision in ("tf32", "tf32x3") and self.in_channels == 64 and a.num_head_groups == 1
+        return (self.precision in TC_MODES and self.in_channels == 64 and a.num_head_groups == 1
                 and a.num_heads[0] in (2, 4, 8) and len(self.pos_proj) == 4 and self.max_num_win1 <= 127)
 
     def prepare(self, sp_tensor):
@@ -676,13 +688,14 @@ class MixedScaleSparseTransformerCompressBlock(MixedScaleSparseTransformerBlock)
             # task-parallel kernels; second pos_proj layer and K/V projection on the tcgen05 tensor cores
             vs = sp_tensor.voxel_size
             scratch = torch.empty((3 * cap, 64), dtype=torch.float32, device=dev)
-            call("mssvt_compress_attention_tc", 64, a.num_heads[0], n1, self._terms(), a.scale,
+            at = self._attn_terms()
+            call("mssvt_compress_attention_tc", 64, a.num_heads[0], n1, at, a.scale,
                  host_floats([vs[i] * self.win1_size[i] for i in range(3)]),
                  host_floats(sp_tensor.point_cloud_range[0:3]), ptr(self.pos_proj[0].weight),
-                 ptr(self.pos_proj[0].bias), ptr(self._packed(self.pos_proj[2].weight)), ptr(self.pos_proj[2].bias),
-                 ptr(self._packed(a.to_qs[0].weight)), ptr(a.to_qs[0].bias), ptr(self._packed(a.to_kvs[0].weight)),
+                 ptr(self.pos_proj[0].bias), ptr(self._packed(self.pos_proj[2].weight, terms=at)), ptr(self.pos_proj[2].bias),
+                 ptr(self._packed(a.to_qs[0].weight, terms=at)), ptr(a.to_qs[0].bias), ptr(self._packed(a.to_kvs[0].weight, terms=at)),
                  ptr(a.to_kvs[0].bias),
-                 ptr(self._packed(a.projs[0].weight)), ptr(a.projs[0].bias), cap, ptr(total), ptr(win_list), ptr(xn),
+                 ptr(self._packed(a.projs[0].weight, terms=at)), ptr(a.projs[0].bias), cap, ptr(total), ptr(win_list), ptr(xn),
                  ptr(sp_tensor.world_coords()), ptr(k_row), *(ptr(v) for v in plan), ptr(scratch), ptr(attn), stream())
         else:
             S, buf = self._attn_descriptor(sp_tensor, 1, n1, n1)
@@ -748,14 +761,17 @@ class MixedScaleSparseTransformer(nn.Module):
         self.num_point_features = model_cfg.NUM_OUTPUT_FEATURES
         self.set_precision(model_cfg.get('PRECISION', 'tf32x3'))
 
-    PRECISIONS = ("fp32", "tf32", "tf32x3")
+    PRECISIONS = ("fp32", "tf32", "tf32x3", "bf16")
 
     def set_precision(self, precision):
         """'tf32x3' (default): every projection and the FFN on the tcgen05 tensor cores with split operands
-        (3xTF32): fp32-grade results (within 1e-4 of the fp32 reference, measured 1.5e-6) at three MMAs per K
-        step.  'tf32': the same kernels with plain TF32 operands (within 2e-3, measured 6.7e-4), fastest.
-        'fp32': FFMA kernels, no tensor cores (within 1e-4, measured 6e-7).  Shapes the tensor-core kernels do
-        not cover run on the FFMA kernels in every mode."""
+        (3xTF32): fp32-grade results (within 1e-4 of the fp32 reference, measured 1.6e-6) at three MMAs per K
+        step.  'tf32': the same kernels with plain TF32 operands (within 2e-3, measured 1.1e-3).  'bf16': bf16
+        operands (tcgen05.mma.kind::f16, fp32 accumulate) for the FFN GEMMs and the K | V | Q / output projections
+        of the mixed-scale blocks (within 2e-2, rms within 5e-3); the positional embedding stays 3xTF32, the
+        compress block's attention TF32, everything outside the GEMMs fp32.  'fp32': FFMA kernels, no tensor
+        cores (within 1e-4, measured 6e-7).  Shapes the tensor-core kernels do not cover run on the FFMA kernels
+        in every mode."""
         if precision not in self.PRECISIONS:
             raise ValueError("precision must be one of %s" % (self.PRECISIONS,))
         self.precision = precision
