@@ -129,6 +129,7 @@ def test_full_size_frame_properties_150k():
 
 
 TF32_TOL = 2e-3  # relative to max|reference|: FFN GEMMs with TF32 operands on tcgen05, fp32 accumulate
+BF16_TOL, BF16_RMS = 2e-2, 5e-3  # bf16 operands (tcgen05.mma.kind::f16), fp32 accumulate
 
 
 @pytest.mark.parametrize("n_rows,mode", [(1000, 1), (128, 0), (37, 1), (5000, 0)])
@@ -325,7 +326,7 @@ def test_tiny_frames_in_every_mode(n):
     with torch.no_grad():
         want = orc.backbone_forward(state, cfg, list(S0_GRID), list(S0_VOXEL), list(S0_RANGE), feats, coords, 1)
     model = model.cuda().eval()
-    for precision, tol in (("fp32", FEATURE_TOL), ("tf32x3", FEATURE_TOL), ("tf32", TF32_TOL)):
+    for precision, tol in (("fp32", FEATURE_TOL), ("tf32x3", FEATURE_TOL), ("tf32", TF32_TOL), ("bf16", BF16_TOL)):
         model.set_precision(precision)
         with torch.no_grad():
             sp = model({"voxel_features": feats.cuda(), "voxel_coords": coords.cuda().float(),
@@ -395,3 +396,27 @@ def test_backbone_tf32x3_mode_meets_the_fp32_tolerance(name):
     e3 = (outs["tf32x3"] - outs["fp32"]).abs().max().item() / scale
     e1 = (outs["tf32"] - outs["fp32"]).abs().max().item() / scale
     assert e3 <= 2e-5 and e3 < 0.1 * e1, (e3, e1)
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_backbone_bf16_mode_within_stated_tolerance(name):
+    """bf16 mode against the reference golden vectors: indices bit-exact, features within 2e-2 of max|ref| with
+    rms <= 5e-3; the mode really runs other arithmetic than tf32 (results differ)"""
+    blob, cfg, state = load_golden(name)
+    cfg["PRECISION"] = "bf16"
+    feats, coords = torch.from_numpy(blob["voxel_features"]), torch.from_numpy(blob["voxel_coords"])
+    model, sp = run_product(cfg, state, blob["grid"], blob["pc_range"], feats, coords, int(blob["batch_size"]))
+    assert model.backbone[0].precision == "bf16" and model.backbone[0]._terms() == 0
+    assert torch.equal(sp.indices.cpu(), torch.from_numpy(blob["out_indices"]))
+    ref = torch.from_numpy(blob["out_features"])
+    got = sp.features.cpu()
+    scale = ref.abs().max().item()
+    err = (got - ref).abs().max().item()
+    rms = (got - ref).pow(2).mean().sqrt().item()
+    assert err <= BF16_TOL * scale and rms <= BF16_RMS * scale, (err / scale, rms / scale)
+    model.set_precision("tf32")
+    with torch.no_grad():
+        other = model({"voxel_features": feats.cuda(), "voxel_coords": coords.cuda().float(),
+                       "batch_size": int(blob["batch_size"])})["encoded_spconv_tensor"].features.cpu()
+    assert (other - ref).abs().max().item() < err      # TF32 is closer to the fp32 reference than bf16
+    print("bf16 %s: max %.2e rms %.2e of max|ref|" % (name, err / scale, rms / scale))
