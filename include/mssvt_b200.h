@@ -87,6 +87,15 @@ int mssvt_window_partition(int x_wgs, int y_wgs, int z_wgs, int x_ws, int y_ws, 
                            int *win_count, void *workspace, long long workspace_bytes,
                            void *stream);
 
+/* The window LIST of mssvt_window_partition without the window hash table: what the fused path needs (it finds
+ * voxels through the grid index, mssvt_grid_index_build).  Numbering through a dense first-voxel array over the
+ * window grid: same rows in the same first-occurrence order, same win_count layout.  The reference-contract
+ * table is produced by mssvt_window_partition (operator API) or, from a list, by mssvt_build_hash_table. */
+long long mssvt_window_list_workspace_bytes(int x_wgs, int y_wgs, int z_wgs, int batch_size, int num_voxels);
+int mssvt_window_list(int x_wgs, int y_wgs, int z_wgs, int x_ws, int y_ws, int z_ws, int num_voxels, int max_wins,
+                      int batch_size, int list_capacity, const int *v_indices, int *win_list, int *win_count,
+                      void *workspace, long long workspace_bytes, void *stream);
+
 /* gather_two_window_voxels_with_hash_wrapper (ms_sparse_attention.cpp:61-120; kernel
  * ..._gpu.cu:193-381).  Same argument order as the reference wrapper; ind_* (W, max_*) padded
  * with -1, coord_* (W, max_*, 3) padded with 0, all written in full by this call. */

@@ -25,6 +25,8 @@ _SIGNATURES = {
     "mssvt_hash_lookup": [I, I, P, P, P, P, P],
     "mssvt_window_partition_workspace_bytes": [I],
     "mssvt_window_partition": [I] * 11 + [P, P, P, P, P, L, P],
+    "mssvt_window_list_workspace_bytes": [I] * 5,
+    "mssvt_window_list": [I] * 10 + [P, P, P, P, L, P],
     "mssvt_gather_two_window": [I] * 16 + [P] * 14 + [P],
     "mssvt_gather_one_window": [I] * 10 + [P] * 5 + [P],
     "mssvt_group_features": [I, I, I, I, P, P, P, P, P, P],
@@ -62,10 +64,10 @@ _SIGNATURES = {
     "mssvt_version": [],
     "mssvt_launch_count": [],
 }
-_RESTYPES = {"mssvt_window_partition_workspace_bytes": L, "mssvt_grid_index_words": L, "mssvt_version": ctypes.c_char_p,
+_RESTYPES = {"mssvt_window_partition_workspace_bytes": L, "mssvt_window_list_workspace_bytes": L, "mssvt_grid_index_words": L, "mssvt_version": ctypes.c_char_p,
              "mssvt_vfe_bitmap_words": L,
              "mssvt_launch_count": L}
-_NO_STATUS = {"mssvt_window_partition_workspace_bytes", "mssvt_grid_index_words", "mssvt_vfe_bitmap_words", "mssvt_fps_log2_block", "mssvt_version",
+_NO_STATUS = {"mssvt_window_partition_workspace_bytes", "mssvt_window_list_workspace_bytes", "mssvt_grid_index_words", "mssvt_vfe_bitmap_words", "mssvt_fps_log2_block", "mssvt_version",
               "mssvt_sizeof_attn_shape", "mssvt_sizeof_ffn_shape", "mssvt_last_cuda_error",
               "mssvt_launch_count"}
 _ERRORS = {-1: "invalid argument", -2: "CUDA launch/runtime error", -3: "workspace too small"}

@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(WIN_BLOCK)
 k_win_emit(int x_ws, int y_ws, int z_ws, int num_voxels, int hash_size, int batch_size,
            int max_wins, int list_capacity, const int4 *__restrict__ v_indices,
            int *__restrict__ table, const int *__restrict__ slot_of,
-           const int *__restrict__ block_counts, const int *__restrict__ win_count,
+           const int *__restrict__ block_counts, int *win_count,
            int4 *__restrict__ win_list, int *__restrict__ overflow) {
     __shared__ int s_warp[WIN_BLOCK / 32];
     __shared__ int s_base;
@@ -346,6 +346,13 @@ k_win_emit(int x_ws, int y_ws, int z_ws, int num_voxels, int hash_size, int batc
     int base = s_base;
     __syncthreads();
 
+    // win_count[B] (all openers, written by k_win_count and read by nobody in this kernel) becomes the number of
+    // rows actually in the list, so that every consumer's loop bound is the kept count
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        int kept = 0;
+        for (int i = 0; i < batch_size; ++i) kept += min(win_count[i], max_wins);
+        win_count[batch_size] = min(kept, list_capacity);
+    }
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     int slot = t < num_voxels ? slot_of[t] : -1;
     int opens = slot >= 0;
@@ -374,13 +381,106 @@ k_win_emit(int x_ws, int y_ws, int z_ws, int num_voxels, int hash_size, int batc
     table[((size_t)c.x * hash_size + slot) * 2 + 1] = local;
 }
 
-// win_count[B] (all openers, written by k_win_count) -> number of rows actually in the list, so that every
-// consumer's loop bound is the kept count; the per-sample entries keep the raw counts.
-__global__ void k_win_clamp_total(int batch_size, int max_wins, int list_capacity, int *__restrict__ win_count) {
-    if (threadIdx.x || blockIdx.x) return;
-    int kept = 0;
-    for (int i = 0; i < batch_size; ++i) kept += min(win_count[i], max_wins);
-    win_count[batch_size] = min(kept, list_capacity);
+// ------------------------------------------------------------------------------- window partition, dense form
+//
+// The fused path needs the window LIST only (voxels are found through the grid index, not through the window
+// hash), so it numbers the windows through a dense array over the window grid: first[b][cell] = lowest voxel
+// index that falls into the window (atomicMin), a voxel opens its window iff it is that voxel, openers are
+// ranked in voxel order (same first-occurrence numbering as the hash form, bit-identical lists).  No probing,
+// no (B, H, 2) table to fill: 1 MB instead of 3.2 MB of initialisation for the S0 grid.
+
+__device__ __forceinline__ long long wd_cell(int4 c, int x_wgs, int y_wgs, int z_wgs, int x_ws, int y_ws, int z_ws) {
+    const int wz = c.y / z_ws, wy = c.z / y_ws, wx = c.w / x_ws;
+    if (c.y < 0 || c.z < 0 || c.w < 0 || wx >= x_wgs || wy >= y_wgs || wz >= z_wgs) return -1;
+    return ((long long)c.x * x_wgs + wx) * y_wgs * z_wgs + (long long)wy * z_wgs + wz;
+}
+
+__global__ void k_wd_first(int x_wgs, int y_wgs, int z_wgs, int x_ws, int y_ws, int z_ws, int num_voxels,
+                           const int4 *__restrict__ v_indices, int *__restrict__ first) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= num_voxels) return;
+    const long long cell = wd_cell(__ldg(v_indices + t), x_wgs, y_wgs, z_wgs, x_ws, y_ws, z_ws);
+    if (cell >= 0) atomicMin(first + cell, t);
+}
+
+// openers per block and per sample (opens[t] kept as a flag byte for the emit pass)
+__global__ void __launch_bounds__(WIN_BLOCK)
+k_wd_count(int x_wgs, int y_wgs, int z_wgs, int x_ws, int y_ws, int z_ws, int num_voxels, int batch_size,
+           const int4 *__restrict__ v_indices, const int *__restrict__ first, unsigned char *__restrict__ opens_flag,
+           int *__restrict__ block_counts, int *__restrict__ win_count) {
+    __shared__ int s_total;
+    if (threadIdx.x == 0) s_total = 0;
+    __syncthreads();
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int opens = 0, b = -1;
+    if (t < num_voxels) {
+        const int4 c = __ldg(v_indices + t);
+        const long long cell = wd_cell(c, x_wgs, y_wgs, z_wgs, x_ws, y_ws, z_ws);
+        b = c.x;
+        opens = cell >= 0 && first[cell] == t;
+        opens_flag[t] = (unsigned char)opens;
+    }
+    const unsigned ball = __ballot_sync(0xffffffffu, opens);
+    if ((threadIdx.x & 31) == 0 && ball) atomicAdd(&s_total, __popc(ball));
+    if (opens) {
+        const unsigned peers = __match_any_sync(__activemask(), b);
+        if ((peers & lanemask_lt()) == 0) atomicAdd(win_count + b, __popc(peers));
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        block_counts[blockIdx.x] = s_total;
+        if (s_total) atomicAdd(win_count + batch_size, s_total);
+    }
+}
+
+__global__ void __launch_bounds__(WIN_BLOCK)
+k_wd_emit(int x_ws, int y_ws, int z_ws, int num_voxels, int batch_size, int max_wins, int list_capacity,
+          const int4 *__restrict__ v_indices, const unsigned char *__restrict__ opens_flag,
+          const int *__restrict__ block_counts, int *win_count, int4 *__restrict__ win_list,
+          int *__restrict__ overflow) {
+    __shared__ int s_warp[WIN_BLOCK / 32];
+    __shared__ int s_base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int part = 0;
+    for (int i = threadIdx.x; i < blockIdx.x; i += blockDim.x) part += block_counts[i];
+    part = __reduce_add_sync(0xffffffffu, part);
+    if (lane == 0) s_warp[warp] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int sum = 0;
+        for (int i = 0; i < WIN_BLOCK / 32; ++i) sum += s_warp[i];
+        s_base = sum;
+    }
+    __syncthreads();
+    const int base = s_base;
+    __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x == 0) {   // (see k_win_emit: the list length every consumer uses)
+        int kept = 0;
+        for (int i = 0; i < batch_size; ++i) kept += min(win_count[i], max_wins);
+        win_count[batch_size] = min(kept, list_capacity);
+    }
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int opens = t < num_voxels ? opens_flag[t] : 0;
+    const unsigned ball = __ballot_sync(0xffffffffu, opens);
+    if (lane == 0) s_warp[warp] = __popc(ball);
+    __syncthreads();
+    int before = 0;
+    for (int i = 0; i < warp; ++i) before += s_warp[i];
+    if (!opens) return;
+    const int rank = base + before + __popc(ball & lanemask_lt());
+    const int4 c = __ldg(v_indices + t);
+    int first_row = 0, first_kept = 0;
+    for (int i = 0; i < c.x; ++i) {
+        const int n = win_count[i];
+        first_row += n;
+        first_kept += min(n, max_wins);
+    }
+    const int local = rank - first_row, row = first_kept + local;
+    if (local >= max_wins || row >= list_capacity) {
+        atomicAdd(overflow, 1);
+        return;
+    }
+    win_list[row] = make_int4(c.x, c.y / z_ws, c.z / y_ws, c.w / x_ws);
 }
 
 }  // namespace mssvt
@@ -388,6 +488,48 @@ __global__ void k_win_clamp_total(int batch_size, int max_wins, int list_capacit
 using namespace mssvt;
 
 extern "C" {
+
+long long mssvt_window_list_workspace_bytes(int x_wgs, int y_wgs, int z_wgs, int batch_size, int num_voxels) {
+    const long long cells = (long long)batch_size * x_wgs * y_wgs * z_wgs;
+    const long long blocks = (num_voxels + WIN_BLOCK - 1) / WIN_BLOCK;
+    return (cells + blocks + 8) * 4 + ((long long)num_voxels + 15) / 16 * 16;
+}
+
+/* The window LIST of mssvt_window_partition without the window hash table (what the fused path needs: it
+ * finds voxels through the grid index).  Same rows in the same first-occurrence order, same win_count layout
+ * (per-sample counts, [B] rows in the list, [B + 1] windows dropped).  workspace:
+ * mssvt_window_list_workspace_bytes(...) bytes. */
+int mssvt_window_list(int x_wgs, int y_wgs, int z_wgs, int x_ws, int y_ws, int z_ws, int num_voxels, int max_wins,
+                      int batch_size, int list_capacity, const int *v_indices, int *win_list, int *win_count,
+                      void *workspace, long long workspace_bytes, void *stream) {
+    if (!win_count || batch_size <= 0 || num_voxels < 0 || x_ws <= 0 || y_ws <= 0 || z_ws <= 0 || x_wgs <= 0 ||
+        y_wgs <= 0 || z_wgs <= 0)
+        return MSSVT_ERR_INVALID;
+    if (workspace_bytes < mssvt_window_list_workspace_bytes(x_wgs, y_wgs, z_wgs, batch_size, num_voxels))
+        return MSSVT_ERR_WORKSPACE;
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = fill_i32(win_count, batch_size + 2, 0, s);
+    if (rc || num_voxels == 0) return rc;
+    if (!v_indices || !win_list || !workspace) return MSSVT_ERR_INVALID;
+    const long long cells = (long long)batch_size * x_wgs * y_wgs * z_wgs;
+    const int blocks = div_up(num_voxels, WIN_BLOCK);
+    int *first = (int *)workspace;
+    int *block_counts = first + cells;
+    unsigned char *opens_flag = (unsigned char *)(block_counts + blocks + 8);
+    cudaError_t e = cudaMemsetAsync(first, 0x7f, (size_t)cells * 4, s);   // 0x7f7f7f7f: above every voxel index
+    if (e != cudaSuccess) { g_last_cuda_error = (int)e; return MSSVT_ERR_LAUNCH; }
+    ++g_launches;
+    k_wd_first<<<div_up(num_voxels, 256), 256, 0, s>>>(x_wgs, y_wgs, z_wgs, x_ws, y_ws, z_ws, num_voxels,
+                                                       (const int4 *)v_indices, first);
+    ++g_launches;
+    k_wd_count<<<blocks, WIN_BLOCK, 0, s>>>(x_wgs, y_wgs, z_wgs, x_ws, y_ws, z_ws, num_voxels, batch_size,
+                                            (const int4 *)v_indices, first, opens_flag, block_counts, win_count);
+    ++g_launches;
+    k_wd_emit<<<blocks, WIN_BLOCK, 0, s>>>(x_ws, y_ws, z_ws, num_voxels, batch_size, max_wins, list_capacity,
+                                           (const int4 *)v_indices, opens_flag, block_counts, win_count,
+                                           (int4 *)win_list, win_count + batch_size + 1);
+    return check_launch();
+}
 
 int mssvt_last_cuda_error(void) { return g_last_cuda_error; }
 long long mssvt_launch_count(void) { return g_launches; }
@@ -539,8 +681,6 @@ int mssvt_window_partition(int x_wgs, int y_wgs, int z_wgs, int x_ws, int y_ws, 
                                             max_wins, list_capacity, (const int4 *)v_indices, table,
                                             slot_of, block_counts, win_count, (int4 *)win_list,
                                             win_count + batch_size + 1);
-    ++g_launches;
-    k_win_clamp_total<<<1, 32, 0, s>>>(batch_size, max_wins, list_capacity, win_count);
     return check_launch();
 }
 

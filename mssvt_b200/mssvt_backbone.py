@@ -279,10 +279,11 @@ class MixedScaleSparseTransformerBlock(nn.Module):
         key = ("win", tuple(self.win1_size), self.max_num_wins)
         if key not in cache:
             grid = [sp_tensor.spatial_shape[i] // self.win1_size[i] for i in range(3)]
-            win_list, table, win_count = mssvt_ops.window_partition_device(
-                self.win1_size, self.max_num_wins, sp_tensor.batch_size, sp_tensor.hash_size, grid,
-                sp_tensor.indices)
-            cache[key] = (grid, win_list, table, win_count)
+            # the list only: the fused kernels find voxels through the grid index, the reference's window hash is
+            # not needed here (SparseTensor.map_table builds the contract table lazily when somebody asks)
+            win_list, win_count = mssvt_ops.window_list_device(
+                self.win1_size, self.max_num_wins, sp_tensor.batch_size, grid, sp_tensor.indices)
+            cache[key] = (grid, win_list, None, win_count)
         return cache[key]
 
     def geometry(self, sp_tensor, taps=False):
@@ -360,7 +361,8 @@ class MixedScaleSparseTransformerBlock(nn.Module):
         scan_ws = torch.empty((cap + 1 + 1023) // 1024 + 1, **i32)
         call("mssvt_exclusive_scan", cap, ptr(g["total"]), ptr(g["meta"]), 4, ptr(g["q_base"]), ptr(scan_ws),
              stream())
-        call("mssvt_query_src", cap, ptr(g["total"]), nq, ptr(g["meta"]), ptr(g["q_base"]), ptr(g["q_src"]), stream())
+        if not interp or not self._tc_supported(nq):     # (only the merge kernel without interpolation reads it)
+            call("mssvt_query_src", cap, ptr(g["total"]), nq, ptr(g["meta"]), ptr(g["q_base"]), ptr(g["q_src"]), stream())
         cache[key] = g
         return g
 
@@ -621,7 +623,7 @@ class MixedScaleSparseTransformerCompressBlock(MixedScaleSparseTransformerBlock)
         sp_tensor.spatial_shape = grid
         sp_tensor.voxel_size = [vs[i] * self.win1_size[i] for i in range(3)]
         sp_tensor.gather_dict = None
-        sp_tensor.map_table = win_table
+        sp_tensor.map_table = None     # (built lazily from the new indices: SparseTensor.map_table)
         return sp_tensor
 
     def _attn_terms(self):
@@ -710,7 +712,7 @@ class MixedScaleSparseTransformerCompressBlock(MixedScaleSparseTransformerBlock)
         sp_tensor.spatial_shape = grid
         sp_tensor.voxel_size = [vs[i] * self.win1_size[i] for i in range(3)]
         sp_tensor.gather_dict = None
-        sp_tensor.map_table = win_table
+        sp_tensor.map_table = None     # (built from the new indices on first access: SparseTensor.map_table)
         sp_tensor.note_window_overflow(win_count[B + 1:B + 2])
         sp_tensor._taps = {"k_row": k_row, "attn": attn}
         return sp_tensor

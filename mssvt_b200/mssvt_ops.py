@@ -72,6 +72,24 @@ def window_partition_device(win_size, max_num_wins, batch_size, hash_size, spati
     return win_list, table, win_count
 
 
+def window_list_device(win_size, max_num_wins, batch_size, spatial_shape, voxel_indices, capacity=None):
+    """The window list of window_partition_device WITHOUT the window hash table (the fused backbone finds voxels
+    through its grid index): (win_list (capacity, 4), win_count (B + 2)) on the device, same rows, same order."""
+    x_ws, y_ws, z_ws = (int(v) for v in win_size)
+    x_wgs, y_wgs, z_wgs = (int(v) for v in spatial_shape)
+    voxel_indices = _i32(voxel_indices)
+    n, dev = voxel_indices.shape[0], voxel_indices.device
+    if capacity is None:
+        capacity = min(n, batch_size * max_num_wins)
+    win_list = torch.empty((max(capacity, 1), 4), dtype=torch.int32, device=dev)
+    win_count = torch.empty(batch_size + 2, dtype=torch.int32, device=dev)
+    ws_bytes = call("mssvt_window_list_workspace_bytes", x_wgs, y_wgs, z_wgs, batch_size, n)
+    workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    call("mssvt_window_list", x_wgs, y_wgs, z_wgs, x_ws, y_ws, z_ws, n, max_num_wins, batch_size, capacity,
+         ptr(voxel_indices), ptr(win_list), ptr(win_count), ptr(workspace), ws_bytes, stream())
+    return win_list, win_count
+
+
 class WindowPartition(Function):
     """mssvt_ops.py:29-60.  Rows are ordered by first occurrence in voxel order (one legal
     outcome of the reference's atomicAdd numbering, and the same on every run)."""

@@ -151,3 +151,34 @@ def test_graph_replay_follows_in_place_weight_updates():
         lin.weight = torch.nn.Parameter(lin.weight.clone())
     with pytest.raises(RuntimeError, match="storage"):
         graphed.replay()
+
+
+@pytest.mark.parametrize("win,batch", [([3, 3, 3], 2), ([1, 1, 32], 3), ([2, 2, 4], 1)])
+def test_hash_free_window_list_equals_window_partition(win, batch):
+    """mssvt_window_list (dense first-voxel array, what the fused path uses) gives the rows of
+    mssvt_window_partition (window hash of the reference contract) in the same order, also when windows are dropped;
+    and the output tensor's lazily built map_table answers window lookups like the partition's table"""
+    from mssvt_b200 import mssvt_ops
+    _, coords = synth_frame(7, 5000, batch_size=batch, crop=0.25)
+    c = torch.from_numpy(coords).cuda()
+    grid = [S0_GRID[i] // win[i] for i in range(3)]
+    for max_wins in (90000, 300):
+        a_list, table, a_cnt = mssvt_ops.window_partition_device(win, max_wins, batch, 400000, grid, c)
+        b_list, b_cnt = mssvt_ops.window_list_device(win, max_wins, batch, grid, c)
+        assert torch.equal(a_cnt, b_cnt)
+        n = int(a_cnt[batch])
+        assert n > 0 and torch.equal(a_list[:n], b_list[:n])
+    # lazily built contract table of a compress block's output == the table the partition kernel fills
+    cfg = s0_model_cfg()
+    model, _ = build(cfg)
+    model = model.cuda().eval()
+    feats = torch.randn(c.shape[0], 64, device="cuda")
+    with torch.no_grad():
+        sp = model({"voxel_features": feats, "voxel_coords": c.float(), "batch_size": batch})["encoded_spconv_tensor"]
+    pillars, table, cnt = mssvt_ops.window_partition_device([1, 1, 32], 90000, batch, 400000, [468, 468, 1], c)
+    n = int(cnt[batch])
+    assert torch.equal(sp.indices, pillars[:n])
+    keys = (sp.indices[:, 3] * 468 + sp.indices[:, 2]).int()        # x * Y * Z + y * Z + z on the (468, 468, 1) grid
+    got = mssvt_ops.hash_lookup(sp.map_table, sp.indices[:, 0].contiguous(), keys)
+    want = mssvt_ops.hash_lookup(table, sp.indices[:, 0].contiguous(), keys)
+    assert torch.equal(got, want) and int(got.min()) >= 0
