@@ -163,45 +163,71 @@ k_ffn_tc(FfnTcParams P, int n_cap, const int *__restrict__ n_dev, const float *_
 #ifdef MSSVT_TRACE
     long long tr[12] = {0};
 #endif
-    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, phase ^= 1u) {
-        TRACE(0);
+    // ---- the load phase of a tile: this thread's half of the residual row u (registers).  Global rows move
+    //      through a warp-private staging area so that every load / store instruction of a warp covers whole
+    //      128-byte lines (RPI rows x CH floats), not 32 rows.  Called one tile AHEAD (software pipelining): the
+    //      loads of tile i + 1 are issued while the second GEMM of tile i runs, so that the memory system and
+    //      the tensor pipe work at the same time even with a single CTA on the SM (3xTF32).
+    // mode 2, the index half of the chain: the voxel's win1 slot names its 3 nearest query slots -> pointers to
+    // their projected rows + blend weights.  The chain slot -> window record -> rows is three dependent global
+    // accesses; its links are issued in three STAGES spread over the phases of the previous tile (volatile loads:
+    // they stay where they are written), each consumed a phase later, so that no warp ever waits for them:
+    //     stage 0 (top of tile i)          vox_slot of the row in tile i + 1
+    //     stage 1 (first GEMM issued)      #real queries, first query id, nn indices / weights of that slot
+    //     stage 2 (second GEMM issued)     pointers -> load_tile gathers the rows
+    struct MergeIdx { const float *p0, *p1, *p2; float w0, w1, w2; bool cov; int slot, nqr, q0; unsigned nn; };
+    auto ldg_v = [](const int *p) { int v; asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p)); return v; };
+    auto ldg_vf = [](const float *p) { float v; asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p)); return v; };
+    auto ldg_vb = [](const unsigned char *p) { unsigned v; asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(p)); return v; };
+    auto index_stage0 = [&](int tile, MergeIdx &ix) {
+        ix.slot = -1;
+        if constexpr (C == 64) {
+            const int row = tile * TC_ROWS + r;
+            if (P.mode == 2 && row < n) ix.slot = ldg_v(P.vox_slot + row);
+        }
+    };
+    auto index_stage1 = [&](MergeIdx &ix) {
+        ix.nqr = ix.q0 = 0; ix.nn = 0u; ix.w0 = ix.w1 = ix.w2 = 0.f;
+        if constexpr (C == 64) {
+            asm volatile("" : "+r"(ix.slot));
+            if (ix.slot >= 0) {
+                const int w = ix.slot / P.cap1;
+                ix.nqr = ldg_v(P.meta + 4 * (size_t)w);
+                ix.q0 = ldg_v(P.q_base + w);
+                const unsigned char *ni = P.nn_idx + (size_t)ix.slot * 3;
+                ix.nn = ldg_vb(ni) | (ldg_vb(ni + 1) << 8) | (ldg_vb(ni + 2) << 16);
+                const float *nw = P.nn_w + (size_t)ix.slot * 3;
+                ix.w0 = ldg_vf(nw); ix.w1 = ldg_vf(nw + 1); ix.w2 = ldg_vf(nw + 2);
+            }
+        }
+    };
+    auto index_stage2 = [&](MergeIdx &ix) {
+        ix.p0 = ix.p1 = ix.p2 = nullptr;
+        ix.cov = ix.slot >= 0;
+        if constexpr (C == 64) {
+            asm volatile("" : "+r"(ix.nqr), "+r"(ix.q0), "+r"(ix.nn));
+            if (ix.cov) {
+                const int n0 = ix.nn & 0xff, n1 = (ix.nn >> 8) & 0xff, n2 = (ix.nn >> 16) & 0xff;
+                // padded query slots (index >= #real queries) are zero rows in the reference
+                if (n0 < ix.nqr) ix.p0 = P.pbuf + (size_t)(ix.q0 + n0) * 64 + half * 32;
+                if (n1 < ix.nqr) ix.p1 = P.pbuf + (size_t)(ix.q0 + n1) * 64 + half * 32;
+                if (n2 < ix.nqr) ix.p2 = P.pbuf + (size_t)(ix.q0 + n2) * 64 + half * 32;
+            }
+        }
+    };
+    auto load_tile = [&](int tile, const MergeIdx &ix, float *u) {
         const int row = tile * TC_ROWS + r;
         const bool live = row < n;
         tile_row0 = tile * TC_ROWS + (warp & 3) * 32;
-        {   // the next tile's rows: start them on their way from HBM to L2 now, a whole tile time ahead
-            const int nrow = row + (int)gridDim.x * TC_ROWS;
-            if (nrow < n) {
-                if (P.mode != 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(merged + (size_t)nrow * C + half * CH));
-                if (P.mode != 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(x + (size_t)nrow * C + half * CH));
-            }
-        }
-        // ---- 1. this thread's half of the residual row u (registers), LayerNorm, A operand.
-        //      Global rows move through a warp-private staging area so that every load / store
-        //      instruction of a warp covers whole 128-byte lines (RPI rows x CH floats), not 32 rows
-        float u[CH];
         {
             float4 mv[CH / 4];
-            bool cov = false;
+            bool cov = ix.cov;
             if constexpr (C == 64) {
                 if (P.mode == 2) {
-                    // the voxel's win1 slot names its 3 nearest query slots; their projected rows are fetched
-                    // warp-cooperatively and blended in the reference's order (same arithmetic as k_tca_merge)
-                    const float *p0 = nullptr, *p1 = nullptr, *p2 = nullptr;
-                    float w0 = 0.f, w1 = 0.f, w2 = 0.f;
-                    const int slot = live ? __ldg(P.vox_slot + row) : -1;
-                    if (slot >= 0) {
-                        cov = true;
-                        const int w = slot / P.cap1;
-                        const int nqr = __ldg(P.meta + 4 * (size_t)w), q0 = __ldg(P.q_base + w);
-                        const unsigned char *ni = P.nn_idx + (size_t)slot * 3;
-                        const float *nw = P.nn_w + (size_t)slot * 3;
-                        const int n0 = ni[0], n1 = ni[1], n2 = ni[2];
-                        // padded query slots (index >= #real queries) are zero rows in the reference
-                        if (n0 < nqr) p0 = P.pbuf + (size_t)(q0 + n0) * 64 + half * 32;
-                        if (n1 < nqr) p1 = P.pbuf + (size_t)(q0 + n1) * 64 + half * 32;
-                        if (n2 < nqr) p2 = P.pbuf + (size_t)(q0 + n2) * 64 + half * 32;
-                        w0 = __ldg(nw); w1 = __ldg(nw + 1); w2 = __ldg(nw + 2);
-                    }
+                    // the projected rows are fetched warp-cooperatively and blended in the reference's order (same
+                    // arithmetic as k_tca_merge)
+                    const float *p0 = ix.p0, *p1 = ix.p1, *p2 = ix.p2;
+                    const float w0 = ix.w0, w1 = ix.w1, w2 = ix.w2;
                     float4 v[8];
                     warp_rows_load(stg, (const float4 *)p0, mv);
 #pragma unroll
@@ -237,6 +263,41 @@ k_ffn_tc(FfnTcParams P, int n_cap, const int *__restrict__ n_dev, const float *_
                 }
             }
         }
+    };
+
+    // PIPE: the loads of tile i + 1 are software-pipelined under the GEMMs of tile i.  Pays with ONE CTA per SM
+    // (3xTF32: 90 -> 73 us per launch); with two CTAs per SM the other CTA already fills those gaps and the 64 extra
+    // live registers only cause spills, so the plain order is kept there.
+    constexpr bool PIPE = TERMS == 3;
+    float u[CH];
+    MergeIdx ix;
+    if (PIPE && (int)blockIdx.x < tiles) {
+        index_stage0(blockIdx.x, ix);
+        index_stage1(ix);
+        index_stage2(ix);
+        load_tile(blockIdx.x, ix, u);
+    }
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, phase ^= 1u) {
+        TRACE(0);
+        const int row = tile * TC_ROWS + r;
+        const bool live = row < n;
+        (void)live;
+        const int next_tile = PIPE ? tile + (int)gridDim.x : tiles;
+        if (!PIPE) {
+            index_stage0(tile, ix);
+            index_stage1(ix);
+            index_stage2(ix);
+            load_tile(tile, ix, u);
+        }
+        if (next_tile < tiles) index_stage0(next_tile, ix);
+        {   // rows two tiles ahead: start them on their way from HBM to L2 now
+            const int nrow = row + 2 * (int)gridDim.x * TC_ROWS;
+            if (nrow < n) {
+                if (P.mode != 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(merged + (size_t)nrow * C + half * CH));
+                if (P.mode != 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(x + (size_t)nrow * C + half * CH));
+            }
+        }
+        // ---- 1. LayerNorm of u, A operand
         float part = 0.f;
 #pragma unroll
         for (int c = 0; c < CH; ++c) part += u[c];
@@ -295,6 +356,7 @@ k_ffn_tc(FfnTcParams P, int n_cap, const int *__restrict__ n_dev, const float *_
             }
             umma_commit(bar1);
         }
+        if (next_tile < tiles) index_stage1(ix);
         TRACE(3);
         mbar_wait(bar1, phase);
         TRACE(4);
@@ -350,6 +412,14 @@ k_ffn_tc(FfnTcParams P, int n_cap, const int *__restrict__ n_dev, const float *_
             umma_commit(bar2);
         }
         TRACE(7);
+        // ---- software pipeline: the next tile's loads run while the second GEMM does (the A tile, which hosts the
+        //      staging areas, is free again: the first GEMM is complete, the second reads its A operand from TMEM)
+        float un[PIPE ? CH : 1];
+        if (PIPE && next_tile < tiles) {
+            index_stage2(ix);
+            load_tile(next_tile, ix, un);
+        }
+        tile_row0 = tile * TC_ROWS + (warp & 3) * 32;      // (back to this tile for the stores below)
         mbar_wait(bar2, phase);
         TRACE(8);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -398,6 +468,10 @@ k_ffn_tc(FfnTcParams P, int n_cap, const int *__restrict__ n_dev, const float *_
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();  // TMEM and the operand tiles are free for the next tile
         TRACE(10);
+        if (PIPE && next_tile < tiles) {
+#pragma unroll
+            for (int c = 0; c < (PIPE ? CH : 1); ++c) u[c] = un[c];
+        }
     }
 #ifdef MSSVT_TRACE
     if (tid == 0 && blockIdx.x == 0 && tr[10])
