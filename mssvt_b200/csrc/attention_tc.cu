@@ -435,6 +435,7 @@ k_tca_tile(TcAttnParams P, int win_cap, const int2 *__restrict__ tiles, const in
         // while the MMA runs: role and feature row id of this thread in the NEXT tile
         int n_kind = 0, n_l = 0, n_row = 0;
         if (more) role(tl_next, (const int4 *)(sHdr + (buf ^ 1) * (TCA_TW * 32)), n_kind, n_l, n_row);
+        KTRACE(11);
         mbar_wait(bar, phase);
         phase ^= 1u;
         tc_fence_after();
@@ -584,6 +585,7 @@ k_tca_tile(TcAttnParams P, int win_cap, const int2 *__restrict__ tiles, const in
             if (n_kind) { nx = __ldg(xyz + 3 * (size_t)n_row); ny = __ldg(xyz + 3 * (size_t)n_row + 1); nz = __ldg(xyz + 3 * (size_t)n_row + 2); }
             warp_rows_copy_async(stg, n_kind ? (const float4 *)(xn + (size_t)n_row * TCA_C + g * TCA_SD) : nullptr);
         }
+        KTRACE(12);
         mbar_wait(bar, phase);
         phase ^= 1u;
         tc_fence_after();
@@ -608,8 +610,8 @@ k_tca_tile(TcAttnParams P, int win_cap, const int2 *__restrict__ tiles, const in
     }
 #ifdef MSSVT_TRACE
     if (tid == 0 && blockIdx.x == gridDim.x - 1 && tr[10])
-        printf("tile g%d: pos+sync %lld | rows in %lld | mma1 wait %lld | A1+sync %lld | roles(next)+mma2 %lld | unload+sync %lld | scores+sync %lld | softmax+AV+sync %lld | gather(next)+mma3 %lld | out+sync %lld | total %lld clk\n", g,
-               tr[1] - tr[0], tr[2] - tr[1], tr[3] - tr[2], tr[4] - tr[3], tr[5] - tr[4], tr[6] - tr[5], tr[7] - tr[6], tr[8] - tr[7], tr[9] - tr[8], tr[10] - tr[9], tr[10] - tr[0]);
+        printf("tile g%d: pos+sync %lld | rows in %lld | mma1 wait %lld | A1+sync %lld | mma2 issue + roles(next) %lld + wait %lld | unload+sync %lld | scores+sync %lld | softmax+AV+sync %lld | mma3 issue + gather(next) %lld + wait %lld | out+sync %lld | total %lld clk\n", g,
+               tr[1] - tr[0], tr[2] - tr[1], tr[3] - tr[2], tr[4] - tr[3], tr[11] - tr[4], tr[5] - tr[11], tr[6] - tr[5], tr[7] - tr[6], tr[8] - tr[7], tr[12] - tr[8], tr[9] - tr[12], tr[10] - tr[9], tr[10] - tr[0]);
 #endif
     stage_packed_wait();
     tc_fence_before();
