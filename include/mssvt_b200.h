@@ -238,7 +238,7 @@ int mssvt_block_attention(const void *shape, int shape_bytes, const float *param
 int mssvt_attention_tiles(int heads_per_group, int nq, int key_num_sample, int win_capacity,
                           const int *win_count_total, const int *win_list, const int *meta, const int *q_base,
                           const float *win_cell, const float *range_min, int *tiles, int *tile_count,
-                          int *win_rec, float *win_ctr, void *stream);
+                          int *win_rec, float *win_ctr, unsigned char *tile_rows, void *stream);
 
 /* The same step (mssvt_backbone.py:260-336 + mssvt_utils.py:88-157) as ONE tile kernel on the tcgen05 tensor
  * cores (mssvt_b200/csrc/attention_tc.cu): per tile of <= 128 rows (distinct keys + real queries of consecutive
@@ -249,7 +249,7 @@ int mssvt_attention_tiles(int heads_per_group, int nq, int key_num_sample, int w
  * packed with terms = 3; wkvq0 / wkvq1 = per head group the [96][32] matrix [Wk; Wv; scale * Wq]; wp0 / wp1 = the
  * group's [32][32] output projection (packed with `terms`); bq / bkv / bp: the nn.Linear biases.
  * rep_row / meta from mssvt_block_geometry; q_base = mssvt_exclusive_scan(meta[:, 0]) (win_capacity + 1 ints),
- * q_src = mssvt_query_src, vox_slot from the geometry; tiles / tile_count / win_rec / win_ctr =
+ * q_src = mssvt_query_src, vox_slot from the geometry; tiles / tile_count / win_rec / win_ctr / tile_rows =
  * mssvt_attention_tiles; scratch: 3 * num_voxels * 64 floats (projected query rows in the last third).
  * Supported: C = 64, two groups of 32 channels with 1, 2 or 4 heads each, nq <= 32,
  * key_num_sample <= 63, cap1 <= 128; -1 otherwise. */
@@ -262,7 +262,8 @@ int mssvt_block_attention_tc(int C, int heads_per_group, int nq, int key_num_sam
                              const int *rep_row, const int *meta, const int *q_base, const int *q_src,
                              const int *vox_slot, const unsigned char *nn_idx,
                              const float *nn_w, const int *tiles, const int *tile_count, const int *win_rec,
-                             const float *win_ctr, int num_voxels, float *scratch, float *merged, void *stream);
+                             const float *win_ctr, const unsigned char *tile_rows, int num_voxels, float *scratch,
+                             float *merged, void *stream);
 
 /* Attention of a one-window (compress) block (mssvt_backbone.py:361-383): out (cap, C). */
 int mssvt_compress_attention(const void *shape, int shape_bytes, const float *params,

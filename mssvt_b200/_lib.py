@@ -45,8 +45,8 @@ _SIGNATURES = {
     "mssvt_window_rows": [I] * 8 + [P, I, P, P, P, P, P, P, P],
     "mssvt_layernorm": [I, P, I, P, P, P, F, P, P],
     "mssvt_block_attention": [P, I, P, I] + [P] * 11 + [P],
-    "mssvt_attention_tiles": [I] * 4 + [P] * 10 + [P],
-    "mssvt_block_attention_tc": [I] * 7 + [F] + [P] * 11 + [I] + [P] * 15 + [I, P, P] + [P],
+    "mssvt_attention_tiles": [I] * 4 + [P] * 11 + [P],
+    "mssvt_block_attention_tc": [I] * 7 + [F] + [P] * 11 + [I] + [P] * 16 + [I, P, P] + [P],
     "mssvt_compress_attention": [P, I, P, I] + [P] * 6 + [P],
     "mssvt_compress_tiles": [I, I] + [P] * 9 + [P],
     "mssvt_compress_attention_tc": [I, I, I, I, F] + [P] * 12 + [I] + [P] * 11 + [P],

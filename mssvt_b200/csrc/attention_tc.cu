@@ -47,6 +47,7 @@ namespace mssvt {
 #define TCA_SBUD 2048    // score slots per tile: sum over its windows of #queries x #keys x heads
 #define TCA_QMAX 48      // queries per tile (rows of the output-projection operand)
 #define TCA_PLAN_WB 64   // windows planned by one warp
+#define TCA_HDR_BYTES (TCA_TW * 32 + TCA_THREADS)   // window records + centres + row table of one tile
 #define TCA_C 64
 #define TCA_SD 32
 
@@ -109,6 +110,41 @@ k_tca_plan(int heads, int win_cap, const int *__restrict__ win_count_total, cons
     if (lane == 0 && a > 0) tiles[(size_t)g * win_cap + atomicAdd(tile_count + g, 1)] = make_int2(ts, nw);
 }
 
+// Row table of every tile: byte t of a tile = window (within the tile, 6 bits) | kind << 6 (1 = distinct key,
+// 2 = real query, 0 = idle row).  One warp per tile, made once per frame geometry with the plan; the tile kernel
+// then finds the role of a row with one byte load instead of two binary searches over the window offsets
+// (every instruction on the critical path of a tile costs ~20 clocks at 16 warps per SM).
+__global__ void __launch_bounds__(256)
+k_tca_rows(int win_cap, const int2 *__restrict__ tiles, const int *__restrict__ tile_count,
+           const int4 *__restrict__ win_rec, unsigned char *__restrict__ tile_rows) {
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int g = 0; g < 2; ++g) {
+        const int T = min(win_cap, __ldg(tile_count + g));
+        for (int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < T; t += warps) {
+            const int2 tl = __ldg(tiles + (size_t)g * win_cap + t);
+            int4 rec = make_int4(0, 0, 0, 0);
+            if (lane < tl.y) rec = __ldg(win_rec + (size_t)g * win_cap + tl.x + lane);
+            const int last_z = __shfl_sync(0xffffffffu, rec.z, tl.y - 1), last_y = __shfl_sync(0xffffffffu, rec.y, tl.y - 1);
+            const int nT = (last_z & 0xff) + ((last_y >> 8) & 0xff);
+            unsigned char *out = tile_rows + ((size_t)g * win_cap + t) * TCA_THREADS;
+            unsigned mine[4] = {0u, 0u, 0u, 0u};       // this lane's 4 consecutive rows: 4 * lane ..
+            for (int l = 0; l < tl.y; ++l) {
+                const int y = __shfl_sync(0xffffffffu, rec.y, l), z = __shfl_sync(0xffffffffu, rec.z, l);
+                const int k0 = z & 0xff, k1 = k0 + ((y >> 8) & 0xff);               // key rows of window l
+                const int q0 = nT + ((z >> 8) & 0xff), q1 = q0 + (y & 0xff);         // query rows of window l
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int row = 4 * lane + i;
+                    if (row >= k0 && row < k1) mine[i] = (unsigned)l | 0x40u;
+                    if (row >= q0 && row < q1) mine[i] = (unsigned)l | 0x80u;
+                }
+            }
+            *(unsigned *)(out + 4 * lane) = mine[0] | (mine[1] << 8) | (mine[2] << 16) | (mine[3] << 24);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------- the tile kernel
 
 // shared-memory carve-up of k_tca_tile (bytes); NT = operand tiles per matrix: hi [, lo]
@@ -123,24 +159,14 @@ struct TcaSmem {
         ao = apos + 8192;                          // nt x [QMAX / 8][chunks][8][16 B]            6 KB each (TF32)
         rows = ao + nt * TCA_QMAX * TCA_SD * eb;   // gather staging, later V / Q rows [128][32]          16 KB
         hdr = rows + TCA_THREADS * TCA_SD * 4;     // (the MMA reads 128 rows of `ao`: it runs into `rows`)
-        misc = hdr + 2 * TCA_TW * 32;              // 2 x {window records [TW] int4, window centres [TW] float4}
-        total = misc + 128 * 4 + TCA_QMAX * 4 + 8 + 16 + 128;   // biases, sQwin, barrier
+        misc = hdr + 2 * TCA_HDR_BYTES;            // 2 x {window records [TW] int4, centres [TW] float4, row table [128]}
+        total = misc + 128 * 4 + 8 + 16 + 128;     // biases, barrier
     }
 };
 
 // window records of a tile: offsets of the key rows / query rows are packed in rec.z (see k_tca_plan)
 __device__ __forceinline__ int rec_koff(const int4 &r) { return r.z & 0xff; }
 __device__ __forceinline__ int rec_qoff(const int4 &r) { return (r.z >> 8) & 0xff; }
-// largest l in [0, n) whose offset (bits [shift, shift + 8) of rec.z) is <= v
-__device__ __forceinline__ int tile_window(const int4 *rec, int n, int shift, int v) {
-    int lo = 0, hi = n;
-    while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (((rec[mid].z >> shift) & 0xff) <= v) lo = mid; else hi = mid;
-    }
-    return lo;
-}
-
 __device__ __forceinline__ float ex2_fast(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -171,7 +197,8 @@ __device__ __forceinline__ void warp_rows_copy_async(char *stg, const float4 *my
 template <int HEADS, int TERMS>
 __global__ void __launch_bounds__(TCA_THREADS, TERMS == 3 ? 3 : 4)
 k_tca_tile(TcAttnParams P, int win_cap, const int2 *__restrict__ tiles, const int *__restrict__ tile_count,
-           const int4 *__restrict__ win_rec, const float4 *__restrict__ win_ctr, const float *__restrict__ xn,
+           const int4 *__restrict__ win_rec, const float4 *__restrict__ win_ctr,
+           const unsigned char *__restrict__ tile_rows, const float *__restrict__ xn,
            const float *__restrict__ xyz, const int *__restrict__ rep_row, const int *__restrict__ q_row,
            float *__restrict__ Pbuf) {
     constexpr int HD = TCA_SD / HEADS;
@@ -202,15 +229,15 @@ k_tca_tile(TcAttnParams P, int win_cap, const int2 *__restrict__ tiles, const in
     const int first = g ? b - c0b : c0b, stride = g ? G - G0 : G0, T = g ? T1 : T0;
     tiles += (size_t)g * win_cap;
     win_rec += (size_t)g * win_cap;
+    tile_rows += (size_t)g * win_cap * TCA_THREADS;
 
     const TcaSmem L(NT, EB);
     char *sWpos = smem_raw + L.wpos, *sWkvq = smem_raw + L.wkvq, *sWp = smem_raw + L.wp;
     char *sApos = smem_raw + L.apos, *sAO = smem_raw + L.ao, *sRows = smem_raw + L.rows;
     float *sS = (float *)sApos;                             // [SBUD] scores: window-major, [key][query][head]
-    char *sHdr = smem_raw + L.hdr;                          // 2 x {int4 rec[TW], float4 ctr[TW]}
+    char *sHdr = smem_raw + L.hdr;                          // 2 x {int4 rec[TW], float4 ctr[TW], uint8 rows[128]}
     float *sBias = (float *)(smem_raw + L.misc);            // [32] bq * scale, [32] bv, [32] bp (+ pad)
-    int *sQwin = (int *)(sBias + 128);                      // [QMAX] window of each query of the tile
-    uint64_t *sBar = (uint64_t *)(sQwin + TCA_QMAX);
+    uint64_t *sBar = (uint64_t *)(sBias + 128);
     uint32_t *sTmem = (uint32_t *)(sBar + 1);
     char *stg = sRows + warp * 4096;                        // this warp's staging area
 
@@ -247,33 +274,38 @@ k_tca_tile(TcAttnParams P, int win_cap, const int2 *__restrict__ tiles, const in
     const long long t_alloc = clock64();
 #endif
 
-    // header of a tile (window records + centres) -> buffer `buf`, asynchronously
-    auto header_async = [&](int2 tl, int buf) {
+    // header of tile number t (window records + centres + row table) -> buffer `buf`, asynchronously
+    auto header_async = [&](int t, int2 tl, int buf) {
+        const uint32_t d = smem_u32(sHdr + buf * TCA_HDR_BYTES);
         if (tid < tl.y) {
-            const uint32_t d = smem_u32(sHdr + buf * (TCA_TW * 32));
             asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d + (uint32_t)tid * 16u), "l"(win_rec + tl.x + tid) : "memory");
             asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d + (uint32_t)(TCA_TW * 16 + tid * 16)), "l"(win_ctr + tl.x + tid) : "memory");
+        } else if (tid >= TCA_THREADS - 8) {
+            const int c = tid - (TCA_THREADS - 8);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d + (uint32_t)(TCA_TW * 32 + c * 16)),
+                         "l"(tile_rows + (size_t)t * TCA_THREADS + c * 16) : "memory");
         }
     };
     // role of this thread's row in a tile whose header is in shared memory: kind 1 = distinct key of window l,
     // 2 = real query of window l, 0 = idle; -> global feature row (issued load)
-    auto role = [&](int2 tl, const int4 *rec, int &kind, int &l, int &row) {
-        const int4 last = rec[tl.y - 1];
-        const int nT = rec_koff(last) + ((last.y >> 8) & 0xff), nQ = rec_qoff(last) + (last.y & 0xff);
-        kind = tid < nT ? 1 : tid < nT + nQ ? 2 : 0;
-        l = 0; row = 0;
+    auto role = [&](int2 tl, const char *hdr, int &kind, int &l, int &row) {
+        const int4 *rec = (const int4 *)hdr;
+        const unsigned code = ((const unsigned char *)(hdr + TCA_TW * 32))[tid];
+        kind = (int)(code >> 6);
+        l = (int)(code & 63u);
+        row = 0;
         if (kind == 1) {
-            l = tile_window(rec, tl.y, 0, tid);
             row = __ldg(rep_row + (size_t)(tl.x + l) * 2 * K + g * K + (tid - rec_koff(rec[l])));
         } else if (kind == 2) {
-            l = tile_window(rec, tl.y, 8, tid - nT);
+            const int4 last = rec[tl.y - 1];
+            const int nT = rec_koff(last) + ((last.y >> 8) & 0xff);
             row = __ldg(q_row + (size_t)(tl.x + l) * nq + (tid - nT - rec_qoff(rec[l])));
         }
     };
 
     int2 tl = first < T ? __ldg(tiles + first) : make_int2(0, 0);
     int2 tl_next = first + stride < T ? __ldg(tiles + first + stride) : make_int2(0, 0);
-    if (first < T) header_async(tl, 0);
+    if (first < T) header_async(first, tl, 0);
     stage_packed_wait();
     tc_fence_before();
     __syncthreads();
@@ -298,7 +330,7 @@ k_tca_tile(TcAttnParams P, int win_cap, const int2 *__restrict__ tiles, const in
     int kind = 0, l = 0, row = 0;
     float px = 0.f, py = 0.f, pz = 0.f;
     if (first < T) {
-        role(tl, (const int4 *)sHdr, kind, l, row);
+        role(tl, sHdr, kind, l, row);
         if (kind) { px = __ldg(xyz + 3 * (size_t)row); py = __ldg(xyz + 3 * (size_t)row + 1); pz = __ldg(xyz + 3 * (size_t)row + 2); }
         warp_rows_copy_async(stg, kind ? (const float4 *)(xn + (size_t)row * TCA_C + g * TCA_SD) : nullptr);
     }
@@ -309,11 +341,12 @@ k_tca_tile(TcAttnParams P, int win_cap, const int2 *__restrict__ tiles, const in
     int buf = 0;
     for (int t = first; t < T; t += stride, buf ^= 1) {
         KTRACE(0);
-        const int4 *sRec = (const int4 *)(sHdr + buf * (TCA_TW * 32));
+        const int4 *sRec = (const int4 *)(sHdr + buf * TCA_HDR_BYTES);
+        const unsigned char *sRowTab = (const unsigned char *)(sHdr + buf * TCA_HDR_BYTES + TCA_TW * 32);
         const float4 *sCtr = (const float4 *)(sRec + TCA_TW);
         const int nwin = tl.y;
         const bool more = t + stride < T;
-        if (more) header_async(tl_next, buf ^ 1);            // the next tile's window records: on their way now
+        if (more) header_async(t + stride, tl_next, buf ^ 1);   // the next tile's window records: on their way now
         const int2 tl_after = t + 2 * stride < T ? __ldg(tiles + t + 2 * stride) : make_int2(0, 0);
         const int4 last = sRec[nwin - 1];
         const int nT = rec_koff(last) + ((last.y >> 8) & 0xff), nQ = rec_qoff(last) + (last.y & 0xff);
@@ -332,7 +365,6 @@ k_tca_tile(TcAttnParams P, int win_cap, const int2 *__restrict__ tiles, const in
                     const int r = (rec.y >> 8) & 0xff, mult = rec.y >> 16;
                     masked = mult > 0 && j == r - 1;  // last distinct key stands for all masked slots
                 }
-                else sQwin[tid - nT] = l;
                 // masked key: relative offset zeroed
                 p0 = masked ? make_float4(0.f, 0.f, 0.f, ctr.x)
                             : make_float4(__fsub_rn(px, ctr.x), __fsub_rn(py, ctr.y), __fsub_rn(pz, ctr.z), ctr.x);
@@ -432,9 +464,10 @@ k_tca_tile(TcAttnParams P, int win_cap, const int2 *__restrict__ tiles, const in
             }
             umma_commit(bar);
         }
+        KTRACE(13);
         // while the MMA runs: role and feature row id of this thread in the NEXT tile
         int n_kind = 0, n_l = 0, n_row = 0;
-        if (more) role(tl_next, (const int4 *)(sHdr + (buf ^ 1) * (TCA_TW * 32)), n_kind, n_l, n_row);
+        if (more) role(tl_next, sHdr + (buf ^ 1) * TCA_HDR_BYTES, n_kind, n_l, n_row);
         KTRACE(11);
         mbar_wait(bar, phase);
         phase ^= 1u;
@@ -504,7 +537,7 @@ k_tca_tile(TcAttnParams P, int win_cap, const int2 *__restrict__ tiles, const in
             constexpr int DPT = HD / 2;   // channels per thread (16 / 8 / 4)
             const int half = e & 1, qh = e >> 1;
             const int h = qh % HEADS, qs = qh / HEADS;
-            const int4 rec = sRec[sQwin[qs]];
+            const int4 rec = sRec[sRowTab[nT + qs] & 63];
             const int s = qs - rec_qoff(rec);
             const int wq = rec.y & 0xff, r = (rec.y >> 8) & 0xff, mult = rec.y >> 16;
             const float *sc = sS + (rec.z >> 16) + s * HEADS + h;  // + key * wq * HEADS
@@ -577,6 +610,7 @@ k_tca_tile(TcAttnParams P, int win_cap, const int2 *__restrict__ tiles, const in
             }
             umma_commit(bar);
         }
+        KTRACE(14);
         // the V / Q rows are consumed: the staging area takes the feature rows of the next tile
         float nx = 0.f, ny = 0.f, nz = 0.f;
         asm volatile("" : "+r"(n_row));   // (keeps every use of the row id -- address arithmetic included -- down here:
@@ -610,8 +644,8 @@ k_tca_tile(TcAttnParams P, int win_cap, const int2 *__restrict__ tiles, const in
     }
 #ifdef MSSVT_TRACE
     if (tid == 0 && blockIdx.x == gridDim.x - 1 && tr[10])
-        printf("tile g%d: pos+sync %lld | rows in %lld | mma1 wait %lld | A1+sync %lld | mma2 issue + roles(next) %lld + wait %lld | unload+sync %lld | scores+sync %lld | softmax+AV+sync %lld | mma3 issue + gather(next) %lld + wait %lld | out+sync %lld | total %lld clk\n", g,
-               tr[1] - tr[0], tr[2] - tr[1], tr[3] - tr[2], tr[4] - tr[3], tr[11] - tr[4], tr[5] - tr[11], tr[6] - tr[5], tr[7] - tr[6], tr[8] - tr[7], tr[12] - tr[8], tr[9] - tr[12], tr[10] - tr[9], tr[10] - tr[0]);
+        printf("tile g%d: pos+sync %lld | rows in %lld | mma1 wait %lld | A1+sync %lld | mma2 issue %lld + roles(next) %lld + wait %lld | unload+sync %lld | scores+sync %lld | softmax+AV+sync %lld | mma3 issue %lld + gather(next) %lld + wait %lld | out+sync %lld | total %lld clk\n", g,
+               tr[1] - tr[0], tr[2] - tr[1], tr[3] - tr[2], tr[4] - tr[3], tr[13] - tr[4], tr[11] - tr[13], tr[5] - tr[11], tr[6] - tr[5], tr[7] - tr[6], tr[8] - tr[7], tr[14] - tr[8], tr[12] - tr[14], tr[9] - tr[12], tr[10] - tr[9], tr[10] - tr[0]);
 #endif
     stage_packed_wait();
     tc_fence_before();
@@ -690,16 +724,16 @@ extern "C" {
 /* Tile plan of the tensor-core window attention: a function of the geometry (meta, q_base, win_list)
  * only, made once and shared by every block / launch over the same window lists.
  * tiles (2, win_capacity, 2) int, tile_count (2) int, win_rec (2, win_capacity, 4) int, win_ctr
- * (win_capacity, 4) float: opaque to the caller. */
+ * (win_capacity, 4) float, tile_rows (2, win_capacity, 128) bytes: opaque to the caller. */
 int mssvt_attention_tiles(int heads_per_group, int nq, int key_num_sample, int win_capacity,
                           const int *win_count_total, const int *win_list, const int *meta, const int *q_base,
                           const float *win_cell, const float *range_min, int *tiles, int *tile_count,
-                          int *win_rec, float *win_ctr, void *stream) {
+                          int *win_rec, float *win_ctr, unsigned char *tile_rows, void *stream) {
     if (heads_per_group <= 0 || nq <= 0 || nq > 32 || key_num_sample <= 0 || key_num_sample > 63 ||
         nq * (key_num_sample + 1) * heads_per_group > TCA_SBUD || win_capacity < 0)
         return MSSVT_ERR_INVALID;
     if (!win_count_total || !win_list || !meta || !q_base || !win_cell || !range_min || !tiles || !tile_count ||
-        !win_rec || !win_ctr)
+        !win_rec || !win_ctr || !tile_rows)
         return MSSVT_ERR_INVALID;
     cudaStream_t s = (cudaStream_t)stream;
     if (cudaMemsetAsync(tile_count, 0, 2 * sizeof(int), s) != cudaSuccess) return MSSVT_ERR_LAUNCH;
@@ -711,6 +745,9 @@ int mssvt_attention_tiles(int heads_per_group, int nq, int key_num_sample, int w
                                                make_float3(win_cell[0], win_cell[1], win_cell[2]),
                                                make_float3(range_min[0], range_min[1], range_min[2]),
                                                (int2 *)tiles, tile_count, (int4 *)win_rec, (float4 *)win_ctr);
+    ++g_launches;
+    k_tca_rows<<<MSSVT_NUM_SMS * 2, 256, 0, s>>>(win_capacity, (const int2 *)tiles, tile_count, (const int4 *)win_rec,
+                                                 tile_rows);
     return check_launch();
 }
 
@@ -733,7 +770,8 @@ int mssvt_block_attention_tc(int C, int heads_per_group, int nq, int key_num_sam
                              const int *rep_row, const int *meta, const int *q_base, const int *q_src,
                              const int *vox_slot, const unsigned char *nn_idx,
                              const float *nn_w, const int *tiles, const int *tile_count, const int *win_rec,
-                             const float *win_ctr, int num_voxels, float *scratch, float *merged, void *stream) {
+                             const float *win_ctr, const unsigned char *tile_rows, int num_voxels, float *scratch,
+                             float *merged, void *stream) {
     if (C != 64 || (heads_per_group != 1 && heads_per_group != 2 && heads_per_group != 4) || nq <= 0 || nq > 32 ||
         key_num_sample <= 0 || key_num_sample > 63 || cap1 <= 0 || cap1 > 128 || win_capacity < 0 || num_voxels < 0 ||
         nq * (key_num_sample + 1) * heads_per_group > TCA_SBUD || (terms != 0 && terms != 1 && terms != 3))
@@ -741,7 +779,7 @@ int mssvt_block_attention_tc(int C, int heads_per_group, int nq, int key_num_sam
     if (win_capacity == 0) return MSSVT_OK;
     if (!wpos_packed || !wkvq0 || !wkvq1 || !wp0 || !wp1 || !bq0 || !bq1 || !bkv0 || !bkv1 || !bp0 || !bp1 ||
         !win_count_total || !xn || !xyz || !q_row || !rep_row || !meta || !q_base || !q_src || !tiles ||
-        !tile_count || !win_rec || !win_ctr || !scratch || (!merged && !interp))
+        !tile_count || !win_rec || !win_ctr || !tile_rows || !scratch || (!merged && !interp))
         return MSSVT_ERR_INVALID;
     if (interp && (!vox_slot || !nn_idx || !nn_w)) return MSSVT_ERR_INVALID;
     TcAttnParams P;
@@ -763,7 +801,7 @@ int mssvt_block_attention_tc(int C, int heads_per_group, int nq, int key_num_sam
 #define TCA_LAUNCH(H, T)                                                                                   \
     cudaFuncSetAttribute(k_tca_tile<H, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
     launch_pdl(k_tca_tile<H, T>, dim3(grid), dim3(TCA_THREADS), smem, s, P, win_capacity, (const int2 *)tiles, \
-               tile_count, (const int4 *)win_rec, (const float4 *)win_ctr, xn, xyz, rep_row, q_row, Pbuf)
+               tile_count, (const int4 *)win_rec, (const float4 *)win_ctr, tile_rows, xn, xyz, rep_row, q_row, Pbuf)
     if (terms == 0) {
         if (heads_per_group == 1) { TCA_LAUNCH(1, 0); }
         else if (heads_per_group == 2) { TCA_LAUNCH(2, 0); }

@@ -389,7 +389,8 @@ class MixedScaleSparseTransformerBlock(nn.Module):
             cap, dev = g["cap"], g["meta"].device
             i32 = dict(dtype=torch.int32, device=dev)
             plan = (torch.empty((2, cap, 2), **i32), torch.empty(2, **i32), torch.empty((2, cap, 4), **i32),
-                    torch.empty((cap, 4), dtype=torch.float32, device=dev))
+                    torch.empty((cap, 4), dtype=torch.float32, device=dev),
+                    torch.empty((2, cap, 128), dtype=torch.uint8, device=dev))      # (only #tiles rows are touched)
             vs = sp_tensor.voxel_size
             call("mssvt_attention_tiles", heads, g["nq"], self.key_num_sample, cap, ptr(g["total"]),
                  ptr(g["win_list"]), ptr(g["meta"]), ptr(g["q_base"]),
