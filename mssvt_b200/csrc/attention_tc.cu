@@ -160,7 +160,7 @@ struct TcaSmem {
         rows = ao + nt * TCA_QMAX * TCA_SD * eb;   // gather staging, later V / Q rows [128][32]          16 KB
         hdr = rows + TCA_THREADS * TCA_SD * 4;     // (the MMA reads 128 rows of `ao`: it runs into `rows`)
         misc = hdr + 2 * TCA_HDR_BYTES;            // 2 x {window records [TW] int4, centres [TW] float4, row table [128]}
-        total = misc + 128 * 4 + 8 + 16 + 128;     // biases, barrier
+        total = misc + 128 * 4 + 16 + 16 + 128;    // biases, barriers
     }
 };
 
@@ -237,8 +237,8 @@ k_tca_tile(TcAttnParams P, int win_cap, const int2 *__restrict__ tiles, const in
     float *sS = (float *)sApos;                             // [SBUD] scores: window-major, [key][query][head]
     char *sHdr = smem_raw + L.hdr;                          // 2 x {int4 rec[TW], float4 ctr[TW], uint8 rows[128]}
     float *sBias = (float *)(smem_raw + L.misc);            // [32] bq * scale, [32] bv, [32] bp (+ pad)
-    uint64_t *sBar = (uint64_t *)(sBias + 128);
-    uint32_t *sTmem = (uint32_t *)(sBar + 1);
+    uint64_t *sBar = (uint64_t *)(sBias + 128);             // [0] MMA completion, [1] weights landed (TMA bulk copies)
+    uint32_t *sTmem = (uint32_t *)(sBar + 2);
     char *stg = sRows + warp * 4096;                        // this warp's staging area
 
     // weights of this scale: asynchronous 16-byte copies, waited for before the first MMA
@@ -251,8 +251,15 @@ k_tca_tile(TcAttnParams P, int win_cap, const int2 *__restrict__ tiles, const in
                          "l"((const char *)P.wpos + hl * 2048 + ch * 1024 + (g * 32 + n) * 16) : "memory");
         }
     }
-    stage_packed(P.wkvq[g], NT * 96 * 32 * EB / 4, sWkvq);
-    stage_packed(P.wp[g], NT * 32 * 32 * EB / 4, sWp);
+    const uint32_t bar_w = smem_u32(sBar + 1);
+    if (tid == 0) {
+        mbar_init(bar_w, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        // the group's projection matrices (packed once on the host side): two bulk copies of the TMA engine
+        bulk_expect(bar_w, (uint32_t)(NT * (96 + 32) * 32 * EB));
+        bulk_copy_g2s(P.wkvq[g], (uint32_t)(NT * 96 * 32 * EB), sWkvq, bar_w);
+        bulk_copy_g2s(P.wp[g], (uint32_t)(NT * 32 * 32 * EB), sWp, bar_w);
+    }
     if (tid < 32) {
         sBias[tid] = __ldg(P.bq[g] + tid) * P.scale;
         sBias[32 + tid] = __ldg(P.bkv[g] + 32 + tid);
@@ -310,6 +317,7 @@ k_tca_tile(TcAttnParams P, int win_cap, const int2 *__restrict__ tiles, const in
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    mbar_wait(bar_w, 0);
 #ifdef MSSVT_TRACE
     if (tid == 0 && (blockIdx.x % 97) == 0)
         printf("tile kernel prologue (block %d): pdl wait %lld | stage issue %lld | tmem alloc %lld | copies + sync %lld clk\n",

@@ -72,11 +72,18 @@ k_ffn_tc(FfnTcParams P, int n_cap, const int *__restrict__ n_dev, const float *_
     char *sW2 = sW1 + NT * F * C * EB;            // NT x [chunks][C][16 B]
     float *s_vec = (float *)(sW2 + NT * C * F * EB);   // ln_g[C], ln_b[C], b1[F], b2[C], next_g[C], next_b[C]
     float *s_red = s_vec + 5 * C + F;             // [4][2][128] partial row sums of the two half-row threads
-    uint64_t *s_bar = (uint64_t *)(s_red + 8 * TC_ROWS);  // 2 mbarriers (8-byte aligned: C, F even)
-    uint32_t *s_tmem = (uint32_t *)(s_bar + 2);
-
-    stage_packed(P.w1, NT * F * C * EB / 4, sW1);
-    stage_packed(P.w2, NT * C * F * EB / 4, sW2);
+    uint64_t *s_bar = (uint64_t *)(s_red + 8 * TC_ROWS);  // 3 mbarriers (8-byte aligned: C, F even)
+    uint32_t *s_tmem = (uint32_t *)(s_bar + 3);
+    const uint32_t bar_w = smem_u32(s_bar + 2);           // weights landed (TMA bulk copies)
+    if (tid == 0) {
+        mbar_init(bar_w, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        // W1 and W2 (packed once on the host side) come in as two bulk copies of the TMA engine
+        const uint32_t wbytes = (uint32_t)(NT * F * C * EB);
+        bulk_expect(bar_w, 2u * wbytes);
+        bulk_copy_g2s(P.w1, wbytes, sW1, bar_w);
+        bulk_copy_g2s(P.w2, wbytes, sW2, bar_w);
+    }
     for (int i = tid; i < C; i += TC_THREADS) {
         s_vec[i] = __ldg(P.ln_g + i);
         s_vec[C + i] = __ldg(P.ln_b + i);
@@ -336,9 +343,9 @@ k_ffn_tc(FfnTcParams P, int n_cap, const int *__restrict__ n_dev, const float *_
                 if (TERMS == 3) *(float4 *)(sA + TC_ROWS * C * 4 + (uint32_t)(half * (CH / 4) + c) * a_lbo + my_row_off) = lo;
             }
         }
-        stage_packed_wait();  // (first tile: the weight copies overlapped the loads and the LayerNorm)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
+        if (tile == (int)blockIdx.x) mbar_wait(bar_w, 0);  // (first tile: the weight copies overlapped the loads and the LayerNorm)
         TRACE(2);
         // ---- 2. D1[128 x F] = A[128 x C] . W1^T, one K = 8 slice (two 16-byte chunks) per MMA
         if (tid == 0) {
@@ -553,9 +560,9 @@ int mssvt_ffn_tc(int C, int F, int mode, int terms, float eps, const float *ln_g
     if (mode == 2 && (C != 64 || !x || !vox_slot || !meta || !q_base || !nn_idx || !nn_w || !projected || cap1 <= 0))
         return MSSVT_ERR_INVALID;
     const int nt = terms == 3 ? 2 : 1;
-    size_t smem = nt * ((size_t)TC_ROWS * C * 4 + 2 * (size_t)F * C * 4) + (size_t)(5 * C + F + 8 * TC_ROWS) * 4 + 2 * 8 + 16 + 128;
+    size_t smem = nt * ((size_t)TC_ROWS * C * 4 + 2 * (size_t)F * C * 4) + (size_t)(5 * C + F + 8 * TC_ROWS) * 4 + 3 * 8 + 16 + 128;
     if (terms == 0)  // bf16 operands: the A region keeps the size of the fp32 staging area, the weights halve
-        smem = (size_t)TC_ROWS * C * 4 + 2 * (size_t)F * C * 2 + (size_t)(5 * C + F + 8 * TC_ROWS) * 4 + 2 * 8 + 16 + 128;
+        smem = (size_t)TC_ROWS * C * 4 + 2 * (size_t)F * C * 2 + (size_t)(5 * C + F + 8 * TC_ROWS) * 4 + 3 * 8 + 16 + 128;
     if (smem > 227 * 1024) return MSSVT_ERR_INVALID;
     if (xn_next && (!next_ln_g || !next_ln_b)) return MSSVT_ERR_INVALID;
     FfnTcParams P = {F, mode, eps, w1, b1, w2, b2, ln_g, ln_b, next_ln_g, next_ln_b, next_eps,

@@ -295,6 +295,21 @@ __device__ __forceinline__ void stage_packed(const float *__restrict__ packed, i
 }
 __device__ __forceinline__ void stage_packed_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+// The same for whole matrices, by the TMA engine: ONE thread posts the expected byte count on an mbarrier and
+// issues one bulk copy global -> shared per matrix (cp.async.bulk, SASS UBLKCP); no thread touches the data,
+// and the copy lands through the async proxy, the one tcgen05.mma reads shared memory through.  Every thread
+// waits on the barrier (phase 0) before the first MMA that uses the weights.  src / dst 16-byte aligned, bytes a
+// multiple of 16.
+__device__ __forceinline__ void bulk_expect(uint32_t mbar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(const void *src, uint32_t bytes, char *dst, uint32_t mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(mbar)
+                 : "memory");
+}
+
 
 // one full warp; `last`: this CTA allocates nothing more (the permit is given back, so that other CTAs of the SM
 // do not queue behind it)

@@ -249,7 +249,8 @@ def test_pack_operand_tf32_layout_and_rounding(rows, k):
 
 def test_attention_tile_plan_invariants():
     """mssvt_attention_tiles: per scale, every window with a real query lies in exactly one tile; a tile
-    holds <= 128 key tasks, <= 128 queries, <= 32 windows, <= 2048 score slots; offsets are prefix sums"""
+    holds <= 128 rows (distinct keys + real queries), <= 48 queries, <= 32 windows, <= 2048 score slots; offsets
+    are prefix sums; the row table names the window and the kind of every row"""
     from mssvt_b200.config import block_cfg
     from mssvt_b200.mssvt_backbone import MixedScaleSparseTransformerBlock
     from mssvt_b200.mssvt_utils import SparseTensor
@@ -262,7 +263,7 @@ def test_attention_tile_plan_invariants():
                       spatial_shape=list(S0_GRID), voxel_size=list(S0_VOXEL), point_cloud_range=list(S0_RANGE),
                       batch_size=1, hash_size=400000, map_table=None, gather_dict=None)
     g = blk.geometry(sp)
-    tiles, tile_count, win_rec, win_ctr = (t.cpu() for t in blk._tile_plan(sp, g, 2))
+    tiles, tile_count, win_rec, win_ctr, tile_rows = (t.cpu() for t in blk._tile_plan(sp, g, 2))
     W = int(g["total"].item())
     meta, q_base = g["meta"][:W].cpu(), g["q_base"][:W + 1].cpu()
     heads = 2
@@ -278,7 +279,15 @@ def test_attention_tile_plan_invariants():
             assert 0 < nw <= 32 and ws + nw <= W
             seen[ws:ws + nw] += 1
             r, q = nrep[ws:ws + nw], nqr[ws:ws + nw]
-            assert int(r.sum()) <= 128 and int(q.sum()) <= 128 and int((r * q).sum()) * heads <= 2048
+            assert int(r.sum() + q.sum()) <= 128 and int(q.sum()) <= 48 and int((r * q).sum()) * heads <= 2048
+            # row table: keys of window l, then (behind all keys) the queries of window l; the rest idle
+            want_rows = torch.zeros(128, dtype=torch.uint8)
+            nT, at_k, at_q = int(r.sum()), 0, 0
+            for l in range(nw):
+                want_rows[at_k:at_k + int(r[l])] = l | 0x40
+                want_rows[nT + at_q:nT + at_q + int(q[l])] = l | 0x80
+                at_k, at_q = at_k + int(r[l]), at_q + int(q[l])
+            assert torch.equal(tile_rows[s, t], want_rows)
             off = rec[ws:ws + nw, 2]
             zero = torch.zeros(1, dtype=r.dtype)
             assert torch.equal(off & 0xff, torch.cat([zero, r.cumsum(0)[:-1]]).int())
