@@ -77,5 +77,52 @@ def test_dynamic_vfe_edge_cases():
     same = torch.tensor([[0, 1.0, 1.0, 0.0, 0.3, 0.4]] * 7).cuda()                                  # one voxel, 7 points
     out = vfe({"points": same, "batch_size": 1})
     assert out["voxel_coords"].shape == (1, 4) and bool((out["point_voxel"] == 0).all())
-    with pytest.raises(RuntimeError):
-        vfe.train()({"points": same, "batch_size": 1})
+    out_t = vfe.train()({"points": same, "batch_size": 1})       # training mode: batch statistics, differentiable
+    assert out_t["voxel_features"].requires_grad and out_t["voxel_coords"].shape == (1, 4)
+
+
+def test_dynamic_vfe_training_mode_batch_statistics_and_gradients():
+    """train(): BatchNorm1d uses the statistics of the in-range points (dynamic_vfe.py:57-66, 124-130) and the
+    module is differentiable; checked against the same mathematics in plain PyTorch on the CPU (torch.unique +
+    scatter), coordinates bit-exact, features and parameter gradients within 1e-4"""
+    g = torch.Generator().manual_seed(3)
+    n = 20000
+    xyz = (torch.rand((n, 3), generator=g) - 0.5) * torch.tensor([40.0, 40.0, 5.0]) + torch.tensor([0.0, 0.0, 1.0])
+    xyz[:200] += 500.0                                                       # some points outside the range
+    points = torch.cat([torch.randint(0, 2, (n, 1), generator=g).float(), xyz, torch.rand((n, 2), generator=g)], 1)
+    from mssvt_b200.synth import S0_GRID, S0_RANGE, S0_VOXEL
+    torch.manual_seed(0)
+    vfe = DynamicVFE(AttrDict(NUM_FILTERS=[32, 64]), 5, list(S0_VOXEL), list(S0_GRID), list(S0_RANGE))
+    ref = DynamicVFE(AttrDict(NUM_FILTERS=[32, 64]), 5, list(S0_VOXEL), list(S0_GRID), list(S0_RANGE))
+    ref.load_state_dict(vfe.state_dict())
+    vfe = vfe.cuda().train()
+    out = vfe({"points": points.cuda(), "batch_size": 2})
+    (out["voxel_features"] ** 2).mean().backward()
+    # the reference mathematics on the CPU
+    vs, lo = torch.tensor(S0_VOXEL), torch.tensor(S0_RANGE[:3])
+    pc = torch.floor((points[:, 1:4] - lo) / vs).int()
+    m = ((pc >= 0) & (pc < torch.tensor(S0_GRID))).all(1)
+    p, pc = points[m], pc[m]
+    key = ((p[:, 0].long() * S0_GRID[0] + pc[:, 0]) * S0_GRID[1] + pc[:, 1]) * S0_GRID[2] + pc[:, 2]
+    unq, inv = torch.unique(key, return_inverse=True)
+    V = unq.shape[0]
+    smax = lambda t: t.new_zeros((V, t.shape[1])).scatter_reduce(0, inv.unsqueeze(1).expand_as(t), t, "amax", include_self=False)
+    mean = torch.zeros(V, 3).index_add_(0, inv, p[:, 1:4]) / torch.bincount(inv, minlength=V).unsqueeze(1)
+    off = torch.tensor([S0_VOXEL[i] / 2 + S0_RANGE[i] for i in range(3)])
+    x = torch.cat([p[:, 1:6], p[:, 1:4] - mean[inv], p[:, 1:4] - (pc * vs + off)], 1)
+    ref.train()
+    for i, blk in enumerate(ref.pfn):
+        x = blk(x)
+        if i == 0:
+            x = torch.cat((x, smax(x)[inv]), 1)
+    want = smax(x)
+    (want ** 2).mean().backward()
+    coords = torch.stack([unq // (S0_GRID[0] * S0_GRID[1] * S0_GRID[2]), unq % S0_GRID[2], (unq // S0_GRID[2]) % S0_GRID[1],
+                          (unq // (S0_GRID[1] * S0_GRID[2])) % S0_GRID[0]], 1).int()
+    assert torch.equal(out["voxel_coords"].cpu(), coords)
+    assert (out["voxel_features"].detach().cpu() - want.detach()).abs().max().item() <= 1e-4 * want.abs().max().item()
+    gscale = max(b.grad.abs().max().item() for b in ref.parameters())   # (a Linear bias in front of a BatchNorm has
+    for (n1, a), (_, b) in zip(vfe.named_parameters(), ref.named_parameters()):   #  a mathematically zero gradient)
+        assert (a.grad.cpu() - b.grad).abs().max().item() <= 1e-4 * gscale, n1
+    # the running statistics were updated like nn.BatchNorm1d does
+    assert torch.allclose(vfe.pfn[0][1].running_mean.cpu(), ref.pfn[0][1].running_mean, atol=1e-5)
