@@ -10,7 +10,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmssvt_b200.so")
+# MSSVT_B200_LIB: another build of the same library (tools/build_trace_lib.sh, kernel experiments); never a fallback
+LIB_PATH = os.environ.get("MSSVT_B200_LIB") or os.path.join(_HERE, "libmssvt_b200.so")
 _lib = None
 
 P, I, L, F = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_float

@@ -173,27 +173,44 @@ __device__ __forceinline__ float ex2_fast(float x) {
     return y;
 }
 
-// 8 lanes per 128-byte slice: the warp copies the rows of its 32 lanes (my_src: this lane's row, nullptr = none)
-// asynchronously into its 4 KB staging area (16-byte chunks XOR-swizzled by the row)
-__device__ __forceinline__ void warp_rows_copy_async(char *stg, const float4 *my_src) {
+// 8 lanes per 128-byte slice: the warp copies the 128-byte slices (at `base`, row pitch TCA_C floats) of the
+// feature rows of its 32 lanes (my_row: this lane's row, < 0 = none) asynchronously into its 4 KB staging area
+// (16-byte chunks XOR-swizzled by the row).  Straight-line code: the eight row ids are shuffled first, the
+// copies are predicated (a branch per copy serialised shuffle -> compare -> branch -> copy eight times).
+__device__ __forceinline__ void warp_rows_copy_async(char *stg, const float *base, int my_row) {
     const int lane = threadIdx.x & 31, st_row = lane >> 3, st_ch = lane & 7;
-    const uint32_t base = smem_u32(stg);
+    const uint32_t dst = smem_u32(stg);
+    int rows[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) rows[i] = __shfl_sync(0xffffffffu, my_row, 4 * i + st_row);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int rr = 4 * i + st_row;
-        const float4 *p = (const float4 *)__shfl_sync(0xffffffffu, (unsigned long long)my_src, rr);
-        if (p) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(base + (uint32_t)(rr * 128 + ((st_ch ^ (rr & 7)) << 4))),
-                            "l"(p + st_ch) : "memory");
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.ge.s32 p, %2, 0;\n\t"
+            "@p cp.async.cg.shared.global [%0], [%1], 16;\n\t"
+            "}\n" ::"r"(dst + (uint32_t)(rr * 128 + ((st_ch ^ (rr & 7)) << 4))),
+            "l"(base + (size_t)max(rows[i], 0) * TCA_C + st_ch * 4), "r"(rows[i])
+            : "memory");
     }
 }
 
-// Software pipeline over the tiles of a CTA.  The loads of a tile form a chain of dependent global accesses
-// (tile record -> window records -> row ids -> coordinates + feature rows, ~3 L2 latencies); every link of
-// tile i + 1 is issued one phase of tile i ahead of its use and lands in shared memory (cp.async) or in a few
-// registers, so that a tile starts with its operands on the way:
-//     window records of i + 1: cp.async while tile i builds its positional operand
-//     row ids of i + 1:        loaded while MMA 2 of tile i runs
-//     feature rows of i + 1:   cp.async into the staging area once tile i is done with it (after softmax / AV)
+// Software pipeline over the tiles of a CTA.  Two things are pipelined ACROSS tiles:
+//   * the loads of a tile form a chain of dependent global accesses (tile record -> window records -> row ids
+//     -> coordinates + feature rows, ~3 L2 latencies); every link of tile i + 1 is issued one phase of tile i
+//     ahead of its use and lands in shared memory (cp.async groups) or in a few registers:
+//         window records of i + 1: cp.async at the top of tile i
+//         row ids of i + 1:        loaded while MMA 2 of tile i runs
+//         coordinates of i + 1:    loaded before the softmax of tile i
+//         feature rows of i + 1:   cp.async into the staging area once tile i is done with it (after softmax / AV)
+//   * the tensor-core round trips: the positional operand of tile i + 1 is built at the end of tile i, and MMA 1
+//     of tile i + 1 is issued TOGETHER with MMA 3 (output projection) of tile i under one commit; tile i + 1
+//     starts by reading both results.  A tile therefore costs two MMA round trips and five CTA barriers
+//     (before: three and nine); the projected rows of tile i leave the CTA at the top of tile i + 1.
+// TMEM columns: [0,32) pos -> A1 (MMA 1 of the NEXT tile may overwrite it as soon as MMA 2 is complete),
+// [32,64) K, [64,96) V, [96,128) Q -- and, once Q has been unloaded, the output projection (MMA 3).
 template <int HEADS, int TERMS>
 __global__ void __launch_bounds__(TCA_THREADS, TERMS == 3 ? 3 : 4)
 k_tca_tile(TcAttnParams P, int win_cap, const int2 *__restrict__ tiles, const int *__restrict__ tile_count,
@@ -212,11 +229,14 @@ k_tca_tile(TcAttnParams P, int win_cap, const int2 *__restrict__ tiles, const in
     const int K = P.K, nq = P.nq;
 #ifdef MSSVT_TRACE
     const long long t_entry = clock64();
+    auto gtime = []() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
+    const unsigned long long gt0 = gtime();
 #endif
     pdl_launch_dependents();
     pdl_wait();  // (the scale of this CTA, hence its weights, depends on the tile counts: nothing to do before)
 #ifdef MSSVT_TRACE
     const long long t_pdl = clock64();
+    const unsigned long long gt1 = gtime();
 #endif
 
     // ---- every CTA works on one scale (head group) for its whole life; the CTAs of the two scales are
@@ -309,6 +329,28 @@ k_tca_tile(TcAttnParams P, int win_cap, const int2 *__restrict__ tiles, const in
             row = __ldg(q_row + (size_t)(tl.x + l) * nq + (tid - nT - rec_qoff(rec[l])));
         }
     };
+    const uint32_t row_off = (uint32_t)(tid >> 3) * 128u + (uint32_t)(tid & 7) * 16u;   // canonical 8-row groups
+    // positional-embedding input of this thread's row, [rel | centre | 1 | 0] split hi / lo, canonical K-major
+    // [128][8] -> the A operand of MMA 1.  hdr: header of the row's tile; (x, y, z): centre of the row's voxel
+    auto pos_operand = [&](const char *hdr, int kind, int l, float x, float y, float z) {
+        float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1 = p0;
+        if (kind) {
+            const int4 rec = ((const int4 *)hdr)[l];
+            const float4 ctr = ((const float4 *)(hdr + TCA_TW * 16))[l];
+            // the last distinct key of a window stands for all masked slots: relative offset zeroed
+            const bool masked = kind == 1 && (rec.y >> 16) > 0 && tid - rec_koff(rec) == ((rec.y >> 8) & 0xff) - 1;
+            p0 = masked ? make_float4(0.f, 0.f, 0.f, ctr.x)
+                        : make_float4(__fsub_rn(x, ctr.x), __fsub_rn(y, ctr.y), __fsub_rn(z, ctr.z), ctr.x);
+            p1 = make_float4(ctr.y, ctr.z, 1.f, 0.f);
+        }
+        float4 hi, lo;
+        split_tf32(p0, hi, lo);
+        *(float4 *)(sApos + row_off) = hi;
+        *(float4 *)(sApos + 4096 + row_off) = lo;
+        split_tf32(p1, hi, lo);
+        *(float4 *)(sApos + 2048 + row_off) = hi;
+        *(float4 *)(sApos + 4096 + 2048 + row_off) = lo;
+    };
 
     int2 tl = first < T ? __ldg(tiles + first) : make_int2(0, 0);
     int2 tl_next = first + stride < T ? __ldg(tiles + first + stride) : make_int2(0, 0);
@@ -323,84 +365,85 @@ k_tca_tile(TcAttnParams P, int win_cap, const int2 *__restrict__ tiles, const in
         printf("tile kernel prologue (block %d): pdl wait %lld | stage issue %lld | tmem alloc %lld | copies + sync %lld clk\n",
                blockIdx.x, t_pdl - t_entry, t_stage - t_pdl, t_alloc - t_stage, clock64() - t_alloc);
 #endif
-    const uint32_t tm = *sTmem;                              // cols [0,32): pos -> A1 -> projection, [32,128): K|V|Q
+    const uint32_t tm = *sTmem;
     const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
     const uint32_t tm_a = tm, tm_k = tm + 32u, tm_v = tm + 64u, tm_q = tm + 96u;
     const uint32_t tm_alo = TERMS == 3 ? sTmem[1] : 0u;
     const uint32_t id_n32 = umma_idesc_tf32(128, 32), id_n96 = BF ? umma_idesc_bf16(128, 96) : umma_idesc_tf32(128, 96);
     const uint32_t id_p32 = BF ? umma_idesc_bf16(128, 32) : id_n32;   // output projection
-    const uint32_t sWpos_u = smem_u32(sWpos), sWkvq_u = smem_u32(sWkvq), sWp_u = smem_u32(sWp);
-    const uint32_t sApos_u = smem_u32(sApos), sAO_u = smem_u32(sAO);
-    const uint32_t row_off = (uint32_t)(tid >> 3) * 128u + (uint32_t)(tid & 7) * 16u;   // canonical 8-row groups
+    // operand regions as descriptor bases (tile / K chunk = one add on the address field)
+    const UmmaDescBase dWpos = umma_desc_base(smem_u32(sWpos), 512, 128), dWkvq = umma_desc_base(smem_u32(sWkvq), 1536, 128),
+                       dWp = umma_desc_base(smem_u32(sWp), 512, 128), dApos = umma_desc_base(smem_u32(sApos), 2048, 128),
+                       dAO = umma_desc_base(smem_u32(sAO), 128, BF ? 512 : 1024);
     uint32_t phase = 0;
 
-    // pipeline prologue: role, coordinates and feature row of the first tile
+    // One commit for: MMA 3 of the tile that just finished its softmax / AV (output projection of its queries,
+    // operand `ao` -> the Q columns, free since the unload) and MMA 1 of the tile whose positional operand was
+    // just built (-> columns [0,32), always 3xTF32)
+    auto issue_proj_and_pos = [&](bool with_proj, bool with_pos) {
+        if (issuer_elected()) {
+            tc_fence_after();
+            if (with_proj) {
+                if constexpr (BF) {
+#pragma unroll
+                    for (int k = 0; k < TCA_SD / 16; ++k)
+                        umma_bf16(tm_q, umma_desc_at(dAO, (uint32_t)k * 256u), umma_desc_at(dWp, (uint32_t)k * 1024u), id_p32,
+                                  k > 0 ? 1u : 0u);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < TCA_SD / 8; ++k) {
+                        const uint64_t ah = umma_desc_at(dAO, (uint32_t)k * 256u), wh = umma_desc_at(dWp, (uint32_t)k * 1024u);
+                        umma_tf32(tm_q, ah, wh, id_n32, k > 0 ? 1u : 0u);
+                        if (TERMS == 3) {
+                            umma_tf32(tm_q, umma_desc_at(dAO, TCA_QMAX * TCA_SD * 4 + (uint32_t)k * 256u), wh, id_n32, 1u);
+                            umma_tf32(tm_q, ah, umma_desc_at(dWp, 32u * 32u * 4u + (uint32_t)k * 1024u), id_n32, 1u);
+                        }
+                    }
+                }
+            }
+            if (with_pos) {
+                const uint64_t ah = umma_desc_at(dApos, 0u), al = umma_desc_at(dApos, 4096u);
+                const uint64_t wh = umma_desc_at(dWpos, 0u), wl = umma_desc_at(dWpos, 1024u);
+                umma_tf32(tm_a, ah, wh, id_n32, 0u);
+                umma_tf32(tm_a, al, wh, id_n32, 1u);
+                umma_tf32(tm_a, ah, wl, id_n32, 1u);
+            }
+            umma_commit(bar);
+        }
+        __syncwarp();
+    };
+
+    // pipeline prologue: role, coordinates, feature rows and positional operand of the first tile; MMA 1
     int kind = 0, l = 0, row = 0;
-    float px = 0.f, py = 0.f, pz = 0.f;
     if (first < T) {
         role(tl, sHdr, kind, l, row);
+        float px = 0.f, py = 0.f, pz = 0.f;
         if (kind) { px = __ldg(xyz + 3 * (size_t)row); py = __ldg(xyz + 3 * (size_t)row + 1); pz = __ldg(xyz + 3 * (size_t)row + 2); }
-        warp_rows_copy_async(stg, kind ? (const float4 *)(xn + (size_t)row * TCA_C + g * TCA_SD) : nullptr);
+        warp_rows_copy_async(stg, xn + g * TCA_SD, kind ? row : -1);
+        cp_async_commit();
+        pos_operand(sHdr, kind, l, px, py, pz);
+        fence_async_smem();
+        __syncthreads();
+        issue_proj_and_pos(false, true);
     }
 
 #ifdef MSSVT_TRACE
     long long tr[16] = {0};
 #endif
-    int buf = 0;
+    int buf = 0, prev_nQ = 0, prev_q0 = 0;
     for (int t = first; t < T; t += stride, buf ^= 1) {
         KTRACE(0);
-        const int4 *sRec = (const int4 *)(sHdr + buf * TCA_HDR_BYTES);
-        const unsigned char *sRowTab = (const unsigned char *)(sHdr + buf * TCA_HDR_BYTES + TCA_TW * 32);
-        const float4 *sCtr = (const float4 *)(sRec + TCA_TW);
+        const char *hdr = sHdr + buf * TCA_HDR_BYTES, *hdr_next = sHdr + (buf ^ 1) * TCA_HDR_BYTES;
+        const int4 *sRec = (const int4 *)hdr;
+        const unsigned char *sRowTab = (const unsigned char *)(hdr + TCA_TW * 32);
         const int nwin = tl.y;
         const bool more = t + stride < T;
         if (more) header_async(t + stride, tl_next, buf ^ 1);   // the next tile's window records: on their way now
+        cp_async_commit();
         const int2 tl_after = t + 2 * stride < T ? __ldg(tiles + t + 2 * stride) : make_int2(0, 0);
-        const int4 last = sRec[nwin - 1];
-        const int nT = rec_koff(last) + ((last.y >> 8) & 0xff), nQ = rec_qoff(last) + (last.y & 0xff);
-        const bool is_key = kind == 1, is_query = kind == 2;
-        int j = 0, nqr = 0, soff = 0, qrow0 = 0;
-        bool masked = false;
-        {
-            // ---- 1. positional-embedding input [rel | centre | 1 | 0], split hi / lo, canonical K-major [128][8]
-            float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1 = p0;
-            if (kind) {
-                const int4 rec = sRec[l];
-                const float4 ctr = sCtr[l];
-                if (is_key) {
-                    j = tid - rec_koff(rec);
-                    nqr = rec.y & 0xff; soff = rec.z >> 16; qrow0 = nT + rec_qoff(rec);
-                    const int r = (rec.y >> 8) & 0xff, mult = rec.y >> 16;
-                    masked = mult > 0 && j == r - 1;  // last distinct key stands for all masked slots
-                }
-                // masked key: relative offset zeroed
-                p0 = masked ? make_float4(0.f, 0.f, 0.f, ctr.x)
-                            : make_float4(__fsub_rn(px, ctr.x), __fsub_rn(py, ctr.y), __fsub_rn(pz, ctr.z), ctr.x);
-                p1 = make_float4(ctr.y, ctr.z, 1.f, 0.f);
-            }
-            float4 hi, lo;
-            split_tf32(p0, hi, lo);
-            *(float4 *)(sApos + row_off) = hi;
-            *(float4 *)(sApos + 4096 + row_off) = lo;
-            split_tf32(p1, hi, lo);
-            *(float4 *)(sApos + 2048 + row_off) = hi;
-            *(float4 *)(sApos + 4096 + 2048 + row_off) = lo;
-        }
-        fence_async_smem();
-        __syncthreads();
-        KTRACE(1);
-        if (tid == 0) {
-            tc_fence_after();
-            const uint64_t ah = umma_smem_desc(sApos_u, 2048, 128), al = umma_smem_desc(sApos_u + 4096u, 2048, 128);
-            const uint64_t wh = umma_smem_desc(sWpos_u, 512, 128), wl = umma_smem_desc(sWpos_u + 1024u, 512, 128);
-            umma_tf32(tm_a, ah, wh, id_n32, 0u);
-            umma_tf32(tm_a, al, wh, id_n32, 1u);
-            umma_tf32(tm_a, ah, wl, id_n32, 1u);
-            umma_commit(bar);
-        }
-        // the warp's 32 feature rows (copied by its own lanes) have landed, and so has the next header
+        // the warp's 32 feature rows (copied by its own lanes at the end of the previous tile) have landed
         float4 xv[TCA_SD / 4];
-        stage_packed_wait();
+        cp_async_wait_group<1>();
         __syncwarp();
         {
             const int lane = tid & 31;
@@ -408,11 +451,23 @@ k_tca_tile(TcAttnParams P, int win_cap, const int2 *__restrict__ tiles, const in
             for (int q = 0; q < 8; ++q)
                 xv[q] = kind ? *(const float4 *)(stg + lane * 128 + ((q ^ (lane & 7)) << 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        KTRACE(2);
-        mbar_wait(bar, phase);
+        KTRACE(1);
+        mbar_wait(bar, phase);   // MMA 1 of this tile (+ MMA 3 of the previous one)
         phase ^= 1u;
         tc_fence_after();
-        KTRACE(3);
+        KTRACE(2);
+        // ---- 5 (of the previous tile). projected rows of its queries (contiguous compact ids) -> (#queries, 64) array
+        if (warp * 32 < prev_nQ) {   // (warp-uniform)
+            float d[TCA_SD];
+            tmem_ld32(tm_q + lane_off, d);
+            if (tid < prev_nQ) {
+                float4 *dst = (float4 *)(Pbuf + (size_t)(prev_q0 + tid) * TCA_C + g * TCA_SD);
+#pragma unroll
+                for (int c4 = 0; c4 < TCA_SD / 4; ++c4)
+                    dst[c4] = make_float4(d[4 * c4] + sBias[64 + 4 * c4], d[4 * c4 + 1] + sBias[64 + 4 * c4 + 1],
+                                          d[4 * c4 + 2] + sBias[64 + 4 * c4 + 2], d[4 * c4 + 3] + sBias[64 + 4 * c4 + 3]);
+            }
+        }
         {
             // ---- 2. A1 = xn slice + relu(pos), TF32, written back over the accumulator (A operand from TMEM)
             float d[TCA_SD];
@@ -448,39 +503,51 @@ k_tca_tile(TcAttnParams P, int win_cap, const int2 *__restrict__ tiles, const in
             if constexpr (!BF) tmem_st32(tm_a + lane_off, d);
             tmem_st_wait();
         }
+        cp_async_wait_group<0>();   // this thread's part of the next header
         tc_fence_before();
-        __syncthreads();   // (also: every thread's header copies are complete -> the next header is visible)
-        KTRACE(4);
+        __syncthreads();            // (also: every thread's header copies are complete -> the next header is visible)
+        KTRACE(3);
         // ---- [K | V | Q] = A1 [Wk; Wv; scale Wq]^T: K in TMEM columns 32..63, V in 64..95, Q in 96..127
-        if (tid == 0) {
+        if (issuer_elected()) {
             tc_fence_after();
             if constexpr (BF) {
 #pragma unroll
                 for (int k = 0; k < TCA_SD / 16; ++k)   // K = 16 per MMA: 8 packed A columns, two 16-byte B chunks
-                    umma_bf16_ts(tm_k, tm_a + (uint32_t)k * 8u, umma_smem_desc(sWkvq_u + (uint32_t)k * 2u * 1536u, 1536, 128),
-                                 id_n96, k > 0 ? 1u : 0u);
+                    umma_bf16_ts(tm_k, tm_a + (uint32_t)k * 8u, umma_desc_at(dWkvq, (uint32_t)k * 2u * 1536u), id_n96, k > 0 ? 1u : 0u);
             } else
 #pragma unroll
             for (int k = 0; k < TCA_SD / 8; ++k) {
-                const uint64_t wh = umma_smem_desc(sWkvq_u + (uint32_t)k * 2u * 1536u, 1536, 128);
+                const uint64_t wh = umma_desc_at(dWkvq, (uint32_t)k * 2u * 1536u);
                 umma_tf32_ts(tm_k, tm_a + (uint32_t)k * 8u, wh, id_n96, k > 0 ? 1u : 0u);
                 if (TERMS == 3) {
                     umma_tf32_ts(tm_k, tm_alo + (uint32_t)k * 8u, wh, id_n96, 1u);
-                    umma_tf32_ts(tm_k, tm_a + (uint32_t)k * 8u,
-                                 umma_smem_desc(sWkvq_u + 96u * 32u * 4u + (uint32_t)k * 2u * 1536u, 1536, 128), id_n96, 1u);
+                    umma_tf32_ts(tm_k, tm_a + (uint32_t)k * 8u, umma_desc_at(dWkvq, 96u * 32u * 4u + (uint32_t)k * 2u * 1536u), id_n96, 1u);
                 }
             }
             umma_commit(bar);
         }
-        KTRACE(13);
-        // while the MMA runs: role and feature row id of this thread in the NEXT tile
+        __syncwarp();
+        KTRACE(4);
+        // while the MMA runs: role and feature row id of this thread in the NEXT tile, this tile's bookkeeping
         int n_kind = 0, n_l = 0, n_row = 0;
-        if (more) role(tl_next, sHdr + (buf ^ 1) * TCA_HDR_BYTES, n_kind, n_l, n_row);
-        KTRACE(11);
+        if (more) role(tl_next, hdr_next, n_kind, n_l, n_row);
+        const int4 last = sRec[nwin - 1];
+        const int nT = rec_koff(last) + ((last.y >> 8) & 0xff), nQ = rec_qoff(last) + (last.y & 0xff);
+        const bool is_key = kind == 1, is_query = kind == 2;
+        int j = 0, nqr = 0, soff = 0, qrow0 = 0;
+        bool masked = false;
+        if (is_key) {
+            const int4 rec = sRec[l];
+            j = tid - rec_koff(rec);
+            nqr = rec.y & 0xff; soff = rec.z >> 16; qrow0 = nT + rec_qoff(rec);
+            masked = (rec.y >> 16) > 0 && j == ((rec.y >> 8) & 0xff) - 1;  // last distinct key stands for all masked slots
+        }
+        const int q0_tile = sRec[0].x;
+        KTRACE(5);
         mbar_wait(bar, phase);
         phase ^= 1u;
         tc_fence_after();
-        KTRACE(5);
+        KTRACE(6);
         // ---- rows back from TMEM: V of the key rows and Q (+ bias) of the query rows -> shared memory (16-byte
         //      chunks XOR-swizzled by the row), K of this thread's key stays in registers.  Biases: q.(k + bk)
         //      shifts every score of a query by the same q.bk, which the softmax cancels, so bk is dropped;
@@ -514,7 +581,7 @@ k_tca_tile(TcAttnParams P, int win_cap, const int2 *__restrict__ tiles, const in
         }
         tc_fence_before();
         __syncthreads();
-        KTRACE(6);
+        KTRACE(7);
         // ---- 3. scores of this thread's key against the queries of its window
         if (is_key) {
             const float bias = masked ? -100.0f : 0.f;  // additive mask of the reference
@@ -537,7 +604,12 @@ k_tca_tile(TcAttnParams P, int win_cap, const int2 *__restrict__ tiles, const in
             }
         }
         __syncthreads();
-        KTRACE(7);
+        KTRACE(8);
+        // the next tile's coordinates: on their way during the softmax (the row id was loaded a phase ago; its use --
+        // address arithmetic included -- is kept down here so that its load is not waited for up there)
+        float nx = 0.f, ny = 0.f, nz = 0.f;
+        asm volatile("" : "+r"(n_row));
+        if (n_kind) { nx = __ldg(xyz + 3 * (size_t)n_row); ny = __ldg(xyz + 3 * (size_t)n_row + 1); nz = __ldg(xyz + 3 * (size_t)n_row + 2); }
         // ---- 4. softmax over the window's distinct keys and AV, thread = (query, head, half of the head);
         //      head outputs (+ bv) -> rows of the output-projection operand (canonical K-major, 8-row groups of
         //      8 chunks: byte = (q / 8) * 1024 + chunk * 128 + (q % 8) * 16)
@@ -594,66 +666,48 @@ k_tca_tile(TcAttnParams P, int win_cap, const int2 *__restrict__ tiles, const in
                 if (TERMS == 3) *(float4 *)(dst + TCA_QMAX * TCA_SD * 4 + d4 * 128) = lo;
             }
         }
+        __syncthreads();   // scores and V / Q rows are consumed: their memory takes the next tile's operands
+        KTRACE(9);
+        if (more) {
+            warp_rows_copy_async(stg, xn + g * TCA_SD, n_kind ? n_row : -1);
+            pos_operand(hdr_next, n_kind, n_l, nx, ny, nz);
+        }
+        cp_async_commit();
         fence_async_smem();
         __syncthreads();
-        KTRACE(8);
-        // ---- output projection of the group: rows = the tile's queries
-        if (tid == 0) {
-            tc_fence_after();
-            if constexpr (BF) {
-#pragma unroll
-                for (int k = 0; k < TCA_SD / 16; ++k)
-                    umma_bf16(tm_a, umma_smem_desc(sAO_u + (uint32_t)k * 256u, 128, 512),
-                              umma_smem_desc(sWp_u + (uint32_t)k * 1024u, 512, 128), id_p32, k > 0 ? 1u : 0u);
-            } else
-#pragma unroll
-            for (int k = 0; k < TCA_SD / 8; ++k) {
-                const uint64_t ah = umma_smem_desc(sAO_u + (uint32_t)k * 256u, 128, 1024);
-                const uint64_t wh = umma_smem_desc(sWp_u + (uint32_t)k * 1024u, 512, 128);
-                umma_tf32(tm_a, ah, wh, id_n32, k > 0 ? 1u : 0u);
-                if (TERMS == 3) {
-                    umma_tf32(tm_a, umma_smem_desc(sAO_u + TCA_QMAX * TCA_SD * 4 + (uint32_t)k * 256u, 128, 1024), wh, id_n32, 1u);
-                    umma_tf32(tm_a, ah, umma_smem_desc(sWp_u + 32u * 32u * 4u + (uint32_t)k * 1024u, 512, 128), id_n32, 1u);
-                }
-            }
-            umma_commit(bar);
-        }
-        KTRACE(14);
-        // the V / Q rows are consumed: the staging area takes the feature rows of the next tile
-        float nx = 0.f, ny = 0.f, nz = 0.f;
-        asm volatile("" : "+r"(n_row));   // (keeps every use of the row id -- address arithmetic included -- down here:
-                                          //  its load was issued a phase ago and must not be waited for up there)
-        if (more) {
-            if (n_kind) { nx = __ldg(xyz + 3 * (size_t)n_row); ny = __ldg(xyz + 3 * (size_t)n_row + 1); nz = __ldg(xyz + 3 * (size_t)n_row + 2); }
-            warp_rows_copy_async(stg, n_kind ? (const float4 *)(xn + (size_t)n_row * TCA_C + g * TCA_SD) : nullptr);
-        }
-        KTRACE(12);
+        KTRACE(10);
+        issue_proj_and_pos(true, more);
+        KTRACE(11);
+        prev_nQ = nQ; prev_q0 = q0_tile;
+        kind = n_kind; l = n_l; row = n_row;
+        tl = tl_next; tl_next = tl_after;
+    }
+    // the projected rows of the CTA's last tile
+    if (first < T) {
         mbar_wait(bar, phase);
-        phase ^= 1u;
         tc_fence_after();
-        KTRACE(9);
-        // ---- 5. projected rows of the tile's queries (contiguous compact ids) -> (#queries, 64) array
-        if (warp * 32 < nQ) {   // (warp-uniform)
+        if (warp * 32 < prev_nQ) {
             float d[TCA_SD];
-            tmem_ld32(tm_a + lane_off, d);
-            if (tid < nQ) {
-                float4 *dst = (float4 *)(Pbuf + (size_t)(sRec[0].x + tid) * TCA_C + g * TCA_SD);
+            tmem_ld32(tm_q + lane_off, d);
+            if (tid < prev_nQ) {
+                float4 *dst = (float4 *)(Pbuf + (size_t)(prev_q0 + tid) * TCA_C + g * TCA_SD);
 #pragma unroll
                 for (int c4 = 0; c4 < TCA_SD / 4; ++c4)
                     dst[c4] = make_float4(d[4 * c4] + sBias[64 + 4 * c4], d[4 * c4 + 1] + sBias[64 + 4 * c4 + 1],
                                           d[4 * c4 + 2] + sBias[64 + 4 * c4 + 2], d[4 * c4 + 3] + sBias[64 + 4 * c4 + 3]);
             }
         }
-        tc_fence_before();
-        __syncthreads();
-        KTRACE(10);
-        kind = n_kind; l = n_l; row = n_row; px = nx; py = ny; pz = nz;
-        tl = tl_next; tl_next = tl_after;
     }
 #ifdef MSSVT_TRACE
-    if (tid == 0 && blockIdx.x == gridDim.x - 1 && tr[10])
-        printf("tile g%d: pos+sync %lld | rows in %lld | mma1 wait %lld | A1+sync %lld | mma2 issue %lld + roles(next) %lld + wait %lld | unload+sync %lld | scores+sync %lld | softmax+AV+sync %lld | mma3 issue %lld + gather(next) %lld + wait %lld | out+sync %lld | total %lld clk\n", g,
-               tr[1] - tr[0], tr[2] - tr[1], tr[3] - tr[2], tr[4] - tr[3], tr[13] - tr[4], tr[11] - tr[13], tr[5] - tr[11], tr[6] - tr[5], tr[7] - tr[6], tr[8] - tr[7], tr[14] - tr[8], tr[12] - tr[14], tr[9] - tr[12], tr[10] - tr[9], tr[10] - tr[0]);
+    if (tid == 0 && blockIdx.x == gridDim.x - 1 && tr[11])
+        printf("tile g%d: rows in %lld | wait A %lld | proj(prev)+A1+sync %lld | mma2 issue %lld | roles(next) %lld | wait %lld | unload+sync %lld | scores+sync %lld | softmax+AV+sync %lld | gather+pos(next)+sync %lld | issue %lld | total %lld clk\n", g,
+               tr[1] - tr[0], tr[2] - tr[1], tr[3] - tr[2], tr[4] - tr[3], tr[5] - tr[4], tr[6] - tr[5], tr[7] - tr[6], tr[8] - tr[7], tr[9] - tr[8], tr[10] - tr[9], tr[11] - tr[10], tr[11] - tr[0]);
+#endif
+#ifdef MSSVT_TRACE
+    if (tid == 0 && (blockIdx.x % 59) == 0)
+        printf("tile cta %3d (sm %2u, scale %d, %d tiles): entry %llu | pdl wait +%llu | exit +%llu ns\n", blockIdx.x,
+               [] { unsigned s; asm("mov.u32 %0, %%smid;" : "=r"(s)); return s; }(), g, first < T ? (T - first + stride - 1) / stride : 0,
+               gt0 % 100000000ull, gt1 - gt0, gtime() - gt0);
 #endif
     stage_packed_wait();
     tc_fence_before();
@@ -804,6 +858,9 @@ int mssvt_block_attention_tc(int C, int heads_per_group, int nq, int key_num_sam
     int per_sm = (int)(227 * 1024 / (smem + 1024));
     const int tmem_limit = terms == 3 ? 3 : 4;   // 160 / 128 TMEM columns each
     per_sm = per_sm > tmem_limit ? tmem_limit : per_sm < 1 ? 1 : per_sm;
+#ifdef TCA_MAX_PER_SM   // (occupancy experiments)
+    if (per_sm > TCA_MAX_PER_SM) per_sm = TCA_MAX_PER_SM;
+#endif
     const int grid = MSSVT_NUM_SMS * per_sm;
     ++g_launches;
 #define TCA_LAUNCH(H, T)                                                                                   \

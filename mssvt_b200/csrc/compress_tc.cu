@@ -257,7 +257,7 @@ k_tcc_keys(TccParams P, const int2 *__restrict__ tiles, const int *__restrict__ 
         stage_packed_wait();
         fence_async_smem();
         __syncthreads();
-        if (tid == 0) {  // D1 = A1 W2^T
+        if (issuer_elected()) {  // D1 = A1 W2^T
             tc_fence_after();
 #pragma unroll
             for (int k = 0; k < TCC_C / 8; ++k)
@@ -290,7 +290,7 @@ k_tcc_keys(TccParams P, const int2 *__restrict__ tiles, const int *__restrict__ 
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
-        if (tid == 0) {  // D2 = A2 Wkv^T
+        if (issuer_elected()) {  // D2 = A2 Wkv^T
             tc_fence_after();
 #pragma unroll
             for (int k = 0; k < TCC_C / 8; ++k)

@@ -32,7 +32,10 @@ namespace mssvt {
 #else
 #define TRACE(i) do {} while (0)
 #endif
-#define TC_THREADS 256   // two threads per row: warps w and w + 4 reach the same 32 TMEM lanes
+// TPR threads share a row (= TMEM lane): warps w, w + 4, ... reach the same 32 TMEM lanes, each owns C / TPR channels
+// and F / TPR hidden columns.  TPR = 2: 256 threads per tile; TPR = 4 (C = 64): 512 threads per tile -- the kernel is
+// bound by the dependent-instruction latency of its per-row epilogues (a tile takes the same ~13 k clocks alone on
+// an SM and next to a second CTA), so halving the per-thread chains and doubling the warps is what speeds it up.
 
 struct FfnTcParams {
     int F, mode;            // hidden width; 0: u = merged, 1: u = covered ? merged + x : 2 x
@@ -52,17 +55,24 @@ struct FfnTcParams {
 
 // TERMS: 1 = TF32 operands, 3 = split operands (3xTF32), 0 = bf16 operands (kind::f16; half the operand bytes,
 // the hidden tile packed two per TMEM column)
-template <int C, int TERMS>
-__global__ void __launch_bounds__(TC_THREADS, TERMS == 3 ? 1 : 2)
+template <int C, int TERMS, int TPR>
+__global__ void __launch_bounds__(TC_ROWS * TPR, TERMS == 3 ? 1 : 2)
 k_ffn_tc(FfnTcParams P, int n_cap, const int *__restrict__ n_dev, const float *__restrict__ x,
          const float *__restrict__ merged, const unsigned char *__restrict__ covered,
          float *__restrict__ y, float *__restrict__ xn_next) {
-    constexpr int CH = C / 2;  // channels per thread: two threads (warps w and w + 4) share a row
+    constexpr int TC_THREADS = TC_ROWS * TPR;
+    constexpr int CH = C / TPR;  // channels per thread
+    static_assert(CH == 32 || CH == 16, "a thread owns 16 or 32 channels of its row");
     extern __shared__ __align__(128) char smem_raw[];
+#ifdef MSSVT_TRACE
+    unsigned long long gt[8] = {0};   // %globaltimer (ns) timeline of this CTA
+    auto gtime = []() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
+    gt[0] = gtime();
+#endif
     pdl_launch_dependents();
-    const int F = P.F, FH = F / 2;
+    const int F = P.F, FH = F / TPR;
     const int tid = threadIdx.x, warp = tid >> 5;
-    const int r = tid & (TC_ROWS - 1), half = tid >> 7;
+    const int r = tid & (TC_ROWS - 1), half = tid >> 7;   // half: which part of the row (0 .. TPR - 1)
     // carve shared memory
     constexpr int NT = TERMS == 3 ? 2 : 1;        // operand tiles: hi [, lo] (3xTF32, see tc_common.cuh)
     constexpr bool BF = TERMS == 0;               // bf16 operands
@@ -71,8 +81,8 @@ k_ffn_tc(FfnTcParams P, int n_cap, const int *__restrict__ n_dev, const float *_
     char *sW1 = sA + (BF ? TC_ROWS * C * 4 : NT * TC_ROWS * C * 4);   // NT x [chunks][F][16 B]
     char *sW2 = sW1 + NT * F * C * EB;            // NT x [chunks][C][16 B]
     float *s_vec = (float *)(sW2 + NT * C * F * EB);   // ln_g[C], ln_b[C], b1[F], b2[C], next_g[C], next_b[C]
-    float *s_red = s_vec + 5 * C + F;             // [4][2][128] partial row sums of the two half-row threads
-    uint64_t *s_bar = (uint64_t *)(s_red + 8 * TC_ROWS);  // 3 mbarriers (8-byte aligned: C, F even)
+    float *s_red = s_vec + 5 * C + F;             // [4][TPR][128] partial row sums of the threads of a row
+    uint64_t *s_bar = (uint64_t *)(s_red + 4 * TPR * TC_ROWS);  // 3 mbarriers (8-byte aligned: C, F even)
     uint32_t *s_tmem = (uint32_t *)(s_bar + 3);
     const uint32_t bar_w = smem_u32(s_bar + 2);           // weights landed (TMA bulk copies)
     if (tid == 0) {
@@ -119,18 +129,34 @@ k_ffn_tc(FfnTcParams P, int n_cap, const int *__restrict__ n_dev, const float *_
     const uint32_t idesc1 = BF ? umma_idesc_bf16(TC_ROWS, F) : umma_idesc_tf32(TC_ROWS, F);
     const uint32_t idesc2 = BF ? umma_idesc_bf16(TC_ROWS, C) : umma_idesc_tf32(TC_ROWS, C);
     const uint32_t a_lbo = TC_ROWS * 16, w1_lbo = (uint32_t)F * 16, w2_lbo = (uint32_t)C * 16;
-    const uint32_t sA_u = smem_u32(sA), sW1_u = smem_u32(sW1), sW2_u = smem_u32(sW2);
+    const UmmaDescBase dA = umma_desc_base(smem_u32(sA), a_lbo, 128), dW1 = umma_desc_base(smem_u32(sW1), w1_lbo, 128),
+                       dW2 = umma_desc_base(smem_u32(sW2), w2_lbo, 128);
 
+#ifdef MSSVT_TRACE
+    gt[1] = gtime();
+#endif
     pdl_wait();  // (everything above touched static parameters only)
+#ifdef MSSVT_TRACE
+    gt[2] = gtime();
+#endif
     const int n = n_dev ? min(n_cap, __ldg(n_dev)) : n_cap;
     const int tiles = (n + TC_ROWS - 1) / TC_ROWS;
     uint32_t phase = 0;
     const uint32_t my_row_off = (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u;
     float *red_mine = s_red + half * TC_ROWS + r;
-    const float *red_other = s_red + (half ^ 1) * TC_ROWS + r;
+    // sum of the row's TPR partials in slot `which` (the same order in every thread of the row)
+    auto red_sum = [&](int which) {
+        const float *p = s_red + which * TPR * TC_ROWS + r;
+        float t = p[0];
+#pragma unroll
+        for (int i = 1; i < TPR; ++i) t += p[i * TC_ROWS];
+        return t;
+    };
     // warp-private staging inside the A tile (free between the second GEMM of a tile and the A stores of
     // the next): 32 half-rows of CH floats, 16-byte chunks XOR-swizzled by the row -> conflict-free both ways
-    constexpr int CPR = CH / 4, RPI = 32 / CPR;  // chunks per half-row, rows per warp instruction
+    constexpr int CPR = CH / 4, RPI = 32 / CPR;  // chunks per part-row, rows per warp instruction
+    constexpr int SWS = CH == 32 ? 0 : 1;        // swizzle key of a row: (row >> SWS) & (CPR - 1) -- 8 consecutive lanes
+                                                 // (one 128-byte wavefront) always hit 8 different 16-byte bank groups
     const int lane = tid & 31;
     char *stg = sA + warp * (32 * CH * 4);
     const int st_row = lane / CPR, st_ch = lane % CPR;
@@ -146,23 +172,81 @@ k_ffn_tc(FfnTcParams P, int n_cap, const int *__restrict__ n_dev, const float *_
 #pragma unroll
         for (int i = 0; i < CPR; ++i) {
             const int rr = RPI * i + st_row;
-            *(float4 *)(stg + rr * (CH * 4) + ((st_ch ^ (rr & (CPR - 1))) << 4)) = v[i];
+            *(float4 *)(stg + rr * (CH * 4) + ((st_ch ^ ((rr >> SWS) & (CPR - 1))) << 4)) = v[i];
         }
         __syncwarp();
 #pragma unroll
-        for (int q = 0; q < CPR; ++q) dst[q] = *(const float4 *)(stg + lane * (CH * 4) + ((q ^ (lane & (CPR - 1))) << 4));
+        for (int q = 0; q < CPR; ++q) dst[q] = *(const float4 *)(stg + lane * (CH * 4) + ((q ^ ((lane >> SWS) & (CPR - 1))) << 4));
+        __syncwarp();
+    };
+    // the same for rows named by a pointer per lane (my_src: this lane's CH-float segment, nullptr = a zero row)
+    auto gather_in = [&](const float *my_src, float4 *dst) {
+        float4 v[CPR];
+#pragma unroll
+        for (int i = 0; i < CPR; ++i) {
+            const float4 *p = (const float4 *)__shfl_sync(0xffffffffu, (unsigned long long)my_src, RPI * i + st_row);
+            v[i] = p ? __ldg(p + st_ch) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < CPR; ++i) {
+            const int rr = RPI * i + st_row;
+            *(float4 *)(stg + rr * (CH * 4) + ((st_ch ^ ((rr >> SWS) & (CPR - 1))) << 4)) = v[i];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < CPR; ++q) dst[q] = *(const float4 *)(stg + lane * (CH * 4) + ((q ^ ((lane >> SWS) & (CPR - 1))) << 4));
+        __syncwarp();
+    };
+    // two row sets per memory round trip: all global loads of both are issued before the first is parked in the
+    // staging area (a tile's load phase is a chain of dependent round trips; this halves it).  Set a: rows named by a
+    // pointer per lane; set b: rows named by a pointer per lane (b_src == nullptr) or the tile's rows of `b_src`
+    auto gather_in2 = [&](const float *a_ptr, float4 *da, const float *b_ptr, const float *__restrict__ b_src, float4 *db) {
+        float4 va[CPR], vb[CPR];
+#pragma unroll
+        for (int i = 0; i < CPR; ++i) {
+            const float4 *p = (const float4 *)__shfl_sync(0xffffffffu, (unsigned long long)a_ptr, RPI * i + st_row);
+            va[i] = p ? __ldg(p + st_ch) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < CPR; ++i) {
+            if (b_src) {
+                const int grow = tile_row0 + RPI * i + st_row;
+                vb[i] = grow < n ? __ldg((const float4 *)(b_src + (size_t)grow * C + half * CH) + st_ch)
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
+                const float4 *p = (const float4 *)__shfl_sync(0xffffffffu, (unsigned long long)b_ptr, RPI * i + st_row);
+                vb[i] = p ? __ldg(p + st_ch) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < CPR; ++i) {
+            const int rr = RPI * i + st_row;
+            *(float4 *)(stg + rr * (CH * 4) + ((st_ch ^ ((rr >> SWS) & (CPR - 1))) << 4)) = va[i];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < CPR; ++q) da[q] = *(const float4 *)(stg + lane * (CH * 4) + ((q ^ ((lane >> SWS) & (CPR - 1))) << 4));
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < CPR; ++i) {
+            const int rr = RPI * i + st_row;
+            *(float4 *)(stg + rr * (CH * 4) + ((st_ch ^ ((rr >> SWS) & (CPR - 1))) << 4)) = vb[i];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < CPR; ++q) db[q] = *(const float4 *)(stg + lane * (CH * 4) + ((q ^ ((lane >> SWS) & (CPR - 1))) << 4));
         __syncwarp();
     };
     auto stage_out = [&](float *__restrict__ dst, const float4 *src) {
 #pragma unroll
-        for (int q = 0; q < CPR; ++q) *(float4 *)(stg + lane * (CH * 4) + ((q ^ (lane & (CPR - 1))) << 4)) = src[q];
+        for (int q = 0; q < CPR; ++q) *(float4 *)(stg + lane * (CH * 4) + ((q ^ ((lane >> SWS) & (CPR - 1))) << 4)) = src[q];
         __syncwarp();
 #pragma unroll
         for (int i = 0; i < CPR; ++i) {
             const int rr = RPI * i + st_row, grow = tile_row0 + rr;
             if (grow < n)
                 *((float4 *)(dst + (size_t)grow * C + half * CH) + st_ch) =
-                    *(const float4 *)(stg + rr * (CH * 4) + ((st_ch ^ (rr & (CPR - 1))) << 4));
+                    *(const float4 *)(stg + rr * (CH * 4) + ((st_ch ^ ((rr >> SWS) & (CPR - 1))) << 4));
         }
         __syncwarp();
     };
@@ -216,9 +300,9 @@ k_ffn_tc(FfnTcParams P, int n_cap, const int *__restrict__ n_dev, const float *_
             if (ix.cov) {
                 const int n0 = ix.nn & 0xff, n1 = (ix.nn >> 8) & 0xff, n2 = (ix.nn >> 16) & 0xff;
                 // padded query slots (index >= #real queries) are zero rows in the reference
-                if (n0 < ix.nqr) ix.p0 = P.pbuf + (size_t)(ix.q0 + n0) * 64 + half * 32;
-                if (n1 < ix.nqr) ix.p1 = P.pbuf + (size_t)(ix.q0 + n1) * 64 + half * 32;
-                if (n2 < ix.nqr) ix.p2 = P.pbuf + (size_t)(ix.q0 + n2) * 64 + half * 32;
+                if (n0 < ix.nqr) ix.p0 = P.pbuf + (size_t)(ix.q0 + n0) * 64 + half * CH;
+                if (n1 < ix.nqr) ix.p1 = P.pbuf + (size_t)(ix.q0 + n1) * 64 + half * CH;
+                if (n2 < ix.nqr) ix.p2 = P.pbuf + (size_t)(ix.q0 + n2) * 64 + half * CH;
             }
         }
     };
@@ -235,22 +319,24 @@ k_ffn_tc(FfnTcParams P, int n_cap, const int *__restrict__ n_dev, const float *_
                     // arithmetic as k_tca_merge)
                     const float *p0 = ix.p0, *p1 = ix.p1, *p2 = ix.p2;
                     const float w0 = ix.w0, w1 = ix.w1, w2 = ix.w2;
-                    float4 v[8];
-                    warp_rows_load(stg, (const float4 *)p0, mv);
+                    float4 v[CPR];
+                    gather_in2(p0, mv, p1, nullptr, v);
 #pragma unroll
-                    for (int q = 0; q < 8; ++q)
-                        mv[q] = make_float4(__fmul_rn(mv[q].x, w0), __fmul_rn(mv[q].y, w0), __fmul_rn(mv[q].z, w0),
-                                            __fmul_rn(mv[q].w, w0));
-                    warp_rows_load(stg, (const float4 *)p1, v);
+                    for (int q = 0; q < CPR; ++q)
+                        mv[q] = make_float4(__fadd_rn(__fmul_rn(mv[q].x, w0), __fmul_rn(v[q].x, w1)), __fadd_rn(__fmul_rn(mv[q].y, w0), __fmul_rn(v[q].y, w1)),
+                                            __fadd_rn(__fmul_rn(mv[q].z, w0), __fmul_rn(v[q].z, w1)), __fadd_rn(__fmul_rn(mv[q].w, w0), __fmul_rn(v[q].w, w1)));
+                    float4 xv[CPR];
+                    gather_in2(p2, v, nullptr, x, xv);
+                    if (!live) cov = false;
 #pragma unroll
-                    for (int q = 0; q < 8; ++q)
-                        mv[q] = make_float4(__fadd_rn(mv[q].x, __fmul_rn(v[q].x, w1)), __fadd_rn(mv[q].y, __fmul_rn(v[q].y, w1)),
-                                            __fadd_rn(mv[q].z, __fmul_rn(v[q].z, w1)), __fadd_rn(mv[q].w, __fmul_rn(v[q].w, w1)));
-                    warp_rows_load(stg, (const float4 *)p2, v);
-#pragma unroll
-                    for (int q = 0; q < 8; ++q)
-                        mv[q] = make_float4(__fadd_rn(mv[q].x, __fmul_rn(v[q].x, w2)), __fadd_rn(mv[q].y, __fmul_rn(v[q].y, w2)),
-                                            __fadd_rn(mv[q].z, __fmul_rn(v[q].z, w2)), __fadd_rn(mv[q].w, __fmul_rn(v[q].w, w2)));
+                    for (int c = 0; c < CPR; ++c) {
+                        const float4 xx = xv[c];
+                        float4 m = make_float4(__fadd_rn(mv[c].x, __fmul_rn(v[c].x, w2)), __fadd_rn(mv[c].y, __fmul_rn(v[c].y, w2)),
+                                               __fadd_rn(mv[c].z, __fmul_rn(v[c].z, w2)), __fadd_rn(mv[c].w, __fmul_rn(v[c].w, w2)));
+                        if (!cov) m = xx;
+                        u[4 * c] = m.x + xx.x; u[4 * c + 1] = m.y + xx.y; u[4 * c + 2] = m.z + xx.z; u[4 * c + 3] = m.w + xx.w;
+                    }
+                    return;
                 }
             }
             if (P.mode != 2) stage_in(merged, mv);
@@ -278,24 +364,20 @@ k_ffn_tc(FfnTcParams P, int n_cap, const int *__restrict__ n_dev, const float *_
     constexpr bool PIPE = TERMS == 3;
     float u[CH];
     MergeIdx ix;
-    if (PIPE && (int)blockIdx.x < tiles) {
+    if ((int)blockIdx.x < tiles) {
         index_stage0(blockIdx.x, ix);
         index_stage1(ix);
         index_stage2(ix);
-        load_tile(blockIdx.x, ix, u);
+        if (PIPE) load_tile(blockIdx.x, ix, u);
     }
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, phase ^= 1u) {
         TRACE(0);
         const int row = tile * TC_ROWS + r;
         const bool live = row < n;
         (void)live;
-        const int next_tile = PIPE ? tile + (int)gridDim.x : tiles;
-        if (!PIPE) {
-            index_stage0(tile, ix);
-            index_stage1(ix);
-            index_stage2(ix);
-            load_tile(tile, ix, u);
-        }
+        // (both orders: the index chain of the NEXT tile's rows is issued in stages during this tile, see above)
+        const int next_tile = tile + (int)gridDim.x;
+        if (!PIPE) load_tile(tile, ix, u);
         if (next_tile < tiles) index_stage0(next_tile, ix);
         {   // rows two tiles ahead: start them on their way from HBM to L2 now
             const int nrow = row + 2 * (int)gridDim.x * TC_ROWS;
@@ -311,13 +393,13 @@ k_ffn_tc(FfnTcParams P, int n_cap, const int *__restrict__ n_dev, const float *_
         TRACE(1);
         red_mine[0] = part;
         __syncthreads();
-        const float mean = (part + red_other[0]) * (1.0f / C);
+        const float mean = red_sum(0) * (1.0f / C);
         part = 0.f;
 #pragma unroll
         for (int c = 0; c < CH; ++c) { const float d = u[c] - mean; part = fmaf(d, d, part); }
-        red_mine[2 * TC_ROWS] = part;
+        red_mine[TPR * TC_ROWS] = part;
         __syncthreads();
-        const float rstd = rsqrtf((part + red_other[2 * TC_ROWS]) * (1.0f / C) + P.eps);
+        const float rstd = rsqrtf(red_sum(1) * (1.0f / C) + P.eps);
         if constexpr (BF) {
             // 16-byte chunks of 8 bf16: chunk = channel / 8
 #pragma unroll
@@ -348,18 +430,23 @@ k_ffn_tc(FfnTcParams P, int n_cap, const int *__restrict__ n_dev, const float *_
         if (tile == (int)blockIdx.x) mbar_wait(bar_w, 0);  // (first tile: the weight copies overlapped the loads and the LayerNorm)
         TRACE(2);
         // ---- 2. D1[128 x F] = A[128 x C] . W1^T, one K = 8 slice (two 16-byte chunks) per MMA
-        if (tid == 0) {
+        if (issuer_elected()) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if constexpr (BF) {
 #pragma unroll
                 for (int k = 0; k < C / 16; ++k)       // K = 16 per MMA: two 16-byte chunks of 8 elements
-                    umma_bf16(tmem_d1, umma_smem_desc(sA_u + (uint32_t)k * 2u * a_lbo, a_lbo, 128),
-                              umma_smem_desc(sW1_u + (uint32_t)k * 2u * w1_lbo, w1_lbo, 128), idesc1, k > 0 ? 1u : 0u);
+                    umma_bf16(tmem_d1, umma_desc_at(dA, (uint32_t)k * 2u * a_lbo), umma_desc_at(dW1, (uint32_t)k * 2u * w1_lbo),
+                              idesc1, k > 0 ? 1u : 0u);
             } else {
 #pragma unroll
-                for (int k = 0; k < C / 8; ++k)
-                    umma_step<TERMS>(tmem_d1, sA_u + (uint32_t)k * 2u * a_lbo, a_lbo, TC_ROWS * C * 4,
-                                     sW1_u + (uint32_t)k * 2u * w1_lbo, w1_lbo, (uint32_t)(F * C * 4), idesc1, k == 0);
+                for (int k = 0; k < C / 8; ++k) {
+                    const uint64_t ah = umma_desc_at(dA, (uint32_t)k * 2u * a_lbo), bh = umma_desc_at(dW1, (uint32_t)k * 2u * w1_lbo);
+                    umma_tf32(tmem_d1, ah, bh, idesc1, k > 0 ? 1u : 0u);
+                    if (TERMS == 3) {
+                        umma_tf32(tmem_d1, umma_desc_at(dA, (uint32_t)(TC_ROWS * C * 4) + (uint32_t)k * 2u * a_lbo), bh, idesc1, 1u);
+                        umma_tf32(tmem_d1, ah, umma_desc_at(dW1, (uint32_t)(F * C * 4) + (uint32_t)k * 2u * w1_lbo), idesc1, 1u);
+                    }
+                }
             }
             umma_commit(bar1);
         }
@@ -399,21 +486,20 @@ k_ffn_tc(FfnTcParams P, int n_cap, const int *__restrict__ n_dev, const float *_
         __syncthreads();
         TRACE(6);
         // ---- 4. D2[128 x C] = H[128 x F] . W2^T, H read from TMEM
-        if (tid == 0) {
+        if (issuer_elected()) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if constexpr (BF) {
                 for (int k = 0; k < F / 16; ++k)       // A: 8 packed columns per K = 16 step
-                    umma_bf16_ts(tmem_d2, tmem_hlo + (uint32_t)k * 8u,
-                                 umma_smem_desc(sW2_u + (uint32_t)k * 2u * w2_lbo, w2_lbo, 128), idesc2, k > 0 ? 1u : 0u);
+                    umma_bf16_ts(tmem_d2, tmem_hlo + (uint32_t)k * 8u, umma_desc_at(dW2, (uint32_t)k * 2u * w2_lbo), idesc2,
+                                 k > 0 ? 1u : 0u);
             } else
             for (int k = 0; k < F / 8; ++k) {
-                const uint64_t db = umma_smem_desc(sW2_u + (uint32_t)k * 2u * w2_lbo, w2_lbo, 128);
+                const uint64_t db = umma_desc_at(dW2, (uint32_t)k * 2u * w2_lbo);
                 umma_tf32_ts(tmem_d2, tmem_d1 + (uint32_t)k * 8u, db, idesc2, k > 0 ? 1u : 0u);
                 if (TERMS == 3) {
                     umma_tf32_ts(tmem_d2, tmem_hlo + (uint32_t)k * 8u, db, idesc2, 1u);
                     umma_tf32_ts(tmem_d2, tmem_d1 + (uint32_t)k * 8u,
-                                 umma_smem_desc(sW2_u + (uint32_t)(C * F * 4) + (uint32_t)k * 2u * w2_lbo, w2_lbo, 128),
-                                 idesc2, 1u);
+                                 umma_desc_at(dW2, (uint32_t)(C * F * 4) + (uint32_t)k * 2u * w2_lbo), idesc2, 1u);
                 }
             }
             umma_commit(bar2);
@@ -422,9 +508,9 @@ k_ffn_tc(FfnTcParams P, int n_cap, const int *__restrict__ n_dev, const float *_
         // ---- software pipeline: the next tile's loads run while the second GEMM does (the A tile, which hosts the
         //      staging areas, is free again: the first GEMM is complete, the second reads its A operand from TMEM)
         float un[PIPE ? CH : 1];
-        if (PIPE && next_tile < tiles) {
+        if (next_tile < tiles) {
             index_stage2(ix);
-            load_tile(next_tile, ix, un);
+            if (PIPE) load_tile(next_tile, ix, un);
         }
         tile_row0 = tile * TC_ROWS + (warp & 3) * 32;      // (back to this tile for the stores below)
         mbar_wait(bar2, phase);
@@ -432,16 +518,11 @@ k_ffn_tc(FfnTcParams P, int n_cap, const int *__restrict__ n_dev, const float *_
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         // ---- 5. y = u + D2 + b2 (in place in u), optionally xn_next = LayerNorm_next(y)
         {
-            float d[32];
-            if constexpr (CH == 32) {
-                tmem_ld32(tmem_d2 + lane_off + (uint32_t)(half * 32), d);
+            float d[CH];
+            if constexpr (CH == 32) tmem_ld32(tmem_d2 + lane_off + (uint32_t)(half * 32), d);
+            else tmem_ld16(tmem_d2 + lane_off + (uint32_t)(half * 16), d);
 #pragma unroll
-                for (int i = 0; i < CH; ++i) u[i] += d[i] + s_b2[i];
-            } else {  // C = 32: both threads of a row read all 32 columns and keep their 16
-                tmem_ld32(tmem_d2 + lane_off, d);
-#pragma unroll
-                for (int i = 0; i < CH; ++i) u[i] += (half ? d[CH + i] : d[i]) + s_b2[i];
-            }
+            for (int i = 0; i < CH; ++i) u[i] += d[i] + s_b2[i];
         }
         {
             float4 o[CH / 4];
@@ -453,15 +534,15 @@ k_ffn_tc(FfnTcParams P, int n_cap, const int *__restrict__ n_dev, const float *_
             part = 0.f;
 #pragma unroll
             for (int c = 0; c < CH; ++c) part += u[c];
-            red_mine[4 * TC_ROWS] = part;
+            red_mine[2 * TPR * TC_ROWS] = part;
             __syncthreads();
-            const float m2 = (part + red_other[4 * TC_ROWS]) * (1.0f / C);
+            const float m2 = red_sum(2) * (1.0f / C);
             part = 0.f;
 #pragma unroll
             for (int c = 0; c < CH; ++c) { const float dd = u[c] - m2; part = fmaf(dd, dd, part); }
-            red_mine[6 * TC_ROWS] = part;
+            red_mine[3 * TPR * TC_ROWS] = part;
             __syncthreads();
-            const float r2 = rsqrtf((part + red_other[6 * TC_ROWS]) * (1.0f / C) + P.next_eps);
+            const float r2 = rsqrtf(red_sum(3) * (1.0f / C) + P.next_eps);
             float4 o[CH / 4];
 #pragma unroll
             for (int q = 0; q < CH / 4; ++q)
@@ -475,12 +556,21 @@ k_ffn_tc(FfnTcParams P, int n_cap, const int *__restrict__ n_dev, const float *_
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();  // TMEM and the operand tiles are free for the next tile
         TRACE(10);
+#ifdef MSSVT_TRACE
+        if (tile == (int)blockIdx.x) gt[3] = gtime();
+        gt[4] = gtime();
+        gt[5] += 1;
+#endif
         if (PIPE && next_tile < tiles) {
 #pragma unroll
             for (int c = 0; c < (PIPE ? CH : 1); ++c) u[c] = un[c];
         }
     }
 #ifdef MSSVT_TRACE
+    if (tid == 0 && (blockIdx.x % 41) == 0)
+        printf("ffn cta %3d (sm %2u): entry %llu | prologue +%llu | pdl wait +%llu | first tile +%llu | last tile (%llu) +%llu ns\n",
+               blockIdx.x, [] { unsigned s; asm("mov.u32 %0, %%smid;" : "=r"(s)); return s; }(), gt[0] % 100000000ull,
+               gt[1] - gt[0], gt[2] - gt[0], gt[3] - gt[0], gt[5], gt[4] - gt[0]);
     if (tid == 0 && blockIdx.x == 0 && tr[10])
         printf("ffn tile: load+sum %lld | LN+A+sync %lld | issue1 %lld | wait1 %lld | epi1 %lld | sync %lld | issue2 %lld | wait2 %lld | epi2+store %lld | sync %lld | total %lld clk\n",
                tr[1] - tr[0], tr[2] - tr[1], tr[3] - tr[2], tr[4] - tr[3], tr[5] - tr[4], tr[6] - tr[5], tr[7] - tr[6], tr[8] - tr[7], tr[9] - tr[8], tr[10] - tr[9], tr[10] - tr[0]);
@@ -560,9 +650,17 @@ int mssvt_ffn_tc(int C, int F, int mode, int terms, float eps, const float *ln_g
     if (mode == 2 && (C != 64 || !x || !vox_slot || !meta || !q_base || !nn_idx || !nn_w || !projected || cap1 <= 0))
         return MSSVT_ERR_INVALID;
     const int nt = terms == 3 ? 2 : 1;
-    size_t smem = nt * ((size_t)TC_ROWS * C * 4 + 2 * (size_t)F * C * 4) + (size_t)(5 * C + F + 8 * TC_ROWS) * 4 + 3 * 8 + 16 + 128;
+    // threads per row: four where the shape allows it (16 channels and F / 4 hidden columns per thread)
+    // (measured at 150 k rows: 54 -> 62 us with TF32 operands, 66 -> 70 us with split operands: the tile time is made of
+    //  memory round trips and MMA round trips, not of the per-thread instruction chains -- the default stays two)
+#ifdef FFN_TPR4
+    const int tpr = (C == 64 && (F & 127) == 0) ? 4 : 2;
+#else
+    const int tpr = 2;
+#endif
+    size_t smem = nt * ((size_t)TC_ROWS * C * 4 + 2 * (size_t)F * C * 4) + (size_t)(5 * C + F + 4 * tpr * TC_ROWS) * 4 + 3 * 8 + 16 + 128;
     if (terms == 0)  // bf16 operands: the A region keeps the size of the fp32 staging area, the weights halve
-        smem = (size_t)TC_ROWS * C * 4 + 2 * (size_t)F * C * 2 + (size_t)(5 * C + F + 8 * TC_ROWS) * 4 + 3 * 8 + 16 + 128;
+        smem = (size_t)TC_ROWS * C * 4 + 2 * (size_t)F * C * 2 + (size_t)(5 * C + F + 4 * tpr * TC_ROWS) * 4 + 3 * 8 + 16 + 128;
     if (smem > 227 * 1024) return MSSVT_ERR_INVALID;
     if (xn_next && (!next_ln_g || !next_ln_b)) return MSSVT_ERR_INVALID;
     FfnTcParams P = {F, mode, eps, w1, b1, w2, b2, ln_g, ln_b, next_ln_g, next_ln_b, next_eps,
@@ -573,18 +671,26 @@ int mssvt_ffn_tc(int C, int F, int mode, int terms, float eps, const float *ln_g
     int per_sm = (int)(227 * 1024 / (smem + 1024));
     if (per_sm > 512 / tmem_cols) per_sm = 512 / tmem_cols;
     per_sm = per_sm > 2 ? 2 : per_sm < 1 ? 1 : per_sm;
+#ifdef FFN_MAX_PER_SM   // (occupancy experiments)
+    if (per_sm > FFN_MAX_PER_SM) per_sm = FFN_MAX_PER_SM;
+#endif
     int grid = tiles < MSSVT_NUM_SMS * per_sm ? tiles : MSSVT_NUM_SMS * per_sm;
     ++g_launches;
-#define FFN_TC_LAUNCH(CC, TT)                                                                              \
-    cudaFuncSetAttribute(k_ffn_tc<CC, TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
-    launch_pdl(k_ffn_tc<CC, TT>, dim3(grid), dim3(TC_THREADS), smem, (cudaStream_t)stream, P, num_rows,        \
+#define FFN_TC_LAUNCH(CC, TT, RR)                                                                          \
+    cudaFuncSetAttribute(k_ffn_tc<CC, TT, RR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
+    launch_pdl(k_ffn_tc<CC, TT, RR>, dim3(grid), dim3(TC_ROWS * RR), smem, (cudaStream_t)stream, P, num_rows,  \
                num_rows_dev, x, merged, covered, y, xn_next)
-    if (C == 64 && terms == 0) { FFN_TC_LAUNCH(64, 0); }
-    else if (terms == 0) { FFN_TC_LAUNCH(32, 0); }
-    else if (C == 64 && terms == 3) { FFN_TC_LAUNCH(64, 3); }
-    else if (C == 64) { FFN_TC_LAUNCH(64, 1); }
-    else if (terms == 3) { FFN_TC_LAUNCH(32, 3); }
-    else { FFN_TC_LAUNCH(32, 1); }
+    if (tpr == 4) {
+        if (terms == 0) { FFN_TC_LAUNCH(64, 0, 4); }
+        else if (terms == 3) { FFN_TC_LAUNCH(64, 3, 4); }
+        else { FFN_TC_LAUNCH(64, 1, 4); }
+    }
+    else if (C == 64 && terms == 0) { FFN_TC_LAUNCH(64, 0, 2); }
+    else if (terms == 0) { FFN_TC_LAUNCH(32, 0, 2); }
+    else if (C == 64 && terms == 3) { FFN_TC_LAUNCH(64, 3, 2); }
+    else if (C == 64) { FFN_TC_LAUNCH(64, 1, 2); }
+    else if (terms == 3) { FFN_TC_LAUNCH(32, 3, 2); }
+    else { FFN_TC_LAUNCH(32, 1, 2); }
 #undef FFN_TC_LAUNCH
     return check_launch();
 }

@@ -21,6 +21,22 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t lbo_
     return d;                // base_offset 0, layout_type 0 (SWIZZLE_NONE)
 }
 
+// The same descriptor as (base, byte offset): the base is built once per operand region and kept in two registers,
+// a tile / K chunk inside the region is one 32-bit add on the address field (shared-memory addresses >> 4 fit the
+// 14-bit field with room to spare, so the add never carries out of it).  The issuing thread then spends one uniform
+// add per MMA instead of rebuilding add / shift / mask / or chains in front of every tcgen05.mma.
+struct UmmaDescBase { uint32_t lo, hi; };
+__device__ __forceinline__ UmmaDescBase umma_desc_base(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    UmmaDescBase b;
+    b.lo = ((saddr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+    b.hi = ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14);
+    asm volatile("" : "+r"(b.lo));   // (opaque: the compiler must not re-derive it from the address at every use)
+    return b;
+}
+__device__ __forceinline__ uint64_t umma_desc_at(const UmmaDescBase &b, uint32_t byte_off) {
+    return ((uint64_t)b.hi << 32) | (uint64_t)(b.lo + (byte_off >> 4));
+}
+
 // kind::tf32, fp32 accumulate, both operands K-major
 __host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -294,6 +310,11 @@ __device__ __forceinline__ void stage_packed(const float *__restrict__ packed, i
                      : "memory");
 }
 __device__ __forceinline__ void stage_packed_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// cp.async groups: commit what this thread has issued so far as one group; wait until at most N of its most
+// recent groups are still in flight
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // The same for whole matrices, by the TMA engine: ONE thread posts the expected byte count on an mbarrier and
 // issues one bulk copy global -> shared per matrix (cp.async.bulk, SASS UBLKCP); no thread touches the data,
@@ -323,6 +344,25 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {  /
     __syncwarp();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
 }
+// One lane of a converged warp (elect.sync): the issuing thread of tcgen05.mma / commit.  Used under a warp-uniform
+// condition (`warp_uniform() == 0 && elect_one()`), the compiler keeps the descriptors on the uniform datapath
+// instead of looping over the "possibly different" values of a divergent `tid == 0` branch (R2UR under BRA.U.ANY).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ int warp_uniform() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+// `if (issuer_elected()) { tcgen05.mma ...; tcgen05.commit }`: one lane of warp 0.  (Evaluated at the site: one
+// shuffle, instead of a flag that would have to live in a register across the whole tile loop.)
+__device__ __forceinline__ bool issuer_elected() { return warp_uniform() == 0 && elect_one(); }
+
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }

@@ -113,7 +113,7 @@ k_tc_linear(TclParams P, Producer prod, float *__restrict__ out) {
         stage_packed_wait();
         fence_async_smem();
         __syncthreads();
-        if (tid == 0) {
+        if (issuer_elected()) {
             tc_fence_after();
 #pragma unroll
             for (int k = 0; k < TCL_C / 8; ++k)
