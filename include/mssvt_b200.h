@@ -313,6 +313,13 @@ int mssvt_pack_operand_tf32(const float *w, int n_rows, int k, int terms, float 
  * k % 16 == 0.  mssvt_ffn_tc and mssvt_block_attention_tc take these copies when called with terms = 0. */
 int mssvt_pack_operand_bf16(const float *w, int n_rows, int k, void *packed, void *stream);
 
+/* Self-check of the tensor-map (TMA, cp.async.bulk.tensor) row movement mssvt_ffn_tc uses for its dense row tiles
+ * (mssvt_b200/csrc/tma.cuh): copies a row-major (num_rows, 64) fp32 matrix src -> dst through box loads, swizzled
+ * shared-memory boxes read and re-written by their owning lanes, and box stores; dst == src bit for bit, rows past
+ * num_rows untouched.  (No reference counterpart: the reference moves rows with plain loads / stores.)
+ * MSSVT_ERR_LAUNCH if the driver does not provide cuTensorMapEncodeTiled. */
+int mssvt_tma_copy_rows(const float *src, float *dst, int num_rows, void *stream);
+
 /* The same FFN on the tcgen05 tensor cores: TF32 operands, fp32 accumulation in TMEM, LayerNorm and
  * the residual stream in fp32 (mssvt_b200/csrc/ffn_tc.cu).  w1 [F][C] and w2 [C][F] (nn.Linear layout) packed by
  * mssvt_pack_operand_tf32.  Supported shapes: C in {32, 64}, F % 64 == 0, F + C <= 512; -1 otherwise.

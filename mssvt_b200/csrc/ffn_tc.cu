@@ -22,11 +22,24 @@
 // Precision: TF32 operands (10-bit mantissa, round-to-nearest), fp32 accumulation in TMEM; the
 // residual stream u and the LayerNorm stay fp32.  Selected with precision = "tf32"; the exact
 // FFMA kernel in block.cu stays the default (tests state the tolerance for each).
-#include "tc_common.cuh"
+#include <cstring>
+#include "tma.cuh"
 
 namespace mssvt {
 
 #define TC_ROWS 128
+// Which kernels move their dense row tiles by TMA (tma.cuh).  Measured per launch at 150 k rows, S0:
+//   box STORES of y / the next LayerNorm rows: 51.0 -> 47.0 us (TF32 operands), 47.8 -> 43.4 us (bf16): the rows cross the LSU
+//       data pipe once (STS) instead of three times (STS, LDS, STG) and leave asynchronously; with split operands
+//       (one CTA per SM, loads software-pipelined) 65.3 -> 66.4 us: not used there;
+//   box LOAD of x (mode 2) next to the gathers of the projected rows: 47.1 -> 51.9 us (TF32), 64.8 -> 68.9 us (split):
+//       slower -- x then has to be held in registers next to both gathered row sets (spills), and the load phase is
+//       bound by the gathers, not by x.  Kept selectable (-DFFN_TMA_LOAD), off by default.
+#ifdef FFN_NO_TMA   // (A/B builds: rows through the LDG -> STS -> LDS staging everywhere)
+#define FFN_TMA_SHAPE(C, TPR, TERMS) false
+#else
+#define FFN_TMA_SHAPE(C, TPR, TERMS) ((C) == 64 && (TPR) == 2 && (TERMS) != 3)
+#endif
 #ifdef MSSVT_TRACE
 #define TRACE(i) do { if (tid == 0 && blockIdx.x == 0 && tile == (int)blockIdx.x + (int)gridDim.x) tr[i] = clock64(); } while (0)
 #else
@@ -59,11 +72,12 @@ template <int C, int TERMS, int TPR>
 __global__ void __launch_bounds__(TC_ROWS * TPR, TERMS == 3 ? 1 : 2)
 k_ffn_tc(FfnTcParams P, int n_cap, const int *__restrict__ n_dev, const float *__restrict__ x,
          const float *__restrict__ merged, const unsigned char *__restrict__ covered,
-         float *__restrict__ y, float *__restrict__ xn_next) {
+         float *__restrict__ y, float *__restrict__ xn_next, const __grid_constant__ CUtensorMap tm_x,
+         const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUtensorMap tm_xn) {
     constexpr int TC_THREADS = TC_ROWS * TPR;
     constexpr int CH = C / TPR;  // channels per thread
     static_assert(CH == 32 || CH == 16, "a thread owns 16 or 32 channels of its row");
-    extern __shared__ __align__(128) char smem_raw[];
+    extern __shared__ __align__(1024) char smem_raw[];
 #ifdef MSSVT_TRACE
     unsigned long long gt[8] = {0};   // %globaltimer (ns) timeline of this CTA
     auto gtime = []() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
@@ -82,8 +96,21 @@ k_ffn_tc(FfnTcParams P, int n_cap, const int *__restrict__ n_dev, const float *_
     char *sW2 = sW1 + NT * F * C * EB;            // NT x [chunks][C][16 B]
     float *s_vec = (float *)(sW2 + NT * C * F * EB);   // ln_g[C], ln_b[C], b1[F], b2[C], next_g[C], next_b[C]
     float *s_red = s_vec + 5 * C + F;             // [4][TPR][128] partial row sums of the threads of a row
-    uint64_t *s_bar = (uint64_t *)(s_red + 4 * TPR * TC_ROWS);  // 3 mbarriers (8-byte aligned: C, F even)
-    uint32_t *s_tmem = (uint32_t *)(s_bar + 3);
+    uint64_t *s_bar = (uint64_t *)(s_red + 4 * TPR * TC_ROWS);  // 3 mbarriers (8-byte aligned: C, F even) + one per warp
+    uint32_t *s_tmem = (uint32_t *)(s_bar + 3 + 4 * TPR);        //   (the warp's TMA row loads)
+    // TMA: the dense row tiles (x in mode 2, y, the next LayerNorm rows) move as one box per warp (tma.cuh)
+    constexpr bool TMA = FFN_TMA_SHAPE(C, TPR, TERMS);
+#ifdef FFN_TMA_LOAD
+    constexpr bool TMA_LD = TMA;
+#else
+    constexpr bool TMA_LD = false;
+#endif
+    const uint32_t xbar = smem_u32(s_bar + 3 + warp);
+    uint32_t xphase = 0;
+    if (TMA && (tid & 31) == 0) {
+        mbar_init(xbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     const uint32_t bar_w = smem_u32(s_bar + 2);           // weights landed (TMA bulk copies)
     if (tid == 0) {
         mbar_init(bar_w, 1);
@@ -159,6 +186,9 @@ k_ffn_tc(FfnTcParams P, int n_cap, const int *__restrict__ n_dev, const float *_
                                                  // (one 128-byte wavefront) always hit 8 different 16-byte bank groups
     const int lane = tid & 31;
     char *stg = sA + warp * (32 * CH * 4);
+    // second box of the warp where the A region holds two tiles (split operands: the lo tile): x lands there while the
+    // gathers use `stg`, the next LayerNorm rows leave from there while y leaves from `stg`
+    char *stg2 = TERMS == 3 ? sA + TC_ROWS * C * 4 + warp * (32 * CH * 4) : stg;
     const int st_row = lane / CPR, st_ch = lane % CPR;
     int tile_row0 = 0;  // first row of the warp's 32 rows in the current tile
     auto stage_in = [&](const float *__restrict__ src, float4 *dst) {
@@ -237,6 +267,18 @@ k_ffn_tc(FfnTcParams P, int n_cap, const int *__restrict__ n_dev, const float *_
         for (int q = 0; q < CPR; ++q) db[q] = *(const float4 *)(stg + lane * (CH * 4) + ((q ^ ((lane >> SWS) & (CPR - 1))) << 4));
         __syncwarp();
     };
+    // the warp's 32 part-rows leave as one TMA box from `from` (the rows are written with the box swizzle)
+    auto box_out = [&](const CUtensorMap *map, char *from, const float4 *src) {
+#pragma unroll
+        for (int q = 0; q < CPR; ++q) *(float4 *)(from + tma_swz(lane, q)) = src[q];
+        fence_async_smem();
+        __syncwarp();
+        if (elect_one()) {
+            tma_store_box(map, half * CH, tile_row0, from);
+            tma_store_commit();
+        }
+        __syncwarp();
+    };
     auto stage_out = [&](float *__restrict__ dst, const float4 *src) {
 #pragma unroll
         for (int q = 0; q < CPR; ++q) *(float4 *)(stg + lane * (CH * 4) + ((q ^ ((lane >> SWS) & (CPR - 1))) << 4)) = src[q];
@@ -310,6 +352,10 @@ k_ffn_tc(FfnTcParams P, int n_cap, const int *__restrict__ n_dev, const float *_
         const int row = tile * TC_ROWS + r;
         const bool live = row < n;
         tile_row0 = tile * TC_ROWS + (warp & 3) * 32;
+        if (TMA) {   // the boxes of the previous tile's stores have been read out of the staging regions
+            tma_store_wait_read();
+            __syncwarp();
+        }
         {
             float4 mv[CH / 4];
             bool cov = ix.cov;
@@ -320,6 +366,56 @@ k_ffn_tc(FfnTcParams P, int n_cap, const int *__restrict__ n_dev, const float *_
                     const float *p0 = ix.p0, *p1 = ix.p1, *p2 = ix.p2;
                     const float w0 = ix.w0, w1 = ix.w1, w2 = ix.w2;
                     float4 v[CPR];
+                    if (TMA_LD) {
+                        // x: one box load into the warp's region, in flight together with the gathers of p0 / p1
+                        if (elect_one()) {
+                            bulk_expect(xbar, TMA_BOX_BYTES);
+                            tma_load_box(stg2, &tm_x, half * CH, tile_row0, xbar);
+                        }
+                        __syncwarp();
+                        float4 va[CPR], vb[CPR], xv[CPR];
+#pragma unroll
+                        for (int i = 0; i < CPR; ++i) {
+                            const float4 *pa = (const float4 *)__shfl_sync(0xffffffffu, (unsigned long long)p0, RPI * i + st_row);
+                            va[i] = pa ? __ldg(pa + st_ch) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+#pragma unroll
+                        for (int i = 0; i < CPR; ++i) {
+                            const float4 *pb = (const float4 *)__shfl_sync(0xffffffffu, (unsigned long long)p1, RPI * i + st_row);
+                            vb[i] = pb ? __ldg(pb + st_ch) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                        mbar_wait(xbar, xphase);
+                        xphase ^= 1u;
+#pragma unroll
+                        for (int q = 0; q < CPR; ++q) xv[q] = *(const float4 *)(stg2 + tma_swz(lane, q));
+                        __syncwarp();
+#pragma unroll
+                        for (int i = 0; i < CPR; ++i) *(float4 *)(stg + tma_swz(RPI * i + st_row, st_ch)) = va[i];
+                        __syncwarp();
+#pragma unroll
+                        for (int q = 0; q < CPR; ++q) mv[q] = *(const float4 *)(stg + tma_swz(lane, q));
+                        __syncwarp();
+#pragma unroll
+                        for (int i = 0; i < CPR; ++i) *(float4 *)(stg + tma_swz(RPI * i + st_row, st_ch)) = vb[i];
+                        __syncwarp();
+#pragma unroll
+                        for (int q = 0; q < CPR; ++q) v[q] = *(const float4 *)(stg + tma_swz(lane, q));
+                        __syncwarp();
+#pragma unroll
+                        for (int q = 0; q < CPR; ++q)
+                            mv[q] = make_float4(__fadd_rn(__fmul_rn(mv[q].x, w0), __fmul_rn(v[q].x, w1)), __fadd_rn(__fmul_rn(mv[q].y, w0), __fmul_rn(v[q].y, w1)),
+                                                __fadd_rn(__fmul_rn(mv[q].z, w0), __fmul_rn(v[q].z, w1)), __fadd_rn(__fmul_rn(mv[q].w, w0), __fmul_rn(v[q].w, w1)));
+                        gather_in(p2, v);
+#pragma unroll
+                        for (int c = 0; c < CPR; ++c) {
+                            const float4 xx = xv[c];
+                            float4 m = make_float4(__fadd_rn(mv[c].x, __fmul_rn(v[c].x, w2)), __fadd_rn(mv[c].y, __fmul_rn(v[c].y, w2)),
+                                                   __fadd_rn(mv[c].z, __fmul_rn(v[c].z, w2)), __fadd_rn(mv[c].w, __fmul_rn(v[c].w, w2)));
+                            if (!cov) m = xx;
+                            u[4 * c] = m.x + xx.x; u[4 * c + 1] = m.y + xx.y; u[4 * c + 2] = m.z + xx.z; u[4 * c + 3] = m.w + xx.w;
+                        }
+                        return;
+                    }
                     gather_in2(p0, mv, p1, nullptr, v);
 #pragma unroll
                     for (int q = 0; q < CPR; ++q)
@@ -387,6 +483,7 @@ k_ffn_tc(FfnTcParams P, int n_cap, const int *__restrict__ n_dev, const float *_
             }
         }
         // ---- 1. LayerNorm of u, A operand
+        if (TMA) tma_store_wait_read();   // (the A tiles host the boxes of the previous tile's stores; barriers follow)
         float part = 0.f;
 #pragma unroll
         for (int c = 0; c < CH; ++c) part += u[c];
@@ -528,7 +625,8 @@ k_ffn_tc(FfnTcParams P, int n_cap, const int *__restrict__ n_dev, const float *_
             float4 o[CH / 4];
 #pragma unroll
             for (int q = 0; q < CH / 4; ++q) o[q] = make_float4(u[4 * q], u[4 * q + 1], u[4 * q + 2], u[4 * q + 3]);
-            stage_out(y, o);
+            if (TMA) box_out(&tm_y, stg, o);
+            else stage_out(y, o);
         }
         if (xn_next) {  // (uniform over the CTA)
             part = 0.f;
@@ -550,7 +648,15 @@ k_ffn_tc(FfnTcParams P, int n_cap, const int *__restrict__ n_dev, const float *_
                                    (u[4 * q + 1] - m2) * r2 * s_ng[4 * q + 1] + s_nb[4 * q + 1],
                                    (u[4 * q + 2] - m2) * r2 * s_ng[4 * q + 2] + s_nb[4 * q + 2],
                                    (u[4 * q + 3] - m2) * r2 * s_ng[4 * q + 3] + s_nb[4 * q + 3]);
-            stage_out(xn_next, o);
+            if (TMA) {
+                if (TERMS != 3) {   // one box per warp: y's box has been read out of it by now
+                    tma_store_wait_read();
+                    __syncwarp();
+                }
+                box_out(&tm_xn, stg2, o);
+            } else {
+                stage_out(xn_next, o);
+            }
         }
         TRACE(9);
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -575,6 +681,7 @@ k_ffn_tc(FfnTcParams P, int n_cap, const int *__restrict__ n_dev, const float *_
         printf("ffn tile: load+sum %lld | LN+A+sync %lld | issue1 %lld | wait1 %lld | epi1 %lld | sync %lld | issue2 %lld | wait2 %lld | epi2+store %lld | sync %lld | total %lld clk\n",
                tr[1] - tr[0], tr[2] - tr[1], tr[3] - tr[2], tr[4] - tr[3], tr[5] - tr[4], tr[6] - tr[5], tr[7] - tr[6], tr[8] - tr[7], tr[9] - tr[8], tr[10] - tr[9], tr[10] - tr[0]);
 #endif
+    if (TMA) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the last tile's rows are on their way out
     if (warp == 0) tmem_dealloc(tmem_base, tmem_cols);
 }
 
@@ -603,11 +710,71 @@ __global__ void k_pack_operand_bf16(const float *__restrict__ src, int n_rows, i
     *(uint4 *)at = make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
 }
 
+// Self-check of the tensor-map row movement the FFN relies on: (rows, 64) fp32 src -> dst through TMA box loads,
+// per-lane reads / writes of the swizzled boxes and TMA box stores, with the FFN's own thread -> row mapping.
+__global__ void __launch_bounds__(256)
+k_tma_copy_rows(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ CUtensorMap dst_map, int rows) {
+    extern __shared__ __align__(1024) char smem_raw[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    char *box = smem_raw + warp * TMA_BOX_BYTES;
+    uint64_t *bars = (uint64_t *)(smem_raw + 8 * TMA_BOX_BYTES);
+    const uint32_t bar = smem_u32(bars + warp);
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    uint32_t phase = 0;
+    const int tiles = (rows + TC_ROWS - 1) / TC_ROWS;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, phase ^= 1u) {
+        const int row0 = tile * TC_ROWS + (warp & 3) * 32, col0 = (warp >> 2) * 32;
+        tma_store_wait_read();
+        __syncwarp();
+        if (elect_one()) {
+            bulk_expect(bar, TMA_BOX_BYTES);
+            tma_load_box(box, &src_map, col0, row0, bar);
+        }
+        __syncwarp();
+        mbar_wait(bar, phase);
+        float4 v[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) v[c] = *(const float4 *)(box + tma_swz(lane, c));
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 8; ++c) *(float4 *)(box + tma_swz(lane, c)) = v[c];
+        fence_async_smem();
+        __syncwarp();
+        if (elect_one()) {
+            tma_store_box(&dst_map, col0, row0, box);
+            tma_store_commit();
+        }
+        __syncwarp();
+    }
+    tma_store_wait_read();
+}
+
 }  // namespace mssvt
 
 using namespace mssvt;
 
 extern "C" {
+
+// Copies a row-major (num_rows, 64) fp32 matrix through the tensor-map (TMA) row movement of the tensor-core FFN:
+// box loads, swizzled shared-memory boxes read and written by the owning lanes, box stores.  A self-check of that
+// plumbing (driver entry point, tensor maps, swizzle, bounds clipping of the last tile); dst == src bit for bit.
+int mssvt_tma_copy_rows(const float *src, float *dst, int num_rows, void *stream) {
+    if (!src || !dst || num_rows < 0) return MSSVT_ERR_INVALID;
+    if (num_rows == 0) return MSSVT_OK;
+    CUtensorMap ms, md;
+    if (!tma_rows_map(&ms, src, num_rows, 64) || !tma_rows_map(&md, dst, num_rows, 64)) return MSSVT_ERR_LAUNCH;
+    const int tiles = (num_rows + TC_ROWS - 1) / TC_ROWS;
+    const int grid = tiles < MSSVT_NUM_SMS * 4 ? tiles : MSSVT_NUM_SMS * 4;
+    const size_t smem = 8 * TMA_BOX_BYTES + 64;
+    cudaFuncSetAttribute(k_tma_copy_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    ++g_launches;
+    k_tma_copy_rows<<<grid, 256, smem, (cudaStream_t)stream>>>(ms, md, num_rows);
+    return check_launch();
+}
 
 // The bf16 form of mssvt_pack_operand_tf32 (precision mode "bf16", tcgen05.mma.kind::f16): packed holds
 // n_rows * k bf16 (2 bytes each).  n_rows % 8 == 0, k % 16 == 0.
@@ -658,13 +825,19 @@ int mssvt_ffn_tc(int C, int F, int mode, int terms, float eps, const float *ln_g
 #else
     const int tpr = 2;
 #endif
-    size_t smem = nt * ((size_t)TC_ROWS * C * 4 + 2 * (size_t)F * C * 4) + (size_t)(5 * C + F + 4 * tpr * TC_ROWS) * 4 + 3 * 8 + 16 + 128;
+    size_t smem = nt * ((size_t)TC_ROWS * C * 4 + 2 * (size_t)F * C * 4) + (size_t)(5 * C + F + 4 * tpr * TC_ROWS) * 4 + (3 + 4 * tpr) * 8 + 16 + 128;
     if (terms == 0)  // bf16 operands: the A region keeps the size of the fp32 staging area, the weights halve
-        smem = (size_t)TC_ROWS * C * 4 + 2 * (size_t)F * C * 2 + (size_t)(5 * C + F + 4 * tpr * TC_ROWS) * 4 + 3 * 8 + 16 + 128;
+        smem = (size_t)TC_ROWS * C * 4 + 2 * (size_t)F * C * 2 + (size_t)(5 * C + F + 4 * tpr * TC_ROWS) * 4 + (3 + 4 * tpr) * 8 + 16 + 128;
     if (smem > 227 * 1024) return MSSVT_ERR_INVALID;
     if (xn_next && (!next_ln_g || !next_ln_b)) return MSSVT_ERR_INVALID;
     FfnTcParams P = {F, mode, eps, w1, b1, w2, b2, ln_g, ln_b, next_ln_g, next_ln_b, next_eps,
                      vox_slot, meta, q_base, nn_idx, nn_w, projected, cap1};
+    // dense row tiles by TMA (tma.cuh): tensor maps over the capacity rows of x (mode 2), y and the next LayerNorm rows
+    CUtensorMap tm_x, tm_y, tm_xn;
+    memset(&tm_x, 0, sizeof(tm_x)); memset(&tm_y, 0, sizeof(tm_y)); memset(&tm_xn, 0, sizeof(tm_xn));
+    if (FFN_TMA_SHAPE(C, tpr, terms) && !(tma_rows_map(&tm_y, y, num_rows, C) && (mode != 2 || tma_rows_map(&tm_x, x, num_rows, C)) &&
+                                   (!xn_next || tma_rows_map(&tm_xn, xn_next, num_rows, C))))
+        return MSSVT_ERR_LAUNCH;   // (no cuTensorMapEncodeTiled in this driver, or a misaligned buffer)
     int tiles = (num_rows + TC_ROWS - 1) / TC_ROWS;
     int tmem_cols = 32;
     while (tmem_cols < F + C + (terms == 3 ? F : terms == 0 ? F / 2 : 0)) tmem_cols <<= 1;
@@ -679,7 +852,7 @@ int mssvt_ffn_tc(int C, int F, int mode, int terms, float eps, const float *ln_g
 #define FFN_TC_LAUNCH(CC, TT, RR)                                                                          \
     cudaFuncSetAttribute(k_ffn_tc<CC, TT, RR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
     launch_pdl(k_ffn_tc<CC, TT, RR>, dim3(grid), dim3(TC_ROWS * RR), smem, (cudaStream_t)stream, P, num_rows,  \
-               num_rows_dev, x, merged, covered, y, xn_next)
+               num_rows_dev, x, merged, covered, y, xn_next, tm_x, tm_y, tm_xn)
     if (tpr == 4) {
         if (terms == 0) { FFN_TC_LAUNCH(64, 0, 4); }
         else if (terms == 3) { FFN_TC_LAUNCH(64, 3, 4); }

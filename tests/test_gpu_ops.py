@@ -297,3 +297,19 @@ def test_attention_tile_plan_invariants():
     cell = torch.tensor([S0_VOXEL[i] * 3 for i in range(3)])
     want = (g["win_list"][:W].cpu()[:, [3, 2, 1]].float() + 0.5) * cell + torch.tensor(S0_RANGE[:3])
     assert torch.allclose(win_ctr[:W, :3], want, atol=1e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rows", [1, 31, 128, 1000, 150001])
+def test_tma_copy_rows(rows):
+    """tensor-map row movement of the tensor-core FFN (tma.cuh): box loads / swizzled boxes / box stores copy a
+    (rows, 64) matrix bit for bit and never write past the last row (partial tiles are clipped by the tensor map)"""
+    import torch
+    from mssvt_b200._lib import call, ptr, stream
+    torch.manual_seed(rows)
+    src = torch.randn(rows, 64, device="cuda")
+    dst = torch.full((rows + 40, 64), -7.0, device="cuda")
+    call("mssvt_tma_copy_rows", ptr(src), ptr(dst), rows, stream())
+    torch.cuda.synchronize()
+    assert torch.equal(dst[:rows], src)
+    assert bool((dst[rows:] == -7.0).all())
