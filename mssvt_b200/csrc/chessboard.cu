@@ -242,12 +242,15 @@ __device__ __forceinline__ void fps_list(const int *s_off, int cnt, int n, int l
 
 // three nearest of nq known points (padding sits at the origin, quirk Q4) for one win1 voxel, and the normalised
 // 1/d weights: three_nn_kernel_fast (interpolate_gpu.cu:16-59) + mssvt_backbone.py:305-307
-__device__ __forceinline__ void three_nn_slot(float ux, float uy, float uz, const float *s_known, int nq,
+// nreal: the first nreal known points are real, the rest is padding.  All padded points coincide, and ties keep the
+// earlier index (strict <), so at most the first three of them can ever enter the result: the scan stops there.
+__device__ __forceinline__ void three_nn_slot(float ux, float uy, float uz, const float *s_known, int nq, int nreal,
                                               unsigned char *oi, float *ow) {
     const float INF = __int_as_float(0x7f800000);
     float b1 = INF, b2 = INF, b3 = INF;
     int i1 = 0, i2 = 0, i3 = 0;
-    for (int k = 0; k < nq; ++k) {
+    const int kmax = min(nq, nreal + 3);
+    for (int k = 0; k < kmax; ++k) {
         float dx = __fsub_rn(ux, s_known[3 * k]);
         float dy = __fsub_rn(uy, s_known[3 * k + 1]);
         float dz = __fsub_rn(uz, s_known[3 * k + 2]);
@@ -383,7 +386,7 @@ k_block_geometry(GeoParams P, TablePtrs tabs, int win_cap, const int *__restrict
                 }
                 int p = s_off[list_at[2] + i];
                 three_nn_slot(world_coord(cx + off_x(p), P.cell[0], P.lo[0]), world_coord(cy + off_y(p), P.cell[1], P.lo[1]),
-                              world_coord(cz + off_z(p), P.cell[2], P.lo[2]), s_known, nq, oi, ow);
+                              world_coord(cz + off_z(p), P.cell[2], P.lo[2]), s_known, nq, cnt[qL], oi, ow);
             }
         }
         __syncwarp();
@@ -434,7 +437,7 @@ k_block_queries(int nq, int cap1, int interp, int win_cap, const int *__restrict
                     continue;
                 }
                 three_nn_slot(__ldg(xyz + 3 * (size_t)row), __ldg(xyz + 3 * (size_t)row + 1), __ldg(xyz + 3 * (size_t)row + 2),
-                              s_known, nq, oi, ow);
+                              s_known, nq, nqr, oi, ow);
             }
         }
         __syncwarp();

@@ -34,6 +34,10 @@ __global__ void k_fill_i32x4(int4 *__restrict__ p, size_t n16, int *__restrict__
 // fill `count` int32 with `value`; p must be 16-byte aligned (torch allocations are).
 int fill_i32(int *p, size_t count, int value, cudaStream_t s) {
     if (count == 0) return MSSVT_OK;
+    if (value == 0 || value == -1) {   // a byte pattern: a memset node instead of a kernel
+        if (cudaMemsetAsync(p, value == 0 ? 0 : 0xff, count * sizeof(int), s) != cudaSuccess) return MSSVT_ERR_LAUNCH;
+        return MSSVT_OK;
+    }
     size_t n16 = count / 4;
     int ntail = (int)(count % 4);
     int grid = persistent_grid((long long)(n16 ? n16 : 1), 256, 8);

@@ -13,6 +13,7 @@ with no host synchronisation; a compress block synchronises once to size its out
 Inference only for now: training needs the backward kernels.
 """
 import ctypes
+import warnings
 
 import numpy as np
 import torch
@@ -24,6 +25,22 @@ from .mssvt_utils import MixedScaleAttention, SparseTensor, sample_counts
 
 
 TC_MODES = ("tf32", "tf32x3", "bf16")     # precision modes that run on the tcgen05 kernels
+_FFMA_WARNED = set()
+
+
+def _warn_ffma(module, what, ok):
+    """One warning per (module class, kernel) when a tensor-core precision mode is asked for but the shape is
+    outside the tcgen05 kernels' family: the exact FFMA kernel runs instead (same results, ~5x slower)."""
+    if ok or module.precision not in TC_MODES:
+        return ok
+    key = (type(module).__name__, what)
+    if key not in _FFMA_WARNED:
+        _FFMA_WARNED.add(key)
+        warnings.warn("mssvt_b200: %s of %s is outside the shape family of the tcgen05 kernels (C = 64, 2 x 32-channel head "
+                      "groups / one-group compress block, see DESIGN.md section 9): precision mode '%s' runs the exact "
+                      "fp32 FFMA kernel for it (about 5x slower)" % (what, key[0], module.precision), RuntimeWarning,
+                      stacklevel=3)
+    return ok
 
 
 class DropPath(nn.Module):
@@ -369,10 +386,11 @@ class MixedScaleSparseTransformerBlock(nn.Module):
     def _tc_supported(self, nq):
         """shape family of the tensor-core window attention (mssvt_block_attention_tc)"""
         a = self.ms_attn
-        return (self.precision in TC_MODES and self.in_channels == 64 and a.scale_dims == [32, 32]
-                and a.num_heads[0] == a.num_heads[1] and a.num_heads[0] in (1, 2, 4) and nq <= 32
-                and self.key_num_sample <= 63 and self.max_num_win1 <= 128 and len(self.pos_proj) == 2
-                and nq * (self.key_num_sample + 1) * a.num_heads[0] <= 2048)
+        return _warn_ffma(self, "the window attention", (
+            self.precision in TC_MODES and self.in_channels == 64 and a.scale_dims == [32, 32]
+            and a.num_heads[0] == a.num_heads[1] and a.num_heads[0] in (1, 2, 4) and nq <= 32
+            and self.key_num_sample <= 63 and self.max_num_win1 <= 128 and len(self.pos_proj) == 2
+            and nq * (self.key_num_sample + 1) * a.num_heads[0] <= 2048))
 
     def prepare(self, sp_tensor):
         """Coordinate-only part of the block (window list, chessboard / FPS geometry, tile plan); cached on
@@ -511,9 +529,10 @@ class MixedScaleSparseTransformerBlock(nn.Module):
 
     def _ffn_tc_supported(self, S):
         t = self._terms()
-        return (self.precision in TC_MODES and S.C_out == 0 and S.C in (32, 64) and S.F % 64 == 0
-                and S.F * (2 if t == 3 else 1) + S.C + (S.F // 2 if t == 0 else 0) <= 512     # TMEM columns
-                and (128 * S.C + 2 * S.F * S.C) * 4 * (2 if t == 3 else 1) < 220 * 1024)      # shared memory
+        return _warn_ffma(self, "the FFN", (
+            self.precision in TC_MODES and S.C_out == 0 and S.C in (32, 64) and S.F % 64 == 0
+            and S.F * (2 if t == 3 else 1) + S.C + (S.F // 2 if t == 0 else 0) <= 512     # TMEM columns
+            and (128 * S.C + 2 * S.F * S.C) * 4 * (2 if t == 3 else 1) < 220 * 1024))     # shared memory
 
     def _ffn(self, S, buf, n_rows, x, merged, covered, n_dev=None, merge_src=None):
         """merge_src = (vox_slot, meta, q_base, nn_idx, nn_w, projected rows, cap1): the interpolation + merge
@@ -634,8 +653,9 @@ class MixedScaleSparseTransformerCompressBlock(MixedScaleSparseTransformerBlock)
 
     def _tc_supported(self):
         a = self.ms_attn
-        return (self.precision in TC_MODES and self.in_channels == 64 and a.num_head_groups == 1
-                and a.num_heads[0] in (2, 4, 8) and len(self.pos_proj) == 4 and self.max_num_win1 <= 127)
+        return _warn_ffma(self, "the compress attention", (
+            self.precision in TC_MODES and self.in_channels == 64 and a.num_head_groups == 1
+            and a.num_heads[0] in (2, 4, 8) and len(self.pos_proj) == 4 and self.max_num_win1 <= 127))
 
     def prepare(self, sp_tensor):
         """Coordinate-only part of the block: pillar window list, window rows, tile plan.  Cached on the

@@ -420,3 +420,19 @@ def test_backbone_bf16_mode_within_stated_tolerance(name):
                        "batch_size": int(blob["batch_size"])})["encoded_spconv_tensor"].features.cpu()
     assert (other - ref).abs().max().item() < err      # TF32 is closer to the fp32 reference than bf16
     print("bf16 %s: max %.2e rms %.2e of max|ref|" % (name, err / scale, rms / scale))
+
+
+def test_shape_outside_the_tensor_core_family_warns():
+    """a tensor-core precision mode on a shape the tcgen05 kernels do not cover runs the FFMA kernels (same results)
+    and says so -- once per kind of kernel -- instead of silently being five times slower"""
+    import mssvt_b200.mssvt_backbone as mb
+    blob, cfg, state = load_golden("mixed_b3_n500")     # (two-group compress block, capped lists, out_linear ...)
+    cfg["PRECISION"] = "tf32x3"
+    mb._FFMA_WARNED.clear()
+    feats, coords = torch.from_numpy(blob["voxel_features"]), torch.from_numpy(blob["voxel_coords"])
+    with pytest.warns(RuntimeWarning, match="outside the shape family of the tcgen05 kernels"):
+        run_product(cfg, state, blob["grid"], blob["pc_range"], feats, coords, int(blob["batch_size"]))
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("error", RuntimeWarning)     # the second forward stays quiet
+        run_product(cfg, state, blob["grid"], blob["pc_range"], feats, coords, int(blob["batch_size"]))
