@@ -173,30 +173,6 @@ __device__ __forceinline__ float ex2_fast(float x) {
     return y;
 }
 
-// 8 lanes per 128-byte slice: the warp copies the 128-byte slices (at `base`, row pitch TCA_C floats) of the
-// feature rows of its 32 lanes (my_row: this lane's row, < 0 = none) asynchronously into its 4 KB staging area
-// (16-byte chunks XOR-swizzled by the row).  Straight-line code: the eight row ids are shuffled first, the
-// copies are predicated (a branch per copy serialised shuffle -> compare -> branch -> copy eight times).
-__device__ __forceinline__ void warp_rows_copy_async(char *stg, const float *base, int my_row) {
-    const int lane = threadIdx.x & 31, st_row = lane >> 3, st_ch = lane & 7;
-    const uint32_t dst = smem_u32(stg);
-    int rows[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) rows[i] = __shfl_sync(0xffffffffu, my_row, 4 * i + st_row);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int rr = 4 * i + st_row;
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "setp.ge.s32 p, %2, 0;\n\t"
-            "@p cp.async.cg.shared.global [%0], [%1], 16;\n\t"
-            "}\n" ::"r"(dst + (uint32_t)(rr * 128 + ((st_ch ^ (rr & 7)) << 4))),
-            "l"(base + (size_t)max(rows[i], 0) * TCA_C + st_ch * 4), "r"(rows[i])
-            : "memory");
-    }
-}
-
 // Software pipeline over the tiles of a CTA.  Two things are pipelined ACROSS tiles:
 //   * the loads of a tile form a chain of dependent global accesses (tile record -> window records -> row ids
 //     -> coordinates + feature rows, ~3 L2 latencies); every link of tile i + 1 is issued one phase of tile i

@@ -1,22 +1,24 @@
-// compress_tc.cu -- attention of the one-window (compress) block, task-parallel, with the second
-// positional-embedding layer and the K/V projection on the tcgen05 tensor cores (sm_100a).
-// Same mathematics as k_compress_attention in attention.cu
+// compress_tc.cu -- attention of the one-window (compress) block as a tile kernel on the tcgen05 tensor cores
+// (sm_100a).  Same mathematics as k_compress_attention in attention.cu
 // (MixedScaleSparseTransformerCompressBlock.forward, mssvt_backbone.py:361-383):
 //
-//   k_tc_linear   (tc_linear.cuh) q = (Wq pooled + bq) * scale, on tcgen05
 //   k_tcc_plan    #real slots per window, tiles of <= 128 key tasks, window centres
 //   k_tcc_pool    channel-wise max over the window's rows (zero padding included)
-//   k_tcc_keys    task = key of a window: one per voxel + one "pad key" per window that has padded
-//                 slots (all padded slots carry the same key: zero feature, offset 0 - centre, mask -100,
-//                 multiplicity = #padded slots).  128 keys per tile:
-//                   A1 = relu(pos layer 1)               -> 8 x tcgen05.mma  D1 = A1 W2^T        (N = 64)
-//                   A2 = xn + relu(D1 + b2)              -> 8 x tcgen05.mma  D2 = A2 Wkv^T       (N = 128)
-//                 K|V come back per thread through tcgen05.ld; scores against the window's query,
-//                 then softmax + AV with one thread per (window, head, quarter head).
+//   k_tc_linear   (tc_linear.cuh) q = (Wq pooled + bq) * scale, on tcgen05
+//   k_tcc_tile    task = key of a window: one per voxel + one "pad key" per window that has padded slots (all padded
+//                 slots carry the same key: zero feature, offset 0 - centre, mask -100, multiplicity = #padded slots).
+//                 128 tasks per tile, three chained tcgen05 GEMMs with every A operand in TMEM:
+//                   pos [128 x 8]                         -> MMA 0 (K = 8):  first positional layer        (N = 64)
+//                   A1 = relu(D0)             (in place)  -> MMA 1:          D1 = A1 W2^T                  (N = 64)
+//                   A2 = xn + relu(D1 + b2)   (in place)  -> MMA 2:          K | V = A2 Wkv^T              (N = 128)
+//                 K | V come back per thread through tcgen05.ld; scores against the window's query, then softmax + AV
+//                 with one thread per (window, head, quarter head).  Loads of the next tile software-pipelined under
+//                 the current one; tile groups share the CTA's weights (see the kernel).
 //   k_tc_linear   output projection -> one row per window, on tcgen05
 //
 // Supported shape: C = 64, one head group (2, 4 or 8 heads), two-layer pos_proj, max_num_win1 <= 127.
-// Everything else runs on k_compress_attention.  TF32 operands for the two tensor-core GEMMs only.
+// Everything else runs on k_compress_attention.  TF32 (or split 3xTF32) operands for the GEMMs; the bf16 mode uses
+// the TF32 kernel here.
 #include "tc_linear.cuh"
 
 namespace mssvt {
@@ -27,6 +29,8 @@ namespace mssvt {
 #define TCC_PLAN_WB 128  // windows planned by one warp
 #define TCC_C 64
 #define TCC_VPITCH 68    // V row pitch in floats (16-byte aligned, conflict-free for quarter warps)
+#define TCC_HDR_CTR (2 * TCC_TW * 4)                 // header: records [TW] int (+ pad), then centres [TW] float4
+#define TCC_HDR_BYTES (TCC_HDR_CTR + TCC_TW * 16)
 
 struct TccParams {
     int n1, heads;
@@ -122,196 +126,302 @@ k_tcc_pool(int n1, int win_cap, const int *__restrict__ win_count_total, const i
 
 // ------------------------------------------------------------------------------- keys + attention
 
-// largest l in [0, n) with off[l] <= v (off[n] > v)
-__device__ __forceinline__ int tcc_tile_window(const int *off, int n, int v) {
-    int lo = 0, hi = n;
-    while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (off[mid] <= v) lo = mid; else hi = mid;
+// shared-memory carve-up of k_tcc_tile (bytes).  Common to the CTA: the weights; per tile group: operands, rows, header
+struct TccSmem {
+    int wpos, w2, wkv, bias, group0, group_bytes, apos, rows, hdr, bar, total;
+    __host__ __device__ TccSmem(int nt, int heads, int groups) {
+        wpos = 0;                                     // [hi | lo] x [2 chunks][64][16 B]                          4 KB
+        w2 = wpos + 4096;                             // nt x [16 chunks][64][16 B]                         16 KB each
+        wkv = w2 + nt * 64 * 64 * 4;                  // nt x [16 chunks][128][16 B]                        32 KB each
+        bias = wkv + nt * 128 * 64 * 4;               // b2 [64], bkv [128]
+        group0 = bias + (64 + 128) * 4;
+        apos = 0;                                     // [hi | lo] x [2 chunks][128][16 B]; later the scores       8 KB
+        rows = apos + 8192;                           // gather staging [8 warps][32 rows][128 B], later V [128][VPITCH]
+        hdr = rows + TCC_ROWS * TCC_VPITCH * 4;       // 2 x {cnt [TW], toff [TW + 1], ctr [TW] float4}
+        bar = hdr + 2 * TCC_HDR_BYTES;                // mbarrier of the group
+        group_bytes = (bar + 16 + 127) & ~127;
+        (void)heads;
+        total = group0 + groups * group_bytes + 16;   // + TMEM base
     }
-    return lo;
-}
+};
 
-// 256 threads per tile of 128 key tasks: threads t and t + 128 share task row t = TMEM lane t and own one
-// half of the channels / of the heads each (HEADS >= 2)
-template <int HEADS, int TERMS>
-__global__ void __launch_bounds__(TCC_THREADS, TERMS == 3 ? 1 : 2)
-k_tcc_keys(TccParams P, const int2 *__restrict__ tiles, const int *__restrict__ tile_count,
+// One tile = 128 key tasks of consecutive pillar windows: one per voxel + one "pad key" per window that has padded
+// slots.  A tile GROUP of 256 threads owns a tile: threads t and t + 128 share task row t = TMEM lane t and own one
+// half of the channels / heads each.  A CTA hosts G groups that share one copy of the weights and run their tile loops
+// independently (named barriers): G = 1 and two CTAs per SM with TF32 operands, G = 2 and one CTA per SM with split
+// operands (the doubled weight tiles then leave room for one copy per SM only).  Per tile, four chained GEMMs with M = 128:
+//   1. pos = [offset to the window centre | centre | 1 | 0] (8 values, hi / lo) -> shared memory;  MMA 0 (K = 8, always
+//      3xTF32): the first positional layer of all rows -> TMEM [0, 64)
+//   2. tcgen05.ld, ReLU, rounded, tcgen05.st IN PLACE: the A operand of MMA 1 = second positional layer (W2, N = 64)
+//      -> TMEM [128, 192)
+//   3. A2 = xn + relu(D1 + b2) -> TMEM [0, 64) (+ lo [64, 128)): the A operand of MMA 2 = K | V projection (N = 128)
+//      -> TMEM [128, 256)
+//   4. K | V back per thread; scores against the window's (single, max-pooled) query; softmax over the window's keys with
+//      the multiplicity of the pad key; AV with one thread per (window, head, quarter head) -> one row per window.
+// No operand ever sits in shared memory except the 8-wide positional input; the loads of tile i + 1 (window records ->
+// row ids -> coordinates + feature rows) are issued a phase ahead of their use under tile i, and MMA 0 of tile i + 1 is
+// issued at the end of tile i.
+template <int HEADS, int TERMS, int G>
+__global__ void __launch_bounds__(256 * G, G == 1 ? 2 : 1)
+k_tcc_tile(TccParams P, const int2 *__restrict__ tiles, const int *__restrict__ tile_count,
            const int *__restrict__ win_rec, const float4 *__restrict__ win_ctr, const float *__restrict__ xn,
            const float *__restrict__ xyz, const int *__restrict__ k_row, const float *__restrict__ Qc,
            float *__restrict__ Oc) {
     constexpr int HD = TCC_C / HEADS;
     constexpr int DPT = HD / 4;
     constexpr int HH = HEADS / 2;  // heads per thread
+    constexpr int NT = TERMS == 3 ? 2 : 1;
     pdl_launch_dependents();
     extern __shared__ __align__(128) char smem_raw[];
-    const int tid = threadIdx.x, warp = tid >> 5;
-    const int r = tid & (TCC_ROWS - 1), half = tid >> 7;
+    const int tid = threadIdx.x, grp = tid >> 8, gtid = tid & 255;
+    const int gw = (tid >> 5) & 7;                 // warp within the group
+    const int r = gtid & (TCC_ROWS - 1), half = gtid >> 7, lane = tid & 31;
     const int n1 = P.n1;
+    const TccSmem L(NT, HEADS, G);
+    char *sWpos = smem_raw + L.wpos, *sW2 = smem_raw + L.w2, *sWkv = smem_raw + L.wkv;
+    float *sB2 = (float *)(smem_raw + L.bias), *sBkv = sB2 + 64;
+    char *gbase = smem_raw + L.group0 + grp * L.group_bytes;
+    char *sApos = gbase + L.apos, *sRows = gbase + L.rows, *sHdr = gbase + L.hdr;
+    float *sS = (float *)sApos;                    // [128][HEADS] scores (the positional operand is consumed by then)
+    float *sV = (float *)sRows;                    // [128][VPITCH]
+    uint64_t *sBar = (uint64_t *)(gbase + L.bar);
+    uint32_t *sTmem = (uint32_t *)(smem_raw + L.group0 + G * L.group_bytes);
+    char *stg = sRows + gw * 4096;                 // this warp's staging area (32 half rows of 128 bytes)
+    const uint32_t group_barrier = 1u + (uint32_t)grp;
+    auto group_sync = [&]() { asm volatile("bar.sync %0, 256;" ::"r"(group_barrier) : "memory"); };
 
-    constexpr int NT = TERMS == 3 ? 2 : 1;                  // operand tiles: hi [, lo] (3xTF32, tc_common.cuh)
-    constexpr int A_TILE = TCC_ROWS * TCC_C * 4;            // 32 KB
-    constexpr int A_REGION = NT * A_TILE > TCC_ROWS * TCC_VPITCH * 4 ? NT * A_TILE : TCC_ROWS * TCC_VPITCH * 4;
-    char *sW2 = smem_raw;                                   // NT x [64 x 64] canonical TF32    16 KB each
-    char *sWkv = sW2 + NT * 64 * 64 * 4;                    // NT x [128 x 64] canonical TF32   32 KB each
-    char *sA = sWkv + NT * 128 * 64 * 4;                    // NT x [128 x 64] canonical (32 KB each) ...
-    float *sV = (float *)sA;                                // ... reused as V [128][VPITCH] (34 KB)
-    float *sPos = (float *)(sA + A_REGION);                 // [64][8]
-    float *sB2 = sPos + 64 * 8;                             // [64]
-    float *sBkv = sB2 + 64;                                 // [128]
-    float *sS = sBkv + 128;                                 // [128][HEADS] scores
-    float4 *sCtr = (float4 *)(sS + TCC_ROWS * HEADS);       // [TW] window centres
-    int *sCnt = (int *)(sCtr + TCC_TW);                     // [TW] real keys per window
-    int *sToff = sCnt + TCC_TW;                             // [TW + 1] first key task of each window (+ end)
-    uint64_t *sBar = (uint64_t *)(sToff + TCC_TW + 2);
-    uint32_t *sTmem = (uint32_t *)(sBar + 1);
-
+    // ---- weights (static parameters: before the dependency wait)
     stage_packed(P.pos2_w, NT * 64 * 64, sW2);
     stage_packed(P.wkv, NT * 128 * 64, sWkv);
-    for (int i = tid; i < 64 * 8; i += TCC_THREADS) {
-        const int c = i >> 3, k = i & 7;
-        sPos[i] = k < 6 ? __ldg(P.pos_w + c * 6 + k) : k == 6 ? __ldg(P.pos_b + c) : 0.f;
+    for (int i = tid; i < 128; i += 256 * G) {   // first positional layer [64][8] = [pos_w | pos_b | 0], hi / lo, canonical
+        const int n = i & 63, ch = i >> 6;
+        float4 w, hi, lo;
+        if (ch == 0) w = make_float4(__ldg(P.pos_w + n * 6), __ldg(P.pos_w + n * 6 + 1), __ldg(P.pos_w + n * 6 + 2), __ldg(P.pos_w + n * 6 + 3));
+        else w = make_float4(__ldg(P.pos_w + n * 6 + 4), __ldg(P.pos_w + n * 6 + 5), __ldg(P.pos_b + n), 0.f);
+        split_tf32(w, hi, lo);
+        *(float4 *)(sWpos + ch * 1024 + n * 16) = hi;
+        *(float4 *)(sWpos + 2048 + ch * 1024 + n * 16) = lo;
     }
     if (tid < 64) sB2[tid] = __ldg(P.pos2_b + tid);
     if (tid < 128) sBkv[tid] = __ldg(P.bkv + tid);
     const uint32_t bar = smem_u32(sBar);
-    if (tid == 0) {
+    if (gtid == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0) tmem_alloc(smem_u32(sTmem), 256);
+    if (tid < 32) tmem_alloc(smem_u32(sTmem), 256 * G);
+    stage_packed_wait();
+    fence_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *sTmem;
-    const uint32_t tmem_d1 = tmem_base, tmem_d2 = tmem_base + 64u;  // D1: 64 columns, D2: 128 columns
-    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
-    const uint32_t idesc1 = umma_idesc_tf32(128, 64), idesc2 = umma_idesc_tf32(128, 128);
-    const uint32_t sA_u = smem_u32(sA), sW2_u = smem_u32(sW2), sWkv_u = smem_u32(sWkv);
-    const uint32_t a_lbo = TCC_ROWS * 16, w2_lbo = 64 * 16, wkv_lbo = 128 * 16;
-    const uint32_t my_row_off = (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u;
+    const uint32_t tb = *sTmem + (uint32_t)(grp * 256);
+    const uint32_t tm_a = tb, tm_alo = tb + 64u, tm_d = tb + 128u;   // A hi / A lo (split operands) / D1, then K | V
+    const uint32_t lane_off = (uint32_t)((gw & 3) * 32) << 16;
+    const uint32_t id_n64 = umma_idesc_tf32(128, 64), id_n128 = umma_idesc_tf32(128, 128);
+    const UmmaDescBase dWpos = umma_desc_base(smem_u32(sWpos), 1024, 128), dApos = umma_desc_base(smem_u32(sApos), 2048, 128),
+                       dW2 = umma_desc_base(smem_u32(sW2), 64 * 16, 128), dWkv = umma_desc_base(smem_u32(sWkv), 128 * 16, 128);
+    const uint32_t row_off = (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u;   // canonical 8-row groups
     uint32_t phase = 0;
     pdl_wait();  // (everything above touched static parameters only)
     const int T = __ldg(tile_count);
+    const int first = blockIdx.x * G + grp, stride = gridDim.x * G;
 
-    for (int t = blockIdx.x; t < T; t += gridDim.x) {
-        const int2 tl = __ldg(tiles + t);
-        const int nwin = tl.y;
-        if (tid < nwin) {
-            const int rec = __ldg(win_rec + tl.x + tid);
-            const int cnt = rec & 0xff;
-            sCnt[tid] = cnt;
-            sToff[tid] = rec >> 8;
-            sCtr[tid] = __ldg(win_ctr + tl.x + tid);
-            if (tid == nwin - 1) sToff[nwin] = (rec >> 8) + cnt + (cnt < n1 ? 1 : 0);
+    // header of a tile (per window: #real keys, first key task, centre) -> buffer `buf`, asynchronously
+    auto header_async = [&](int2 tl, int buf) {
+        char *h = sHdr + buf * TCC_HDR_BYTES;
+        if (gtid < tl.y) {
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(h + gtid * 4)), "l"(win_rec + tl.x + gtid) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(h + TCC_HDR_CTR + gtid * 16)), "l"(win_ctr + tl.x + gtid) : "memory");
         }
-        __syncthreads();
-        const int nT = sToff[nwin];
-        // the windows' query rows are read after the second MMA: pull them into L1 now
-        if (tid < 2 * nwin)
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(Qc + (size_t)tl.x * TCC_C + (size_t)tid * 32));
-
-        // ---- A1 = relu(pos layer 1 (offset to the window centre, centre)), this thread's 32 channels
-        const bool is_task = r < nT;
-        int l = 0, row = -1;
-        bool pad = false;
-        float rx = 0.f, ry = 0.f, rz = 0.f;
-        float4 ctr = make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    // role of this thread's task row in a tile whose header has landed: window l, key j, pad key?; -> feature row (issued load)
+    auto role = [&](int2 tl, const char *h, int &l, int &row, bool &is_task, bool &pad) {
+        const int *rec = (const int *)h;
+        // (records: cnt | first task << 8; the window of a task by binary search over the first tasks)
+        int lo = 0, hi = tl.y;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if ((rec[mid] >> 8) <= r) lo = mid; else hi = mid;
+        }
+        l = lo;
+        const int last = rec[tl.y - 1], cl = last & 0xff;
+        const int nT = (last >> 8) + cl + (cl < n1 ? 1 : 0);
+        is_task = r < nT;
+        const int j = r - (rec[l] >> 8);
+        pad = j >= (rec[l] & 0xff);
+        row = -1;
+        if (is_task && !pad) row = __ldg(k_row + (size_t)(tl.x + l) * n1 + j);
+    };
+    // positional input of this thread's row -> the A operand of MMA 0 (one writer per row: half 0)
+    auto pos_operand = [&](const char *h, int l, bool is_task, float x, float y, float z) {
+        if (half) return;
+        float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1 = p0;
         if (is_task) {
-            l = tcc_tile_window(sToff, nwin, r);
-            const int j = r - sToff[l];
-            pad = j >= sCnt[l];
-            ctr = sCtr[l];
-            float px = 0.f, py = 0.f, pz = 0.f;  // padded slots: grouped coordinate 0 -> offset 0 - centre
-            if (!pad) {
-                row = __ldg(k_row + (size_t)(tl.x + l) * n1 + j);
-                px = __ldg(xyz + 3 * (size_t)row); py = __ldg(xyz + 3 * (size_t)row + 1);
-                pz = __ldg(xyz + 3 * (size_t)row + 2);
-            }
-            rx = __fsub_rn(px, ctr.x); ry = __fsub_rn(py, ctr.y); rz = __fsub_rn(pz, ctr.z);
+            const float4 ctr = ((const float4 *)(h + TCC_HDR_CTR))[l];
+            // (padded slots: grouped coordinate 0 -> offset 0 - centre, quirk Q6: x = y = z = 0 for the pad key)
+            p0 = make_float4(__fsub_rn(x, ctr.x), __fsub_rn(y, ctr.y), __fsub_rn(z, ctr.z), ctr.x);
+            p1 = make_float4(ctr.y, ctr.z, 1.f, 0.f);
         }
-        // the feature rows (needed after the first MMA) are gathered now, 8 lanes per 128-byte half row,
-        // through the A tile's memory (pad key: zero feature)
-        float4 f[8];
-        warp_rows_load(sA + warp * 4096, is_task && !pad ? (const float4 *)(xn + (size_t)row * TCC_C + 32 * half) : nullptr, f);
-        __syncthreads();  // every warp is done with its staging area: the A tile may be written
-        if (is_task) {
-#pragma unroll 4
-            for (int c4 = 0; c4 < 8; ++c4) {
-                float o[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const float4 wa = *(const float4 *)(sPos + (32 * half + 4 * c4 + k) * 8);
-                    const float4 wb = *(const float4 *)(sPos + (32 * half + 4 * c4 + k) * 8 + 4);
-                    float a = wb.z;
-                    a = fmaf(wa.x, rx, a); a = fmaf(wa.y, ry, a); a = fmaf(wa.z, rz, a);
-                    a = fmaf(wa.w, ctr.x, a); a = fmaf(wb.x, ctr.y, a); a = fmaf(wb.y, ctr.z, a);
-                    o[k] = fmaxf(a, 0.f);
-                }
-                float4 hi, lo;
-                split_tf32(make_float4(o[0], o[1], o[2], o[3]), hi, lo);
-                *(float4 *)(sA + (uint32_t)(8 * half + c4) * a_lbo + my_row_off) = hi;
-                if (TERMS == 3) *(float4 *)(sA + A_TILE + (uint32_t)(8 * half + c4) * a_lbo + my_row_off) = lo;
-            }
-        }
-        stage_packed_wait();
-        fence_async_smem();
-        __syncthreads();
-        if (issuer_elected()) {  // D1 = A1 W2^T
+        float4 hi, lo;
+        split_tf32(p0, hi, lo);
+        *(float4 *)(sApos + row_off) = hi;
+        *(float4 *)(sApos + 4096 + row_off) = lo;
+        split_tf32(p1, hi, lo);
+        *(float4 *)(sApos + 2048 + row_off) = hi;
+        *(float4 *)(sApos + 4096 + 2048 + row_off) = lo;
+    };
+    auto issue_pos = [&]() {   // MMA 0 of the tile whose positional operand was just built
+        if (((warp_uniform() & 7) == 0) && elect_one()) {
             tc_fence_after();
-#pragma unroll
-            for (int k = 0; k < TCC_C / 8; ++k)
-                umma_step<TERMS>(tmem_d1, sA_u + (uint32_t)k * 2u * a_lbo, a_lbo, A_TILE,
-                                 sW2_u + (uint32_t)k * 2u * w2_lbo, w2_lbo, 64 * 64 * 4, idesc1, k == 0);
+            const uint64_t ah = umma_desc_at(dApos, 0u), al = umma_desc_at(dApos, 4096u);
+            const uint64_t wh = umma_desc_at(dWpos, 0u), wl = umma_desc_at(dWpos, 2048u);
+            umma_tf32(tm_a, ah, wh, id_n64, 0u);
+            umma_tf32(tm_a, al, wh, id_n64, 1u);
+            umma_tf32(tm_a, ah, wl, id_n64, 1u);
             umma_commit(bar);
         }
-        mbar_wait(bar, phase);
-        phase ^= 1u;
-        tc_fence_after();
-        // ---- A2 = xn + relu(D1 + b2)
-        {
-            float d[32];
-            tmem_ld32(tmem_d1 + lane_off + (uint32_t)(32 * half), d);
-            if (is_task) {
-                const float *b2 = sB2 + 32 * half;
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    float4 v, hi, lo;
-                    v.x = f[q].x + fmaxf(d[4 * q] + b2[4 * q], 0.f);
-                    v.y = f[q].y + fmaxf(d[4 * q + 1] + b2[4 * q + 1], 0.f);
-                    v.z = f[q].z + fmaxf(d[4 * q + 2] + b2[4 * q + 2], 0.f);
-                    v.w = f[q].w + fmaxf(d[4 * q + 3] + b2[4 * q + 3], 0.f);
-                    split_tf32(v, hi, lo);
-                    *(float4 *)(sA + (uint32_t)(8 * half + q) * a_lbo + my_row_off) = hi;
-                    if (TERMS == 3) *(float4 *)(sA + A_TILE + (uint32_t)(8 * half + q) * a_lbo + my_row_off) = lo;
-                }
-            }
-        }
+        __syncwarp();
+    };
+
+    int2 tl = first < T ? __ldg(tiles + first) : make_int2(0, 0);
+    int2 tl_next = first + stride < T ? __ldg(tiles + first + stride) : make_int2(0, 0);
+    int l = 0, row = -1;
+    bool is_task = false, pad = false;
+    if (first < T) {   // pipeline prologue: header, role, coordinates, feature rows, positional operand, MMA 0 of the first tile
+        header_async(tl, 0);
+        stage_packed_wait();
+        group_sync();
+        role(tl, sHdr, l, row, is_task, pad);
+        float px = 0.f, py = 0.f, pz = 0.f;
+        if (row >= 0) { px = __ldg(xyz + 3 * (size_t)row); py = __ldg(xyz + 3 * (size_t)row + 1); pz = __ldg(xyz + 3 * (size_t)row + 2); }
+        warp_rows_copy_async(stg, xn + 32 * half, row);
+        cp_async_commit();
+        pos_operand(sHdr, l, is_task, px, py, pz);
         fence_async_smem();
         tc_fence_before();
-        __syncthreads();
-        if (issuer_elected()) {  // D2 = A2 Wkv^T
+        group_sync();
+        issue_pos();
+    }
+    int buf = 0;
+    for (int t = first; t < T; t += stride, buf ^= 1) {
+        const char *hdr = sHdr + buf * TCC_HDR_BYTES, *hdr_next = sHdr + (buf ^ 1) * TCC_HDR_BYTES;
+        const int *sRec = (const int *)hdr;
+        const int nwin = tl.y;
+        const bool more = t + stride < T;
+        if (more) header_async(tl_next, buf ^ 1);   // the next tile's window records: on their way now
+        cp_async_commit();
+        const int2 tl_after = t + 2 * stride < T ? __ldg(tiles + t + 2 * stride) : make_int2(0, 0);
+        // the windows' query rows are read after the last MMA: pull them into L1 now
+        if (gtid < 2 * nwin) prefetch_l1(Qc + (size_t)tl.x * TCC_C + (size_t)gtid * 32);
+        // the warp's 32 half rows (copied by its own lanes at the end of the previous tile) have landed
+        float4 f[8];
+        cp_async_wait_group<1>();
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            f[q] = row >= 0 ? *(const float4 *)(stg + lane * 128 + ((q ^ (lane & 7)) << 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        mbar_wait(bar, phase);   // MMA 0 of this tile
+        phase ^= 1u;
+        tc_fence_after();
+        {
+            // ---- 2. A1 = relu(first positional layer), written back over the accumulator: the A operand of MMA 1
+            float d[32];
+            tmem_ld32(tm_a + lane_off + (uint32_t)(32 * half), d);
+            if (TERMS == 3) {
+                float lo[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) split_tf32(fmaxf(d[i], 0.f), d[i], lo[i]);
+                tmem_st32(tm_alo + lane_off + (uint32_t)(32 * half), lo);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) d[i] = to_tf32(fmaxf(d[i], 0.f));
+            }
+            tmem_st32(tm_a + lane_off + (uint32_t)(32 * half), d);
+            tmem_st_wait();
+        }
+        cp_async_wait_group<0>();   // this thread's part of the next header
+        tc_fence_before();
+        group_sync();               // (also: the next header is visible to the group)
+        if (((warp_uniform() & 7) == 0) && elect_one()) {   // D1 = A1 W2^T -> [128, 192)
             tc_fence_after();
 #pragma unroll
-            for (int k = 0; k < TCC_C / 8; ++k)
-                umma_step<TERMS>(tmem_d2, sA_u + (uint32_t)k * 2u * a_lbo, a_lbo, A_TILE,
-                                 sWkv_u + (uint32_t)k * 2u * wkv_lbo, wkv_lbo, 128 * 64 * 4, idesc2, k == 0);
+            for (int k = 0; k < TCC_C / 8; ++k) {
+                const uint64_t wh = umma_desc_at(dW2, (uint32_t)k * 2u * 64u * 16u);
+                umma_tf32_ts(tm_d, tm_a + (uint32_t)k * 8u, wh, id_n64, k > 0 ? 1u : 0u);
+                if (TERMS == 3) {
+                    umma_tf32_ts(tm_d, tm_alo + (uint32_t)k * 8u, wh, id_n64, 1u);
+                    umma_tf32_ts(tm_d, tm_a + (uint32_t)k * 8u, umma_desc_at(dW2, 64u * 64u * 4u + (uint32_t)k * 2u * 64u * 16u), id_n64, 1u);
+                }
+            }
             umma_commit(bar);
         }
+        __syncwarp();
+        // while the MMA runs: role and feature row id of this thread in the NEXT tile
+        int n_l = 0, n_row = -1;
+        bool n_task = false, n_pad = false;
+        if (more) role(tl_next, hdr_next, n_l, n_row, n_task, n_pad);
         mbar_wait(bar, phase);
         phase ^= 1u;
         tc_fence_after();
-        // ---- scores of this thread's heads against the window's query (K = columns 0..63 of D2),
-        //      V = columns 64..127
+        {
+            // ---- 3. A2 = xn + relu(D1 + b2): the A operand of MMA 2
+            float d[32];
+            tmem_ld32(tm_d + lane_off + (uint32_t)(32 * half), d);
+            const float *b2 = sB2 + 32 * half;
+            if (TERMS == 3) {
+                float lo[32];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    split_tf32(f[q].x + fmaxf(d[4 * q] + b2[4 * q], 0.f), d[4 * q], lo[4 * q]);
+                    split_tf32(f[q].y + fmaxf(d[4 * q + 1] + b2[4 * q + 1], 0.f), d[4 * q + 1], lo[4 * q + 1]);
+                    split_tf32(f[q].z + fmaxf(d[4 * q + 2] + b2[4 * q + 2], 0.f), d[4 * q + 2], lo[4 * q + 2]);
+                    split_tf32(f[q].w + fmaxf(d[4 * q + 3] + b2[4 * q + 3], 0.f), d[4 * q + 3], lo[4 * q + 3]);
+                }
+                tmem_st32(tm_alo + lane_off + (uint32_t)(32 * half), lo);
+            } else {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    d[4 * q] = to_tf32(f[q].x + fmaxf(d[4 * q] + b2[4 * q], 0.f));
+                    d[4 * q + 1] = to_tf32(f[q].y + fmaxf(d[4 * q + 1] + b2[4 * q + 1], 0.f));
+                    d[4 * q + 2] = to_tf32(f[q].z + fmaxf(d[4 * q + 2] + b2[4 * q + 2], 0.f));
+                    d[4 * q + 3] = to_tf32(f[q].w + fmaxf(d[4 * q + 3] + b2[4 * q + 3], 0.f));
+                }
+            }
+            tmem_st32(tm_a + lane_off + (uint32_t)(32 * half), d);
+            tmem_st_wait();
+        }
+        tc_fence_before();
+        group_sync();
+        if (((warp_uniform() & 7) == 0) && elect_one()) {   // K | V = A2 Wkv^T -> [128, 256)
+            tc_fence_after();
+#pragma unroll
+            for (int k = 0; k < TCC_C / 8; ++k) {
+                const uint64_t wh = umma_desc_at(dWkv, (uint32_t)k * 2u * 128u * 16u);
+                umma_tf32_ts(tm_d, tm_a + (uint32_t)k * 8u, wh, id_n128, k > 0 ? 1u : 0u);
+                if (TERMS == 3) {
+                    umma_tf32_ts(tm_d, tm_alo + (uint32_t)k * 8u, wh, id_n128, 1u);
+                    umma_tf32_ts(tm_d, tm_a + (uint32_t)k * 8u, umma_desc_at(dWkv, 128u * 64u * 4u + (uint32_t)k * 2u * 128u * 16u), id_n128, 1u);
+                }
+            }
+            umma_commit(bar);
+        }
+        __syncwarp();
+        // the next tile's coordinates: on their way during the last MMA (the row id was loaded a phase ago)
+        float nx = 0.f, ny = 0.f, nz = 0.f;
+        asm volatile("" : "+r"(n_row));
+        if (n_row >= 0) { nx = __ldg(xyz + 3 * (size_t)n_row); ny = __ldg(xyz + 3 * (size_t)n_row + 1); nz = __ldg(xyz + 3 * (size_t)n_row + 2); }
+        mbar_wait(bar, phase);
+        phase ^= 1u;
+        tc_fence_after();
+        // ---- 4. scores of this thread's heads against the window's query (K = columns 0..63 of D2), V = columns 64..127
         {
             float sc[HH];
 #pragma unroll
             for (int h = 0; h < HH; ++h) sc[h] = 0.f;
             float d[32], vv[32];
-            tmem_ld32(tmem_d2 + lane_off + (uint32_t)(32 * half), d);
-            tmem_ld32(tmem_d2 + lane_off + 64u + (uint32_t)(32 * half), vv);
-            tc_fence_before();
-            __syncthreads();  // all K|V are in registers: the A tile may become V
+            tmem_ld32(tm_d + lane_off + (uint32_t)(32 * half), d);
+            tmem_ld32(tm_d + lane_off + 64u + (uint32_t)(32 * half), vv);
             if (is_task) {
                 const float4 *qv = (const float4 *)(Qc + (size_t)(tl.x + l) * TCC_C + 32 * half);
                 // (biases: the K bias shifts all scores of the query equally -> cancelled by the softmax;
@@ -333,11 +443,12 @@ k_tcc_keys(TccParams P, const int2 *__restrict__ tiles, const int *__restrict__ 
                         make_float4(vv[4 * c4], vv[4 * c4 + 1], vv[4 * c4 + 2], vv[4 * c4 + 3]);
             }
         }
-        __syncthreads();
+        tc_fence_before();
+        group_sync();
         // ---- softmax over the window's keys and AV, thread = (window, head, quarter of the head)
-        for (int e = tid; e < nwin * HEADS * 4; e += TCC_THREADS) {
+        for (int e = gtid; e < nwin * HEADS * 4; e += 256) {
             const int dq = e & 3, lh = e >> 2, h = lh % HEADS, lw = lh / HEADS;
-            const int t0 = sToff[lw], cnt = sCnt[lw];
+            const int rec = sRec[lw], t0 = rec >> 8, cnt = rec & 0xff;
             const int nk = cnt + (cnt < n1 ? 1 : 0);
             const float *sc = sS + t0 * HEADS + h;
             float mx = -3.0e38f;
@@ -359,19 +470,27 @@ k_tcc_keys(TccParams P, const int2 *__restrict__ tiles, const int *__restrict__ 
 #pragma unroll
             for (int d = 0; d < DPT; ++d) dst[d] = fmaf(acc[d], inv, bv[d]);
         }
-        __syncthreads();
+        group_sync();   // scores and V rows are consumed: their memory takes the next tile's operands
+        if (more) {
+            warp_rows_copy_async(stg, xn + 32 * half, n_row);
+            pos_operand(hdr_next, n_l, n_task, nx, ny, nz);
+        }
+        cp_async_commit();
+        fence_async_smem();
+        tc_fence_before();
+        group_sync();
+        if (more) issue_pos();
+        l = n_l; row = n_row; is_task = n_task; pad = n_pad;
+        tl = tl_next; tl_next = tl_after;
     }
+    stage_packed_wait();
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem_base, 256);
+    if (tid < 32) tmem_dealloc(*sTmem, 256 * G);
 }
 
-static size_t tcc_keys_smem_bytes(int heads, int terms) {
-    const size_t nt = terms == 3 ? 2 : 1;
-    size_t a_region = nt * TCC_ROWS * TCC_C * 4;
-    if (a_region < (size_t)TCC_ROWS * TCC_VPITCH * 4) a_region = (size_t)TCC_ROWS * TCC_VPITCH * 4;
-    return nt * (64 * 64 * 4 + 128 * 64 * 4) + a_region + (size_t)(64 * 8 + 64 + 128 + TCC_ROWS * heads) * 4 +
-           TCC_TW * 16 + (2 * TCC_TW + 2) * 4 + 8 + 16 + 128;
+static size_t tcc_tile_smem_bytes(int heads, int terms, int groups) {
+    return (size_t)TccSmem(terms == 3 ? 2 : 1, heads, groups).total + 128;
 }
 
 }  // namespace mssvt
@@ -443,23 +562,24 @@ int mssvt_compress_attention_tc(int C, int heads, int n1, int terms, float scale
         tcl_launch(L, rows, win_capacity, Qc, s, terms);
     }
 
-    const size_t smem = tcc_keys_smem_bytes(heads, terms);
+    // TF32 operands: one tile group per CTA, two CTAs per SM; split operands: two groups share the CTA's weights
+    const int groups = terms == 3 ? 2 : 1;
+    const size_t smem = tcc_tile_smem_bytes(heads, terms, groups);
     if (smem > 227 * 1024) return MSSVT_ERR_INVALID;
-    const int per_sm = smem <= 110 * 1024 ? 2 : 1;  // 2 x 256 TMEM columns = all 512
-    const int grid = MSSVT_NUM_SMS * per_sm;
+    const int grid = MSSVT_NUM_SMS * (groups == 1 ? 2 : 1);
     ++g_launches;
-#define TCC_LAUNCH(H, T)                                                                                  \
-    cudaFuncSetAttribute(k_tcc_keys<H, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
-    launch_pdl(k_tcc_keys<H, T>, dim3(grid), dim3(TCC_THREADS), smem, s, P, tiles, tile_count, win_rec, win_ctr, xn, \
+#define TCC_LAUNCH(H, T, GG)                                                                               \
+    cudaFuncSetAttribute(k_tcc_tile<H, T, GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
+    launch_pdl(k_tcc_tile<H, T, GG>, dim3(grid), dim3(256 * GG), smem, s, P, tiles, tile_count, win_rec, win_ctr, xn, \
                xyz, k_row, (const float *)Qc, Oc)
     if (terms == 3) {
-        if (heads == 2) { TCC_LAUNCH(2, 3); }
-        else if (heads == 4) { TCC_LAUNCH(4, 3); }
-        else { TCC_LAUNCH(8, 3); }
+        if (heads == 2) { TCC_LAUNCH(2, 3, 2); }
+        else if (heads == 4) { TCC_LAUNCH(4, 3, 2); }
+        else { TCC_LAUNCH(8, 3, 2); }
     } else {
-        if (heads == 2) { TCC_LAUNCH(2, 1); }
-        else if (heads == 4) { TCC_LAUNCH(4, 1); }
-        else { TCC_LAUNCH(8, 1); }
+        if (heads == 2) { TCC_LAUNCH(2, 1, 1); }
+        else if (heads == 4) { TCC_LAUNCH(4, 1, 1); }
+        else { TCC_LAUNCH(8, 1, 1); }
     }
 #undef TCC_LAUNCH
 

@@ -274,6 +274,30 @@ __device__ __forceinline__ void warp_rows_store(char *stg, float4 *my_dst, const
     __syncwarp();
 }
 
+// 8 lanes per 128-byte slice: the warp copies the 128-byte slices (at `base`, row pitch 64 floats) of the
+// feature rows of its 32 lanes (my_row: this lane's row, < 0 = none) asynchronously into its 4 KB staging area
+// (16-byte chunks XOR-swizzled by the row).  Straight-line code: the eight row ids are shuffled first, the
+// copies are predicated (a branch per copy serialised shuffle -> compare -> branch -> copy eight times).
+__device__ __forceinline__ void warp_rows_copy_async(char *stg, const float *base, int my_row) {
+    const int lane = threadIdx.x & 31, st_row = lane >> 3, st_ch = lane & 7;
+    const uint32_t dst = smem_u32(stg);
+    int rows[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) rows[i] = __shfl_sync(0xffffffffu, my_row, 4 * i + st_row);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int rr = 4 * i + st_row;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.ge.s32 p, %2, 0;\n\t"
+            "@p cp.async.cg.shared.global [%0], [%1], 16;\n\t"
+            "}\n" ::"r"(dst + (uint32_t)(rr * 128 + ((st_ch ^ (rr & 7)) << 4))),
+            "l"(base + (size_t)max(rows[i], 0) * 64 + st_ch * 4), "r"(rows[i])
+            : "memory");
+    }
+}
+
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // ---- "3xTF32": a = a_hi + a_lo with a_hi = tf32(a), a_lo = tf32(a - a_hi) (and the same for the weights);
