@@ -156,7 +156,14 @@ k_scan_emit(int n_cap, const int *__restrict__ n_dev, const int *__restrict__ sr
     if (blockIdx.x * 1024 > n) return;  // (the block holding index n still writes the total)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int part = 0;
-    for (int b = threadIdx.x; b < (int)blockIdx.x; b += 1024) part += block_sums[b];
+    if (block_sums) {
+        for (int b = threadIdx.x; b < (int)blockIdx.x; b += 1024) part += block_sums[b];
+    } else {
+        // single pass: the block sums everything in front of it itself (b independent loads per thread; the lists this
+        // scans are 10^4..10^5 long, so the last block reads ~100 elements per thread out of L2 -- cheaper than a second
+        // kernel in the serial coordinate prefix of a frame)
+        for (int j = threadIdx.x; j < (int)blockIdx.x * 1024; j += 1024) part += __ldg(src + (size_t)j * stride);
+    }
     part = __reduce_add_sync(0xffffffffu, part);
     if (lane == 0) s_warp[warp] = part;
     __syncthreads();
@@ -640,6 +647,11 @@ int mssvt_exclusive_scan(int n_cap, const int *n_dev, const int *src, int stride
     if (n_cap < 0 || stride <= 0 || !dst || !workspace || (n_cap && !src)) return MSSVT_ERR_INVALID;
     cudaStream_t s = (cudaStream_t)stream;
     const int blocks = div_up((long long)n_cap + 1, 1024);
+    if (n_cap <= 262144) {   // one pass: every block sums what precedes it itself (see k_scan_emit)
+        ++g_launches;
+        k_scan_emit<<<blocks, 1024, 0, s>>>(n_cap, n_dev, src, stride, nullptr, dst);
+        return check_launch();
+    }
     ++g_launches;
     k_scan_block_sums<<<blocks, 1024, 0, s>>>(n_cap, n_dev, src, stride, workspace);
     ++g_launches;

@@ -313,3 +313,21 @@ def test_tma_copy_rows(rows):
     torch.cuda.synchronize()
     assert torch.equal(dst[:rows], src)
     assert bool((dst[rows:] == -7.0).all())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cap,n,stride", [(1, 1, 1), (5000, 3777, 4), (150000, 39031, 4), (262144, 262144, 1), (300000, 299999, 2)])
+def test_exclusive_scan(cap, n, stride):
+    """mssvt_exclusive_scan, single-pass form (lists up to 262144) and two-pass form: dst[i] = sum of src[j * stride], j < i,
+    for i in [0, n] with the count read on the device"""
+    import torch
+    from mssvt_b200._lib import call, ptr, stream
+    g = torch.Generator().manual_seed(cap)
+    src = torch.randint(0, 13, (cap, stride), generator=g, dtype=torch.int32).cuda()
+    n_dev = torch.tensor([n], dtype=torch.int32, device="cuda")
+    dst = torch.full((cap + 1,), -1, dtype=torch.int32, device="cuda")
+    ws = torch.empty((cap + 1 + 1023) // 1024 + 1, dtype=torch.int32, device="cuda")
+    call("mssvt_exclusive_scan", cap, ptr(n_dev), ptr(src), stride, ptr(dst), ptr(ws), stream())
+    want = torch.zeros(n + 1, dtype=torch.int64)
+    want[1:] = torch.cumsum(src[:n, 0].cpu().long(), 0)
+    assert torch.equal(dst[:n + 1].cpu().long(), want)
