@@ -329,13 +329,60 @@ k_block_geometry(GeoParams P, TablePtrs tabs, int win_cap, const int *__restrict
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
             const int L = 2 + s, n = g.cap[L];
+            if (!out.k_row) {
+                // Only the SET of distinct keys is asked for (rep_row / meta: what the tensor-core attention reads).  FPS
+                // keeps picking while some slot is at a positive distance from the picks, i.e. until every distinct
+                // position has been picked: the real voxels (different cells) and, if the list has padded slots and no
+                // real voxel sits at offset 0, the one position all padded slots share (a key aliased to the sample's
+                // first voxel, quirk Q1).  With at most K distinct positions the set is known without running FPS --
+                // always for the 3^3 lists, for nearly all 5^3 lists; the K - #distinct remaining picks are index 0 =
+                // the masked key.  Keys are listed in list order instead of pick order (a softmax over a set).
+                const int c = cnt[L];
+                int ic = -1;   // the real slot at offset 0 (at most one), -1: none
+                for (int i0 = 0; i0 < c; i0 += 32) {
+                    const int i = i0 + lane;
+                    const unsigned m = __ballot_sync(0xffffffffu, i < c && s_off[list_at[L] + i] == 0);
+                    if (m) ic = i0 + __ffs(m) - 1;
+                }
+                // The padded position and a real voxel at offset 0 coincide: they always carry the same distance, the
+                // tie order of the reference's block reduction decides which of the two is picked (the other one is at
+                // distance 0 from then on).  Slot 0 is the first pick by definition.
+                bool alias = false;   // the padded position is a key (aliased to the sample's first voxel)
+                int excl = -1;        // real slot that is never picked
+                if (c < n) {
+                    if (ic < 0) alias = true;
+                    else if (ic > 0) {
+                        const int B = 1 << P.log2b[s];
+                        unsigned tie_pad = 0;
+                        for (int k = c + lane; k < n; k += 32) tie_pad = max(tie_pad, fps_tie(k, B, P.log2b[s]));
+                        tie_pad = __reduce_max_sync(0xffffffffu, tie_pad);
+                        if (tie_pad > fps_tie(ic, B, P.log2b[s])) { alias = true; excl = ic; }
+                    }
+                }
+                const int nreal = c - (excl >= 0 ? 1 : 0), ndist = nreal + (alias ? 1 : 0);
+                if (ndist <= K) {
+                    int *rr = out.rep_row + (size_t)w * 2 * K + s * K;
+                    for (int i = lane; i < c; i += 32)
+                        if (i != excl) rr[i - (excl >= 0 && i > excl ? 1 : 0)] = row0 + s_ind[list_at[L] + i];
+                    if (lane == 0) {
+                        const int nmask = K - ndist;
+                        if (alias) rr[nreal] = row0;
+                        if (nmask > 0) rr[ndist] = row0 + s_ind[list_at[L]];
+                        out.meta[4 * (size_t)w + 2 + s] = (ndist + (nmask > 0 ? 1 : 0)) | (nmask << 8);
+                    }
+                    __syncwarp();
+                    continue;
+                }
+            }
             fps_list(s_off + list_at[L], cnt[L], n, P.log2b[s], K, s_min, s_pick + s * K);
             for (int j = lane; j < K; j += 32) {
                 int f = s_pick[s * K + j];
                 int v = f < cnt[L] ? s_ind[list_at[L] + f] : -1;
                 // (ind.float() gathered at f, + 0.1).int(): -1 -> 0, anything >= 0 unchanged
-                out.k_row[(size_t)w * 2 * K + s * K + j] = row0 + max(v, 0);
-                out.k_mask[(size_t)w * 2 * K + s * K + j] = (j > 0 && f == 0) ? 1 : 0;
+                if (out.k_row) {
+                    out.k_row[(size_t)w * 2 * K + s * K + j] = row0 + max(v, 0);
+                    out.k_mask[(size_t)w * 2 * K + s * K + j] = (j > 0 && f == 0) ? 1 : 0;
+                }
                 if (out.fps_idx) out.fps_idx[(size_t)w * 2 * K + s * K + j] = f;
             }
             if (out.rep_row) {
@@ -571,9 +618,10 @@ int mssvt_block_geometry(int x_max, int y_max, int z_max, int x_ws, int y_ws, in
         cbs_pattern > 2 || max_win1 <= 0 || max_win2 <= 0 || win_capacity < 0)
         return MSSVT_ERR_INVALID;
     if (!voxel_size || !range_min || !win_count_total || !win_list || !grid_cells || !grid_vals ||
-        !v_start || !q_row ||
-        !win1_row || !k_row || !k_mask || !covered)
+        !v_start || !q_row || !win1_row || !covered)
         return MSSVT_ERR_INVALID;
+    // k_row / k_mask are optional together: without them only the distinct-key form (rep_row / meta) is produced
+    if ((k_row == nullptr) != (k_mask == nullptr) || (!k_row && !rep_row) || (!k_row && fps_idx_tap)) return MSSVT_ERR_INVALID;
     if (use_interp && (!nn_idx || !nn_w)) return MSSVT_ERR_INVALID;
     int nq = cbs_pattern == 0 ? num_even : cbs_pattern == 1 ? num_odd : max_win1;
     if (nq <= 0 || nq > 255) return MSSVT_ERR_INVALID;

@@ -244,7 +244,7 @@ class MixedScaleSparseTransformerBlock(nn.Module):
         GroupingOperation (our CUDA forward + scatter-add backward) over global rows."""
         x = sp_tensor.features.float().contiguous()
         N, C = x.shape
-        g = self.geometry(sp_tensor)
+        g = self.geometry(sp_tensor, keys=True)
         W, dropped = (int(v) for v in g["win_count"][sp_tensor.batch_size:sp_tensor.batch_size + 2].tolist())
         if dropped:
             raise RuntimeError("window partition: %d windows exceed max_num_wins" % dropped)
@@ -303,7 +303,7 @@ class MixedScaleSparseTransformerBlock(nn.Module):
             cache[key] = (grid, win_list, None, win_count)
         return cache[key]
 
-    def geometry(self, sp_tensor, taps=False):
+    def geometry(self, sp_tensor, taps=False, keys=False):
         """Coordinate-only part of the block (windows, chessboard lists, FPS keys, masks, three-NN), computed once
         per (coordinates, window configuration) and cached on the tensor.  Blocks that differ only in cbs_pattern
         share the expensive part -- chessboard probes, both FPS passes, key lists -- through one
@@ -313,15 +313,19 @@ class MixedScaleSparseTransformerBlock(nn.Module):
         interp = bool(self.use_feature_interpolation)
         base = (tuple(self.win1_size), tuple(self.win2_size), self.max_num_win1, self.max_num_win2,
                 self.key_num_sample, interp, self.max_num_wins)
-        key = ("geo", base, self.cbs_pattern, bool(taps))
+        nq = {0: self.max_num_even, 1: self.max_num_odd, 2: self.max_num_win1}[self.cbs_pattern]
+        # per-slot key rows / masks (the reference's padded form) only for who reads them: the FFMA kernel, the autograd
+        # path, the taps.  The tensor-core attention reads the distinct-key form, which mssvt_block_geometry can produce
+        # without running FPS for almost every window
+        need_keys = bool(taps or keys or not self._tc_supported(nq))
+        key = ("geo", base, self.cbs_pattern, bool(taps), need_keys)
         if key in cache:
             return cache[key]
         dev = sp_tensor.indices.device
         N, B, K = sp_tensor.indices.shape[0], sp_tensor.batch_size, self.key_num_sample
-        nq = {0: self.max_num_even, 1: self.max_num_odd, 2: self.max_num_win1}[self.cbs_pattern]
         i32 = dict(dtype=torch.int32, device=dev)
         u8 = dict(dtype=torch.uint8, device=dev)
-        shared = cache.get(("geo-shared", base)) if interp and not taps else None
+        shared = cache.get(("geo-shared", base, need_keys)) if interp and not taps else None
         if shared is not None:
             # another pattern over the same windows: only the query-dependent maps are new
             cap = shared["cap"]
@@ -346,8 +350,8 @@ class MixedScaleSparseTransformerBlock(nn.Module):
                 "win_list": win_list, "win_count": win_count, "total": win_count[B:B + 1], "cap": cap, "nq": nq,
                 "q_row": torch.empty((cap, nq), **i32),
                 "win1_row": torch.empty((cap, self.max_num_win1), **i32),
-                "k_row": torch.empty((cap, 2 * K), **i32),
-                "k_mask": torch.empty((cap, 2 * K), **u8),
+                "k_row": torch.empty((cap, 2 * K), **i32) if need_keys else None,
+                "k_mask": torch.empty((cap, 2 * K), **u8) if need_keys else None,
                 "nn_idx": torch.empty((cap, self.max_num_win1, 3), **u8) if interp else None,
                 "nn_w": torch.empty((cap, self.max_num_win1, 3), dtype=torch.float32, device=dev) if interp else None,
                 "covered": torch.empty(N, **u8),
@@ -373,7 +377,7 @@ class MixedScaleSparseTransformerBlock(nn.Module):
                  ptr(g["nn_w"]), ptr(g["covered"]), ptr(g["fps_idx"]), ptr(g["counts"]), ptr(g["rep_row"]),
                  ptr(g["meta"]), ptr(g["vox_slot"]), ptr(g["odd_row"]), ptr(g["even_row"]), stream())
             if share:
-                cache[("geo-shared", base)] = g
+                cache[("geo-shared", base, need_keys)] = g
         # compact query ids for the task-parallel kernels: q_base[w] = #real queries of windows < w
         scan_ws = torch.empty((cap + 1 + 1023) // 1024 + 1, **i32)
         call("mssvt_exclusive_scan", cap, ptr(g["total"]), ptr(g["meta"]), 4, ptr(g["q_base"]), ptr(scan_ws),

@@ -331,3 +331,47 @@ def test_exclusive_scan(cap, n, stride):
     want = torch.zeros(n + 1, dtype=torch.int64)
     want[1:] = torch.cumsum(src[:n, 0].cpu().long(), 0)
     assert torch.equal(dst[:n + 1].cpu().long(), want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,crop", [(30000, 0.45), (6000, 0.12)])
+def test_geometry_distinct_key_sets_without_fps(n, crop):
+    """mssvt_block_geometry without k_row / k_mask (what the tensor-core attention asks for) derives the distinct keys of a
+    window without running FPS whenever the list has at most K distinct positions; against the full form (FPS picks,
+    bit-exact vs the reference elsewhere): same key SET per window and scale, same masked key, same multiplicity.
+    The dense crop has 5^3 lists with more than K voxels, where the real FPS has to run in both forms."""
+    import torch
+    from mssvt_b200.config import block_cfg
+    from mssvt_b200.mssvt_backbone import MixedScaleSparseTransformerBlock
+    from mssvt_b200.mssvt_utils import SparseTensor
+    from mssvt_b200.synth import S0_GRID, S0_RANGE, S0_VOXEL, synth_frame
+    cfg = block_cfg()
+    blk = MixedScaleSparseTransformerBlock(cfg, 64, 128, 64, [2, 2], drop_path=0.0, window_size=cfg.window_size,
+                                           cbs_pattern=1).cuda().eval()
+    blk.precision = "tf32x3"
+    feats, coords = synth_frame(7, n, crop=crop)
+    sp = SparseTensor(features=torch.from_numpy(feats).cuda(), indices=torch.from_numpy(coords).cuda(),
+                      spatial_shape=list(S0_GRID), voxel_size=list(S0_VOXEL), point_cloud_range=list(S0_RANGE),
+                      batch_size=1, hash_size=400000, map_table=None, gather_dict=None)
+    fast, full = blk.geometry(sp), blk.geometry(sp, keys=True)
+    assert fast["k_row"] is None and full["k_row"] is not None
+    W, K = int(full["total"].item()), blk.key_num_sample
+    assert int(fast["total"].item()) == W
+    mf, mu = fast["meta"][:W].cpu(), full["meta"][:W].cpu()
+    assert torch.equal(mf, mu)                      # (#queries, #win1 voxels, nrep | nmask << 8 per scale)
+    rf, ru = fast["rep_row"][:W].cpu(), full["rep_row"][:W].cpu()
+    many = 0
+    for s in range(2):
+        nrep, nmask = (mu[:, 2 + s] & 0xff).tolist(), (mu[:, 2 + s] >> 8).tolist()
+        for w in range(W):
+            a, b = rf[w, s * K:s * K + nrep[w]].tolist(), ru[w, s * K:s * K + nrep[w]].tolist()
+            live = nrep[w] - (1 if nmask[w] else 0)
+            assert sorted(a[:live]) == sorted(b[:live]), (w, s)
+            if nmask[w]:
+                assert a[-1] == b[-1], (w, s)
+            else:
+                many += 1
+    assert many > 0 or crop > 0.2        # (the dense crop exercises lists where FPS has to choose)
+    for k in ("q_row", "win1_row", "nn_idx", "nn_w", "covered", "vox_slot"):
+        assert torch.equal(fast[k][:W] if fast[k].shape[0] >= W and k not in ("covered", "vox_slot") else fast[k],
+                           full[k][:W] if full[k].shape[0] >= W and k not in ("covered", "vox_slot") else full[k]), k
