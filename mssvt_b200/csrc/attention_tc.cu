@@ -72,13 +72,16 @@ k_tca_plan(int heads, int win_cap, const int *__restrict__ win_count_total, cons
            const int4 *__restrict__ meta, const int *__restrict__ q_base, float3 win_cell, float3 lo,
            int2 *__restrict__ tiles, int *__restrict__ tile_count, int4 *__restrict__ win_rec,
            float4 *__restrict__ win_ctr) {
+    __shared__ int2 s_tiles[8][TCA_PLAN_WB];   // the tiles of a warp's chunk (at most one per window)
     const int num_wins = min(win_cap, __ldg(win_count_total));
     const int lane = threadIdx.x & 31;
     const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int g = wid & 1, w0 = (wid >> 1) * TCA_PLAN_WB;
     if (w0 >= num_wins) return;
+    int2 *mine = s_tiles[threadIdx.x >> 5];
     const int w1 = min(w0 + TCA_PLAN_WB, num_wins);
     int ts = w0, a = 0, aq = 0, as = 0, nw = 0;  // open tile: first window, key rows, query rows, score slots, windows
+    int nt = 0;                                  // tiles closed so far
     for (int wb = w0; wb < w1; wb += 32) {
         const int w = wb + lane;
         int nqr = 0, r = 0, mult = 0, qb = 0;
@@ -98,7 +101,10 @@ k_tca_plan(int heads, int win_cap, const int *__restrict__ win_count_total, cons
             const int ri = __shfl_sync(0xffffffffu, r, i), qi = __shfl_sync(0xffffffffu, nqr, i);
             const int si = qi * ri * heads;
             if (nw > 0 && (a + aq + ri + qi > TCA_THREADS || aq + qi > TCA_QMAX || as + si > TCA_SBUD || nw == TCA_TW)) {
-                if (lane == 0 && a > 0) tiles[(size_t)g * win_cap + atomicAdd(tile_count + g, 1)] = make_int2(ts, nw);
+                if (a > 0) {   // (a tile without key rows has no real query either: nobody would read it)
+                    if (lane == 0) mine[nt] = make_int2(ts, nw);
+                    ++nt;
+                }
                 ts = wb + i; a = aq = as = nw = 0;
             }
             if (i == lane) { my_a = a; my_aq = aq; my_as = as; }
@@ -107,17 +113,29 @@ k_tca_plan(int heads, int win_cap, const int *__restrict__ win_count_total, cons
         if (w < w1)
             win_rec[(size_t)g * win_cap + w] = make_int4(qb, nqr | (r << 8) | (mult << 16), my_a | (my_aq << 8) | (my_as << 16), 0);
     }
-    if (lane == 0 && a > 0) tiles[(size_t)g * win_cap + atomicAdd(tile_count + g, 1)] = make_int2(ts, nw);
+    if (a > 0) {
+        if (lane == 0) mine[nt] = make_int2(ts, nw);
+        ++nt;
+    }
+    // one slot reservation per chunk (a same-address atomic per TILE made the 8 000 tiles of a frame queue up at the L2)
+    int base = 0;
+    if (lane == 0 && nt > 0) base = atomicAdd(tile_count + g, nt);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    __syncwarp();
+    for (int i = lane; i < nt; i += 32) tiles[(size_t)g * win_cap + base + i] = mine[i];
 }
 
 // Row table of every tile: byte t of a tile = window (within the tile, 6 bits) | kind << 6 (1 = distinct key,
-// 2 = real query, 0 = idle row).  One warp per tile, made once per frame geometry with the plan; the tile kernel
-// then finds the role of a row with one byte load instead of two binary searches over the window offsets
+// 2 = real query, 0 = idle row).  One warp per tile, lane = window: every lane marks the rows of its window in a
+// 128-byte line of shared memory, the warp writes the line out.  Made once per frame geometry with the plan; the tile
+// kernel then finds the role of a row with one byte load instead of two binary searches over the window offsets
 // (every instruction on the critical path of a tile costs ~20 clocks at 16 warps per SM).
 __global__ void __launch_bounds__(256)
 k_tca_rows(int win_cap, const int2 *__restrict__ tiles, const int *__restrict__ tile_count,
            const int4 *__restrict__ win_rec, unsigned char *__restrict__ tile_rows) {
+    __shared__ __align__(16) unsigned char s_line[8][TCA_THREADS];
     const int lane = threadIdx.x & 31;
+    unsigned char *line = s_line[threadIdx.x >> 5];
     const int warps = (gridDim.x * blockDim.x) >> 5;
     for (int g = 0; g < 2; ++g) {
         const int T = min(win_cap, __ldg(tile_count + g));
@@ -126,21 +144,18 @@ k_tca_rows(int win_cap, const int2 *__restrict__ tiles, const int *__restrict__ 
             int4 rec = make_int4(0, 0, 0, 0);
             if (lane < tl.y) rec = __ldg(win_rec + (size_t)g * win_cap + tl.x + lane);
             const int last_z = __shfl_sync(0xffffffffu, rec.z, tl.y - 1), last_y = __shfl_sync(0xffffffffu, rec.y, tl.y - 1);
-            const int nT = (last_z & 0xff) + ((last_y >> 8) & 0xff);
-            unsigned char *out = tile_rows + ((size_t)g * win_cap + t) * TCA_THREADS;
-            unsigned mine[4] = {0u, 0u, 0u, 0u};       // this lane's 4 consecutive rows: 4 * lane ..
-            for (int l = 0; l < tl.y; ++l) {
-                const int y = __shfl_sync(0xffffffffu, rec.y, l), z = __shfl_sync(0xffffffffu, rec.z, l);
-                const int k0 = z & 0xff, k1 = k0 + ((y >> 8) & 0xff);               // key rows of window l
-                const int q0 = nT + ((z >> 8) & 0xff), q1 = q0 + (y & 0xff);         // query rows of window l
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int row = 4 * lane + i;
-                    if (row >= k0 && row < k1) mine[i] = (unsigned)l | 0x40u;
-                    if (row >= q0 && row < q1) mine[i] = (unsigned)l | 0x80u;
-                }
+            const int nT = (last_z & 0xff) + ((last_y >> 8) & 0xff);      // key rows of the tile; the queries follow
+            *(unsigned *)(line + 4 * lane) = 0u;
+            __syncwarp();
+            if (lane < tl.y) {
+                const int k0 = rec.z & 0xff, nk = (rec.y >> 8) & 0xff;           // key rows of this lane's window
+                const int q0 = nT + ((rec.z >> 8) & 0xff), nqw = rec.y & 0xff;    // its query rows
+                for (int i = 0; i < nk; ++i) line[k0 + i] = (unsigned char)(lane | 0x40);
+                for (int i = 0; i < nqw; ++i) line[q0 + i] = (unsigned char)(lane | 0x80);
             }
-            *(unsigned *)(out + 4 * lane) = mine[0] | (mine[1] << 8) | (mine[2] << 16) | (mine[3] << 24);
+            __syncwarp();
+            *(unsigned *)(tile_rows + ((size_t)g * win_cap + t) * TCA_THREADS + 4 * lane) = *(const unsigned *)(line + 4 * lane);
+            __syncwarp();
         }
     }
 }

@@ -73,6 +73,10 @@ __device__ __forceinline__ void probe_window(const GatherShape &g, int4 win, con
 #pragma unroll
         for (int L = 0; L < 4; ++L) {
             if (g.cap[L] == 0) continue;
+            // (table segments that feed list L: odd [0, e0), even [e0, e1), win1 [0, e2), win2 everything; a pass
+            //  of 32 offsets that does not touch them appends nothing to L -- three of four passes for win1 and its parts)
+            const int src_lo = L == 1 ? e0 : 0, src_hi = L == 0 ? e0 : L == 1 ? e1 : L == 2 ? e2 : total;
+            if (base >= src_hi || base + 32 <= src_lo) continue;
             bool mine = hit && ((member >> L) & 1u);
             unsigned m = __ballot_sync(0xffffffffu, mine);
             int pos = cnt[L] + __popc(m & lanemask_lt());

@@ -162,7 +162,16 @@ k_scan_emit(int n_cap, const int *__restrict__ n_dev, const int *__restrict__ sr
         // single pass: the block sums everything in front of it itself (b independent loads per thread; the lists this
         // scans are 10^4..10^5 long, so the last block reads ~100 elements per thread out of L2 -- cheaper than a second
         // kernel in the serial coordinate prefix of a frame)
-        for (int j = threadIdx.x; j < (int)blockIdx.x * 1024; j += 1024) part += __ldg(src + (size_t)j * stride);
+        const int limit = (int)blockIdx.x * 1024;
+        int j = threadIdx.x, p1 = 0, p2 = 0, p3 = 0, p4 = 0, p5 = 0, p6 = 0, p7 = 0;
+        for (; j + 7 * 1024 < limit; j += 8 * 1024) {   // eight independent loads in flight per thread
+            part += __ldg(src + (size_t)j * stride);              p1 += __ldg(src + (size_t)(j + 1024) * stride);
+            p2 += __ldg(src + (size_t)(j + 2048) * stride);       p3 += __ldg(src + (size_t)(j + 3072) * stride);
+            p4 += __ldg(src + (size_t)(j + 4096) * stride);       p5 += __ldg(src + (size_t)(j + 5120) * stride);
+            p6 += __ldg(src + (size_t)(j + 6144) * stride);       p7 += __ldg(src + (size_t)(j + 7168) * stride);
+        }
+        for (; j < limit; j += 1024) part += __ldg(src + (size_t)j * stride);
+        part += p1 + p2 + p3 + p4 + p5 + p6 + p7;
     }
     part = __reduce_add_sync(0xffffffffu, part);
     if (lane == 0) s_warp[warp] = part;
