@@ -313,6 +313,13 @@ int mssvt_pack_operand_tf32(const float *w, int n_rows, int k, int terms, float 
  * k % 16 == 0.  mssvt_ffn_tc and mssvt_block_attention_tc take these copies when called with terms = 0. */
 int mssvt_pack_operand_bf16(const float *w, int n_rows, int k, void *packed, void *stream);
 
+/* The split bf16 form (precision mode "bf16x3", terms = 2): w = w_hi + w_mid with w_hi = bf16(w), w_mid = bf16(w - w_hi);
+ * packed = [hi | mid] = 2 * n_rows * k bf16 in the layout above.  The *_tc entry points called with terms = 2 split their
+ * activations the same way and issue A_hi W_hi + A_mid W_hi + A_hi W_mid per K = 16 step on kind::f16: ~16 significant
+ * bits per operand (results within 1e-4 of an fp32 reference, measured ~2e-5) from operand tiles of the size of one
+ * TF32 tile. */
+int mssvt_pack_operand_bf16x2(const float *w, int n_rows, int k, void *packed, void *stream);
+
 /* Self-check of the tensor-map (TMA, cp.async.bulk.tensor) row movement mssvt_ffn_tc uses for its dense row tiles
  * (mssvt_b200/csrc/tma.cuh): copies a row-major (num_rows, 64) fp32 matrix src -> dst through box loads, swizzled
  * shared-memory boxes read and re-written by their owning lanes, and box stores; dst == src bit for bit, rows past

@@ -54,6 +54,7 @@ _SIGNATURES = {
     "mssvt_ffn": [P, I, P, I, P, P, P, P, P, P],
     "mssvt_pack_operand_tf32": [P, I, I, I, P, P],
     "mssvt_pack_operand_bf16": [P, I, I, P, P],
+    "mssvt_pack_operand_bf16x2": [P, I, I, P, P],
     "mssvt_tma_copy_rows": [P, P, I, P],
     "mssvt_ffn_tc": [I, I, I, I, F] + [P] * 6 + [I, P, P, P, P, P, P, P, F, P] + [P] * 6 + [I, P],
     "mssvt_dense_scatter": [I, P, I, I, I, I, I, P, P, P, P],

@@ -210,8 +210,8 @@ k_tca_tile(TcAttnParams P, int win_cap, const int2 *__restrict__ tiles, const in
            const float *__restrict__ xyz, const int *__restrict__ rep_row, const int *__restrict__ q_row,
            float *__restrict__ Pbuf) {
     constexpr int HD = TCA_SD / HEADS;
-    constexpr int NT = TERMS == 3 ? 2 : 1;       // operand tiles: hi [, lo] (3xTF32, tc_common.cuh)
-    constexpr bool BF = TERMS == 0;              // bf16 operands (kind::f16) for the K|V|Q and output projections
+    constexpr int NT = TERMS == 3 || TERMS == 2 ? 2 : 1;   // operand tiles: hi [, lo] (3xTF32) / hi [, mid] (bf16x3), tc_common.cuh
+    constexpr bool BF = TERMS == 0 || TERMS == 2;          // bf16 operands (kind::f16) for the K|V|Q and output projections
     constexpr int EB = BF ? 2 : 4;
     // TMEM: 128 columns; the 3xTF32 kernel takes 32 more (low half of the A operand) as a SECOND allocation:
     // 160 columns per CTA keep three CTAs on an SM, one 256-column allocation would allow two
@@ -377,9 +377,14 @@ k_tca_tile(TcAttnParams P, int win_cap, const int2 *__restrict__ tiles, const in
             if (with_proj) {
                 if constexpr (BF) {
 #pragma unroll
-                    for (int k = 0; k < TCA_SD / 16; ++k)
-                        umma_bf16(tm_q, umma_desc_at(dAO, (uint32_t)k * 256u), umma_desc_at(dWp, (uint32_t)k * 1024u), id_p32,
-                                  k > 0 ? 1u : 0u);
+                    for (int k = 0; k < TCA_SD / 16; ++k) {
+                        const uint64_t ah = umma_desc_at(dAO, (uint32_t)k * 256u), wh = umma_desc_at(dWp, (uint32_t)k * 1024u);
+                        umma_bf16(tm_q, ah, wh, id_p32, k > 0 ? 1u : 0u);
+                        if (TERMS == 2) {
+                            umma_bf16(tm_q, umma_desc_at(dAO, TCA_QMAX * TCA_SD * 2 + (uint32_t)k * 256u), wh, id_p32, 1u);
+                            umma_bf16(tm_q, ah, umma_desc_at(dWp, 32u * 32u * 2u + (uint32_t)k * 1024u), id_p32, 1u);
+                        }
+                    }
                 } else {
 #pragma unroll
                     for (int k = 0; k < TCA_SD / 8; ++k) {
@@ -465,13 +470,21 @@ k_tca_tile(TcAttnParams P, int win_cap, const int2 *__restrict__ tiles, const in
             tmem_ld32(tm_a + lane_off, d);
             if constexpr (BF) {
                 // packed bf16 pairs: channel k in column k / 2 (16 columns, in place over the accumulator)
-                uint32_t w[TCA_SD / 2];
+                uint32_t w[TCA_SD / 2], wm[TCA_SD / 2];
 #pragma unroll
                 for (int c4 = 0; c4 < TCA_SD / 4; ++c4) {
-                    w[2 * c4] = pack_bf16x2(xv[c4].x + fmaxf(d[4 * c4], 0.f), xv[c4].y + fmaxf(d[4 * c4 + 1], 0.f));
-                    w[2 * c4 + 1] = pack_bf16x2(xv[c4].z + fmaxf(d[4 * c4 + 2], 0.f), xv[c4].w + fmaxf(d[4 * c4 + 3], 0.f));
+                    const float a0 = xv[c4].x + fmaxf(d[4 * c4], 0.f), a1 = xv[c4].y + fmaxf(d[4 * c4 + 1], 0.f);
+                    const float a2 = xv[c4].z + fmaxf(d[4 * c4 + 2], 0.f), a3 = xv[c4].w + fmaxf(d[4 * c4 + 3], 0.f);
+                    if (TERMS == 2) {
+                        split_bf16x2(a0, a1, w[2 * c4], wm[2 * c4]);
+                        split_bf16x2(a2, a3, w[2 * c4 + 1], wm[2 * c4 + 1]);
+                    } else {
+                        w[2 * c4] = pack_bf16x2(a0, a1);
+                        w[2 * c4 + 1] = pack_bf16x2(a2, a3);
+                    }
                 }
                 tmem_st16(tm_a + lane_off, w);
+                if (TERMS == 2) tmem_st16(tm_a + 16u + lane_off, wm);   // (mid parts: columns 16..31 of the same accumulator)
             } else if (TERMS == 3) {
                 float lo[TCA_SD];
 #pragma unroll
@@ -503,8 +516,14 @@ k_tca_tile(TcAttnParams P, int win_cap, const int2 *__restrict__ tiles, const in
             tc_fence_after();
             if constexpr (BF) {
 #pragma unroll
-                for (int k = 0; k < TCA_SD / 16; ++k)   // K = 16 per MMA: 8 packed A columns, two 16-byte B chunks
-                    umma_bf16_ts(tm_k, tm_a + (uint32_t)k * 8u, umma_desc_at(dWkvq, (uint32_t)k * 2u * 1536u), id_n96, k > 0 ? 1u : 0u);
+                for (int k = 0; k < TCA_SD / 16; ++k) {   // K = 16 per MMA: 8 packed A columns, two 16-byte B chunks
+                    const uint64_t wh = umma_desc_at(dWkvq, (uint32_t)k * 2u * 1536u);
+                    umma_bf16_ts(tm_k, tm_a + (uint32_t)k * 8u, wh, id_n96, k > 0 ? 1u : 0u);
+                    if (TERMS == 2) {
+                        umma_bf16_ts(tm_k, tm_a + 16u + (uint32_t)k * 8u, wh, id_n96, 1u);
+                        umma_bf16_ts(tm_k, tm_a + (uint32_t)k * 8u, umma_desc_at(dWkvq, 96u * 32u * 2u + (uint32_t)k * 2u * 1536u), id_n96, 1u);
+                    }
+                }
             } else
 #pragma unroll
             for (int k = 0; k < TCA_SD / 8; ++k) {
@@ -642,8 +661,16 @@ k_tca_tile(TcAttnParams P, int win_cap, const int2 *__restrict__ tiles, const in
 #pragma unroll
                 for (int d = 0; d < DPT; d += 2) {
                     const int c = c0 + d;      // (pairs never straddle a chunk: c0 and DPT are multiples of 4)
-                    *(uint32_t *)(dst + ((c >> 3) - (c0 >> 3)) * 128 + ((c & 7) - (c0 & 7)) * 2) =
-                        pack_bf16x2(fmaf(acc[d], inv, bv[d]), fmaf(acc[d + 1], inv, bv[d + 1]));
+                    char *at = dst + ((c >> 3) - (c0 >> 3)) * 128 + ((c & 7) - (c0 & 7)) * 2;
+                    const float o0 = fmaf(acc[d], inv, bv[d]), o1 = fmaf(acc[d + 1], inv, bv[d + 1]);
+                    if (TERMS == 2) {
+                        uint32_t hi, mid;
+                        split_bf16x2(o0, o1, hi, mid);
+                        *(uint32_t *)at = hi;
+                        *(uint32_t *)(at + TCA_QMAX * TCA_SD * 2) = mid;   // second tile: the mid parts
+                    } else {
+                        *(uint32_t *)at = pack_bf16x2(o0, o1);
+                    }
                 }
                 continue;
             }
@@ -827,7 +854,7 @@ int mssvt_block_attention_tc(int C, int heads_per_group, int nq, int key_num_sam
                              float *merged, void *stream) {
     if (C != 64 || (heads_per_group != 1 && heads_per_group != 2 && heads_per_group != 4) || nq <= 0 || nq > 32 ||
         key_num_sample <= 0 || key_num_sample > 63 || cap1 <= 0 || cap1 > 128 || win_capacity < 0 || num_voxels < 0 ||
-        nq * (key_num_sample + 1) * heads_per_group > TCA_SBUD || (terms != 0 && terms != 1 && terms != 3))
+        nq * (key_num_sample + 1) * heads_per_group > TCA_SBUD || (terms != 0 && terms != 1 && terms != 2 && terms != 3))
         return MSSVT_ERR_INVALID;
     if (win_capacity == 0) return MSSVT_OK;
     if (!wpos_packed || !wkvq0 || !wkvq1 || !wp0 || !wp1 || !bq0 || !bq1 || !bkv0 || !bkv1 || !bp0 || !bp1 ||
@@ -841,7 +868,7 @@ int mssvt_block_attention_tc(int C, int heads_per_group, int nq, int key_num_sam
     P.wpos = wpos_packed;
     P.wkvq[0] = wkvq0; P.wkvq[1] = wkvq1; P.wp[0] = wp0; P.wp[1] = wp1;
     P.bq[0] = bq0; P.bq[1] = bq1; P.bkv[0] = bkv0; P.bkv[1] = bkv1; P.bp[0] = bp0; P.bp[1] = bp1;
-    const size_t smem = (size_t)TcaSmem(terms == 3 ? 2 : 1, terms == 0 ? 2 : 4).total;
+    const size_t smem = (size_t)TcaSmem(terms == 3 || terms == 2 ? 2 : 1, terms == 0 || terms == 2 ? 2 : 4).total;
     float *Pbuf = scratch + 2 * (size_t)num_voxels * 64;
     cudaStream_t s = (cudaStream_t)stream;
     const int wide = MSSVT_NUM_SMS * 8;  // grid-stride kernels: 8 CTAs of 256 threads per SM
@@ -858,7 +885,11 @@ int mssvt_block_attention_tc(int C, int heads_per_group, int nq, int key_num_sam
     cudaFuncSetAttribute(k_tca_tile<H, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
     launch_pdl(k_tca_tile<H, T>, dim3(grid), dim3(TCA_THREADS), smem, s, P, win_capacity, (const int2 *)tiles, \
                tile_count, (const int4 *)win_rec, (const float4 *)win_ctr, tile_rows, xn, xyz, rep_row, q_row, Pbuf)
-    if (terms == 0) {
+    if (terms == 2) {
+        if (heads_per_group == 1) { TCA_LAUNCH(1, 2); }
+        else if (heads_per_group == 2) { TCA_LAUNCH(2, 2); }
+        else { TCA_LAUNCH(4, 2); }
+    } else if (terms == 0) {
         if (heads_per_group == 1) { TCA_LAUNCH(1, 0); }
         else if (heads_per_group == 2) { TCA_LAUNCH(2, 0); }
         else { TCA_LAUNCH(4, 0); }

@@ -89,12 +89,13 @@ k_ffn_tc(FfnTcParams P, int n_cap, const int *__restrict__ n_dev, const float *_
     const int r = tid & (TC_ROWS - 1), half = tid >> 7;   // half: which part of the row (0 .. TPR - 1)
     // carve shared memory
     constexpr int NT = TERMS == 3 ? 2 : 1;        // operand tiles: hi [, lo] (3xTF32, see tc_common.cuh)
-    constexpr bool BF = TERMS == 0;               // bf16 operands
+    constexpr bool BF = TERMS == 0 || TERMS == 2; // bf16 operands (TERMS == 2: split in two, hi + mid: "bf16x3")
     constexpr int EB = BF ? 2 : 4;                // bytes per operand element
+    constexpr int NW = TERMS == 3 || TERMS == 2 ? 2 : 1;   // tiles per weight matrix
     char *sA = smem_raw;                          // NT x [chunks][128][16 B] (at least the 32 KB staging area)
     char *sW1 = sA + (BF ? TC_ROWS * C * 4 : NT * TC_ROWS * C * 4);   // NT x [chunks][F][16 B]
-    char *sW2 = sW1 + NT * F * C * EB;            // NT x [chunks][C][16 B]
-    float *s_vec = (float *)(sW2 + NT * C * F * EB);   // ln_g[C], ln_b[C], b1[F], b2[C], next_g[C], next_b[C]
+    char *sW2 = sW1 + NW * F * C * EB;            // NW x [chunks][C][16 B]
+    float *s_vec = (float *)(sW2 + NW * C * F * EB);   // ln_g[C], ln_b[C], b1[F], b2[C], next_g[C], next_b[C]
     float *s_red = s_vec + 5 * C + F;             // [4][TPR][128] partial row sums of the threads of a row
     uint64_t *s_bar = (uint64_t *)(s_red + 4 * TPR * TC_ROWS);  // 3 mbarriers (8-byte aligned: C, F even) + one per warp
     uint32_t *s_tmem = (uint32_t *)(s_bar + 3 + 4 * TPR);        //   (the warp's TMA row loads)
@@ -116,7 +117,7 @@ k_ffn_tc(FfnTcParams P, int n_cap, const int *__restrict__ n_dev, const float *_
         mbar_init(bar_w, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         // W1 and W2 (packed once on the host side) come in as two bulk copies of the TMA engine
-        const uint32_t wbytes = (uint32_t)(NT * F * C * EB);
+        const uint32_t wbytes = (uint32_t)(NW * F * C * EB);
         bulk_expect(bar_w, 2u * wbytes);
         bulk_copy_g2s(P.w1, wbytes, sW1, bar_w);
         bulk_copy_g2s(P.w2, wbytes, sW2, bar_w);
@@ -141,7 +142,7 @@ k_ffn_tc(FfnTcParams P, int n_cap, const int *__restrict__ n_dev, const float *_
     }
     // TMEM: F columns for D1 / hidden + C columns for D2, rounded up to a power of two >= 32
     uint32_t tmem_cols = 32;
-    while (tmem_cols < (uint32_t)(F + C + (TERMS == 3 ? F : BF ? F / 2 : 0))) tmem_cols <<= 1;
+    while (tmem_cols < (uint32_t)(F + C + (TERMS == 3 ? F : BF ? F / 2 : 0))) tmem_cols <<= 1;   // (bf16x3: mid parts in place)
     if (warp == 0) tmem_alloc(smem_u32(s_tmem), tmem_cols);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // staged weights -> async proxy
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -501,13 +502,17 @@ k_ffn_tc(FfnTcParams P, int n_cap, const int *__restrict__ n_dev, const float *_
             // 16-byte chunks of 8 bf16: chunk = channel / 8
 #pragma unroll
             for (int c = 0; c < CH / 8; ++c) {
-                uint32_t w[4];
+                uint32_t w[4], wm[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const int i = 8 * c + 2 * q;
-                    w[q] = pack_bf16x2((u[i] - mean) * rstd * s_g[i] + s_b[i], (u[i + 1] - mean) * rstd * s_g[i + 1] + s_b[i + 1]);
+                    const float v0 = (u[i] - mean) * rstd * s_g[i] + s_b[i], v1 = (u[i + 1] - mean) * rstd * s_g[i + 1] + s_b[i + 1];
+                    if (TERMS == 2) split_bf16x2(v0, v1, w[q], wm[q]);
+                    else w[q] = pack_bf16x2(v0, v1);
                 }
                 *(uint4 *)(sA + (uint32_t)(half * (CH / 8) + c) * a_lbo + my_row_off) = make_uint4(w[0], w[1], w[2], w[3]);
+                if (TERMS == 2)   // second tile: the mid parts
+                    *(uint4 *)(sA + TC_ROWS * C * 2 + (uint32_t)(half * (CH / 8) + c) * a_lbo + my_row_off) = make_uint4(wm[0], wm[1], wm[2], wm[3]);
             }
         } else {
 #pragma unroll
@@ -531,9 +536,14 @@ k_ffn_tc(FfnTcParams P, int n_cap, const int *__restrict__ n_dev, const float *_
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if constexpr (BF) {
 #pragma unroll
-                for (int k = 0; k < C / 16; ++k)       // K = 16 per MMA: two 16-byte chunks of 8 elements
-                    umma_bf16(tmem_d1, umma_desc_at(dA, (uint32_t)k * 2u * a_lbo), umma_desc_at(dW1, (uint32_t)k * 2u * w1_lbo),
-                              idesc1, k > 0 ? 1u : 0u);
+                for (int k = 0; k < C / 16; ++k) {     // K = 16 per MMA: two 16-byte chunks of 8 elements
+                    const uint64_t ah = umma_desc_at(dA, (uint32_t)k * 2u * a_lbo), bh = umma_desc_at(dW1, (uint32_t)k * 2u * w1_lbo);
+                    umma_bf16(tmem_d1, ah, bh, idesc1, k > 0 ? 1u : 0u);
+                    if (TERMS == 2) {
+                        umma_bf16(tmem_d1, umma_desc_at(dA, (uint32_t)(TC_ROWS * C * 2) + (uint32_t)k * 2u * a_lbo), bh, idesc1, 1u);
+                        umma_bf16(tmem_d1, ah, umma_desc_at(dW1, (uint32_t)(F * C * 2) + (uint32_t)k * 2u * w1_lbo), idesc1, 1u);
+                    }
+                }
             } else {
 #pragma unroll
                 for (int k = 0; k < C / 8; ++k) {
@@ -559,11 +569,17 @@ k_ffn_tc(FfnTcParams P, int n_cap, const int *__restrict__ n_dev, const float *_
             tmem_ld32(col, d);
             if constexpr (BF) {
                 // relu(D1 + b1) as packed bf16 pairs: hidden element k lives in column k / 2 of the packed tile
-                uint32_t w[16];
+                uint32_t w[16], wm[16];
 #pragma unroll
-                for (int i = 0; i < 16; ++i)
-                    w[i] = pack_bf16x2(fmaxf(d[2 * i] + s_b1[c0 + 2 * i], 0.f), fmaxf(d[2 * i + 1] + s_b1[c0 + 2 * i + 1], 0.f));
+                for (int i = 0; i < 16; ++i) {
+                    const float h0 = fmaxf(d[2 * i] + s_b1[c0 + 2 * i], 0.f), h1 = fmaxf(d[2 * i + 1] + s_b1[c0 + 2 * i + 1], 0.f);
+                    if (TERMS == 2) split_bf16x2(h0, h1, w[i], wm[i]);
+                    else w[i] = pack_bf16x2(h0, h1);
+                }
                 tmem_st16(tmem_hlo + lane_off + (uint32_t)((half * FH + c0) / 2), w);
+                // the mid parts go back IN PLACE over the first half of this thread's own D1 columns (already read:
+                // hidden element k = half * FH + j sits in column half * FH + j / 2)
+                if (TERMS == 2) tmem_st16(tmem_d1 + lane_off + (uint32_t)(half * FH + c0 / 2), wm);
                 continue;
             }
             if (TERMS == 3) {
@@ -586,9 +602,16 @@ k_ffn_tc(FfnTcParams P, int n_cap, const int *__restrict__ n_dev, const float *_
         if (issuer_elected()) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if constexpr (BF) {
-                for (int k = 0; k < F / 16; ++k)       // A: 8 packed columns per K = 16 step
-                    umma_bf16_ts(tmem_d2, tmem_hlo + (uint32_t)k * 8u, umma_desc_at(dW2, (uint32_t)k * 2u * w2_lbo), idesc2,
-                                 k > 0 ? 1u : 0u);
+                for (int k = 0; k < F / 16; ++k) {     // A: 8 packed columns per K = 16 step
+                    const uint64_t db = umma_desc_at(dW2, (uint32_t)k * 2u * w2_lbo);
+                    umma_bf16_ts(tmem_d2, tmem_hlo + (uint32_t)k * 8u, db, idesc2, k > 0 ? 1u : 0u);
+                    if (TERMS == 2) {
+                        const int hk = 16 * k, hh = hk / FH;       // (mid parts: per half of the hidden row, see above)
+                        umma_bf16_ts(tmem_d2, tmem_d1 + (uint32_t)(hh * FH + (hk - hh * FH) / 2), db, idesc2, 1u);
+                        umma_bf16_ts(tmem_d2, tmem_hlo + (uint32_t)k * 8u,
+                                     umma_desc_at(dW2, (uint32_t)(C * F * 2) + (uint32_t)k * 2u * w2_lbo), idesc2, 1u);
+                    }
+                }
             } else
             for (int k = 0; k < F / 8; ++k) {
                 const uint64_t db = umma_desc_at(dW2, (uint32_t)k * 2u * w2_lbo);
@@ -700,14 +723,18 @@ __global__ void k_pack_operand_tf32(const float *__restrict__ src, int n_rows, i
 }
 
 // row-major [n_rows][k] fp32 -> canonical K-major UMMA layout of bf16 (8-row x 16-byte core matrices = 8 elements)
-__global__ void k_pack_operand_bf16(const float *__restrict__ src, int n_rows, int k, uint4 *__restrict__ dst) {
+__global__ void k_pack_operand_bf16(const float *__restrict__ src, int n_rows, int k, int tiles, uint4 *__restrict__ dst) {
     const int chunks = k >> 3;
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n_rows * chunks) return;
     const int n = e / chunks, c = e - n * chunks;
     const float4 a = __ldg((const float4 *)(src + (size_t)n * k) + 2 * c), b = __ldg((const float4 *)(src + (size_t)n * k) + 2 * c + 1);
     char *at = (char *)dst + (size_t)c * n_rows * 16 + (n >> 3) * 128 + (n & 7) * 16;
-    *(uint4 *)at = make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
+    uint32_t h[4], m[4];
+    split_bf16x2(a.x, a.y, h[0], m[0]); split_bf16x2(a.z, a.w, h[1], m[1]);
+    split_bf16x2(b.x, b.y, h[2], m[2]); split_bf16x2(b.z, b.w, h[3], m[3]);
+    *(uint4 *)at = make_uint4(h[0], h[1], h[2], h[3]);
+    if (tiles == 2) *(uint4 *)(at + (size_t)n_rows * k * 2) = make_uint4(m[0], m[1], m[2], m[3]);   // second tile: the mid parts
 }
 
 // Self-check of the tensor-map row movement the FFN relies on: (rows, 64) fp32 src -> dst through TMA box loads,
@@ -782,7 +809,17 @@ int mssvt_pack_operand_bf16(const float *w, int n_rows, int k, void *packed, voi
     if (!w || !packed || n_rows <= 0 || k <= 0 || (n_rows & 7) || (k & 15)) return MSSVT_ERR_INVALID;
     const int n = n_rows * (k >> 3);
     ++g_launches;
-    k_pack_operand_bf16<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, n_rows, k, (uint4 *)packed);
+    k_pack_operand_bf16<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, n_rows, k, 1, (uint4 *)packed);
+    return check_launch();
+}
+
+// The split form ("bf16x3", terms = 2 of the *_tc entry points): w = w_hi + w_mid, two bf16 each; packed = [hi | mid] =
+// 2 * n_rows * k bf16.
+int mssvt_pack_operand_bf16x2(const float *w, int n_rows, int k, void *packed, void *stream) {
+    if (!w || !packed || n_rows <= 0 || k <= 0 || (n_rows & 7) || (k & 15)) return MSSVT_ERR_INVALID;
+    const int n = n_rows * (k >> 3);
+    ++g_launches;
+    k_pack_operand_bf16<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, n_rows, k, 2, (uint4 *)packed);
     return check_launch();
 }
 
@@ -807,8 +844,9 @@ int mssvt_ffn_tc(int C, int F, int mode, int terms, float eps, const float *ln_g
                  const float *next_ln_g, const float *next_ln_b, float next_eps, float *xn_next,
                  const int *vox_slot, const int *meta, const int *q_base, const unsigned char *nn_idx,
                  const float *nn_w, const float *projected, int cap1, void *stream) {
-    if ((C != 32 && C != 64) || F <= 0 || (F & 63) || F + C + (terms == 3 ? F : terms == 0 ? F / 2 : 0) > 512 || num_rows < 0 ||
-        (terms != 0 && terms != 1 && terms != 3))
+    const bool bf = terms == 0 || terms == 2;
+    if ((C != 32 && C != 64) || F <= 0 || (F & 63) || F + C + (terms == 3 ? F : bf ? F / 2 : 0) > 512 || num_rows < 0 ||
+        (terms != 0 && terms != 1 && terms != 2 && terms != 3))
         return MSSVT_ERR_INVALID;
     if (num_rows == 0) return MSSVT_OK;
     if (mode < 0 || mode > 2 || !ln_g || !ln_b || !w1 || !b1 || !w2 || !b2 || !y || (mode != 2 && !merged) ||
@@ -821,13 +859,13 @@ int mssvt_ffn_tc(int C, int F, int mode, int terms, float eps, const float *ln_g
     // (measured at 150 k rows: 54 -> 62 us with TF32 operands, 66 -> 70 us with split operands: the tile time is made of
     //  memory round trips and MMA round trips, not of the per-thread instruction chains -- the default stays two)
 #ifdef FFN_TPR4
-    const int tpr = (C == 64 && (F & 127) == 0) ? 4 : 2;
+    const int tpr = (C == 64 && (F & 127) == 0 && terms != 2) ? 4 : 2;
 #else
     const int tpr = 2;
 #endif
     size_t smem = nt * ((size_t)TC_ROWS * C * 4 + 2 * (size_t)F * C * 4) + (size_t)(5 * C + F + 4 * tpr * TC_ROWS) * 4 + (3 + 4 * tpr) * 8 + 16 + 128;
-    if (terms == 0)  // bf16 operands: the A region keeps the size of the fp32 staging area, the weights halve
-        smem = (size_t)TC_ROWS * C * 4 + 2 * (size_t)F * C * 2 + (size_t)(5 * C + F + 4 * tpr * TC_ROWS) * 4 + (3 + 4 * tpr) * 8 + 16 + 128;
+    if (bf)  // bf16 operands: the A region keeps the size of the fp32 staging area, the weights halve (one or two tiles each)
+        smem = (size_t)TC_ROWS * C * 4 + (terms == 2 ? 2 : 1) * 2 * (size_t)F * C * 2 + (size_t)(5 * C + F + 4 * tpr * TC_ROWS) * 4 + (3 + 4 * tpr) * 8 + 16 + 128;
     if (smem > 227 * 1024) return MSSVT_ERR_INVALID;
     if (xn_next && (!next_ln_g || !next_ln_b)) return MSSVT_ERR_INVALID;
     FfnTcParams P = {F, mode, eps, w1, b1, w2, b2, ln_g, ln_b, next_ln_g, next_ln_b, next_eps,
@@ -840,7 +878,7 @@ int mssvt_ffn_tc(int C, int F, int mode, int terms, float eps, const float *ln_g
         return MSSVT_ERR_LAUNCH;   // (no cuTensorMapEncodeTiled in this driver, or a misaligned buffer)
     int tiles = (num_rows + TC_ROWS - 1) / TC_ROWS;
     int tmem_cols = 32;
-    while (tmem_cols < F + C + (terms == 3 ? F : terms == 0 ? F / 2 : 0)) tmem_cols <<= 1;
+    while (tmem_cols < F + C + (terms == 3 ? F : bf ? F / 2 : 0)) tmem_cols <<= 1;
     int per_sm = (int)(227 * 1024 / (smem + 1024));
     if (per_sm > 512 / tmem_cols) per_sm = 512 / tmem_cols;
     per_sm = per_sm > 2 ? 2 : per_sm < 1 ? 1 : per_sm;
@@ -858,6 +896,8 @@ int mssvt_ffn_tc(int C, int F, int mode, int terms, float eps, const float *ln_g
         else if (terms == 3) { FFN_TC_LAUNCH(64, 3, 4); }
         else { FFN_TC_LAUNCH(64, 1, 4); }
     }
+    else if (C == 64 && terms == 2) { FFN_TC_LAUNCH(64, 2, 2); }
+    else if (terms == 2) { FFN_TC_LAUNCH(32, 2, 2); }
     else if (C == 64 && terms == 0) { FFN_TC_LAUNCH(64, 0, 2); }
     else if (terms == 0) { FFN_TC_LAUNCH(32, 0, 2); }
     else if (C == 64 && terms == 3) { FFN_TC_LAUNCH(64, 3, 2); }

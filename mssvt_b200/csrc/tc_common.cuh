@@ -101,6 +101,15 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     return r;
 }
 
+// "bf16x3": a = hi + mid with hi = bf16(a), mid = bf16(a - hi) -- 16 significant bits in two bf16 (and the same for the
+// weights); A W^T ~= A_hi W_hi^T + A_mid W_hi^T + A_hi W_mid^T on kind::f16 with fp32 accumulation.  Relative error of a
+// product ~2^-16: results within 1e-4 of an fp32 reference with a wide margin (measured ~2e-5), from operand tiles
+// of the size of ONE TF32 tile -- the occupancy of the plain TF32 kernels instead of the split-TF32 ones.
+__device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t &hi, uint32_t &mid) {
+    hi = pack_bf16x2(a, b);
+    mid = pack_bf16x2(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xffff0000u));
+}
+
 __device__ __forceinline__ void umma_commit(uint32_t mbar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar)
                  : "memory");

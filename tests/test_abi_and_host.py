@@ -102,14 +102,15 @@ def test_precision_modes_and_module_mirrors_on_cpu():
     from mssvt_b200.mssvt_backbone import MixedScaleSparseTransformer
     from mssvt_b200.synth import S0_GRID, S0_RANGE, S0_VOXEL
     model = MixedScaleSparseTransformer(s0_model_cfg(), 64, list(S0_GRID), list(S0_VOXEL), list(S0_RANGE))
-    assert model.precision == "tf32x3" and all(b.precision == "tf32x3" for b in model.backbone)
-    for mode in ("fp32", "tf32", "bf16", "tf32x3"):
+    assert model.precision == "bf16x3" and all(b.precision == "bf16x3" for b in model.backbone)
+    for mode in ("fp32", "tf32", "bf16", "bf16x3", "tf32x3"):
         assert model.set_precision(mode).backbone[-1].precision == mode
     with pytest.raises(ValueError):
         model.set_precision("fp16")
-    assert model.backbone[0]._terms() == 3 and model.set_precision("tf32").backbone[0]._terms() == 1
+    assert model.set_precision("tf32x3").backbone[0]._terms() == 3 and model.set_precision("tf32").backbone[0]._terms() == 1
     # bf16: kind::f16 operands for the blocks and every FFN; the compress attention kernels stay TF32
     assert model.set_precision("bf16").backbone[0]._terms() == 0 and model.backbone[-1]._attn_terms() == 1
+    assert model.set_precision("bf16x3").backbone[0]._terms() == 2 and model.backbone[-1]._attn_terms() == 3
     with pytest.raises(RuntimeError, match="CUDA tensors only"):   # no CPU path, also for the graph capture
         model.eval()({"voxel_features": torch.zeros(1, 64), "voxel_coords": torch.zeros(1, 4), "batch_size": 1})
     vfe = DynamicVFE(AttrDict(NUM_FILTERS=[32, 64]), 5, list(S0_VOXEL), list(S0_GRID), list(S0_RANGE))

@@ -33,10 +33,10 @@ def to_local(rows, win_b, v_start):
     return torch.where(rows >= 0, rows - base, rows)
 
 
-@pytest.mark.parametrize("precision", ["fp32", "tf32x3"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32x3", "bf16x3"])
 @pytest.mark.parametrize("name", GOLDEN_CASES)
 def test_backbone_matches_reference_golden(name, precision):
-    """both fp32-grade modes: FFMA kernels and split-operand tensor-core kernels (the default)"""
+    """the modes held to the fp32 bar: FFMA kernels and the two split-operand tensor-core forms"""
     blob, cfg, state = load_golden(name)
     cfg["PRECISION"] = precision
     feats, coords = torch.from_numpy(blob["voxel_features"]), torch.from_numpy(blob["voxel_coords"])
@@ -326,7 +326,7 @@ def test_tiny_frames_in_every_mode(n):
     with torch.no_grad():
         want = orc.backbone_forward(state, cfg, list(S0_GRID), list(S0_VOXEL), list(S0_RANGE), feats, coords, 1)
     model = model.cuda().eval()
-    for precision, tol in (("fp32", FEATURE_TOL), ("tf32x3", FEATURE_TOL), ("tf32", TF32_TOL), ("bf16", BF16_TOL)):
+    for precision, tol in (("fp32", FEATURE_TOL), ("tf32x3", FEATURE_TOL), ("bf16x3", FEATURE_TOL), ("tf32", TF32_TOL), ("bf16", BF16_TOL)):
         model.set_precision(precision)
         with torch.no_grad():
             sp = model({"voxel_features": feats.cuda(), "voxel_coords": coords.cuda().float(),

@@ -17,7 +17,7 @@ from mssvt_b200.synth import S0_GRID, S0_RANGE, S0_VOXEL, synth_frame
 
 pytestmark = pytest.mark.gpu
 
-MODES = (("fp32", 1e-4, None), ("tf32x3", 1e-4, None), ("tf32", 2e-3, None), ("bf16", 2e-2, 5e-3))
+MODES = (("fp32", 1e-4, None), ("tf32x3", 1e-4, None), ("bf16x3", 1e-4, None), ("tf32", 2e-3, None), ("bf16", 2e-2, 5e-3))
 
 
 def build(cfg):
