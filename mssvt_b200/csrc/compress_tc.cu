@@ -129,6 +129,7 @@ k_tcc_pool(int n1, int win_cap, const int *__restrict__ win_count_total, const i
 // shared-memory carve-up of k_tcc_tile (bytes).  Common to the CTA: the weights; per tile group: operands, rows, header
 struct TccSmem {
     int wpos, w2, wkv, bias, group0, group_bytes, apos, rows, hdr, bar, total;
+    // nt = operand tiles per weight matrix in units of ONE TF32 tile (split TF32: 2; TF32 and split bf16: 1)
     __host__ __device__ TccSmem(int nt, int heads, int groups) {
         wpos = 0;                                     // [hi | lo] x [2 chunks][64][16 B]                          4 KB
         w2 = wpos + 4096;                             // nt x [16 chunks][64][16 B]                         16 KB each
@@ -170,7 +171,8 @@ k_tcc_tile(TccParams P, const int2 *__restrict__ tiles, const int *__restrict__ 
     constexpr int HD = TCC_C / HEADS;
     constexpr int DPT = HD / 4;
     constexpr int HH = HEADS / 2;  // heads per thread
-    constexpr int NT = TERMS == 3 ? 2 : 1;
+    constexpr int NT = TERMS == 3 ? 2 : 1;         // (split bf16: two bf16 tiles = the bytes of one TF32 tile)
+    constexpr bool BF = TERMS == 2;                // split bf16 operands (hi + mid, kind::f16) for W2 and Wkv
     pdl_launch_dependents();
     extern __shared__ __align__(128) char smem_raw[];
     const int tid = threadIdx.x, grp = tid >> 8, gtid = tid & 255;
@@ -217,8 +219,13 @@ k_tcc_tile(TccParams P, const int2 *__restrict__ tiles, const int *__restrict__ 
     tc_fence_after();
     const uint32_t tb = *sTmem + (uint32_t)(grp * 256);
     const uint32_t tm_a = tb, tm_alo = tb + 64u, tm_d = tb + 128u;   // A hi / A lo (split operands) / D1, then K | V
+    // split bf16: operands packed two per column.  A1 = [hi 64..95 | mid 96..127] (MMA 0's accumulator in 0..63 is still
+    // being read by the row's other thread), A2 = [hi 0..31 | mid 32..63]
+    const uint32_t tm_a1 = BF ? tb + 64u : tb, tm_a1m = tb + 96u, tm_a2m = tb + 32u;
     const uint32_t lane_off = (uint32_t)((gw & 3) * 32) << 16;
-    const uint32_t id_n64 = umma_idesc_tf32(128, 64), id_n128 = umma_idesc_tf32(128, 128);
+    const uint32_t id_pos = umma_idesc_tf32(128, 64);
+    const uint32_t id_n64 = BF ? umma_idesc_bf16(128, 64) : umma_idesc_tf32(128, 64);
+    const uint32_t id_n128 = BF ? umma_idesc_bf16(128, 128) : umma_idesc_tf32(128, 128);
     const UmmaDescBase dWpos = umma_desc_base(smem_u32(sWpos), 1024, 128), dApos = umma_desc_base(smem_u32(sApos), 2048, 128),
                        dW2 = umma_desc_base(smem_u32(sW2), 64 * 16, 128), dWkv = umma_desc_base(smem_u32(sWkv), 128 * 16, 128);
     const uint32_t row_off = (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u;   // canonical 8-row groups
@@ -276,9 +283,9 @@ k_tcc_tile(TccParams P, const int2 *__restrict__ tiles, const int *__restrict__ 
             tc_fence_after();
             const uint64_t ah = umma_desc_at(dApos, 0u), al = umma_desc_at(dApos, 4096u);
             const uint64_t wh = umma_desc_at(dWpos, 0u), wl = umma_desc_at(dWpos, 2048u);
-            umma_tf32(tm_a, ah, wh, id_n64, 0u);
-            umma_tf32(tm_a, al, wh, id_n64, 1u);
-            umma_tf32(tm_a, ah, wl, id_n64, 1u);
+            umma_tf32(tm_a, ah, wh, id_pos, 0u);
+            umma_tf32(tm_a, al, wh, id_pos, 1u);
+            umma_tf32(tm_a, ah, wl, id_pos, 1u);
             umma_commit(bar);
         }
         __syncwarp();
@@ -328,16 +335,24 @@ k_tcc_tile(TccParams P, const int2 *__restrict__ tiles, const int *__restrict__ 
             // ---- 2. A1 = relu(first positional layer), written back over the accumulator: the A operand of MMA 1
             float d[32];
             tmem_ld32(tm_a + lane_off + (uint32_t)(32 * half), d);
-            if (TERMS == 3) {
-                float lo[32];
+            if constexpr (BF) {
+                uint32_t w[16], wm[16];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) split_tf32(fmaxf(d[i], 0.f), d[i], lo[i]);
-                tmem_st32(tm_alo + lane_off + (uint32_t)(32 * half), lo);
+                for (int i = 0; i < 16; ++i) split_bf16x2(fmaxf(d[2 * i], 0.f), fmaxf(d[2 * i + 1], 0.f), w[i], wm[i]);
+                tmem_st16(tm_a1 + lane_off + (uint32_t)(16 * half), w);
+                tmem_st16(tm_a1m + lane_off + (uint32_t)(16 * half), wm);
             } else {
+                if (TERMS == 3) {
+                    float lo[32];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) d[i] = to_tf32(fmaxf(d[i], 0.f));
+                    for (int i = 0; i < 32; ++i) split_tf32(fmaxf(d[i], 0.f), d[i], lo[i]);
+                    tmem_st32(tm_alo + lane_off + (uint32_t)(32 * half), lo);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) d[i] = to_tf32(fmaxf(d[i], 0.f));
+                }
+                tmem_st32(tm_a + lane_off + (uint32_t)(32 * half), d);
             }
-            tmem_st32(tm_a + lane_off + (uint32_t)(32 * half), d);
             tmem_st_wait();
         }
         cp_async_wait_group<0>();   // this thread's part of the next header
@@ -345,6 +360,15 @@ k_tcc_tile(TccParams P, const int2 *__restrict__ tiles, const int *__restrict__ 
         group_sync();               // (also: the next header is visible to the group)
         if (((warp_uniform() & 7) == 0) && elect_one()) {   // D1 = A1 W2^T -> [128, 192)
             tc_fence_after();
+            if constexpr (BF) {
+#pragma unroll
+                for (int k = 0; k < TCC_C / 16; ++k) {   // K = 16 per MMA: 8 packed A columns, two 16-byte B chunks
+                    const uint64_t wh = umma_desc_at(dW2, (uint32_t)k * 2u * 64u * 16u);
+                    umma_bf16_ts(tm_d, tm_a1 + (uint32_t)k * 8u, wh, id_n64, k > 0 ? 1u : 0u);
+                    umma_bf16_ts(tm_d, tm_a1m + (uint32_t)k * 8u, wh, id_n64, 1u);
+                    umma_bf16_ts(tm_d, tm_a1 + (uint32_t)k * 8u, umma_desc_at(dW2, 64u * 64u * 2u + (uint32_t)k * 2u * 64u * 16u), id_n64, 1u);
+                }
+            } else
 #pragma unroll
             for (int k = 0; k < TCC_C / 8; ++k) {
                 const uint64_t wh = umma_desc_at(dW2, (uint32_t)k * 2u * 64u * 16u);
@@ -369,7 +393,16 @@ k_tcc_tile(TccParams P, const int2 *__restrict__ tiles, const int *__restrict__ 
             float d[32];
             tmem_ld32(tm_d + lane_off + (uint32_t)(32 * half), d);
             const float *b2 = sB2 + 32 * half;
-            if (TERMS == 3) {
+            if constexpr (BF) {
+                uint32_t w[16], wm[16];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    split_bf16x2(f[q].x + fmaxf(d[4 * q] + b2[4 * q], 0.f), f[q].y + fmaxf(d[4 * q + 1] + b2[4 * q + 1], 0.f), w[2 * q], wm[2 * q]);
+                    split_bf16x2(f[q].z + fmaxf(d[4 * q + 2] + b2[4 * q + 2], 0.f), f[q].w + fmaxf(d[4 * q + 3] + b2[4 * q + 3], 0.f), w[2 * q + 1], wm[2 * q + 1]);
+                }
+                tmem_st16(tm_a + lane_off + (uint32_t)(16 * half), w);
+                tmem_st16(tm_a2m + lane_off + (uint32_t)(16 * half), wm);
+            } else if (TERMS == 3) {
                 float lo[32];
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
@@ -388,13 +421,22 @@ k_tcc_tile(TccParams P, const int2 *__restrict__ tiles, const int *__restrict__ 
                     d[4 * q + 3] = to_tf32(f[q].w + fmaxf(d[4 * q + 3] + b2[4 * q + 3], 0.f));
                 }
             }
-            tmem_st32(tm_a + lane_off + (uint32_t)(32 * half), d);
+            if constexpr (!BF) tmem_st32(tm_a + lane_off + (uint32_t)(32 * half), d);
             tmem_st_wait();
         }
         tc_fence_before();
         group_sync();
         if (((warp_uniform() & 7) == 0) && elect_one()) {   // K | V = A2 Wkv^T -> [128, 256)
             tc_fence_after();
+            if constexpr (BF) {
+#pragma unroll
+                for (int k = 0; k < TCC_C / 16; ++k) {
+                    const uint64_t wh = umma_desc_at(dWkv, (uint32_t)k * 2u * 128u * 16u);
+                    umma_bf16_ts(tm_d, tm_a + (uint32_t)k * 8u, wh, id_n128, k > 0 ? 1u : 0u);
+                    umma_bf16_ts(tm_d, tm_a2m + (uint32_t)k * 8u, wh, id_n128, 1u);
+                    umma_bf16_ts(tm_d, tm_a + (uint32_t)k * 8u, umma_desc_at(dWkv, 128u * 64u * 2u + (uint32_t)k * 2u * 128u * 16u), id_n128, 1u);
+                }
+            } else
 #pragma unroll
             for (int k = 0; k < TCC_C / 8; ++k) {
                 const uint64_t wh = umma_desc_at(dWkv, (uint32_t)k * 2u * 128u * 16u);
@@ -536,13 +578,16 @@ int mssvt_compress_attention_tc(int C, int heads, int n1, int terms, float scale
                                 const int *tile_count, const int *win_rec, const float *win_ctr_in, float *scratch,
                                 float *out, void *stream) {
     if (C != 64 || (heads != 2 && heads != 4 && heads != 8) || n1 <= 0 || n1 > 127 || win_capacity < 0 ||
-        (terms != 1 && terms != 3))
+        (terms != 1 && terms != 2 && terms != 3))
         return MSSVT_ERR_INVALID;
     if (win_capacity == 0) return MSSVT_OK;
     if (!win_cell || !range_min || !pos_w || !pos_b || !pos2_w || !pos2_b || !wq || !bq || !wkv || !bkv || !wp || !bp ||
         !win_count_total || !win_list || !xn || !xyz || !k_row || !tiles_in || !tile_count || !win_rec || !win_ctr_in ||
         !scratch || !out)
         return MSSVT_ERR_INVALID;
+    // terms = 2 (split bf16): pos2_w / wkv packed by mssvt_pack_operand_bf16x2; the two small row-wise projections
+    // (query, output) have no bf16 form and take wq / wp packed with terms = 3
+    const int lin_terms = terms == 2 ? 3 : terms;
     TccParams P;
     P.n1 = n1; P.heads = heads; P.scale = scale;
     for (int i = 0; i < 3; ++i) { P.win_cell[i] = win_cell[i]; P.lo[i] = range_min[i]; }
@@ -559,7 +604,7 @@ int mssvt_compress_attention_tc(int C, int heads, int n1, int terms, float scale
     {
         const TclCopyRows rows = {pooled, win_count_total, nullptr, win_capacity};
         const TclParams L = {wq, bq, nullptr, scale};
-        tcl_launch(L, rows, win_capacity, Qc, s, terms);
+        tcl_launch(L, rows, win_capacity, Qc, s, lin_terms);
     }
 
     // TF32 operands: one tile group per CTA, two CTAs per SM; split operands: two groups share the CTA's weights
@@ -572,7 +617,11 @@ int mssvt_compress_attention_tc(int C, int heads, int n1, int terms, float scale
     cudaFuncSetAttribute(k_tcc_tile<H, T, GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
     launch_pdl(k_tcc_tile<H, T, GG>, dim3(grid), dim3(256 * GG), smem, s, P, tiles, tile_count, win_rec, win_ctr, xn, \
                xyz, k_row, (const float *)Qc, Oc)
-    if (terms == 3) {
+    if (terms == 2) {
+        if (heads == 2) { TCC_LAUNCH(2, 2, 1); }
+        else if (heads == 4) { TCC_LAUNCH(4, 2, 1); }
+        else { TCC_LAUNCH(8, 2, 1); }
+    } else if (terms == 3) {
         if (heads == 2) { TCC_LAUNCH(2, 3, 2); }
         else if (heads == 4) { TCC_LAUNCH(4, 3, 2); }
         else { TCC_LAUNCH(8, 3, 2); }
@@ -586,7 +635,7 @@ int mssvt_compress_attention_tc(int C, int heads, int n1, int terms, float scale
     {
         const TclCopyRows rows = {Oc, win_count_total, nullptr, win_capacity};
         const TclParams L = {wp, bp, nullptr, 1.0f};
-        tcl_launch(L, rows, win_capacity, out, s, terms);
+        tcl_launch(L, rows, win_capacity, out, s, lin_terms);
     }
     return check_launch();
 }

@@ -656,9 +656,10 @@ class MixedScaleSparseTransformerCompressBlock(MixedScaleSparseTransformerBlock)
         return sp_tensor
 
     def _attn_terms(self):
-        """the compress attention kernels have no bf16 forms: in bf16 mode they run with TF32 operands, in bf16x3
-        mode with split TF32 operands (the block's FFN does run in the bf16 forms)"""
-        return {"bf16": 1, "bf16x3": 3}.get(self.precision, self._terms())
+        """the compress attention kernels have no plain bf16 form: in bf16 mode they run with TF32 operands (the
+        block's FFN does run in bf16); in bf16x3 mode the tile kernel runs with split bf16 operands and the two small
+        row-wise projections (query, output) with split TF32 operands"""
+        return {"bf16": 1}.get(self.precision, self._terms())
 
     def _tc_supported(self):
         a = self.ms_attn
@@ -721,13 +722,14 @@ class MixedScaleSparseTransformerCompressBlock(MixedScaleSparseTransformerBlock)
             vs = sp_tensor.voxel_size
             scratch = torch.empty((3 * cap, 64), dtype=torch.float32, device=dev)
             at = self._attn_terms()
+            lt = 3 if at == 2 else at       # (the query / output projections have no bf16 form: split TF32 in bf16x3 mode)
             call("mssvt_compress_attention_tc", 64, a.num_heads[0], n1, at, a.scale,
                  host_floats([vs[i] * self.win1_size[i] for i in range(3)]),
                  host_floats(sp_tensor.point_cloud_range[0:3]), ptr(self.pos_proj[0].weight),
                  ptr(self.pos_proj[0].bias), ptr(self._packed(self.pos_proj[2].weight, terms=at)), ptr(self.pos_proj[2].bias),
-                 ptr(self._packed(a.to_qs[0].weight, terms=at)), ptr(a.to_qs[0].bias), ptr(self._packed(a.to_kvs[0].weight, terms=at)),
+                 ptr(self._packed(a.to_qs[0].weight, terms=lt)), ptr(a.to_qs[0].bias), ptr(self._packed(a.to_kvs[0].weight, terms=at)),
                  ptr(a.to_kvs[0].bias),
-                 ptr(self._packed(a.projs[0].weight, terms=at)), ptr(a.projs[0].bias), cap, ptr(total), ptr(win_list), ptr(xn),
+                 ptr(self._packed(a.projs[0].weight, terms=lt)), ptr(a.projs[0].bias), cap, ptr(total), ptr(win_list), ptr(xn),
                  ptr(sp_tensor.world_coords()), ptr(k_row), *(ptr(v) for v in plan), ptr(scratch), ptr(attn), stream())
         else:
             S, buf = self._attn_descriptor(sp_tensor, 1, n1, n1)

@@ -110,7 +110,7 @@ def test_precision_modes_and_module_mirrors_on_cpu():
     assert model.set_precision("tf32x3").backbone[0]._terms() == 3 and model.set_precision("tf32").backbone[0]._terms() == 1
     # bf16: kind::f16 operands for the blocks and every FFN; the compress attention kernels stay TF32
     assert model.set_precision("bf16").backbone[0]._terms() == 0 and model.backbone[-1]._attn_terms() == 1
-    assert model.set_precision("bf16x3").backbone[0]._terms() == 2 and model.backbone[-1]._attn_terms() == 3
+    assert model.set_precision("bf16x3").backbone[0]._terms() == 2 and model.backbone[-1]._attn_terms() == 2
     with pytest.raises(RuntimeError, match="CUDA tensors only"):   # no CPU path, also for the graph capture
         model.eval()({"voxel_features": torch.zeros(1, 64), "voxel_coords": torch.zeros(1, 4), "batch_size": 1})
     vfe = DynamicVFE(AttrDict(NUM_FILTERS=[32, 64]), 5, list(S0_VOXEL), list(S0_GRID), list(S0_RANGE))
