@@ -51,7 +51,7 @@ class ClockSampler:
 
     def __init__(self, device_index):
         self.idx, self.samples, self.reasons, self.max_mhz = device_index, [], set(), None
-        self._stop, self._thread, self._err = False, None, None
+        self._stop, self._thread, self._err, self._ready = False, None, None, None
 
     def _run(self):
         try:
@@ -62,13 +62,18 @@ class ClockSampler:
             get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
                 nv.nvmlDeviceGetCurrentClocksThrottleReasons
             names = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
-            while not self._stop:
+            self._ready.set()
+            while True:          # (at least one sample, however short the timed region is)
                 self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
                 mask = int(get_reasons(h))
                 self.reasons.update(n for n, bit in names.items() if mask & bit)
+                if self._stop:
+                    break
                 time.sleep(0.001)
         except Exception as e:  # noqa: BLE001
             self._err = repr(e)
+        finally:
+            self._ready.set()
 
     def _physical_index(self, nv):
         vis = os.environ.get("CUDA_VISIBLE_DEVICES")
@@ -80,9 +85,11 @@ class ClockSampler:
 
     def start(self):
         import threading
+        self._ready = threading.Event()
         self._thread = threading.Thread(target=self._run, daemon=True)
         self._thread.start()
-        time.sleep(0.01)       # let NVML initialise before the timed region opens
+        self._ready.wait(timeout=5.0)   # NVML is initialised and sampling before the timed region opens (a frame loop of
+                                        # 20 steps lasts 15 ms: a fixed 10 ms head start lost the race on a slow nvmlInit)
 
     def stop(self):
         self._stop = True

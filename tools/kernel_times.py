@@ -18,7 +18,7 @@ from mssvt_b200.synth import S0_GRID, S0_RANGE, S0_VOXEL, synth_frame  # noqa: E
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--precision", default="tf32")
+    ap.add_argument("--precision", default="bf16x3")
     ap.add_argument("--n", type=int, default=150000)
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--patterns", default="1,1,1")
