@@ -323,6 +323,9 @@ class MixedScaleSparseTransformerBlock(nn.Module):
         need_keys = bool(taps or keys or not self._tc_supported(nq))
         key = ("geo", base, self.cbs_pattern, bool(taps), need_keys)
         if key in cache:
+            ev = sp_tensor.__dict__.get("_geo_events", {}).pop(key, None)
+            if ev is not None:      # made on the side branch of the forward (_fork_side_work): join it here
+                torch.cuda.current_stream().wait_event(ev)
             return cache[key]
         dev = sp_tensor.indices.device
         N, B, K = sp_tensor.indices.shape[0], sp_tensor.batch_size, self.key_num_sample
@@ -909,6 +912,34 @@ class MixedScaleSparseTransformer(nn.Module):
                 hand_over([v for k, v in sp_tensor._cache().items() if k not in known])
                 sp_tensor._prepare_event = torch.cuda.Event()
                 sp_tensor._prepare_event.record(side)
+        # Blocks that differ from the first one only in their chessboard pattern: their query maps, compact numbering and
+        # tile plan derive from the first block's geometry.  The first block's geometry is made now (main stream), theirs
+        # on the side branch while the first block's attention and FFN run; geometry() joins the branch at first use.
+        others, seen = [], {first.cbs_pattern} if isinstance(first, MixedScaleSparseTransformerBlock) else set()
+        if isinstance(first, MixedScaleSparseTransformerBlock) and first.use_feature_interpolation:
+            for blk in self.backbone[1:]:
+                if isinstance(blk, MixedScaleSparseTransformerBlock) and blk.cbs_pattern not in seen and \
+                        blk.__dict__.get("_geo_patterns") is first.__dict__.get("_geo_patterns") and \
+                        first.__dict__.get("_geo_patterns") is not None:
+                    seen.add(blk.cbs_pattern)
+                    others.append(blk)
+        if others:
+            first.prepare(sp_tensor)
+            geo0 = torch.cuda.Event()
+            geo0.record(main)
+            events = sp_tensor.__dict__.setdefault("_geo_events", {})
+            with torch.cuda.stream(side):
+                side.wait_event(geo0)
+                for blk in others:
+                    known = set(sp_tensor._cache().keys())
+                    blk.prepare(sp_tensor)
+                    fresh = [k for k in sp_tensor._cache().keys() if k not in known]
+                    hand_over([sp_tensor._cache()[k] for k in fresh])
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                    for k in fresh:
+                        if k and k[0] == "geo":
+                            events[k] = ev
 
 
 class GraphedForward:
