@@ -436,3 +436,32 @@ def test_shape_outside_the_tensor_core_family_warns():
     with warnings.catch_warnings():
         warnings.simplefilter("error", RuntimeWarning)     # the second forward stays quiet
         run_product(cfg, state, blob["grid"], blob["pc_range"], feats, coords, int(blob["batch_size"]))
+
+
+@pytest.mark.parametrize("block_heads,compress_heads", [((1, 1), 2), ((4, 4), 8), ((2, 2), 4)])
+def test_other_head_counts_of_the_tensor_core_family(block_heads, compress_heads):
+    """the tcgen05 kernels are templated on the heads per group (1 / 2 / 4 in the mixed-scale blocks, 2 / 4 / 8 in the
+    compress block); every instantiation, in every tensor-core mode, against the live oracle (no FFMA fallback)"""
+    import warnings
+    from mssvt_b200.config import AttrDict, block_cfg, compress_cfg
+    feats, coords = synth_frame(21, 4000, crop=0.1)
+    feats, coords = torch.from_numpy(feats), torch.from_numpy(coords)
+    blocks = [block_cfg(num_heads=block_heads, cbs_pattern=p) for p in (1, 0)] + [compress_cfg(num_heads=(compress_heads,))]
+    cfg = AttrDict(NAME="MixedScaleSparseTransformer", HASH_SIZE=400000, NUM_OUTPUT_FEATURES=64, PARAMS=blocks)
+    torch.manual_seed(3)
+    model = MixedScaleSparseTransformer(cfg, 64, list(S0_GRID), list(S0_VOXEL), list(S0_RANGE))
+    state = {k: v.clone() for k, v in model.state_dict().items()}
+    with torch.no_grad():
+        want = orc.backbone_forward(state, cfg, list(S0_GRID), list(S0_VOXEL), list(S0_RANGE), feats, coords, 1)
+    model = model.cuda().eval()
+    scale = want.features.abs().max().item()
+    for precision, tol in (("bf16x3", FEATURE_TOL), ("tf32x3", FEATURE_TOL), ("tf32", TF32_TOL), ("bf16", BF16_TOL)):
+        model.set_precision(precision)
+        with warnings.catch_warnings():
+            warnings.simplefilter("error", RuntimeWarning)      # (a fallback to the FFMA kernels would warn)
+            with torch.no_grad():
+                sp = model({"voxel_features": feats.cuda(), "voxel_coords": coords.cuda().float(),
+                            "batch_size": 1})["encoded_spconv_tensor"]
+        assert torch.equal(sp.indices.cpu(), want.indices)
+        err = (sp.features.cpu() - want.features).abs().max().item()
+        assert err <= tol * scale, (precision, block_heads, compress_heads, err / scale)
