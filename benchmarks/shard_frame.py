@@ -26,7 +26,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--voxels", type=int, default=1000000)
     ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--precision", default="tf32")
+    ap.add_argument("--precision", default="bf16x3")
     args = ap.parse_args()
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
     out = os.fdopen(os.dup(1), "w")

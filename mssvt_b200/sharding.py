@@ -147,6 +147,45 @@ class SlabPlan:
         self.owned_local = rng(p[1], p[4])
         self.alias_local = rows.new_zeros(1)
         self.alias_mine = torch.tensor([p[1] == 0 and p[4] > 0], device=dev)
+        # the same row sets as (first, last) ranges of the local tensor: every set is contiguous here, so the local
+        # frame is a slice of the inputs and the halo rows travel from / into views (no gather, no scatter)
+        off = lambda a, b: (a - start + extra, b - start + extra)
+        self.global_range = (start, end, extra)
+        self.ranges = {"send_left": off(p[1], p[2]) if has_l else None, "send_right": off(p[3], p[4]) if has_r else None,
+                       "recv_left": off(p[0], p[1]) if has_l else None, "recv_right": off(p[4], p[5]) if has_r else None}
+
+    def exchange_many(self, tensors, group=None):
+        """exchange() for several (n_local, C) tensors at once: ONE batch of point-to-point transfers and ONE
+        all-reduce for the lot (the y rows and the next LayerNorm rows of a block travel together).  With the
+        contiguous row sets of a frame sorted in x the halo rows are sent from and received into slices of the
+        tensors themselves."""
+        tensors = [t for t in tensors if t is not None]
+        if self.world == 1 or not tensors:
+            return tensors
+        ranges = getattr(self, "ranges", None)
+        if ranges is None:
+            for t in tensors:
+                self.exchange(t, group)
+            return tensors
+        ops = []
+        for peer, send, recv in ((self.rank - 1, ranges["send_left"], ranges["recv_left"]),
+                                 (self.rank + 1, ranges["send_right"], ranges["recv_right"])):
+            if peer < 0 or peer >= self.world or send is None:
+                continue
+            for t in tensors:
+                if send[1] > send[0]:
+                    ops.append(dist.P2POp(dist.isend, t[send[0]:send[1]], peer, group))
+                if recv[1] > recv[0]:
+                    ops.append(dist.P2POp(dist.irecv, t[recv[0]:recv[1]], peer, group))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        # the samples' first voxels (local row 0 here): exactly one rank contributes a non-zero row
+        alias = torch.stack([t[0] for t in tensors]) * self.alias_mine.to(tensors[0].dtype)
+        dist.all_reduce(alias, group=group)
+        for i, t in enumerate(tensors):
+            t[0].copy_(alias[i])
+        return tensors
 
     def exchange(self, features, group=None):
         """overwrite the halo rows of `features` (n_local, C) with the owners' values"""
@@ -196,8 +235,16 @@ def sharded_backbone_forward(model, voxel_features, voxel_coords, batch_size, ra
     halo = max([(int(b.win2_size[0]) - int(b.win1_size[0]) + 1) // 2 for b in blocks if b.win2_size is not None] + [0])
     plan = SlabPlan(coords, win_x, halo, rank, world, grid_x=int(model.grid_size[0]),
                     sorted_single_sample=bool(sorted_by_x) and batch_size == 1)
-    sp = model._sparse_tensor(voxel_features.index_select(0, plan.local_rows).contiguous(),
-                              coords.index_select(0, plan.local_rows).contiguous(), batch_size)
+    span = getattr(plan, "global_range", None)
+    if span is not None and not span[2]:          # a slice of the inputs (nothing rides in front)
+        local_f, local_c = voxel_features[span[0]:span[1]], coords[span[0]:span[1]]
+    elif span is not None:                        # the sample's first voxel + a slice
+        local_f = torch.cat([voxel_features[:1], voxel_features[span[0]:span[1]]])
+        local_c = torch.cat([coords[:1], coords[span[0]:span[1]]])
+    else:
+        local_f = voxel_features.index_select(0, plan.local_rows)
+        local_c = coords.index_select(0, plan.local_rows)
+    sp = model._sparse_tensor(local_f.contiguous(), local_c.contiguous(), batch_size)
     mark("plan + local frame")
     with torch.no_grad():
         for i, block in enumerate(blocks):
@@ -205,12 +252,18 @@ def sharded_backbone_forward(model, voxel_features, voxel_coords, batch_size, ra
             mark("block %d" % i)
             if isinstance(block, Compress):
                 break
-            plan.exchange(sp.features, group)
-            pre = getattr(sp, "_xn_ready", None)
-            if pre is not None:            # the next block's LayerNorm rows ride along (written by the FFN epilogue)
-                plan.exchange(pre[1], group)
+            pre = getattr(sp, "_xn_ready", None)   # the next block's LayerNorm rows ride along (written by the FFN epilogue)
+            plan.exchange_many([sp.features, pre[1] if pre is not None else None], group)
             mark("exchange %d" % i)
         feats, idx = sp.features, sp.indices
+        if isinstance(blocks[-1], Compress) and span is not None:
+            # rows ascend in x, windows are listed by first occurrence: the owned output rows are one range
+            wx = int(blocks[-1].win1_size[0])
+            px = (idx[:, 3] * wx).contiguous()
+            a, b = torch.searchsorted(px, torch.tensor([plan.lo, plan.hi], device=px.device, dtype=px.dtype)).tolist()
+            out = feats[a:b], idx[a:b], plan
+            mark("owned rows")
+            return out
         if isinstance(blocks[-1], Compress):
             wx = int(blocks[-1].win1_size[0])   # output rows are windows of the compress grid
             keep = (idx[:, 3].long() * wx >= plan.lo) & (idx[:, 3].long() * wx < plan.hi)

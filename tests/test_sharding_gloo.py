@@ -122,3 +122,51 @@ def test_slab_plan_sorted_fast_path_equals_generic_path():
                              "alias_local"):
                     assert torch.equal(getattr(a, name), getattr(b, name)), (seed, world, r, name)
                 assert a.alias_mine.tolist() == b.alias_mine.tolist()
+
+
+def _slab_many_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from mssvt_b200.sharding import SlabPlan
+    from mssvt_b200.synth import synth_frame
+    _, coords = synth_frame(3, 6000, crop=0.25)
+    coords = torch.from_numpy(coords)
+    plan = SlabPlan(coords, 3, 1, rank, world, grid_x=468, sorted_single_sample=True)
+    # the row ranges of the sorted plan are its index lists
+    ok_ranges = all(
+        (plan.ranges[k] is None and getattr(plan, k).numel() == 0) or
+        (plan.ranges[k] is not None and torch.equal(torch.arange(*plan.ranges[k]), getattr(plan, k)))
+        for k in ("send_left", "send_right", "recv_left", "recv_right"))
+    start, end, extra = plan.global_range
+    ok_ranges = ok_ranges and torch.equal(plan.local_rows[extra:], torch.arange(start, end)) and \
+        (extra == 0 or int(plan.local_rows[0]) == 0)
+    # two tensors travel in one batch: "y" = global row id, "xn" = 1000000 + global row id, owned rows only
+    y = torch.full((plan.local_rows.shape[0], 4), -1.0)
+    xn = torch.full((plan.local_rows.shape[0], 4), -1.0)
+    y[plan.owned_local] = plan.local_rows[plan.owned_local].float().unsqueeze(1)
+    xn[plan.owned_local] = 1000000.0 + plan.local_rows[plan.owned_local].float().unsqueeze(1)
+    plan.exchange_many([y, None, xn])
+    ok = bool((y[:, 0] == plan.local_rows.float()).all()) and bool((xn[:, 0] == 1000000.0 + plan.local_rows.float()).all())
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (ok_ranges, ok))
+    if rank == 0:
+        out.put(gathered)
+    dist.destroy_process_group()
+
+
+def test_sorted_plan_exchanges_several_tensors_from_views_world3():
+    """the halo rows of y and of the next LayerNorm rows in ONE batch of point-to-point transfers, sent from and
+    received into slices of the tensors (frames sorted in x), plus the samples' first voxels in one all-reduce"""
+    world = 3
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_slab_many_worker, args=(r, world, port, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    gathered = out.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(g[0] for g in gathered) and all(g[1] for g in gathered), gathered
