@@ -55,7 +55,7 @@ k_group_features(int B, int M, int C, int ns, const float *__restrict__ features
             __syncthreads();
             if ((C & 3) == 0) {
                 const int c4 = C >> 2;
-                for (int e = threadIdx.x; e < cur * c4; e += GF_THREADS) {
+                for (int e = threadIdx.x; e < cur * c4; e += blockDim.x) {
                     int s = e / c4, q = e - s * c4;
                     int row = s_rows[s];
                     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -64,7 +64,7 @@ k_group_features(int B, int M, int C, int ns, const float *__restrict__ features
                     t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
                 }
             } else {
-                for (int e = threadIdx.x; e < cur * C; e += GF_THREADS) {
+                for (int e = threadIdx.x; e < cur * C; e += blockDim.x) {
                     int s = e / C, c = e - s * C;
                     int row = s_rows[s];
                     tile[s * pitch + c] = row >= 0 ? __ldg(features + (size_t)row * C + c) : 0.f;
@@ -72,7 +72,7 @@ k_group_features(int B, int M, int C, int ns, const float *__restrict__ features
             }
             __syncthreads();
             float *dst = out + (size_t)m * C * ns + s0;
-            for (int e = threadIdx.x; e < C * GF_STILE; e += GF_THREADS) {
+            for (int e = threadIdx.x; e < C * GF_STILE; e += blockDim.x) {
                 int c = e / GF_STILE, s = e - c * GF_STILE;
                 if (s < cur) dst[(size_t)c * ns + s] = tile[s * pitch + c];
             }
@@ -293,10 +293,13 @@ int mssvt_group_features(int B, int M, int C, int nsample, const float *features
     if (!features || !features_batch_cnt || !idx || !idx_batch_cnt || !out) return MSSVT_ERR_INVALID;
     size_t smem = (size_t)GF_STILE * (C + 1) * sizeof(float);
     cudaFuncSetAttribute(k_group_features, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    // a pass of one CTA is a chain idx -> rows -> transposed stores with a barrier between the links; narrow rows
+    // (C <= 32: 4 KB per pass) take smaller CTAs, twice as many of them per SM
+    const int threads = C <= 32 ? 128 : GF_THREADS, cap = C <= 32 ? 16 : 8;
     int per_sm = (int)(200 * 1024 / (smem + 1024));
-    per_sm = per_sm > 8 ? 8 : per_sm < 1 ? 1 : per_sm;
+    per_sm = per_sm > cap ? cap : per_sm < 1 ? 1 : per_sm;
     ++g_launches;
-    k_group_features<<<persistent_grid(M, 1, per_sm), GF_THREADS, smem, (cudaStream_t)stream>>>(
+    k_group_features<<<persistent_grid(M, 1, per_sm), threads, smem, (cudaStream_t)stream>>>(
         B, M, C, nsample, features, features_batch_cnt, idx, idx_batch_cnt, out);
     return check_launch();
 }
