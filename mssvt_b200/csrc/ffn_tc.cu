@@ -417,6 +417,64 @@ k_ffn_tc(FfnTcParams P, int n_cap, const int *__restrict__ n_dev, const float *_
                         }
                         return;
                     }
+#ifndef FFN_BLEND_PER_ROW
+                    // The blend happens in the lanes that FETCH the rows (RPI rows per instruction, CPR lanes per row):
+                    // a lane holds the same 16-byte chunk of the row's three projected rows and of x, blends them in
+                    // the reference's order and parks ONE chunk of u = (covered ? blend : x) + x -- one shared-memory
+                    // store and load per part row instead of four of each.  Half of the row groups per memory round trip.
+                    // (48.8 -> 45.5 us per launch with split bf16 operands, 44.2 -> 40.8 us with bf16; with split TF32
+                    //  operands -- one CTA per SM, loads under the second GEMM -- 65.3 -> 66.3 us: the per-row form stays there.)
+                    if constexpr (TERMS != 3) {
+                    if (!live) cov = false;
+#pragma unroll
+                    for (int h2 = 0; h2 < 2; ++h2) {
+                        float4 ua[CPR / 2];
+                        {
+                            float4 va[CPR / 2], vb[CPR / 2], vc[CPR / 2], vx[CPR / 2];
+                            float wa[CPR / 2], wb[CPR / 2], wc[CPR / 2];
+                            bool cv[CPR / 2];
+#pragma unroll
+                            for (int j = 0; j < CPR / 2; ++j) {
+                                const int rr = RPI * (h2 * (CPR / 2) + j) + st_row, grow = tile_row0 + rr;
+                                const float4 *pa = (const float4 *)__shfl_sync(0xffffffffu, (unsigned long long)p0, rr);
+                                const float4 *pb = (const float4 *)__shfl_sync(0xffffffffu, (unsigned long long)p1, rr);
+                                const float4 *pc = (const float4 *)__shfl_sync(0xffffffffu, (unsigned long long)p2, rr);
+                                wa[j] = __shfl_sync(0xffffffffu, w0, rr); wb[j] = __shfl_sync(0xffffffffu, w1, rr);
+                                wc[j] = __shfl_sync(0xffffffffu, w2, rr);
+                                cv[j] = __shfl_sync(0xffffffffu, (int)cov, rr) != 0;
+                                const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+                                va[j] = pa ? __ldg(pa + st_ch) : zero;
+                                vb[j] = pb ? __ldg(pb + st_ch) : zero;
+                                vc[j] = pc ? __ldg(pc + st_ch) : zero;
+                                vx[j] = grow < n ? __ldg((const float4 *)(x + (size_t)grow * C + half * CH) + st_ch) : zero;
+                            }
+#pragma unroll
+                            for (int j = 0; j < CPR / 2; ++j) {
+                                float4 m;
+                                m.x = __fadd_rn(__fadd_rn(__fmul_rn(va[j].x, wa[j]), __fmul_rn(vb[j].x, wb[j])), __fmul_rn(vc[j].x, wc[j]));
+                                m.y = __fadd_rn(__fadd_rn(__fmul_rn(va[j].y, wa[j]), __fmul_rn(vb[j].y, wb[j])), __fmul_rn(vc[j].y, wc[j]));
+                                m.z = __fadd_rn(__fadd_rn(__fmul_rn(va[j].z, wa[j]), __fmul_rn(vb[j].z, wb[j])), __fmul_rn(vc[j].z, wc[j]));
+                                m.w = __fadd_rn(__fadd_rn(__fmul_rn(va[j].w, wa[j]), __fmul_rn(vb[j].w, wb[j])), __fmul_rn(vc[j].w, wc[j]));
+                                if (!cv[j]) m = vx[j];
+                                ua[j] = make_float4(m.x + vx[j].x, m.y + vx[j].y, m.z + vx[j].z, m.w + vx[j].w);
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < CPR / 2; ++j) {
+                            const int rr = RPI * (h2 * (CPR / 2) + j) + st_row;
+                            *(float4 *)(stg + rr * (CH * 4) + ((st_ch ^ ((rr >> SWS) & (CPR - 1))) << 4)) = ua[j];
+                        }
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int q = 0; q < CPR; ++q) {
+                        const float4 t = *(const float4 *)(stg + lane * (CH * 4) + ((q ^ ((lane >> SWS) & (CPR - 1))) << 4));
+                        u[4 * q] = t.x; u[4 * q + 1] = t.y; u[4 * q + 2] = t.z; u[4 * q + 3] = t.w;
+                    }
+                    __syncwarp();
+                    return;
+                    }
+#endif
                     gather_in2(p0, mv, p1, nullptr, v);
 #pragma unroll
                     for (int q = 0; q < CPR; ++q)
