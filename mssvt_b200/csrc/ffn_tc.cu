@@ -949,12 +949,14 @@ int mssvt_ffn_tc(int C, int F, int mode, int terms, float eps, const float *ln_g
     cudaFuncSetAttribute(k_ffn_tc<CC, TT, RR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
     launch_pdl(k_ffn_tc<CC, TT, RR>, dim3(grid), dim3(TC_ROWS * RR), smem, (cudaStream_t)stream, P, num_rows,  \
                num_rows_dev, x, merged, covered, y, xn_next, tm_x, tm_y, tm_xn)
+#ifdef FFN_TPR4   // (the four-threads-per-row kernels are only built for the experiment)
     if (tpr == 4) {
         if (terms == 0) { FFN_TC_LAUNCH(64, 0, 4); }
         else if (terms == 3) { FFN_TC_LAUNCH(64, 3, 4); }
         else { FFN_TC_LAUNCH(64, 1, 4); }
-    }
-    else if (C == 64 && terms == 2) { FFN_TC_LAUNCH(64, 2, 2); }
+    } else
+#endif
+    if (C == 64 && terms == 2) { FFN_TC_LAUNCH(64, 2, 2); }
     else if (terms == 2) { FFN_TC_LAUNCH(32, 2, 2); }
     else if (C == 64 && terms == 0) { FFN_TC_LAUNCH(64, 0, 2); }
     else if (terms == 0) { FFN_TC_LAUNCH(32, 0, 2); }
