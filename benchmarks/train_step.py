@@ -5,8 +5,10 @@ one frame per GPU per step, DDP gradient all-reduce over NCCL when launched unde
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \
         --master-port 29533 benchmarks/train_step.py --amp
 
-Training runs the autograd path of the blocks: index maps from the fused geometry kernels, row gathers
-through mssvt_group_features / mssvt_group_features_grad, dense math in torch (bf16 autocast with --amp).
+Training runs the ragged path of the blocks (default): index maps from the fused geometry kernels, the window
+attention and the three-NN blend forward + backward in the hand-written kernels of csrc/train.cu on compact window
+lists, the projections / FFN as torch GEMMs (bf16 autocast with --amp).  --path padded = torch autograd over the
+reference's padded tensors (the cross-check path), for comparison.
 Loss = mean of the squared `.dense()` output (synthetic).  Prints one JSON line.
 """
 import argparse
@@ -19,6 +21,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from mssvt_b200.config import s0_model_cfg  # noqa: E402
+from mssvt_b200 import mssvt_backbone  # noqa: E402
 from mssvt_b200.mssvt_backbone import MixedScaleSparseTransformer  # noqa: E402
 from mssvt_b200.synth import S0_GRID, S0_RANGE, S0_VOXEL, synth_frame  # noqa: E402
 
@@ -30,6 +33,8 @@ def main():
     ap.add_argument("--voxels", type=int, default=150000)
     ap.add_argument("--amp", action="store_true", help="bf16 autocast for the dense math")
     ap.add_argument("--tf32", action="store_true", help="allow TF32 tensor-core matmuls in torch (default: fp32 SIMT)")
+    ap.add_argument("--path", choices=("ragged", "padded"), default="ragged", help="training path of the blocks")
+    ap.add_argument("--profile", default=None, help="write a torch.profiler kernel table of two steps to this file")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -41,6 +46,7 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
     torch.backends.cuda.matmul.allow_tf32 = bool(args.tf32)
+    mssvt_backbone.TRAIN_PATH = args.path
     torch.manual_seed(0)
     model = MixedScaleSparseTransformer(s0_model_cfg(), 64, list(S0_GRID), list(S0_VOXEL), list(S0_RANGE)).to(dev)
     model.train()
@@ -98,6 +104,14 @@ def main():
         t = torch.tensor([n0.elapsed_time(n1) / args.steps], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_nosync = float(t.item())
+    if args.profile and rank == 0:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+            for i in range(2):
+                step(i)
+            torch.cuda.synchronize()
+        with open(args.profile, "w") as f:
+            f.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=45, max_name_column_width=90))
     if rank == 0:
         grad_bytes = sum(p.numel() for p in model.parameters()) * 4
         print(json.dumps({"metric": "mssvt_backbone_train_step_ms", "value": ms, "unit": "ms/step", "n_gpus": world,
@@ -106,7 +120,7 @@ def main():
                           "gradient_bytes": grad_bytes,
                           "steps": args.steps, "warmup": args.warmup, "higher_is_better": False,
                           "voxels_per_s": args.voxels * world / (ms * 1e-3), "wall_ms_per_step": wall / args.steps * 1e3,
-                          "dtype": "bf16 autocast" if args.amp else "tf32 matmuls" if args.tf32 else "fp32", "loss": float(loss),
+                          "dtype": "bf16 autocast" if args.amp else "tf32 matmuls" if args.tf32 else "fp32", "loss": float(loss), "train_path": args.path,
                           "config": {"workload": "S0 backbone fwd+bwd+AdamW, one synthetic %d-voxel frame per GPU per "
                                                  "step, loss = mean(dense()^2), DDP all-reduce when world > 1" % args.voxels}}),
               file=out, flush=True)

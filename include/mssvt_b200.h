@@ -378,6 +378,60 @@ int mssvt_vfe_features(int num_points, const float *points, int point_stride, in
                        const float *xyz_sum, int voxel_capacity, const float *w0, const float *b0, int c0,
                        const float *w1, const float *b1, int c1, float *scratch, float *out, void *stream);
 
+/* ---- training path: forward + backward of the window attention on the compact (ragged)
+ * form, replacing autograd over the padded tensors of MixedScaleAttention.forward (mssvt_utils.py:100-157:
+ * softmax(q k^T * scale + (-100) * key_mask) v per window and head, with the masked slots of a window all
+ * holding one key).  Windows are CSR lists: queries of window w = rows [q_off[w], q_off[w + 1]) of q, keys =
+ * rows [key_off[w], key_off[w + 1]) of k / v; key_mult[w] > 0: the LAST key of the window is the masked one
+ * (additive -100) and stands for key_mult[w] identical slots.  q_win (num_queries) / k_win (num_keys) = window
+ * of each row.  Rows have heads * head_dim channels (head_dim in {8, 16, 32}) at row strides ld* (floats,
+ * multiples of 4; 16-byte aligned bases).  lse (num_queries, heads): log-sum-exp of every softmax row. */
+int mssvt_ragged_attention_fwd(int heads, int head_dim, float scale, int num_queries, const int *q_win,
+                               const int *key_off, const int *key_mult, const float *q, int ldq, const float *k,
+                               int ldk, const float *v, int ldv, float *out, int ldo, float *lse, void *stream);
+
+/* Backward of the above: grad_q / grad_k / grad_v from grad_out (autograd of mssvt_utils.py:123-139).  Every
+ * key row belongs to one window, so dK / dV are accumulated by the thread that owns the row: no atomics,
+ * deterministic.  delta (num_queries, heads) is scratch (grad_out . out per softmax row). */
+int mssvt_ragged_attention_bwd(int heads, int head_dim, float scale, int num_queries, int num_keys, const int *q_win,
+                               const int *k_win, const int *q_off, const int *key_off, const int *key_mult,
+                               const float *q, int ldq, const float *k, int ldk, const float *v, int ldv,
+                               const float *out, int ldo, const float *lse, const float *grad_out, int ldgo,
+                               float *delta, float *grad_q, int ldgq, float *grad_k, int ldgk, float *grad_v,
+                               int ldgv, void *stream);
+
+/* Three-NN feature interpolation + merge back to voxels (mssvt_backbone.py:318-333; the reference blends in
+ * torch): out[v] = sum_j weights[v, j] * rows[src[v, j]] over the (num_voxels, 3) maps; src < 0: a padded query
+ * slot = zero row; src[v, 0] == -2: voxel not covered by any window, out[v] = x[v] (quirk Q5).  C % 4 == 0. */
+int mssvt_interp_merge_fwd(int num_voxels, int C, const int *src, const float *weights, const float *rows,
+                           const float *x, float *out, void *stream);
+
+/* Its backward: grad_rows (num_rows, C) zeroed then accumulated with vector atomics, grad_x (num_voxels, C)
+ * written in full (grad_out on uncovered voxels, zero elsewhere). */
+int mssvt_interp_merge_bwd(int num_voxels, int C, int num_rows, const int *src, const float *weights,
+                           const float *grad_out, float *grad_rows, float *grad_x, void *stream);
+
+/* Gather + positional embedding of compact rows (mssvt_backbone.py:288-300, the one-layer pos_proj of the two-window
+ * block = Conv1d(6 -> C, 1) + ReLU, on the rows that exist instead of the padded (W, C, n) tensors):
+ * out[r, 0:cs] = xn[rows[r], c0:c0+cs] + relu(pos_w[c0:c0+cs] . [xyz[rows[r]] - centre[win[r]] | centre[win[r]]] + pos_b)
+ * with the relative offset zeroed where masked[r] (the key that stands for the masked slots); rows[r] < 0: zero
+ * features at position 0.  xn (N, C), xyz (N, 3), centre (W, 3), out (num_rows, cs), cs in {32, 64}. */
+int mssvt_embed_rows_fwd(int num_rows, int c0, int cs, int C, const int *rows, const int *win,
+                         const unsigned char *masked, const float *xn, const float *xyz, const float *centre,
+                         const float *pos_w, const float *pos_b, float *out, void *stream);
+
+/* Its backward: ACCUMULATES into grad_xn (N, C) (vector atomics), grad_w (C, 6) and grad_b (C) -- the caller zeroes
+ * them once and calls this for every row set that read the same xn / pos_proj. */
+int mssvt_embed_rows_bwd(int num_rows, int c0, int cs, int C, const int *rows, const int *win,
+                         const unsigned char *masked, const float *xyz, const float *centre, const float *pos_w,
+                         const float *pos_b, const float *grad_out, float *grad_xn, float *grad_w, float *grad_b,
+                         void *stream);
+
+/* Backward of mssvt_layernorm (nn.LayerNorm, mssvt_backbone.py:210, 340): grad_x (num_rows, C), grad_gamma / grad_beta
+ * (C) zeroed then accumulated; the row statistics are recomputed from x.  C in {64, 128}. */
+int mssvt_layernorm_bwd(int num_rows, int C, const float *x, const float *gamma, float eps, const float *grad_y,
+                        float *grad_x, float *grad_gamma, float *grad_beta, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

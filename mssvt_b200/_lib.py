@@ -63,6 +63,13 @@ _SIGNATURES = {
     "mssvt_vfe_bitmap_words": [I, I, I, I],
     "mssvt_vfe_voxelize": [I, P, I, I, I, I, I] + [P] * 9 + [P],
     "mssvt_vfe_features": [I, P, I, I, I, I, I] + [P] * 5 + [I, P, P, I, P, P, I, P, P] + [P],
+    "mssvt_ragged_attention_fwd": [I, I, F, I, P, P, P, P, I, P, I, P, I, P, I, P, P],
+    "mssvt_ragged_attention_bwd": [I, I, F, I, I, P, P, P, P, P, P, I, P, I, P, I, P, I, P, P, I, P, P, I, P, I, P, I, P],
+    "mssvt_embed_rows_fwd": [I, I, I, I] + [P] * 9 + [P],
+    "mssvt_embed_rows_bwd": [I, I, I, I] + [P] * 11 + [P],
+    "mssvt_layernorm_bwd": [I, I, P, P, F, P, P, P, P, P],
+    "mssvt_interp_merge_fwd": [I, I, P, P, P, P, P, P],
+    "mssvt_interp_merge_bwd": [I, I, I, P, P, P, P, P, P],
     "mssvt_last_cuda_error": [],
     "mssvt_version": [],
     "mssvt_launch_count": [],

@@ -10,9 +10,11 @@ synchronises with the host at least 2B times.  Here a block is
                 role the reference's unused `recycle_dict` argument hints at)
     mssvt_layernorm -> mssvt_block_attention -> mssvt_ffn
 with no host synchronisation; a compress block synchronises once to size its output.
-Inference only for now: training needs the backward kernels.
+Training runs the window attention on the compact (ragged) form through the hand-written
+forward / backward kernels of csrc/train.cu (train_ops.py); the dense projections around them are torch GEMMs.
 """
 import ctypes
+import os
 import warnings
 
 import numpy as np
@@ -22,6 +24,11 @@ from torch import nn
 from . import mssvt_ops
 from ._lib import AttnShape, FfnShape, call, ptr, stream, host_floats
 from .mssvt_utils import MixedScaleAttention, SparseTensor, sample_counts
+from .train_ops import WindowLists, embed_rows, interp_merge, layer_norm_rows, ragged_window_attention
+
+# Training path: "ragged" = compact window lists + the kernels of csrc/train.cu (default); "padded" = torch autograd over the
+# reference's padded (W, nk, C) tensors (kept as the cross-check of the ragged path and for attention dropout > 0)
+TRAIN_PATH = os.environ.get("MSSVT_B200_TRAIN_PATH", "ragged")
 
 
 TC_MODES = ("tf32", "tf32x3", "bf16", "bf16x3")     # precision modes that run on the tcgen05 kernels
@@ -237,14 +244,136 @@ class MixedScaleSparseTransformerBlock(nn.Module):
         return y.transpose(1, 2)                                             # (W, C, n)
 
     def _ffn_autograd(self, u):
-        act = self.linear2(self.dropout1(self.activation(self.linear1(self.norm2(u)))))
+        # (LayerNorm forward / backward in mssvt_layernorm / mssvt_layernorm_bwd, except on the torch cross-check path)
+        un = self.norm2(u) if TRAIN_PATH == "padded" else layer_norm_rows(self.norm2, u)
+        act = self.linear2(self.dropout1(self.activation(self.linear1(un))))
         y = u + self.drop_path(self.dropout1(act))
         return self.out_linear(y) if hasattr(self, 'out_linear') else y
 
+    def _pos_embed_rows(self, pos, c0=0, c1=None):
+        """pos_proj on compact rows (R, 6) -> (R, c1 - c0): a one-layer embedding only evaluates the channel slice asked for"""
+        layers, y = list(self.pos_proj), pos
+        one = len(layers) == 2
+        for layer in layers:
+            if isinstance(layer, nn.ReLU):
+                y = torch.relu(y)
+            else:
+                w, b = layer.weight[:, :, 0], layer.bias
+                if one and c1 is not None:
+                    w, b = w[c0:c1], b[c0:c1]
+                y = torch.nn.functional.linear(y, w, b)
+        return y if one or c1 is None else y[:, c0:c1]
+
+    def _ragged_supported(self):
+        a = self.ms_attn
+        return (TRAIN_PATH != "padded" and a.per_head_dim in (8, 16, 32) and self.in_channels % 4 == 0
+                and not (self.training and a.dropout > 0))      # (dropout on the attention matrix: padded path)
+
+    def _window_lists(self, sp_tensor, g, W):
+        """Compact (CSR) form of the block's windows for the training kernels, made once per geometry: real queries
+        window by window, per head group the distinct keys of every window that has a query (rep_row / meta of
+        mssvt_block_geometry: the masked key last, with its multiplicity), and the three-NN map of every voxel in
+        compact query ids."""
+        if ("ragged",) in g:      # (a tuple key: not inherited by the geometry of another cbs_pattern, see geometry())
+            return g[("ragged",)]
+        dev, K, N = g["q_row"].device, self.key_num_sample, sp_tensor.indices.shape[0]
+        meta, q_row = g["meta"][:W], g["q_row"][:W]
+        win_id = torch.arange(W, device=dev)
+        q_real = q_row >= 0
+        nqr = q_real.sum(1)
+        q_off = torch.zeros(W + 1, dtype=torch.int64, device=dev)
+        q_off[1:] = torch.cumsum(nqr, 0)
+        q_rows = q_row[q_real].long()
+        q_win = win_id[:, None].expand(-1, q_row.shape[1])[q_real]
+        L = {"q_rows": q_rows, "q_win": q_win, "groups": []}
+        ar = torch.arange(K, device=dev)[None]
+        for s in range(2):
+            m = meta[:, 2 + s]
+            nrep = torch.where(nqr > 0, m & 0xff, torch.zeros_like(m)).long()
+            mult = (m >> 8).long()
+            sel = ar < nrep[:, None]
+            rows = g["rep_row"][:W, s * K:(s + 1) * K][sel].long()
+            k_win = win_id[:, None].expand(-1, K)[sel]
+            masked = ((ar == (nrep - 1)[:, None]) & (mult > 0)[:, None])[sel]
+            key_off = torch.zeros(W + 1, dtype=torch.int64, device=dev)
+            key_off[1:] = torch.cumsum(nrep, 0)
+            L["groups"].append((rows, k_win, masked, WindowLists(q_off, q_win, key_off, k_win, mult)))
+        if self.use_feature_interpolation:
+            slot = g["vox_slot"][:N].long()
+            cov = slot >= 0
+            sl = slot.clamp(min=0)
+            w_of = sl // self.max_num_win1
+            nn_idx = g["nn_idx"][:W].reshape(-1, 3)[sl].long()                  # (N, 3) query slots of the voxel's window
+            src = torch.where(nn_idx < nqr[w_of][:, None], q_off[w_of][:, None] + nn_idx,
+                              torch.full_like(nn_idx, -1))                      # padded query slot: a zero row
+            src[~cov] = -2                                                      # Q5: uncovered voxels keep x
+            L["merge_src"] = src.to(torch.int32).contiguous()
+            L["merge_w"] = g["nn_w"][:W].reshape(-1, 3)[sl].contiguous()
+        g[("ragged",)] = L
+        return L
+
     def _forward_autograd(self, sp_tensor):
-        """mssvt_backbone.py:201-346 as an autograd graph.  Index maps (windows, chessboard lists, FPS
-        keys, masks, three-NN) come from mssvt_block_geometry and carry no gradient; every row gather is
-        GroupingOperation (our CUDA forward + scatter-add backward) over global rows."""
+        """mssvt_backbone.py:201-346 for training, on the compact form: no padded tensor is built.  Rows of the
+        layer-normed features are gathered per (window, distinct key) and (window, real query), the positional
+        embedding and the q / kv / output projections are GEMMs over those rows, softmax(q k^T) v and its backward
+        run in mssvt_ragged_attention_fwd / _bwd, the three-NN blend in mssvt_interp_merge_fwd / _bwd."""
+        if not self._ragged_supported():
+            return self._forward_autograd_padded(sp_tensor)
+        x = sp_tensor.features.float().contiguous()
+        N, C = x.shape
+        g = self.geometry(sp_tensor)
+        W, dropped = (int(v) for v in g["win_count"][sp_tensor.batch_size:sp_tensor.batch_size + 2].tolist())
+        if dropped:
+            raise RuntimeError("window partition: %d windows exceed max_num_wins" % dropped)
+        L = self._window_lists(sp_tensor, g, W)
+        a = self.ms_attn
+        xn = layer_norm_rows(self.norm1, x)
+        xyz = sp_tensor.world_coords()
+        centre = self._window_centres(sp_tensor, g["win_list"][:W]).squeeze(-1).contiguous()   # (W, 3)
+        # row sets of the block: the real queries (all channels), per head group its distinct keys (the group's slice)
+        sets, c0 = [(L["q_rows"], L["q_win"], None, 0, C)], 0
+        for s in range(len(a.num_heads)):
+            rows, k_win, masked, _ = L["groups"][s]
+            sets.append((rows, k_win, masked, c0, a.group_c_idx[s]))
+            c0 = a.group_c_idx[s]
+        if len(self.pos_proj) == 2 and all(t[4] - t[3] in (32, 64) for t in sets):
+            # gather + positional embedding forward / backward in mssvt_embed_rows_fwd / _bwd
+            emb = embed_rows(xn, self.pos_proj[0].weight[:, :, 0], self.pos_proj[0].bias, xyz, centre, sets)
+        else:
+            def embed(rows, win, masked, c0, c1):
+                with torch.no_grad():
+                    ctr = centre[win]
+                    rel = xyz[rows] - ctr
+                    if masked is not None:
+                        rel = rel * (~masked).unsqueeze(1)                             # masked key: offset zeroed
+                    pos = torch.cat((rel, ctr), 1)
+                return xn[:, c0:c1].index_select(0, rows) + self._pos_embed_rows(pos, c0, c1)
+            emb = [embed(*t) for t in sets]
+        q_fea = emb[0]                                                                 # (#queries, C)
+        outs, c0 = [], 0
+        for s, heads in enumerate(a.num_heads):
+            c1 = a.group_c_idx[s]
+            lists = L["groups"][s][3]
+            q = a.to_qs[s](q_fea[:, c0:c1])
+            kv = a.to_kvs[s](emb[1 + s])                                                # (#keys of the group, 2 sd) = [K | V]
+            o = ragged_window_attention(q, kv, lists, heads, a.scale)
+            outs.append(a.proj_drop(a.projs[s](o)))
+            c0 = c1
+        attn = torch.cat(outs, 1)                                                      # (#queries, C)
+        if self.use_feature_interpolation:
+            merged = interp_merge(attn, x, L["merge_src"], L["merge_w"])
+        else:
+            merged = x.index_copy(0, L["q_rows"], attn)                                # Q5: all other rows keep x
+        u = self.drop_path(merged) + x
+        sp_tensor.features = self._ffn_autograd(u)
+        sp_tensor.gather_dict = None
+        return sp_tensor
+
+    def _forward_autograd_padded(self, sp_tensor):
+        """mssvt_backbone.py:201-346 as an autograd graph over the reference's padded tensors.  Index maps (windows,
+        chessboard lists, FPS keys, masks, three-NN) come from mssvt_block_geometry and carry no gradient; every row
+        gather is GroupingOperation (our CUDA forward + scatter-add backward) over global rows.  Cross-check of the
+        ragged path, and the path for attention dropout > 0."""
         x = sp_tensor.features.float().contiguous()
         N, C = x.shape
         g = self.geometry(sp_tensor, keys=True)
@@ -630,7 +759,53 @@ class MixedScaleSparseTransformerCompressBlock(MixedScaleSparseTransformerBlock)
     """mssvt_backbone.py:349-398: one query per window, output re-indexed to the window grid."""
 
     def _forward_autograd_compress(self, sp_tensor, x, k_row, grid, win_list, win_table, win_count):
-        """training path (see MixedScaleSparseTransformerBlock._forward_autograd)"""
+        """Training path on the compact form (see MixedScaleSparseTransformerBlock._forward_autograd): keys of a window =
+        its voxels + ONE pad key (zero features at position 0, quirk Q6) standing for the n1 - #voxels padded slots."""
+        if not self._ragged_supported():
+            return self._forward_autograd_compress_padded(sp_tensor, x, k_row, grid, win_list, win_table, win_count)
+        B, (N, C), dev = sp_tensor.batch_size, x.shape, x.device
+        W, dropped = (int(v) for v in win_count[B:B + 2].tolist())
+        if dropped:
+            raise RuntimeError("compress block: %d windows exceed max_num_wins" % dropped)
+        n1, a = self.max_num_win1, self.ms_attn
+        k_row = k_row[:W]
+        win_id = torch.arange(W, device=dev)
+        cnt = (k_row >= 0).sum(1)
+        has_pad = cnt < n1
+        nrep = cnt + has_pad.long()
+        ext = torch.cat((k_row, k_row.new_full((W, 1), -1)), 1)                        # slot #voxels is the pad key
+        sel = torch.arange(n1 + 1, device=dev)[None] < nrep[:, None]
+        rows = ext[sel].long()
+        k_win = win_id[:, None].expand(-1, n1 + 1)[sel]
+        key_off = torch.zeros(W + 1, dtype=torch.int64, device=dev)
+        key_off[1:] = torch.cumsum(nrep, 0)
+        lists = WindowLists(torch.arange(W + 1, device=dev), win_id, key_off, k_win,
+                            torch.where(has_pad, n1 - cnt, torch.zeros_like(cnt)))
+        xn = layer_norm_rows(self.norm1, x)
+        idx = torch.where(rows < 0, torch.full_like(rows, N), rows)                    # pad key -> the appended zero row
+        k_x = torch.cat((xn, xn.new_zeros(1, C)), 0).index_select(0, idx)              # (#keys, C)
+        centre = self._window_centres(sp_tensor, win_list[:W]).squeeze(-1)
+        with torch.no_grad():
+            xyz = sp_tensor.world_coords()
+            ctr = centre[k_win]
+            pos = torch.cat((torch.cat((xyz, xyz.new_zeros(1, 3)), 0)[idx] - ctr, ctr), 1)   # Q6: padded slots sit at 0 - centre
+        # Q6: the max-pooled query sees the zero padding of the slots
+        q_init = torch.where(has_pad[:, None], xn.new_zeros(1, 1), xn.new_full((1, 1), float("-inf"))).expand(W, C).contiguous()
+        q_fea = q_init.scatter_reduce(0, k_win[:, None].expand(-1, C), k_x, "amax", include_self=True)
+        q = a.to_qs[0](q_fea)
+        kv = a.to_kvs[0](k_x + self._pos_embed_rows(pos))
+        attn = a.proj_drop(a.projs[0](ragged_window_attention(q, kv, lists, a.num_heads[0], a.scale)))   # (W, C)
+        vs = sp_tensor.voxel_size
+        sp_tensor.features = self._ffn_autograd(attn)
+        sp_tensor.indices = win_list[:W]
+        sp_tensor.spatial_shape = grid
+        sp_tensor.voxel_size = [vs[i] * self.win1_size[i] for i in range(3)]
+        sp_tensor.gather_dict = None
+        sp_tensor.map_table = None     # (built lazily from the new indices: SparseTensor.map_table)
+        return sp_tensor
+
+    def _forward_autograd_compress_padded(self, sp_tensor, x, k_row, grid, win_list, win_table, win_count):
+        """training path over the reference's padded tensors (cross-check of the ragged path)"""
         B, N, dev = sp_tensor.batch_size, x.shape[0], x.device
         W, dropped = (int(v) for v in win_count[B:B + 2].tolist())
         if dropped:
@@ -657,6 +832,10 @@ class MixedScaleSparseTransformerCompressBlock(MixedScaleSparseTransformerBlock)
         sp_tensor.gather_dict = None
         sp_tensor.map_table = None     # (built lazily from the new indices: SparseTensor.map_table)
         return sp_tensor
+
+    def _ragged_supported(self):
+        # (with several head groups the reference splits the SLOTS of a window between the groups: padded path)
+        return super()._ragged_supported() and self.ms_attn.num_head_groups == 1
 
     def _attn_terms(self):
         """the compress attention kernels have no plain bf16 form: in bf16 mode they run with TF32 operands (the

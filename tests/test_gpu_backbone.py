@@ -245,7 +245,8 @@ def test_training_path_gradients_cuda_gather_backward_vs_autograd_indexing(monke
     """Same graph twice: row gathers through GroupingOperation (mssvt_group_features /
     mssvt_group_features_grad, the CUDA scatter-add) and through plain torch indexing (autograd's own
     backward).  Input and parameter gradients must agree (fp32 atomics: order-dependent rounding only)."""
-    from mssvt_b200 import mssvt_ops
+    from mssvt_b200 import mssvt_backbone, mssvt_ops
+    monkeypatch.setattr(mssvt_backbone, "TRAIN_PATH", "padded")   # (the path that gathers through GroupingOperation)
     blob, cfg, state = load_golden("s0_b2_n1200")
     feats, coords = torch.from_numpy(blob["voxel_features"]), torch.from_numpy(blob["voxel_coords"])
 
