@@ -432,6 +432,21 @@ int mssvt_embed_rows_bwd(int num_rows, int c0, int cs, int C, const int *rows, c
 int mssvt_layernorm_bwd(int num_rows, int C, const float *x, const float *gamma, float eps, const float *grad_y,
                         float *grad_x, float *grad_gamma, float *grad_beta, void *stream);
 
+/* nn.Linear over rows for the training path (the q / kv / output projections of mssvt_utils.py:108-146 over compact
+ * window rows, linear1 / linear2 of the FFN, mssvt_backbone.py:340-344): y (num_rows, N) = x (num_rows, K) w^T + bias,
+ * optional ReLU; w (N, K) row-major as nn.Linear stores it, bias may be NULL; K, N in {32, 64, 128}; row strides ldx / ldy
+ * in floats (multiples of 4, 16-byte aligned bases).  terms = 3: split-TF32 operands on mma.sync (fp32-grade), 1: plain
+ * TF32.  The input gradient is the same call on the transposed weight (dx = dy w). */
+int mssvt_linear_rows_fwd(int num_rows, int K, int N, int terms, const float *x, int ldx, const float *w,
+                          const float *bias, int relu, float *y, int ldy, void *stream);
+
+/* Weight / bias gradient of the above: grad_w (N, K) = grad_y^T x, grad_b (N) = column sums of grad_y (may be NULL), one
+ * pass over the rows, per-CTA partial sums reduced in a fixed order (deterministic).  workspace: at least
+ * mssvt_linear_rows_wgrad_workspace_floats(K, N) floats. */
+long long mssvt_linear_rows_wgrad_workspace_floats(int K, int N);
+int mssvt_linear_rows_wgrad(int num_rows, int K, int N, int terms, const float *grad_y, int ldgy, const float *x,
+                            int ldx, float *workspace, float *grad_w, float *grad_b, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

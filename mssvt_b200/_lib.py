@@ -68,16 +68,19 @@ _SIGNATURES = {
     "mssvt_embed_rows_fwd": [I, I, I, I] + [P] * 9 + [P],
     "mssvt_embed_rows_bwd": [I, I, I, I] + [P] * 11 + [P],
     "mssvt_layernorm_bwd": [I, I, P, P, F, P, P, P, P, P],
+    "mssvt_linear_rows_fwd": [I, I, I, I, P, I, P, P, I, P, I, P],
+    "mssvt_linear_rows_wgrad_workspace_floats": [I, I],
+    "mssvt_linear_rows_wgrad": [I, I, I, I, P, I, P, I, P, P, P, P],
     "mssvt_interp_merge_fwd": [I, I, P, P, P, P, P, P],
     "mssvt_interp_merge_bwd": [I, I, I, P, P, P, P, P, P],
     "mssvt_last_cuda_error": [],
     "mssvt_version": [],
     "mssvt_launch_count": [],
 }
-_RESTYPES = {"mssvt_window_partition_workspace_bytes": L, "mssvt_window_list_workspace_bytes": L, "mssvt_grid_index_words": L, "mssvt_version": ctypes.c_char_p,
+_RESTYPES = {"mssvt_linear_rows_wgrad_workspace_floats": L, "mssvt_window_partition_workspace_bytes": L, "mssvt_window_list_workspace_bytes": L, "mssvt_grid_index_words": L, "mssvt_version": ctypes.c_char_p,
              "mssvt_vfe_bitmap_words": L,
              "mssvt_launch_count": L}
-_NO_STATUS = {"mssvt_window_partition_workspace_bytes", "mssvt_window_list_workspace_bytes", "mssvt_grid_index_words", "mssvt_vfe_bitmap_words", "mssvt_fps_log2_block", "mssvt_version",
+_NO_STATUS = {"mssvt_linear_rows_wgrad_workspace_floats", "mssvt_window_partition_workspace_bytes", "mssvt_window_list_workspace_bytes", "mssvt_grid_index_words", "mssvt_vfe_bitmap_words", "mssvt_fps_log2_block", "mssvt_version",
               "mssvt_sizeof_attn_shape", "mssvt_sizeof_ffn_shape", "mssvt_last_cuda_error",
               "mssvt_launch_count"}
 _ERRORS = {-1: "invalid argument", -2: "CUDA launch/runtime error", -3: "workspace too small"}

@@ -24,7 +24,7 @@ from torch import nn
 from . import mssvt_ops
 from ._lib import AttnShape, FfnShape, call, ptr, stream, host_floats
 from .mssvt_utils import MixedScaleAttention, SparseTensor, sample_counts
-from .train_ops import WindowLists, embed_rows, interp_merge, layer_norm_rows, ragged_window_attention
+from .train_ops import WindowLists, embed_rows, interp_merge, layer_norm_rows, linear_rows, ragged_window_attention
 
 # Training path: "ragged" = compact window lists + the kernels of csrc/train.cu (default); "padded" = torch autograd over the
 # reference's padded (W, nk, C) tensors (kept as the cross-check of the ragged path and for attention dropout > 0)
@@ -245,8 +245,10 @@ class MixedScaleSparseTransformerBlock(nn.Module):
 
     def _ffn_autograd(self, u):
         # (LayerNorm forward / backward in mssvt_layernorm / mssvt_layernorm_bwd, except on the torch cross-check path)
-        un = self.norm2(u) if TRAIN_PATH == "padded" else layer_norm_rows(self.norm2, u)
-        act = self.linear2(self.dropout1(self.activation(self.linear1(un))))
+        if TRAIN_PATH == "padded":
+            act = self.linear2(self.dropout1(self.activation(self.linear1(self.norm2(u)))))
+        else:       # linear layers forward / backward in mssvt_linear_rows_fwd / _wgrad (ReLU in the epilogue)
+            act = linear_rows(self.linear2, self.dropout1(linear_rows(self.linear1, layer_norm_rows(self.norm2, u), relu=True)))
         y = u + self.drop_path(self.dropout1(act))
         return self.out_linear(y) if hasattr(self, 'out_linear') else y
 
@@ -354,10 +356,10 @@ class MixedScaleSparseTransformerBlock(nn.Module):
         for s, heads in enumerate(a.num_heads):
             c1 = a.group_c_idx[s]
             lists = L["groups"][s][3]
-            q = a.to_qs[s](q_fea[:, c0:c1])
-            kv = a.to_kvs[s](emb[1 + s])                                                # (#keys of the group, 2 sd) = [K | V]
+            q = linear_rows(a.to_qs[s], q_fea[:, c0:c1])
+            kv = linear_rows(a.to_kvs[s], emb[1 + s])                                   # (#keys of the group, 2 sd) = [K | V]
             o = ragged_window_attention(q, kv, lists, heads, a.scale)
-            outs.append(a.proj_drop(a.projs[s](o)))
+            outs.append(a.proj_drop(linear_rows(a.projs[s], o)))
             c0 = c1
         attn = torch.cat(outs, 1)                                                      # (#queries, C)
         if self.use_feature_interpolation:
@@ -792,9 +794,9 @@ class MixedScaleSparseTransformerCompressBlock(MixedScaleSparseTransformerBlock)
         # Q6: the max-pooled query sees the zero padding of the slots
         q_init = torch.where(has_pad[:, None], xn.new_zeros(1, 1), xn.new_full((1, 1), float("-inf"))).expand(W, C).contiguous()
         q_fea = q_init.scatter_reduce(0, k_win[:, None].expand(-1, C), k_x, "amax", include_self=True)
-        q = a.to_qs[0](q_fea)
-        kv = a.to_kvs[0](k_x + self._pos_embed_rows(pos))
-        attn = a.proj_drop(a.projs[0](ragged_window_attention(q, kv, lists, a.num_heads[0], a.scale)))   # (W, C)
+        q = linear_rows(a.to_qs[0], q_fea)
+        kv = linear_rows(a.to_kvs[0], k_x + self._pos_embed_rows(pos))
+        attn = a.proj_drop(linear_rows(a.projs[0], ragged_window_attention(q, kv, lists, a.num_heads[0], a.scale)))   # (W, C)
         vs = sp_tensor.voxel_size
         sp_tensor.features = self._ffn_autograd(attn)
         sp_tensor.indices = win_list[:W]

@@ -172,3 +172,68 @@ def layer_norm_rows(norm, x):
     if x.dim() == 2 and x.shape[1] in (64, 128) and x.shape[0] > 0 and norm.elementwise_affine and norm.bias is not None:
         return LayerNormRows.apply(x, norm.weight, norm.bias, norm.eps)
     return norm(x)
+
+
+def _rows_view_ok(t):
+    return (t.dim() == 2 and t.dtype == torch.float32 and t.stride(1) == 1 and t.stride(0) % 4 == 0
+            and t.data_ptr() % 16 == 0)
+
+
+def _linear_terms():
+    """split-TF32 operands (fp32-grade results) unless the user has allowed plain TF32 matmuls in torch"""
+    return 1 if torch.backends.cuda.matmul.allow_tf32 else 3
+
+
+class LinearRows(Function):
+    """nn.Linear over (R, K) rows, K / N in {32, 64, 128}: forward and input gradient in mssvt_linear_rows_fwd, weight /
+    bias gradient in mssvt_linear_rows_wgrad (one pass over the rows, deterministic).  x may be a column slice of a wider
+    matrix (row stride passed down)."""
+
+    @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, x, weight, bias, relu):
+        if not _rows_view_ok(x):
+            x = x.contiguous()
+        weight = weight.contiguous()
+        N, K = weight.shape
+        y = torch.empty((x.shape[0], N), dtype=torch.float32, device=x.device)
+        terms = _linear_terms()
+        call("mssvt_linear_rows_fwd", x.shape[0], K, N, terms, _ptr_view(x), x.stride(0), ptr(weight),
+             None if bias is None else ptr(bias.contiguous()), int(bool(relu)), ptr(y), N, stream())
+        ctx.save_for_backward(x, weight, y if relu else None)
+        ctx.has_bias, ctx.terms = bias is not None, terms
+        return y
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, grad_y):
+        x, weight, y = ctx.saved_tensors
+        N, K = weight.shape
+        grad_y = grad_y.float()
+        if y is not None:
+            grad_y = grad_y * (y > 0)                       # ReLU fused into the forward epilogue
+        if not _rows_view_ok(grad_y):
+            grad_y = grad_y.contiguous()
+        R, dev = x.shape[0], x.device
+        g_x = None
+        if ctx.needs_input_grad[0]:
+            g_x = torch.empty((R, K), dtype=torch.float32, device=dev)
+            call("mssvt_linear_rows_fwd", R, N, K, ctx.terms, _ptr_view(grad_y), grad_y.stride(0),
+                 ptr(weight.t().contiguous()), None, 0, ptr(g_x), K, stream())
+        g_w, g_b = torch.empty_like(weight), None
+        if ctx.has_bias:
+            g_b = torch.empty(N, dtype=torch.float32, device=dev)
+        ws = torch.empty(call("mssvt_linear_rows_wgrad_workspace_floats", K, N), dtype=torch.float32, device=dev)
+        call("mssvt_linear_rows_wgrad", R, K, N, ctx.terms, _ptr_view(grad_y), grad_y.stride(0), _ptr_view(x), x.stride(0),
+             ptr(ws), ptr(g_w), ptr(g_b), stream())
+        return g_x, g_w, g_b, None
+
+
+def linear_rows(layer, x, relu=False):
+    """nn.Linear module `layer` applied to rows x (optionally followed by ReLU) through the hand-written kernels where
+    they cover the shape, torch otherwise"""
+    if (x.dim() == 2 and x.shape[0] > 0 and layer.in_features in (32, 64, 128) and layer.out_features in (32, 64, 128)
+            and x.is_cuda):
+        return LinearRows.apply(x, layer.weight, layer.bias, relu)
+    y = layer(x)
+    return torch.relu(y) if relu else y

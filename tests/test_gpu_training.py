@@ -16,7 +16,8 @@ from mssvt_b200 import mssvt_backbone
 from mssvt_b200.config import s0_model_cfg
 from mssvt_b200.mssvt_backbone import MixedScaleSparseTransformer
 from mssvt_b200.synth import S0_GRID, S0_RANGE, S0_VOXEL, synth_frame
-from mssvt_b200.train_ops import WindowLists, embed_rows, interp_merge, layer_norm_rows, ragged_window_attention
+from mssvt_b200.train_ops import (WindowLists, embed_rows, interp_merge, layer_norm_rows, linear_rows,
+                                  ragged_window_attention)
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-4
@@ -196,6 +197,40 @@ def test_embed_rows_forward_backward_vs_torch():
     for got, want, name in ((a1.grad, a2.grad, "dxn"), (w1.grad, w2.grad, "dw"), (b1.grad, b2.grad, "db")):
         err = (got.double() - want).abs().max().item()
         assert err <= TOL * want.abs().max().item(), (name, err, want.abs().max().item())
+
+
+@pytest.mark.parametrize("K", [32, 64, 128])
+@pytest.mark.parametrize("N", [32, 64, 128])
+def test_linear_rows_forward_backward_vs_torch_float64(K, N):
+    """mssvt_linear_rows_fwd / _wgrad (split-TF32 mma.sync) against nn.Linear in float64: a row count that is no multiple
+    of any tile, x as a column slice of a wider matrix, with and without the fused ReLU; fp32-grade bar"""
+    torch.manual_seed(K * 7 + N)
+    R = 70001
+    wide = torch.randn(R, K + 32, device="cuda")
+    layer = torch.nn.Linear(K, N).cuda()
+    ref = torch.nn.Linear(K, N).cuda().double()
+    ref.load_state_dict({k: v.double() for k, v in layer.state_dict().items()})
+    go = torch.randn(R, N, device="cuda")
+    for relu in (False, True):
+        layer.zero_grad()
+        ref.zero_grad()
+        w1 = wide.clone().requires_grad_(True)
+        y = linear_rows(layer, w1[:, 32:], relu=relu)
+        y.backward(go)
+        w2 = wide.double().requires_grad_(True)
+        y2 = ref(w2[:, 32:])
+        if relu:
+            y2 = torch.relu(y2)
+        y2.backward(go.double())
+        for got, want, name in ((y, y2, "y"), (w1.grad, w2.grad, "dx"), (layer.weight.grad, ref.weight.grad, "dw"),
+                                (layer.bias.grad, ref.bias.grad, "db")):
+            err = (got.double() - want).abs().max().item()
+            assert err <= 2e-5 * want.abs().max().item(), (name, relu, err, want.abs().max().item())
+    # deterministic weight gradient (fixed-order reduction of the per-CTA partial sums)
+    g1 = layer.weight.grad.clone()
+    layer.zero_grad()
+    linear_rows(layer, wide[:, 32:], relu=True).backward(go)
+    assert torch.equal(g1, layer.weight.grad)
 
 
 def _train_run(cfg, state, grid, pc_range, feats, coords, batch, path, monkeypatch, train=True):
