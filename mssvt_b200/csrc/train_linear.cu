@@ -227,10 +227,12 @@ k_linear_wgrad_reduce(int ctas, int nk, int n, const float *__restrict__ part_w,
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < nk) {
         float s = 0.f;
-        for (int c = 0; c < ctas; ++c) s += __ldg(part_w + (size_t)c * nk + i);
+#pragma unroll 8
+        for (int c = 0; c < ctas; ++c) s += __ldg(part_w + (size_t)c * nk + i);   // (fixed order: deterministic)
         gw[i] = s;
     } else if (i < nk + n && gb) {
         float s = 0.f;
+#pragma unroll 8
         for (int c = 0; c < ctas; ++c) s += __ldg(part_b + (size_t)c * n + (i - nk));
         gb[i - nk] = s;
     }

@@ -271,33 +271,43 @@ class MixedScaleSparseTransformerBlock(nn.Module):
         return (TRAIN_PATH != "padded" and a.per_head_dim in (8, 16, 32) and self.in_channels % 4 == 0
                 and not (self.training and a.dropout > 0))      # (dropout on the attention matrix: padded path)
 
-    def _window_lists(self, sp_tensor, g, W):
+    def _window_lists(self, sp_tensor, g):
         """Compact (CSR) form of the block's windows for the training kernels, made once per geometry: real queries
         window by window, per head group the distinct keys of every window that has a query (rep_row / meta of
         mssvt_block_geometry: the masked key last, with its multiplicity), and the three-NN map of every voxel in
-        compact query ids."""
+        compact query ids.  ONE host synchronisation (window count + the three list lengths in one copy); the lists
+        themselves are cut with nonzero_static at the known lengths, over the capacity-sized geometry arrays with the
+        rows past the window count masked out."""
         if ("ragged",) in g:      # (a tuple key: not inherited by the geometry of another cbs_pattern, see geometry())
             return g[("ragged",)]
-        dev, K, N = g["q_row"].device, self.key_num_sample, sp_tensor.indices.shape[0]
-        meta, q_row = g["meta"][:W], g["q_row"][:W]
-        win_id = torch.arange(W, device=dev)
-        q_real = q_row >= 0
+        dev, K, N, B = g["q_row"].device, self.key_num_sample, sp_tensor.indices.shape[0], sp_tensor.batch_size
+        cap, meta, q_row = g["cap"], g["meta"], g["q_row"]
+        nq = q_row.shape[1]
+        valid = torch.arange(cap, device=dev) < g["total"]                      # rows past the window count: garbage
+        q_real = (q_row >= 0) & valid[:, None]
         nqr = q_real.sum(1)
-        q_off = torch.zeros(W + 1, dtype=torch.int64, device=dev)
-        q_off[1:] = torch.cumsum(nqr, 0)
-        q_rows = q_row[q_real].long()
-        q_win = win_id[:, None].expand(-1, q_row.shape[1])[q_real]
-        L = {"q_rows": q_rows, "q_win": q_win, "groups": []}
-        ar = torch.arange(K, device=dev)[None]
+        nreps, mults = [], []
         for s in range(2):
             m = meta[:, 2 + s]
-            nrep = torch.where(nqr > 0, m & 0xff, torch.zeros_like(m)).long()
-            mult = (m >> 8).long()
-            sel = ar < nrep[:, None]
-            rows = g["rep_row"][:W, s * K:(s + 1) * K][sel].long()
-            k_win = win_id[:, None].expand(-1, K)[sel]
-            masked = ((ar == (nrep - 1)[:, None]) & (mult > 0)[:, None])[sel]
-            key_off = torch.zeros(W + 1, dtype=torch.int64, device=dev)
+            nreps.append(torch.where(valid & (nqr > 0), m & 0xff, torch.zeros_like(m)).long())
+            mults.append(torch.where(valid, m >> 8, torch.zeros_like(m)).long())
+        W, dropped, n_q, n_k0, n_k1 = torch.stack(
+            [g["win_count"][B].long(), g["win_count"][B + 1].long(), nqr.sum(), nreps[0].sum(), nreps[1].sum()]).tolist()
+        if dropped:
+            raise RuntimeError("window partition: %d windows exceed max_num_wins" % dropped)
+        q_off = torch.zeros(cap + 1, dtype=torch.int64, device=dev)
+        q_off[1:] = torch.cumsum(nqr, 0)
+        qi = torch.nonzero_static(q_real.reshape(-1), size=n_q).squeeze(1)      # row-major: window by window, slot order
+        q_win = qi // nq
+        L = {"W": W, "q_rows": q_row.reshape(-1)[qi].long(), "q_win": q_win, "groups": []}
+        ar = torch.arange(K, device=dev)[None]
+        for s, n_k in enumerate((n_k0, n_k1)):
+            nrep, mult = nreps[s], mults[s]
+            ki = torch.nonzero_static((ar < nrep[:, None]).reshape(-1), size=n_k).squeeze(1)
+            k_win, j = ki // K, ki % K
+            rows = g["rep_row"][k_win, s * K + j].long()
+            masked = (j == nrep[k_win] - 1) & (mult[k_win] > 0)
+            key_off = torch.zeros(cap + 1, dtype=torch.int64, device=dev)
             key_off[1:] = torch.cumsum(nrep, 0)
             L["groups"].append((rows, k_win, masked, WindowLists(q_off, q_win, key_off, k_win, mult)))
         if self.use_feature_interpolation:
@@ -305,12 +315,12 @@ class MixedScaleSparseTransformerBlock(nn.Module):
             cov = slot >= 0
             sl = slot.clamp(min=0)
             w_of = sl // self.max_num_win1
-            nn_idx = g["nn_idx"][:W].reshape(-1, 3)[sl].long()                  # (N, 3) query slots of the voxel's window
+            nn_idx = g["nn_idx"].reshape(-1, 3)[sl].long()                      # (N, 3) query slots of the voxel's window
             src = torch.where(nn_idx < nqr[w_of][:, None], q_off[w_of][:, None] + nn_idx,
                               torch.full_like(nn_idx, -1))                      # padded query slot: a zero row
-            src[~cov] = -2                                                      # Q5: uncovered voxels keep x
+            src = torch.where(cov[:, None], src, torch.full_like(src, -2))      # Q5: uncovered voxels keep x
             L["merge_src"] = src.to(torch.int32).contiguous()
-            L["merge_w"] = g["nn_w"][:W].reshape(-1, 3)[sl].contiguous()
+            L["merge_w"] = g["nn_w"].reshape(-1, 3)[sl].contiguous()
         g[("ragged",)] = L
         return L
 
@@ -324,14 +334,15 @@ class MixedScaleSparseTransformerBlock(nn.Module):
         x = sp_tensor.features.float().contiguous()
         N, C = x.shape
         g = self.geometry(sp_tensor)
-        W, dropped = (int(v) for v in g["win_count"][sp_tensor.batch_size:sp_tensor.batch_size + 2].tolist())
-        if dropped:
-            raise RuntimeError("window partition: %d windows exceed max_num_wins" % dropped)
-        L = self._window_lists(sp_tensor, g, W)
+        L = self._window_lists(sp_tensor, g)
         a = self.ms_attn
         xn = layer_norm_rows(self.norm1, x)
         xyz = sp_tensor.world_coords()
-        centre = self._window_centres(sp_tensor, g["win_list"][:W]).squeeze(-1).contiguous()   # (W, 3)
+        cache = sp_tensor._cache()
+        ckey = ("win-centres", tuple(self.win1_size), self.max_num_wins)
+        if ckey not in cache:      # (capacity rows: the ones past the window count are never referenced)
+            cache[ckey] = self._window_centres(sp_tensor, g["win_list"]).squeeze(-1).contiguous()
+        centre = cache[ckey]                                                           # (cap, 3)
         # row sets of the block: the real queries (all channels), per head group its distinct keys (the group's slice)
         sets, c0 = [(L["q_rows"], L["q_win"], None, 0, C)], 0
         for s in range(len(a.num_heads)):
@@ -766,27 +777,29 @@ class MixedScaleSparseTransformerCompressBlock(MixedScaleSparseTransformerBlock)
         if not self._ragged_supported():
             return self._forward_autograd_compress_padded(sp_tensor, x, k_row, grid, win_list, win_table, win_count)
         B, (N, C), dev = sp_tensor.batch_size, x.shape, x.device
-        W, dropped = (int(v) for v in win_count[B:B + 2].tolist())
+        n1, a, cap = self.max_num_win1, self.ms_attn, win_list.shape[0]
+        valid = torch.arange(cap, device=dev) < win_count[B]                           # rows past the window count: garbage
+        cnt = ((k_row >= 0) & valid[:, None]).sum(1)
+        has_pad = (cnt < n1) & valid
+        nrep = cnt + has_pad.long()
+        # the one host synchronisation of the block: window count and list length in one copy
+        W, dropped, n_k = torch.stack([win_count[B].long(), win_count[B + 1].long(), nrep.sum()]).tolist()
         if dropped:
             raise RuntimeError("compress block: %d windows exceed max_num_wins" % dropped)
-        n1, a = self.max_num_win1, self.ms_attn
-        k_row = k_row[:W]
-        win_id = torch.arange(W, device=dev)
-        cnt = (k_row >= 0).sum(1)
-        has_pad = cnt < n1
-        nrep = cnt + has_pad.long()
-        ext = torch.cat((k_row, k_row.new_full((W, 1), -1)), 1)                        # slot #voxels is the pad key
+        ext = torch.cat((k_row, k_row.new_full((cap, 1), -1)), 1)                      # slot #voxels is the pad key
         sel = torch.arange(n1 + 1, device=dev)[None] < nrep[:, None]
-        rows = ext[sel].long()
-        k_win = win_id[:, None].expand(-1, n1 + 1)[sel]
-        key_off = torch.zeros(W + 1, dtype=torch.int64, device=dev)
+        ki = torch.nonzero_static(sel.reshape(-1), size=n_k).squeeze(1)
+        k_win = ki // (n1 + 1)
+        rows = ext.reshape(-1)[ki].long()
+        key_off = torch.zeros(cap + 1, dtype=torch.int64, device=dev)
         key_off[1:] = torch.cumsum(nrep, 0)
-        lists = WindowLists(torch.arange(W + 1, device=dev), win_id, key_off, k_win,
+        lists = WindowLists(torch.arange(cap + 1, device=dev), torch.arange(W, device=dev), key_off, k_win,
                             torch.where(has_pad, n1 - cnt, torch.zeros_like(cnt)))
+        has_pad = has_pad[:W]
         xn = layer_norm_rows(self.norm1, x)
         idx = torch.where(rows < 0, torch.full_like(rows, N), rows)                    # pad key -> the appended zero row
         k_x = torch.cat((xn, xn.new_zeros(1, C)), 0).index_select(0, idx)              # (#keys, C)
-        centre = self._window_centres(sp_tensor, win_list[:W]).squeeze(-1)
+        centre = self._window_centres(sp_tensor, win_list).squeeze(-1)                 # (cap, 3)
         with torch.no_grad():
             xyz = sp_tensor.world_coords()
             ctr = centre[k_win]
