@@ -33,6 +33,7 @@ def main():
     ap.add_argument("--voxels", type=int, default=150000)
     ap.add_argument("--amp", action="store_true", help="bf16 autocast for the dense math")
     ap.add_argument("--tf32", action="store_true", help="allow TF32 tensor-core matmuls in torch (default: fp32 SIMT)")
+    ap.add_argument("--batch", type=int, default=1, help="frames per GPU per step (batch_size of the forward)")
     ap.add_argument("--path", choices=("ragged", "padded"), default="ragged", help="training path of the blocks")
     ap.add_argument("--profile", default=None, help="write a torch.profiler kernel table of two steps to this file")
     args = ap.parse_args()
@@ -54,14 +55,20 @@ def main():
     opt = torch.optim.AdamW(model.parameters(), lr=1e-4)
     frames = []
     for i in range(4):
-        f, c = synth_frame(1000 * rank + i, args.voxels)
-        frames.append((torch.from_numpy(f).to(dev), torch.from_numpy(c).to(dev)))
+        fs, cs = [], []
+        for b in range(args.batch):           # samples of a step: concatenated, batch index in column 0
+            f, c = synth_frame(1000 * rank + args.batch * i + b, args.voxels)
+            c = c.copy()
+            c[:, 0] = b
+            fs.append(torch.from_numpy(f))
+            cs.append(torch.from_numpy(c))
+        frames.append((torch.cat(fs).to(dev), torch.cat(cs).to(dev)))
 
     def step(i):
         f, c = frames[i % len(frames)]
         opt.zero_grad(set_to_none=True)
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=args.amp):
-            sp = net({"voxel_features": f, "voxel_coords": c, "batch_size": 1})["encoded_spconv_tensor"]
+            sp = net({"voxel_features": f, "voxel_coords": c, "batch_size": args.batch})["encoded_spconv_tensor"]
             loss = (sp.dense().float() ** 2).mean()
         loss.backward()
         opt.step()
@@ -119,10 +126,10 @@ def main():
                           "allreduce_share": None if ms_nosync is None else max(0.0, (ms - ms_nosync) / ms),
                           "gradient_bytes": grad_bytes,
                           "steps": args.steps, "warmup": args.warmup, "higher_is_better": False,
-                          "voxels_per_s": args.voxels * world / (ms * 1e-3), "wall_ms_per_step": wall / args.steps * 1e3,
+                          "voxels_per_s": args.voxels * args.batch * world / (ms * 1e-3), "frames_per_gpu_per_step": args.batch, "wall_ms_per_step": wall / args.steps * 1e3,
                           "dtype": "bf16 autocast" if args.amp else "tf32 matmuls" if args.tf32 else "fp32", "loss": float(loss), "train_path": args.path,
-                          "config": {"workload": "S0 backbone fwd+bwd+AdamW, one synthetic %d-voxel frame per GPU per "
-                                                 "step, loss = mean(dense()^2), DDP all-reduce when world > 1" % args.voxels}}),
+                          "config": {"workload": "S0 backbone fwd+bwd+AdamW, %d synthetic %d-voxel frame(s) per GPU per "
+                                                 "step, loss = mean(dense()^2), DDP all-reduce when world > 1" % (args.batch, args.voxels)}}),
               file=out, flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -179,6 +179,9 @@ def _rows_view_ok(t):
             and t.data_ptr() % 16 == 0)
 
 
+_WGRAD_WS = {}       # (K, N) -> workspace floats of mssvt_linear_rows_wgrad
+
+
 def _linear_terms():
     """split-TF32 operands (fp32-grade results) unless the user has allowed plain TF32 matmuls in torch"""
     return 1 if torch.backends.cuda.matmul.allow_tf32 else 3
@@ -223,7 +226,9 @@ class LinearRows(Function):
         g_w, g_b = torch.empty_like(weight), None
         if ctx.has_bias:
             g_b = torch.empty(N, dtype=torch.float32, device=dev)
-        ws = torch.empty(call("mssvt_linear_rows_wgrad_workspace_floats", K, N), dtype=torch.float32, device=dev)
+        if (K, N) not in _WGRAD_WS:
+            _WGRAD_WS[(K, N)] = call("mssvt_linear_rows_wgrad_workspace_floats", K, N)
+        ws = torch.empty(_WGRAD_WS[(K, N)], dtype=torch.float32, device=dev)
         call("mssvt_linear_rows_wgrad", R, K, N, ctx.terms, _ptr_view(grad_y), grad_y.stride(0), _ptr_view(x), x.stride(0),
              ptr(ws), ptr(g_w), ptr(g_b), stream())
         return g_x, g_w, g_b, None
