@@ -415,7 +415,9 @@ int mssvt_interp_merge_bwd(int num_voxels, int C, int num_rows, const int *src, 
  * block = Conv1d(6 -> C, 1) + ReLU, on the rows that exist instead of the padded (W, C, n) tensors):
  * out[r, 0:cs] = xn[rows[r], c0:c0+cs] + relu(pos_w[c0:c0+cs] . [xyz[rows[r]] - centre[win[r]] | centre[win[r]]] + pos_b)
  * with the relative offset zeroed where masked[r] (the key that stands for the masked slots); rows[r] < 0: zero
- * features at position 0.  xn (N, C), xyz (N, 3), centre (W, 3), out (num_rows, cs), cs in {32, 64}. */
+ * features at position 0.  xn (N, C), xyz (N, 3), centre (W, 3), out (num_rows, cs), cs in {32, 64}.
+ * xn == NULL: the embedding alone (first layer of the compress block's two-layer pos_proj, mssvt_backbone.py:51-54);
+ * pos_w == NULL: the row gather alone. */
 int mssvt_embed_rows_fwd(int num_rows, int c0, int cs, int C, const int *rows, const int *win,
                          const unsigned char *masked, const float *xn, const float *xyz, const float *centre,
                          const float *pos_w, const float *pos_b, float *out, void *stream);
@@ -446,6 +448,16 @@ int mssvt_linear_rows_fwd(int num_rows, int K, int N, int terms, const float *x,
 long long mssvt_linear_rows_wgrad_workspace_floats(int K, int N);
 int mssvt_linear_rows_wgrad(int num_rows, int K, int N, int terms, const float *grad_y, int ldgy, const float *x,
                             int ldx, float *workspace, float *grad_w, float *grad_b, void *stream);
+
+/* Max over the rows of every window (the max-pooled query of the compress block, mssvt_backbone.py:373, on compact
+ * rows: rows [key_off[w], key_off[w + 1]) of `rows` (R, C) belong to window w).  out (num_windows, C); arg
+ * (num_windows, C) int: the row that supplied each channel (first on ties, -1 for an empty window). */
+int mssvt_segment_max_fwd(int num_windows, int C, const int *key_off, const float *rows, float *out, int *arg,
+                          void *stream);
+
+/* Its backward: grad_rows (num_rows, C) written in full (grad_out[k_win[r]] where row r supplied the channel, else 0). */
+int mssvt_segment_max_bwd(int num_rows, int C, const int *k_win, const int *arg, const float *grad_out,
+                          float *grad_rows, void *stream);
 
 #ifdef __cplusplus
 }

@@ -71,6 +71,8 @@ _SIGNATURES = {
     "mssvt_linear_rows_fwd": [I, I, I, I, P, I, P, P, I, P, I, P],
     "mssvt_linear_rows_wgrad_workspace_floats": [I, I],
     "mssvt_linear_rows_wgrad": [I, I, I, I, P, I, P, I, P, P, P, P],
+    "mssvt_segment_max_fwd": [I, I, P, P, P, P, P],
+    "mssvt_segment_max_bwd": [I, I, P, P, P, P, P],
     "mssvt_interp_merge_fwd": [I, I, P, P, P, P, P, P],
     "mssvt_interp_merge_bwd": [I, I, I, P, P, P, P, P, P],
     "mssvt_last_cuda_error": [],

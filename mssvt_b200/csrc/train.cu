@@ -246,10 +246,12 @@ k_embed_rows_fwd(EmbedRows E, const float *__restrict__ xn, float *__restrict__ 
     const int r = (int)(e / LPR), l = (int)(e % LPR), c = E.c0 + 4 * l;
     const int row = __ldg(E.rows + r);
     float pos[6];
-    embed_pos(E, r, row, pos);
-    float4 v = row >= 0 ? __ldg((const float4 *)(xn + (size_t)row * E.ldx + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    v.x += fmaxf(embed_pre(E, c, pos), 0.f); v.y += fmaxf(embed_pre(E, c + 1, pos), 0.f);
-    v.z += fmaxf(embed_pre(E, c + 2, pos), 0.f); v.w += fmaxf(embed_pre(E, c + 3, pos), 0.f);
+    if (E.w) embed_pos(E, r, row, pos);
+    float4 v = (xn && row >= 0) ? __ldg((const float4 *)(xn + (size_t)row * E.ldx + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (E.w) {   // (without weights: the gather alone)
+        v.x += fmaxf(embed_pre(E, c, pos), 0.f); v.y += fmaxf(embed_pre(E, c + 1, pos), 0.f);
+        v.z += fmaxf(embed_pre(E, c + 2, pos), 0.f); v.w += fmaxf(embed_pre(E, c + 3, pos), 0.f);
+    }
     ((float4 *)out)[e] = v;
 }
 
@@ -274,9 +276,10 @@ k_embed_rows_bwd(EmbedRows E, const float *__restrict__ gout, float *__restrict_
     for (int r = blockIdx.x * (blockDim.x / LPR) + threadIdx.x / LPR; r < E.n_rows; r += rows_per_pass) {
         const int row = __ldg(E.rows + r);
         float pos[6];
-        embed_pos(E, r, row, pos);
+        if (E.w) embed_pos(E, r, row, pos);
         const float4 g = __ldg((const float4 *)gout + (size_t)r * LPR + l);
-        if (row >= 0) atomicAdd((float4 *)(gxn + (size_t)row * E.ldx + c), g);
+        if (gxn && row >= 0) atomicAdd((float4 *)(gxn + (size_t)row * E.ldx + c), g);
+        if (!E.w) continue;
         const float gk[4] = {g.x, g.y, g.z, g.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -287,6 +290,7 @@ k_embed_rows_bwd(EmbedRows E, const float *__restrict__ gout, float *__restrict_
             }
         }
     }
+    if (!E.w) return;   // (uniform over the grid)
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         atomicAdd(s_acc + (4 * l + k) * 7 + 6, ab[k]);
@@ -299,6 +303,43 @@ k_embed_rows_bwd(EmbedRows E, const float *__restrict__ gout, float *__restrict_
         if (j == 6) atomicAdd(gb + ch, s_acc[i]);
         else atomicAdd(gw + 6 * ch + j, s_acc[i]);
     }
+}
+
+
+// ---- max over the rows of a window (the max-pooled query of the compress block, mssvt_backbone.py:373: the compact key
+//      rows of a window are contiguous and include its zero pad row when the window has padded slots, quirk Q6).
+//      arg = the row that supplied each channel (first one on ties, like torch.max): the backward routes the gradient
+//      there; a row belongs to one window, so the backward writes every row once and needs no atomics.
+__global__ void __launch_bounds__(256)
+k_segment_max_fwd(int n_win, int c4n, const int *__restrict__ key_off, const float4 *__restrict__ rows,
+                  float4 *__restrict__ out, int4 *__restrict__ arg) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (long long)n_win * c4n) return;
+    const int w = (int)(e / c4n), c = (int)(e % c4n);
+    const int k0 = __ldg(key_off + w), k1 = __ldg(key_off + w + 1);
+    float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+    int4 a = make_int4(-1, -1, -1, -1);
+    for (int k = k0; k < k1; ++k) {
+        const float4 v = __ldg(rows + (size_t)k * c4n + c);
+        if (k == k0 || v.x > m.x) { m.x = v.x; a.x = k; }
+        if (k == k0 || v.y > m.y) { m.y = v.y; a.y = k; }
+        if (k == k0 || v.z > m.z) { m.z = v.z; a.z = k; }
+        if (k == k0 || v.w > m.w) { m.w = v.w; a.w = k; }
+    }
+    out[e] = m;
+    arg[e] = a;
+}
+
+__global__ void __launch_bounds__(256)
+k_segment_max_bwd(int n_rows, int c4n, const int *__restrict__ k_win, const int4 *__restrict__ arg,
+                  const float4 *__restrict__ gout, float4 *__restrict__ grows) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (long long)n_rows * c4n) return;
+    const int k = (int)(e / c4n), c = (int)(e % c4n);
+    const int w = __ldg(k_win + k);
+    const int4 a = __ldg(arg + (size_t)w * c4n + c);
+    const float4 g = __ldg(gout + (size_t)w * c4n + c);
+    grows[e] = make_float4(a.x == k ? g.x : 0.f, a.y == k ? g.y : 0.f, a.z == k ? g.z : 0.f, a.w == k ? g.w : 0.f);
 }
 
 // ---- LayerNorm backward over rows of C = 4 * LPR channels (statistics recomputed from x): LPR lanes per row with a
@@ -469,7 +510,7 @@ int mssvt_embed_rows_fwd(int num_rows, int c0, int cs, int C, const int *rows, c
                          const float *pos_w, const float *pos_b, float *out, void *stream) {
     if (num_rows < 0 || c0 < 0 || (c0 & 3) || (C & 3) || c0 + cs > C || (cs != 32 && cs != 64)) return MSSVT_ERR_INVALID;
     if (num_rows == 0) return MSSVT_OK;
-    if (!rows || !win || !xn || !xyz || !centre || !pos_w || !pos_b || !out) return MSSVT_ERR_INVALID;
+    if (!rows || !win || !out || (!xn && !pos_w) || (pos_w && (!xyz || !centre || !pos_b))) return MSSVT_ERR_INVALID;
     const EmbedRows E = {rows, win, masked, xyz, centre, pos_w, pos_b, num_rows, c0, C};
     const long long items = (long long)num_rows * (cs / 4);
     if (cs == 32) k_embed_rows_fwd<8><<<div_up(items, 256), 256, 0, (cudaStream_t)stream>>>(E, xn, out);
@@ -484,7 +525,7 @@ int mssvt_embed_rows_bwd(int num_rows, int c0, int cs, int C, const int *rows, c
                          void *stream) {
     if (num_rows < 0 || c0 < 0 || (c0 & 3) || (C & 3) || c0 + cs > C || (cs != 32 && cs != 64)) return MSSVT_ERR_INVALID;
     if (num_rows == 0) return MSSVT_OK;
-    if (!rows || !win || !xyz || !centre || !pos_w || !pos_b || !grad_out || !grad_xn || !grad_w || !grad_b)
+    if (!rows || !win || !grad_out || (!grad_xn && !pos_w) || (pos_w && (!xyz || !centre || !pos_b || !grad_w || !grad_b)))
         return MSSVT_ERR_INVALID;
     const EmbedRows E = {rows, win, masked, xyz, centre, pos_w, pos_b, num_rows, c0, C};
     const int grid = persistent_grid((long long)num_rows * (cs / 4), 256, 8, 1);
@@ -507,6 +548,28 @@ int mssvt_layernorm_bwd(int num_rows, int C, const float *x, const float *gamma,
     const int grid = persistent_grid((long long)num_rows * (C / 4), 256, 8, 1);
     if (C == 64) k_layernorm_bwd<16><<<grid, 256, 0, s>>>(num_rows, x, gamma, eps, grad_y, grad_x, grad_gamma, grad_beta);
     else k_layernorm_bwd<32><<<grid, 256, 0, s>>>(num_rows, x, gamma, eps, grad_y, grad_x, grad_gamma, grad_beta);
+    ++g_launches;
+    return check_launch();
+}
+
+int mssvt_segment_max_fwd(int num_windows, int C, const int *key_off, const float *rows, float *out, int *arg,
+                          void *stream) {
+    if (num_windows < 0 || C <= 0 || (C & 3)) return MSSVT_ERR_INVALID;
+    if (num_windows == 0) return MSSVT_OK;
+    if (!key_off || !rows || !out || !arg) return MSSVT_ERR_INVALID;
+    k_segment_max_fwd<<<div_up((long long)num_windows * (C / 4), 256), 256, 0, (cudaStream_t)stream>>>(
+        num_windows, C / 4, key_off, (const float4 *)rows, (float4 *)out, (int4 *)arg);
+    ++g_launches;
+    return check_launch();
+}
+
+int mssvt_segment_max_bwd(int num_rows, int C, const int *k_win, const int *arg, const float *grad_out,
+                          float *grad_rows, void *stream) {
+    if (num_rows < 0 || C <= 0 || (C & 3)) return MSSVT_ERR_INVALID;
+    if (num_rows == 0) return MSSVT_OK;
+    if (!k_win || !arg || !grad_out || !grad_rows) return MSSVT_ERR_INVALID;
+    k_segment_max_bwd<<<div_up((long long)num_rows * (C / 4), 256), 256, 0, (cudaStream_t)stream>>>(
+        num_rows, C / 4, k_win, (const int4 *)arg, (const float4 *)grad_out, (float4 *)grad_rows);
     ++g_launches;
     return check_launch();
 }

@@ -220,21 +220,31 @@ k_linear_wgrad(int R, const float *__restrict__ dY, int ldy, const float *__rest
     if (tid < N) part_b[(size_t)blockIdx.x * N + tid] = bsum;
 }
 
-// sums of the per-CTA partial results in a fixed order
+// sums of the per-CTA partial results in a fixed order: 32 outputs x 8 slices of the partial list per CTA (a slice
+// adds its partials in order, the 8 slice sums are added in order)
 __global__ void __launch_bounds__(256)
 k_linear_wgrad_reduce(int ctas, int nk, int n, const float *__restrict__ part_w, const float *__restrict__ part_b,
                       float *__restrict__ gw, float *__restrict__ gb) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ float s_part[8][32];
+    const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + lane;
+    const int per = (ctas + 7) / 8, c0 = slice * per, c1 = min(ctas, c0 + per);
+    float s = 0.f;
     if (i < nk) {
-        float s = 0.f;
-#pragma unroll 8
-        for (int c = 0; c < ctas; ++c) s += __ldg(part_w + (size_t)c * nk + i);   // (fixed order: deterministic)
-        gw[i] = s;
-    } else if (i < nk + n && gb) {
-        float s = 0.f;
-#pragma unroll 8
-        for (int c = 0; c < ctas; ++c) s += __ldg(part_b + (size_t)c * n + (i - nk));
-        gb[i - nk] = s;
+#pragma unroll 4
+        for (int c = c0; c < c1; ++c) s += __ldg(part_w + (size_t)c * nk + i);
+    } else if (i < nk + n) {
+#pragma unroll 4
+        for (int c = c0; c < c1; ++c) s += __ldg(part_b + (size_t)c * n + (i - nk));
+    }
+    s_part[slice][lane] = s;
+    __syncthreads();
+    if (slice == 0 && i < nk + n) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += s_part[k][lane];
+        if (i < nk) gw[i] = t;
+        else if (gb) gb[i - nk] = t;
     }
 }
 
@@ -258,7 +268,7 @@ static int linear_wgrad(int R, const float *gy, int ldgy, const float *x, int ld
         k_linear_wgrad<K, N, SPLIT><<<ctas, WG_THREADS, 0, s>>>(R, gy, ldgy, x, ldx, part_w, part_b);
         ++g_launches;
     }
-    k_linear_wgrad_reduce<<<div_up(N * K + N, 256), 256, 0, s>>>(ctas, N * K, N, part_w, part_b, gw, gb);
+    k_linear_wgrad_reduce<<<div_up(N * K + N, 32), 256, 0, s>>>(ctas, N * K, N, part_w, part_b, gw, gb);
     ++g_launches;
     return check_launch();
 }

@@ -24,7 +24,8 @@ from torch import nn
 from . import mssvt_ops
 from ._lib import AttnShape, FfnShape, call, ptr, stream, host_floats
 from .mssvt_utils import MixedScaleAttention, SparseTensor, sample_counts
-from .train_ops import WindowLists, embed_rows, interp_merge, layer_norm_rows, linear_rows, ragged_window_attention
+from .train_ops import (WindowLists, embed_rows, interp_merge, layer_norm_rows, linear_rows, ragged_window_attention,
+                        segment_max)
 
 # Training path: "ragged" = compact window lists + the kernels of csrc/train.cu (default); "padded" = torch autograd over the
 # reference's padded (W, nk, C) tensors (kept as the cross-check of the ragged path and for attention dropout > 0)
@@ -51,6 +52,15 @@ def _warn_ffma(module, what, ok):
                       "fp32 FFMA kernel for it (about 5x slower)" % (what, key[0], module.precision), RuntimeWarning,
                       stacklevel=3)
     return ok
+
+
+def _conv1x1_rows(conv, x, relu=False):
+    """a Conv1d(k = 1) layer of pos_proj applied to compact rows (R, C_in) through the row-linear kernels"""
+    from .train_ops import LinearRows
+    if conv.in_channels in (32, 64, 128) and conv.out_channels in (32, 64, 128) and x.shape[0] > 0:
+        return LinearRows.apply(x, conv.weight[:, :, 0], conv.bias, relu)
+    y = torch.nn.functional.linear(x, conv.weight[:, :, 0], conv.bias)
+    return torch.relu(y) if relu else y
 
 
 class DropPath(nn.Module):
@@ -795,20 +805,29 @@ class MixedScaleSparseTransformerCompressBlock(MixedScaleSparseTransformerBlock)
         key_off[1:] = torch.cumsum(nrep, 0)
         lists = WindowLists(torch.arange(cap + 1, device=dev), torch.arange(W, device=dev), key_off, k_win,
                             torch.where(has_pad, n1 - cnt, torch.zeros_like(cnt)))
-        has_pad = has_pad[:W]
         xn = layer_norm_rows(self.norm1, x)
-        idx = torch.where(rows < 0, torch.full_like(rows, N), rows)                    # pad key -> the appended zero row
-        k_x = torch.cat((xn, xn.new_zeros(1, C)), 0).index_select(0, idx)              # (#keys, C)
-        centre = self._window_centres(sp_tensor, win_list).squeeze(-1)                 # (cap, 3)
-        with torch.no_grad():
-            xyz = sp_tensor.world_coords()
-            ctr = centre[k_win]
-            pos = torch.cat((torch.cat((xyz, xyz.new_zeros(1, 3)), 0)[idx] - ctr, ctr), 1)   # Q6: padded slots sit at 0 - centre
-        # Q6: the max-pooled query sees the zero padding of the slots
-        q_init = torch.where(has_pad[:, None], xn.new_zeros(1, 1), xn.new_full((1, 1), float("-inf"))).expand(W, C).contiguous()
-        q_fea = q_init.scatter_reduce(0, k_win[:, None].expand(-1, C), k_x, "amax", include_self=True)
+        centre = self._window_centres(sp_tensor, win_list).squeeze(-1).contiguous()    # (cap, 3)
+        xyz = sp_tensor.world_coords()
+        if C == 64 and len(self.pos_proj) == 4 and self.pos_proj[0].out_channels == 64:
+            # row gather (the pad key: a zero row) and the first embedding layer (Q6: padded slots sit at 0 - centre)
+            # forward / backward in mssvt_embed_rows_fwd / _bwd, the second layer in mssvt_linear_rows_*
+            k_x, h1 = embed_rows(xn, self.pos_proj[0].weight[:, :, 0], self.pos_proj[0].bias, xyz, centre,
+                                 [(rows, k_win, None, 0, C, "x"), (rows, k_win, None, 0, C, "pos")])
+        else:
+            k_x = h1 = None
+        if k_x is None:
+            idx = torch.where(rows < 0, torch.full_like(rows, N), rows)                # pad key -> the appended zero row
+            k_x = torch.cat((xn, xn.new_zeros(1, C)), 0).index_select(0, idx)          # (#keys, C)
+            with torch.no_grad():
+                ctr = centre[k_win]
+                pos = torch.cat((torch.cat((xyz, xyz.new_zeros(1, 3)), 0)[idx] - ctr, ctr), 1)
+            k_pos = self._pos_embed_rows(pos)
+        else:
+            k_pos = _conv1x1_rows(self.pos_proj[2], h1, relu=True)
+        # Q6: the max-pooled query sees the zero padding of the slots (the pad row is one of the window's rows)
+        q_fea = segment_max(k_x, lists, W)
         q = linear_rows(a.to_qs[0], q_fea)
-        kv = linear_rows(a.to_kvs[0], k_x + self._pos_embed_rows(pos))
+        kv = linear_rows(a.to_kvs[0], k_x + k_pos)
         attn = a.proj_drop(linear_rows(a.projs[0], ragged_window_attention(q, kv, lists, a.num_heads[0], a.scale)))   # (W, C)
         vs = sp_tensor.voxel_size
         sp_tensor.features = self._ffn_autograd(attn)

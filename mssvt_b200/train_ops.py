@@ -102,9 +102,10 @@ interp_merge = InterpMerge.apply
 
 
 class EmbedRows(Function):
-    """Row sets of one block through mssvt_embed_rows_fwd / _bwd: for every set (rows, win, masked, c0, c1) the
-    tensor xn[rows, c0:c1] + relu(pos_proj([xyz[rows] - centre[win] | centre[win]]))[c0:c1].  One Function for all
-    sets of a block so that the gradient of xn and of pos_proj is accumulated in one buffer each."""
+    """Row sets of one block through mssvt_embed_rows_fwd / _bwd: for every set (rows, win, masked, c0, c1[, part]) the
+    tensor xn[rows, c0:c1] + relu(pos_proj([xyz[rows] - centre[win] | centre[win]]))[c0:c1]; part = "x": the gathered
+    rows alone, "pos": the embedding alone.  One Function for all sets of a block so that the gradient of xn and of
+    pos_proj is accumulated in one buffer each."""
 
     @staticmethod
     @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
@@ -112,14 +113,18 @@ class EmbedRows(Function):
         xn, pos_w, pos_b = xn.contiguous(), pos_w.contiguous(), pos_b.contiguous()
         xyz, centre = xyz.float().contiguous(), centre.float().contiguous()
         C, outs, packed = xn.shape[1], [], []
-        for rows, win, masked, c0, c1 in sets:
+        for t in sets:
+            rows, win, masked, c0, c1 = t[:5]
+            part = t[5] if len(t) > 5 else "both"
             rows, win = rows.to(torch.int32).contiguous(), win.to(torch.int32).contiguous()
             masked = None if masked is None else masked.to(torch.uint8).contiguous()
             out = torch.empty((rows.shape[0], c1 - c0), dtype=torch.float32, device=xn.device)
-            call("mssvt_embed_rows_fwd", rows.shape[0], c0, c1 - c0, C, ptr(rows), ptr(win), ptr(masked), ptr(xn), ptr(xyz),
-                 ptr(centre), ptr(pos_w), ptr(pos_b), ptr(out), stream())
+            use_x, use_pos = part != "pos", part != "x"
+            call("mssvt_embed_rows_fwd", rows.shape[0], c0, c1 - c0, C, ptr(rows), ptr(win), ptr(masked),
+                 ptr(xn) if use_x else None, ptr(xyz), ptr(centre), ptr(pos_w) if use_pos else None, ptr(pos_b), ptr(out),
+                 stream())
             outs.append(out)
-            packed.append((rows, win, masked, c0, c1))
+            packed.append((rows, win, masked, c0, c1, use_x, use_pos))
         ctx.save_for_backward(pos_w, pos_b, xyz, centre)
         ctx.sets, ctx.xn_shape = packed, xn.shape
         return tuple(outs)
@@ -130,17 +135,47 @@ class EmbedRows(Function):
         pos_w, pos_b, xyz, centre = ctx.saved_tensors
         g_xn = torch.zeros(ctx.xn_shape, dtype=torch.float32, device=pos_w.device)
         g_w, g_b = torch.zeros_like(pos_w), torch.zeros_like(pos_b)
-        for (rows, win, masked, c0, c1), g in zip(ctx.sets, grads):
+        for (rows, win, masked, c0, c1, use_x, use_pos), g in zip(ctx.sets, grads):
             if g is None:
                 continue
             g = g.float().contiguous()
             call("mssvt_embed_rows_bwd", rows.shape[0], c0, c1 - c0, ctx.xn_shape[1], ptr(rows), ptr(win), ptr(masked),
-                 ptr(xyz), ptr(centre), ptr(pos_w), ptr(pos_b), ptr(g), ptr(g_xn), ptr(g_w), ptr(g_b), stream())
+                 ptr(xyz), ptr(centre), ptr(pos_w) if use_pos else None, ptr(pos_b), ptr(g), ptr(g_xn) if use_x else None,
+                 ptr(g_w), ptr(g_b), stream())
         return (g_xn, g_w, g_b, None, None) + (None,) * len(ctx.sets)
 
 
 def embed_rows(xn, pos_w, pos_b, xyz, centre, sets):
     return EmbedRows.apply(xn, pos_w, pos_b, xyz, centre, *sets)
+
+
+class SegmentMax(Function):
+    """max over the compact rows of every window (mssvt_segment_max_fwd / _bwd): rows (R, C) -> (num_windows, C)"""
+
+    @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, rows, lists, num_windows):
+        rows = rows.contiguous()
+        C = rows.shape[1]
+        out = torch.empty((num_windows, C), dtype=torch.float32, device=rows.device)
+        arg = torch.empty((num_windows, C), dtype=torch.int32, device=rows.device)
+        call("mssvt_segment_max_fwd", num_windows, C, ptr(lists.key_off), ptr(rows), ptr(out), ptr(arg), stream())
+        ctx.save_for_backward(arg)
+        ctx.lists, ctx.num_rows = lists, rows.shape[0]
+        return out
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, grad_out):
+        (arg,) = ctx.saved_tensors
+        grad_out = grad_out.float().contiguous()
+        g = torch.empty((ctx.num_rows, grad_out.shape[1]), dtype=torch.float32, device=grad_out.device)
+        call("mssvt_segment_max_bwd", ctx.num_rows, grad_out.shape[1], ptr(ctx.lists.k_win), ptr(arg), ptr(grad_out), ptr(g),
+             stream())
+        return g, None, None
+
+
+segment_max = SegmentMax.apply
 
 
 class LayerNormRows(Function):

@@ -17,7 +17,7 @@ from mssvt_b200.config import s0_model_cfg
 from mssvt_b200.mssvt_backbone import MixedScaleSparseTransformer
 from mssvt_b200.synth import S0_GRID, S0_RANGE, S0_VOXEL, synth_frame
 from mssvt_b200.train_ops import (WindowLists, embed_rows, interp_merge, layer_norm_rows, linear_rows,
-                                  ragged_window_attention)
+                                  ragged_window_attention, segment_max)
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-4
@@ -171,26 +171,29 @@ def test_embed_rows_forward_backward_vs_torch():
     centre = torch.randn(W, 3, device="cuda") * 10
     pw, pb = torch.randn(C, 6, device="cuda") * 0.3, torch.randn(C, device="cuda") * 0.3
     sets = []
-    for n_rows, c0, c1, with_mask in ((900, 0, 64, False), (7001, 0, 32, True), (5000, 32, 64, True)):
+    for n_rows, c0, c1, with_mask, part in ((900, 0, 64, False, "both"), (7001, 0, 32, True, "both"), (5000, 32, 64, True, "both"),
+                                            (3001, 0, 64, False, "x"), (3001, 0, 64, False, "pos")):
         rows = rng.integers(0, N, n_rows)
         rows[rng.random(n_rows) < 0.05] = -1
         win = rng.integers(0, W, n_rows)
         masked = torch.from_numpy(rng.random(n_rows) < 0.3).cuda() if with_mask else None
-        sets.append((torch.from_numpy(rows).cuda(), torch.from_numpy(win).cuda(), masked, c0, c1))
+        sets.append((torch.from_numpy(rows).cuda(), torch.from_numpy(win).cuda(), masked, c0, c1, part))
     gos = [torch.randn(t[0].shape[0], t[4] - t[3], device="cuda") for t in sets]
     a1, w1, b1 = xn.clone().requires_grad_(True), pw.clone().requires_grad_(True), pb.clone().requires_grad_(True)
     outs = embed_rows(a1, w1, b1, xyz, centre, sets)
     torch.autograd.backward(outs, gos)
     a2, w2, b2 = xn.double().requires_grad_(True), pw.double().requires_grad_(True), pb.double().requires_grad_(True)
     refs = []
-    for rows, win, masked, c0, c1 in sets:
+    for rows, win, masked, c0, c1, part in sets:
         idx = torch.where(rows < 0, torch.full_like(rows, N), rows)
         ctr = centre.double()[win]
         rel = torch.cat((xyz.double(), xyz.new_zeros(1, 3).double()))[idx] - ctr
         if masked is not None:
             rel = rel * (~masked).unsqueeze(1)
         pos = torch.cat((rel, ctr), 1)
-        refs.append(torch.cat((a2, a2.new_zeros(1, C)))[idx][:, c0:c1] + torch.relu(torch.nn.functional.linear(pos, w2[c0:c1], b2[c0:c1])))
+        ref_x = torch.cat((a2, a2.new_zeros(1, C)))[idx][:, c0:c1]
+        ref_p = torch.relu(torch.nn.functional.linear(pos, w2[c0:c1], b2[c0:c1]))
+        refs.append(ref_x if part == "x" else ref_p if part == "pos" else ref_x + ref_p)
     torch.autograd.backward(refs, [g.double() for g in gos])
     for o, r in zip(outs, refs):
         assert (o.double() - r).abs().max().item() <= TOL * r.abs().max().item()
@@ -232,6 +235,24 @@ def test_linear_rows_forward_backward_vs_torch_float64(K, N):
     layer.zero_grad()
     linear_rows(layer, wide[:, 32:], relu=True).backward(go)
     assert torch.equal(g1, layer.weight.grad)
+
+
+def test_segment_max_forward_backward_vs_torch():
+    rng = np.random.default_rng(4)
+    lists, nq, nk, mult = random_lists(rng, 500, 1, 20)
+    W, C = 500, 64
+    torch.manual_seed(8)
+    rows = torch.randn(lists.num_keys, C, device="cuda")
+    go = torch.randn(W, C, device="cuda")
+    r1 = rows.clone().requires_grad_(True)
+    out = segment_max(r1, lists, W)
+    out.backward(go)
+    r2 = rows.clone().requires_grad_(True)
+    ko = lists.key_off.cpu().tolist()
+    ref = torch.stack([r2[ko[w]:ko[w + 1]].max(0)[0] if ko[w + 1] > ko[w] else r2.new_zeros(C) for w in range(W)])
+    ref.backward(go)
+    assert torch.equal(out, ref.detach())
+    assert torch.equal(r1.grad, r2.grad)
 
 
 def _train_run(cfg, state, grid, pc_range, feats, coords, batch, path, monkeypatch, train=True):
