@@ -303,3 +303,22 @@ def test_ragged_training_path_vs_padded_autograd_20k_frame(monkeypatch):
     state = {k: v.clone() for k, v in ref_model.state_dict().items()}
     args = (s0_model_cfg(cbs_patterns=(1, 0, 2)), state, S0_GRID, S0_RANGE, feats, coords, 1)
     _compare_runs(_train_run(*args, "ragged", monkeypatch), _train_run(*args, "padded", monkeypatch))
+
+
+def test_ragged_training_path_batch_with_empty_sample_and_overflow(monkeypatch):
+    """three samples, the middle one empty: ragged == padded; max_num_wins below the window count raises in training too"""
+    feats, coords = synth_frame(5, 3000, batch_size=3, crop=0.3)
+    keep = coords[:, 0] != 1
+    feats, coords = torch.from_numpy(feats[keep]), torch.from_numpy(coords[keep])
+    torch.manual_seed(5)
+    cfg = s0_model_cfg(cbs_patterns=(2, 1, 0))
+    ref_model = MixedScaleSparseTransformer(cfg, 64, list(S0_GRID), list(S0_VOXEL), list(S0_RANGE))
+    state = {k: v.clone() for k, v in ref_model.state_dict().items()}
+    args = (cfg, state, S0_GRID, S0_RANGE, feats, coords, 3)
+    _compare_runs(_train_run(*args, "ragged", monkeypatch), _train_run(*args, "padded", monkeypatch))
+    monkeypatch.setattr(mssvt_backbone, "TRAIN_PATH", "ragged")
+    model = MixedScaleSparseTransformer(cfg, 64, list(S0_GRID), list(S0_VOXEL), list(S0_RANGE)).cuda().train()
+    for b in model.backbone:
+        b.max_num_wins = 50
+    with pytest.raises(RuntimeError, match="max_num_wins"):
+        model({"voxel_features": feats.cuda().requires_grad_(True), "voxel_coords": coords.cuda().float(), "batch_size": 3})
