@@ -459,6 +459,32 @@ int mssvt_segment_max_fwd(int num_windows, int C, const int *key_off, const floa
 int mssvt_segment_max_bwd(int num_rows, int C, const int *k_win, const int *arg, const float *grad_out,
                           float *grad_rows, void *stream);
 
+/* ---- compact window lists of the training path, built on the device (mssvt_b200/csrc/train_lists.cu) from the maps of
+ * mssvt_block_geometry.  counts (cap, 4) = {#real queries, #distinct keys of head group 0, of group 1, 0} per window (key
+ * counts zeroed for windows without a query); mult (2, cap) = multiplicity of each group's masked key.  The offsets are
+ * mssvt_exclusive_scan over the columns of counts; the caller reads the three totals once, allocates the lists and calls
+ * mssvt_ragged_lists_fill: q_rows / q_win (#queries), per group k_rows / k_win / k_masked (#keys). */
+int mssvt_ragged_lists_count(int win_capacity, const int *win_count_total, const int *meta, int *counts, int *mult,
+                             void *stream);
+int mssvt_ragged_lists_fill(int win_capacity, const int *win_count_total, int nq, int K, const int *counts,
+                            const int *mult, const int *q_off, const int *key_off0, const int *key_off1,
+                            const int *q_row, const int *rep_row, int *q_rows, int *q_win, int *k_rows0, int *k_win0,
+                            unsigned char *k_masked0, int *k_rows1, int *k_win1, unsigned char *k_masked1,
+                            void *stream);
+
+/* src (num_voxels, 3) / weights (num_voxels, 3) of mssvt_interp_merge_fwd from vox_slot / nn_idx / nn_w of the geometry:
+ * compact query ids (q_off[window] + slot), -1 for a padded query slot, -2 for a voxel outside every window. */
+int mssvt_ragged_merge_map(int num_voxels, int max_win1, const int *vox_slot, const int *meta, const int *q_off,
+                           const unsigned char *nn_idx, const float *nn_w, int *src, float *weights, void *stream);
+
+/* The same for the compress block (keys of a window = the voxels of k_row (cap, max_win1) + one pad key when slots are left,
+ * quirk Q6): counts (cap), mult (cap) = number of padded slots; rows (#keys) = voxel row or -1 for the pad key, k_win. */
+int mssvt_compress_lists_count(int win_capacity, const int *win_count_total, int max_win1, const int *k_row,
+                               int *counts, int *mult, void *stream);
+int mssvt_compress_lists_fill(int win_capacity, const int *win_count_total, int max_win1, const int *counts,
+                              const int *mult, const int *key_off, const int *k_row, int *rows, int *k_win,
+                              void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -71,6 +71,11 @@ _SIGNATURES = {
     "mssvt_linear_rows_fwd": [I, I, I, I, P, I, P, P, I, P, I, P],
     "mssvt_linear_rows_wgrad_workspace_floats": [I, I],
     "mssvt_linear_rows_wgrad": [I, I, I, I, P, I, P, I, P, P, P, P],
+    "mssvt_ragged_lists_count": [I, P, P, P, P, P],
+    "mssvt_ragged_lists_fill": [I, P, I, I] + [P] * 15 + [P],
+    "mssvt_ragged_merge_map": [I, I] + [P] * 7 + [P],
+    "mssvt_compress_lists_count": [I, P, I, P, P, P, P],
+    "mssvt_compress_lists_fill": [I, P, I] + [P] * 6 + [P],
     "mssvt_segment_max_fwd": [I, I, P, P, P, P, P],
     "mssvt_segment_max_bwd": [I, I, P, P, P, P, P],
     "mssvt_interp_merge_fwd": [I, I, P, P, P, P, P, P],

@@ -30,6 +30,9 @@ from .train_ops import (WindowLists, embed_rows, interp_merge, layer_norm_rows, 
 # Training path: "ragged" = compact window lists + the kernels of csrc/train.cu (default); "padded" = torch autograd over the
 # reference's padded (W, nk, C) tensors (kept as the cross-check of the ragged path and for attention dropout > 0)
 TRAIN_PATH = os.environ.get("MSSVT_B200_TRAIN_PATH", "ragged")
+# The compact window lists of the ragged path: "cuda" = built by the kernels of csrc/train_lists.cu (default), "torch" = the same
+# lists from torch index operations (the cross-check of those kernels; also what the CPU test of the host logic runs)
+TRAIN_LISTS = os.environ.get("MSSVT_B200_TRAIN_LISTS", "cuda")
 
 
 TC_MODES = ("tf32", "tf32x3", "bf16", "bf16x3")     # precision modes that run on the tcgen05 kernels
@@ -276,13 +279,56 @@ class MixedScaleSparseTransformerBlock(nn.Module):
                 y = torch.nn.functional.linear(y, w, b)
         return y if one or c1 is None else y[:, c0:c1]
 
-    def _ragged_supported(self):
+    def _ragged_supported(self, groups=2):
+        """shape family of the training kernels (csrc/train.cu); everything else trains on the padded autograd path"""
         a = self.ms_attn
         return (TRAIN_PATH != "padded" and a.per_head_dim in (8, 16, 32) and self.in_channels % 4 == 0
+                and a.num_head_groups == groups
                 and not (self.training and a.dropout > 0))      # (dropout on the attention matrix: padded path)
 
     def _window_lists(self, sp_tensor, g):
-        """Compact (CSR) form of the block's windows for the training kernels, made once per geometry: real queries
+        """Compact (CSR) form of the block's windows for the training kernels, made once per geometry, on the device:
+        mssvt_ragged_lists_count -> two exclusive scans (the query offsets are the geometry's q_base) -> ONE host copy of the
+        window count and the three list lengths -> mssvt_ragged_lists_fill, mssvt_ragged_merge_map."""
+        if ("ragged",) in g:
+            return g[("ragged",)]
+        if TRAIN_LISTS == "torch" or not g["q_row"].is_cuda:
+            return self._window_lists_torch(sp_tensor, g)
+        dev, K, N, B = g["q_row"].device, self.key_num_sample, sp_tensor.indices.shape[0], sp_tensor.batch_size
+        cap, nq = g["cap"], g["q_row"].shape[1]
+        i32 = dict(dtype=torch.int32, device=dev)
+        cnt, mult = torch.empty((cap, 4), **i32), torch.empty((2, cap), **i32)
+        call("mssvt_ragged_lists_count", cap, ptr(g["total"]), ptr(g["meta"]), ptr(cnt), ptr(mult), stream())
+        q_off, key_off = g["q_base"], [torch.empty(cap + 1, **i32) for _ in range(2)]
+        ws = torch.empty((cap + 1 + 1023) // 1024 + 1, **i32)
+        for s in range(2):
+            call("mssvt_exclusive_scan", cap, ptr(g["total"]), ptr(cnt.view(-1)[1 + s:]), 4, ptr(key_off[s]), ptr(ws), stream())
+        at = g["total"].clamp(max=cap).long()
+        W, dropped, n_q, n_k0, n_k1 = torch.cat(
+            [g["win_count"][B:B + 2], q_off[at], key_off[0][at], key_off[1][at]]).tolist()      # the one synchronisation
+        if dropped:
+            raise RuntimeError("window partition: %d windows exceed max_num_wins" % dropped)
+        q_rows, q_win = torch.empty(n_q, **i32), torch.empty(n_q, **i32)
+        k_rows = [torch.empty(n, **i32) for n in (n_k0, n_k1)]
+        k_win = [torch.empty(n, **i32) for n in (n_k0, n_k1)]
+        k_masked = [torch.empty(n, dtype=torch.uint8, device=dev) for n in (n_k0, n_k1)]
+        call("mssvt_ragged_lists_fill", cap, ptr(g["total"]), nq, K, ptr(cnt), ptr(mult), ptr(q_off), ptr(key_off[0]),
+             ptr(key_off[1]), ptr(g["q_row"]), ptr(g["rep_row"]), ptr(q_rows), ptr(q_win), ptr(k_rows[0]), ptr(k_win[0]),
+             ptr(k_masked[0]), ptr(k_rows[1]), ptr(k_win[1]), ptr(k_masked[1]), stream())
+        L = {"W": min(W, cap), "q_rows": q_rows, "q_win": q_win,
+             "groups": [(k_rows[s], k_win[s], k_masked[s].bool(), WindowLists(q_off, q_win, key_off[s], k_win[s], mult[s]))
+                        for s in range(2)]}
+        if self.use_feature_interpolation:
+            src = torch.empty((N, 3), **i32)
+            wgt = torch.empty((N, 3), dtype=torch.float32, device=dev)
+            call("mssvt_ragged_merge_map", N, self.max_num_win1, ptr(g["vox_slot"]), ptr(g["meta"]), ptr(q_off),
+                 ptr(g["nn_idx"]), ptr(g["nn_w"]), ptr(src), ptr(wgt), stream())
+            L["merge_src"], L["merge_w"] = src, wgt
+        g[("ragged",)] = L
+        return L
+
+    def _window_lists_torch(self, sp_tensor, g):
+        """The same lists from torch index operations (cross-check of the list kernels; runs on CPU tensors too): real queries
         window by window, per head group the distinct keys of every window that has a query (rep_row / meta of
         mssvt_block_geometry: the masked key last, with its multiplicity), and the three-NN map of every voxel in
         compact query ids.  ONE host synchronisation (window count + the three list lengths in one copy); the lists
@@ -781,13 +827,29 @@ class MixedScaleSparseTransformerBlock(nn.Module):
 class MixedScaleSparseTransformerCompressBlock(MixedScaleSparseTransformerBlock):
     """mssvt_backbone.py:349-398: one query per window, output re-indexed to the window grid."""
 
-    def _forward_autograd_compress(self, sp_tensor, x, k_row, grid, win_list, win_table, win_count):
-        """Training path on the compact form (see MixedScaleSparseTransformerBlock._forward_autograd): keys of a window =
-        its voxels + ONE pad key (zero features at position 0, quirk Q6) standing for the n1 - #voxels padded slots."""
-        if not self._ragged_supported():
-            return self._forward_autograd_compress_padded(sp_tensor, x, k_row, grid, win_list, win_table, win_count)
-        B, (N, C), dev = sp_tensor.batch_size, x.shape, x.device
-        n1, a, cap = self.max_num_win1, self.ms_attn, win_list.shape[0]
+    def _compress_lists(self, k_row, win_count, B, cap, n1):
+        """compact key lists of the compress block on the device (mssvt_compress_lists_count -> scan -> one host copy of the
+        window count and the list length -> mssvt_compress_lists_fill): -> (W, rows (-1 = pad key), k_win, WindowLists)"""
+        dev = k_row.device
+        i32 = dict(dtype=torch.int32, device=dev)
+        total = win_count[B:B + 1]
+        cnt, mult, key_off = torch.empty(cap, **i32), torch.empty(cap, **i32), torch.empty(cap + 1, **i32)
+        call("mssvt_compress_lists_count", cap, ptr(total), n1, ptr(k_row), ptr(cnt), ptr(mult), stream())
+        ws = torch.empty((cap + 1 + 1023) // 1024 + 1, **i32)
+        call("mssvt_exclusive_scan", cap, ptr(total), ptr(cnt), 1, ptr(key_off), ptr(ws), stream())
+        W, dropped, n_k = torch.cat([win_count[B:B + 2], key_off[total.clamp(max=cap).long()]]).tolist()
+        if dropped:
+            raise RuntimeError("compress block: %d windows exceed max_num_wins" % dropped)
+        W = min(W, cap)
+        rows, k_win = torch.empty(n_k, **i32), torch.empty(n_k, **i32)
+        call("mssvt_compress_lists_fill", cap, ptr(total), n1, ptr(cnt), ptr(mult), ptr(key_off), ptr(k_row), ptr(rows),
+             ptr(k_win), stream())
+        ar = torch.arange(cap + 1, **i32)
+        return W, rows, k_win, WindowLists(ar, ar[:W], key_off, k_win, mult)
+
+    def _compress_lists_torch(self, k_row, win_count, B, cap, n1):
+        """the same lists from torch index operations (cross-check of the list kernels)"""
+        dev = k_row.device
         valid = torch.arange(cap, device=dev) < win_count[B]                           # rows past the window count: garbage
         cnt = ((k_row >= 0) & valid[:, None]).sum(1)
         has_pad = (cnt < n1) & valid
@@ -805,6 +867,17 @@ class MixedScaleSparseTransformerCompressBlock(MixedScaleSparseTransformerBlock)
         key_off[1:] = torch.cumsum(nrep, 0)
         lists = WindowLists(torch.arange(cap + 1, device=dev), torch.arange(W, device=dev), key_off, k_win,
                             torch.where(has_pad, n1 - cnt, torch.zeros_like(cnt)))
+        return W, rows, k_win, lists
+
+    def _forward_autograd_compress(self, sp_tensor, x, k_row, grid, win_list, win_table, win_count):
+        """Training path on the compact form (see MixedScaleSparseTransformerBlock._forward_autograd): keys of a window =
+        its voxels + ONE pad key (zero features at position 0, quirk Q6) standing for the n1 - #voxels padded slots."""
+        if not self._ragged_supported():
+            return self._forward_autograd_compress_padded(sp_tensor, x, k_row, grid, win_list, win_table, win_count)
+        B, (N, C), dev = sp_tensor.batch_size, x.shape, x.device
+        n1, a, cap = self.max_num_win1, self.ms_attn, win_list.shape[0]
+        W, rows, k_win, lists = (self._compress_lists_torch if TRAIN_LISTS == "torch" else self._compress_lists)(
+            k_row, win_count, B, cap, n1)
         xn = layer_norm_rows(self.norm1, x)
         centre = self._window_centres(sp_tensor, win_list).squeeze(-1).contiguous()    # (cap, 3)
         xyz = sp_tensor.world_coords()
@@ -869,7 +942,7 @@ class MixedScaleSparseTransformerCompressBlock(MixedScaleSparseTransformerBlock)
 
     def _ragged_supported(self):
         # (with several head groups the reference splits the SLOTS of a window between the groups: padded path)
-        return super()._ragged_supported() and self.ms_attn.num_head_groups == 1
+        return super()._ragged_supported(groups=1)
 
     def _attn_terms(self):
         """the compress attention kernels have no plain bf16 form: in bf16 mode they run with TF32 operands (the

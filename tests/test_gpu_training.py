@@ -322,3 +322,35 @@ def test_ragged_training_path_batch_with_empty_sample_and_overflow(monkeypatch):
         b.max_num_wins = 50
     with pytest.raises(RuntimeError, match="max_num_wins"):
         model({"voxel_features": feats.cuda().requires_grad_(True), "voxel_coords": coords.cuda().float(), "batch_size": 3})
+
+
+def test_device_window_lists_match_the_torch_lists():
+    """csrc/train_lists.cu (mssvt_ragged_lists_*, mssvt_ragged_merge_map, mssvt_compress_lists_*) against the same lists
+    from torch index operations, which tests/test_training_host.py checks against brute force on the CPU"""
+    feats, coords = synth_frame(3, 6000, batch_size=2, crop=0.25)
+    model = MixedScaleSparseTransformer(s0_model_cfg(cbs_patterns=(1, 0, 2)), 64, list(S0_GRID), list(S0_VOXEL),
+                                        list(S0_RANGE)).cuda()
+    sp = model._sparse_tensor(torch.from_numpy(feats).cuda(), torch.from_numpy(coords).cuda(), 2)
+    for blk in model.backbone[:3]:
+        g = blk.geometry(sp)
+        L1 = blk._window_lists(sp, g)
+        del g[("ragged",)]
+        L2 = blk._window_lists_torch(sp, g)
+        del g[("ragged",)]
+        W = L1["W"]
+        assert W == L2["W"] and W > 100
+        assert torch.equal(L1["q_rows"].long(), L2["q_rows"]) and torch.equal(L1["q_win"].long(), L2["q_win"])
+        assert torch.equal(L1["merge_src"], L2["merge_src"])
+        cov = L1["merge_src"][:, 0] != -2
+        assert torch.equal(L1["merge_w"][cov], L2["merge_w"][cov])
+        for (r1, w1, m1, l1), (r2, w2, m2, l2) in zip(L1["groups"], L2["groups"]):
+            assert r1.numel() > 0 and torch.equal(r1.long(), r2) and torch.equal(w1.long(), w2) and torch.equal(m1, m2)
+            assert torch.equal(l1.key_off[:W + 1], l2.key_off[:W + 1]) and torch.equal(l1.q_off[:W + 1], l2.q_off[:W + 1])
+            assert torch.equal(l1.key_mult[:W], l2.key_mult[:W])
+    cb = model.backbone[3]
+    grid, win_list, win_table, win_count, k_row, plan = cb.prepare(sp)
+    a = cb._compress_lists(k_row, win_count, 2, win_list.shape[0], cb.max_num_win1)
+    b = cb._compress_lists_torch(k_row, win_count, 2, win_list.shape[0], cb.max_num_win1)
+    W = a[0]
+    assert W == b[0] and torch.equal(a[1].long(), b[1]) and torch.equal(a[2].long(), b[2])
+    assert torch.equal(a[3].key_off[:W + 1], b[3].key_off[:W + 1]) and torch.equal(a[3].key_mult[:W], b[3].key_mult[:W])
