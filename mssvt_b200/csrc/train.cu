@@ -231,32 +231,49 @@ __device__ __forceinline__ void embed_pos(const EmbedRows &E, int r, int row, fl
     pos[3] = cx; pos[4] = cy; pos[5] = cz;
 }
 
-__device__ __forceinline__ float embed_pre(const EmbedRows &E, int c, const float pos[6]) {
-    float a = __ldg(E.b + c);
+// weights of a lane's four channels: [k][0..5] = W[c + k][:], [k][6] = b[c + k] (28 registers, loaded once per thread)
+struct EmbedW {
+    float w[4][7];
+    __device__ __forceinline__ void load(const EmbedRows &E, int c) {
 #pragma unroll
-    for (int j = 0; j < 6; ++j) a = fmaf(__ldg(E.w + 6 * c + j), pos[j], a);
-    return a;
-}
+        for (int k = 0; k < 4; ++k) {
+#pragma unroll
+            for (int j = 0; j < 6; ++j) w[k][j] = __ldg(E.w + 6 * (c + k) + j);
+            w[k][6] = __ldg(E.b + c + k);
+        }
+    }
+    __device__ __forceinline__ float pre(int k, const float pos[6]) const {
+        float a = w[k][6];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) a = fmaf(w[k][j], pos[j], a);
+        return a;
+    }
+};
 
+// grid-stride over rows with a FIXED channel group per thread (blockDim.x % LPR == 0), so that the group's weights stay in
+// registers
 template <int LPR>
 __global__ void __launch_bounds__(256)
 k_embed_rows_fwd(EmbedRows E, const float *__restrict__ xn, float *__restrict__ out) {
-    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= (long long)E.n_rows * LPR) return;
-    const int r = (int)(e / LPR), l = (int)(e % LPR), c = E.c0 + 4 * l;
-    const int row = __ldg(E.rows + r);
-    float pos[6];
-    if (E.w) embed_pos(E, r, row, pos);
-    float4 v = (xn && row >= 0) ? __ldg((const float4 *)(xn + (size_t)row * E.ldx + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    if (E.w) {   // (without weights: the gather alone)
-        v.x += fmaxf(embed_pre(E, c, pos), 0.f); v.y += fmaxf(embed_pre(E, c + 1, pos), 0.f);
-        v.z += fmaxf(embed_pre(E, c + 2, pos), 0.f); v.w += fmaxf(embed_pre(E, c + 3, pos), 0.f);
+    const int l = threadIdx.x % LPR, c = E.c0 + 4 * l;
+    const int rows_per_pass = gridDim.x * (blockDim.x / LPR);
+    EmbedW W;
+    if (E.w) W.load(E, c);
+    for (int r = blockIdx.x * (blockDim.x / LPR) + threadIdx.x / LPR; r < E.n_rows; r += rows_per_pass) {
+        const int row = __ldg(E.rows + r);
+        float4 v = (xn && row >= 0) ? __ldg((const float4 *)(xn + (size_t)row * E.ldx + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (E.w) {   // (without weights: the gather alone)
+            float pos[6];
+            embed_pos(E, r, row, pos);
+            v.x += fmaxf(W.pre(0, pos), 0.f); v.y += fmaxf(W.pre(1, pos), 0.f);
+            v.z += fmaxf(W.pre(2, pos), 0.f); v.w += fmaxf(W.pre(3, pos), 0.f);
+        }
+        ((float4 *)out)[(size_t)r * LPR + l] = v;
     }
-    ((float4 *)out)[e] = v;
 }
 
-// backward: grad_xn rows by vector atomics (a voxel is a key of up to 125 windows), grad_w / grad_b per thread over a
-// grid-stride loop with a FIXED channel group, then one shared-memory and one global reduction per CTA
+// backward: grad_xn rows by vector atomics (a voxel is a key of up to 125 windows), grad_w / grad_b per thread over the
+// grid-stride loop, then one shared-memory and one global reduction per CTA
 template <int LPR>
 __global__ void __launch_bounds__(256)
 k_embed_rows_bwd(EmbedRows E, const float *__restrict__ gout, float *__restrict__ gxn, float *__restrict__ gw,
@@ -266,6 +283,8 @@ k_embed_rows_bwd(EmbedRows E, const float *__restrict__ gout, float *__restrict_
     __syncthreads();
     const int l = threadIdx.x % LPR, c = E.c0 + 4 * l;       // (blockDim.x % LPR == 0)
     const int rows_per_pass = gridDim.x * (blockDim.x / LPR);
+    EmbedW W;
+    if (E.w) W.load(E, c);
     float aw[4][6], ab[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -275,15 +294,15 @@ k_embed_rows_bwd(EmbedRows E, const float *__restrict__ gout, float *__restrict_
     }
     for (int r = blockIdx.x * (blockDim.x / LPR) + threadIdx.x / LPR; r < E.n_rows; r += rows_per_pass) {
         const int row = __ldg(E.rows + r);
-        float pos[6];
-        if (E.w) embed_pos(E, r, row, pos);
         const float4 g = __ldg((const float4 *)gout + (size_t)r * LPR + l);
         if (gxn && row >= 0) atomicAdd((float4 *)(gxn + (size_t)row * E.ldx + c), g);
         if (!E.w) continue;
+        float pos[6];
+        embed_pos(E, r, row, pos);
         const float gk[4] = {g.x, g.y, g.z, g.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            if (embed_pre(E, c + k, pos) > 0.f) {
+            if (W.pre(k, pos) > 0.f) {
                 ab[k] += gk[k];
 #pragma unroll
                 for (int j = 0; j < 6; ++j) aw[k][j] = fmaf(gk[k], pos[j], aw[k][j]);
@@ -304,7 +323,6 @@ k_embed_rows_bwd(EmbedRows E, const float *__restrict__ gout, float *__restrict_
         else atomicAdd(gw + 6 * ch + j, s_acc[i]);
     }
 }
-
 
 // ---- max over the rows of a window (the max-pooled query of the compress block, mssvt_backbone.py:373: the compact key
 //      rows of a window are contiguous and include its zero pad row when the window has padded slots, quirk Q6).
@@ -512,9 +530,9 @@ int mssvt_embed_rows_fwd(int num_rows, int c0, int cs, int C, const int *rows, c
     if (num_rows == 0) return MSSVT_OK;
     if (!rows || !win || !out || (!xn && !pos_w) || (pos_w && (!xyz || !centre || !pos_b))) return MSSVT_ERR_INVALID;
     const EmbedRows E = {rows, win, masked, xyz, centre, pos_w, pos_b, num_rows, c0, C};
-    const long long items = (long long)num_rows * (cs / 4);
-    if (cs == 32) k_embed_rows_fwd<8><<<div_up(items, 256), 256, 0, (cudaStream_t)stream>>>(E, xn, out);
-    else k_embed_rows_fwd<16><<<div_up(items, 256), 256, 0, (cudaStream_t)stream>>>(E, xn, out);
+    const int grid = persistent_grid((long long)num_rows * (cs / 4), 256, 8, 2);
+    if (cs == 32) k_embed_rows_fwd<8><<<grid, 256, 0, (cudaStream_t)stream>>>(E, xn, out);
+    else k_embed_rows_fwd<16><<<grid, 256, 0, (cudaStream_t)stream>>>(E, xn, out);
     ++g_launches;
     return check_launch();
 }

@@ -13,23 +13,24 @@
 //                    the 8 warps of a CTA and kept in registers across the CTA's tiles; per-CTA partial results are
 //                    written out and summed by k_linear_wgrad_reduce in a fixed order (no atomics: deterministic).
 // Arithmetic: warp-level mma.sync m16n8k8 TF32 with fp32 accumulation; SPLIT = every operand as hi + lo TF32 and three
-// MMAs per product (the 3xTF32 scheme of the inference kernels): fp32-grade results (the parity-grade default).
+// MMAs per product (the 3xTF32 scheme of the inference kernels, here with truncated instead of rounded halves): fp32-grade
+// results (the parity-grade default).
 // tcgen05 would not move these kernels: the tensor pipe is idle most of the time either way.
 #include "common.cuh"
 
 namespace mssvt {
 
+// Operand split for the 3xTF32 scheme WITHOUT conversion instructions (cvt.rna.tf32 runs on the quarter-rate conversion
+// pipe and was the bound of the 128-channel kernels): hi = the value truncated to TF32 (one AND), lo = v - hi (exact in
+// fp32; the tensor core ignores the 13 low mantissa bits of an operand, i.e. truncates lo itself).  |v - hi - tf32(lo)| <=
+// 2^-20 |v|: the products hi*hi + lo*hi + hi*lo keep ~20 significant bits.
 __device__ __forceinline__ void tf32_split(float v, uint32_t &hi, uint32_t &lo) {
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(v));
-    const float r = v - __uint_as_float(hi);
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+    hi = __float_as_uint(v) & 0xffffe000u;
+    lo = __float_as_uint(v - __uint_as_float(hi));
 }
 
-__device__ __forceinline__ uint32_t tf32_round(float v) {
-    uint32_t hi;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(v));
-    return hi;
-}
+// plain TF32 operand, rounded to nearest (ties away from zero) with two integer operations
+__device__ __forceinline__ uint32_t tf32_round(float v) { return (__float_as_uint(v) + 0x1000u) & 0xffffe000u; }
 
 // D (16 x 8) += A (16 x 8, row) B (8 x 8, col).  Lane = 4 g + t: a0 (g, t) a1 (g + 8, t) a2 (g, t + 4) a3 (g + 8, t + 4);
 // b0 (k = t, n = g) b1 (k = t + 4, n = g); c0 (g, 2t) c1 (g, 2t + 1) c2 (g + 8, 2t) c3 (g + 8, 2t + 1)

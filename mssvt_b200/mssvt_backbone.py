@@ -432,7 +432,7 @@ class MixedScaleSparseTransformerBlock(nn.Module):
         if self.use_feature_interpolation:
             merged = interp_merge(attn, x, L["merge_src"], L["merge_w"])
         else:
-            merged = x.index_copy(0, L["q_rows"], attn)                                # Q5: all other rows keep x
+            merged = x.index_copy(0, L["q_rows"].long(), attn)                         # Q5: all other rows keep x
         u = self.drop_path(merged) + x
         sp_tensor.features = self._ffn_autograd(u)
         sp_tensor.gather_dict = None

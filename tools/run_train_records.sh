@@ -10,8 +10,8 @@ for b in 1 2 4; do
 done
 timeout 90 python benchmarks/train_step.py --steps 8 --warmup 3 --batch 2 --tf32 > gpurun_out/${tag}_train_ragged_tf32_b2.json 2>/dev/null
 timeout 90 python benchmarks/train_step.py --steps 8 --warmup 3 --batch 2 --amp > gpurun_out/${tag}_train_ragged_amp_b2.json 2>/dev/null
-timeout 90 python benchmarks/train_step.py --steps 4 --warmup 3 --batch 1 --path padded > gpurun_out/${tag}_train_padded_fp32_b1.json 2>/dev/null
-timeout 90 python benchmarks/train_step.py --steps 4 --warmup 3 --batch 1 --profile gpurun_out/${tag}_train_torch_profile.txt > /dev/null 2>&1
+timeout 90 python benchmarks/train_step.py --steps 4 --warmup 3 --passes 1 --batch 1 --path padded > gpurun_out/${tag}_train_padded_fp32_b1.json 2>/dev/null
+timeout 90 python benchmarks/train_step.py --steps 4 --warmup 3 --passes 1 --batch 1 --profile gpurun_out/${tag}_train_torch_profile.txt > /dev/null 2>&1
 timeout 240 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv \
-  --log-file gpurun_out/${tag}_train_launches.csv python benchmarks/train_step.py --steps 1 --warmup 2 > /dev/null 2>&1
+  --log-file gpurun_out/${tag}_train_launches.csv python benchmarks/train_step.py --steps 1 --warmup 2 --passes 1 > /dev/null 2>&1
 cat gpurun_out/${tag}_train_*.json | cut -c1-100
