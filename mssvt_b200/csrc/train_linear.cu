@@ -13,20 +13,26 @@
 //                    the 8 warps of a CTA and kept in registers across the CTA's tiles; per-CTA partial results are
 //                    written out and summed by k_linear_wgrad_reduce in a fixed order (no atomics: deterministic).
 // Arithmetic: warp-level mma.sync m16n8k8 TF32 with fp32 accumulation; SPLIT = every operand as hi + lo TF32 and three
-// MMAs per product (the 3xTF32 scheme of the inference kernels, here with truncated instead of rounded halves): fp32-grade
+// MMAs per product (the 3xTF32 scheme of the inference kernels): fp32-grade
 // results (the parity-grade default).
 // tcgen05 would not move these kernels: the tensor pipe is idle most of the time either way.
 #include "common.cuh"
 
 namespace mssvt {
 
-// Operand split for the 3xTF32 scheme WITHOUT conversion instructions (cvt.rna.tf32 runs on the quarter-rate conversion
-// pipe and was the bound of the 128-channel kernels): hi = the value truncated to TF32 (one AND), lo = v - hi (exact in
-// fp32; the tensor core ignores the 13 low mantissa bits of an operand, i.e. truncates lo itself).  |v - hi - tf32(lo)| <=
-// 2^-20 |v|: the products hi*hi + lo*hi + hi*lo keep ~20 significant bits.
+// Operand split for the 3xTF32 scheme with integer operations instead of conversion instructions (cvt.rna.tf32 runs on the
+// quarter-rate conversion pipe): hi = v rounded to TF32 (ties away from zero: one ADD + one AND on the bits), lo = v - hi
+// (exact in fp32), rounded the same way -- the accuracy of the cvt.rna form: |v - hi - lo| <= 2^-22 |v|.
+// -DMSSVT_TF32_SPLIT_TRUNC: both halves truncated instead (two operations per operand, 2^-20): measured, not used -- logits
+// of keys far from their window (the aliased key of quirk Q1) are sums of large products, where the coarser halves show.
 __device__ __forceinline__ void tf32_split(float v, uint32_t &hi, uint32_t &lo) {
+#ifdef MSSVT_TF32_SPLIT_TRUNC
     hi = __float_as_uint(v) & 0xffffe000u;
     lo = __float_as_uint(v - __uint_as_float(hi));
+#else
+    hi = (__float_as_uint(v) + 0x1000u) & 0xffffe000u;
+    lo = (__float_as_uint(v - __uint_as_float(hi)) + 0x1000u) & 0xffffe000u;
+#endif
 }
 
 // plain TF32 operand, rounded to nearest (ties away from zero) with two integer operations
