@@ -103,7 +103,6 @@ def main():
     # costs after overlap with the backward pass
     ms_nosync = None
     if world > 1:
-        import contextlib
         with net.no_sync():
             for i in range(2):
                 step(i)
