@@ -235,9 +235,10 @@ class MixedScaleSparseTransformerBlock(nn.Module):
 
     # ---- training path / fused inference path -------------------------------------------------
     def _differentiable(self, x):
-        """Training (or any call that needs gradients) takes the autograd path: geometry from the fused
-        kernels, feature gathers through mssvt_group_features / mssvt_group_features_grad, dense math
-        in torch.  Inference takes the fused kernels."""
+        """Training (or any call that needs gradients) takes _forward_autograd: geometry from the fused kernels, then
+        the hand-written forward / backward kernels of csrc/train*.cu on compact window lists (train_ops.py); the
+        padded form (row gathers through mssvt_group_features / _grad, dense math in torch autograd) is kept as the
+        cross-check.  Inference takes the fused kernels."""
         return torch.is_grad_enabled() and (self.training or x.requires_grad)
 
     def _window_centres(self, sp_tensor, win_list):

@@ -276,9 +276,9 @@ class MixedScaleAttention(nn.Module):
         self.dropout = dropout
 
     def forward(self, query, keys, batch_first=False, query_mask=None, key_masks=None):
-        """Differentiable dense form (mssvt_utils.py:88-157), used by the TRAINING path of the blocks;
-        inference runs the same mathematics inside the fused window kernels (mssvt_block_attention[_tc] /
-        mssvt_compress_attention[_tc]) and never comes through here.  query (b, nq, C), keys (b, G * nk, C)
+        """Differentiable dense form (mssvt_utils.py:88-157), used by the PADDED training path of the blocks (the
+        cross-check of the ragged training kernels, train_ops.py); inference runs the same mathematics inside the fused
+        window kernels (mssvt_block_attention[_tc] / mssvt_compress_attention[_tc]) and never comes through here.  query (b, nq, C), keys (b, G * nk, C)
         when batch_first; head group g reads channel slice g of the queries and key chunk g only; key_masks
         (b, G * nk) bool (True = masked, additive -100 like the reference); padded queries give zero rows."""
         if not query.is_cuda:
