@@ -97,3 +97,33 @@ def test_masked_key_multiplicity_identity_outputs_and_gradients():
     assert torch.allclose(out_p, out_c, atol=1e-12)
     for a, b in zip(gp, gc):
         assert torch.allclose(a, b, atol=1e-12)
+
+
+def test_compress_lists_match_brute_force():
+    """keys of a pillar window = its voxels + one pad key (row -1) standing for the padded slots (quirk Q6)"""
+    rng = np.random.default_rng(3)
+    model = MixedScaleSparseTransformer(s0_model_cfg(), 64, list(S0_GRID), list(S0_VOXEL), list(S0_RANGE))
+    blk = model.backbone[3]
+    n1, cap, W, B = blk.max_num_win1, 90, 61, 2
+    k_row = rng.integers(-9, 1000, (cap, n1)).astype(np.int32)            # rows past W: garbage
+    want_rows, want_win, want_off, want_mult = [], [], [0], []
+    for w in range(W):
+        c = int(rng.integers(1, n1 + 1))
+        k_row[w] = -1
+        k_row[w, :c] = rng.integers(0, 1000, c)
+        rows = [int(v) for v in k_row[w, :c]] + ([-1] if c < n1 else [])
+        want_rows += rows
+        want_win += [w] * len(rows)
+        want_off.append(want_off[-1] + len(rows))
+        want_mult.append(n1 - c)
+    win_count = torch.tensor([30, 31, W, 0], dtype=torch.int32)           # per-sample counts, total, dropped
+    got_w, rows, k_win, lists = blk._compress_lists_torch(torch.from_numpy(k_row), win_count, B, cap, n1)
+    assert got_w == W and rows.tolist() == want_rows and k_win.tolist() == want_win
+    assert lists.key_off.tolist()[:W + 1] == want_off and lists.key_mult.tolist()[:W] == want_mult
+    assert lists.q_off.tolist()[:W + 1] == list(range(W + 1)) and lists.q_win.tolist() == list(range(W))
+    win_count[B + 1] = 4
+    try:
+        blk._compress_lists_torch(torch.from_numpy(k_row), win_count, B, cap, n1)
+        assert False, "dropped windows must raise"
+    except RuntimeError as e:
+        assert "max_num_wins" in str(e)
