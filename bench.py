@@ -13,7 +13,9 @@ frames, config 4: sharded by frame, no data-path collective, weak scaling).
   e2e    = the same metric through the module API from pinned HOST buffers: H2D of the step's
            features + coordinates, forward, D2H of the output features + indices, every step;
   roofline      = the dominant kernel of the step against the measured HBM peak;
-  cpu_baseline  = the CPU oracle on the host cores, bounded sample (rank 0, N = 1 only).
+  cpu_baseline  = the CPU oracle on the host cores, bounded sample (rank 0, N = 1 only);
+  train_step    = side measurement after everything else (N = 1 only, never part of `value`): one training step
+                  (forward + backward + AdamW) through the hand-written training kernels.
 """
 import argparse
 import json
@@ -614,10 +616,52 @@ def our_arm(args):
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"], want = cpu_baseline(budget_s=20.0)
             line["parity"] = arm.parity(want, [args.precision] + others)
+        if world == 1 and not args.no_train_probe:
+            try:        # a side measurement: it must not cost the line
+                line["train_step"] = train_step_probe(torch.device("cuda", local))
+            except Exception as e:  # noqa: BLE001
+                line["train_step"] = {"error": repr(e)}
         emit(line)
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
+
+
+def train_step_probe(device, steps=8, warmup=3):
+    """SURVEY 8(f) rank 2 beside the headline: one training step (forward + backward + AdamW) of the same S0 backbone on
+    150 k-voxel frames through the hand-written training kernels (csrc/train*.cu), CUDA-event timed after the headline is
+    measured.  A side measurement; the records are benchmarks/train_step.py's (profiles/r02_train/)."""
+    from mssvt_b200.mssvt_backbone import MixedScaleSparseTransformer
+    torch.manual_seed(0)
+    model = MixedScaleSparseTransformer(s0_model_cfg(), 64, list(S0_GRID), list(S0_VOXEL), list(S0_RANGE)).to(device).train()
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4)
+    frames = []
+    for i in range(2):
+        f, c = synth_frame(100 + i, N_VOXELS)
+        frames.append((torch.from_numpy(f).to(device), torch.from_numpy(c).to(device)))
+
+    def step(i):
+        f, c = frames[i % len(frames)]
+        opt.zero_grad(set_to_none=True)
+        sp = model({"voxel_features": f, "voxel_coords": c, "batch_size": 1})["encoded_spconv_tensor"]
+        loss = (sp.dense() ** 2).mean()
+        loss.backward()
+        opt.step()
+
+    for i in range(warmup):
+        step(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    del model, opt, frames
+    return {"ms_per_step": ms, "voxels_per_s": N_VOXELS / (ms * 1e-3), "steps": steps, "warmup": warmup, "dtype": "tf32x3",
+            "what": "forward + backward + AdamW, one %d-voxel frame per step, hand-written forward / backward kernels on compact "
+                    "window lists (split-TF32 row-linear kernels), loss = mean(dense()^2); not part of `value`" % N_VOXELS}
 
 
 # ----------------------------------------------------------------------------- CPU arm
@@ -747,6 +791,7 @@ def main():
                          "bf16 operands, features within the fp32 bar of 1e-4).  The other tensor-core modes are measured "
                          "too and reported under `modes`")
     ap.add_argument("--no-modes", dest="modes", action="store_false", help="skip the other precision modes")
+    ap.add_argument("--no-train-probe", action="store_true", help="skip the training-step side measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
