@@ -272,8 +272,9 @@ class LinearRows(Function):
 def linear_rows(layer, x, relu=False):
     """nn.Linear module `layer` applied to rows x (optionally followed by ReLU) through the hand-written kernels where
     they cover the shape, torch otherwise"""
-    if (x.dim() == 2 and x.shape[0] > 0 and layer.in_features in (32, 64, 128) and layer.out_features in (32, 64, 128)
-            and x.is_cuda):
+    if not x.is_cuda:
+        raise RuntimeError("mssvt_b200 operators run on CUDA tensors only (got a %s tensor); there is no CPU path" % x.device.type)
+    if x.dim() == 2 and x.shape[0] > 0 and layer.in_features in (32, 64, 128) and layer.out_features in (32, 64, 128):
         return LinearRows.apply(x, layer.weight, layer.bias, relu)
     y = layer(x)
     return torch.relu(y) if relu else y

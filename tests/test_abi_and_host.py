@@ -162,3 +162,22 @@ def test_slab_plan_aligns_to_every_window_grid_and_rejects_narrow_slabs():
     narrow = torch.from_numpy(np.stack([np.zeros(64, np.int32)] * 3 + [np.arange(64, dtype=np.int32) % 2], 1))
     with pytest.raises(ValueError, match="narrower than the halo"):
         SlabPlan(narrow, 2, 3, 0, 4, grid_x=2)
+
+
+def test_training_ops_refuse_cpu_tensors():
+    """the autograd.Functions of the training path (train_ops.py) have no CPU path either"""
+    from mssvt_b200.train_ops import (WindowLists, embed_rows, interp_merge, layer_norm_rows, linear_rows,
+                                      ragged_window_attention, segment_max)
+    t = lambda *a: torch.tensor(a, dtype=torch.int32)
+    lists = WindowLists(t(0, 1), t(0), t(0, 1), t(0), t(0))
+    z = torch.zeros(1, dtype=torch.long)
+    calls = [lambda: ragged_window_attention(torch.randn(1, 32), torch.randn(1, 64), lists, 2, 0.25),
+             lambda: interp_merge(torch.randn(2, 64), torch.randn(3, 64), torch.zeros(3, 3, dtype=torch.int32), torch.rand(3, 3)),
+             lambda: layer_norm_rows(torch.nn.LayerNorm(64), torch.randn(5, 64)),
+             lambda: linear_rows(torch.nn.Linear(64, 128), torch.randn(5, 64)),
+             lambda: segment_max(torch.randn(1, 64), lists, 1),
+             lambda: embed_rows(torch.randn(4, 64), torch.randn(64, 6), torch.randn(64), torch.randn(4, 3), torch.randn(1, 3),
+                                [(z, z, None, 0, 64)])]
+    for fn in calls:
+        with pytest.raises(RuntimeError, match="CUDA tensors only"):
+            fn()
